@@ -1,0 +1,174 @@
+"""Pins the CPU oracle against every vector the reference's tests hold for the
+hot path.  CPU-only."""
+import hashlib
+
+import pytest
+
+from conftest import load_golden
+
+N = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+P = 2**256 - 2**32 - 977
+H = bytes.fromhex
+
+
+def b32(x):
+    return x.to_bytes(32, "big")
+
+
+def test_gentable_sha256(oracle):
+    # internal/gentable/point_mul_table.bin: 8160 multiples of G
+    k = load_golden("kats.json")
+    tb = oracle.gen_table_bytes()
+    assert hashlib.sha256(tb).hexdigest() == k["gentable_sha256"]
+    for s in k["gentable_samples"]:
+        off = (s["i"] * 255 + s["j"]) * 64
+        assert tb[off:off + 64].hex() == s["xy"]
+        # entry (i, j) is (j+1) * 256^i * G
+        out, st = oracle.scalar_base_mult(b32(((s["j"] + 1) << (8 * s["i"])) % N))
+        assert st == 1 and out[1:].hex() == s["xy"]
+
+
+def test_generator_encodings(oracle):
+    # point_test.go:38-57
+    k = load_golden("kats.json")
+    out, st = oracle.point_decode(H(k["g_compressed"]))
+    assert st == 1 and out.hex() == k["g_uncompressed"]
+    out, st = oracle.point_decode(H(k["g_uncompressed"]))
+    assert st == 1 and out.hex() == k["g_uncompressed"]
+    for vt in (False, True):
+        out, st = oracle.scalar_base_mult(b32(1), vartime=vt)
+        assert st == 1 and out.hex() == k["g_uncompressed"]
+
+
+def test_scalar_mult_small_and_libsecp_kat(oracle):
+    # point_test.go:214-261
+    k = load_golden("kats.json")
+    g = H(k["g_uncompressed"])
+    for mode in (0, 1, 2):
+        out, st = oracle.scalar_mult(b32(0), g, mode)
+        assert st == 2
+        out, st = oracle.scalar_mult(b32(1), g, mode)
+        assert st == 1 and out == g
+        out, st = oracle.scalar_mult(b32(2), g, mode)
+        two_g, _ = oracle.point_add(g, 1, g, 1)
+        assert out == two_g
+        out, st = oracle.scalar_mult(H(k["libsecp_xn"]), H(k["libsecp_a"]), mode)
+        assert st == 1 and out.hex() == k["libsecp_b"]
+
+
+def test_glv_split_boundaries(oracle):
+    # point_mul_glv_test.go:17-96
+    k = load_golden("kats.json")
+    lam = int(k["lambda"], 16)
+    scalars = [0, 1, 0x1234567890ABCDEF << 100] + [int(x, 16) for x in k["glv_split_scalars"]]
+    for v in scalars:
+        k1b, k2b = oracle.sc_split_glv(b32(v))
+        k1, k2 = int.from_bytes(k1b, "big"), int.from_bytes(k2b, "big")
+        assert (k1 + k2 * lam) % N == v
+        for x in (k1, k2):
+            if x > N // 2:
+                x = N - x
+            assert x < 2**128
+
+
+def test_scalar_edges(oracle):
+    # scalar_test.go:26-54, 76-95
+    for raw, red in ((N, 0), (N + 1, 1), (N + 2, 2), (N + 2**128, 2**128)):
+        out, did = oracle.sc_set_bytes(b32(raw))
+        assert did == 1 and int.from_bytes(out, "big") == red
+        assert not oracle.sc_bytes_are_canonical(b32(raw))
+    half = N // 2
+    assert oracle.sc_is_gt_half_n(b32(half)) == 0
+    assert oracle.sc_is_gt_half_n(b32(half - 1)) == 0
+    assert oracle.sc_is_gt_half_n(b32(half + 1)) == 1
+    assert oracle.sc_is_gt_half_n(b32(half + 2)) == 1
+    assert int.from_bytes(oracle.sc_invert(b32(0)), "big") == 0
+    for v in (1, 2, N - 1, 0xDEADBEEF << 77):
+        assert int.from_bytes(oracle.sc_invert(b32(v)), "big") == pow(v, -1, N)
+
+
+def test_field_edges(oracle):
+    # internal/field/field_test.go:29-104
+    for raw, red in ((P, 0), (P + 1, 1), (P + 2, 2), (P + 2**32, 2**32)):
+        out, did = oracle.fe_set_bytes(b32(raw))
+        assert did == 1 and int.from_bytes(out, "big") == red
+        assert not oracle.fe_bytes_are_canonical(b32(raw))
+    assert int.from_bytes(oracle.fe_invert(b32(0)), "big") == 0
+    for v in (1, 2, P - 1, 0xC0FFEE << 200):
+        assert int.from_bytes(oracle.fe_invert(b32(v)), "big") == pow(v, -1, P)
+    # c2^2 = 11 flavour: sqrt of a square returns a root, non-residue flags 0
+    r, ok = oracle.fe_sqrt(b32(4))
+    assert ok == 1 and pow(int.from_bytes(r, "big"), 2, P) == 4
+    r, ok = oracle.fe_sqrt(b32(3))  # 3 is a non-residue mod p
+    assert (ok, int.from_bytes(r, "big")) == (0, 0) or pow(int.from_bytes(r, "big"), 2, P) == 3
+
+
+def test_wycheproof_ecdsa(oracle):
+    # secec/wycheproof_test.go:317-438 over the cases that reach the arithmetic
+    doc = load_golden("wycheproof_ecdsa.json")
+    assert len(doc["cases"]) == 432
+    for c in doc["cases"]:
+        pk, dg = H(c["pk"]), H(c["digest"])[:32]
+        ok = oracle.ecdsa_verify(pk, dg, H(c["r"]) + H(c["s"]))
+        assert bool(ok) == c["valid"], c
+        # exhaustive recovery-id cross-check (wycheproof_test.go:421-438)
+        rec = False
+        for v in range(4):
+            q, st = oracle.ecdsa_recover(dg, H(c["r"]) + H(c["s"]) + bytes([v]))
+            rec |= (st == 1 and q == pk)
+        assert rec == bool(ok), c
+
+
+def test_wycheproof_ecdh(oracle):
+    # secec/wycheproof_test.go:207-306
+    doc = load_golden("wycheproof_ecdh.json")
+    n_shared = 0
+    for c in doc["cases"]:
+        pt65, st = oracle.point_decode(H(c["point"]))
+        if c["shared"] == "":
+            assert st == 0, c
+            continue
+        assert st == 1, c
+        x, st = oracle.ecdh(H(c["priv"]), pt65)
+        assert st == 1 and x.hex() == c["shared"], c
+        n_shared += 1
+    assert n_shared == 947
+
+
+def test_bip340(oracle):
+    # secec/bitcoin/schnorr_test.go:149-246
+    doc = load_golden("bip340.json")
+    assert len(doc["rows"]) == 19
+    for r in doc["rows"]:
+        ok = oracle.schnorr_verify(H(r["pk"]), H(r["msg"]), H(r["sig"]))
+        assert bool(ok) == r["valid"], r
+        if r["sk"]:
+            out, st = oracle.scalar_base_mult(H(r["sk"]))
+            assert st == 1 and out[1:33].hex() == r["pk"]
+
+
+def test_rfc6979_rows(oracle):
+    # secec/ecdsa_k_test.go:244-278
+    doc = load_golden("rfc6979.json")
+    for r in doc["rows"]:
+        pk, st = oracle.scalar_base_mult(H(r["priv"]))
+        assert st == 1
+        sig = H(r["r"]) + H(r["s"])
+        assert oracle.ecdsa_verify(pk, H(r["digest"]), sig) == 1
+        assert oracle.ecdsa_verify(pk, H(r["digest"]), sig, 1) == 1  # all low-s
+        bad = bytearray(sig); bad[5] ^= 1
+        assert oracle.ecdsa_verify(pk, H(r["digest"]), bytes(bad)) == 0
+
+
+def test_nonce_reuse_pairs(oracle):
+    # secec/ecdsa_k_test.go:44-70 -- fixed (key, r, s) pairs incl. a high-s one
+    d = H("000000000000000000000000" + "E5C4D0A8249A6F27E5E0C9D534F4DA15223F42AD")
+    pk, _ = oracle.scalar_base_mult(d)
+    m1 = hashlib.sha256(b"This is Fail(TM). But it's not Epic(TM) yet...").digest()
+    m2 = hashlib.sha256(b"With private keys you can SIGN THINGS").digest()
+    r = H("317365e5fada9ddf645d224952c398b3bfa5dcb4d11803213ee6565639ad25be")
+    s1 = H("c69a9505efb9a417b5f59f62ad7cd8140947b2e2189fb7ef111a8206d2ed8aa5")
+    s2 = H("14577cbf24e320e45c14efe63b4190e2e00f9936102f00d67cb5e79113ef5a9b")
+    assert oracle.ecdsa_verify(pk, m2, r + s2) == 1
+    assert oracle.ecdsa_verify(pk, m1, r + s1) == 1
+    assert oracle.ecdsa_verify(pk, m1, r + s1, 1) == 0  # s1 > n/2 (RejectMalleable)
