@@ -1,0 +1,152 @@
+/*
+ * secp256k1_b200.h -- C ABI of the B200-native batched secp256k1 engine.
+ *
+ * The reference (gitlab.com/yawning/secp256k1-voi, Go) has no FFI boundary of
+ * its own; its exported Go API is the contract.  Each entry point below is the
+ * batch form of one reference call and cites it (paths relative to the
+ * reference root).  INTEGRATION.md shows the cgo binding a maintainer adds.
+ *
+ * Conventions (inherited from the reference):
+ *   - every encoding is big-endian: scalars / digests / x-coordinates 32 B,
+ *     compact signatures r||s 64 B (recoverable r||s||v 65 B), points SEC 1
+ *     uncompressed 65 B (04||X||Y);
+ *   - n items, row-major, caller owns every buffer; calls are synchronous and
+ *     retain no pointer after returning (the cgo pointer rule);
+ *   - call-level misuse / CUDA failure: negative int return, never abort;
+ *     data-level outcomes: one status byte per item;
+ *   - a context is bound to one CUDA device and may be used from any thread
+ *     (calls on one context serialise on an internal mutex); use one context
+ *     per GPU, one process per GPU for multi-GPU runs;
+ *   - there is NO CPU fallback: without a usable CUDA device s256_init fails.
+ *
+ * The *_dev twins take device pointers and a cudaStream_t (as void*; NULL =
+ * default stream), enqueue the work and return without synchronising; they
+ * are what bench.py times with inputs resident in HBM.
+ */
+#ifndef SECP256K1_B200_H
+#define SECP256K1_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct s256_ctx s256_ctx;
+
+/* return codes */
+#define S256_SUCCESS 0
+#define S256_ERR_NO_DEVICE (-1)   /* no CUDA device / wrong architecture */
+#define S256_ERR_CUDA (-2)        /* a CUDA runtime call failed (see s256_last_cuda_error) */
+#define S256_ERR_ARG (-3)         /* NULL pointer, bad length: the reference panics here */
+#define S256_ERR_NOMEM (-4)
+#define S256_ERR_UNIMPLEMENTED (-5)
+#define S256_ERR_NCCL (-6)
+
+/* per-item status bytes */
+#define S256_ST_INVALID 0   /* input rejected (bad point / scalar / signature encoding) */
+#define S256_ST_OK 1        /* output is a finite point / verification succeeded */
+#define S256_ST_IDENTITY 2  /* result is the point at infinity (output bytes zeroed);
+                               the reference encodes it as the single byte 0x00
+                               (point_s11n.go:75-77) or returns an error (XBytes, :123-125) */
+
+/* flags */
+#define S256_FLAG_REJECT_MALLEABLE 1u /* ECDSAOptions.RejectMalleable, secec/ecdsa.go:72-75,212 */
+
+/* --- lifecycle ----------------------------------------------------------- */
+/* device < 0: use the calling thread's current device.  max_batch = 0 picks
+ * the default chunk capacity (2^20 items); larger batches are processed in
+ * chunks.  Builds the generator tables on the device (the reference does this
+ * at package init, point_mul_table.go:75-100,147-160). */
+int s256_init(s256_ctx **ctx, int device, size_t max_batch);
+void s256_free(s256_ctx *ctx);
+const char *s256_strerror(int code);
+const char *s256_last_cuda_error(const s256_ctx *ctx);
+int s256_device(const s256_ctx *ctx);
+
+/* --- Point.ScalarBaseMult (point_mul_table.go:168) + UncompressedBytes
+ *     (point_s11n.go:66).  Constant time.  k32 is decoded like
+ *     NewScalarFromBytes (scalar.go:248: reduced mod n). */
+int s256_scalar_base_mult(s256_ctx *ctx, const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status);
+int s256_scalar_base_mult_dev(s256_ctx *ctx, const uint8_t *d_k32, size_t n, uint8_t *d_out65, uint8_t *d_status,
+                              void *stream);
+
+/* --- Point.ScalarMult (point_mul_glv.go:257) + UncompressedBytes.  Constant
+ *     time in the scalar.  pt65 decoded like NewPointFromBytes
+ *     (point_s11n.go:234,178). */
+int s256_scalar_mult(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, uint8_t *out65,
+                     uint8_t *status);
+int s256_scalar_mult_dev(s256_ctx *ctx, const uint8_t *d_k32, const uint8_t *d_pt65, size_t n, uint8_t *d_out65,
+                         uint8_t *d_status, void *stream);
+
+/* --- PrivateKey.ECDH (secec/secec.go:53): x(k*P), 32 B; identity is an
+ *     error (status S256_ST_IDENTITY). */
+int s256_ecdh(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, uint8_t *x32, uint8_t *status);
+int s256_ecdh_dev(s256_ctx *ctx, const uint8_t *d_k32, const uint8_t *d_pt65, size_t n, uint8_t *d_x32,
+                  uint8_t *d_status, void *stream);
+
+/* --- Point.DoubleScalarMultBasepointVartime (point_mul_glv.go:307):
+ *     u1*G + u2*P, variable time. */
+int s256_double_scalar_mult_basepoint_vartime(s256_ctx *ctx, const uint8_t *u1_32, const uint8_t *u2_32,
+                                              const uint8_t *pt65, size_t n, uint8_t *out65, uint8_t *status);
+int s256_double_scalar_mult_basepoint_vartime_dev(s256_ctx *ctx, const uint8_t *d_u1_32, const uint8_t *d_u2_32,
+                                                  const uint8_t *d_pt65, size_t n, uint8_t *d_out65,
+                                                  uint8_t *d_status, void *stream);
+
+/* --- secec.PublicKey.Verify with EncodingCompact (secec/ecdsa.go:171 ->
+ *     secec/s11n.go:129 -> verify, ecdsa.go:392).  pk65 is decoded like
+ *     secec.NewPublicKey (secec/secec.go:188); digest32 is the leftmost
+ *     32 bytes of the digest (ecdsa.go:477).  ok[i] in {0,1}. */
+int s256_ecdsa_verify(s256_ctx *ctx, const uint8_t *pk65, const uint8_t *digest32, const uint8_t *sig64,
+                      uint32_t flags, size_t n, uint8_t *ok);
+int s256_ecdsa_verify_dev(s256_ctx *ctx, const uint8_t *d_pk65, const uint8_t *d_digest32, const uint8_t *d_sig64,
+                          uint32_t flags, size_t n, uint8_t *d_ok, void *stream);
+
+/* --- secec.RecoverPublicKey (secec/ecdsa.go:244) on r||s||v
+ *     (secec/s11n.go:156). */
+int s256_ecdsa_recover(s256_ctx *ctx, const uint8_t *digest32, const uint8_t *sig65, size_t n, uint8_t *pk65,
+                       uint8_t *status);
+int s256_ecdsa_recover_dev(s256_ctx *ctx, const uint8_t *d_digest32, const uint8_t *d_sig65, size_t n,
+                           uint8_t *d_pk65, uint8_t *d_status, void *stream);
+
+/* --- bitcoin.SchnorrPublicKey.Verify (secec/bitcoin/schnorr.go:221) incl.
+ *     NewSchnorrPublicKey / lift_x (:257).  msg is n rows of msg_len bytes. */
+int s256_schnorr_verify(s256_ctx *ctx, const uint8_t *pkx32, const uint8_t *msg, size_t msg_len,
+                        const uint8_t *sig64, size_t n, uint8_t *ok);
+int s256_schnorr_verify_dev(s256_ctx *ctx, const uint8_t *d_pkx32, const uint8_t *d_msg, size_t msg_len,
+                            const uint8_t *d_sig64, size_t n, uint8_t *d_ok, void *stream);
+
+/* --- Point.MultiScalarMult[Vartime] (point_mul_multi.go:25,73): sum k_i*P_i
+ *     over this context's items -> one 65-byte point.  n == 0 gives the
+ *     identity.  *status: S256_ST_OK / S256_ST_IDENTITY / S256_ST_INVALID (a
+ *     point failed to decode).  s256_msm_partial returns the projective
+ *     partial sum (X||Y||Z, 96 B big-endian) for the caller to combine across
+ *     GPUs (one small gather), and s256_msm_combine folds m partials. */
+int s256_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, uint8_t *out65,
+             uint8_t *status);
+int s256_msm_partial(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime,
+                     uint8_t *partial96, uint8_t *status);
+int s256_msm_combine(s256_ctx *ctx, const uint8_t *partials96, size_t m, uint8_t *out65, uint8_t *status);
+
+/* --- measurement / debug hooks (not part of the reference surface) -------- */
+/* Regenerates multiples d * 2^(wbits*w) * G, d in [1, 2^wbits), w in [0, nwin)
+ * as X||Y (64 B each), window-major: with wbits = 8, nwin = 32 this is byte for
+ * byte internal/gentable/point_mul_table.bin. */
+int s256_debug_gen_table(s256_ctx *ctx, int wbits, int nwin, uint8_t *out);
+/* out32[i] = a32[i] (op) b32[i] in F_p (op 0 mul, 1 add, 2 sub, 3 inv(a), 4 sqrt(a) or zeros)
+ * or Z_n (op 16 mul, 17 add, 18 inv(a)); inputs are reduced like SetBytes. */
+int s256_debug_field_op(s256_ctx *ctx, int op, const uint8_t *a32, const uint8_t *b32, size_t n, uint8_t *out32);
+/* Integer-multiply peak: runs independent IMAD.WIDE.U32 chains on every SM and
+ * returns MAC32 per second (the roofline denominator). */
+int s256_microbench_imad(s256_ctx *ctx, int iters, double *mac32_per_s, double *ms);
+/* Number of kernel launches issued through this context so far. */
+uint64_t s256_launch_count(const s256_ctx *ctx);
+/* MAC32 (32x32->64 multiply-accumulates) executed per item by each path,
+ * derived from the modmul counts in DESIGN.md; key is an entry point name. */
+double s256_mac32_per_item(const char *entry_point);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SECP256K1_B200_H */

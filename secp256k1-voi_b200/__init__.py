@@ -1,0 +1,338 @@
+"""B200-native batched secp256k1 engine: Python view of the C ABI.
+
+Everything here is a thin ctypes layer over `lib/libsecp256k1_b200.so`
+(include/secp256k1_b200.h); the names follow the reference's Go API
+(secp256k1.Point.ScalarBaseMult, .ScalarMult, .DoubleScalarMultBasepointVartime,
+.MultiScalarMult, secec.PublicKey.Verify, secec.RecoverPublicKey,
+secec.PrivateKey.ECDH, bitcoin.SchnorrPublicKey.Verify) in batch form.
+
+There is no CPU path: importing works anywhere (so the symbol table can be
+checked), but creating an Engine without a CUDA device raises.
+
+Inputs are either host arrays (numpy uint8 / bytes; the library copies in and
+out) or CUDA torch tensors (uint8, contiguous; the `_dev` entry points run on
+torch's current stream and return torch tensors without synchronising).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+from . import synth  # noqa: F401  (re-exported)
+
+ST_INVALID, ST_OK, ST_IDENTITY = 0, 1, 2
+FLAG_REJECT_MALLEABLE = 1
+
+EXPORTED_SYMBOLS = [
+    "s256_init", "s256_free", "s256_strerror", "s256_last_cuda_error", "s256_device",
+    "s256_scalar_base_mult", "s256_scalar_base_mult_dev",
+    "s256_scalar_mult", "s256_scalar_mult_dev",
+    "s256_ecdh", "s256_ecdh_dev",
+    "s256_double_scalar_mult_basepoint_vartime", "s256_double_scalar_mult_basepoint_vartime_dev",
+    "s256_ecdsa_verify", "s256_ecdsa_verify_dev",
+    "s256_ecdsa_recover", "s256_ecdsa_recover_dev",
+    "s256_schnorr_verify", "s256_schnorr_verify_dev",
+    "s256_msm", "s256_msm_partial", "s256_msm_combine",
+    "s256_debug_gen_table", "s256_debug_field_op", "s256_microbench_imad",
+    "s256_launch_count", "s256_mac32_per_item",
+]
+
+_lib = None
+
+
+class S256Error(RuntimeError):
+    pass
+
+
+def library_path():
+    return _build.LIB
+
+
+def load_library():
+    """Loads (building first if stale and nvcc is present) the C-ABI library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    try:
+        _build.build()
+    except FileNotFoundError:
+        pass  # no nvcc on this box: use the prebuilt library shipped in-tree
+    if not os.path.exists(_build.LIB):
+        raise S256Error(f"{_build.LIB} is missing: run `python -m __graft_entry__` / build() where nvcc exists; "
+                        "there is no fallback implementation")
+    lib = C.CDLL(_build.LIB)
+    lib.s256_strerror.restype = C.c_char_p
+    lib.s256_last_cuda_error.restype = C.c_char_p
+    lib.s256_last_cuda_error.argtypes = [C.c_void_p]
+    lib.s256_launch_count.restype = C.c_uint64
+    lib.s256_launch_count.argtypes = [C.c_void_p]
+    lib.s256_mac32_per_item.restype = C.c_double
+    lib.s256_mac32_per_item.argtypes = [C.c_char_p]
+    lib.s256_free.argtypes = [C.c_void_p]
+    lib.s256_free.restype = None
+    _lib = lib
+    return lib
+
+
+def mac32_per_item(entry_point):
+    return load_library().s256_mac32_per_item(entry_point.encode())
+
+
+def _is_torch_cuda(x):
+    return hasattr(x, "is_cuda") and x.is_cuda
+
+
+def _host(x, width):
+    if isinstance(x, (bytes, bytearray, memoryview)):
+        x = np.frombuffer(bytes(x), dtype=np.uint8)
+    a = np.ascontiguousarray(x, dtype=np.uint8)
+    if width:
+        a = a.reshape(-1, width)
+    return a
+
+
+class Engine:
+    """One context on one GPU (s256_init).  Use one Engine per process/GPU."""
+
+    def __init__(self, device=-1, max_batch=0):
+        self._lib = load_library()
+        self._ctx = C.c_void_p()
+        rc = self._lib.s256_init(C.byref(self._ctx), int(device), C.c_size_t(max_batch))
+        if rc != 0:
+            self._ctx = C.c_void_p()
+            raise S256Error(f"s256_init failed: {self._lib.s256_strerror(rc).decode()} (rc={rc})")
+
+    # -- plumbing -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.s256_free(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            detail = self._lib.s256_last_cuda_error(self._ctx).decode()
+            raise S256Error(f"{what}: {self._lib.s256_strerror(rc).decode()} (rc={rc}) {detail}")
+
+    @property
+    def device(self):
+        return self._lib.s256_device(self._ctx)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.s256_launch_count(self._ctx))
+
+    @staticmethod
+    def _hp(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    @staticmethod
+    def _dev_args(*tensors):
+        import torch
+        for t in tensors:
+            if t.dtype != torch.uint8 or not t.is_contiguous():
+                raise S256Error("device inputs must be contiguous uint8 CUDA tensors")
+        return [C.c_void_p(t.data_ptr()) for t in tensors]
+
+    @staticmethod
+    def _stream():
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # -- Point.ScalarBaseMult (point_mul_table.go:168) ------------------------
+    def scalar_base_mult(self, k32):
+        if _is_torch_cuda(k32):
+            import torch
+            n = k32.numel() // 32
+            out = torch.empty((n, 65), dtype=torch.uint8, device=k32.device)
+            st = torch.empty(n, dtype=torch.uint8, device=k32.device)
+            a = self._dev_args(k32, out, st)
+            self._check(self._lib.s256_scalar_base_mult_dev(self._ctx, a[0], C.c_size_t(n), a[1], a[2], self._stream()),
+                        "scalar_base_mult_dev")
+            return out, st
+        k = _host(k32, 32)
+        n = len(k)
+        out = np.zeros((n, 65), np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_scalar_base_mult(self._ctx, self._hp(k), C.c_size_t(n), self._hp(out), self._hp(st)),
+                    "scalar_base_mult")
+        return out, st
+
+    # -- Point.ScalarMult (point_mul_glv.go:257), constant time ---------------
+    def scalar_mult(self, k32, pt65):
+        if _is_torch_cuda(k32):
+            import torch
+            n = k32.numel() // 32
+            out = torch.empty((n, 65), dtype=torch.uint8, device=k32.device)
+            st = torch.empty(n, dtype=torch.uint8, device=k32.device)
+            a = self._dev_args(k32, pt65, out, st)
+            self._check(self._lib.s256_scalar_mult_dev(self._ctx, a[0], a[1], C.c_size_t(n), a[2], a[3], self._stream()),
+                        "scalar_mult_dev")
+            return out, st
+        k, p = _host(k32, 32), _host(pt65, 65)
+        n = len(k)
+        if len(p) != n:
+            raise ValueError("len(scalars) != len(points)")
+        out = np.zeros((n, 65), np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_scalar_mult(self._ctx, self._hp(k), self._hp(p), C.c_size_t(n), self._hp(out), self._hp(st)),
+                    "scalar_mult")
+        return out, st
+
+    # -- PrivateKey.ECDH (secec/secec.go:53) ----------------------------------
+    def ecdh(self, k32, pt65):
+        if _is_torch_cuda(k32):
+            import torch
+            n = k32.numel() // 32
+            out = torch.empty((n, 32), dtype=torch.uint8, device=k32.device)
+            st = torch.empty(n, dtype=torch.uint8, device=k32.device)
+            a = self._dev_args(k32, pt65, out, st)
+            self._check(self._lib.s256_ecdh_dev(self._ctx, a[0], a[1], C.c_size_t(n), a[2], a[3], self._stream()), "ecdh_dev")
+            return out, st
+        k, p = _host(k32, 32), _host(pt65, 65)
+        n = len(k)
+        if len(p) != n:
+            raise ValueError("len(scalars) != len(points)")
+        out = np.zeros((n, 32), np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_ecdh(self._ctx, self._hp(k), self._hp(p), C.c_size_t(n), self._hp(out), self._hp(st)), "ecdh")
+        return out, st
+
+    # -- Point.DoubleScalarMultBasepointVartime (point_mul_glv.go:307) --------
+    def double_scalar_mult_basepoint_vartime(self, u1, u2, pt65):
+        if _is_torch_cuda(u1):
+            import torch
+            n = u1.numel() // 32
+            out = torch.empty((n, 65), dtype=torch.uint8, device=u1.device)
+            st = torch.empty(n, dtype=torch.uint8, device=u1.device)
+            a = self._dev_args(u1, u2, pt65, out, st)
+            self._check(self._lib.s256_double_scalar_mult_basepoint_vartime_dev(
+                self._ctx, a[0], a[1], a[2], C.c_size_t(n), a[3], a[4], self._stream()), "double_scalar_mult_dev")
+            return out, st
+        a1, a2, p = _host(u1, 32), _host(u2, 32), _host(pt65, 65)
+        n = len(a1)
+        if len(a2) != n or len(p) != n:
+            raise ValueError("length mismatch")
+        out = np.zeros((n, 65), np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_double_scalar_mult_basepoint_vartime(
+            self._ctx, self._hp(a1), self._hp(a2), self._hp(p), C.c_size_t(n), self._hp(out), self._hp(st)),
+            "double_scalar_mult_basepoint_vartime")
+        return out, st
+
+    # -- secec.PublicKey.Verify, EncodingCompact (secec/ecdsa.go:171) ---------
+    def ecdsa_verify(self, pk65, digest32, sig64, flags=0):
+        if _is_torch_cuda(pk65):
+            import torch
+            n = pk65.numel() // 65
+            ok = torch.empty(n, dtype=torch.uint8, device=pk65.device)
+            a = self._dev_args(pk65, digest32, sig64, ok)
+            self._check(self._lib.s256_ecdsa_verify_dev(self._ctx, a[0], a[1], a[2], C.c_uint32(flags), C.c_size_t(n), a[3],
+                                                        self._stream()), "ecdsa_verify_dev")
+            return ok
+        pk, dg, sg = _host(pk65, 65), _host(digest32, 32), _host(sig64, 64)
+        n = len(pk)
+        if len(dg) != n or len(sg) != n:
+            raise ValueError("length mismatch")
+        ok = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_ecdsa_verify(self._ctx, self._hp(pk), self._hp(dg), self._hp(sg), C.c_uint32(flags),
+                                                C.c_size_t(n), self._hp(ok)), "ecdsa_verify")
+        return ok
+
+    # -- secec.RecoverPublicKey (secec/ecdsa.go:244) ---------------------------
+    def ecdsa_recover(self, digest32, sig65):
+        if _is_torch_cuda(digest32):
+            import torch
+            n = digest32.numel() // 32
+            out = torch.empty((n, 65), dtype=torch.uint8, device=digest32.device)
+            st = torch.empty(n, dtype=torch.uint8, device=digest32.device)
+            a = self._dev_args(digest32, sig65, out, st)
+            self._check(self._lib.s256_ecdsa_recover_dev(self._ctx, a[0], a[1], C.c_size_t(n), a[2], a[3], self._stream()),
+                        "ecdsa_recover_dev")
+            return out, st
+        dg, sg = _host(digest32, 32), _host(sig65, 65)
+        n = len(dg)
+        if len(sg) != n:
+            raise ValueError("length mismatch")
+        out = np.zeros((n, 65), np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_ecdsa_recover(self._ctx, self._hp(dg), self._hp(sg), C.c_size_t(n), self._hp(out), self._hp(st)),
+                    "ecdsa_recover")
+        return out, st
+
+    # -- bitcoin.SchnorrPublicKey.Verify (secec/bitcoin/schnorr.go:221) --------
+    def schnorr_verify(self, pkx32, msg, sig64):
+        if _is_torch_cuda(pkx32):
+            import torch
+            n = pkx32.numel() // 32
+            msg_len = msg.numel() // n if n else 0
+            ok = torch.empty(n, dtype=torch.uint8, device=pkx32.device)
+            a = self._dev_args(pkx32, msg, sig64, ok)
+            self._check(self._lib.s256_schnorr_verify_dev(self._ctx, a[0], a[1], C.c_size_t(msg_len), a[2], C.c_size_t(n), a[3],
+                                                          self._stream()), "schnorr_verify_dev")
+            return ok
+        pk, sg = _host(pkx32, 32), _host(sig64, 64)
+        n = len(pk)
+        m = _host(msg, 0).reshape(n, -1) if n else np.zeros((0, 0), np.uint8)
+        if len(sg) != n:
+            raise ValueError("length mismatch")
+        ok = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_schnorr_verify(self._ctx, self._hp(pk), self._hp(m), C.c_size_t(m.shape[1] if n else 0),
+                                                  self._hp(sg), C.c_size_t(n), self._hp(ok)), "schnorr_verify")
+        return ok
+
+    # -- Point.MultiScalarMult[Vartime] (point_mul_multi.go:25,73) -------------
+    def msm(self, k32, pt65, vartime=True):
+        k, p = _host(k32, 32), _host(pt65, 65)
+        n = len(k)
+        if len(p) != n:
+            # the reference panics: point_mul_multi.go:27-29
+            raise ValueError("secp256k1: len(scalars) != len(points)")
+        out = np.zeros(65, np.uint8)
+        st = C.c_uint8(0)
+        self._check(self._lib.s256_msm(self._ctx, self._hp(k), self._hp(p), C.c_size_t(n), int(vartime), self._hp(out),
+                                       C.byref(st)), "msm")
+        return out, st.value
+
+    def msm_partial(self, k32, pt65, vartime=True):
+        k, p = _host(k32, 32), _host(pt65, 65)
+        n = len(k)
+        if len(p) != n:
+            raise ValueError("secp256k1: len(scalars) != len(points)")
+        out = np.zeros(96, np.uint8)
+        st = C.c_uint8(0)
+        self._check(self._lib.s256_msm_partial(self._ctx, self._hp(k), self._hp(p), C.c_size_t(n), int(vartime),
+                                               self._hp(out), C.byref(st)), "msm_partial")
+        return out, st.value
+
+    def msm_combine(self, partials96):
+        p = _host(partials96, 96)
+        out = np.zeros(65, np.uint8)
+        st = C.c_uint8(0)
+        self._check(self._lib.s256_msm_combine(self._ctx, self._hp(p), C.c_size_t(len(p)), self._hp(out), C.byref(st)),
+                    "msm_combine")
+        return out, st.value
+
+    # -- measurement / debug ----------------------------------------------------
+    def debug_gen_table(self, wbits, nwin):
+        out = np.zeros(((2 ** wbits - 1) * nwin, 64), np.uint8)
+        self._check(self._lib.s256_debug_gen_table(self._ctx, int(wbits), int(nwin), self._hp(out)), "debug_gen_table")
+        return out
+
+    def debug_field_op(self, op, a32, b32):
+        a, b = _host(a32, 32), _host(b32, 32)
+        out = np.zeros((len(a), 32), np.uint8)
+        self._check(self._lib.s256_debug_field_op(self._ctx, int(op), self._hp(a), self._hp(b), C.c_size_t(len(a)),
+                                                  self._hp(out)), "debug_field_op")
+        return out
+
+    def microbench_imad(self, iters=4096):
+        rate, ms = C.c_double(0), C.c_double(0)
+        self._check(self._lib.s256_microbench_imad(self._ctx, int(iters), C.byref(rate), C.byref(ms)), "microbench_imad")
+        return rate.value, ms.value

@@ -1,0 +1,691 @@
+// api.cu -- C ABI (include/secp256k1_b200.h) over the sm_100a kernels.
+//
+// Host side only orchestrates: device buffers, copies, launches.  There is no
+// CPU implementation of any curve operation in this library: without a CUDA
+// device every entry point fails with S256_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+
+#include "../../include/secp256k1_b200.h"
+#include "kernels.cuh"
+
+using namespace s256;
+
+// ---------------------------------------------------------------------------
+// __global__ wrappers
+// ---------------------------------------------------------------------------
+#define S256_TPB 128
+
+__global__ void __launch_bounds__(S256_TPB) k_gen_table(apt *out, int wb, size_t total) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    uint32_t w = (uint32_t)(idx >> wb), d = (uint32_t)(idx & ((1u << wb) - 1u));
+    apt a;
+    item_gen_multiple(a, w, d, wb);
+    out[idx] = a;
+}
+
+__global__ void __launch_bounds__(S256_TPB) k_decode_uncompressed(const uint8_t *pt65, size_t n, apt *aff,
+                                                                  uint8_t *pvalid) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    apt a;
+    pvalid[i] = item_decode_uncompressed(a, pt65 + 65 * i);
+    aff[i] = a;
+}
+
+// BIP-340 lift_x: x-only key, even y (secec/bitcoin/schnorr.go:257-275)
+__global__ void __launch_bounds__(S256_TPB) k_decode_xonly(const uint8_t *pkx32, size_t n, apt *aff, uint8_t *pvalid) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    apt a;
+    pvalid[i] = item_decode_xonly(a, pkx32 + 32 * i);
+    aff[i] = a;
+}
+
+// RecoverPoint (point_s11n.go:245-282): x = r (+ n if v & 2), parity v & 1
+__global__ void __launch_bounds__(S256_TPB) k_decode_recover(const uint8_t *sig65, size_t n, apt *aff,
+                                                             uint8_t *pvalid) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    apt a;
+    pvalid[i] = item_decode_recover(a, sig65 + 65 * i);
+    aff[i] = a;
+}
+
+template <int K, bool RECOVER>
+__global__ void __launch_bounds__(S256_TPB) k_ecdsa_scalars(const uint8_t *digest32, const uint8_t *sig, size_t n,
+                                                            uint32_t flags, sc *u1, int8_t *dig1, int8_t *dig2,
+                                                            uint8_t *sfl) {
+    size_t stride = (n + K - 1) / K;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= stride) return;
+    if (!RECOVER)
+        group_ecdsa_scalars<K>(t, stride, n, digest32, sig, flags, u1, dig1, dig2, sfl);
+    else
+        group_recover_scalars<K>(t, stride, n, digest32, sig, u1, dig1, dig2, sfl);
+}
+
+__global__ void __launch_bounds__(S256_TPB) k_plain_scalars(const uint8_t *u1b, const uint8_t *u2b, size_t n, sc *u1,
+                                                            int8_t *dig1, int8_t *dig2, uint8_t *sfl) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    item_plain_scalars(i, n, u1b, u2b, u1, dig1, dig2, sfl);
+}
+
+// secec/bitcoin/schnorr.go:420-449: r < p, s < n (zero allowed), e = H(r||P||m) mod n;
+// R = s*G + (-e)*P (:244-245)
+__global__ void __launch_bounds__(S256_TPB) k_schnorr_scalars(const uint8_t *pkx32, const uint8_t *msg, size_t msg_len,
+                                                              const uint8_t *sig64, size_t n, sc *u1, int8_t *dig1,
+                                                              int8_t *dig2, uint8_t *sfl) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    item_schnorr_scalars(i, n, pkx32, msg, msg_len, sig64, u1, dig1, dig2, sfl);
+}
+
+#ifndef S256_DSM_MINB
+#define S256_DSM_MINB 3
+#endif
+__global__ void __launch_bounds__(S256_TPB, S256_DSM_MINB)
+    k_dsm(size_t n, const apt *aff, const sc *u1, const int8_t *dig1, const int8_t *dig2, const uint8_t *sfl, pt *tbl,
+          pt *res, const apt *comb) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    item_dsm(i, n, aff, u1, dig1, dig2, sfl, tbl, res, comb);
+}
+
+__global__ void __launch_bounds__(S256_TPB) k_ecdsa_finish(size_t n, const pt *res, const uint8_t *sig64,
+                                                           const uint8_t *pvalid, const uint8_t *sfl, uint8_t *ok) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pt R = res[i];
+    uint32_t valid = (uint32_t)(pvalid[i] != 0) & (uint32_t)(sfl[i] & SFL_VALID);
+    ok[i] = item_ecdsa_finish(R, sig64 + 64 * i, valid);
+}
+
+// in-status = pvalid (may be null) AND sfl valid bit (may be null)
+template <int K>
+__global__ void __launch_bounds__(S256_TPB) k_finish_affine(size_t n, const pt *res, const uint8_t *pvalid,
+                                                            const uint8_t *sfl, uint8_t *comb_status, int mode,
+                                                            uint8_t *out, uint8_t *status, const uint8_t *sig64) {
+    size_t stride = (n + K - 1) / K;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= stride) return;
+    group_finish<K>(t, stride, n, res, pvalid, sfl, comb_status, mode, out, status, sig64);
+}
+
+#ifndef S256_BM_MINB
+#define S256_BM_MINB 3
+#endif
+__global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
+    k_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_g, pt *res) {
+    extern __shared__ uint4 smem_raw[];
+    apt *tab = reinterpret_cast<apt *>(smem_raw);
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(tab_g);
+        const int nvec = CT_NW * CT_SZ * (int)sizeof(apt) / 16;
+        for (int v = threadIdx.x; v < nvec; v += blockDim.x) smem_raw[v] = src[v];
+    }
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        sc k;
+        sc_from_be32(k, k32 + 32 * i);
+        pt acc;
+        item_base_mult_ct(acc, k, tab);
+        res[i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a32, const uint8_t *b32, size_t n,
+                                                       uint8_t *out32) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (op < 16) {
+        fe a, b, r;
+        fe_from_be32(a, a32 + 32 * i);
+        fe_from_be32(b, b32 + 32 * i);
+        switch (op) {
+            case 0: fe_mul(r, a, b); break;
+            case 1: fe_add(r, a, b); break;
+            case 2: fe_sub(r, a, b); break;
+            case 3: fe_invert(r, a); break;
+            case 4: fe_sqrt(r, a); break;
+            case 5: fe_mul_small(r, a, 21u); break;
+            case 6: fe_sqr(r, a); break;
+            default: r = fe_zero();
+        }
+        fe_normalize(r, r);
+        fe_to_be32(out32 + 32 * i, r);
+    } else {
+        sc a, b, r;
+        sc_from_be32(a, a32 + 32 * i);
+        sc_from_be32(b, b32 + 32 * i);
+        switch (op) {
+            case 16: sc_mul(r, a, b); break;
+            case 17: sc_add(r, a, b); break;
+            case 18: sc_invert(r, a); break;
+            default: r = sc_zero();
+        }
+        sc_to_be32(out32 + 32 * i, r);
+    }
+}
+
+// Integer-multiply peak: 8 independent IMAD.WIDE.U32 accumulator chains per thread.
+__global__ void __launch_bounds__(256) k_imad_peak(uint32_t seed, int iters, unsigned long long *sink) {
+    uint32_t a = seed ^ (threadIdx.x * 2654435761u), b = seed + blockIdx.x * 40503u + 1u;
+    unsigned long long c0 = a, c1 = b, c2 = a + 1, c3 = b + 2, c4 = a + 3, c5 = b + 4, c6 = a + 5, c7 = b + 6;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            asm volatile(
+                "mad.wide.u32 %0,%8,%9,%0; mad.wide.u32 %1,%8,%9,%1; mad.wide.u32 %2,%8,%9,%2; mad.wide.u32 %3,%8,%9,%3;"
+                "mad.wide.u32 %4,%8,%9,%4; mad.wide.u32 %5,%8,%9,%5; mad.wide.u32 %6,%8,%9,%6; mad.wide.u32 %7,%8,%9,%7;"
+                : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7)
+                : "r"(a), "r"(b));
+        }
+    }
+    unsigned long long s = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+    if (s == 0x123456789ULL) sink[0] = s;  // keeps the chains alive
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+struct s256_ctx {
+    int device = -1;
+    size_t cap = 0;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    std::string last_err;
+    std::atomic<uint64_t> launches{0};
+    // constant tables
+    apt *comb = nullptr;    // [COMB_NW][COMB_SZ]
+    apt *ct_tab = nullptr;  // [CT_NW][CT_SZ]
+    // per-chunk scratch
+    apt *aff = nullptr;
+    sc *u1 = nullptr;
+    int8_t *dig1 = nullptr, *dig2 = nullptr;
+    uint8_t *sfl = nullptr, *pvalid = nullptr, *cstat = nullptr;
+    pt *tbl = nullptr, *res = nullptr;
+    // staging for the host-pointer entry points
+    uint8_t *in_a = nullptr, *in_b = nullptr, *in_c = nullptr, *out = nullptr, *st = nullptr;
+    size_t in_b_bytes = 0;
+    unsigned long long *sink = nullptr;
+};
+
+#define CK(call)                                                                     \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            ctx->last_err = std::string(#call) + ": " + cudaGetErrorString(e_);      \
+            return S256_ERR_CUDA;                                                    \
+        }                                                                            \
+    } while (0)
+
+static inline unsigned grid_for(size_t n) { return (unsigned)((n + S256_TPB - 1) / S256_TPB); }
+#define LAUNCH(ctx, kern, grid, smem, strm, ...)                  \
+    do {                                                          \
+        kern<<<(grid), S256_TPB, (smem), (strm)>>>(__VA_ARGS__);  \
+        (ctx)->launches.fetch_add(1, std::memory_order_relaxed);  \
+    } while (0)
+
+struct dev_guard {
+    int prev = -1;
+    explicit dev_guard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~dev_guard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+extern "C" const char *s256_strerror(int code) {
+    switch (code) {
+        case S256_SUCCESS: return "success";
+        case S256_ERR_NO_DEVICE: return "no usable CUDA device (sm_100 required; there is no CPU fallback)";
+        case S256_ERR_CUDA: return "CUDA runtime error";
+        case S256_ERR_ARG: return "invalid argument";
+        case S256_ERR_NOMEM: return "out of memory";
+        case S256_ERR_UNIMPLEMENTED: return "not implemented";
+        case S256_ERR_NCCL: return "NCCL error";
+        default: return "unknown error";
+    }
+}
+extern "C" const char *s256_last_cuda_error(const s256_ctx *ctx) { return ctx ? ctx->last_err.c_str() : ""; }
+extern "C" int s256_device(const s256_ctx *ctx) { return ctx ? ctx->device : -1; }
+extern "C" uint64_t s256_launch_count(const s256_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+extern "C" void s256_free(s256_ctx *ctx) {
+    if (!ctx) return;
+    {
+        dev_guard g(ctx->device);
+        void *ptrs[] = {ctx->comb, ctx->ct_tab, ctx->aff, ctx->u1,   ctx->dig1, ctx->dig2, ctx->sfl, ctx->pvalid,
+                        ctx->cstat, ctx->tbl,   ctx->res, ctx->in_a, ctx->in_b, ctx->in_c, ctx->out, ctx->st,
+                        ctx->sink};
+        for (void *p : ptrs)
+            if (p) cudaFree(p);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+static int ctx_alloc(s256_ctx *ctx) {
+    size_t cap = ctx->cap;
+    CK(cudaMalloc(&ctx->comb, sizeof(apt) * COMB_NW * COMB_SZ));
+    CK(cudaMalloc(&ctx->ct_tab, sizeof(apt) * CT_NW * CT_SZ));
+    CK(cudaMalloc(&ctx->aff, sizeof(apt) * cap));
+    CK(cudaMalloc(&ctx->u1, sizeof(sc) * cap));
+    CK(cudaMalloc(&ctx->dig1, (size_t)DSM_ND * cap));
+    CK(cudaMalloc(&ctx->dig2, (size_t)DSM_ND * cap));
+    CK(cudaMalloc(&ctx->sfl, cap));
+    CK(cudaMalloc(&ctx->pvalid, cap));
+    CK(cudaMalloc(&ctx->cstat, cap));
+    CK(cudaMalloc(&ctx->tbl, sizeof(pt) * DSM_TS * cap));
+    CK(cudaMalloc(&ctx->res, sizeof(pt) * cap));
+    CK(cudaMalloc(&ctx->in_a, 65 * cap));
+    CK(cudaMalloc(&ctx->in_c, 65 * cap));
+    CK(cudaMalloc(&ctx->in_b, 32 * cap));
+    ctx->in_b_bytes = 32 * cap;
+    CK(cudaMalloc(&ctx->out, 65 * cap));
+    CK(cudaMalloc(&ctx->st, cap));
+    CK(cudaMalloc(&ctx->sink, 8));
+    return S256_SUCCESS;
+}
+
+extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
+    if (!out) return S256_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return S256_ERR_NO_DEVICE;
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return S256_ERR_NO_DEVICE;
+    if (device >= count) return S256_ERR_ARG;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return S256_ERR_NO_DEVICE;
+    if (prop.major != 10) return S256_ERR_NO_DEVICE;  // sm_100a code only
+    s256_ctx *ctx = new (std::nothrow) s256_ctx;
+    if (!ctx) return S256_ERR_NOMEM;
+    ctx->device = device;
+    ctx->cap = max_batch ? max_batch : ((size_t)1 << 20);
+    dev_guard g(device);
+    int rc = ctx_alloc(ctx);
+    if (rc == S256_SUCCESS && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
+        rc = S256_ERR_CUDA;
+    if (rc == S256_SUCCESS) {
+        // generator tables (reference: package init, point_mul_table.go:75-100,147-160)
+        size_t total = (size_t)COMB_NW * COMB_SZ;
+        LAUNCH(ctx, k_gen_table, grid_for(total), 0, ctx->stream, ctx->comb, COMB_WB, total);
+        total = (size_t)CT_NW * CT_SZ;
+        LAUNCH(ctx, k_gen_table, grid_for(total), 0, ctx->stream, ctx->ct_tab, 4, total);
+        cudaFuncSetAttribute(k_base_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(CT_NW * CT_SZ * sizeof(apt)));
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "s256_init: table generation failed: %s\n", cudaGetErrorString(e));
+            rc = S256_ERR_CUDA;
+        }
+    }
+    if (rc != S256_SUCCESS) {
+        s256_free(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return S256_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
+// device-pointer pipelines (one chunk <= cap)
+// ---------------------------------------------------------------------------
+static void enqueue_dsm(s256_ctx *ctx, size_t n, cudaStream_t s) {
+    LAUNCH(ctx, k_dsm, grid_for(n), 0, s, n, ctx->aff, ctx->u1, ctx->dig1, ctx->dig2, ctx->sfl, ctx->tbl, ctx->res,
+           ctx->comb);
+}
+constexpr int INV_K = 16;
+static inline unsigned grid_for_groups(size_t n, int k) { return grid_for((n + k - 1) / k); }
+
+static int chunk_ecdsa_verify(s256_ctx *ctx, const uint8_t *pk, const uint8_t *dg, const uint8_t *sig, uint32_t flags,
+                              size_t n, uint8_t *ok, cudaStream_t s) {
+    LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pk, n, ctx->aff, ctx->pvalid);
+    LAUNCH(ctx, (k_ecdsa_scalars<INV_K, false>), grid_for_groups(n, INV_K), 0, s, dg, sig, n, flags, ctx->u1, ctx->dig1,
+           ctx->dig2, ctx->sfl);
+    enqueue_dsm(ctx, n, s);
+    LAUNCH(ctx, k_ecdsa_finish, grid_for(n), 0, s, n, ctx->res, sig, ctx->pvalid, ctx->sfl, ok);
+    return S256_SUCCESS;
+}
+static int chunk_ecdsa_recover(s256_ctx *ctx, const uint8_t *dg, const uint8_t *sig65, size_t n, uint8_t *pk65,
+                               uint8_t *status, cudaStream_t s) {
+    LAUNCH(ctx, k_decode_recover, grid_for(n), 0, s, sig65, n, ctx->aff, ctx->pvalid);
+    LAUNCH(ctx, (k_ecdsa_scalars<INV_K, true>), grid_for_groups(n, INV_K), 0, s, dg, sig65, n, 0u, ctx->u1, ctx->dig1,
+           ctx->dig2, ctx->sfl);
+    enqueue_dsm(ctx, n, s);
+    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, ctx->res, ctx->pvalid, ctx->sfl, ctx->cstat,
+           3, pk65, status, (const uint8_t *)nullptr);
+    return S256_SUCCESS;
+}
+static int chunk_schnorr_verify(s256_ctx *ctx, const uint8_t *pkx, const uint8_t *msg, size_t msg_len,
+                                const uint8_t *sig, size_t n, uint8_t *ok, cudaStream_t s) {
+    LAUNCH(ctx, k_decode_xonly, grid_for(n), 0, s, pkx, n, ctx->aff, ctx->pvalid);
+    LAUNCH(ctx, k_schnorr_scalars, grid_for(n), 0, s, pkx, msg, msg_len, sig, n, ctx->u1, ctx->dig1, ctx->dig2,
+           ctx->sfl);
+    enqueue_dsm(ctx, n, s);
+    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, ctx->res, ctx->pvalid, ctx->sfl, ctx->cstat,
+           2, (uint8_t *)nullptr, ok, sig);
+    return S256_SUCCESS;
+}
+static int chunk_dsm(s256_ctx *ctx, const uint8_t *u1, const uint8_t *u2, const uint8_t *pt65, size_t n,
+                     uint8_t *out65, uint8_t *status, cudaStream_t s) {
+    LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pt65, n, ctx->aff, ctx->pvalid);
+    LAUNCH(ctx, k_plain_scalars, grid_for(n), 0, s, u1, u2, n, ctx->u1, ctx->dig1, ctx->dig2, ctx->sfl);
+    enqueue_dsm(ctx, n, s);
+    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, ctx->res, ctx->pvalid,
+           (const uint8_t *)nullptr, ctx->cstat, 0, out65, status, (const uint8_t *)nullptr);
+    return S256_SUCCESS;
+}
+static int chunk_base_mult(s256_ctx *ctx, const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status,
+                           cudaStream_t s) {
+    unsigned grid = grid_for(n);
+    unsigned maxg = 148u * S256_BM_MINB;
+    if (grid > maxg) grid = maxg;
+    LAUNCH(ctx, k_base_mult_ct, grid, CT_NW * CT_SZ * sizeof(apt), s, k32, n, ctx->ct_tab, ctx->res);
+    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, ctx->res, (const uint8_t *)nullptr,
+           (const uint8_t *)nullptr, ctx->cstat, 0, out65, status, (const uint8_t *)nullptr);
+    return S256_SUCCESS;
+}
+
+// Runs `body(offset, count)` over chunks of at most cap items.
+template <typename F>
+static int for_chunks(s256_ctx *ctx, size_t n, F body) {
+    for (size_t off = 0; off < n; off += ctx->cap) {
+        size_t c = n - off < ctx->cap ? n - off : ctx->cap;
+        int rc = body(off, c);
+        if (rc != S256_SUCCESS) return rc;
+    }
+    return S256_SUCCESS;
+}
+static int check_launch(s256_ctx *ctx) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        ctx->last_err = std::string("kernel launch: ") + cudaGetErrorString(e);
+        return S256_ERR_CUDA;
+    }
+    return S256_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
+// exported entry points
+// ---------------------------------------------------------------------------
+#define ENTER(ctx)                       \
+    if (!(ctx)) return S256_ERR_ARG;     \
+    std::lock_guard<std::mutex> lk_((ctx)->mu); \
+    dev_guard dg_((ctx)->device)
+
+extern "C" int s256_ecdsa_verify_dev(s256_ctx *ctx, const uint8_t *pk, const uint8_t *dg, const uint8_t *sig,
+                                     uint32_t flags, size_t n, uint8_t *ok, void *stream) {
+    ENTER(ctx);
+    if (n && (!pk || !dg || !sig || !ok)) return S256_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        return chunk_ecdsa_verify(ctx, pk + 65 * off, dg + 32 * off, sig + 64 * off, flags, c, ok + off, s);
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+extern "C" int s256_ecdsa_verify(s256_ctx *ctx, const uint8_t *pk, const uint8_t *dg, const uint8_t *sig,
+                                 uint32_t flags, size_t n, uint8_t *ok) {
+    ENTER(ctx);
+    if (n && (!pk || !dg || !sig || !ok)) return S256_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        CK(cudaMemcpyAsync(ctx->in_a, pk + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->in_b, dg + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->in_c, sig + 64 * off, 64 * c, cudaMemcpyHostToDevice, s));
+        int r = chunk_ecdsa_verify(ctx, ctx->in_a, ctx->in_b, ctx->in_c, flags, c, ctx->st, s);
+        if (r != S256_SUCCESS) return r;
+        CK(cudaMemcpyAsync(ok + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return S256_SUCCESS;
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+
+extern "C" int s256_ecdsa_recover_dev(s256_ctx *ctx, const uint8_t *dg, const uint8_t *sig65, size_t n, uint8_t *pk65,
+                                      uint8_t *status, void *stream) {
+    ENTER(ctx);
+    if (n && (!dg || !sig65 || !pk65 || !status)) return S256_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        return chunk_ecdsa_recover(ctx, dg + 32 * off, sig65 + 65 * off, c, pk65 + 65 * off, status + off, s);
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+extern "C" int s256_ecdsa_recover(s256_ctx *ctx, const uint8_t *dg, const uint8_t *sig65, size_t n, uint8_t *pk65,
+                                  uint8_t *status) {
+    ENTER(ctx);
+    if (n && (!dg || !sig65 || !pk65 || !status)) return S256_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        CK(cudaMemcpyAsync(ctx->in_b, dg + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->in_c, sig65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
+        int r = chunk_ecdsa_recover(ctx, ctx->in_b, ctx->in_c, c, ctx->out, ctx->st, s);
+        if (r != S256_SUCCESS) return r;
+        CK(cudaMemcpyAsync(pk65 + 65 * off, ctx->out, 65 * c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return S256_SUCCESS;
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+
+extern "C" int s256_schnorr_verify_dev(s256_ctx *ctx, const uint8_t *pkx, const uint8_t *msg, size_t msg_len,
+                                       const uint8_t *sig, size_t n, uint8_t *ok, void *stream) {
+    ENTER(ctx);
+    if (n && (!pkx || (!msg && msg_len) || !sig || !ok)) return S256_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        return chunk_schnorr_verify(ctx, pkx + 32 * off, msg + msg_len * off, msg_len, sig + 64 * off, c, ok + off, s);
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+extern "C" int s256_schnorr_verify(s256_ctx *ctx, const uint8_t *pkx, const uint8_t *msg, size_t msg_len,
+                                   const uint8_t *sig, size_t n, uint8_t *ok) {
+    ENTER(ctx);
+    if (n && (!pkx || (!msg && msg_len) || !sig || !ok)) return S256_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    size_t need = (msg_len ? msg_len : 1) * (n < ctx->cap ? n : ctx->cap);
+    if (need > ctx->in_b_bytes) {
+        if (ctx->in_b) cudaFree(ctx->in_b);
+        ctx->in_b = nullptr;
+        ctx->in_b_bytes = 0;
+        CK(cudaMalloc(&ctx->in_b, need));
+        ctx->in_b_bytes = need;
+    }
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        CK(cudaMemcpyAsync(ctx->in_a, pkx + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        if (msg_len) CK(cudaMemcpyAsync(ctx->in_b, msg + msg_len * off, msg_len * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->in_c, sig + 64 * off, 64 * c, cudaMemcpyHostToDevice, s));
+        int r = chunk_schnorr_verify(ctx, ctx->in_a, ctx->in_b, msg_len, ctx->in_c, c, ctx->st, s);
+        if (r != S256_SUCCESS) return r;
+        CK(cudaMemcpyAsync(ok + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return S256_SUCCESS;
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+
+extern "C" int s256_double_scalar_mult_basepoint_vartime_dev(s256_ctx *ctx, const uint8_t *u1, const uint8_t *u2,
+                                                             const uint8_t *pt65, size_t n, uint8_t *out65,
+                                                             uint8_t *status, void *stream) {
+    ENTER(ctx);
+    if (n && (!u1 || !u2 || !pt65 || !out65 || !status)) return S256_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        return chunk_dsm(ctx, u1 + 32 * off, u2 + 32 * off, pt65 + 65 * off, c, out65 + 65 * off, status + off, s);
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+extern "C" int s256_double_scalar_mult_basepoint_vartime(s256_ctx *ctx, const uint8_t *u1, const uint8_t *u2,
+                                                         const uint8_t *pt65, size_t n, uint8_t *out65,
+                                                         uint8_t *status) {
+    ENTER(ctx);
+    if (n && (!u1 || !u2 || !pt65 || !out65 || !status)) return S256_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        CK(cudaMemcpyAsync(ctx->in_a, pt65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->in_b, u1 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->in_c, u2 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        int r = chunk_dsm(ctx, ctx->in_b, ctx->in_c, ctx->in_a, c, ctx->out, ctx->st, s);
+        if (r != S256_SUCCESS) return r;
+        CK(cudaMemcpyAsync(out65 + 65 * off, ctx->out, 65 * c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return S256_SUCCESS;
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+
+extern "C" int s256_scalar_base_mult_dev(s256_ctx *ctx, const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status,
+                                         void *stream) {
+    ENTER(ctx);
+    if (n && (!k32 || !out65 || !status)) return S256_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        return chunk_base_mult(ctx, k32 + 32 * off, c, out65 + 65 * off, status + off, s);
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+extern "C" int s256_scalar_base_mult(s256_ctx *ctx, const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status) {
+    ENTER(ctx);
+    if (n && (!k32 || !out65 || !status)) return S256_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        CK(cudaMemcpyAsync(ctx->in_b, k32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        int r = chunk_base_mult(ctx, ctx->in_b, c, ctx->out, ctx->st, s);
+        if (r != S256_SUCCESS) return r;
+        CK(cudaMemcpyAsync(out65 + 65 * off, ctx->out, 65 * c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return S256_SUCCESS;
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+
+// --- not yet built this round --------------------------------------------------
+extern "C" int s256_scalar_mult(s256_ctx *, const uint8_t *, const uint8_t *, size_t, uint8_t *, uint8_t *) {
+    return S256_ERR_UNIMPLEMENTED;
+}
+extern "C" int s256_scalar_mult_dev(s256_ctx *, const uint8_t *, const uint8_t *, size_t, uint8_t *, uint8_t *,
+                                    void *) {
+    return S256_ERR_UNIMPLEMENTED;
+}
+extern "C" int s256_ecdh(s256_ctx *, const uint8_t *, const uint8_t *, size_t, uint8_t *, uint8_t *) {
+    return S256_ERR_UNIMPLEMENTED;
+}
+extern "C" int s256_ecdh_dev(s256_ctx *, const uint8_t *, const uint8_t *, size_t, uint8_t *, uint8_t *, void *) {
+    return S256_ERR_UNIMPLEMENTED;
+}
+extern "C" int s256_msm(s256_ctx *, const uint8_t *, const uint8_t *, size_t, int, uint8_t *, uint8_t *) {
+    return S256_ERR_UNIMPLEMENTED;
+}
+extern "C" int s256_msm_partial(s256_ctx *, const uint8_t *, const uint8_t *, size_t, int, uint8_t *, uint8_t *) {
+    return S256_ERR_UNIMPLEMENTED;
+}
+extern "C" int s256_msm_combine(s256_ctx *, const uint8_t *, size_t, uint8_t *, uint8_t *) {
+    return S256_ERR_UNIMPLEMENTED;
+}
+
+// ---------------------------------------------------------------------------
+// debug / measurement
+// ---------------------------------------------------------------------------
+extern "C" int s256_debug_gen_table(s256_ctx *ctx, int wbits, int nwin, uint8_t *out) {
+    ENTER(ctx);
+    if (!out || wbits < 1 || wbits > 16 || nwin < 1 || wbits * nwin > 256) return S256_ERR_ARG;
+    size_t total = (size_t)nwin << wbits;
+    apt *d = nullptr;
+    CK(cudaMalloc(&d, total * sizeof(apt)));
+    LAUNCH(ctx, k_gen_table, grid_for(total), 0, ctx->stream, d, wbits, total);
+    apt *h = (apt *)malloc(total * sizeof(apt));
+    cudaError_t e = cudaMemcpyAsync(h, d, total * sizeof(apt), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        free(h);
+        ctx->last_err = cudaGetErrorString(e);
+        return S256_ERR_CUDA;
+    }
+    // byte serialisation only (BE X || Y per entry, d = 0 skipped)
+    for (int w = 0; w < nwin; w++)
+        for (size_t dgt = 1; dgt < ((size_t)1 << wbits); dgt++) {
+            const apt &a = h[((size_t)w << wbits) + dgt];
+            fe_to_be32(out, a.x);
+            fe_to_be32(out + 32, a.y);
+            out += 64;
+        }
+    free(h);
+    return S256_SUCCESS;
+}
+
+extern "C" int s256_debug_field_op(s256_ctx *ctx, int op, const uint8_t *a32, const uint8_t *b32, size_t n,
+                                   uint8_t *out32) {
+    ENTER(ctx);
+    if (n && (!a32 || !b32 || !out32)) return S256_ERR_ARG;
+    if (n > ctx->cap) return S256_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->in_a, a32, 32 * n, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(ctx->in_c, b32, 32 * n, cudaMemcpyHostToDevice, s));
+    LAUNCH(ctx, k_field_op, grid_for(n), 0, s, op, ctx->in_a, ctx->in_c, n, ctx->out);
+    CK(cudaMemcpyAsync(out32, ctx->out, 32 * n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return check_launch(ctx);
+}
+
+extern "C" int s256_microbench_imad(s256_ctx *ctx, int iters, double *mac32_per_s, double *ms_out) {
+    ENTER(ctx);
+    if (iters < 1) return S256_ERR_ARG;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int blocks = 148 * 8, threads = 256;
+    k_imad_peak<<<blocks, threads, 0, ctx->stream>>>(12345u, 16, ctx->sink);  // warm-up
+    CK(cudaEventRecord(e0, ctx->stream));
+    k_imad_peak<<<blocks, threads, 0, ctx->stream>>>(12345u, iters, ctx->sink);
+    ctx->launches.fetch_add(2);
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    double macs = (double)blocks * threads * (double)iters * 64.0;
+    if (mac32_per_s) *mac32_per_s = macs / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return check_launch(ctx);
+}
+
+// MAC32 per item actually executed (DESIGN.md "work per item"): F_p modmul = 73,
+// small-constant mul = 9, Z_n modmul = 139 (64 + 40 + 30 + 5).
+extern "C" double s256_mac32_per_item(const char *name) {
+    const double M = 73, SM = 9, ZN = 139;
+    const double dbl = 8 * M + SM, add = 12 * M + 2 * SM, mix = 11 * M + 2 * SM;
+    const double inv_fe = 270 * M, inv_sc = 330 * ZN;
+    const double table = (DSM_TS / 2) * dbl + (DSM_TS / 2 - 1) * mix;
+    const double ladder = (DSM_ND - 1) * DSM_W * dbl + 2 * DSM_ND * add + DSM_ND * M;
+    const double comb = COMB_NW * mix;
+    const double dsm = table + ladder + comb;
+    const double split = 3 * ZN + 2 * 64;
+    const double affine = (3 + 2) * M + inv_fe / INV_K;
+    std::string s(name ? name : "");
+    if (s == "ecdsa_verify") return 3 * M + (5 * ZN + inv_sc / INV_K + split) + dsm + 2 * M;
+    if (s == "ecdsa_recover") return 276 * M + (6 * ZN + inv_sc / INV_K + split) + dsm + affine;
+    if (s == "schnorr_verify") return 276 * M + (ZN + split) + dsm + affine;
+    if (s == "double_scalar_mult_basepoint_vartime") return 3 * M + split + dsm + affine;
+    if (s == "scalar_base_mult") return CT_NW * mix + affine;
+    return 0.0;
+}

@@ -1,0 +1,507 @@
+// kernels.cuh -- the batched secp256k1 kernels (sm_100a).
+//
+// One item per thread for the curve work; K items per thread where a
+// Montgomery-trick batched inversion amortises a Fermat chain.  Every kernel
+// body is a plain S256_HD "item" function plus a thin __global__ wrapper, so
+// tests/hostsim can run the identical logic on a CPU-only box.
+//
+// Device scratch (all per item, SoA, see api.cu):
+//   aff   apt   decoded / validated affine input point           64 B
+//   u1    sc    G-side scalar                                    32 B
+//   dig1/2 int8 [ND][n] signed window digits of the GLV halves   2*ND B
+//   sfl   u8    bit0 scalars-valid, bit1 negate P, bit2 negate lambda*P
+//   tbl   pt    [TS] multiples 1..TS of P (projective)           96*TS B
+//   res   pt    projective result                                96 B
+#pragma once
+#include "fe.cuh"
+#include "point.cuh"
+#include "sc.cuh"
+#include "sha256.cuh"
+
+namespace s256 {
+
+// per-item window for the variable-base half of u1*G + u2*P
+#ifndef S256_W
+#define S256_W 5
+#endif
+constexpr int DSM_W = S256_W;
+constexpr int DSM_ND = glv_recode<DSM_W>::ND;  // digits per 128-bit half
+constexpr int DSM_TS = 1 << (DSM_W - 1);       // table entries 1..TS
+// fixed-base comb for the G half: COMB_NW windows of COMB_WB bits
+#ifndef S256_COMB_WB
+#define S256_COMB_WB 16
+#endif
+constexpr int COMB_WB = S256_COMB_WB;
+constexpr int COMB_NW = (256 + COMB_WB - 1) / COMB_WB;
+constexpr int COMB_SZ = 1 << COMB_WB;
+// constant-time fixed-base table: 64 windows of 4 bits, entries 1..15
+constexpr int CT_NW = 64;
+constexpr int CT_SZ = 16;
+
+enum : uint8_t { ST_INVALID = 0, ST_OK = 1, ST_IDENTITY = 2 };
+enum : uint32_t { FLAG_REJECT_MALLEABLE = 1u };
+enum : uint8_t { SFL_VALID = 1, SFL_NEG1 = 2, SFL_NEG2 = 4 };
+
+// ---------------------------------------------------------------------------
+// table generation: out[w * 2^wb + d] = d * 2^(wb*w) * G, affine; d = 0 unused.
+// Plain double-and-add from G with a per-thread Fermat inversion: init only.
+// (internal/gentable/point_mul_table.go:16-49 produces the same multiples.)
+// ---------------------------------------------------------------------------
+S256_HD void item_gen_multiple(apt &out, uint32_t w, uint32_t d, int wb) {
+    if (d == 0) {
+        out.x = fe_zero();
+        out.y = fe_zero();
+        return;
+    }
+    apt g = apt_generator();
+    pt acc;
+    pt_set_identity(acc);
+    for (int b = wb - 1; b >= 0; b--) {
+        pt_double(acc, acc);
+        if ((d >> b) & 1u) pt_add_mixed(acc, acc, g.x, g.y);
+    }
+    int nd = wb * (int)w;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = 0; k < nd; k++) pt_double(acc, acc);
+    fe zi;
+    fe_invert(zi, acc.z);
+    fe_mul(out.x, acc.x, zi);
+    fe_mul(out.y, acc.y, zi);
+    fe_normalize(out.x, out.x);
+    fe_normalize(out.y, out.y);
+}
+
+// ---------------------------------------------------------------------------
+// point decoding (SEC 1).  Invalid inputs are replaced by G so that the curve
+// kernels run on sane data; the valid byte carries the verdict.
+// ---------------------------------------------------------------------------
+// point_s11n.go:178-213 -- 04 || X || Y, canonical coordinates, on curve
+S256_HD uint8_t item_decode_uncompressed(apt &out, const uint8_t *b) {
+    apt a;
+    fe_from_be32(a.x, b + 1);
+    fe_from_be32(a.y, b + 33);
+    uint32_t ok = (uint32_t)(b[0] == 0x04) & fe_limbs_are_canonical(a.x) & fe_limbs_are_canonical(a.y);
+    ok &= apt_on_curve(a);
+    apt g = apt_generator();
+    fe_cmov(out.x, g.x, a.x, ok);
+    fe_cmov(out.y, g.y, a.y, ok);
+    return (uint8_t)ok;
+}
+// point_s11n.go:140-172 -- x canonical, y = sqrt(x^3 + 7) with the requested
+// parity.  Used for BIP-340 lift_x (parity 0, schnorr.go:257-275) and
+// RecoverPoint (point_s11n.go:245-282).
+S256_HD uint8_t item_decompress(apt &out, const fe &x, uint32_t x_ok, uint32_t want_odd) {
+    fe yy, y, yn;
+    fe_curve_rhs(yy, x);
+    uint32_t ok = x_ok & fe_sqrt(y, yy);
+    fe_normalize(y, y);
+    fe_neg(yn, y);
+    fe_normalize(yn, yn);
+    uint32_t flip = (y.v[0] & 1u) ^ (want_odd & 1u);
+    fe_cmov(y, y, yn, flip);
+    apt g = apt_generator();
+    fe_cmov(out.x, g.x, x, ok);
+    fe_cmov(out.y, g.y, y, ok);
+    return (uint8_t)ok;
+}
+
+// ---------------------------------------------------------------------------
+// scalar preparation for R = u1*G + u2*P: GLV-split u2, sign-normalise,
+// recode both halves into signed W-bit digits.
+// ---------------------------------------------------------------------------
+S256_HD void item_store_scalars(const sc &u1, const sc &u2, uint32_t valid, size_t i, size_t n, sc *u1_out,
+                                int8_t *dig1, int8_t *dig2, uint8_t *sfl) {
+    uint32_t m1[4], m2[4], neg1, neg2;
+    sc_split_glv_abs(m1, neg1, m2, neg2, u2);
+    int8_t d1[DSM_ND], d2[DSM_ND];
+    glv_recode<DSM_W>::run(d1, m1);
+    glv_recode<DSM_W>::run(d2, m2);
+#pragma unroll
+    for (int s = 0; s < DSM_ND; s++) {
+        dig1[(size_t)s * n + i] = d1[s];
+        dig2[(size_t)s * n + i] = d2[s];
+    }
+    u1_out[i] = u1;
+    sfl[i] = (uint8_t)((valid ? SFL_VALID : 0) | (neg1 ? SFL_NEG1 : 0) | (neg2 ? SFL_NEG2 : 0));
+}
+
+// secec/ecdsa.go:392-470 steps 1-4 and secec/s11n.go:129-145: r, s canonical
+// and non-zero, optional low-s rule (ecdsa.go:212), e = leftmost 32 digest
+// bytes mod n (ecdsa.go:477-486).  s is replaced by 1 when invalid so the
+// shared inversion stays well defined.
+struct ecdsa_parsed {
+    sc r, s, e;
+    uint32_t valid;
+};
+S256_HD void item_ecdsa_parse(ecdsa_parsed &o, const uint8_t *digest32, const uint8_t *sig64, uint32_t flags) {
+    uint32_t rr = sc_from_be32(o.r, sig64);
+    uint32_t sr = sc_from_be32(o.s, sig64 + 32);
+    uint32_t ok = (1u - rr) & (1u - sr) & (1u - sc_is_zero(o.r)) & (1u - sc_is_zero(o.s));
+    if (flags & FLAG_REJECT_MALLEABLE) ok &= 1u - sc_is_gt_half_n(o.s);
+    sc_from_be32(o.e, digest32);
+    sc one = sc_one();
+    sc_cmov(o.s, one, o.s, ok);
+    o.valid = ok;
+}
+
+// K items per thread, strided by `stride` so that a warp touches consecutive
+// items: Montgomery's trick shares one x^(n-2) chain between K inversions.
+template <int K>
+S256_HD void group_ecdsa_scalars(size_t t, size_t stride, size_t n, const uint8_t *digest32, const uint8_t *sig64,
+                                 uint32_t flags, sc *u1_out, int8_t *dig1, int8_t *dig2, uint8_t *sfl) {
+    sc pre[K];
+    sc run = sc_one();
+    ecdsa_parsed p;
+    for (int m = 0; m < K; m++) {
+        size_t i = t + (size_t)m * stride;
+        pre[m] = run;
+        if (i < n) {
+            item_ecdsa_parse(p, digest32 + 32 * i, sig64 + 64 * i, flags);
+            sc_mul(run, run, p.s);
+        }
+    }
+    sc inv;
+    sc_invert(inv, run);
+    for (int m = K - 1; m >= 0; m--) {
+        size_t i = t + (size_t)m * stride;
+        if (i >= n) continue;
+        item_ecdsa_parse(p, digest32 + 32 * i, sig64 + 64 * i, flags);
+        sc sinv, u1, u2;
+        sc_mul(sinv, inv, pre[m]);
+        sc_mul(inv, inv, p.s);
+        sc_mul(u1, p.e, sinv);  // ecdsa.go:429
+        sc_mul(u2, p.r, sinv);  // ecdsa.go:430
+        item_store_scalars(u1, u2, p.valid, i, n, u1_out, dig1, dig2, sfl);
+    }
+}
+
+// raw u1, u2 (DoubleScalarMultBasepointVartime called directly): reduce like
+// NewScalarFromBytes.
+S256_HD void item_plain_scalars(size_t i, size_t n, const uint8_t *u1b, const uint8_t *u2b, sc *u1_out, int8_t *dig1,
+                                int8_t *dig2, uint8_t *sfl) {
+    sc u1, u2;
+    sc_from_be32(u1, u1b + 32 * i);
+    sc_from_be32(u2, u2b + 32 * i);
+    item_store_scalars(u1, u2, 1u, i, n, u1_out, dig1, dig2, sfl);
+}
+
+// BIP-340 lift_x: x-only key, even y (secec/bitcoin/schnorr.go:257-275)
+S256_HD uint8_t item_decode_xonly(apt &out, const uint8_t *pkx32) {
+    fe x;
+    fe_from_be32(x, pkx32);
+    return item_decompress(out, x, fe_limbs_are_canonical(x), 0u);
+}
+// RecoverPoint (point_s11n.go:245-282): x = r (+ n if v & 2), parity v & 1.
+// r + n must stay below p -- the reference's round-trip sanity check.
+S256_HD uint8_t item_decode_recover(apt &out, const uint8_t *sig65) {
+    uint32_t v = sig65[64];
+    sc r;
+    uint32_t ok = 1u - sc_from_be32(r, sig65);
+    ok &= (uint32_t)(v < 4);
+    fe x;
+#pragma unroll
+    for (int k = 0; k < 8; k++) x.v[k] = r.v[k];
+    if (v & 2u) {
+        fe nn = fe_group_order();
+        uint64_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            acc = (acc >> 32) + x.v[k] + nn.v[k];
+            x.v[k] = (uint32_t)acc;
+        }
+        ok &= (1u - (uint32_t)(acc >> 32)) & fe_limbs_are_canonical(x);
+    }
+    return item_decompress(out, x, ok, v & 1u);
+}
+
+// secec/ecdsa.go:244-282: u1 = -e / r, u2 = s / r over r||s||v rows (65 B),
+// K items per thread sharing one inversion.
+template <int K>
+S256_HD void group_recover_scalars(size_t t, size_t stride, size_t n, const uint8_t *digest32, const uint8_t *sig65,
+                                   sc *u1_out, int8_t *dig1, int8_t *dig2, uint8_t *sfl) {
+    sc pre[K];
+    sc run = sc_one();
+    const sc one = sc_one();
+    ecdsa_parsed p;
+    for (int m = 0; m < K; m++) {
+        size_t i = t + (size_t)m * stride;
+        pre[m] = run;
+        if (i < n) {
+            item_ecdsa_parse(p, digest32 + 32 * i, sig65 + 65 * i, 0u);
+            sc_cmov(p.r, one, p.r, p.valid);
+            sc_mul(run, run, p.r);
+        }
+    }
+    sc inv;
+    sc_invert(inv, run);
+    for (int m = K - 1; m >= 0; m--) {
+        size_t i = t + (size_t)m * stride;
+        if (i >= n) continue;
+        item_ecdsa_parse(p, digest32 + 32 * i, sig65 + 65 * i, 0u);
+        sc_cmov(p.r, one, p.r, p.valid);
+        sc rinv, ne, a, b2;
+        sc_mul(rinv, inv, pre[m]);
+        sc_mul(inv, inv, p.r);
+        sc_neg(ne, p.e);
+        sc_mul(a, ne, rinv);
+        sc_mul(b2, p.s, rinv);
+        item_store_scalars(a, b2, p.valid, i, n, u1_out, dig1, dig2, sfl);
+    }
+}
+
+// secec/bitcoin/schnorr.go:420-449: r < p, s < n (zero allowed),
+// e = H(r||P||m) mod n; R = s*G + (-e)*P (:244-245)
+S256_HD void item_schnorr_scalars(size_t i, size_t n, const uint8_t *pkx32, const uint8_t *msg, size_t msg_len,
+                                  const uint8_t *sig64, sc *u1_out, int8_t *dig1, int8_t *dig2, uint8_t *sfl) {
+    const uint8_t *sg = sig64 + 64 * i;
+    fe r;
+    fe_from_be32(r, sg);
+    sc s, e, ne;
+    uint32_t ok = fe_limbs_are_canonical(r) & (1u - sc_from_be32(s, sg + 32));
+    uint8_t eb[32];
+    bip340_challenge(eb, sg, pkx32 + 32 * i, msg + msg_len * i, msg_len);
+    sc_from_be32(e, eb);
+    sc_neg(ne, e);
+    item_store_scalars(s, ne, ok, i, n, u1_out, dig1, dig2, sfl);
+}
+
+// ---------------------------------------------------------------------------
+// R = u1*G + u2*P, variable time (point_mul_glv.go:307-317 and everything
+// under it).  Signed fixed windows with uniform control flow replace the
+// reference's zero-digit skipping (a warp only skips when all 32 lanes do).
+//   table : [1..TS]P by doublings and mixed additions (P is affine)
+//   ladder: ND steps of W doublings + two complete additions, the lambda half
+//           reusing the same table through x -> beta*x
+//   G half: COMB_NW mixed additions from the precomputed comb, no doublings
+// ---------------------------------------------------------------------------
+S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
+                      const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
+    pt *T = tbl + i * (size_t)DSM_TS;
+    {
+        apt P = aff[i];
+        pt cur;
+        pt_from_affine(cur, P);
+        T[0] = cur;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int k = 2; k <= DSM_TS; k += 2) {
+            pt h = T[k / 2 - 1];
+            pt_double(cur, h);
+            T[k - 1] = cur;
+            if (k < DSM_TS) {
+                pt_add_mixed(cur, cur, P.x, P.y);
+                T[k] = cur;
+            }
+        }
+    }
+    uint32_t fl = sfl[i];
+    pt acc;
+    pt_set_identity(acc);
+    const fe beta = fe_beta();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int s = DSM_ND - 1; s >= 0; s--) {
+        if (s != DSM_ND - 1) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int k = 0; k < DSM_W; k++) pt_double(acc, acc);
+        }
+        int da = dig1[(size_t)s * n + i];
+        int db = dig2[(size_t)s * n + i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int h = 0; h < 2; h++) {
+            int d = h ? db : da;
+            if (d != 0) {
+                uint32_t neg = (uint32_t)(d < 0) ^ ((fl >> (1 + h)) & 1u);
+                int mag = d < 0 ? -d : d;
+                pt q = T[mag - 1];
+                if (h) fe_mul(q.x, q.x, beta);
+                if (neg) fe_neg(q.y, q.y);
+                pt_add(acc, acc, q);
+            }
+        }
+    }
+    sc u1 = u1s[i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int w = 0; w < COMB_NW; w++) {
+        int bit = w * COMB_WB;
+        uint32_t d = u1.v[bit >> 5] >> (bit & 31);
+        if ((bit & 31) + COMB_WB > 32 && (bit >> 5) + 1 < 8) d |= u1.v[(bit >> 5) + 1] << (32 - (bit & 31));
+        d &= (uint32_t)COMB_SZ - 1u;
+        if (d != 0) {
+            apt g = comb[(size_t)w * COMB_SZ + d];
+            pt_add_mixed(acc, acc, g.x, g.y);
+        }
+    }
+    res[i] = acc;
+}
+
+// ---------------------------------------------------------------------------
+// ECDSA finish (secec/ecdsa.go:450-467) without leaving projective space:
+// x(R) mod n == r  <=>  X == r*Z  or  (r + n < p and X == (r + n)*Z).
+// ---------------------------------------------------------------------------
+S256_HD uint8_t item_ecdsa_finish(const pt &R, const uint8_t *sig64, uint32_t valid) {
+    fe r, rn, t;
+    fe_from_be32(r, sig64);
+    uint32_t ok = valid & (1u - pt_is_identity(R));
+    fe_mul(t, r, R.z);
+    uint32_t m1 = fe_equal(t, R.x);
+    // r + n as an integer; usable iff it does not wrap and is < p
+    fe nn = fe_group_order();
+    uint64_t acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        acc = (acc >> 32) + r.v[k] + nn.v[k];
+        rn.v[k] = (uint32_t)acc;
+    }
+    uint32_t fits = (1u - (uint32_t)(acc >> 32)) & fe_limbs_are_canonical(rn);
+    fe_mul(t, rn, R.z);
+    uint32_t m2 = fits & fe_equal(t, R.x);
+    return (uint8_t)(ok & (m1 | m2));
+}
+
+// ---------------------------------------------------------------------------
+// projective -> affine for K results per thread with one shared Fermat chain
+// (replaces the per-point inversion of point_projective.go:278-302), then the
+// SEC 1 encodings of point_s11n.go:66-134.  Branch-free on the point value
+// (identity handled by select), so the constant-time paths can use it.
+// mode 0: 65-byte uncompressed + status; mode 1: 32-byte x + status (ECDH,
+// secec/secec.go:53-56: identity is an error); mode 2: BIP-340 acceptance
+// (schnorr.go:451-478): not identity, y even, x == sig[0:32].
+// ---------------------------------------------------------------------------
+template <int K>
+S256_HD void group_finish_affine(size_t t, size_t stride, size_t n, const pt *res, const uint8_t *in_status, int mode,
+                                 uint8_t *out, uint8_t *status, const uint8_t *sig64) {
+    fe pre[K];
+    fe run = fe_one();
+    const fe one = fe_one();
+    for (int m = 0; m < K; m++) {
+        size_t i = t + (size_t)m * stride;
+        pre[m] = run;
+        if (i < n) {
+            fe z = res[i].z;
+            fe_cmov(z, z, one, fe_is_zero(z));
+            fe_mul(run, run, z);
+        }
+    }
+    fe inv;
+    fe_invert(inv, run);
+    for (int m = K - 1; m >= 0; m--) {
+        size_t i = t + (size_t)m * stride;
+        if (i >= n) continue;
+        pt R = res[i];
+        uint32_t ident = fe_is_zero(R.z);
+        fe z;
+        fe_cmov(z, R.z, one, ident);
+        fe zi, x, y;
+        fe_mul(zi, inv, pre[m]);
+        fe_mul(inv, inv, z);
+        fe_mul(x, R.x, zi);
+        fe_mul(y, R.y, zi);
+        fe_normalize(x, x);
+        fe_normalize(y, y);
+        uint32_t in_ok = in_status ? (uint32_t)(in_status[i] != 0) : 1u;
+        uint32_t keep = in_ok & (1u - ident);
+        uint32_t km = 0u - keep;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            x.v[k] &= km;
+            y.v[k] &= km;
+        }
+        uint8_t st = (uint8_t)(in_ok ? (ident ? ST_IDENTITY : ST_OK) : ST_INVALID);
+        if (mode == 0) {
+            uint8_t *o = out + 65 * i;
+            o[0] = (uint8_t)(keep ? 0x04 : 0x00);
+            fe_to_be32(o + 1, x);
+            fe_to_be32(o + 33, y);
+            status[i] = st;
+        } else if (mode == 1) {
+            fe_to_be32(out + 32 * i, x);
+            status[i] = st;
+        } else {
+            fe r;
+            fe_from_be32(r, sig64 + 64 * i);
+            uint32_t same = 1;
+#pragma unroll
+            for (int k = 0; k < 8; k++) same &= (uint32_t)(r.v[k] == x.v[k]);
+            status[i] = (uint8_t)(keep & same & (1u - (y.v[0] & 1u)));
+        }
+    }
+}
+
+// k_finish_affine body: fold the validity sources (decoded point, scalar
+// parse) into cstat, convert, and for mode 3 (RecoverPublicKey) turn an
+// identity result into an error (secec/secec.go:206-209).
+template <int K>
+S256_HD void group_finish(size_t t, size_t stride, size_t n, const pt *res, const uint8_t *pvalid, const uint8_t *sfl,
+                          uint8_t *cstat, int mode, uint8_t *out, uint8_t *status, const uint8_t *sig64) {
+    for (int m = 0; m < K; m++) {
+        size_t i = t + (size_t)m * stride;
+        if (i < n) {
+            uint32_t v = 1;
+            if (pvalid) v &= (uint32_t)(pvalid[i] != 0);
+            if (sfl) v &= (uint32_t)(sfl[i] & SFL_VALID);
+            cstat[i] = (uint8_t)v;
+        }
+    }
+    group_finish_affine<K>(t, stride, n, res, cstat, mode == 3 ? 0 : mode, out, status, sig64);
+    if (mode == 3) {
+        for (int m = 0; m < K; m++) {
+            size_t i = t + (size_t)m * stride;
+            if (i < n && status[i] == ST_IDENTITY) status[i] = ST_INVALID;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// constant-time fixed-base multiplication (point_mul_table.go:168-194):
+// 64 four-bit windows, every window scans all 15 table entries with masks
+// (the GPU counterpart of point_mul_table_amd64.s:81-130) -- the table is
+// staged in shared memory and every lane reads the same address, so neither
+// the address stream nor the bank pattern depends on the scalar.  Digit 0 is
+// resolved by select after a dummy mixed add (point_mul_table.go:118-129).
+// ---------------------------------------------------------------------------
+S256_HD void item_base_mult_ct(pt &acc, const sc &k, const apt *tab /* [64][16], entry 0 unused */) {
+    pt_set_identity(acc);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int w = 0; w < CT_NW; w++) {
+        uint32_t d = (k.v[w >> 3] >> ((w & 7) * 4)) & 0xFu;
+        apt sel;
+        sel.x = fe_zero();
+        sel.y = fe_zero();
+        const apt *row = tab + w * CT_SZ;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 3
+#endif
+        for (uint32_t j = 1; j < CT_SZ; j++) {
+            uint32_t m = 0u - (uint32_t)(j == d);
+            apt e = row[j];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                sel.x.v[q] |= e.x.v[q] & m;
+                sel.y.v[q] |= e.y.v[q] & m;
+            }
+        }
+        // d == 0 selected nothing: add a well-formed dummy (entry 1) and discard
+        uint32_t zero = (uint32_t)(d == 0);
+        apt e1 = row[1];
+        fe_cmov(sel.x, sel.x, e1.x, zero);
+        fe_cmov(sel.y, sel.y, e1.y, zero);
+        pt sum;
+        pt_add_mixed(sum, acc, sel.x, sel.y);
+        pt_cmov(acc, sum, acc, zero);
+    }
+}
+
+}  // namespace s256

@@ -1,0 +1,95 @@
+// sha256.cuh -- SHA-256 (FIPS 180-4) per thread, for the BIP-340 challenge
+// e = SHA256(SHA256(tag) || SHA256(tag) || r || P || m) with tag
+// "BIP0340/challenge" (secec/bitcoin/schnorr.go:309-320, :445-446; the
+// reference uses Go's crypto/sha256).  The state after the 64-byte tag block
+// is a constant, so each item hashes only r || P || m.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include "fe.cuh"
+
+namespace s256 {
+
+S256_HD uint32_t sha_rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+
+S256_HD uint32_t sha_k(int i) {
+    const uint32_t K[64] = {
+        0x428a2f98u, 0x71374491u, 0xb5c0fbcfu, 0xe9b5dba5u, 0x3956c25bu, 0x59f111f1u, 0x923f82a4u, 0xab1c5ed5u,
+        0xd807aa98u, 0x12835b01u, 0x243185beu, 0x550c7dc3u, 0x72be5d74u, 0x80deb1feu, 0x9bdc06a7u, 0xc19bf174u,
+        0xe49b69c1u, 0xefbe4786u, 0x0fc19dc6u, 0x240ca1ccu, 0x2de92c6fu, 0x4a7484aau, 0x5cb0a9dcu, 0x76f988dau,
+        0x983e5152u, 0xa831c66du, 0xb00327c8u, 0xbf597fc7u, 0xc6e00bf3u, 0xd5a79147u, 0x06ca6351u, 0x14292967u,
+        0x27b70a85u, 0x2e1b2138u, 0x4d2c6dfcu, 0x53380d13u, 0x650a7354u, 0x766a0abbu, 0x81c2c92eu, 0x92722c85u,
+        0xa2bfe8a1u, 0xa81a664bu, 0xc24b8b70u, 0xc76c51a3u, 0xd192e819u, 0xd6990624u, 0xf40e3585u, 0x106aa070u,
+        0x19a4c116u, 0x1e376c08u, 0x2748774cu, 0x34b0bcb5u, 0x391c0cb3u, 0x4ed8aa4au, 0x5b9cca4fu, 0x682e6ff3u,
+        0x748f82eeu, 0x78a5636fu, 0x84c87814u, 0x8cc70208u, 0x90befffau, 0xa4506cebu, 0xbef9a3f7u, 0xc67178f2u};
+    return K[i];
+}
+
+// one compression; w[16] is consumed (used as the rolling schedule)
+S256_HD void sha256_compress(uint32_t h[8], uint32_t w[16]) {
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        if (i >= 16) {
+            uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
+            uint32_t s0 = sha_rotr(w15, 7) ^ sha_rotr(w15, 18) ^ (w15 >> 3);
+            uint32_t s1 = sha_rotr(w2, 17) ^ sha_rotr(w2, 19) ^ (w2 >> 10);
+            w[i & 15] = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+        }
+        uint32_t S1 = sha_rotr(e, 6) ^ sha_rotr(e, 11) ^ sha_rotr(e, 25);
+        uint32_t ch = (e & f) ^ (~e & g);
+        uint32_t t1 = hh + S1 + ch + sha_k(i) + w[i & 15];
+        uint32_t S0 = sha_rotr(a, 2) ^ sha_rotr(a, 13) ^ sha_rotr(a, 22);
+        uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+        uint32_t t2 = S0 + mj;
+        hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+
+// out32 = BIP-340 challenge hash of (r32 || px32 || msg[0..msg_len))
+S256_HD void bip340_challenge(uint8_t out32[32], const uint8_t *r32, const uint8_t *px32, const uint8_t *msg,
+                              size_t msg_len) {
+    // state after SHA256("BIP0340/challenge") twice (one 64-byte block)
+    uint32_t h[8] = {0x9cecba11u, 0x23925381u, 0x11679112u, 0xd1627e0fu,
+                     0x97c87550u, 0x003cc765u, 0x90f61164u, 0x33e9b66au};
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        w[i] = ((uint32_t)r32[4 * i] << 24) | ((uint32_t)r32[4 * i + 1] << 16) | ((uint32_t)r32[4 * i + 2] << 8) | r32[4 * i + 3];
+        w[8 + i] = ((uint32_t)px32[4 * i] << 24) | ((uint32_t)px32[4 * i + 1] << 16) | ((uint32_t)px32[4 * i + 2] << 8) | px32[4 * i + 3];
+    }
+    sha256_compress(h, w);
+    // message + padding; total length = 128 + msg_len bytes
+    uint64_t total_bits = (uint64_t)(128 + msg_len) * 8;
+    size_t off = 0;
+    bool done = false, pad_started = false;
+    while (!done) {
+        uint8_t blk[64];
+        int fill = 0;
+        while (fill < 64 && off < msg_len) blk[fill++] = msg[off++];
+        if (fill < 64 && !pad_started) {
+            blk[fill++] = 0x80;
+            pad_started = true;
+        }
+        if (pad_started && fill <= 56) {
+            while (fill < 56) blk[fill++] = 0;
+            for (int i = 0; i < 8; i++) blk[56 + i] = (uint8_t)(total_bits >> (56 - 8 * i));
+            done = true;
+        } else {
+            while (fill < 64) blk[fill++] = 0;
+        }
+        for (int i = 0; i < 16; i++)
+            w[i] = ((uint32_t)blk[4 * i] << 24) | ((uint32_t)blk[4 * i + 1] << 16) | ((uint32_t)blk[4 * i + 2] << 8) | blk[4 * i + 3];
+        sha256_compress(h, w);
+    }
+    for (int i = 0; i < 8; i++) {
+        out32[4 * i] = (uint8_t)(h[i] >> 24);
+        out32[4 * i + 1] = (uint8_t)(h[i] >> 16);
+        out32[4 * i + 2] = (uint8_t)(h[i] >> 8);
+        out32[4 * i + 3] = (uint8_t)h[i];
+    }
+}
+
+}  // namespace s256

@@ -1,0 +1,85 @@
+"""ctypes view of tests/hostsim/hostsim.cpp (CPU simulation of the kernel
+logic; test infrastructure only, see the header of hostsim.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_SO = os.path.join(_HERE, "_build", "hostsim.so")
+_lib = None
+
+
+def _deps():
+    csrc = os.path.join(_ROOT, "secp256k1-voi_b200", "csrc")
+    return [os.path.join(_HERE, "hostsim.cpp")] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        stale = not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in _deps())
+        if stale:
+            os.makedirs(os.path.dirname(_SO), exist_ok=True)
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-x", "c++",
+                                   "-o", _SO, os.path.join(_HERE, "hostsim.cpp")])
+        _lib = C.CDLL(_SO)
+    return _lib
+
+
+def _a(x, w):
+    return np.ascontiguousarray(x, dtype=np.uint8).reshape(-1, w)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def ecdsa_verify(pk, dg, sig, flags=0):
+    pk, dg, sig = _a(pk, 65), _a(dg, 32), _a(sig, 64)
+    n = len(pk); ok = np.zeros(n, np.uint8)
+    lib().sim_ecdsa_verify(_p(pk), _p(dg), _p(sig), C.c_uint32(flags), C.c_size_t(n), _p(ok))
+    return ok
+
+
+def ecdsa_recover(dg, sig65):
+    dg, sig65 = _a(dg, 32), _a(sig65, 65)
+    n = len(dg); out = np.zeros((n, 65), np.uint8); st = np.zeros(n, np.uint8)
+    lib().sim_ecdsa_recover(_p(dg), _p(sig65), C.c_size_t(n), _p(out), _p(st))
+    return out, st
+
+
+def schnorr_verify(pkx, msg, sig):
+    pkx, sig = _a(pkx, 32), _a(sig, 64)
+    n = len(pkx)
+    msg = np.ascontiguousarray(msg, dtype=np.uint8).reshape(n, -1)
+    ok = np.zeros(n, np.uint8)
+    lib().sim_schnorr_verify(_p(pkx), _p(msg), C.c_size_t(msg.shape[1]), _p(sig), C.c_size_t(n), _p(ok))
+    return ok
+
+
+def double_scalar_mult(u1, u2, pts):
+    u1, u2, pts = _a(u1, 32), _a(u2, 32), _a(pts, 65)
+    n = len(u1); out = np.zeros((n, 65), np.uint8); st = np.zeros(n, np.uint8)
+    lib().sim_double_scalar_mult(_p(u1), _p(u2), _p(pts), C.c_size_t(n), _p(out), _p(st))
+    return out, st
+
+
+def scalar_base_mult(k):
+    k = _a(k, 32); n = len(k); out = np.zeros((n, 65), np.uint8); st = np.zeros(n, np.uint8)
+    lib().sim_scalar_base_mult(_p(k), C.c_size_t(n), _p(out), _p(st))
+    return out, st
+
+
+def gen_table(wbits, nwin):
+    out = np.zeros(((2 ** wbits - 1) * nwin, 64), np.uint8)
+    lib().sim_gen_table(wbits, nwin, _p(out))
+    return out
+
+
+def field_op(op, a, b):
+    a, b = _a(a, 32), _a(b, 32); n = len(a); out = np.zeros((n, 32), np.uint8)
+    lib().sim_field_op(op, _p(a), _p(b), C.c_size_t(n), _p(out))
+    return out

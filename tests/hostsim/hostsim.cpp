@@ -1,0 +1,160 @@
+// hostsim.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles secp256k1-voi_b200/csrc/kernels.cuh with g++ (portable limb
+// arithmetic instead of PTX) and drives the *same* item/group functions in the
+// same order as api.cu's pipelines, one "thread" at a time.  It exists because
+// the build container has no GPU: kernel logic (recoding, ladders, batched
+// inversion, encodings) is debugged here against the oracle before GPU time
+// is spent.  It is never linked into, or called by, the product library.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../secp256k1-voi_b200/csrc/kernels.cuh"
+
+using namespace s256;
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+static std::vector<apt> g_comb, g_ct;
+static constexpr int K = 16;
+
+static void ensure_tables() {
+    if (!g_ct.empty()) return;
+    g_ct.resize((size_t)CT_NW * CT_SZ);
+    for (size_t idx = 0; idx < g_ct.size(); idx++) item_gen_multiple(g_ct[idx], (uint32_t)(idx >> 4), (uint32_t)(idx & 15), 4);
+}
+// The comb has 2^20 entries; generating it with the bit-serial routine is too
+// slow on one CPU core, so the simulation fills only the entries a batch uses.
+static std::vector<uint8_t> g_comb_have;
+static void ensure_comb_entry(uint32_t w, uint32_t d) {
+    if (g_comb.empty()) {
+        g_comb.resize((size_t)COMB_NW * COMB_SZ);
+        g_comb_have.assign(g_comb.size(), 0);
+    }
+    size_t idx = (size_t)w * COMB_SZ + d;
+    if (!g_comb_have[idx]) {
+        item_gen_multiple(g_comb[idx], w, d, COMB_WB);
+        g_comb_have[idx] = 1;
+    }
+}
+
+struct scratch {
+    std::vector<apt> aff;
+    std::vector<sc> u1;
+    std::vector<int8_t> dig1, dig2;
+    std::vector<uint8_t> sfl, pvalid, cstat;
+    std::vector<pt> tbl, res;
+    explicit scratch(size_t n)
+        : aff(n), u1(n), dig1(n * DSM_ND), dig2(n * DSM_ND), sfl(n), pvalid(n), cstat(n), tbl(n * DSM_TS), res(n) {}
+};
+
+static void run_dsm(scratch &s, size_t n) {
+    for (size_t i = 0; i < n; i++)
+        for (int w = 0; w < COMB_NW; w++) {
+            int bit = w * COMB_WB;
+            uint32_t d = s.u1[i].v[bit >> 5] >> (bit & 31);
+            if ((bit & 31) + COMB_WB > 32 && (bit >> 5) + 1 < 8) d |= s.u1[i].v[(bit >> 5) + 1] << (32 - (bit & 31));
+            d &= (uint32_t)COMB_SZ - 1u;
+            if (d) ensure_comb_entry((uint32_t)w, d);
+        }
+    if (g_comb.empty()) ensure_comb_entry(0, 1);
+    for (size_t i = 0; i < n; i++)
+        item_dsm(i, n, s.aff.data(), s.u1.data(), s.dig1.data(), s.dig2.data(), s.sfl.data(), s.tbl.data(), s.res.data(),
+                 g_comb.data());
+}
+static void run_finish(scratch &s, size_t n, bool use_pvalid, bool use_sfl, int mode, uint8_t *out, uint8_t *status,
+                       const uint8_t *sig) {
+    size_t stride = (n + K - 1) / K;
+    for (size_t t = 0; t < stride; t++)
+        group_finish<K>(t, stride, n, s.res.data(), use_pvalid ? s.pvalid.data() : nullptr,
+                        use_sfl ? s.sfl.data() : nullptr, s.cstat.data(), mode, out, status, sig);
+}
+
+EXPORT void sim_ecdsa_verify(const uint8_t *pk, const uint8_t *dg, const uint8_t *sig, uint32_t flags, size_t n, uint8_t *ok) {
+    scratch s(n);
+    for (size_t i = 0; i < n; i++) s.pvalid[i] = item_decode_uncompressed(s.aff[i], pk + 65 * i);
+    size_t stride = (n + K - 1) / K;
+    for (size_t t = 0; t < stride; t++)
+        group_ecdsa_scalars<K>(t, stride, n, dg, sig, flags, s.u1.data(), s.dig1.data(), s.dig2.data(), s.sfl.data());
+    run_dsm(s, n);
+    for (size_t i = 0; i < n; i++) {
+        uint32_t valid = (uint32_t)(s.pvalid[i] != 0) & (uint32_t)(s.sfl[i] & SFL_VALID);
+        ok[i] = item_ecdsa_finish(s.res[i], sig + 64 * i, valid);
+    }
+}
+EXPORT void sim_ecdsa_recover(const uint8_t *dg, const uint8_t *sig65, size_t n, uint8_t *pk65, uint8_t *status) {
+    scratch s(n);
+    for (size_t i = 0; i < n; i++) s.pvalid[i] = item_decode_recover(s.aff[i], sig65 + 65 * i);
+    size_t stride = (n + K - 1) / K;
+    for (size_t t = 0; t < stride; t++)
+        group_recover_scalars<K>(t, stride, n, dg, sig65, s.u1.data(), s.dig1.data(), s.dig2.data(), s.sfl.data());
+    run_dsm(s, n);
+    run_finish(s, n, true, true, 3, pk65, status, nullptr);
+}
+EXPORT void sim_schnorr_verify(const uint8_t *pkx, const uint8_t *msg, size_t msg_len, const uint8_t *sig, size_t n, uint8_t *ok) {
+    scratch s(n);
+    for (size_t i = 0; i < n; i++) s.pvalid[i] = item_decode_xonly(s.aff[i], pkx + 32 * i);
+    for (size_t i = 0; i < n; i++)
+        item_schnorr_scalars(i, n, pkx, msg, msg_len, sig, s.u1.data(), s.dig1.data(), s.dig2.data(), s.sfl.data());
+    run_dsm(s, n);
+    run_finish(s, n, true, true, 2, nullptr, ok, sig);
+}
+EXPORT void sim_double_scalar_mult(const uint8_t *u1, const uint8_t *u2, const uint8_t *pt65, size_t n, uint8_t *out65, uint8_t *status) {
+    scratch s(n);
+    for (size_t i = 0; i < n; i++) s.pvalid[i] = item_decode_uncompressed(s.aff[i], pt65 + 65 * i);
+    for (size_t i = 0; i < n; i++) item_plain_scalars(i, n, u1, u2, s.u1.data(), s.dig1.data(), s.dig2.data(), s.sfl.data());
+    run_dsm(s, n);
+    run_finish(s, n, true, false, 0, out65, status, nullptr);
+}
+EXPORT void sim_scalar_base_mult(const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status) {
+    ensure_tables();
+    scratch s(n);
+    for (size_t i = 0; i < n; i++) {
+        sc k;
+        sc_from_be32(k, k32 + 32 * i);
+        item_base_mult_ct(s.res[i], k, g_ct.data());
+    }
+    run_finish(s, n, false, false, 0, out65, status, nullptr);
+}
+EXPORT void sim_gen_table(int wbits, int nwin, uint8_t *out) {
+    for (int w = 0; w < nwin; w++)
+        for (uint32_t d = 1; d < (1u << wbits); d++) {
+            apt a;
+            item_gen_multiple(a, (uint32_t)w, d, wbits);
+            fe_to_be32(out, a.x);
+            fe_to_be32(out + 32, a.y);
+            out += 64;
+        }
+}
+EXPORT void sim_field_op(int op, const uint8_t *a32, const uint8_t *b32, size_t n, uint8_t *out32) {
+    for (size_t i = 0; i < n; i++) {
+        if (op < 16) {
+            fe a, b, r;
+            fe_from_be32(a, a32 + 32 * i);
+            fe_from_be32(b, b32 + 32 * i);
+            switch (op) {
+                case 0: fe_mul(r, a, b); break;
+                case 1: fe_add(r, a, b); break;
+                case 2: fe_sub(r, a, b); break;
+                case 3: fe_invert(r, a); break;
+                case 4: fe_sqrt(r, a); break;
+                case 5: fe_mul_small(r, a, 21u); break;
+                case 6: fe_sqr(r, a); break;
+                default: r = fe_zero();
+            }
+            fe_normalize(r, r);
+            fe_to_be32(out32 + 32 * i, r);
+        } else {
+            sc a, b, r;
+            sc_from_be32(a, a32 + 32 * i);
+            sc_from_be32(b, b32 + 32 * i);
+            switch (op) {
+                case 16: sc_mul(r, a, b); break;
+                case 17: sc_add(r, a, b); break;
+                case 18: sc_invert(r, a); break;
+                default: r = sc_zero();
+            }
+            sc_to_be32(out32 + 32 * i, r);
+        }
+    }
+}

@@ -1,0 +1,66 @@
+"""Kernel LOGIC parity on CPU: the item functions of csrc/kernels.cuh compiled
+with g++ (portable limb arithmetic) and driven through the same pipelines as
+api.cu, checked against the oracle and the golden vectors.  The product (PTX
+arithmetic, real launches) is checked by test_gpu_parity.py on the B200."""
+import numpy as np
+import pytest
+
+import hostsim as hs
+import parity_suites as ps
+
+
+class Backend:
+    ecdsa_verify = staticmethod(hs.ecdsa_verify)
+    ecdsa_recover = staticmethod(hs.ecdsa_recover)
+    schnorr_verify = staticmethod(hs.schnorr_verify)
+    double_scalar_mult_basepoint_vartime = staticmethod(hs.double_scalar_mult)
+    scalar_base_mult = staticmethod(hs.scalar_base_mult)
+    debug_field_op = staticmethod(hs.field_op)
+    debug_gen_table = staticmethod(hs.gen_table)
+
+
+be = Backend()
+
+
+def test_field_ops():
+    ps.check_field_ops(be, n=64)
+
+
+def test_gen_table_matches_reference_bin():
+    ps.check_gen_table(be)
+
+
+def test_base_mult(oracle):
+    ps.check_base_mult(be, oracle, n=32)
+
+
+def test_rfc6979(oracle):
+    ps.check_rfc6979_and_kats(be, oracle)
+
+
+def test_wycheproof_ecdsa_subset(oracle):
+    ps.check_wycheproof_ecdsa(be, oracle, limit=8)
+
+
+def test_bip340():
+    ps.check_bip340(be)
+
+
+def test_ecdsa_synth(oracle):
+    ps.check_ecdsa_synth(be, oracle, n=64)
+
+
+def test_schnorr_synth(oracle):
+    ps.check_schnorr_synth(be, oracle, n=32)
+
+
+def test_ecdsa_edges(oracle):
+    ps.check_ecdsa_edges(be, oracle)
+
+
+def test_double_scalar_mult(oracle):
+    ps.check_double_scalar_mult(be, oracle, n=40)
+
+
+def test_recover(oracle):
+    ps.check_recover_synth(be, oracle, n=16)
