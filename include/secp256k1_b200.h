@@ -32,6 +32,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
 
 typedef struct s256_ctx s256_ctx;
 
@@ -140,12 +143,19 @@ int s256_debug_field_op(s256_ctx *ctx, int op, const uint8_t *a32, const uint8_t
 /* Integer-multiply peak: runs independent IMAD.WIDE.U32 chains on every SM and
  * returns MAC32 per second (the roofline denominator). */
 int s256_microbench_imad(s256_ctx *ctx, int iters, double *mac32_per_s, double *ms);
+/* CUDA-event timing of the dominant kernel (the u1*G + u2*P ladder) on the stream
+ * it is launched on: enable, run steps, read the summed device time. */
+int s256_profile_enable(s256_ctx *ctx, int enable);
+int s256_profile_read(s256_ctx *ctx, double *dsm_ms_total, uint64_t *dsm_launches);
 /* Number of kernel launches issued through this context so far. */
 uint64_t s256_launch_count(const s256_ctx *ctx);
 /* MAC32 (32x32->64 multiply-accumulates) executed per item by each path,
  * derived from the modmul counts in DESIGN.md; key is an entry point name. */
 double s256_mac32_per_item(const char *entry_point);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = [
     "s256_schnorr_verify", "s256_schnorr_verify_dev",
     "s256_msm", "s256_msm_partial", "s256_msm_combine",
     "s256_debug_gen_table", "s256_debug_field_op", "s256_microbench_imad",
+    "s256_profile_enable", "s256_profile_read",
     "s256_launch_count", "s256_mac32_per_item",
 ]
 
@@ -331,6 +332,15 @@ class Engine:
         self._check(self._lib.s256_debug_field_op(self._ctx, int(op), self._hp(a), self._hp(b), C.c_size_t(len(a)),
                                                   self._hp(out)), "debug_field_op")
         return out
+
+    def profile_enable(self, on=True):
+        self._check(self._lib.s256_profile_enable(self._ctx, int(bool(on))), "profile_enable")
+
+    def profile_read(self):
+        """(summed device ms of the ladder kernel, number of its launches) since profile_enable."""
+        ms, cnt = C.c_double(0), C.c_uint64(0)
+        self._check(self._lib.s256_profile_read(self._ctx, C.byref(ms), C.byref(cnt)), "profile_read")
+        return ms.value, int(cnt.value)
 
     def microbench_imad(self, iters=4096):
         rate, ms = C.c_double(0), C.c_double(0)

@@ -11,6 +11,8 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/secp256k1_b200.h"
 #include "kernels.cuh"
@@ -218,6 +220,9 @@ struct s256_ctx {
     uint8_t *in_a = nullptr, *in_b = nullptr, *in_c = nullptr, *out = nullptr, *st = nullptr;
     size_t in_b_bytes = 0;
     unsigned long long *sink = nullptr;
+    // optional per-kernel timing of the dominant kernel (bench.py roofline)
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dsm_events;
 };
 
 #define CK(call)                                                                     \
@@ -346,8 +351,18 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
 // device-pointer pipelines (one chunk <= cap)
 // ---------------------------------------------------------------------------
 static void enqueue_dsm(s256_ctx *ctx, size_t n, cudaStream_t s) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ctx->profiling) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, s);
+    }
     LAUNCH(ctx, k_dsm, grid_for(n), 0, s, n, ctx->aff, ctx->u1, ctx->dig1, ctx->dig2, ctx->sfl, ctx->tbl, ctx->res,
            ctx->comb);
+    if (ctx->profiling) {
+        cudaEventRecord(e1, s);
+        ctx->dsm_events.emplace_back(e0, e1);
+    }
 }
 constexpr int INV_K = 16;
 static inline unsigned grid_for_groups(size_t n, int k) { return grid_for((n + k - 1) / k); }
@@ -667,6 +682,37 @@ extern "C" int s256_microbench_imad(s256_ctx *ctx, int iters, double *mac32_per_
     if (mac32_per_s) *mac32_per_s = macs / (ms * 1e-3);
     if (ms_out) *ms_out = ms;
     return check_launch(ctx);
+}
+
+// Per-kernel timing of k_dsm with CUDA events on the launching stream: enable, run
+// steps, then read (synchronises on the recorded events and clears them).
+extern "C" int s256_profile_enable(s256_ctx *ctx, int enable) {
+    ENTER(ctx);
+    for (auto &pr : ctx->dsm_events) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    ctx->dsm_events.clear();
+    ctx->profiling = enable != 0;
+    return S256_SUCCESS;
+}
+extern "C" int s256_profile_read(s256_ctx *ctx, double *dsm_ms_total, uint64_t *dsm_launches) {
+    ENTER(ctx);
+    double total = 0;
+    uint64_t cnt = 0;
+    for (auto &pr : ctx->dsm_events) {
+        CK(cudaEventSynchronize(pr.second));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        total += ms;
+        cnt++;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    ctx->dsm_events.clear();
+    if (dsm_ms_total) *dsm_ms_total = total;
+    if (dsm_launches) *dsm_launches = cnt;
+    return S256_SUCCESS;
 }
 
 // MAC32 per item actually executed (DESIGN.md "work per item"): F_p modmul = 73,

@@ -1,0 +1,48 @@
+"""CPU-side checks of the boundary: the C-ABI library builds for sm_100a, loads,
+exports every symbol include/secp256k1_b200.h declares, and refuses to run
+without a GPU (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "secp256k1_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(s256_\w+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(s256):
+    lib = s256.load_library()
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), n
+    assert sorted(s256.EXPORTED_SYMBOLS) == names
+
+
+def test_no_cpu_fallback(s256):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(s256.S256Error):
+        s256.Engine()
+
+
+def test_product_does_not_reference_oracle():
+    pkg = os.path.join(ROOT, "secp256k1-voi_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in src.lower() or f == "synth.py", os.path.join(dirpath, f)
+
+
+def test_work_model(s256):
+    v = s256.mac32_per_item("ecdsa_verify")
+    assert 1.0e5 < v < 2.6e5  # below the reference algorithm's 257 995
+    assert s256.mac32_per_item("scalar_base_mult") > 5e4

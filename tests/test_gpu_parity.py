@@ -1,0 +1,108 @@
+"""Parity of the PRODUCT (sm_100a kernels through the C ABI) with the oracle.
+Runs on the B200 box: python -m pytest tests -m gpu"""
+import hashlib
+
+import numpy as np
+import pytest
+
+import parity_suites as ps
+
+pytestmark = pytest.mark.gpu
+
+
+def test_field_ops_ptx(engine):
+    ps.check_field_ops(engine, n=4096)
+
+
+def test_gen_table_matches_reference_bin(engine):
+    ps.check_gen_table(engine)
+
+
+def test_base_mult_config1(engine, oracle):
+    # BASELINE.json configs[0]: 4096 scalars + affine encode, bit-exact
+    ps.check_base_mult(engine, oracle, n=4096)
+
+
+def test_rfc6979(engine, oracle):
+    ps.check_rfc6979_and_kats(engine, oracle)
+
+
+def test_wycheproof_ecdsa_all(engine, oracle):
+    ps.check_wycheproof_ecdsa(engine, oracle)
+
+
+def test_bip340(engine):
+    ps.check_bip340(engine)
+
+
+def test_ecdsa_synth(engine, oracle):
+    ps.check_ecdsa_synth(engine, oracle, n=4096)
+
+
+def test_schnorr_synth(engine, oracle):
+    ps.check_schnorr_synth(engine, oracle, n=2048)
+
+
+def test_ecdsa_edges(engine, oracle):
+    ps.check_ecdsa_edges(engine, oracle)
+
+
+def test_double_scalar_mult(engine, oracle):
+    ps.check_double_scalar_mult(engine, oracle, n=2048)
+
+
+def test_recover(engine, oracle):
+    ps.check_recover_synth(engine, oracle, n=512)
+
+
+def test_empty_and_ragged(engine):
+    z = np.zeros((0, 32), np.uint8)
+    out, st = engine.scalar_base_mult(z)
+    assert out.shape == (0, 65) and st.shape == (0,)
+    assert engine.ecdsa_verify(np.zeros((0, 65), np.uint8), z, np.zeros((0, 64), np.uint8)).shape == (0,)
+    with pytest.raises(ValueError):
+        engine.ecdsa_verify(np.zeros((2, 65), np.uint8), np.zeros((1, 32), np.uint8), np.zeros((2, 64), np.uint8))
+    # sizes around the warp / CTA / inversion-group boundaries
+    for n in (1, 15, 16, 17, 31, 33, 127, 129, 1000):
+        ks = ps.synth.base_mult_scalars(n, start=100)
+        out, st = engine.scalar_base_mult(ks)
+        out2, st2 = engine.scalar_base_mult(ks[::-1].copy())
+        assert np.array_equal(out, out2[::-1]) and np.array_equal(st, st2[::-1])
+
+
+def test_device_pointer_path_matches_host_path(engine, oracle):
+    import torch
+    w = ps.synth.ecdsa_batch(1024, ps.oracle_base_mult(oracle))
+    host = engine.ecdsa_verify(w["pk65"], w["digest32"], w["sig64"])
+    dev = engine.ecdsa_verify(torch.from_numpy(w["pk65"]).cuda(), torch.from_numpy(w["digest32"]).cuda(),
+                              torch.from_numpy(w["sig64"]).cuda())
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy(), host)
+    assert np.array_equal(host, w["expected"])
+
+
+def test_chunking_beyond_capacity(s256, oracle):
+    # a context with a tiny capacity must give the same answers chunk by chunk
+    eng = s256.Engine(max_batch=192)
+    try:
+        w = ps.synth.ecdsa_batch(700, ps.oracle_base_mult(oracle))
+        assert np.array_equal(eng.ecdsa_verify(w["pk65"], w["digest32"], w["sig64"]), w["expected"])
+        ks = ps.synth.base_mult_scalars(500)
+        out, st = eng.scalar_base_mult(ks)
+        exp, est = oracle.batch_scalar_base_mult(ks)
+        assert np.array_equal(out, exp) and np.array_equal(st, est)
+    finally:
+        eng.close()
+
+
+def test_full_size_properties(engine):
+    """BASELINE config 2 size (2^20): valid-by-construction signatures made with
+    the engine's own k*G, 1/16 corrupted -> the boolean vector must equal the
+    construction; a checksum pins run-to-run determinism."""
+    n = 1 << 20
+    w = ps.synth.ecdsa_batch(n, engine.scalar_base_mult)
+    a = engine.ecdsa_verify(w["pk65"], w["digest32"], w["sig64"])
+    assert np.array_equal(a, w["expected"])
+    b = engine.ecdsa_verify(w["pk65"], w["digest32"], w["sig64"])
+    assert hashlib.sha256(a.tobytes()).digest() == hashlib.sha256(b.tobytes()).digest()
+    assert int(a.sum()) == n - n // 16
