@@ -143,6 +143,9 @@ int s256_debug_field_op(s256_ctx *ctx, int op, const uint8_t *a32, const uint8_t
 /* Integer-multiply peak: runs independent IMAD.WIDE.U32 chains on every SM and
  * returns MAC32 per second (the roofline denominator). */
 int s256_microbench_imad(s256_ctx *ctx, int iters, double *mac32_per_s, double *ms);
+/* Other probes of the integer pipes (variant ids in csrc/microbench.cuh): carry-chained
+ * IMAD.WIDE.X, 32-bit IMAD, IMAD.HI, IADD3.X chains, mixed issue. */
+int s256_microbench_variant(s256_ctx *ctx, int variant, int iters, double *ops_per_s, double *ms);
 /* CUDA-event timing of the dominant kernel (the u1*G + u2*P ladder) on the stream
  * it is launched on: enable, run steps, read the summed device time. */
 int s256_profile_enable(s256_ctx *ctx, int enable);

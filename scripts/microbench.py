@@ -1,0 +1,14 @@
+import importlib, json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+pkg = importlib.import_module("secp256k1-voi_b200")
+eng = pkg.Engine(device=0, max_batch=1024)
+names = ["mad_wide(IMAD.WIDE.U32)", "madc_chain(IMAD.WIDE.U32.X)", "mad_lo(IMAD)", "mad_hi(IMAD.HI)", "addc_chain(IADD3.X)", "madc_pair(carry-out only)+addc", "mix(IMAD.WIDE + 2 IADD3.X each)"]
+out = {}
+for v, nm in enumerate(names):
+    best = 0
+    for _ in range(3):
+        r, ms = eng.microbench_variant(v, 4096)
+        best = max(best, r)
+    out[nm] = {"ops_per_s": best, "per_clk_per_sm_at_1965MHz": best / 148 / 1.965e9}
+    print(nm, f"{best/1e12:.3f} Tops/s  ({best/148/1.965e9:.1f} /clk/SM @1965MHz)")
+json.dump(out, open("gpurun_out/microbench.json", "w"), indent=1)

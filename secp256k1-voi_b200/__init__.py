@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "s256_schnorr_verify", "s256_schnorr_verify_dev",
     "s256_msm", "s256_msm_partial", "s256_msm_combine",
     "s256_debug_gen_table", "s256_debug_field_op", "s256_microbench_imad",
-    "s256_profile_enable", "s256_profile_read",
+    "s256_microbench_variant", "s256_profile_enable", "s256_profile_read",
     "s256_launch_count", "s256_mac32_per_item",
 ]
 
@@ -341,6 +341,12 @@ class Engine:
         ms, cnt = C.c_double(0), C.c_uint64(0)
         self._check(self._lib.s256_profile_read(self._ctx, C.byref(ms), C.byref(cnt)), "profile_read")
         return ms.value, int(cnt.value)
+
+    def microbench_variant(self, variant, iters=4096):
+        rate, ms = C.c_double(0), C.c_double(0)
+        self._check(self._lib.s256_microbench_variant(self._ctx, int(variant), int(iters), C.byref(rate), C.byref(ms)),
+                    "microbench_variant")
+        return rate.value, ms.value
 
     def microbench_imad(self, iters=4096):
         rate, ms = C.c_double(0), C.c_double(0)

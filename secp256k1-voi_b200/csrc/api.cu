@@ -16,6 +16,8 @@
 
 #include "../../include/secp256k1_b200.h"
 #include "kernels.cuh"
+#include "microbench.cuh"
+#include "launchers.h"
 
 using namespace s256;
 
@@ -92,7 +94,7 @@ __global__ void __launch_bounds__(S256_TPB) k_schnorr_scalars(const uint8_t *pkx
 }
 
 #ifndef S256_DSM_MINB
-#define S256_DSM_MINB 3
+#define S256_DSM_MINB 4
 #endif
 __global__ void __launch_bounds__(S256_TPB, S256_DSM_MINB)
     k_dsm(size_t n, const apt *aff, const sc *u1, const int8_t *dig1, const int8_t *dig2, const uint8_t *sfl, pt *tbl,
@@ -120,28 +122,6 @@ __global__ void __launch_bounds__(S256_TPB) k_finish_affine(size_t n, const pt *
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= stride) return;
     group_finish<K>(t, stride, n, res, pvalid, sfl, comb_status, mode, out, status, sig64);
-}
-
-#ifndef S256_BM_MINB
-#define S256_BM_MINB 3
-#endif
-__global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
-    k_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_g, pt *res) {
-    extern __shared__ uint4 smem_raw[];
-    apt *tab = reinterpret_cast<apt *>(smem_raw);
-    {
-        const uint4 *src = reinterpret_cast<const uint4 *>(tab_g);
-        const int nvec = CT_NW * CT_SZ * (int)sizeof(apt) / 16;
-        for (int v = threadIdx.x; v < nvec; v += blockDim.x) smem_raw[v] = src[v];
-    }
-    __syncthreads();
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        sc k;
-        sc_from_be32(k, k32 + 32 * i);
-        pt acc;
-        item_base_mult_ct(acc, k, tab);
-        res[i] = acc;
-    }
 }
 
 __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a32, const uint8_t *b32, size_t n,
@@ -176,25 +156,6 @@ __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a3
         }
         sc_to_be32(out32 + 32 * i, r);
     }
-}
-
-// Integer-multiply peak: 8 independent IMAD.WIDE.U32 accumulator chains per thread.
-__global__ void __launch_bounds__(256) k_imad_peak(uint32_t seed, int iters, unsigned long long *sink) {
-    uint32_t a = seed ^ (threadIdx.x * 2654435761u), b = seed + blockIdx.x * 40503u + 1u;
-    unsigned long long c0 = a, c1 = b, c2 = a + 1, c3 = b + 2, c4 = a + 3, c5 = b + 4, c6 = a + 5, c7 = b + 6;
-#pragma unroll 1
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            asm volatile(
-                "mad.wide.u32 %0,%8,%9,%0; mad.wide.u32 %1,%8,%9,%1; mad.wide.u32 %2,%8,%9,%2; mad.wide.u32 %3,%8,%9,%3;"
-                "mad.wide.u32 %4,%8,%9,%4; mad.wide.u32 %5,%8,%9,%5; mad.wide.u32 %6,%8,%9,%6; mad.wide.u32 %7,%8,%9,%7;"
-                : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7)
-                : "r"(a), "r"(b));
-        }
-    }
-    unsigned long long s = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
-    if (s == 0x123456789ULL) sink[0] = s;  // keeps the chains alive
 }
 
 // ---------------------------------------------------------------------------
@@ -331,8 +292,7 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
         LAUNCH(ctx, k_gen_table, grid_for(total), 0, ctx->stream, ctx->comb, COMB_WB, total);
         total = (size_t)CT_NW * CT_SZ;
         LAUNCH(ctx, k_gen_table, grid_for(total), 0, ctx->stream, ctx->ct_tab, 4, total);
-        cudaFuncSetAttribute(k_base_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(CT_NW * CT_SZ * sizeof(apt)));
+        s256_ct_kernels_init();
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
             fprintf(stderr, "s256_init: table generation failed: %s\n", cudaGetErrorString(e));
@@ -407,10 +367,8 @@ static int chunk_dsm(s256_ctx *ctx, const uint8_t *u1, const uint8_t *u2, const 
 }
 static int chunk_base_mult(s256_ctx *ctx, const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status,
                            cudaStream_t s) {
-    unsigned grid = grid_for(n);
-    unsigned maxg = 148u * S256_BM_MINB;
-    if (grid > maxg) grid = maxg;
-    LAUNCH(ctx, k_base_mult_ct, grid, CT_NW * CT_SZ * sizeof(apt), s, k32, n, ctx->ct_tab, ctx->res);
+    s256_launch_base_mult_ct(k32, n, ctx->ct_tab, ctx->res, s);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
     LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, ctx->res, (const uint8_t *)nullptr,
            (const uint8_t *)nullptr, ctx->cstat, 0, out65, status, (const uint8_t *)nullptr);
     return S256_SUCCESS;
@@ -661,29 +619,6 @@ extern "C" int s256_debug_field_op(s256_ctx *ctx, int op, const uint8_t *a32, co
     return check_launch(ctx);
 }
 
-extern "C" int s256_microbench_imad(s256_ctx *ctx, int iters, double *mac32_per_s, double *ms_out) {
-    ENTER(ctx);
-    if (iters < 1) return S256_ERR_ARG;
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    const int blocks = 148 * 8, threads = 256;
-    k_imad_peak<<<blocks, threads, 0, ctx->stream>>>(12345u, 16, ctx->sink);  // warm-up
-    CK(cudaEventRecord(e0, ctx->stream));
-    k_imad_peak<<<blocks, threads, 0, ctx->stream>>>(12345u, iters, ctx->sink);
-    ctx->launches.fetch_add(2);
-    CK(cudaEventRecord(e1, ctx->stream));
-    CK(cudaEventSynchronize(e1));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    double macs = (double)blocks * threads * (double)iters * 64.0;
-    if (mac32_per_s) *mac32_per_s = macs / (ms * 1e-3);
-    if (ms_out) *ms_out = ms;
-    return check_launch(ctx);
-}
-
 // Per-kernel timing of k_dsm with CUDA events on the launching stream: enable, run
 // steps, then read (synchronises on the recorded events and clears them).
 extern "C" int s256_profile_enable(s256_ctx *ctx, int enable) {
@@ -713,6 +648,40 @@ extern "C" int s256_profile_read(s256_ctx *ctx, double *dsm_ms_total, uint64_t *
     if (dsm_ms_total) *dsm_ms_total = total;
     if (dsm_launches) *dsm_launches = cnt;
     return S256_SUCCESS;
+}
+
+// Integer-pipe probes (microbench.cuh): operations per second for one variant.
+template <int V>
+static void launch_probe(int blocks, int iters, cudaStream_t s, unsigned long long *sink) {
+    k_int_probe<V><<<blocks, 256, 0, s>>>(12345u, iters, sink);
+}
+extern "C" int s256_microbench_variant(s256_ctx *ctx, int variant, int iters, double *ops_per_s, double *ms_out) {
+    ENTER(ctx);
+    if (iters < 1 || variant < 0 || variant >= MB_NVARIANTS) return S256_ERR_ARG;
+    typedef void (*fn_t)(int, int, cudaStream_t, unsigned long long *);
+    static const fn_t fns[MB_NVARIANTS] = {launch_probe<0>, launch_probe<1>, launch_probe<2>, launch_probe<3>,
+                                           launch_probe<4>, launch_probe<5>, launch_probe<6>};
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int blocks = 148 * 8;
+    fns[variant](blocks, 16, ctx->stream, ctx->sink);
+    CK(cudaEventRecord(e0, ctx->stream));
+    fns[variant](blocks, iters, ctx->stream, ctx->sink);
+    CK(cudaEventRecord(e1, ctx->stream));
+    ctx->launches.fetch_add(2);
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (ops_per_s) *ops_per_s = (double)blocks * 256 * (double)iters * mb_ops_per_trip(variant) / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return check_launch(ctx);
+}
+
+extern "C" int s256_microbench_imad(s256_ctx *ctx, int iters, double *mac32_per_s, double *ms) {
+    return s256_microbench_variant(ctx, MB_MAD_WIDE, iters, mac32_per_s, ms);
 }
 
 // MAC32 per item actually executed (DESIGN.md "work per item"): F_p modmul = 73,

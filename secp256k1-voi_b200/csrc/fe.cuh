@@ -292,11 +292,25 @@ S256_D void fe_reduce_wide(fe &out, uint32_t r[16]) {
     fe_fold_top(out, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], t8, t9);
 }
 
-S256_D void fe_mul(fe &r, const fe &a, const fe &b) {
+S256_D void fe_mul_inline(fe &r, const fe &a, const fe &b) {
     uint32_t w[16];
     fe_mul_wide(w, a.v, b.v);
     fe_reduce_wide(r, w);
 }
+#ifndef S256_MUL_INLINE
+// Out of line on purpose: one ~2.4 KB body shared by every call site stays
+// resident in the instruction caches (the fully inlined ladder is ~140 KB of
+// straight-line code and stalls on instruction fetch, see profiles/), and the
+// arguments travel in registers (no stack traffic).
+static __device__ __noinline__ fe fe_mul_call(fe a, fe b) {
+    fe r;
+    fe_mul_inline(r, a, b);
+    return r;
+}
+S256_D void fe_mul(fe &r, const fe &a, const fe &b) { r = fe_mul_call(a, b); }
+#else
+S256_D void fe_mul(fe &r, const fe &a, const fe &b) { fe_mul_inline(r, a, b); }
+#endif
 S256_D void fe_sqr(fe &r, const fe &a) { fe_mul(r, a, a); }
 
 // r = a * k for a small constant k (< 2^16): 8 IMAD.WIDE + one fold

@@ -1,0 +1,42 @@
+// kern_ct.cu -- the constant-time kernels (secret scalars).
+#define S256_MUL_INLINE 1
+#include "kernels.cuh"
+#include "launchers.h"
+
+using namespace s256;
+#define S256_TPB 128
+
+#ifndef S256_BM_MINB
+#define S256_BM_MINB 3
+#endif
+__global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
+    k_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_g, pt *res) {
+    extern __shared__ uint4 smem_raw[];
+    apt *tab = reinterpret_cast<apt *>(smem_raw);
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(tab_g);
+        const int nvec = CT_NW * CT_SZ * (int)sizeof(apt) / 16;
+        for (int v = threadIdx.x; v < nvec; v += blockDim.x) smem_raw[v] = src[v];
+    }
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        sc k;
+        sc_from_be32(k, k32 + 32 * i);
+        pt acc;
+        item_base_mult_ct(acc, k, tab);
+        res[i] = acc;
+    }
+}
+
+
+void s256_ct_kernels_init() {
+    cudaFuncSetAttribute(k_base_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(CT_NW * CT_SZ * sizeof(apt)));
+}
+void s256_launch_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_g, pt *res, cudaStream_t s) {
+    unsigned grid = (unsigned)((n + S256_TPB - 1) / S256_TPB);
+    unsigned maxg = 148u * S256_BM_MINB;
+    if (grid > maxg) grid = maxg;
+    if (grid == 0) return;
+    k_base_mult_ct<<<grid, S256_TPB, CT_NW * CT_SZ * sizeof(apt), s>>>(k32, n, tab_g, res);
+}

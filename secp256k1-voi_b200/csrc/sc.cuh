@@ -204,7 +204,7 @@ S256_HD void sc_mul_wide(uint32_t w[16], const uint32_t a[8], const uint32_t b[8
     }
 }
 #if defined(__CUDACC__)
-__host__ __device__ S256_NOINLINE
+static __host__ __device__ S256_NOINLINE
 #else
 inline
 #endif
@@ -218,7 +218,7 @@ S256_HD void sc_sqr(sc &r, const sc &a) { sc_mul(r, a, a); }
 // scalar_invert.go:11-303 -- x^(n-2), Invert(0) = 0.  The top 127 exponent
 // bits are ones (run-of-ones chain), the low 129 go through a 4-bit window.
 #if defined(__CUDACC__)
-__host__ __device__ S256_NOINLINE
+static __host__ __device__ S256_NOINLINE
 #else
 inline
 #endif
