@@ -89,6 +89,10 @@ int s256_ecdh(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, 
 int s256_ecdh_dev(s256_ctx *ctx, const uint8_t *d_k32, const uint8_t *d_pt65, size_t n, uint8_t *d_x32,
                   uint8_t *d_status, void *stream);
 
+/* --- NewPointFromBytes on compressed encodings (point_s11n.go:234,140: 02/03||X,
+ *     canonical x, square root, parity select): 33 B -> 65 B + status. */
+int s256_point_decompress(s256_ctx *ctx, const uint8_t *pt33, size_t n, uint8_t *out65, uint8_t *status);
+
 /* --- Point.DoubleScalarMultBasepointVartime (point_mul_glv.go:307):
  *     u1*G + u2*P, variable time. */
 int s256_double_scalar_mult_basepoint_vartime(s256_ctx *ctx, const uint8_t *u1_32, const uint8_t *u2_32,

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "s256_init", "s256_free", "s256_strerror", "s256_last_cuda_error", "s256_device",
     "s256_scalar_base_mult", "s256_scalar_base_mult_dev",
     "s256_scalar_mult", "s256_scalar_mult_dev",
-    "s256_ecdh", "s256_ecdh_dev",
+    "s256_ecdh", "s256_ecdh_dev", "s256_point_decompress",
     "s256_double_scalar_mult_basepoint_vartime", "s256_double_scalar_mult_basepoint_vartime_dev",
     "s256_ecdsa_verify", "s256_ecdsa_verify_dev",
     "s256_ecdsa_recover", "s256_ecdsa_recover_dev",
@@ -203,6 +203,16 @@ class Engine:
         out = np.zeros((n, 32), np.uint8)
         st = np.zeros(n, np.uint8)
         self._check(self._lib.s256_ecdh(self._ctx, self._hp(k), self._hp(p), C.c_size_t(n), self._hp(out), self._hp(st)), "ecdh")
+        return out, st
+
+    # -- NewPointFromBytes, compressed form (point_s11n.go:140) ---------------
+    def point_decompress(self, pt33):
+        p = _host(pt33, 33)
+        n = len(p)
+        out = np.zeros((n, 65), np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_point_decompress(self._ctx, self._hp(p), C.c_size_t(n), self._hp(out), self._hp(st)),
+                    "point_decompress")
         return out, st
 
     # -- Point.DoubleScalarMultBasepointVartime (point_mul_glv.go:307) --------

@@ -17,6 +17,8 @@
 #include "../../include/secp256k1_b200.h"
 #include "kernels.cuh"
 #include "microbench.cuh"
+#include "msm.cuh"
+#include <cub/device/device_scan.cuh>
 #include "launchers.h"
 
 using namespace s256;
@@ -42,6 +44,32 @@ __global__ void __launch_bounds__(S256_TPB) k_decode_uncompressed(const uint8_t 
     apt a;
     pvalid[i] = item_decode_uncompressed(a, pt65 + 65 * i);
     aff[i] = a;
+}
+
+__global__ void __launch_bounds__(S256_TPB) k_decode_compressed(const uint8_t *pt33, size_t n, apt *aff,
+                                                                uint8_t *pvalid) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    apt a;
+    pvalid[i] = item_decode_compressed(a, pt33 + 33 * i);
+    aff[i] = a;
+}
+// affine (validated) -> 65-byte encoding; invalid -> zeros
+__global__ void __launch_bounds__(S256_TPB) k_encode_affine(const apt *aff, const uint8_t *pvalid, size_t n,
+                                                            uint8_t *out65, uint8_t *status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    apt a = aff[i];
+    uint32_t ok = pvalid[i] != 0;
+    uint8_t *o = out65 + 65 * i;
+    if (ok) {
+        o[0] = 0x04;
+        fe_to_be32(o + 1, a.x);
+        fe_to_be32(o + 33, a.y);
+    } else {
+        for (int b = 0; b < 65; b++) o[b] = 0;
+    }
+    status[i] = ok ? ST_OK : ST_INVALID;
 }
 
 // BIP-340 lift_x: x-only key, even y (secec/bitcoin/schnorr.go:257-275)
@@ -124,6 +152,121 @@ __global__ void __launch_bounds__(S256_TPB) k_finish_affine(size_t n, const pt *
     group_finish<K>(t, stride, n, res, pvalid, sfl, comb_status, mode, out, status, sig64);
 }
 
+// ---- Pippenger MSM (msm.cuh) -------------------------------------------------
+template <bool SCATTER>
+__global__ void __launch_bounds__(S256_TPB) k_msm_digits(const uint8_t *k32, size_t n, msm_plan plan, uint32_t *counts,
+                                                         uint32_t *cursor, uint32_t *entries) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sc k;
+    sc_from_be32(k, k32 + 32 * i);
+    int32_t d[MSM_MAX_WIN];
+    msm_digits(d, k, plan);
+    for (int w = 0; w < plan.nwin; w++) {
+        int32_t dw = d[w];
+        if (dw == 0) continue;
+        uint32_t mag = (uint32_t)(dw < 0 ? -dw : dw);
+        uint32_t b = (uint32_t)w * (uint32_t)plan.nb + (mag - 1u);
+        if (!SCATTER) {
+            atomicAdd(&counts[b], 1u);
+        } else {
+            uint32_t pos = atomicAdd(&cursor[b], 1u);
+            entries[pos] = ((uint32_t)i << 1) | (uint32_t)(dw < 0);
+        }
+    }
+}
+__global__ void __launch_bounds__(S256_TPB) k_msm_buckets(uint32_t total, const uint32_t *offsets,
+                                                          const uint32_t *entries, const apt *aff, pt *buckets) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total) return;
+    pt s;
+    msm_bucket_sum(s, entries, offsets[b], offsets[b + 1], aff);
+    buckets[b] = s;
+}
+#define S256_MSM_WT 256
+__global__ void __launch_bounds__(S256_MSM_WT) k_msm_windows(msm_plan plan, const pt *buckets, pt *win) {
+    __shared__ pt sh[S256_MSM_WT];
+    int w = blockIdx.x, t = threadIdx.x;
+    int per = (plan.nb + S256_MSM_WT - 1) / S256_MSM_WT;
+    int lo = t * per, hi = lo + per;
+    if (hi > plan.nb) hi = plan.nb;
+    pt s;
+    if (lo < hi)
+        msm_segment(s, buckets + (size_t)w * plan.nb, lo, hi);
+    else
+        pt_set_identity(s);
+    sh[t] = s;
+    __syncthreads();
+    for (int stride = S256_MSM_WT / 2; stride >= 1; stride >>= 1) {
+        if (t < stride) {
+            pt a = sh[t], b = sh[t + stride];
+            pt_add(a, a, b);
+            sh[t] = a;
+        }
+        __syncthreads();
+    }
+    if (t == 0) win[w] = sh[0];
+}
+// acc (device, projective) += Horner(win); first = overwrite
+__global__ void k_msm_final(msm_plan plan, const pt *win, pt *acc, int first) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    pt r;
+    msm_horner(r, win, plan);
+    if (!first) {
+        pt a = *acc;
+        pt_add(r, r, a);
+    }
+    *acc = r;
+}
+// out[t] = sum of in[t], in[t + nout], ...   (tree levels of the constant-time MSM)
+__global__ void __launch_bounds__(S256_TPB) k_reduce_points(const pt *in, size_t n, pt *out, size_t nout) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nout) return;
+    pt acc;
+    pt_set_identity(acc);
+    for (size_t i = t; i < n; i += nout) {
+        pt q = in[i];
+        pt_add(acc, acc, q);
+    }
+    out[t] = acc;
+}
+__global__ void k_acc_point(const pt *in, pt *acc, int first) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    pt r = *in;
+    if (!first) {
+        pt a = *acc;
+        pt_add(r, r, a);
+    }
+    *acc = r;
+}
+__global__ void __launch_bounds__(S256_TPB) k_any_invalid(const uint8_t *pvalid, size_t n, uint32_t *flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && pvalid[i] == 0) atomicOr(flag, 1u);
+}
+// partial96 rows -> one projective sum; rows must be points on the curve (or the identity)
+__global__ void k_combine_partials(const uint8_t *partials96, size_t m, pt *out, uint32_t *flag) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    pt acc;
+    pt_set_identity(acc);
+    for (size_t j = 0; j < m; j++) {
+        pt q;
+        pt_from_be96(q, partials96 + 96 * j);
+        uint32_t ok = fe_limbs_are_canonical(q.x) & fe_limbs_are_canonical(q.y) & fe_limbs_are_canonical(q.z) &
+                      pt_on_curve(q);
+        if (!ok) {
+            atomicOr(flag, 1u);
+            continue;
+        }
+        pt_add(acc, acc, q);
+    }
+    *out = acc;
+}
+__global__ void k_export_partial(const pt *acc, uint8_t *out96) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    pt a = *acc;
+    pt_to_be96(out96, a);
+}
+
 __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a32, const uint8_t *b32, size_t n,
                                                        uint8_t *out32) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,6 +324,13 @@ struct s256_ctx {
     uint8_t *in_a = nullptr, *in_b = nullptr, *in_c = nullptr, *out = nullptr, *st = nullptr;
     size_t in_b_bytes = 0;
     unsigned long long *sink = nullptr;
+    // MSM scratch (allocated on first use)
+    size_t msm_cap = 0;
+    uint32_t *msm_counts = nullptr, *msm_offsets = nullptr, *msm_cursor = nullptr, *msm_entries = nullptr;
+    uint32_t *msm_flag = nullptr;
+    pt *msm_buckets = nullptr, *msm_win = nullptr, *msm_acc = nullptr, *msm_tmp = nullptr;
+    void *msm_cub = nullptr;
+    size_t msm_cub_bytes = 0;
     // optional per-kernel timing of the dominant kernel (bench.py roofline)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dsm_events;
@@ -237,7 +387,8 @@ extern "C" void s256_free(s256_ctx *ctx) {
         dev_guard g(ctx->device);
         void *ptrs[] = {ctx->comb, ctx->ct_tab, ctx->aff, ctx->u1,   ctx->dig1, ctx->dig2, ctx->sfl, ctx->pvalid,
                         ctx->cstat, ctx->tbl,   ctx->res, ctx->in_a, ctx->in_b, ctx->in_c, ctx->out, ctx->st,
-                        ctx->sink};
+                        ctx->sink, ctx->msm_counts, ctx->msm_offsets, ctx->msm_cursor, ctx->msm_entries, ctx->msm_flag,
+                        ctx->msm_buckets, ctx->msm_win, ctx->msm_acc, ctx->msm_tmp, ctx->msm_cub};
         for (void *p : ptrs)
             if (p) cudaFree(p);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -371,6 +522,17 @@ static int chunk_base_mult(s256_ctx *ctx, const uint8_t *k32, size_t n, uint8_t 
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, ctx->res, (const uint8_t *)nullptr,
            (const uint8_t *)nullptr, ctx->cstat, 0, out65, status, (const uint8_t *)nullptr);
+    return S256_SUCCESS;
+}
+
+// Point.ScalarMult / PrivateKey.ECDH: decode (public) -> ct ladder -> batched affine
+static int chunk_scalar_mult(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int mode, uint8_t *out,
+                             uint8_t *status, cudaStream_t s) {
+    LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pt65, n, ctx->aff, ctx->pvalid);
+    s256_launch_scalar_mult_ct(n, ctx->aff, k32, ctx->tbl, ctx->res, s);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, ctx->res, ctx->pvalid,
+           (const uint8_t *)nullptr, ctx->cstat, mode, out, status, (const uint8_t *)nullptr);
     return S256_SUCCESS;
 }
 
@@ -550,28 +712,241 @@ extern "C" int s256_scalar_base_mult(s256_ctx *ctx, const uint8_t *k32, size_t n
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
 
-// --- not yet built this round --------------------------------------------------
-extern "C" int s256_scalar_mult(s256_ctx *, const uint8_t *, const uint8_t *, size_t, uint8_t *, uint8_t *) {
-    return S256_ERR_UNIMPLEMENTED;
+static int scalar_mult_common_dev(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int mode,
+                                  uint8_t *out, uint8_t *status, void *stream) {
+    ENTER(ctx);
+    if (n && (!k32 || !pt65 || !out || !status)) return S256_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    size_t w = mode == 1 ? 32 : 65;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        return chunk_scalar_mult(ctx, k32 + 32 * off, pt65 + 65 * off, c, mode, out + w * off, status + off, s);
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
-extern "C" int s256_scalar_mult_dev(s256_ctx *, const uint8_t *, const uint8_t *, size_t, uint8_t *, uint8_t *,
-                                    void *) {
-    return S256_ERR_UNIMPLEMENTED;
+static int scalar_mult_common_host(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int mode,
+                                   uint8_t *out, uint8_t *status) {
+    ENTER(ctx);
+    if (n && (!k32 || !pt65 || !out || !status)) return S256_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    size_t w = mode == 1 ? 32 : 65;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        CK(cudaMemcpyAsync(ctx->in_a, pt65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->in_b, k32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        int r = chunk_scalar_mult(ctx, ctx->in_b, ctx->in_a, c, mode, ctx->out, ctx->st, s);
+        if (r != S256_SUCCESS) return r;
+        CK(cudaMemcpyAsync(out + w * off, ctx->out, w * c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return S256_SUCCESS;
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
-extern "C" int s256_ecdh(s256_ctx *, const uint8_t *, const uint8_t *, size_t, uint8_t *, uint8_t *) {
-    return S256_ERR_UNIMPLEMENTED;
+extern "C" int s256_scalar_mult(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, uint8_t *out65,
+                                uint8_t *status) {
+    return scalar_mult_common_host(ctx, k32, pt65, n, 0, out65, status);
 }
-extern "C" int s256_ecdh_dev(s256_ctx *, const uint8_t *, const uint8_t *, size_t, uint8_t *, uint8_t *, void *) {
-    return S256_ERR_UNIMPLEMENTED;
+extern "C" int s256_scalar_mult_dev(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, uint8_t *out65,
+                                    uint8_t *status, void *stream) {
+    return scalar_mult_common_dev(ctx, k32, pt65, n, 0, out65, status, stream);
 }
-extern "C" int s256_msm(s256_ctx *, const uint8_t *, const uint8_t *, size_t, int, uint8_t *, uint8_t *) {
-    return S256_ERR_UNIMPLEMENTED;
+extern "C" int s256_ecdh(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, uint8_t *x32,
+                         uint8_t *status) {
+    return scalar_mult_common_host(ctx, k32, pt65, n, 1, x32, status);
 }
-extern "C" int s256_msm_partial(s256_ctx *, const uint8_t *, const uint8_t *, size_t, int, uint8_t *, uint8_t *) {
-    return S256_ERR_UNIMPLEMENTED;
+extern "C" int s256_ecdh_dev(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, uint8_t *x32,
+                             uint8_t *status, void *stream) {
+    return scalar_mult_common_dev(ctx, k32, pt65, n, 1, x32, status, stream);
 }
-extern "C" int s256_msm_combine(s256_ctx *, const uint8_t *, size_t, uint8_t *, uint8_t *) {
-    return S256_ERR_UNIMPLEMENTED;
+// NewPointFromBytes on compressed encodings (point_s11n.go:140): 33 B -> 65 B + status
+extern "C" int s256_point_decompress(s256_ctx *ctx, const uint8_t *pt33, size_t n, uint8_t *out65, uint8_t *status) {
+    ENTER(ctx);
+    if (n && (!pt33 || !out65 || !status)) return S256_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        CK(cudaMemcpyAsync(ctx->in_a, pt33 + 33 * off, 33 * c, cudaMemcpyHostToDevice, s));
+        LAUNCH(ctx, k_decode_compressed, grid_for(c), 0, s, ctx->in_a, c, ctx->aff, ctx->pvalid);
+        LAUNCH(ctx, k_encode_affine, grid_for(c), 0, s, ctx->aff, ctx->pvalid, c, ctx->out, ctx->st);
+        CK(cudaMemcpyAsync(out65 + 65 * off, ctx->out, 65 * c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return S256_SUCCESS;
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+
+// ---------------------------------------------------------------------------
+// MSM
+// ---------------------------------------------------------------------------
+static int msm_ensure(s256_ctx *ctx) {
+    if (ctx->msm_cap) return S256_SUCCESS;
+    size_t cap = ctx->cap;
+    msm_plan pl = msm_make_plan(cap);
+    // the largest bucket space over all plans up to cap: nwin * nb grows with c
+    size_t total = (size_t)pl.nwin * pl.nb;
+    for (int c = 4; c <= pl.c; c++) {
+        size_t t = (size_t)(256 / c + 1) << (c - 1);
+        if (t > total) total = t;
+    }
+    CK(cudaMalloc(&ctx->msm_counts, (total + 1) * 4));
+    CK(cudaMalloc(&ctx->msm_offsets, (total + 1) * 4));
+    CK(cudaMalloc(&ctx->msm_cursor, (total + 1) * 4));
+    CK(cudaMalloc(&ctx->msm_entries, (size_t)MSM_MAX_WIN * 4 * (cap < 65536 ? 65536 : cap) / (cap < 65536 ? 1 : 3)));
+    CK(cudaMalloc(&ctx->msm_buckets, total * sizeof(pt)));
+    CK(cudaMalloc(&ctx->msm_win, MSM_MAX_WIN * sizeof(pt)));
+    CK(cudaMalloc(&ctx->msm_acc, sizeof(pt)));
+    CK(cudaMalloc(&ctx->msm_tmp, 4096 * sizeof(pt)));
+    CK(cudaMalloc(&ctx->msm_flag, 4));
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, ctx->msm_counts, ctx->msm_offsets, (int)(total + 1));
+    ctx->msm_cub_bytes = bytes;
+    CK(cudaMalloc(&ctx->msm_cub, bytes));
+    ctx->msm_cap = cap;
+    return S256_SUCCESS;
+}
+// entries needed by a plan: nwin * n uint32
+static size_t msm_entries_capacity(const s256_ctx *ctx) {
+    size_t cap = ctx->cap;
+    return (size_t)MSM_MAX_WIN * (cap < 65536 ? 65536 : cap) / (cap < 65536 ? 1 : 3);
+}
+
+// one chunk (device pointers): msm_acc (+)= sum k_i P_i
+static int chunk_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, int first,
+                     cudaStream_t s) {
+    LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pt65, n, ctx->aff, ctx->pvalid);
+    LAUNCH(ctx, k_any_invalid, grid_for(n), 0, s, ctx->pvalid, n, ctx->msm_flag);
+    if (!vartime || n < 32) {
+        // constant-time flavour (and tiny inputs): ct ladder per item, then a sum tree
+        s256_launch_scalar_mult_ct(n, ctx->aff, k32, ctx->tbl, ctx->res, s);
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        size_t m = n < 2048 ? (n < 32 ? 1 : 32) : 2048;
+        LAUNCH(ctx, k_reduce_points, grid_for(m), 0, s, ctx->res, n, ctx->msm_tmp, m);
+        if (m > 32) {
+            LAUNCH(ctx, k_reduce_points, grid_for(32), 0, s, ctx->msm_tmp, m, ctx->msm_tmp + 2048, (size_t)32);
+            LAUNCH(ctx, k_reduce_points, 1, 0, s, ctx->msm_tmp + 2048, (size_t)32, ctx->msm_tmp + 2048 + 32, (size_t)1);
+            k_acc_point<<<1, 1, 0, s>>>(ctx->msm_tmp + 2048 + 32, ctx->msm_acc, first);
+        } else if (m > 1) {
+            LAUNCH(ctx, k_reduce_points, 1, 0, s, ctx->msm_tmp, m, ctx->msm_tmp + 2048, (size_t)1);
+            k_acc_point<<<1, 1, 0, s>>>(ctx->msm_tmp + 2048, ctx->msm_acc, first);
+        } else {
+            k_acc_point<<<1, 1, 0, s>>>(ctx->msm_tmp, ctx->msm_acc, first);
+        }
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        return S256_SUCCESS;
+    }
+    msm_plan pl = msm_make_plan(n);
+    if ((size_t)pl.nwin * n > msm_entries_capacity(ctx)) {
+        // fall back to a smaller window count is impossible (nwin grows as c shrinks): shrink c's effect by
+        // raising c until the entries fit
+        while (pl.c < MSM_MAX_C && (size_t)(256 / pl.c + 1) * n > msm_entries_capacity(ctx)) {
+            pl.c++;
+            pl.nwin = 256 / pl.c + 1;
+            pl.nb = 1 << (pl.c - 1);
+        }
+    }
+    uint32_t total = (uint32_t)pl.nwin * (uint32_t)pl.nb;
+    CK(cudaMemsetAsync(ctx->msm_counts, 0, ((size_t)total + 1) * 4, s));
+    LAUNCH(ctx, k_msm_digits<false>, grid_for(n), 0, s, k32, n, pl, ctx->msm_counts, ctx->msm_cursor, ctx->msm_entries);
+    size_t bytes = ctx->msm_cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(ctx->msm_cub, bytes, ctx->msm_counts, ctx->msm_offsets, (int)(total + 1), s));
+    CK(cudaMemcpyAsync(ctx->msm_cursor, ctx->msm_offsets, (size_t)total * 4, cudaMemcpyDeviceToDevice, s));
+    LAUNCH(ctx, k_msm_digits<true>, grid_for(n), 0, s, k32, n, pl, ctx->msm_counts, ctx->msm_cursor, ctx->msm_entries);
+    LAUNCH(ctx, k_msm_buckets, grid_for(total), 0, s, total, ctx->msm_offsets, ctx->msm_entries, ctx->aff,
+           ctx->msm_buckets);
+    k_msm_windows<<<pl.nwin, S256_MSM_WT, 0, s>>>(pl, ctx->msm_buckets, ctx->msm_win);
+    k_msm_final<<<1, 1, 0, s>>>(pl, ctx->msm_win, ctx->msm_acc, first);
+    ctx->launches.fetch_add(3, std::memory_order_relaxed);
+    return S256_SUCCESS;
+}
+
+// host pointers -> msm_acc holds the projective sum; *invalid = 1 if a point failed to decode
+static int msm_run(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, uint32_t *invalid) {
+    int rc = msm_ensure(ctx);
+    if (rc != S256_SUCCESS) return rc;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->msm_flag, 0, 4, s));
+    if (n == 0) {
+        pt id;
+        pt_set_identity(id);
+        CK(cudaMemcpyAsync(ctx->msm_acc, &id, sizeof(pt), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    int first = 1;
+    rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        CK(cudaMemcpyAsync(ctx->in_a, pt65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->in_b, k32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        int r = chunk_msm(ctx, ctx->in_b, ctx->in_a, c, vartime, first, s);
+        first = 0;
+        return r;
+    });
+    if (rc != S256_SUCCESS) return rc;
+    CK(cudaMemcpyAsync(invalid, ctx->msm_flag, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return check_launch(ctx);
+}
+// msm_acc -> 65-byte encoding + status
+static int msm_finish(s256_ctx *ctx, uint8_t *out65, uint8_t *status) {
+    cudaStream_t s = ctx->stream;
+    LAUNCH(ctx, k_finish_affine<INV_K>, 1, 0, s, (size_t)1, ctx->msm_acc, (const uint8_t *)nullptr,
+           (const uint8_t *)nullptr, ctx->cstat, 0, ctx->out, ctx->st, (const uint8_t *)nullptr);
+    CK(cudaMemcpyAsync(out65, ctx->out, 65, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(status, ctx->st, 1, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return check_launch(ctx);
+}
+extern "C" int s256_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, uint8_t *out65,
+                        uint8_t *status) {
+    ENTER(ctx);
+    if (!out65 || !status || (n && (!k32 || !pt65))) return S256_ERR_ARG;
+    uint32_t invalid = 0;
+    int rc = msm_run(ctx, k32, pt65, n, vartime, &invalid);
+    if (rc != S256_SUCCESS) return rc;
+    if (invalid) {
+        memset(out65, 0, 65);
+        *status = S256_ST_INVALID;
+        return S256_SUCCESS;
+    }
+    return msm_finish(ctx, out65, status);
+}
+extern "C" int s256_msm_partial(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime,
+                                uint8_t *partial96, uint8_t *status) {
+    ENTER(ctx);
+    if (!partial96 || !status || (n && (!k32 || !pt65))) return S256_ERR_ARG;
+    uint32_t invalid = 0;
+    int rc = msm_run(ctx, k32, pt65, n, vartime, &invalid);
+    if (rc != S256_SUCCESS) return rc;
+    if (invalid) {
+        memset(partial96, 0, 96);
+        *status = S256_ST_INVALID;
+        return S256_SUCCESS;
+    }
+    cudaStream_t s = ctx->stream;
+    k_export_partial<<<1, 1, 0, s>>>(ctx->msm_acc, ctx->out);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    CK(cudaMemcpyAsync(partial96, ctx->out, 96, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *status = S256_ST_OK;
+    return check_launch(ctx);
+}
+extern "C" int s256_msm_combine(s256_ctx *ctx, const uint8_t *partials96, size_t m, uint8_t *out65, uint8_t *status) {
+    ENTER(ctx);
+    if (!out65 || !status || (m && !partials96)) return S256_ERR_ARG;
+    if (96 * m > 65 * ctx->cap) return S256_ERR_ARG;
+    int rc = msm_ensure(ctx);
+    if (rc != S256_SUCCESS) return rc;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->msm_flag, 0, 4, s));
+    if (m) CK(cudaMemcpyAsync(ctx->in_a, partials96, 96 * m, cudaMemcpyHostToDevice, s));
+    k_combine_partials<<<1, 1, 0, s>>>(ctx->in_a, m, ctx->msm_acc, ctx->msm_flag);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    uint32_t invalid = 0;
+    CK(cudaMemcpyAsync(&invalid, ctx->msm_flag, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (invalid) {
+        memset(out65, 0, 65);
+        *status = S256_ST_INVALID;
+        return S256_SUCCESS;
+    }
+    return msm_finish(ctx, out65, status);
 }
 
 // ---------------------------------------------------------------------------
@@ -702,5 +1077,10 @@ extern "C" double s256_mac32_per_item(const char *name) {
     if (s == "schnorr_verify") return 276 * M + (ZN + split) + dsm + affine;
     if (s == "double_scalar_mult_basepoint_vartime") return 3 * M + split + dsm + affine;
     if (s == "scalar_base_mult") return CT_NW * mix + affine;
+    if (s == "scalar_mult" || s == "ecdh") {
+        const double tab = (CTM_TS / 2) * dbl + (CTM_TS / 2 - 1) * mix;
+        const double lad = (CTM_ND - 1) * CTM_W * dbl + 2 * CTM_ND * (add + M);
+        return 3 * M + split + tab + lad + affine;
+    }
     return 0.0;
 }

@@ -37,6 +37,14 @@ constexpr int COMB_SZ = 1 << COMB_WB;
 // constant-time fixed-base table: 64 windows of 4 bits, entries 1..15
 constexpr int CT_NW = 64;
 constexpr int CT_SZ = 16;
+// constant-time variable-base ladder (ScalarMult / ECDH): signed window
+#ifndef S256_CTW
+#define S256_CTW 4
+#endif
+constexpr int CTM_W = S256_CTW;
+constexpr int CTM_ND = glv_recode<CTM_W>::ND;
+constexpr int CTM_TS = 1 << (CTM_W - 1);
+static_assert(CTM_TS <= DSM_TS, "the ct ladder shares the per-item table scratch of the vartime ladder");
 
 enum : uint8_t { ST_INVALID = 0, ST_OK = 1, ST_IDENTITY = 2 };
 enum : uint32_t { FLAG_REJECT_MALLEABLE = 1u };
@@ -502,6 +510,99 @@ S256_HD void item_base_mult_ct(pt &acc, const sc &k, const apt *tab /* [64][16],
         pt_add_mixed(sum, acc, sel.x, sel.y);
         pt_cmov(acc, sum, acc, zero);
     }
+}
+
+// ---------------------------------------------------------------------------
+// constant-time variable-base multiplication k*P (point_mul_glv.go:257-303),
+// the kernel behind Point.ScalarMult and PrivateKey.ECDH.  Same GLV split and
+// sign normalisation as the reference, with ConditionalNegate / lookups done
+// by masks: every step scans ALL table entries (the per-item table lives in
+// global memory at an address that depends only on the item index), the add is
+// always executed (digit 0 selects the identity, which the complete formula
+// absorbs), and nothing branches on k.  The point P is public.
+// ---------------------------------------------------------------------------
+S256_HD void item_scalar_mult_ct(size_t i, const apt *aff, const uint8_t *k32, pt *tbl, pt *res) {
+    pt *T = tbl + i * (size_t)DSM_TS;  // stride shared with the vartime ladder's scratch
+    {
+        apt P = aff[i];
+        pt cur;
+        pt_from_affine(cur, P);
+        T[0] = cur;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int k = 2; k <= CTM_TS; k += 2) {
+            pt h = T[k / 2 - 1];
+            pt_double(cur, h);
+            T[k - 1] = cur;
+            if (k < CTM_TS) {
+                pt_add_mixed(cur, cur, P.x, P.y);
+                T[k] = cur;
+            }
+        }
+    }
+    sc k;
+    sc_from_be32(k, k32 + 32 * i);
+    uint32_t m1[4], m2[4], neg1, neg2;
+    sc_split_glv_abs(m1, neg1, m2, neg2, k);
+    int8_t d1[CTM_ND], d2[CTM_ND];
+    glv_recode<CTM_W>::run(d1, m1);
+    glv_recode<CTM_W>::run(d2, m2);
+    pt acc;
+    pt_set_identity(acc);
+    const fe beta = fe_beta();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int s = CTM_ND - 1; s >= 0; s--) {
+        if (s != CTM_ND - 1) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int q = 0; q < CTM_W; q++) pt_double(acc, acc);
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int h = 0; h < 2; h++) {
+            int32_t d = h ? (int32_t)d2[s] : (int32_t)d1[s];
+            uint32_t sign = (uint32_t)d >> 31;                       // 1 iff d < 0
+            uint32_t mag = (uint32_t)((d ^ -(int32_t)sign) + (int32_t)sign);  // |d|, branch-free
+            uint32_t neg = sign ^ (h ? neg2 : neg1);
+            pt q;
+            q.x = fe_zero();
+            q.y = fe_zero();
+            q.z = fe_zero();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
+            for (uint32_t j = 1; j <= (uint32_t)CTM_TS; j++) {
+                uint32_t m = 0u - (uint32_t)(j == mag);
+                pt e = T[j - 1];
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    q.x.v[w] |= e.x.v[w] & m;
+                    q.y.v[w] |= e.y.v[w] & m;
+                    q.z.v[w] |= e.z.v[w] & m;
+                }
+            }
+            q.y.v[0] |= (uint32_t)(mag == 0);  // digit 0 -> (0 : 1 : 0)
+            fe bx;
+            fe_mul(bx, q.x, beta);
+            fe_cmov(q.x, q.x, bx, (uint32_t)h);
+            fe_cneg(q.y, q.y, neg);
+            pt_add(acc, acc, q);
+        }
+    }
+    res[i] = acc;
+}
+
+// point_s11n.go:140-172 -- SetCompressedBytes: 02/03 || X
+S256_HD uint8_t item_decode_compressed(apt &out, const uint8_t *b) {
+    fe x;
+    fe_from_be32(x, b + 1);
+    uint32_t ok = (uint32_t)((b[0] == 0x02) | (b[0] == 0x03)) & fe_limbs_are_canonical(x);
+    return item_decompress(out, x, ok, (uint32_t)(b[0] & 1u));
 }
 
 }  // namespace s256

@@ -1,0 +1,132 @@
+// msm.cuh -- Pippenger multi-scalar multiplication  sum_i k_i * P_i.
+//
+// Replaces the reference's Straus routine (point_mul_multi.go:25-117), whose
+// l x 15 x 104 B tables do not scale to l = 2^20 (1.6 GB) and which costs
+// ~1000 modmuls per point; only the resulting point is observable, so the
+// algorithm is free.  Variable time in the scalars (MultiScalarMultVartime,
+// :73); the constant-time flavour (:25) is served by the ct ladder per item
+// plus a sum (api.cu).
+//
+//   digits : k -> signed c-bit digits d_w in [-(2^(c-1)-1), 2^(c-1)], nwin windows
+//   sort   : counting sort of (window, |d|) keys: count (atomicAdd) -> exclusive
+//            scan -> scatter; the order inside a bucket is arbitrary, which is
+//            harmless because only the group element matters
+//   buckets: one thread per bucket, mixed complete additions (inputs are affine)
+//   windows: R_w = sum_j j * B_{w,j} by segmented running sums, one CTA per window
+//   final  : Horner over the windows, c doublings between additions
+#pragma once
+#include "fe.cuh"
+#include "point.cuh"
+#include "sc.cuh"
+
+namespace s256 {
+
+constexpr int MSM_MAX_C = 16;
+constexpr int MSM_MAX_WIN = 65;  // c = 4 -> 64 windows + carry
+
+struct msm_plan {
+    int c;         // window bits
+    int nwin;      // windows (the last one only ever holds the recoding carry when c divides 256)
+    int nb;        // buckets per window = 2^(c-1)
+};
+
+S256_HD msm_plan msm_make_plan(size_t n) {
+    int lg = 0;
+    while (((size_t)1 << (lg + 1)) <= n) lg++;
+    int c = lg - 4;
+    if (c < 4) c = 4;
+    if (c > MSM_MAX_C) c = MSM_MAX_C;
+    msm_plan p;
+    p.c = c;
+    p.nwin = 256 / c + 1;
+    p.nb = 1 << (c - 1);
+    return p;
+}
+
+// signed digits of a reduced scalar; d[w] in [-(2^(c-1)-1), 2^(c-1)]
+S256_HD void msm_digits(int32_t *d, const sc &k, const msm_plan &p) {
+    uint32_t carry = 0;
+    for (int w = 0; w < p.nwin; w++) {
+        int bit = w * p.c;
+        uint32_t v = 0;
+        if (bit < 256) {
+            int limb = bit >> 5, sh = bit & 31;
+            v = k.v[limb] >> sh;
+            if (sh + p.c > 32 && limb + 1 < 8) v |= k.v[limb + 1] << (32 - sh);
+            v &= (1u << p.c) - 1u;
+        }
+        v += carry;
+        carry = (v + (1u << (p.c - 1)) - 1u) >> p.c;
+        d[w] = (int32_t)v - (int32_t)(carry << p.c);
+    }
+}
+
+// bucket accumulation: entries hold (point index << 1) | negate
+S256_HD void msm_bucket_sum(pt &out, const uint32_t *entries, uint32_t start, uint32_t end, const apt *aff) {
+    pt acc;
+    pt_set_identity(acc);
+    for (uint32_t e = start; e < end; e++) {
+        uint32_t v = entries[e];
+        apt a = aff[v >> 1];
+        if (v & 1u) fe_neg(a.y, a.y);
+        pt_add_mixed(acc, acc, a.x, a.y);
+    }
+    out = acc;
+}
+
+// sum_{j in (lo, hi]} j * B_j, where B_j = buckets[j - 1]
+S256_HD void msm_segment(pt &out, const pt *buckets, int lo, int hi) {
+    pt run, sum;
+    pt_set_identity(run);
+    pt_set_identity(sum);
+    for (int j = hi; j > lo; j--) {
+        pt b = buckets[j - 1];
+        pt_add(run, run, b);
+        pt_add(sum, sum, run);
+    }
+    // sum = sum_j (j - lo) B_j ; add lo * run
+    pt m;
+    pt_set_identity(m);
+    for (int b = 15; b >= 0; b--) {
+        pt_double(m, m);
+        if ((lo >> b) & 1) pt_add(m, m, run);
+    }
+    pt_add(out, sum, m);
+}
+
+// Horner over window results, highest first
+S256_HD void msm_horner(pt &out, const pt *win, const msm_plan &p) {
+    pt acc = win[p.nwin - 1];
+    for (int w = p.nwin - 2; w >= 0; w--) {
+        for (int k = 0; k < p.c; k++) pt_double(acc, acc);
+        pt t = win[w];
+        pt_add(acc, acc, t);
+    }
+    out = acc;
+}
+
+// projective point <-> 96-byte big-endian X || Y || Z (the cross-GPU partial)
+S256_HD void pt_to_be96(uint8_t *b, const pt &p) {
+    fe t;
+    fe_normalize(t, p.x); fe_to_be32(b, t);
+    fe_normalize(t, p.y); fe_to_be32(b + 32, t);
+    fe_normalize(t, p.z); fe_to_be32(b + 64, t);
+}
+S256_HD void pt_from_be96(pt &p, const uint8_t *b) {
+    fe_from_be32(p.x, b);
+    fe_from_be32(p.y, b + 32);
+    fe_from_be32(p.z, b + 64);
+}
+// Y^2 Z == X^3 + 7 Z^3, or the identity (0 : y : 0)
+S256_HD uint32_t pt_on_curve(const pt &p) {
+    fe l, r, t, z2;
+    fe_sqr(l, p.y); fe_mul(l, l, p.z);
+    fe_sqr(t, p.x); fe_mul(r, t, p.x);
+    fe_sqr(z2, p.z); fe_mul(t, z2, p.z);
+    fe_mul_small(t, t, 7u);
+    fe_add(r, r, t);
+    uint32_t ident = fe_is_zero(p.z) & fe_is_zero(p.x) & (1u - fe_is_zero(p.y));
+    return (fe_equal(l, r) & (1u - fe_is_zero(p.z))) | ident;
+}
+
+}  // namespace s256

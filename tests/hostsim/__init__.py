@@ -83,3 +83,43 @@ def field_op(op, a, b):
     a, b = _a(a, 32), _a(b, 32); n = len(a); out = np.zeros((n, 32), np.uint8)
     lib().sim_field_op(op, _p(a), _p(b), C.c_size_t(n), _p(out))
     return out
+
+
+def scalar_mult(k, pts):
+    k, pts = _a(k, 32), _a(pts, 65); n = len(k); out = np.zeros((n, 65), np.uint8); st = np.zeros(n, np.uint8)
+    lib().sim_scalar_mult(_p(k), _p(pts), C.c_size_t(n), 0, _p(out), _p(st))
+    return out, st
+
+
+def ecdh(k, pts):
+    k, pts = _a(k, 32), _a(pts, 65); n = len(k); out = np.zeros((n, 32), np.uint8); st = np.zeros(n, np.uint8)
+    lib().sim_scalar_mult(_p(k), _p(pts), C.c_size_t(n), 1, _p(out), _p(st))
+    return out, st
+
+
+def point_decompress(p33):
+    p33 = _a(p33, 33); n = len(p33); out = np.zeros((n, 65), np.uint8); st = np.zeros(n, np.uint8)
+    lib().sim_point_decompress(_p(p33), C.c_size_t(n), _p(out), _p(st))
+    return out, st
+
+
+def msm(k, pts, vartime=True, force_c=0):
+    k, pts = _a(k, 32), _a(pts, 65); n = len(k)
+    if len(pts) != n:
+        raise ValueError("secp256k1: len(scalars) != len(points)")
+    out = np.zeros(65, np.uint8); st = C.c_uint8(0)
+    lib().sim_msm(_p(k), _p(pts), C.c_size_t(n), int(vartime), int(force_c), _p(out), C.byref(st), None)
+    return out, st.value
+
+
+def msm_partial(k, pts, vartime=True, force_c=0):
+    k, pts = _a(k, 32), _a(pts, 65); n = len(k)
+    out = np.zeros(65, np.uint8); part = np.zeros(96, np.uint8); st = C.c_uint8(0)
+    lib().sim_msm(_p(k), _p(pts), C.c_size_t(n), int(vartime), int(force_c), _p(out), C.byref(st), _p(part))
+    return part, (1 if st.value in (1, 2) else 0)
+
+
+def msm_combine(parts):
+    parts = _a(parts, 96); out = np.zeros(65, np.uint8); st = C.c_uint8(0)
+    lib().sim_msm_combine(_p(parts), C.c_size_t(len(parts)), _p(out), C.byref(st))
+    return out, st.value

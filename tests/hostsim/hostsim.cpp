@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../secp256k1-voi_b200/csrc/kernels.cuh"
+#include "../../secp256k1-voi_b200/csrc/msm.cuh"
 
 using namespace s256;
 #define EXPORT extern "C" __attribute__((visibility("default")))
@@ -115,6 +116,105 @@ EXPORT void sim_scalar_base_mult(const uint8_t *k32, size_t n, uint8_t *out65, u
         item_base_mult_ct(s.res[i], k, g_ct.data());
     }
     run_finish(s, n, false, false, 0, out65, status, nullptr);
+}
+EXPORT void sim_scalar_mult(const uint8_t *k32, const uint8_t *pt65, size_t n, int mode, uint8_t *out, uint8_t *status) {
+    scratch s(n);
+    for (size_t i = 0; i < n; i++) s.pvalid[i] = item_decode_uncompressed(s.aff[i], pt65 + 65 * i);
+    for (size_t i = 0; i < n; i++) item_scalar_mult_ct(i, s.aff.data(), k32, s.tbl.data(), s.res.data());
+    run_finish(s, n, true, false, mode, out, status, nullptr);
+}
+EXPORT void sim_point_decompress(const uint8_t *pt33, size_t n, uint8_t *out65, uint8_t *status) {
+    for (size_t i = 0; i < n; i++) {
+        apt a;
+        uint8_t ok = item_decode_compressed(a, pt33 + 33 * i);
+        memset(out65 + 65 * i, 0, 65);
+        if (ok) {
+            out65[65 * i] = 4;
+            fe_to_be32(out65 + 65 * i + 1, a.x);
+            fe_to_be32(out65 + 65 * i + 33, a.y);
+        }
+        status[i] = ok ? ST_OK : ST_INVALID;
+    }
+}
+// Pippenger flow of api.cu's chunk_msm, sequentially: digits -> counting sort -> bucket sums ->
+// window running sums (256 "threads" + tree) -> Horner.  force_c > 0 overrides the window size.
+EXPORT void sim_msm(const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, int force_c, uint8_t *out65, uint8_t *status,
+                    uint8_t *partial96) {
+    scratch s(n ? n : 1);
+    bool invalid = false;
+    for (size_t i = 0; i < n; i++) {
+        s.pvalid[i] = item_decode_uncompressed(s.aff[i], pt65 + 65 * i);
+        invalid |= !s.pvalid[i];
+    }
+    pt acc;
+    pt_set_identity(acc);
+    if (n && (!vartime || n < 32) && force_c == 0) {
+        for (size_t i = 0; i < n; i++) item_scalar_mult_ct(i, s.aff.data(), k32, s.tbl.data(), s.res.data());
+        for (size_t i = 0; i < n; i++) pt_add(acc, acc, s.res[i]);
+    } else if (n) {
+        msm_plan pl = msm_make_plan(n);
+        if (force_c) { pl.c = force_c; pl.nwin = 256 / force_c + 1; pl.nb = 1 << (force_c - 1); }
+        size_t total = (size_t)pl.nwin * pl.nb;
+        std::vector<uint32_t> counts(total + 1, 0), offsets(total + 1, 0), cursor(total + 1, 0), entries((size_t)pl.nwin * n);
+        std::vector<int32_t> dig((size_t)pl.nwin * n);
+        for (size_t i = 0; i < n; i++) {
+            sc k;
+            sc_from_be32(k, k32 + 32 * i);
+            int32_t d[MSM_MAX_WIN];
+            msm_digits(d, k, pl);
+            for (int w = 0; w < pl.nwin; w++) {
+                dig[(size_t)w * n + i] = d[w];
+                if (d[w]) counts[(size_t)w * pl.nb + (size_t)(std::abs(d[w]) - 1)]++;
+            }
+        }
+        for (size_t b = 0; b < total; b++) offsets[b + 1] = offsets[b] + counts[b];
+        cursor = offsets;
+        for (size_t i = n; i-- > 0;)  // reverse order: bucket order must not matter
+            for (int w = 0; w < pl.nwin; w++) {
+                int32_t d = dig[(size_t)w * n + i];
+                if (d) entries[cursor[(size_t)w * pl.nb + (size_t)(std::abs(d) - 1)]++] = ((uint32_t)i << 1) | (uint32_t)(d < 0);
+            }
+        std::vector<pt> buckets(total), win(pl.nwin);
+        for (size_t b = 0; b < total; b++) msm_bucket_sum(buckets[b], entries.data(), offsets[b], offsets[b + 1], s.aff.data());
+        const int T = 256;
+        for (int w = 0; w < pl.nwin; w++) {
+            std::vector<pt> sh(T);
+            int per = (pl.nb + T - 1) / T;
+            for (int t = 0; t < T; t++) {
+                int lo = t * per, hi = lo + per;
+                if (hi > pl.nb) hi = pl.nb;
+                if (lo < hi) msm_segment(sh[t], buckets.data() + (size_t)w * pl.nb, lo, hi);
+                else pt_set_identity(sh[t]);
+            }
+            for (int stride = T / 2; stride >= 1; stride >>= 1)
+                for (int t = 0; t < stride; t++) pt_add(sh[t], sh[t], sh[t + stride]);
+            win[w] = sh[0];
+        }
+        msm_horner(acc, win.data(), pl);
+    }
+    memset(out65, 0, 65);
+    if (partial96) pt_to_be96(partial96, acc);
+    if (invalid) { *status = ST_INVALID; if (partial96) memset(partial96, 0, 96); return; }
+    scratch f(1);
+    f.res[0] = acc;
+    run_finish(f, 1, false, false, 0, out65, status, nullptr);
+}
+EXPORT void sim_msm_combine(const uint8_t *partials96, size_t m, uint8_t *out65, uint8_t *status) {
+    pt acc;
+    pt_set_identity(acc);
+    bool bad = false;
+    for (size_t j = 0; j < m; j++) {
+        pt q;
+        pt_from_be96(q, partials96 + 96 * j);
+        uint32_t ok = fe_limbs_are_canonical(q.x) & fe_limbs_are_canonical(q.y) & fe_limbs_are_canonical(q.z) & pt_on_curve(q);
+        if (!ok) { bad = true; continue; }
+        pt_add(acc, acc, q);
+    }
+    memset(out65, 0, 65);
+    if (bad) { *status = ST_INVALID; return; }
+    scratch f(1);
+    f.res[0] = acc;
+    run_finish(f, 1, false, false, 0, out65, status, nullptr);
 }
 EXPORT void sim_gen_table(int wbits, int nwin, uint8_t *out) {
     for (int w = 0; w < nwin; w++)

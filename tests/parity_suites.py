@@ -262,3 +262,141 @@ def check_recover_synth(be, o, n=64):
         hit |= (st[sl] == 1) & (got[sl] == w["pk65"]).all(axis=1)
     assert hit.all()
     assert not st[4 * n:].any()  # v >= 4 is an error (point_s11n.go:246-248)
+
+
+def check_scalar_mult_ecdh(be, o, n=64):
+    w = synth.ecdh_batch(n, oracle_base_mult(o))
+    k, pts = w["k32"].copy(), w["pt65"].copy()
+    # edge scalars: 0, 1, 2, n-1, n (-> 0), n+1, 2^128, lambda, GLV boundary values
+    edge = [0, 1, 2, N - 1, N, N + 1, 2**128, 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72]
+    edge += [int(s, 16) for s in load_golden("kats.json")["glv_split_scalars"]]
+    for j, v in enumerate(edge[:n]):
+        k[j] = np.frombuffer(b32(v % 2**256), np.uint8)
+    got, st = be.scalar_mult(k, pts)
+    exp, est = o.batch_scalar_mult(k, pts)
+    assert np.array_equal(st, est), (st.tolist(), est.tolist())
+    assert np.array_equal(got, exp)
+    assert st[0] == 2 and st[4] == 2
+    # closed form on the untouched tail: k * (d*G) == (k*d mod n) * G
+    cf, _ = o.batch_scalar_base_mult(w["closed_form_scalar"])
+    assert np.array_equal(got[len(edge):], cf[len(edge):])
+    x, xst = be.ecdh(k, pts)
+    ex, exst = o.batch_ecdh(k, pts)
+    assert np.array_equal(xst, exst) and np.array_equal(x, ex)
+    # libsecp256k1 KAT (point_test.go:242-261)
+    kat = load_golden("kats.json")
+    got, st = be.scalar_mult(rows([H(kat["libsecp_xn"])], 32), rows([H(kat["libsecp_a"])], 65))
+    assert st[0] == 1 and got[0].tobytes().hex() == kat["libsecp_b"]
+    # invalid points are rejected, not multiplied
+    bad = pts[:4].copy(); bad[0, 0] = 3; bad[1, 40] ^= 1; bad[2, 1:33] = 0xFF
+    got, st = be.scalar_mult(k[8:12], bad)
+    assert st[:3].tolist() == [0, 0, 0] and st[3] == 1 and not got[:3].any()
+
+
+def check_wycheproof_ecdh(be, o, limit=None):
+    cases = load_golden("wycheproof_ecdh.json")["cases"]
+    if limit:
+        cases = [c for i, c in enumerate(cases) if i % limit == 0 or c["shared"] == "" or len(c["flags"]) > 0 and c["flags"] != ["Normal"]][:400]
+    unc = [c for c in cases if len(c["point"]) == 130]
+    cmp_ = [c for c in cases if len(c["point"]) == 66]
+    # compressed encodings go through the engine's decompressor first
+    if cmp_:
+        out, st = be.point_decompress(rows([H(c["point"]) for c in cmp_], 33))
+        for c, o65, s in zip(cmp_, out, st):
+            assert (s == 1) == (c["shared"] != ""), c
+            c["point65"] = o65.tobytes()
+    for c in unc:
+        c["point65"] = H(c["point"])
+    live = [c for c in cases if "point65" in c and (len(c["point"]) == 130 or c["shared"] != "")]
+    k = rows([H(c["priv"]) for c in live], 32)
+    pts = rows([c["point65"] for c in live], 65)
+    x, st = be.ecdh(k, pts)
+    for c, xi, s in zip(live, x, st):
+        if c["shared"] == "":
+            assert s == 0, c
+        else:
+            assert s == 1 and xi.tobytes().hex() == c["shared"], c
+
+
+def check_point_decompress(be, o, n=64):
+    w = synth.ecdh_batch(n, oracle_base_mult(o))
+    comp = np.zeros((n, 33), np.uint8)
+    comp[:, 0] = 2 + (w["pt65"][:, 64] & 1)
+    comp[:, 1:] = w["pt65"][:, 1:33]
+    out, st = be.point_decompress(comp)
+    assert st.tolist() == [1] * n and np.array_equal(out, w["pt65"])
+    flip = comp.copy(); flip[:, 0] ^= 1
+    out, st = be.point_decompress(flip)
+    assert st.all() and np.array_equal(out[:, :33], w["pt65"][:, :33]) and not np.array_equal(out, w["pt65"])
+    bad = comp[:4].copy(); bad[0, 0] = 4; bad[1, 1:] = 0xFF; bad[2, 1:] = 0; bad[2, 32] = 5  # x = 5: x^3+7 = 132 is a non-residue?
+    out, st = be.point_decompress(bad)
+    exp = [o.point_decode(bytes(b))[1] for b in bad]
+    assert st.tolist() == exp
+    kats = load_golden("kats.json")
+    out, st = be.point_decompress(rows([H(kats["g_compressed"])], 33))
+    assert st[0] == 1 and out[0].tobytes().hex() == kats["g_uncompressed"]
+
+
+def check_msm(be, o, sizes=(0, 1, 2, 31, 32, 33, 64, 300), big=None):
+    """point_mul_multi_test.go:14-70 (sizes 0, 1, 32, 64 vs sum of ScalarMult) and
+    the closed form of config 5: sum s_i * (d_i G) == (sum s_i d_i mod n) G."""
+    w = synth.msm_batch(max(sizes), oracle_base_mult(o))
+    for n in sizes:
+        k, pts = w["k32"][:n], w["pt65"][:n]
+        for vt in (True, False):
+            if not vt and n > 64:
+                continue
+            got, st = be.msm(k, pts, vartime=vt)
+            exp, est = o.msm(k.tobytes(), pts.tobytes(), vartime=vt)
+            assert st == est, (n, vt, st, est)
+            assert got.tobytes() == exp, (n, vt)
+    # structure: zero scalars, repeated points, cancelling pairs, scalars = n-1 / 2^255
+    n = 40
+    k, pts = w["k32"][:n].copy(), w["pt65"][:n].copy()
+    k[0] = 0
+    k[1] = np.frombuffer(b32(N - 1), np.uint8)
+    k[2] = np.frombuffer(b32(2**255), np.uint8)
+    k[3] = np.frombuffer(b32(2**256 - 1), np.uint8)   # reduced like NewScalarFromBytes
+    pts[5] = pts[4]
+    pts[7] = pts[6]; k[7] = np.frombuffer(b32((N - int.from_bytes(k[6].tobytes(), "big")) % N), np.uint8)  # cancels
+    got, st = be.msm(k, pts)
+    exp, est = o.msm(k.tobytes(), pts.tobytes())
+    assert (st, got.tobytes()) == (est, exp)
+    # everything cancels -> identity
+    k2 = np.zeros((2, 32), np.uint8); k2[0, 31] = 5; k2[1] = np.frombuffer(b32(N - 5), np.uint8)
+    p2 = np.concatenate([pts[8:9], pts[8:9]])
+    got, st = be.msm(k2, p2)
+    assert st == 2 and not got.any()
+    # an undecodable point poisons the whole product (the reference cannot even build the Point)
+    bad = pts.copy(); bad[9, 64] ^= 1
+    got, st = be.msm(k, bad)
+    assert st == 0 and not got.any()
+    # length mismatch panics in the reference (point_mul_multi.go:27-29)
+    import pytest
+    with pytest.raises(ValueError):
+        be.msm(k[:3], pts[:4])
+    if big:
+        wb = synth.msm_batch(big, oracle_base_mult(o))
+        got, st = be.msm(wb["k32"], wb["pt65"])
+        exp, est = o.scalar_base_mult(wb["closed_form_scalar"])
+        assert st == est and got.tobytes() == exp
+
+
+def check_msm_sharded(be, o, n=256, shards=4):
+    """Config 5's multi-GPU shape on one device: per-shard partial sums, one gather, one combine."""
+    w = synth.msm_batch(n, oracle_base_mult(o))
+    per = n // shards
+    parts = []
+    for g in range(shards):
+        p, st = be.msm_partial(w["k32"][g * per:(g + 1) * per], w["pt65"][g * per:(g + 1) * per])
+        assert st == 1
+        parts.append(p)
+    got, st = be.msm_combine(np.stack(parts))
+    exp, est = o.scalar_base_mult(w["closed_form_scalar"])
+    assert st == est and got.tobytes() == exp
+    # garbage partials are rejected
+    bad = np.stack(parts); bad[1, 5] ^= 1
+    got, st = be.msm_combine(bad)
+    assert st == 0
+    got, st = be.msm_combine(np.zeros((0, 96), np.uint8))
+    assert st == 2

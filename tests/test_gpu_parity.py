@@ -55,6 +55,26 @@ def test_recover(engine, oracle):
     ps.check_recover_synth(engine, oracle, n=512)
 
 
+def test_scalar_mult_ecdh(engine, oracle):
+    ps.check_scalar_mult_ecdh(engine, oracle, n=2048)
+
+
+def test_wycheproof_ecdh_all(engine, oracle):
+    ps.check_wycheproof_ecdh(engine, oracle)
+
+
+def test_point_decompress(engine, oracle):
+    ps.check_point_decompress(engine, oracle, n=1024)
+
+
+def test_msm(engine, oracle):
+    ps.check_msm(engine, oracle, sizes=(0, 1, 2, 31, 32, 33, 64, 300, 1000, 4096), big=1 << 17)
+
+
+def test_msm_sharded(engine, oracle):
+    ps.check_msm_sharded(engine, oracle, n=4096, shards=8)
+
+
 def test_empty_and_ragged(engine):
     z = np.zeros((0, 32), np.uint8)
     out, st = engine.scalar_base_mult(z)

@@ -15,6 +15,12 @@ class Backend:
     schnorr_verify = staticmethod(hs.schnorr_verify)
     double_scalar_mult_basepoint_vartime = staticmethod(hs.double_scalar_mult)
     scalar_base_mult = staticmethod(hs.scalar_base_mult)
+    scalar_mult = staticmethod(hs.scalar_mult)
+    ecdh = staticmethod(hs.ecdh)
+    point_decompress = staticmethod(hs.point_decompress)
+    msm = staticmethod(hs.msm)
+    msm_partial = staticmethod(hs.msm_partial)
+    msm_combine = staticmethod(hs.msm_combine)
     debug_field_op = staticmethod(hs.field_op)
     debug_gen_table = staticmethod(hs.gen_table)
 
@@ -64,3 +70,32 @@ def test_double_scalar_mult(oracle):
 
 def test_recover(oracle):
     ps.check_recover_synth(be, oracle, n=16)
+
+
+def test_scalar_mult_ecdh(oracle):
+    ps.check_scalar_mult_ecdh(be, oracle, n=40)
+
+
+def test_wycheproof_ecdh_subset(oracle):
+    ps.check_wycheproof_ecdh(be, oracle, limit=12)
+
+
+def test_point_decompress(oracle):
+    ps.check_point_decompress(be, oracle, n=16)
+
+
+def test_msm(oracle):
+    ps.check_msm(be, oracle, sizes=(0, 1, 2, 31, 32, 33, 64, 200))
+
+
+def test_msm_window_sizes(oracle):
+    # every Pippenger window width the planner can pick, incl. the carry-only top window (c | 256)
+    w = ps.synth.msm_batch(48, ps.oracle_base_mult(oracle))
+    exp, est = oracle.msm(w["k32"].tobytes(), w["pt65"].tobytes())
+    for c in (4, 5, 7, 8, 11, 13, 16):
+        got, st = hs.msm(w["k32"], w["pt65"], force_c=c)
+        assert (st, got.tobytes()) == (est, exp), c
+
+
+def test_msm_sharded(oracle):
+    ps.check_msm_sharded(be, oracle, n=128, shards=4)
