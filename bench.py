@@ -272,7 +272,8 @@ def main():
                          "kernel": "k_dsm", "achieved": achieved / 1e12 if achieved else None,
                          "peak": imad_peak / 1e12, "unit": "TMAC32/s",
                          "frac": (achieved / imad_peak) if achieved else None,
-                         "peak_source": "measured live: s256_microbench_imad (independent IMAD.WIDE.U32 chains, all SMs)",
+                         "peak_source": "measured live in this process: s256_microbench_imad (mad.lo.cc/madc.hi.cc chains = "
+                                        "IMAD.WIDE.U32[.X], SASS-checked, all SMs); nominal 148 SM x 32 MAC32/clk x 1.965 GHz = 9.31",
                          "mac32_per_item_kernel": ladder_mac, "mac32_per_item_whole_verify": mac_item,
                          "kernel_ms": dsm_ms / max(dsm_launches, 1), "kernel_share_of_step": dsm_ms / ms_total if world == 1 else None,
                          "whole_step_frac": value / world * mac_item / imad_peak,

@@ -19,6 +19,7 @@ import os
 import numpy as np
 
 from . import build as _build
+from . import parallel  # noqa: F401  (re-exported)
 from . import synth  # noqa: F401  (re-exported)
 
 ST_INVALID, ST_OK, ST_IDENTITY = 0, 1, 2

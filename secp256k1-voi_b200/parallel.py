@@ -1,0 +1,54 @@
+"""Multi-GPU layer: one process per GPU, torch.distributed for the plumbing.
+
+Verification, base-mult, ScalarMult/ECDH, recovery: items are independent, so
+rank g simply owns the contiguous slice [g*n/W, (g+1)*n/W) -- NO collective on
+the data path.  Only the MSM has an exchange step: every
+rank reduces its slice to one projective partial sum (96 bytes) and a single
+all-gather (NCCL over NVLink on GPUs, gloo in the CPU tests) brings the W
+partials together; every rank then folds them with W - 1 complete additions
+and one inversion.  The message is W * 96 B, i.e. pure latency.
+"""
+import numpy as np
+
+
+def shard_range(n, rank, world):
+    """Contiguous slice of n items owned by `rank` (sizes differ by at most 1)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_rows(rank, world, *arrays):
+    n = len(arrays[0])
+    lo, hi = shard_range(n, rank, world)
+    return tuple(a[lo:hi] for a in arrays)
+
+
+def gather_bytes(local_row, group=None, device=None):
+    """All-gathers one fixed-size uint8 row per rank -> (world, len) numpy array."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    t = torch.from_numpy(np.ascontiguousarray(local_row, dtype=np.uint8))
+    if device is not None:
+        t = t.to(device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return np.stack([o.cpu().numpy() for o in out])
+
+
+def msm_sharded(engine, k32_local, pt65_local, vartime=True, group=None, device=None):
+    """Point.MultiScalarMult over a batch sharded across ranks: each rank passes ITS slice.
+    Returns (out65, status) on every rank.  Invalid points anywhere poison the result."""
+    part, st = engine.msm_partial(k32_local, pt65_local, vartime=vartime)
+    row = np.concatenate([np.asarray(part, np.uint8).reshape(96), np.array([st], np.uint8)])
+    rows = gather_bytes(row, group=group, device=device)
+    if (rows[:, 96] != 1).any():
+        return np.zeros(65, np.uint8), 0
+    return engine.msm_combine(rows[:, :96])
+
+
+def verify_sharded(engine, rank, world, pk65, digest32, sig64, flags=0):
+    """secec Verify over this rank's contiguous slice of a global batch (no collective)."""
+    pk, dg, sg = shard_rows(rank, world, pk65, digest32, sig64)
+    return engine.ecdsa_verify(pk, dg, sg, flags)
