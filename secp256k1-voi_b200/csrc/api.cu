@@ -187,9 +187,10 @@ __global__ void __launch_bounds__(S256_TPB) k_msm_buckets(uint32_t total, const 
 __global__ void __launch_bounds__(S256_MSM_WT) k_msm_windows(msm_plan plan, const pt *buckets, pt *win) {
     __shared__ pt sh[S256_MSM_WT];
     int w = blockIdx.x, t = threadIdx.x;
-    int per = (plan.nb + S256_MSM_WT - 1) / S256_MSM_WT;
+    int nbw = msm_window_buckets(plan, w);
+    int per = (nbw + S256_MSM_WT - 1) / S256_MSM_WT;
     int lo = t * per, hi = lo + per;
-    if (hi > plan.nb) hi = plan.nb;
+    if (hi > nbw) hi = nbw;
     pt s;
     if (lo < hi)
         msm_segment(s, buckets + (size_t)w * plan.nb, lo, hi);
@@ -777,20 +778,23 @@ extern "C" int s256_point_decompress(s256_ctx *ctx, const uint8_t *pt33, size_t 
 // ---------------------------------------------------------------------------
 // MSM
 // ---------------------------------------------------------------------------
+static size_t msm_entries_capacity(const s256_ctx *ctx) {
+    // nwin * n entries; the planner uses c >= 12 once n >= 2^16 (nwin <= 22), and c >= 4 (nwin <= 64) below
+    size_t cap = ctx->cap;
+    size_t small = (size_t)MSM_MAX_WIN * (cap < 65536 ? cap : 65536), large = (size_t)22 * cap;
+    return small > large ? small : large;
+}
 static int msm_ensure(s256_ctx *ctx) {
     if (ctx->msm_cap) return S256_SUCCESS;
-    size_t cap = ctx->cap;
-    msm_plan pl = msm_make_plan(cap);
-    // the largest bucket space over all plans up to cap: nwin * nb grows with c
-    size_t total = (size_t)pl.nwin * pl.nb;
-    for (int c = 4; c <= pl.c; c++) {
-        size_t t = (size_t)(256 / c + 1) << (c - 1);
+    size_t total = 0;
+    for (int c = 4; c <= MSM_MAX_C; c++) {
+        size_t t = (size_t)msm_plan_for_c(c).total;
         if (t > total) total = t;
     }
     CK(cudaMalloc(&ctx->msm_counts, (total + 1) * 4));
     CK(cudaMalloc(&ctx->msm_offsets, (total + 1) * 4));
     CK(cudaMalloc(&ctx->msm_cursor, (total + 1) * 4));
-    CK(cudaMalloc(&ctx->msm_entries, (size_t)MSM_MAX_WIN * 4 * (cap < 65536 ? 65536 : cap) / (cap < 65536 ? 1 : 3)));
+    CK(cudaMalloc(&ctx->msm_entries, msm_entries_capacity(ctx) * 4));
     CK(cudaMalloc(&ctx->msm_buckets, total * sizeof(pt)));
     CK(cudaMalloc(&ctx->msm_win, MSM_MAX_WIN * sizeof(pt)));
     CK(cudaMalloc(&ctx->msm_acc, sizeof(pt)));
@@ -800,13 +804,8 @@ static int msm_ensure(s256_ctx *ctx) {
     cub::DeviceScan::ExclusiveSum(nullptr, bytes, ctx->msm_counts, ctx->msm_offsets, (int)(total + 1));
     ctx->msm_cub_bytes = bytes;
     CK(cudaMalloc(&ctx->msm_cub, bytes));
-    ctx->msm_cap = cap;
+    ctx->msm_cap = ctx->cap;
     return S256_SUCCESS;
-}
-// entries needed by a plan: nwin * n uint32
-static size_t msm_entries_capacity(const s256_ctx *ctx) {
-    size_t cap = ctx->cap;
-    return (size_t)MSM_MAX_WIN * (cap < 65536 ? 65536 : cap) / (cap < 65536 ? 1 : 3);
 }
 
 // one chunk (device pointers): msm_acc (+)= sum k_i P_i
@@ -834,16 +833,8 @@ static int chunk_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, siz
         return S256_SUCCESS;
     }
     msm_plan pl = msm_make_plan(n);
-    if ((size_t)pl.nwin * n > msm_entries_capacity(ctx)) {
-        // fall back to a smaller window count is impossible (nwin grows as c shrinks): shrink c's effect by
-        // raising c until the entries fit
-        while (pl.c < MSM_MAX_C && (size_t)(256 / pl.c + 1) * n > msm_entries_capacity(ctx)) {
-            pl.c++;
-            pl.nwin = 256 / pl.c + 1;
-            pl.nb = 1 << (pl.c - 1);
-        }
-    }
-    uint32_t total = (uint32_t)pl.nwin * (uint32_t)pl.nb;
+    while (pl.c < MSM_MAX_C && (size_t)pl.nwin * n > msm_entries_capacity(ctx)) pl = msm_plan_for_c(pl.c + 1);
+    uint32_t total = (uint32_t)pl.total;
     CK(cudaMemsetAsync(ctx->msm_counts, 0, ((size_t)total + 1) * 4, s));
     LAUNCH(ctx, k_msm_digits<false>, grid_for(n), 0, s, k32, n, pl, ctx->msm_counts, ctx->msm_cursor, ctx->msm_entries);
     size_t bytes = ctx->msm_cub_bytes;

@@ -22,42 +22,54 @@
 namespace s256 {
 
 constexpr int MSM_MAX_C = 16;
-constexpr int MSM_MAX_WIN = 65;  // c = 4 -> 64 windows + carry
+constexpr int MSM_MAX_WIN = 64;  // c = 4 -> 64 windows
 
+// Windows 0 .. nwin-2 use signed digits (2^(c-1) buckets each).  The top window keeps
+// its digit UNSIGNED (value + incoming carry, at most 2^top_bits) so that no carry-only
+// window exists: such a window would put half of all points into one bucket.
 struct msm_plan {
     int c;         // window bits
-    int nwin;      // windows (the last one only ever holds the recoding carry when c divides 256)
-    int nb;        // buckets per window = 2^(c-1)
+    int nwin;      // windows = ceil(256 / c)
+    int nb;        // buckets per signed window = 2^(c-1)
+    int nb_top;    // buckets of the top window = 2^top_bits, top_bits = 256 - c*(nwin-1)
+    int total;     // all buckets
 };
 
+S256_HD msm_plan msm_plan_for_c(int c) {
+    msm_plan p;
+    p.c = c;
+    p.nwin = (256 + c - 1) / c;
+    p.nb = 1 << (c - 1);
+    p.nb_top = 1 << (256 - c * (p.nwin - 1));
+    p.total = (p.nwin - 1) * p.nb + p.nb_top;
+    return p;
+}
 S256_HD msm_plan msm_make_plan(size_t n) {
     int lg = 0;
     while (((size_t)1 << (lg + 1)) <= n) lg++;
     int c = lg - 4;
     if (c < 4) c = 4;
     if (c > MSM_MAX_C) c = MSM_MAX_C;
-    msm_plan p;
-    p.c = c;
-    p.nwin = 256 / c + 1;
-    p.nb = 1 << (c - 1);
-    return p;
+    return msm_plan_for_c(c);
 }
+S256_HD int msm_window_buckets(const msm_plan &p, int w) { return w == p.nwin - 1 ? p.nb_top : p.nb; }
 
-// signed digits of a reduced scalar; d[w] in [-(2^(c-1)-1), 2^(c-1)]
+// digits of a reduced scalar: d[w] in [-(2^(c-1)-1), 2^(c-1)] for w < nwin-1, d[nwin-1] in [0, 2^top_bits]
 S256_HD void msm_digits(int32_t *d, const sc &k, const msm_plan &p) {
     uint32_t carry = 0;
     for (int w = 0; w < p.nwin; w++) {
         int bit = w * p.c;
-        uint32_t v = 0;
-        if (bit < 256) {
-            int limb = bit >> 5, sh = bit & 31;
-            v = k.v[limb] >> sh;
-            if (sh + p.c > 32 && limb + 1 < 8) v |= k.v[limb + 1] << (32 - sh);
-            v &= (1u << p.c) - 1u;
-        }
+        int limb = bit >> 5, sh = bit & 31;
+        uint32_t v = k.v[limb] >> sh;
+        if (sh + p.c > 32 && limb + 1 < 8) v |= k.v[limb + 1] << (32 - sh);
+        v &= (1u << p.c) - 1u;  // bits above 255 are zero by construction
         v += carry;
-        carry = (v + (1u << (p.c - 1)) - 1u) >> p.c;
-        d[w] = (int32_t)v - (int32_t)(carry << p.c);
+        if (w == p.nwin - 1) {
+            d[w] = (int32_t)v;
+        } else {
+            carry = (v + (1u << (p.c - 1)) - 1u) >> p.c;
+            d[w] = (int32_t)v - (int32_t)(carry << p.c);
+        }
     }
 }
 
@@ -87,7 +99,7 @@ S256_HD void msm_segment(pt &out, const pt *buckets, int lo, int hi) {
     // sum = sum_j (j - lo) B_j ; add lo * run
     pt m;
     pt_set_identity(m);
-    for (int b = 15; b >= 0; b--) {
+    for (int b = 16; b >= 0; b--) {
         pt_double(m, m);
         if ((lo >> b) & 1) pt_add(m, m, run);
     }

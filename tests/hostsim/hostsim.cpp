@@ -153,8 +153,8 @@ EXPORT void sim_msm(const uint8_t *k32, const uint8_t *pt65, size_t n, int varti
         for (size_t i = 0; i < n; i++) pt_add(acc, acc, s.res[i]);
     } else if (n) {
         msm_plan pl = msm_make_plan(n);
-        if (force_c) { pl.c = force_c; pl.nwin = 256 / force_c + 1; pl.nb = 1 << (force_c - 1); }
-        size_t total = (size_t)pl.nwin * pl.nb;
+        if (force_c) pl = msm_plan_for_c(force_c);
+        size_t total = (size_t)pl.total;
         std::vector<uint32_t> counts(total + 1, 0), offsets(total + 1, 0), cursor(total + 1, 0), entries((size_t)pl.nwin * n);
         std::vector<int32_t> dig((size_t)pl.nwin * n);
         for (size_t i = 0; i < n; i++) {
@@ -179,10 +179,11 @@ EXPORT void sim_msm(const uint8_t *k32, const uint8_t *pt65, size_t n, int varti
         const int T = 256;
         for (int w = 0; w < pl.nwin; w++) {
             std::vector<pt> sh(T);
-            int per = (pl.nb + T - 1) / T;
+            int nbw = msm_window_buckets(pl, w);
+            int per = (nbw + T - 1) / T;
             for (int t = 0; t < T; t++) {
                 int lo = t * per, hi = lo + per;
-                if (hi > pl.nb) hi = pl.nb;
+                if (hi > nbw) hi = nbw;
                 if (lo < hi) msm_segment(sh[t], buckets.data() + (size_t)w * pl.nb, lo, hi);
                 else pt_set_identity(sh[t]);
             }
