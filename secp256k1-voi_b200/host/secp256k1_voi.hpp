@@ -1,0 +1,392 @@
+// secp256k1_voi.hpp -- host-side mirror of the reference's Go API over the C ABI.
+//
+// The reference is Go and there is no Go toolchain in this image, so the host
+// layer above include/secp256k1_b200.h is C++ with the SAME type / method names,
+// argument meaning and error behaviour as the Go packages it mirrors:
+//   secp256k1.Scalar  (scalar.go:52-261)      -> secp256k1::Scalar
+//   secp256k1.Point   (point.go:42-224, point_s11n.go, point_mul_*.go) -> secp256k1::Point
+//   secec.PublicKey.Verify / RecoverPublicKey / PrivateKey.ECDH (secec/ecdsa.go, secec.go)
+//   bitcoin.SchnorrPublicKey.Verify (secec/bitcoin/schnorr.go:221)
+// plus the batch entry points the engine adds (…Batch).  Single-item methods are
+// batches of one: correct, but the GPU only pays off on the batch forms.
+// Misuse that panics in Go throws std::logic_error; data errors that return
+// `error` in Go throw secp256k1::Error or return false exactly where Go does.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/secp256k1_b200.h"
+
+namespace secp256k1 {
+
+constexpr size_t ScalarSize = 32, CoordSize = 32, CompressedPointSize = 33, UncompressedPointSize = 65,
+                 IdentityPointSize = 1;
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// One engine context per process/GPU (the reference builds its tables at package init).
+class Engine {
+  public:
+    static Engine &Default() {
+        static Engine e(-1, 0);
+        return e;
+    }
+    Engine(int device, size_t max_batch) {
+        int rc = s256_init(&ctx_, device, max_batch);
+        if (rc != S256_SUCCESS) throw Error(std::string("s256_init: ") + s256_strerror(rc));
+    }
+    ~Engine() { s256_free(ctx_); }
+    Engine(const Engine &) = delete;
+    Engine &operator=(const Engine &) = delete;
+    s256_ctx *ctx() const { return ctx_; }
+    void check(int rc, const char *what) const {
+        if (rc != S256_SUCCESS)
+            throw Error(std::string(what) + ": " + s256_strerror(rc) + " " + s256_last_cuda_error(ctx_));
+    }
+
+  private:
+    s256_ctx *ctx_ = nullptr;
+};
+
+namespace detail {
+static const uint8_t N_BE[32] = {0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFE,
+                                 0xBA, 0xAE, 0xDC, 0xE6, 0xAF, 0x48, 0xA0, 0x3B, 0xBF, 0xD2, 0x5E, 0x8C, 0xD0, 0x36, 0x41, 0x41};
+inline int cmp_be(const uint8_t *a, const uint8_t *b) { return std::memcmp(a, b, 32); }
+inline void sub_be(uint8_t *r, const uint8_t *a, const uint8_t *b) {
+    int borrow = 0;
+    for (int i = 31; i >= 0; i--) {
+        int d = (int)a[i] - (int)b[i] - borrow;
+        borrow = d < 0;
+        r[i] = (uint8_t)(d + (borrow << 8));
+    }
+}
+}  // namespace detail
+
+// scalar.go: an integer mod n.  Only what the batch path needs lives on the host
+// (decode / encode / range predicates); arithmetic on scalars happens on the GPU.
+class Scalar {
+  public:
+    Scalar() { b_.fill(0); }  // NewScalar(): zero
+    // scalar.go:123 SetBytes: reduces once, returns didReduce
+    uint64_t SetBytes(const uint8_t src[32]) {
+        if (detail::cmp_be(src, detail::N_BE) >= 0) {
+            detail::sub_be(b_.data(), src, detail::N_BE);
+            return 1;
+        }
+        std::memcpy(b_.data(), src, 32);
+        return 0;
+    }
+    // scalar.go:136 SetCanonicalBytes: error if >= n, receiver unchanged
+    void SetCanonicalBytes(const uint8_t src[32]) {
+        if (detail::cmp_be(src, detail::N_BE) >= 0) throw Error("secp256k1: scalar value out of range");
+        std::memcpy(b_.data(), src, 32);
+    }
+    static Scalar NewScalarFromBytes(const uint8_t src[32]) {
+        Scalar s;
+        s.SetBytes(src);
+        return s;
+    }
+    static Scalar NewScalarFromCanonicalBytes(const uint8_t src[32]) {
+        Scalar s;
+        s.SetCanonicalBytes(src);
+        return s;
+    }
+    static Scalar NewScalarFromUint64(uint64_t v) {
+        Scalar s;
+        for (int i = 0; i < 8; i++) s.b_[31 - i] = (uint8_t)(v >> (8 * i));
+        return s;
+    }
+    const std::array<uint8_t, 32> &Bytes() const { return b_; }  // scalar.go:148, canonical big-endian
+    uint64_t IsZero() const {
+        uint8_t acc = 0;
+        for (uint8_t x : b_) acc |= x;
+        return acc == 0;
+    }
+    uint64_t Equal(const Scalar &o) const { return b_ == o.b_; }
+    // scalar.go:190
+    uint64_t IsGreaterThanHalfN() const {
+        static const uint8_t HALF[32] = {0x7F, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF,
+                                         0x5D, 0x57, 0x6E, 0x73, 0x57, 0xA4, 0x50, 0x1D, 0xDF, 0xE9, 0x2F, 0x46, 0x68, 0x1B, 0x20, 0xA0};
+        return detail::cmp_be(b_.data(), HALF) > 0;
+    }
+
+  private:
+    std::array<uint8_t, 32> b_;
+};
+
+// point.go: a curve point or the point at infinity.  Only the affine value is
+// observable in the reference (point_test.go:359-390), so the mirror stores it.
+class Point {
+  public:
+    Point() = default;  // the zero value is NOT valid (point.go:24-26)
+    static Point NewIdentityPoint() {
+        Point p;
+        p.valid_ = true;
+        p.identity_ = true;
+        return p;
+    }
+    static Point NewGeneratorPoint() {
+        static const uint8_t G[65] = {
+            0x04, 0x79, 0xBE, 0x66, 0x7E, 0xF9, 0xDC, 0xBB, 0xAC, 0x55, 0xA0, 0x62, 0x95, 0xCE, 0x87, 0x0B, 0x07,
+            0x02, 0x9B, 0xFC, 0xDB, 0x2D, 0xCE, 0x28, 0xD9, 0x59, 0xF2, 0x81, 0x5B, 0x16, 0xF8, 0x17, 0x98, 0x48,
+            0x3A, 0xDA, 0x77, 0x26, 0xA3, 0xC4, 0x65, 0x5D, 0xA4, 0xFB, 0xFC, 0x0E, 0x11, 0x08, 0xA8, 0xFD, 0x17,
+            0xB4, 0x48, 0xA6, 0x85, 0x54, 0x19, 0x9C, 0x47, 0xD0, 0x8F, 0xFB, 0x10, 0xD4, 0xB8};
+        Point p;
+        p.valid_ = true;
+        std::memcpy(p.enc_.data(), G, 65);
+        return p;
+    }
+    // point_s11n.go:218-241 SetBytes / NewPointFromBytes: 1, 33 or 65 bytes
+    static Point NewPointFromBytes(const uint8_t *src, size_t len, Engine &e = Engine::Default()) {
+        Point p;
+        if (len == IdentityPointSize) {
+            if (src[0] != 0x00) throw Error("secp256k1: invalid encoded point prefix");
+            return NewIdentityPoint();
+        }
+        uint8_t st = 0;
+        if (len == CompressedPointSize) {
+            e.check(s256_point_decompress(e.ctx(), src, 1, p.enc_.data(), &st), "point_decompress");
+        } else if (len == UncompressedPointSize) {
+            // validate by a 1*P constant-time multiplication-free path: decode happens inside every
+            // entry point; use u1 = 0, u2 = 1 so the result is P itself
+            uint8_t zero[32] = {0}, one[32] = {0};
+            one[31] = 1;
+            e.check(s256_double_scalar_mult_basepoint_vartime(e.ctx(), zero, one, src, 1, p.enc_.data(), &st), "decode");
+        } else {
+            throw Error("secp256k1: invalid encoded point");
+        }
+        if (st != S256_ST_OK) throw Error("secp256k1: point not on curve / invalid encoding");
+        p.valid_ = true;
+        return p;
+    }
+    uint64_t IsIdentity() const {
+        assertValid();
+        return identity_;
+    }
+    uint64_t IsYOdd() const {  // point.go:155
+        assertValid();
+        return identity_ ? 0 : (enc_[64] & 1);
+    }
+    uint64_t Equal(const Point &o) const {
+        assertValid();
+        o.assertValid();
+        return identity_ == o.identity_ && (identity_ || enc_ == o.enc_);
+    }
+    // point_s11n.go:66-134
+    std::vector<uint8_t> UncompressedBytes() const {
+        assertValid();
+        if (identity_) return {0x00};
+        return std::vector<uint8_t>(enc_.begin(), enc_.end());
+    }
+    std::vector<uint8_t> CompressedBytes() const {
+        assertValid();
+        if (identity_) return {0x00};
+        std::vector<uint8_t> o(33);
+        o[0] = (uint8_t)(2 + (enc_[64] & 1));
+        std::memcpy(o.data() + 1, enc_.data() + 1, 32);
+        return o;
+    }
+    std::vector<uint8_t> XBytes() const {
+        assertValid();
+        if (identity_) throw Error("secp256k1: point not on curve");  // point_s11n.go:123-125
+        return std::vector<uint8_t>(enc_.begin() + 1, enc_.begin() + 33);
+    }
+
+    // point_mul_table.go:168 -- v = s * G (constant time)
+    Point &ScalarBaseMult(const Scalar &s, Engine &e = Engine::Default()) {
+        uint8_t st = 0;
+        e.check(s256_scalar_base_mult(e.ctx(), s.Bytes().data(), 1, enc_.data(), &st), "ScalarBaseMult");
+        return set(st);
+    }
+    // point_mul_glv.go:257 -- v = s * p (constant time)
+    Point &ScalarMult(const Scalar &s, const Point &p, Engine &e = Engine::Default()) {
+        p.assertValid();
+        if (p.identity_) return *this = NewIdentityPoint();
+        uint8_t st = 0;
+        std::array<uint8_t, 65> in = p.enc_;
+        e.check(s256_scalar_mult(e.ctx(), s.Bytes().data(), in.data(), 1, enc_.data(), &st), "ScalarMult");
+        return set(st);
+    }
+    // point_mul_glv.go:307 -- v = u1 * G + u2 * p (variable time)
+    Point &DoubleScalarMultBasepointVartime(const Scalar &u1, const Scalar &u2, const Point &p,
+                                            Engine &e = Engine::Default()) {
+        p.assertValid();
+        if (p.identity_) return ScalarBaseMult(u1, e);
+        uint8_t st = 0;
+        std::array<uint8_t, 65> in = p.enc_;
+        e.check(s256_double_scalar_mult_basepoint_vartime(e.ctx(), u1.Bytes().data(), u2.Bytes().data(), in.data(), 1,
+                                                          enc_.data(), &st),
+                "DoubleScalarMultBasepointVartime");
+        return set(st);
+    }
+    // point_mul_multi.go:25,73 -- v = sum scalars[i] * points[i]; length mismatch panics
+    Point &MultiScalarMult(const std::vector<Scalar> &scalars, const std::vector<Point> &points, bool vartime = false,
+                           Engine &e = Engine::Default()) {
+        if (scalars.size() != points.size()) throw std::logic_error("secp256k1: len(scalars) != len(points)");
+        std::vector<uint8_t> k, p;
+        for (size_t i = 0; i < scalars.size(); i++) {
+            points[i].assertValid();
+            if (points[i].identity_) continue;  // contributes nothing
+            k.insert(k.end(), scalars[i].Bytes().begin(), scalars[i].Bytes().end());
+            p.insert(p.end(), points[i].enc_.begin(), points[i].enc_.end());
+        }
+        uint8_t st = 0;
+        e.check(s256_msm(e.ctx(), k.data(), p.data(), k.size() / 32, vartime ? 1 : 0, enc_.data(), &st), "MultiScalarMult");
+        return set(st);
+    }
+    Point &MultiScalarMultVartime(const std::vector<Scalar> &s, const std::vector<Point> &p, Engine &e = Engine::Default()) {
+        return MultiScalarMult(s, p, true, e);
+    }
+    // point.go:62 -- v = p + q, through the engine's projective combine
+    Point &Add(const Point &p, const Point &q, Engine &e = Engine::Default()) {
+        p.assertValid();
+        q.assertValid();
+        uint8_t parts[2 * 96], st = 0;
+        p.toPartial(parts);
+        q.toPartial(parts + 96);
+        e.check(s256_msm_combine(e.ctx(), parts, 2, enc_.data(), &st), "Add");
+        return set(st);
+    }
+    const std::array<uint8_t, 65> &raw() const { return enc_; }
+
+  private:
+    void assertValid() const {
+        if (!valid_) throw std::logic_error("secp256k1: use of uninitialized Point");  // point.go:227-233
+    }
+    Point &set(uint8_t st) {
+        if (st == S256_ST_INVALID) throw Error("secp256k1: invalid input");
+        valid_ = true;
+        identity_ = st == S256_ST_IDENTITY;
+        return *this;
+    }
+    void toPartial(uint8_t out[96]) const {
+        std::memset(out, 0, 96);
+        if (identity_) {
+            out[63] = 1;  // (0 : 1 : 0)
+        } else {
+            std::memcpy(out, enc_.data() + 1, 64);
+            out[95] = 1;
+        }
+    }
+    std::array<uint8_t, 65> enc_{};
+    bool valid_ = false, identity_ = false;
+};
+
+// ---- batch entry points the engine adds next to the Go API --------------------------------------
+inline void ScalarBaseMultBatch(const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status, Engine &e = Engine::Default()) {
+    e.check(s256_scalar_base_mult(e.ctx(), k32, n, out65, status), "ScalarBaseMultBatch");
+}
+inline void ScalarMultBatch(const uint8_t *k32, const uint8_t *pt65, size_t n, uint8_t *out65, uint8_t *status,
+                            Engine &e = Engine::Default()) {
+    e.check(s256_scalar_mult(e.ctx(), k32, pt65, n, out65, status), "ScalarMultBatch");
+}
+inline void DoubleScalarMultBasepointVartimeBatch(const uint8_t *u1, const uint8_t *u2, const uint8_t *pt65, size_t n,
+                                                  uint8_t *out65, uint8_t *status, Engine &e = Engine::Default()) {
+    e.check(s256_double_scalar_mult_basepoint_vartime(e.ctx(), u1, u2, pt65, n, out65, status), "DoubleScalarMultBatch");
+}
+
+namespace secec {
+
+struct ECDSAOptions {  // secec/ecdsa.go:55-75 (EncodingCompact path)
+    bool RejectMalleable = false;
+};
+constexpr size_t CompactSignatureSize = 64, CompactRecoverableSignatureSize = 65;
+
+class PublicKey {
+  public:
+    // secec/secec.go:188 NewPublicKey: any SEC 1 encoding, identity rejected
+    static PublicKey NewPublicKey(const uint8_t *key, size_t len, Engine &e = Engine::Default()) {
+        Point p = Point::NewPointFromBytes(key, len, e);
+        if (p.IsIdentity()) throw Error("secp256k1/secec: public key is the point at infinity");
+        PublicKey k;
+        k.point_ = p;
+        return k;
+    }
+    const Point &point() const { return point_; }
+    std::vector<uint8_t> Bytes() const { return point_.UncompressedBytes(); }
+    // secec/ecdsa.go:171 Verify, compact r||s encoding; digest: leftmost 32 bytes are used (ecdsa.go:477)
+    bool Verify(const uint8_t *digest, size_t digest_len, const uint8_t *sig, size_t sig_len, const ECDSAOptions *opts = nullptr,
+                Engine &e = Engine::Default()) const {
+        if (digest_len < 32 || sig_len != CompactSignatureSize) return false;
+        uint8_t ok = 0;
+        e.check(s256_ecdsa_verify(e.ctx(), point_.raw().data(), digest, sig,
+                                  (opts && opts->RejectMalleable) ? S256_FLAG_REJECT_MALLEABLE : 0u, 1, &ok),
+                "Verify");
+        return ok == 1;
+    }
+    bool Equal(const PublicKey &o) const { return point_.Equal(o.point_); }
+
+  private:
+    Point point_;
+};
+
+// secec/ecdsa.go:244 RecoverPublicKey on r || s || v
+inline PublicKey RecoverPublicKey(const uint8_t digest32[32], const uint8_t sig65[65], Engine &e = Engine::Default()) {
+    uint8_t pk[65], st = 0;
+    e.check(s256_ecdsa_recover(e.ctx(), digest32, sig65, 1, pk, &st), "RecoverPublicKey");
+    if (st != S256_ST_OK) throw Error("secp256k1/secec: public key recovery failed");
+    return PublicKey::NewPublicKey(pk, 65, e);
+}
+// secec/secec.go:53 PrivateKey.ECDH: x(k * P)
+inline std::array<uint8_t, 32> ECDH(const Scalar &priv, const PublicKey &remote, Engine &e = Engine::Default()) {
+    std::array<uint8_t, 32> x{};
+    uint8_t st = 0;
+    e.check(s256_ecdh(e.ctx(), priv.Bytes().data(), remote.point().raw().data(), 1, x.data(), &st), "ECDH");
+    if (st != S256_ST_OK) throw Error("secp256k1/secec: ECDH result is the point at infinity");
+    return x;
+}
+// batch forms
+inline void VerifyBatch(const uint8_t *pk65, const uint8_t *digest32, const uint8_t *sig64, size_t n, bool reject_malleable,
+                        uint8_t *ok, Engine &e = Engine::Default()) {
+    e.check(s256_ecdsa_verify(e.ctx(), pk65, digest32, sig64, reject_malleable ? S256_FLAG_REJECT_MALLEABLE : 0u, n, ok), "VerifyBatch");
+}
+inline void RecoverPublicKeyBatch(const uint8_t *digest32, const uint8_t *sig65, size_t n, uint8_t *pk65, uint8_t *status,
+                                  Engine &e = Engine::Default()) {
+    e.check(s256_ecdsa_recover(e.ctx(), digest32, sig65, n, pk65, status), "RecoverPublicKeyBatch");
+}
+inline void ECDHBatch(const uint8_t *k32, const uint8_t *pt65, size_t n, uint8_t *x32, uint8_t *status, Engine &e = Engine::Default()) {
+    e.check(s256_ecdh(e.ctx(), k32, pt65, n, x32, status), "ECDHBatch");
+}
+
+namespace bitcoin {
+constexpr size_t SchnorrPublicKeySize = 32, SchnorrSignatureSize = 64;
+class SchnorrPublicKey {
+  public:
+    // secec/bitcoin/schnorr.go:257 NewSchnorrPublicKey (lift_x is validated here, as in Go)
+    static SchnorrPublicKey NewSchnorrPublicKey(const uint8_t *key, size_t len, Engine &e = Engine::Default()) {
+        if (len != SchnorrPublicKeySize) throw Error("secp256k1/secec/bitcoin: invalid public key");
+        uint8_t cp[33], out[65], st = 0;
+        cp[0] = 0x02;
+        std::memcpy(cp + 1, key, 32);
+        e.check(s256_point_decompress(e.ctx(), cp, 1, out, &st), "lift_x");
+        if (st != S256_ST_OK) throw Error("secp256k1/secec/bitcoin: failed to decompress public key");
+        SchnorrPublicKey k;
+        std::memcpy(k.x_.data(), key, 32);
+        return k;
+    }
+    // secec/bitcoin/schnorr.go:221 Verify
+    bool Verify(const uint8_t *msg, size_t msg_len, const uint8_t *sig, size_t sig_len, Engine &e = Engine::Default()) const {
+        if (sig_len != SchnorrSignatureSize) return false;
+        uint8_t ok = 0;
+        e.check(s256_schnorr_verify(e.ctx(), x_.data(), msg, msg_len, sig, 1, &ok), "SchnorrPublicKey.Verify");
+        return ok == 1;
+    }
+    const std::array<uint8_t, 32> &Bytes() const { return x_; }
+
+  private:
+    std::array<uint8_t, 32> x_{};
+};
+inline void SchnorrVerifyBatch(const uint8_t *pkx32, const uint8_t *msg, size_t msg_len, const uint8_t *sig64, size_t n,
+                               uint8_t *ok, Engine &e = Engine::Default()) {
+    e.check(s256_schnorr_verify(e.ctx(), pkx32, msg, msg_len, sig64, n, ok), "SchnorrVerifyBatch");
+}
+}  // namespace bitcoin
+}  // namespace secec
+}  // namespace secp256k1
