@@ -243,7 +243,7 @@ def main():
     if rank == 0:
         mac_item = pkg.mac32_per_item("ecdsa_verify")
         # dominant kernel: algorithmic MAC32 of one k_dsm launch / its mean duration
-        ladder_mac = _ladder_mac(pkg)
+        ladder_mac = pkg.mac32_per_item("k_dsm")
         achieved = ladder_mac * n / ((dsm_ms / max(dsm_launches, 1)) * 1e-3) if dsm_launches else None
         cpu = None
         if not args.skip_cpu_baseline:
@@ -287,15 +287,6 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
-
-
-def _ladder_mac(pkg):
-    """MAC32 per item executed by the k_dsm kernel alone (table + ladder + comb)."""
-    whole = pkg.mac32_per_item("double_scalar_mult_basepoint_vartime")
-    # subtract the parts of that entry point that run in other kernels: decode (3 M),
-    # GLV split (3 Z_n + 2*64), batched affine conversion (5 M + 270 M / 16)
-    M, ZN = 73.0, 139.0
-    return whole - 3 * M - (3 * ZN + 128) - (5 * M + 270 * M / 16)
 
 
 if __name__ == "__main__":

@@ -7,6 +7,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -131,6 +132,19 @@ __global__ void __launch_bounds__(S256_TPB, S256_DSM_MINB)
     if (i >= n) return;
     item_dsm(i, n, aff, u1, dig1, dig2, sfl, tbl, res, comb);
 }
+
+#ifndef S256_VM_MINB
+#define S256_VM_MINB 4
+#endif
+__global__ void __launch_bounds__(S256_TPB, S256_VM_MINB)
+    k_dsm_vm(size_t n, const apt *aff, const sc *u1, const int8_t *dig1, const int8_t *dig2, const uint8_t *sfl, pt *tbl,
+             pt *res, const apt *comb) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DevFrame<S256_TPB> f{threadIdx.x};
+    item_dsm_vm(f, i, n, aff, u1, dig1, dig2, sfl, tbl, res, comb);
+}
+constexpr size_t VM_SMEM_BYTES = (size_t)VM_SLOTS * 2 * S256_TPB * sizeof(uint4);
 
 __global__ void __launch_bounds__(S256_TPB) k_ecdsa_finish(size_t n, const pt *res, const uint8_t *sig64,
                                                            const uint8_t *pvalid, const uint8_t *sfl, uint8_t *ok) {
@@ -334,6 +348,7 @@ struct s256_ctx {
     size_t msm_cub_bytes = 0;
     // optional per-kernel timing of the dominant kernel (bench.py roofline)
     bool profiling = false;
+    bool use_reg_ladder = true;  // S256_LADDER=vm selects the frame-form ladder (A/B measurements)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dsm_events;
 };
 
@@ -445,6 +460,9 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
         total = (size_t)CT_NW * CT_SZ;
         LAUNCH(ctx, k_gen_table, grid_for(total), 0, ctx->stream, ctx->ct_tab, 4, total);
         s256_ct_kernels_init();
+        cudaFuncSetAttribute(k_dsm_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM_BYTES);
+        const char *lad = getenv("S256_LADDER");
+        ctx->use_reg_ladder = !(lad && std::string(lad) == "vm");  // register form is the faster one (profiles/)
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
             fprintf(stderr, "s256_init: table generation failed: %s\n", cudaGetErrorString(e));
@@ -469,8 +487,12 @@ static void enqueue_dsm(s256_ctx *ctx, size_t n, cudaStream_t s) {
         cudaEventCreate(&e1);
         cudaEventRecord(e0, s);
     }
-    LAUNCH(ctx, k_dsm, grid_for(n), 0, s, n, ctx->aff, ctx->u1, ctx->dig1, ctx->dig2, ctx->sfl, ctx->tbl, ctx->res,
-           ctx->comb);
+    if (ctx->use_reg_ladder)
+        LAUNCH(ctx, k_dsm, grid_for(n), 0, s, n, ctx->aff, ctx->u1, ctx->dig1, ctx->dig2, ctx->sfl, ctx->tbl, ctx->res,
+               ctx->comb);
+    else
+        LAUNCH(ctx, k_dsm_vm, grid_for(n), VM_SMEM_BYTES, s, n, ctx->aff, ctx->u1, ctx->dig1, ctx->dig2, ctx->sfl,
+               ctx->tbl, ctx->res, ctx->comb);
     if (ctx->profiling) {
         cudaEventRecord(e1, s);
         ctx->dsm_events.emplace_back(e0, e1);
@@ -1051,12 +1073,13 @@ extern "C" int s256_microbench_imad(s256_ctx *ctx, int iters, double *mac32_per_
     return s256_microbench_variant(ctx, MB_MADC_CHAIN, iters, mac32_per_s, ms);
 }
 
-// MAC32 per item actually executed (DESIGN.md "work per item"): F_p modmul = 73,
-// small-constant mul = 9, Z_n modmul = 139 (64 + 40 + 30 + 5).
+// MAC32 per item actually executed (DESIGN.md "work per item"): F_p mul = 73 (64 + 9),
+// F_p square = 45 (36 + 9), small-constant mul = 9, Z_n modmul = 139 (64 + 40 + 30 + 5).
 extern "C" double s256_mac32_per_item(const char *name) {
-    const double M = 73, SM = 9, ZN = 139;
-    const double dbl = 8 * M + SM, add = 12 * M + 2 * SM, mix = 11 * M + 2 * SM;
-    const double inv_fe = 270 * M, inv_sc = 330 * ZN;
+    const double M = 73, S = 45, SM = 9, ZN = 139;
+    const double dbl = 6 * M + 2 * S + SM, add = 12 * M + 2 * SM, mix = 11 * M + 2 * SM;
+    const double inv_fe = 255 * S + 15 * M, sqrt_fe = 254 * S + 13 * M + 2 * S + M, inv_sc = 330 * ZN;
+    const double oncurve = 2 * S + M;
     const double table = (DSM_TS / 2) * dbl + (DSM_TS / 2 - 1) * mix;
     const double ladder = (DSM_ND - 1) * DSM_W * dbl + 2 * DSM_ND * add + DSM_ND * M;
     const double comb = COMB_NW * mix;
@@ -1064,15 +1087,16 @@ extern "C" double s256_mac32_per_item(const char *name) {
     const double split = 3 * ZN + 2 * 64;
     const double affine = (3 + 2) * M + inv_fe / INV_K;
     std::string s(name ? name : "");
-    if (s == "ecdsa_verify") return 3 * M + (5 * ZN + inv_sc / INV_K + split) + dsm + 2 * M;
-    if (s == "ecdsa_recover") return 276 * M + (6 * ZN + inv_sc / INV_K + split) + dsm + affine;
-    if (s == "schnorr_verify") return 276 * M + (ZN + split) + dsm + affine;
-    if (s == "double_scalar_mult_basepoint_vartime") return 3 * M + split + dsm + affine;
+    if (s == "k_dsm") return dsm;  // the ladder kernel alone
+    if (s == "ecdsa_verify") return oncurve + (5 * ZN + inv_sc / INV_K + split) + dsm + 2 * M;
+    if (s == "ecdsa_recover") return sqrt_fe + (6 * ZN + inv_sc / INV_K + split) + dsm + affine;
+    if (s == "schnorr_verify") return sqrt_fe + (ZN + split) + dsm + affine;
+    if (s == "double_scalar_mult_basepoint_vartime") return oncurve + split + dsm + affine;
     if (s == "scalar_base_mult") return CT_NW * mix + affine;
     if (s == "scalar_mult" || s == "ecdh") {
         const double tab = (CTM_TS / 2) * dbl + (CTM_TS / 2 - 1) * mix;
         const double lad = (CTM_ND - 1) * CTM_W * dbl + 2 * CTM_ND * (add + M);
-        return 3 * M + split + tab + lad + affine;
+        return oncurve + split + tab + lad + affine;
     }
     return 0.0;
 }

@@ -297,6 +297,19 @@ S256_D void fe_mul_inline(fe &r, const fe &a, const fe &b) {
     fe_mul_wide(w, a.v, b.v);
     fe_reduce_wide(r, w);
 }
+#ifndef S256_NO_SQR
+}  // namespace s256
+#include "fe_sqr_gen.cuh"
+namespace s256 {
+// dedicated squaring: 36 + 9 MAC32 (tools/gen_fe_sqr.py)
+S256_D void fe_sqr_inline(fe &r, const fe &a) {
+    uint32_t w[16];
+    fe_sqr_wide(w, a.v);
+    fe_reduce_wide(r, w);
+}
+#else
+S256_D void fe_sqr_inline(fe &r, const fe &a) { fe_mul_inline(r, a, a); }
+#endif
 #ifndef S256_MUL_INLINE
 // Out of line on purpose: one ~2.4 KB body shared by every call site stays
 // resident in the instruction caches (the fully inlined ladder is ~140 KB of
@@ -307,11 +320,17 @@ static __device__ __noinline__ fe fe_mul_call(fe a, fe b) {
     fe_mul_inline(r, a, b);
     return r;
 }
+static __device__ __noinline__ fe fe_sqr_call(fe a) {
+    fe r;
+    fe_sqr_inline(r, a);
+    return r;
+}
 S256_D void fe_mul(fe &r, const fe &a, const fe &b) { r = fe_mul_call(a, b); }
+S256_D void fe_sqr(fe &r, const fe &a) { r = fe_sqr_call(a); }
 #else
 S256_D void fe_mul(fe &r, const fe &a, const fe &b) { fe_mul_inline(r, a, b); }
+S256_D void fe_sqr(fe &r, const fe &a) { fe_sqr_inline(r, a); }
 #endif
-S256_D void fe_sqr(fe &r, const fe &a) { fe_mul(r, a, a); }
 
 // r = a * k for a small constant k (< 2^16): 8 IMAD.WIDE + one fold
 S256_D void fe_mul_small(fe &r, const fe &a, uint32_t k) {
@@ -378,6 +397,8 @@ S256_HD void fe_mul(fe &r, const fe &a, const fe &b) {
     fe_reduce_wide_portable(r, w);
 }
 S256_HD void fe_sqr(fe &r, const fe &a) { fe_mul(r, a, a); }
+S256_HD void fe_mul_inline(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
+S256_HD void fe_sqr_inline(fe &r, const fe &a) { fe_mul(r, a, a); }
 S256_HD void fe_mul_small(fe &r, const fe &a, uint32_t k) {
     fe kk = fe_from_u32(k);
     fe_mul(r, a, kk);

@@ -17,6 +17,7 @@
 #include "point.cuh"
 #include "sc.cuh"
 #include "sha256.cuh"
+#include "vm.cuh"
 
 namespace s256 {
 
@@ -351,6 +352,76 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
         }
     }
     res[i] = acc;
+}
+
+// The same computation in frame form (vm.cuh): field elements live in per-thread
+// slots (shared memory on the device) and every operation is an out-of-line
+// worker taking slot addresses.  This is the version the product launches; the
+// register form above is kept for A/B measurements.
+template <class F>
+S256_HD void item_dsm_vm(F &f, size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1,
+                         const int8_t *dig2, const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
+    pt *T = tbl + i * (size_t)DSM_TS;
+    f.load_apt(AX, &aff[i]);  // the addend stays P for the whole table build
+    f.load_apt(SX, &aff[i]);
+    f.set(SZ, fe_one());
+    f.store_pt(&T[0], SX);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = 2; k <= DSM_TS; k += 2) {
+        f.load_pt(SX, &T[k / 2 - 1]);
+        vm_pt_double(f);
+        f.store_pt(&T[k - 1], SX);
+        if (k < DSM_TS) {
+            vm_pt_add_mixed(f);
+            f.store_pt(&T[k], SX);
+        }
+    }
+    uint32_t fl = sfl[i];
+    vm_set_identity(f);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int s = DSM_ND - 1; s >= 0; s--) {
+        if (s != DSM_ND - 1) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int k = 0; k < DSM_W; k++) vm_pt_double(f);
+        }
+        int da = dig1[(size_t)s * n + i];
+        int db = dig2[(size_t)s * n + i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int h = 0; h < 2; h++) {
+            int d = h ? db : da;
+            if (d != 0) {
+                uint32_t neg = (uint32_t)(d < 0) ^ ((fl >> (1 + h)) & 1u);
+                int mag = d < 0 ? -d : d;
+                f.load_pt(AX, &T[mag - 1]);
+                if (h) f.mul_beta(AX, AX);
+                if (neg) f.neg(AY, AY);
+                vm_pt_add(f);
+            }
+        }
+    }
+    sc u1 = u1s[i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int w = 0; w < COMB_NW; w++) {
+        int bit = w * COMB_WB;
+        uint32_t d = u1.v[bit >> 5] >> (bit & 31);
+        if ((bit & 31) + COMB_WB > 32 && (bit >> 5) + 1 < 8) d |= u1.v[(bit >> 5) + 1] << (32 - (bit & 31));
+        d &= (uint32_t)COMB_SZ - 1u;
+        if (d != 0) {
+            f.load_apt(AX, &comb[(size_t)w * COMB_SZ + d]);
+            vm_pt_add_mixed(f);
+        }
+    }
+    f.store_pt(&res[i], SX);
 }
 
 // ---------------------------------------------------------------------------

@@ -120,25 +120,32 @@ S256_HD void pt_add_mixed(pt &v, const pt &p, const fe &x2, const fe &y2) {
 }
 
 // v = 2p, complete (6 M + 2 S + 1 m3b + 9 a).
+#if defined(S256_DBL_INLINE) && S256_PTX
+#define S256_DMUL fe_mul_inline
+#define S256_DSQR fe_sqr_inline
+#else
+#define S256_DMUL fe_mul
+#define S256_DSQR fe_sqr
+#endif
 S256_HD void pt_double(pt &v, const pt &p) {
     fe t0, t1, t2, x3, y3, z3;
-    fe_sqr(t0, p.y);
+    S256_DSQR(t0, p.y);
     fe_add(z3, t0, t0);
     fe_add(z3, z3, z3);
     fe_add(z3, z3, z3);
-    fe_mul(t1, p.y, p.z);
-    fe_sqr(t2, p.z);
+    S256_DMUL(t1, p.y, p.z);
+    S256_DSQR(t2, p.z);
     fe_mul_small(t2, t2, S256_B3);
-    fe_mul(x3, t2, z3);
+    S256_DMUL(x3, t2, z3);
     fe_add(y3, t0, t2);
-    fe_mul(z3, t1, z3);
+    S256_DMUL(z3, t1, z3);
     fe_add(t1, t2, t2);
     fe_add(t2, t1, t2);
     fe_sub(t0, t0, t2);
-    fe_mul(y3, t0, y3);
+    S256_DMUL(y3, t0, y3);
     fe_add(y3, x3, y3);
-    fe_mul(t1, p.x, p.y);
-    fe_mul(x3, t0, t1);
+    S256_DMUL(t1, p.x, p.y);
+    S256_DMUL(x3, t0, t1);
     fe_add(x3, x3, x3);
     v.x = x3;
     v.y = y3;

@@ -8,6 +8,7 @@
 // is spent.  It is never linked into, or called by, the product library.
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "../../secp256k1-voi_b200/csrc/kernels.cuh"
@@ -59,9 +60,19 @@ static void run_dsm(scratch &s, size_t n) {
             if (d) ensure_comb_entry((uint32_t)w, d);
         }
     if (g_comb.empty()) ensure_comb_entry(0, 1);
-    for (size_t i = 0; i < n; i++)
-        item_dsm(i, n, s.aff.data(), s.u1.data(), s.dig1.data(), s.dig2.data(), s.sfl.data(), s.tbl.data(), s.res.data(),
-                 g_comb.data());
+    // the frame-form ladder is what the product launches; S256_SIM_LADDER=reg runs the register form
+    const char *lad = getenv("S256_SIM_LADDER");
+    bool reg = lad && std::string(lad) == "reg";
+    for (size_t i = 0; i < n; i++) {
+        if (reg) {
+            item_dsm(i, n, s.aff.data(), s.u1.data(), s.dig1.data(), s.dig2.data(), s.sfl.data(), s.tbl.data(),
+                     s.res.data(), g_comb.data());
+        } else {
+            HostFrame f;
+            item_dsm_vm(f, i, n, s.aff.data(), s.u1.data(), s.dig1.data(), s.dig2.data(), s.sfl.data(), s.tbl.data(),
+                        s.res.data(), g_comb.data());
+        }
+    }
 }
 static void run_finish(scratch &s, size_t n, bool use_pvalid, bool use_sfl, int mode, uint8_t *out, uint8_t *status,
                        const uint8_t *sig) {
