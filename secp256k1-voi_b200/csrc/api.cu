@@ -323,7 +323,7 @@ struct s256_ctx {
     int device = -1;
     size_t cap = 0;
     std::mutex mu;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
     std::string last_err;
     std::atomic<uint64_t> launches{0};
     // constant tables
@@ -348,6 +348,10 @@ struct s256_ctx {
     size_t msm_cub_bytes = 0;
     // optional per-kernel timing of the dominant kernel (bench.py roofline)
     bool profiling = false;
+    // sub-chunks per host-pointer call (S256_PIPE_PARTS).  Measured (scripts/e2e_parts.py): splitting does not
+    // pay -- the batched-inversion kernel is latency bound, so its cost multiplies with the part count.
+    int pipe_parts = 1;
+    cudaEvent_t ev_decode = nullptr;
     bool use_reg_ladder = true;  // S256_LADDER=vm selects the frame-form ladder (A/B measurements)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dsm_events;
 };
@@ -408,6 +412,8 @@ extern "C" void s256_free(s256_ctx *ctx) {
         for (void *p : ptrs)
             if (p) cudaFree(p);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+        if (ctx->ev_decode) cudaEventDestroy(ctx->ev_decode);
     }
     delete ctx;
 }
@@ -451,7 +457,10 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
     ctx->cap = max_batch ? max_batch : ((size_t)1 << 20);
     dev_guard g(device);
     int rc = ctx_alloc(ctx);
-    if (rc == S256_SUCCESS && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
+    if (rc == S256_SUCCESS && (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+                               cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess))
+        rc = S256_ERR_CUDA;
+    if (rc == S256_SUCCESS && cudaEventCreateWithFlags(&ctx->ev_decode, cudaEventDisableTiming) != cudaSuccess)
         rc = S256_ERR_CUDA;
     if (rc == S256_SUCCESS) {
         // generator tables (reference: package init, point_mul_table.go:75-100,147-160)
@@ -461,6 +470,8 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
         LAUNCH(ctx, k_gen_table, grid_for(total), 0, ctx->stream, ctx->ct_tab, 4, total);
         s256_ct_kernels_init();
         cudaFuncSetAttribute(k_dsm_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM_BYTES);
+        const char *pp = getenv("S256_PIPE_PARTS");
+        if (pp && atoi(pp) >= 1 && atoi(pp) <= 16) ctx->pipe_parts = atoi(pp);
         const char *lad = getenv("S256_LADDER");
         ctx->use_reg_ladder = !(lad && std::string(lad) == "vm");  // register form is the faster one (profiles/)
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -480,7 +491,36 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
 // ---------------------------------------------------------------------------
 // device-pointer pipelines (one chunk <= cap)
 // ---------------------------------------------------------------------------
-static void enqueue_dsm(s256_ctx *ctx, size_t n, cudaStream_t s) {
+// A window into the per-item scratch arrays starting at item `off`: sub-chunks of one call work on
+// disjoint windows, so they can be in flight on different streams at the same time.
+struct view {
+    apt *aff;
+    sc *u1;
+    int8_t *dig1, *dig2;
+    uint8_t *sfl, *pvalid, *cstat;
+    pt *tbl, *res;
+    uint8_t *in_a, *in_b, *in_c, *out, *st;
+};
+static view view_at(const s256_ctx *ctx, size_t off) {
+    view v;
+    v.aff = ctx->aff + off;
+    v.u1 = ctx->u1 + off;
+    v.dig1 = ctx->dig1 + (size_t)DSM_ND * off;  // [digit][item] inside the window
+    v.dig2 = ctx->dig2 + (size_t)DSM_ND * off;
+    v.sfl = ctx->sfl + off;
+    v.pvalid = ctx->pvalid + off;
+    v.cstat = ctx->cstat + off;
+    v.tbl = ctx->tbl + (size_t)DSM_TS * off;
+    v.res = ctx->res + off;
+    v.in_a = ctx->in_a + 65 * off;
+    v.in_b = ctx->in_b + 32 * off;
+    v.in_c = ctx->in_c + 65 * off;
+    v.out = ctx->out + 65 * off;
+    v.st = ctx->st + off;
+    return v;
+}
+
+static void enqueue_dsm(s256_ctx *ctx, const view &v, size_t n, cudaStream_t s) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (ctx->profiling) {
         cudaEventCreate(&e0);
@@ -488,11 +528,11 @@ static void enqueue_dsm(s256_ctx *ctx, size_t n, cudaStream_t s) {
         cudaEventRecord(e0, s);
     }
     if (ctx->use_reg_ladder)
-        LAUNCH(ctx, k_dsm, grid_for(n), 0, s, n, ctx->aff, ctx->u1, ctx->dig1, ctx->dig2, ctx->sfl, ctx->tbl, ctx->res,
+        LAUNCH(ctx, k_dsm, grid_for(n), 0, s, n, v.aff, v.u1, v.dig1, v.dig2, v.sfl, v.tbl, v.res,
                ctx->comb);
     else
-        LAUNCH(ctx, k_dsm_vm, grid_for(n), VM_SMEM_BYTES, s, n, ctx->aff, ctx->u1, ctx->dig1, ctx->dig2, ctx->sfl,
-               ctx->tbl, ctx->res, ctx->comb);
+        LAUNCH(ctx, k_dsm_vm, grid_for(n), VM_SMEM_BYTES, s, n, v.aff, v.u1, v.dig1, v.dig2, v.sfl,
+               v.tbl, v.res, ctx->comb);
     if (ctx->profiling) {
         cudaEventRecord(e1, s);
         ctx->dsm_events.emplace_back(e0, e1);
@@ -501,61 +541,69 @@ static void enqueue_dsm(s256_ctx *ctx, size_t n, cudaStream_t s) {
 constexpr int INV_K = 16;
 static inline unsigned grid_for_groups(size_t n, int k) { return grid_for((n + k - 1) / k); }
 
-static int chunk_ecdsa_verify(s256_ctx *ctx, const uint8_t *pk, const uint8_t *dg, const uint8_t *sig, uint32_t flags,
-                              size_t n, uint8_t *ok, cudaStream_t s) {
-    LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pk, n, ctx->aff, ctx->pvalid);
-    LAUNCH(ctx, (k_ecdsa_scalars<INV_K, false>), grid_for_groups(n, INV_K), 0, s, dg, sig, n, flags, ctx->u1, ctx->dig1,
-           ctx->dig2, ctx->sfl);
-    enqueue_dsm(ctx, n, s);
-    LAUNCH(ctx, k_ecdsa_finish, grid_for(n), 0, s, n, ctx->res, sig, ctx->pvalid, ctx->sfl, ok);
+// The scalar kernel needs digest + signature only and the decode kernel the public keys only: when the
+// caller passes a second stream, decode runs there (behind the key copy) and joins through an event.
+static int chunk_ecdsa_verify(s256_ctx *ctx, const view &v, const uint8_t *pk, const uint8_t *dg, const uint8_t *sig, uint32_t flags,
+                              size_t n, uint8_t *ok, cudaStream_t s, cudaStream_t s_decode = nullptr) {
+    LAUNCH(ctx, (k_ecdsa_scalars<INV_K, false>), grid_for_groups(n, INV_K), 0, s, dg, sig, n, flags, v.u1, v.dig1,
+           v.dig2, v.sfl);
+    if (s_decode && s_decode != s) {
+        LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s_decode, pk, n, v.aff, v.pvalid);
+        cudaEventRecord(ctx->ev_decode, s_decode);
+        cudaStreamWaitEvent(s, ctx->ev_decode, 0);
+    } else {
+        LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pk, n, v.aff, v.pvalid);
+    }
+    enqueue_dsm(ctx, v, n, s);
+    LAUNCH(ctx, k_ecdsa_finish, grid_for(n), 0, s, n, v.res, sig, v.pvalid, v.sfl, ok);
     return S256_SUCCESS;
 }
-static int chunk_ecdsa_recover(s256_ctx *ctx, const uint8_t *dg, const uint8_t *sig65, size_t n, uint8_t *pk65,
+static int chunk_ecdsa_recover(s256_ctx *ctx, const view &v, const uint8_t *dg, const uint8_t *sig65, size_t n, uint8_t *pk65,
                                uint8_t *status, cudaStream_t s) {
-    LAUNCH(ctx, k_decode_recover, grid_for(n), 0, s, sig65, n, ctx->aff, ctx->pvalid);
-    LAUNCH(ctx, (k_ecdsa_scalars<INV_K, true>), grid_for_groups(n, INV_K), 0, s, dg, sig65, n, 0u, ctx->u1, ctx->dig1,
-           ctx->dig2, ctx->sfl);
-    enqueue_dsm(ctx, n, s);
-    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, ctx->res, ctx->pvalid, ctx->sfl, ctx->cstat,
+    LAUNCH(ctx, k_decode_recover, grid_for(n), 0, s, sig65, n, v.aff, v.pvalid);
+    LAUNCH(ctx, (k_ecdsa_scalars<INV_K, true>), grid_for_groups(n, INV_K), 0, s, dg, sig65, n, 0u, v.u1, v.dig1,
+           v.dig2, v.sfl);
+    enqueue_dsm(ctx, v, n, s);
+    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, v.res, v.pvalid, v.sfl, v.cstat,
            3, pk65, status, (const uint8_t *)nullptr);
     return S256_SUCCESS;
 }
-static int chunk_schnorr_verify(s256_ctx *ctx, const uint8_t *pkx, const uint8_t *msg, size_t msg_len,
+static int chunk_schnorr_verify(s256_ctx *ctx, const view &v, const uint8_t *pkx, const uint8_t *msg, size_t msg_len,
                                 const uint8_t *sig, size_t n, uint8_t *ok, cudaStream_t s) {
-    LAUNCH(ctx, k_decode_xonly, grid_for(n), 0, s, pkx, n, ctx->aff, ctx->pvalid);
-    LAUNCH(ctx, k_schnorr_scalars, grid_for(n), 0, s, pkx, msg, msg_len, sig, n, ctx->u1, ctx->dig1, ctx->dig2,
-           ctx->sfl);
-    enqueue_dsm(ctx, n, s);
-    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, ctx->res, ctx->pvalid, ctx->sfl, ctx->cstat,
+    LAUNCH(ctx, k_decode_xonly, grid_for(n), 0, s, pkx, n, v.aff, v.pvalid);
+    LAUNCH(ctx, k_schnorr_scalars, grid_for(n), 0, s, pkx, msg, msg_len, sig, n, v.u1, v.dig1, v.dig2,
+           v.sfl);
+    enqueue_dsm(ctx, v, n, s);
+    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, v.res, v.pvalid, v.sfl, v.cstat,
            2, (uint8_t *)nullptr, ok, sig);
     return S256_SUCCESS;
 }
-static int chunk_dsm(s256_ctx *ctx, const uint8_t *u1, const uint8_t *u2, const uint8_t *pt65, size_t n,
+static int chunk_dsm(s256_ctx *ctx, const view &v, const uint8_t *u1, const uint8_t *u2, const uint8_t *pt65, size_t n,
                      uint8_t *out65, uint8_t *status, cudaStream_t s) {
-    LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pt65, n, ctx->aff, ctx->pvalid);
-    LAUNCH(ctx, k_plain_scalars, grid_for(n), 0, s, u1, u2, n, ctx->u1, ctx->dig1, ctx->dig2, ctx->sfl);
-    enqueue_dsm(ctx, n, s);
-    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, ctx->res, ctx->pvalid,
-           (const uint8_t *)nullptr, ctx->cstat, 0, out65, status, (const uint8_t *)nullptr);
+    LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pt65, n, v.aff, v.pvalid);
+    LAUNCH(ctx, k_plain_scalars, grid_for(n), 0, s, u1, u2, n, v.u1, v.dig1, v.dig2, v.sfl);
+    enqueue_dsm(ctx, v, n, s);
+    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, v.res, v.pvalid,
+           (const uint8_t *)nullptr, v.cstat, 0, out65, status, (const uint8_t *)nullptr);
     return S256_SUCCESS;
 }
-static int chunk_base_mult(s256_ctx *ctx, const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status,
+static int chunk_base_mult(s256_ctx *ctx, const view &v, const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status,
                            cudaStream_t s) {
-    s256_launch_base_mult_ct(k32, n, ctx->ct_tab, ctx->res, s);
+    s256_launch_base_mult_ct(k32, n, ctx->ct_tab, v.res, s);
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, ctx->res, (const uint8_t *)nullptr,
-           (const uint8_t *)nullptr, ctx->cstat, 0, out65, status, (const uint8_t *)nullptr);
+    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, v.res, (const uint8_t *)nullptr,
+           (const uint8_t *)nullptr, v.cstat, 0, out65, status, (const uint8_t *)nullptr);
     return S256_SUCCESS;
 }
 
 // Point.ScalarMult / PrivateKey.ECDH: decode (public) -> ct ladder -> batched affine
-static int chunk_scalar_mult(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int mode, uint8_t *out,
+static int chunk_scalar_mult(s256_ctx *ctx, const view &v, const uint8_t *k32, const uint8_t *pt65, size_t n, int mode, uint8_t *out,
                              uint8_t *status, cudaStream_t s) {
-    LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pt65, n, ctx->aff, ctx->pvalid);
-    s256_launch_scalar_mult_ct(n, ctx->aff, k32, ctx->tbl, ctx->res, s);
+    LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pt65, n, v.aff, v.pvalid);
+    s256_launch_scalar_mult_ct(n, v.aff, k32, v.tbl, v.res, s);
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, ctx->res, ctx->pvalid,
-           (const uint8_t *)nullptr, ctx->cstat, mode, out, status, (const uint8_t *)nullptr);
+    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, v.res, v.pvalid,
+           (const uint8_t *)nullptr, v.cstat, mode, out, status, (const uint8_t *)nullptr);
     return S256_SUCCESS;
 }
 
@@ -566,6 +614,30 @@ static int for_chunks(s256_ctx *ctx, size_t n, F body) {
         size_t c = n - off < ctx->cap ? n - off : ctx->cap;
         int rc = body(off, c);
         if (rc != S256_SUCCESS) return rc;
+    }
+    return S256_SUCCESS;
+}
+// Host-pointer calls: the chunk is cut into sub-chunks that alternate between two streams, each
+// doing its own H2D -> kernels -> D2H on a disjoint scratch window, so the copies of one sub-chunk
+// overlap the kernels of the other.  body(view, global offset, count, stream).
+template <typename F>
+static int pipelined(s256_ctx *ctx, size_t n, F body) {
+    const size_t min_sub = 65536;
+    for (size_t off = 0; off < n; off += ctx->cap) {
+        size_t c = n - off < ctx->cap ? n - off : ctx->cap;
+        size_t parts = c / min_sub;
+        if (parts > (size_t)ctx->pipe_parts) parts = (size_t)ctx->pipe_parts;
+        if (parts < 1) parts = 1;
+        size_t sub = (c + parts - 1) / parts;
+        sub = (sub + 127) & ~(size_t)127;
+        int k = 0;
+        for (size_t so = 0; so < c; so += sub, k++) {
+            size_t sc_ = c - so < sub ? c - so : sub;
+            int rc = body(view_at(ctx, so), off + so, sc_, (k & 1) ? ctx->stream2 : ctx->stream);
+            if (rc != S256_SUCCESS) return rc;
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream2));
     }
     return S256_SUCCESS;
 }
@@ -592,7 +664,7 @@ extern "C" int s256_ecdsa_verify_dev(s256_ctx *ctx, const uint8_t *pk, const uin
     if (n && (!pk || !dg || !sig || !ok)) return S256_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        return chunk_ecdsa_verify(ctx, pk + 65 * off, dg + 32 * off, sig + 64 * off, flags, c, ok + off, s);
+        return chunk_ecdsa_verify(ctx, view_at(ctx, 0), pk + 65 * off, dg + 32 * off, sig + 64 * off, flags, c, ok + off, s);
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
@@ -600,15 +672,16 @@ extern "C" int s256_ecdsa_verify(s256_ctx *ctx, const uint8_t *pk, const uint8_t
                                  uint32_t flags, size_t n, uint8_t *ok) {
     ENTER(ctx);
     if (n && (!pk || !dg || !sig || !ok)) return S256_ERR_ARG;
-    cudaStream_t s = ctx->stream;
-    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        CK(cudaMemcpyAsync(ctx->in_a, pk + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->in_b, dg + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->in_c, sig + 64 * off, 64 * c, cudaMemcpyHostToDevice, s));
-        int r = chunk_ecdsa_verify(ctx, ctx->in_a, ctx->in_b, ctx->in_c, flags, c, ctx->st, s);
+    int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t s) {
+        // digest + signature first: the batched inversion starts while the keys are still in flight
+        cudaStream_t s2 = (s == ctx->stream) ? ctx->stream2 : ctx->stream;
+        CK(cudaMemcpyAsync(v.in_b, dg + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(v.in_c, sig + 64 * off, 64 * c, cudaMemcpyHostToDevice, s));
+        bool split = ctx->pipe_parts == 1;
+        CK(cudaMemcpyAsync(v.in_a, pk + 65 * off, 65 * c, cudaMemcpyHostToDevice, split ? s2 : s));
+        int r = chunk_ecdsa_verify(ctx, v, v.in_a, v.in_b, v.in_c, flags, c, v.st, s, split ? s2 : s);
         if (r != S256_SUCCESS) return r;
-        CK(cudaMemcpyAsync(ok + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        CK(cudaMemcpyAsync(ok + off, v.st, c, cudaMemcpyDeviceToHost, s));
         return S256_SUCCESS;
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
@@ -620,7 +693,7 @@ extern "C" int s256_ecdsa_recover_dev(s256_ctx *ctx, const uint8_t *dg, const ui
     if (n && (!dg || !sig65 || !pk65 || !status)) return S256_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        return chunk_ecdsa_recover(ctx, dg + 32 * off, sig65 + 65 * off, c, pk65 + 65 * off, status + off, s);
+        return chunk_ecdsa_recover(ctx, view_at(ctx, 0), dg + 32 * off, sig65 + 65 * off, c, pk65 + 65 * off, status + off, s);
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
@@ -628,15 +701,13 @@ extern "C" int s256_ecdsa_recover(s256_ctx *ctx, const uint8_t *dg, const uint8_
                                   uint8_t *status) {
     ENTER(ctx);
     if (n && (!dg || !sig65 || !pk65 || !status)) return S256_ERR_ARG;
-    cudaStream_t s = ctx->stream;
-    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        CK(cudaMemcpyAsync(ctx->in_b, dg + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->in_c, sig65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
-        int r = chunk_ecdsa_recover(ctx, ctx->in_b, ctx->in_c, c, ctx->out, ctx->st, s);
+    int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t s) {
+        CK(cudaMemcpyAsync(v.in_b, dg + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(v.in_c, sig65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
+        int r = chunk_ecdsa_recover(ctx, v, v.in_b, v.in_c, c, v.out, v.st, s);
         if (r != S256_SUCCESS) return r;
-        CK(cudaMemcpyAsync(pk65 + 65 * off, ctx->out, 65 * c, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        CK(cudaMemcpyAsync(pk65 + 65 * off, v.out, 65 * c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + off, v.st, c, cudaMemcpyDeviceToHost, s));
         return S256_SUCCESS;
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
@@ -648,7 +719,7 @@ extern "C" int s256_schnorr_verify_dev(s256_ctx *ctx, const uint8_t *pkx, const 
     if (n && (!pkx || (!msg && msg_len) || !sig || !ok)) return S256_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        return chunk_schnorr_verify(ctx, pkx + 32 * off, msg + msg_len * off, msg_len, sig + 64 * off, c, ok + off, s);
+        return chunk_schnorr_verify(ctx, view_at(ctx, 0), pkx + 32 * off, msg + msg_len * off, msg_len, sig + 64 * off, c, ok + off, s);
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
@@ -669,7 +740,7 @@ extern "C" int s256_schnorr_verify(s256_ctx *ctx, const uint8_t *pkx, const uint
         CK(cudaMemcpyAsync(ctx->in_a, pkx + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
         if (msg_len) CK(cudaMemcpyAsync(ctx->in_b, msg + msg_len * off, msg_len * c, cudaMemcpyHostToDevice, s));
         CK(cudaMemcpyAsync(ctx->in_c, sig + 64 * off, 64 * c, cudaMemcpyHostToDevice, s));
-        int r = chunk_schnorr_verify(ctx, ctx->in_a, ctx->in_b, msg_len, ctx->in_c, c, ctx->st, s);
+        int r = chunk_schnorr_verify(ctx, view_at(ctx, 0), ctx->in_a, ctx->in_b, msg_len, ctx->in_c, c, ctx->st, s);
         if (r != S256_SUCCESS) return r;
         CK(cudaMemcpyAsync(ok + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -685,7 +756,7 @@ extern "C" int s256_double_scalar_mult_basepoint_vartime_dev(s256_ctx *ctx, cons
     if (n && (!u1 || !u2 || !pt65 || !out65 || !status)) return S256_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        return chunk_dsm(ctx, u1 + 32 * off, u2 + 32 * off, pt65 + 65 * off, c, out65 + 65 * off, status + off, s);
+        return chunk_dsm(ctx, view_at(ctx, 0), u1 + 32 * off, u2 + 32 * off, pt65 + 65 * off, c, out65 + 65 * off, status + off, s);
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
@@ -694,16 +765,14 @@ extern "C" int s256_double_scalar_mult_basepoint_vartime(s256_ctx *ctx, const ui
                                                          uint8_t *status) {
     ENTER(ctx);
     if (n && (!u1 || !u2 || !pt65 || !out65 || !status)) return S256_ERR_ARG;
-    cudaStream_t s = ctx->stream;
-    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        CK(cudaMemcpyAsync(ctx->in_a, pt65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->in_b, u1 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->in_c, u2 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
-        int r = chunk_dsm(ctx, ctx->in_b, ctx->in_c, ctx->in_a, c, ctx->out, ctx->st, s);
+    int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t s) {
+        CK(cudaMemcpyAsync(v.in_a, pt65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(v.in_b, u1 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(v.in_c, u2 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        int r = chunk_dsm(ctx, v, v.in_b, v.in_c, v.in_a, c, v.out, v.st, s);
         if (r != S256_SUCCESS) return r;
-        CK(cudaMemcpyAsync(out65 + 65 * off, ctx->out, 65 * c, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        CK(cudaMemcpyAsync(out65 + 65 * off, v.out, 65 * c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + off, v.st, c, cudaMemcpyDeviceToHost, s));
         return S256_SUCCESS;
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
@@ -715,21 +784,19 @@ extern "C" int s256_scalar_base_mult_dev(s256_ctx *ctx, const uint8_t *k32, size
     if (n && (!k32 || !out65 || !status)) return S256_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        return chunk_base_mult(ctx, k32 + 32 * off, c, out65 + 65 * off, status + off, s);
+        return chunk_base_mult(ctx, view_at(ctx, 0), k32 + 32 * off, c, out65 + 65 * off, status + off, s);
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
 extern "C" int s256_scalar_base_mult(s256_ctx *ctx, const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status) {
     ENTER(ctx);
     if (n && (!k32 || !out65 || !status)) return S256_ERR_ARG;
-    cudaStream_t s = ctx->stream;
-    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        CK(cudaMemcpyAsync(ctx->in_b, k32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
-        int r = chunk_base_mult(ctx, ctx->in_b, c, ctx->out, ctx->st, s);
+    int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t s) {
+        CK(cudaMemcpyAsync(v.in_b, k32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        int r = chunk_base_mult(ctx, v, v.in_b, c, v.out, v.st, s);
         if (r != S256_SUCCESS) return r;
-        CK(cudaMemcpyAsync(out65 + 65 * off, ctx->out, 65 * c, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        CK(cudaMemcpyAsync(out65 + 65 * off, v.out, 65 * c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + off, v.st, c, cudaMemcpyDeviceToHost, s));
         return S256_SUCCESS;
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
@@ -742,7 +809,7 @@ static int scalar_mult_common_dev(s256_ctx *ctx, const uint8_t *k32, const uint8
     cudaStream_t s = (cudaStream_t)stream;
     size_t w = mode == 1 ? 32 : 65;
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        return chunk_scalar_mult(ctx, k32 + 32 * off, pt65 + 65 * off, c, mode, out + w * off, status + off, s);
+        return chunk_scalar_mult(ctx, view_at(ctx, 0), k32 + 32 * off, pt65 + 65 * off, c, mode, out + w * off, status + off, s);
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
@@ -750,16 +817,14 @@ static int scalar_mult_common_host(s256_ctx *ctx, const uint8_t *k32, const uint
                                    uint8_t *out, uint8_t *status) {
     ENTER(ctx);
     if (n && (!k32 || !pt65 || !out || !status)) return S256_ERR_ARG;
-    cudaStream_t s = ctx->stream;
     size_t w = mode == 1 ? 32 : 65;
-    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        CK(cudaMemcpyAsync(ctx->in_a, pt65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->in_b, k32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
-        int r = chunk_scalar_mult(ctx, ctx->in_b, ctx->in_a, c, mode, ctx->out, ctx->st, s);
+    int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t s) {
+        CK(cudaMemcpyAsync(v.in_a, pt65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(v.in_b, k32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        int r = chunk_scalar_mult(ctx, v, v.in_b, v.in_a, c, mode, v.out, v.st, s);
         if (r != S256_SUCCESS) return r;
-        CK(cudaMemcpyAsync(out + w * off, ctx->out, w * c, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        CK(cudaMemcpyAsync(out + w * off, v.out, w * c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + off, v.st, c, cudaMemcpyDeviceToHost, s));
         return S256_SUCCESS;
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
