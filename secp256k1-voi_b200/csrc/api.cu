@@ -37,6 +37,14 @@ __global__ void __launch_bounds__(S256_TPB) k_gen_table(apt *out, int wb, size_t
     item_gen_multiple(a, w, d, wb);
     out[idx] = a;
 }
+// the signed constant-time table: out[w][j] = (j + 1) * 16^w * G, j = 0..7, w = 0..64
+__global__ void __launch_bounds__(S256_TPB) k_gen_ct_table(apt *out) {
+    uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint32_t)(CT_NW * CT_SZ)) return;
+    apt a;
+    item_gen_multiple(a, idx / CT_SZ, idx % CT_SZ + 1u, 4);
+    out[idx] = a;
+}
 
 __global__ void __launch_bounds__(S256_TPB) k_decode_uncompressed(const uint8_t *pt65, size_t n, apt *aff,
                                                                   uint8_t *pvalid) {
@@ -145,6 +153,31 @@ __global__ void __launch_bounds__(S256_TPB, S256_VM_MINB)
     item_dsm_vm(f, i, n, aff, u1, dig1, dig2, sfl, tbl, res, comb);
 }
 constexpr size_t VM_SMEM_BYTES = (size_t)VM_SLOTS * 2 * S256_TPB * sizeof(uint4);
+
+#ifndef S256_SM_MINB
+#define S256_SM_MINB 4
+#endif
+__global__ void __launch_bounds__(S256_TPB, S256_SM_MINB)
+    k_scalar_mult_ct(size_t n, const apt *aff, const uint8_t *k32, pt *tbl, pt *res) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#ifdef S256_CT_TABLE_GLOBAL
+    CtTableGlobal T{tbl + i * (size_t)DSM_TS};
+#else
+    CtTableShared<S256_TPB> T{threadIdx.x};
+#endif
+    item_scalar_mult_ct(i, aff, k32, T, res);
+}
+#ifdef S256_CT_TABLE_GLOBAL
+constexpr size_t CT_SMEM_BYTES = 0;
+#else
+constexpr size_t CT_SMEM_BYTES = (size_t)CTM_TS * 6 * S256_TPB * sizeof(uint4);
+#endif
+static void s256_launch_scalar_mult_ct(size_t n, const apt *aff, const uint8_t *k32, pt *tbl, pt *res, cudaStream_t s) {
+    if (n == 0) return;
+    k_scalar_mult_ct<<<(unsigned)((n + S256_TPB - 1) / S256_TPB), S256_TPB, CT_SMEM_BYTES, s>>>(n, aff, k32, tbl, res);
+}
+
 
 __global__ void __launch_bounds__(S256_TPB) k_ecdsa_finish(size_t n, const pt *res, const uint8_t *sig64,
                                                            const uint8_t *pvalid, const uint8_t *sfl, uint8_t *ok) {
@@ -466,9 +499,10 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
         // generator tables (reference: package init, point_mul_table.go:75-100,147-160)
         size_t total = (size_t)COMB_NW * COMB_SZ;
         LAUNCH(ctx, k_gen_table, grid_for(total), 0, ctx->stream, ctx->comb, COMB_WB, total);
-        total = (size_t)CT_NW * CT_SZ;
-        LAUNCH(ctx, k_gen_table, grid_for(total), 0, ctx->stream, ctx->ct_tab, 4, total);
+        LAUNCH(ctx, k_gen_ct_table, grid_for((size_t)CT_NW * CT_SZ), 0, ctx->stream, ctx->ct_tab);
         s256_ct_kernels_init();
+        if (CT_SMEM_BYTES)
+            cudaFuncSetAttribute(k_scalar_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM_BYTES);
         cudaFuncSetAttribute(k_dsm_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM_BYTES);
         const char *pp = getenv("S256_PIPE_PARTS");
         if (pp && atoi(pp) >= 1 && atoi(pp) <= 16) ctx->pipe_parts = atoi(pp);
@@ -1160,7 +1194,7 @@ extern "C" double s256_mac32_per_item(const char *name) {
     if (s == "scalar_base_mult") return CT_NW * mix + affine;
     if (s == "scalar_mult" || s == "ecdh") {
         const double tab = (CTM_TS / 2) * dbl + (CTM_TS / 2 - 1) * mix;
-        const double lad = (CTM_ND - 1) * CTM_W * dbl + 2 * CTM_ND * (add + M);
+        const double lad = (CTM_ND - 1) * CTM_W * dbl + 2 * CTM_ND * add + CTM_ND * M;
         return oncurve + split + tab + lad + affine;
     }
     return 0.0;

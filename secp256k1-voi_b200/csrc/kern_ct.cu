@@ -1,5 +1,7 @@
 // kern_ct.cu -- the constant-time kernels (secret scalars).
+#ifndef S256_BM_CALL
 #define S256_MUL_INLINE 1
+#endif
 #include "kernels.cuh"
 #include "launchers.h"
 
@@ -7,8 +9,9 @@ using namespace s256;
 #define S256_TPB 128
 
 #ifndef S256_BM_MINB
-#define S256_BM_MINB 3
+#define S256_BM_MINB 4
 #endif
+
 __global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
     k_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_g, pt *res) {
     extern __shared__ uint4 smem_raw[];
@@ -28,20 +31,6 @@ __global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
     }
 }
 
-
-#ifndef S256_SM_MINB
-#define S256_SM_MINB 3
-#endif
-__global__ void __launch_bounds__(S256_TPB, S256_SM_MINB)
-    k_scalar_mult_ct(size_t n, const apt *aff, const uint8_t *k32, pt *tbl, pt *res) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    item_scalar_mult_ct(i, aff, k32, tbl, res);
-}
-void s256_launch_scalar_mult_ct(size_t n, const apt *aff, const uint8_t *k32, pt *tbl, pt *res, cudaStream_t s) {
-    if (n == 0) return;
-    k_scalar_mult_ct<<<(unsigned)((n + S256_TPB - 1) / S256_TPB), S256_TPB, 0, s>>>(n, aff, k32, tbl, res);
-}
 
 void s256_ct_kernels_init() {
     cudaFuncSetAttribute(k_base_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -35,12 +35,13 @@ constexpr int DSM_TS = 1 << (DSM_W - 1);       // table entries 1..TS
 constexpr int COMB_WB = S256_COMB_WB;
 constexpr int COMB_NW = (256 + COMB_WB - 1) / COMB_WB;
 constexpr int COMB_SZ = 1 << COMB_WB;
-// constant-time fixed-base table: 64 windows of 4 bits, entries 1..15
-constexpr int CT_NW = 64;
-constexpr int CT_SZ = 16;
+// constant-time fixed-base table: signed 4-bit digits in [-7, 8] -> 64 windows + one carry window,
+// entries (j + 1) * 16^w * G for j = 0..7 (33 280 bytes: fits shared memory several times per SM)
+constexpr int CT_NW = 65;
+constexpr int CT_SZ = 8;
 // constant-time variable-base ladder (ScalarMult / ECDH): signed window
 #ifndef S256_CTW
-#define S256_CTW 4
+#define S256_CTW 3
 #endif
 constexpr int CTM_W = S256_CTW;
 constexpr int CTM_ND = glv_recode<CTM_W>::ND;
@@ -57,6 +58,7 @@ enum : uint8_t { SFL_VALID = 1, SFL_NEG1 = 2, SFL_NEG2 = 4 };
 // (internal/gentable/point_mul_table.go:16-49 produces the same multiples.)
 // ---------------------------------------------------------------------------
 S256_HD void item_gen_multiple(apt &out, uint32_t w, uint32_t d, int wb) {
+    // d * 2^(wb*w) * G; d may use up to wb + 1 bits (the signed ct table needs d = 2^(wb-1) = 8 with wb = 4)
     if (d == 0) {
         out.x = fe_zero();
         out.y = fe_zero();
@@ -65,7 +67,7 @@ S256_HD void item_gen_multiple(apt &out, uint32_t w, uint32_t d, int wb) {
     apt g = apt_generator();
     pt acc;
     pt_set_identity(acc);
-    for (int b = wb - 1; b >= 0; b--) {
+    for (int b = wb; b >= 0; b--) {
         pt_double(acc, acc);
         if ((d >> b) & 1u) pt_add_mixed(acc, acc, g.x, g.y);
     }
@@ -542,73 +544,105 @@ S256_HD void group_finish(size_t t, size_t stride, size_t n, const pt *res, cons
 }
 
 // ---------------------------------------------------------------------------
-// constant-time fixed-base multiplication (point_mul_table.go:168-194):
-// 64 four-bit windows, every window scans all 15 table entries with masks
-// (the GPU counterpart of point_mul_table_amd64.s:81-130) -- the table is
-// staged in shared memory and every lane reads the same address, so neither
-// the address stream nor the bank pattern depends on the scalar.  Digit 0 is
-// resolved by select after a dummy mixed add (point_mul_table.go:118-129).
+// constant-time fixed-base multiplication (point_mul_table.go:168-194): no
+// doublings, one mixed addition per 4-bit window.  The scalar is recoded
+// branch-free into signed digits d_w in [-7, 8] (65 windows), every window
+// scans all 8 table entries with masks (the GPU counterpart of
+// point_mul_table_amd64.s:81-130) -- the table is staged in shared memory and
+// every lane reads the same address, so neither the address stream nor the
+// bank pattern depends on the scalar -- the sign is applied by select, and
+// digit 0 is resolved by select after a dummy add (point_mul_table.go:118-129).
 // ---------------------------------------------------------------------------
-S256_HD void item_base_mult_ct(pt &acc, const sc &k, const apt *tab /* [64][16], entry 0 unused */) {
+S256_HD void item_base_mult_ct(pt &acc, const sc &k, const apt *tab /* [CT_NW][CT_SZ] */) {
     pt_set_identity(acc);
+    uint32_t carry = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int w = 0; w < CT_NW; w++) {
-        uint32_t d = (k.v[w >> 3] >> ((w & 7) * 4)) & 0xFu;
+        uint32_t v = (w < 64 ? (k.v[(w >> 3) & 7] >> ((w & 7) * 4)) & 0xFu : 0u) + carry;  // 0 .. 16
+        carry = (v + 7u) >> 4;                                                             // 1 iff v > 8
+        int32_t d = (int32_t)v - (int32_t)(carry << 4);                                    // -7 .. 8
+        uint32_t sign = (uint32_t)d >> 31;
+        uint32_t mag = (uint32_t)((d ^ -(int32_t)sign) + (int32_t)sign);
         apt sel;
         sel.x = fe_zero();
         sel.y = fe_zero();
         const apt *row = tab + w * CT_SZ;
 #if defined(__CUDA_ARCH__)
-#pragma unroll 3
+#pragma unroll 2
 #endif
-        for (uint32_t j = 1; j < CT_SZ; j++) {
-            uint32_t m = 0u - (uint32_t)(j == d);
-            apt e = row[j];
+        for (uint32_t j = 1; j <= (uint32_t)CT_SZ; j++) {
+            uint32_t m = 0u - (uint32_t)(j == mag);
+            apt e = row[j - 1];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
                 sel.x.v[q] |= e.x.v[q] & m;
                 sel.y.v[q] |= e.y.v[q] & m;
             }
         }
-        // d == 0 selected nothing: add a well-formed dummy (entry 1) and discard
-        uint32_t zero = (uint32_t)(d == 0);
-        apt e1 = row[1];
+        // mag == 0 selected nothing: add a well-formed dummy (entry 1) and discard the sum
+        uint32_t zero = (uint32_t)(mag == 0);
+        apt e1 = row[0];
         fe_cmov(sel.x, sel.x, e1.x, zero);
         fe_cmov(sel.y, sel.y, e1.y, zero);
+        fe_cneg(sel.y, sel.y, sign);
         pt sum;
         pt_add_mixed(sum, acc, sel.x, sel.y);
         pt_cmov(acc, sum, acc, zero);
     }
 }
 
-// ---------------------------------------------------------------------------
-// constant-time variable-base multiplication k*P (point_mul_glv.go:257-303),
-// the kernel behind Point.ScalarMult and PrivateKey.ECDH.  Same GLV split and
-// sign normalisation as the reference, with ConditionalNegate / lookups done
-// by masks: every step scans ALL table entries (the per-item table lives in
-// global memory at an address that depends only on the item index), the add is
-// always executed (digit 0 selects the identity, which the complete formula
-// absorbs), and nothing branches on k.  The point P is public.
-// ---------------------------------------------------------------------------
-S256_HD void item_scalar_mult_ct(size_t i, const apt *aff, const uint8_t *k32, pt *tbl, pt *res) {
-    pt *T = tbl + i * (size_t)DSM_TS;  // stride shared with the vartime ladder's scratch
+// Table storage policies for the ct ladder: per-item rows in global memory (host simulation, or
+// when shared memory is not used) and per-thread columns in shared memory ([entry][limb group][thread],
+// LDS.128 / STS.128 conflict-free).  Either way the address stream depends only on public values.
+struct CtTableGlobal {
+    pt *T;
+    S256_HD void store(int j, const pt &p) const { T[j] = p; }
+    S256_HD pt load(int j) const { return T[j]; }
+};
+#if defined(__CUDACC__)
+template <int TPB>
+struct CtTableShared {
+    uint32_t t;
+    __device__ __forceinline__ void store(int j, const pt &p) const {
+        extern __shared__ uint4 ct_smem[];
+        const uint32_t *w = p.x.v;  // x, y, z are contiguous: 24 words
+#pragma unroll
+        for (int g = 0; g < 6; g++)
+            ct_smem[(uint32_t)(j * 6 + g) * TPB + t] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+    }
+    __device__ __forceinline__ pt load(int j) const {
+        extern __shared__ uint4 ct_smem[];
+        pt p;
+        uint32_t *w = p.x.v;
+#pragma unroll
+        for (int g = 0; g < 6; g++) {
+            uint4 q = ct_smem[(uint32_t)(j * 6 + g) * TPB + t];
+            w[4 * g] = q.x; w[4 * g + 1] = q.y; w[4 * g + 2] = q.z; w[4 * g + 3] = q.w;
+        }
+        return p;
+    }
+};
+#endif
+
+template <class TAB>
+S256_HD void item_scalar_mult_ct(size_t i, const apt *aff, const uint8_t *k32, const TAB &T, pt *res) {
     {
         apt P = aff[i];
         pt cur;
         pt_from_affine(cur, P);
-        T[0] = cur;
+        T.store(0, cur);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
         for (int k = 2; k <= CTM_TS; k += 2) {
-            pt h = T[k / 2 - 1];
+            pt h = T.load(k / 2 - 1);
             pt_double(cur, h);
-            T[k - 1] = cur;
+            T.store(k - 1, cur);
             if (k < CTM_TS) {
                 pt_add_mixed(cur, cur, P.x, P.y);
-                T[k] = cur;
+                T.store(k, cur);
             }
         }
     }
@@ -637,7 +671,7 @@ S256_HD void item_scalar_mult_ct(size_t i, const apt *aff, const uint8_t *k32, p
 #endif
         for (int h = 0; h < 2; h++) {
             int32_t d = h ? (int32_t)d2[s] : (int32_t)d1[s];
-            uint32_t sign = (uint32_t)d >> 31;                       // 1 iff d < 0
+            uint32_t sign = (uint32_t)d >> 31;                                // 1 iff d < 0
             uint32_t mag = (uint32_t)((d ^ -(int32_t)sign) + (int32_t)sign);  // |d|, branch-free
             uint32_t neg = sign ^ (h ? neg2 : neg1);
             pt q;
@@ -649,7 +683,7 @@ S256_HD void item_scalar_mult_ct(size_t i, const apt *aff, const uint8_t *k32, p
 #endif
             for (uint32_t j = 1; j <= (uint32_t)CTM_TS; j++) {
                 uint32_t m = 0u - (uint32_t)(j == mag);
-                pt e = T[j - 1];
+                pt e = T.load((int)j - 1);
 #pragma unroll
                 for (int w = 0; w < 8; w++) {
                     q.x.v[w] |= e.x.v[w] & m;
@@ -658,9 +692,7 @@ S256_HD void item_scalar_mult_ct(size_t i, const apt *aff, const uint8_t *k32, p
                 }
             }
             q.y.v[0] |= (uint32_t)(mag == 0);  // digit 0 -> (0 : 1 : 0)
-            fe bx;
-            fe_mul(bx, q.x, beta);
-            fe_cmov(q.x, q.x, bx, (uint32_t)h);
+            if (h) fe_mul(q.x, q.x, beta);     // h is the (public) half index, not a secret
             fe_cneg(q.y, q.y, neg);
             pt_add(acc, acc, q);
         }

@@ -11,5 +11,3 @@
 
 void s256_ct_kernels_init();
 void s256_launch_base_mult_ct(const uint8_t *k32, size_t n, const s256::apt *tab_g, s256::pt *res, cudaStream_t s);
-void s256_launch_scalar_mult_ct(size_t n, const s256::apt *aff, const uint8_t *k32, s256::pt *tbl, s256::pt *res,
-                                cudaStream_t s);

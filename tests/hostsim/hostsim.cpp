@@ -23,7 +23,8 @@ static constexpr int K = 16;
 static void ensure_tables() {
     if (!g_ct.empty()) return;
     g_ct.resize((size_t)CT_NW * CT_SZ);
-    for (size_t idx = 0; idx < g_ct.size(); idx++) item_gen_multiple(g_ct[idx], (uint32_t)(idx >> 4), (uint32_t)(idx & 15), 4);
+    for (size_t idx = 0; idx < g_ct.size(); idx++)
+        item_gen_multiple(g_ct[idx], (uint32_t)(idx / CT_SZ), (uint32_t)(idx % CT_SZ) + 1u, 4);
 }
 // The comb has 2^20 entries; generating it with the bit-serial routine is too
 // slow on one CPU core, so the simulation fills only the entries a batch uses.
@@ -131,7 +132,10 @@ EXPORT void sim_scalar_base_mult(const uint8_t *k32, size_t n, uint8_t *out65, u
 EXPORT void sim_scalar_mult(const uint8_t *k32, const uint8_t *pt65, size_t n, int mode, uint8_t *out, uint8_t *status) {
     scratch s(n);
     for (size_t i = 0; i < n; i++) s.pvalid[i] = item_decode_uncompressed(s.aff[i], pt65 + 65 * i);
-    for (size_t i = 0; i < n; i++) item_scalar_mult_ct(i, s.aff.data(), k32, s.tbl.data(), s.res.data());
+    for (size_t i = 0; i < n; i++) {
+        CtTableGlobal T{s.tbl.data() + i * (size_t)DSM_TS};
+        item_scalar_mult_ct(i, s.aff.data(), k32, T, s.res.data());
+    }
     run_finish(s, n, true, false, mode, out, status, nullptr);
 }
 EXPORT void sim_point_decompress(const uint8_t *pt33, size_t n, uint8_t *out65, uint8_t *status) {
@@ -160,7 +164,10 @@ EXPORT void sim_msm(const uint8_t *k32, const uint8_t *pt65, size_t n, int varti
     pt acc;
     pt_set_identity(acc);
     if (n && (!vartime || n < 32) && force_c == 0) {
-        for (size_t i = 0; i < n; i++) item_scalar_mult_ct(i, s.aff.data(), k32, s.tbl.data(), s.res.data());
+        for (size_t i = 0; i < n; i++) {
+            CtTableGlobal T{s.tbl.data() + i * (size_t)DSM_TS};
+            item_scalar_mult_ct(i, s.aff.data(), k32, T, s.res.data());
+        }
         for (size_t i = 0; i < n; i++) pt_add(acc, acc, s.res[i]);
     } else if (n) {
         msm_plan pl = msm_make_plan(n);
