@@ -222,25 +222,36 @@ __global__ void __launch_bounds__(S256_TPB) k_msm_digits(const uint8_t *k32, siz
         }
     }
 }
-__global__ void __launch_bounds__(S256_TPB) k_msm_buckets(uint32_t total, const uint32_t *offsets,
-                                                          const uint32_t *entries, const apt *aff, pt *buckets) {
+// nsl[b] = slices of bucket b (counts -> slice counts), then scanned into sl_off
+__global__ void __launch_bounds__(S256_TPB) k_msm_slice_counts(uint32_t total, const uint32_t *counts, uint32_t *nsl) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= total) return;
-    pt s;
-    msm_bucket_sum(s, entries, offsets[b], offsets[b + 1], aff);
-    buckets[b] = s;
+    if (b < total) nsl[b] = msm_slices_of(counts[b]);
+    if (b == total) nsl[b] = 0;
 }
-#define S256_MSM_WT 256
-__global__ void __launch_bounds__(S256_MSM_WT) k_msm_windows(msm_plan plan, const pt *buckets, pt *win) {
+__global__ void __launch_bounds__(S256_TPB) k_msm_slices(uint32_t max_slices, uint32_t total, const uint32_t *sl_off,
+                                                         const uint32_t *offsets, const uint32_t *entries,
+                                                         const apt *aff, pt *slice_sum) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= max_slices || s >= sl_off[total]) return;
+    uint32_t st, en;
+    msm_slice_range(st, en, s, sl_off, offsets, total);
+    pt r;
+    msm_bucket_sum(r, entries, st, en, aff);
+    slice_sum[s] = r;
+}
+#define S256_MSM_WT 128
+// grid (blocks per window, nwin): every thread reduces MSM_SEG buckets, the CTA folds its threads
+__global__ void __launch_bounds__(S256_MSM_WT) k_msm_windows(msm_plan plan, const pt *slice_sum, const uint32_t *sl_off,
+                                                             pt *winpart, int parts) {
     __shared__ pt sh[S256_MSM_WT];
-    int w = blockIdx.x, t = threadIdx.x;
+    int w = blockIdx.y, t = threadIdx.x;
     int nbw = msm_window_buckets(plan, w);
-    int per = (nbw + S256_MSM_WT - 1) / S256_MSM_WT;
-    int lo = t * per, hi = lo + per;
+    int seg = msm_seg_for(nbw);
+    int lo = (blockIdx.x * S256_MSM_WT + t) * seg, hi = lo + seg;
     if (hi > nbw) hi = nbw;
     pt s;
     if (lo < hi)
-        msm_segment(s, buckets + (size_t)w * plan.nb, lo, hi);
+        msm_segment(s, slice_sum, sl_off, (uint32_t)w * (uint32_t)plan.nb, lo, hi);
     else
         pt_set_identity(s);
     sh[t] = s;
@@ -253,13 +264,24 @@ __global__ void __launch_bounds__(S256_MSM_WT) k_msm_windows(msm_plan plan, cons
         }
         __syncthreads();
     }
-    if (t == 0) win[w] = sh[0];
+    if (t == 0) winpart[w * parts + blockIdx.x] = sh[0];
 }
-// acc (device, projective) += Horner(win); first = overwrite
-__global__ void k_msm_final(msm_plan plan, const pt *win, pt *acc, int first) {
+// win[w * parts] = sum of the `parts` CTA partials of window w (one thread per window)
+__global__ void k_msm_fold(int nwin, pt *winpart, int parts) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwin) return;
+    pt acc = winpart[w * parts];
+    for (int q = 1; q < parts; q++) {
+        pt t = winpart[w * parts + q];
+        pt_add(acc, acc, t);
+    }
+    winpart[w * parts] = acc;
+}
+// acc (device, projective) += Horner(window partials); first = overwrite
+__global__ void k_msm_final(msm_plan plan, const pt *winpart, int parts, pt *acc, int first) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     pt r;
-    msm_horner(r, win, plan);
+    msm_horner(r, winpart, plan, 1, parts);
     if (!first) {
         pt a = *acc;
         pt_add(r, r, a);
@@ -376,6 +398,8 @@ struct s256_ctx {
     size_t msm_cap = 0;
     uint32_t *msm_counts = nullptr, *msm_offsets = nullptr, *msm_cursor = nullptr, *msm_entries = nullptr;
     uint32_t *msm_flag = nullptr;
+    uint32_t *msm_nsl = nullptr, *msm_sloff = nullptr;
+    size_t msm_max_slices = 0;
     pt *msm_buckets = nullptr, *msm_win = nullptr, *msm_acc = nullptr, *msm_tmp = nullptr;
     void *msm_cub = nullptr;
     size_t msm_cub_bytes = 0;
@@ -441,7 +465,7 @@ extern "C" void s256_free(s256_ctx *ctx) {
         void *ptrs[] = {ctx->comb, ctx->ct_tab, ctx->aff, ctx->u1,   ctx->dig1, ctx->dig2, ctx->sfl, ctx->pvalid,
                         ctx->cstat, ctx->tbl,   ctx->res, ctx->in_a, ctx->in_b, ctx->in_c, ctx->out, ctx->st,
                         ctx->sink, ctx->msm_counts, ctx->msm_offsets, ctx->msm_cursor, ctx->msm_entries, ctx->msm_flag,
-                        ctx->msm_buckets, ctx->msm_win, ctx->msm_acc, ctx->msm_tmp, ctx->msm_cub};
+                        ctx->msm_buckets, ctx->msm_win, ctx->msm_acc, ctx->msm_tmp, ctx->msm_cub, ctx->msm_nsl, ctx->msm_sloff};
         for (void *p : ptrs)
             if (p) cudaFree(p);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -573,6 +597,7 @@ static void enqueue_dsm(s256_ctx *ctx, const view &v, size_t n, cudaStream_t s) 
     }
 }
 constexpr int INV_K = 16;
+constexpr int MSM_MAX_PARTS = 16;  // (2^16 buckets) / (128 threads * 32 buckets)
 static inline unsigned grid_for_groups(size_t n, int k) { return grid_for((n + k - 1) / k); }
 
 // The scalar kernel needs digest + signature only and the decode kernel the public keys only: when the
@@ -916,8 +941,12 @@ static int msm_ensure(s256_ctx *ctx) {
     CK(cudaMalloc(&ctx->msm_offsets, (total + 1) * 4));
     CK(cudaMalloc(&ctx->msm_cursor, (total + 1) * 4));
     CK(cudaMalloc(&ctx->msm_entries, msm_entries_capacity(ctx) * 4));
-    CK(cudaMalloc(&ctx->msm_buckets, total * sizeof(pt)));
-    CK(cudaMalloc(&ctx->msm_win, MSM_MAX_WIN * sizeof(pt)));
+    // slice sums: one per bucket at least, plus one per MSM_SLICE entries
+    ctx->msm_max_slices = total + msm_entries_capacity(ctx) / MSM_SLICE + 1;
+    CK(cudaMalloc(&ctx->msm_buckets, ctx->msm_max_slices * sizeof(pt)));
+    CK(cudaMalloc(&ctx->msm_nsl, (total + 1) * 4));
+    CK(cudaMalloc(&ctx->msm_sloff, (total + 1) * 4));
+    CK(cudaMalloc(&ctx->msm_win, (size_t)MSM_MAX_WIN * MSM_MAX_PARTS * sizeof(pt)));
     CK(cudaMalloc(&ctx->msm_acc, sizeof(pt)));
     CK(cudaMalloc(&ctx->msm_tmp, 4096 * sizeof(pt)));
     CK(cudaMalloc(&ctx->msm_flag, 4));
@@ -962,10 +991,22 @@ static int chunk_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, siz
     CK(cub::DeviceScan::ExclusiveSum(ctx->msm_cub, bytes, ctx->msm_counts, ctx->msm_offsets, (int)(total + 1), s));
     CK(cudaMemcpyAsync(ctx->msm_cursor, ctx->msm_offsets, (size_t)total * 4, cudaMemcpyDeviceToDevice, s));
     LAUNCH(ctx, k_msm_digits<true>, grid_for(n), 0, s, k32, n, pl, ctx->msm_counts, ctx->msm_cursor, ctx->msm_entries);
-    LAUNCH(ctx, k_msm_buckets, grid_for(total), 0, s, total, ctx->msm_offsets, ctx->msm_entries, ctx->aff,
-           ctx->msm_buckets);
-    k_msm_windows<<<pl.nwin, S256_MSM_WT, 0, s>>>(pl, ctx->msm_buckets, ctx->msm_win);
-    k_msm_final<<<1, 1, 0, s>>>(pl, ctx->msm_win, ctx->msm_acc, first);
+    // buckets -> slices of <= MSM_SLICE entries
+    LAUNCH(ctx, k_msm_slice_counts, grid_for((size_t)total + 1), 0, s, total, ctx->msm_counts, ctx->msm_nsl);
+    CK(cub::DeviceScan::ExclusiveSum(ctx->msm_cub, bytes, ctx->msm_nsl, ctx->msm_sloff, (int)(total + 1), s));
+    size_t max_slices = (size_t)total + ((size_t)pl.nwin * n) / MSM_SLICE + 1;
+    if (max_slices > ctx->msm_max_slices) max_slices = ctx->msm_max_slices;
+    LAUNCH(ctx, k_msm_slices, grid_for(max_slices), 0, s, (uint32_t)max_slices, total, ctx->msm_sloff, ctx->msm_offsets,
+           ctx->msm_entries, ctx->aff, ctx->msm_buckets);
+    int parts = 1;
+    for (int w = 0; w < pl.nwin; w += pl.nwin - 1 > 0 ? pl.nwin - 1 : 1) {  // first and top window cover both sizes
+        int nbw = msm_window_buckets(pl, w);
+        int p = (nbw + S256_MSM_WT * msm_seg_for(nbw) - 1) / (S256_MSM_WT * msm_seg_for(nbw));
+        if (p > parts) parts = p;
+    }
+    k_msm_windows<<<dim3(parts, pl.nwin), S256_MSM_WT, 0, s>>>(pl, ctx->msm_buckets, ctx->msm_sloff, ctx->msm_win, parts);
+    k_msm_fold<<<1, 64, 0, s>>>(pl.nwin, ctx->msm_win, parts);
+    k_msm_final<<<1, 1, 0, s>>>(pl, ctx->msm_win, parts, ctx->msm_acc, first);
     ctx->launches.fetch_add(3, std::memory_order_relaxed);
     return S256_SUCCESS;
 }

@@ -11,9 +11,12 @@
 //   sort   : counting sort of (window, |d|) keys: count (atomicAdd) -> exclusive
 //            scan -> scatter; the order inside a bucket is arbitrary, which is
 //            harmless because only the group element matters
-//   buckets: one thread per bucket, mixed complete additions (inputs are affine)
-//   windows: R_w = sum_j j * B_{w,j} by segmented running sums, one CTA per window
-//   final  : Horner over the windows, c doublings between additions
+//   slices : buckets are cut into slices of <= MSM_SLICE entries; one thread per slice does
+//            mixed complete additions (inputs are affine).  Slicing bounds the serial work of
+//            dense buckets (e.g. the partial top window) and of skewed scalar distributions
+//   windows: R_w = sum_j j * B_{w,j} by segmented running sums (MSM_SEG buckets per thread,
+//            many CTAs per window), a bucket being the sum of its slices
+//   final  : per-window partials are folded, then Horner over the windows (c doublings each)
 #pragma once
 #include "fe.cuh"
 #include "point.cuh"
@@ -22,6 +25,15 @@
 namespace s256 {
 
 constexpr int MSM_MAX_C = 16;
+constexpr int MSM_SLICE = 64;   // entries per slice
+constexpr int MSM_SEG = 32;     // most buckets one thread reduces in the window stage
+// buckets per thread for a window of nbw buckets: aim for >= 512 threads per window
+S256_HD int msm_seg_for(int nbw) {
+    int seg = nbw >> 9;
+    if (seg < 2) seg = 2;
+    if (seg > MSM_SEG) seg = MSM_SEG;
+    return seg;
+}
 constexpr int MSM_MAX_WIN = 64;  // c = 4 -> 64 windows
 
 // Windows 0 .. nwin-2 use signed digits (2^(c-1) buckets each).  The top window keeps
@@ -73,7 +85,7 @@ S256_HD void msm_digits(int32_t *d, const sc &k, const msm_plan &p) {
     }
 }
 
-// bucket accumulation: entries hold (point index << 1) | negate
+// slice / bucket accumulation: entries hold (point index << 1) | negate
 S256_HD void msm_bucket_sum(pt &out, const uint32_t *entries, uint32_t start, uint32_t end, const apt *aff) {
     pt acc;
     pt_set_identity(acc);
@@ -86,35 +98,71 @@ S256_HD void msm_bucket_sum(pt &out, const uint32_t *entries, uint32_t start, ui
     out = acc;
 }
 
-// sum_{j in (lo, hi]} j * B_j, where B_j = buckets[j - 1]
-S256_HD void msm_segment(pt &out, const pt *buckets, int lo, int hi) {
+// slices of bucket b: max(1, ceil(count / MSM_SLICE))
+S256_HD uint32_t msm_slices_of(uint32_t count) { return count == 0 ? 1u : (count + MSM_SLICE - 1) / MSM_SLICE; }
+
+// bucket b = sum of its slices (almost always exactly one)
+S256_HD void msm_bucket_from_slices(pt &out, const pt *slice_sum, const uint32_t *sl_off, uint32_t b) {
+    uint32_t s0 = sl_off[b], s1 = sl_off[b + 1];
+    out = slice_sum[s0];
+    for (uint32_t s = s0 + 1; s < s1; s++) {
+        pt q = slice_sum[s];
+        pt_add(out, out, q);
+    }
+}
+
+// sum_{j in (lo, hi]} j * B_j for the window whose first bucket is `base`
+S256_HD void msm_segment(pt &out, const pt *slice_sum, const uint32_t *sl_off, uint32_t base, int lo, int hi) {
     pt run, sum;
     pt_set_identity(run);
     pt_set_identity(sum);
     for (int j = hi; j > lo; j--) {
-        pt b = buckets[j - 1];
+        pt b;
+        msm_bucket_from_slices(b, slice_sum, sl_off, base + (uint32_t)(j - 1));
         pt_add(run, run, b);
         pt_add(sum, sum, run);
     }
-    // sum = sum_j (j - lo) B_j ; add lo * run
-    pt m;
-    pt_set_identity(m);
-    for (int b = 16; b >= 0; b--) {
-        pt_double(m, m);
-        if ((lo >> b) & 1) pt_add(m, m, run);
+    // sum = sum_j (j - lo) B_j ; add lo * run (double-and-add from the top set bit of lo)
+    if (lo > 0) {
+        int top = 0;
+        while ((lo >> (top + 1)) != 0) top++;
+        pt m = run;
+        for (int b = top - 1; b >= 0; b--) {
+            pt_double(m, m);
+            if ((lo >> b) & 1) pt_add(m, m, run);
+        }
+        pt_add(sum, sum, m);
     }
-    pt_add(out, sum, m);
+    out = sum;
 }
 
-// Horner over window results, highest first
-S256_HD void msm_horner(pt &out, const pt *win, const msm_plan &p) {
-    pt acc = win[p.nwin - 1];
-    for (int w = p.nwin - 2; w >= 0; w--) {
-        for (int k = 0; k < p.c; k++) pt_double(acc, acc);
-        pt t = win[w];
-        pt_add(acc, acc, t);
+// Horner over window results, highest first; window w is the sum of `parts` partials at win[w * stride ..]
+S256_HD void msm_horner(pt &out, const pt *win, const msm_plan &p, int parts, int stride) {
+    pt acc;
+    pt_set_identity(acc);
+    for (int w = p.nwin - 1; w >= 0; w--) {
+        if (w != p.nwin - 1)
+            for (int k = 0; k < p.c; k++) pt_double(acc, acc);
+        for (int q = 0; q < parts; q++) {
+            pt t = win[w * stride + q];
+            pt_add(acc, acc, t);
+        }
     }
     out = acc;
+}
+// which slice range does slice s cover?  binary search for the bucket, then the entry range
+S256_HD void msm_slice_range(uint32_t &start, uint32_t &end, uint32_t s, const uint32_t *sl_off, const uint32_t *offsets,
+                             uint32_t total_buckets) {
+    uint32_t lo = 0, hi = total_buckets;  // invariant: sl_off[lo] <= s < sl_off[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (sl_off[mid] <= s) lo = mid; else hi = mid;
+    }
+    uint32_t k = s - sl_off[lo];
+    start = offsets[lo] + k * MSM_SLICE;
+    end = start + MSM_SLICE;
+    if (end > offsets[lo + 1]) end = offsets[lo + 1];
+    if (start > end) start = end;
 }
 
 // projective point <-> 96-byte big-endian X || Y || Z (the cross-GPU partial)

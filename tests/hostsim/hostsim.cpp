@@ -192,24 +192,42 @@ EXPORT void sim_msm(const uint8_t *k32, const uint8_t *pt65, size_t n, int varti
                 int32_t d = dig[(size_t)w * n + i];
                 if (d) entries[cursor[(size_t)w * pl.nb + (size_t)(std::abs(d) - 1)]++] = ((uint32_t)i << 1) | (uint32_t)(d < 0);
             }
-        std::vector<pt> buckets(total), win(pl.nwin);
-        for (size_t b = 0; b < total; b++) msm_bucket_sum(buckets[b], entries.data(), offsets[b], offsets[b + 1], s.aff.data());
-        const int T = 256;
-        for (int w = 0; w < pl.nwin; w++) {
-            std::vector<pt> sh(T);
-            int nbw = msm_window_buckets(pl, w);
-            int per = (nbw + T - 1) / T;
-            for (int t = 0; t < T; t++) {
-                int lo = t * per, hi = lo + per;
-                if (hi > nbw) hi = nbw;
-                if (lo < hi) msm_segment(sh[t], buckets.data() + (size_t)w * pl.nb, lo, hi);
-                else pt_set_identity(sh[t]);
-            }
-            for (int stride = T / 2; stride >= 1; stride >>= 1)
-                for (int t = 0; t < stride; t++) pt_add(sh[t], sh[t], sh[t + stride]);
-            win[w] = sh[0];
+        // slices of <= MSM_SLICE entries, exactly as the kernels cut them
+        std::vector<uint32_t> sl_off(total + 1, 0);
+        for (size_t b = 0; b < total; b++) sl_off[b + 1] = sl_off[b] + msm_slices_of(counts[b]);
+        std::vector<pt> slice_sum(sl_off[total]);
+        for (uint32_t sidx = 0; sidx < sl_off[total]; sidx++) {
+            uint32_t st, en;
+            msm_slice_range(st, en, sidx, sl_off.data(), offsets.data(), (uint32_t)total);
+            msm_bucket_sum(slice_sum[sidx], entries.data(), st, en, s.aff.data());
         }
-        msm_horner(acc, win.data(), pl);
+        const int T = 128;
+        int parts = 1;
+        for (int w = 0; w < pl.nwin; w++) {
+            int nbw = msm_window_buckets(pl, w);
+            int p_ = (nbw + T * msm_seg_for(nbw) - 1) / (T * msm_seg_for(nbw));
+            if (p_ > parts) parts = p_;
+        }
+        std::vector<pt> win((size_t)pl.nwin * parts);
+        for (int w = 0; w < pl.nwin; w++) {
+            int nbw = msm_window_buckets(pl, w);
+            for (int blk = 0; blk < parts; blk++) {
+                std::vector<pt> sh(T);
+                int seg = msm_seg_for(nbw);
+                for (int t = 0; t < T; t++) {
+                    int lo = (blk * T + t) * seg, hi = lo + seg;
+                    if (hi > nbw) hi = nbw;
+                    if (lo < hi) msm_segment(sh[t], slice_sum.data(), sl_off.data(), (uint32_t)w * (uint32_t)pl.nb, lo, hi);
+                    else pt_set_identity(sh[t]);
+                }
+                for (int stride = T / 2; stride >= 1; stride >>= 1)
+                    for (int t = 0; t < stride; t++) pt_add(sh[t], sh[t], sh[t + stride]);
+                win[(size_t)w * parts + blk] = sh[0];
+            }
+        }
+        for (int w = 0; w < pl.nwin; w++)
+            for (int q = 1; q < parts; q++) pt_add(win[(size_t)w * parts], win[(size_t)w * parts], win[(size_t)w * parts + q]);
+        msm_horner(acc, win.data(), pl, 1, parts);
     }
     memset(out65, 0, 65);
     if (partial96) pt_to_be96(partial96, acc);

@@ -375,6 +375,12 @@ def check_msm(be, o, sizes=(0, 1, 2, 31, 32, 33, 64, 300), big=None):
     import pytest
     with pytest.raises(ValueError):
         be.msm(k[:3], pts[:4])
+    # skewed scalars: every point lands in the same bucket of every window (exercises bucket slicing)
+    ns = min(max(sizes), 300)
+    ks = np.tile(np.frombuffer(b32(0x123456789ABCDEF0FEDCBA9876543210 << 64 | 0x55AA), np.uint8), (ns, 1))
+    got, st = be.msm(ks, w["pt65"][:ns])
+    exp, est = o.msm(ks.tobytes(), w["pt65"][:ns].tobytes())
+    assert (st, got.tobytes()) == (est, exp)
     if big:
         wb = synth.msm_batch(big, oracle_base_mult(o))
         got, st = be.msm(wb["k32"], wb["pt65"])
