@@ -596,7 +596,10 @@ static void enqueue_dsm(s256_ctx *ctx, const view &v, size_t n, cudaStream_t s) 
         ctx->dsm_events.emplace_back(e0, e1);
     }
 }
-constexpr int INV_K = 16;
+#ifndef S256_INV_K
+#define S256_INV_K 32
+#endif
+constexpr int INV_K = S256_INV_K;
 constexpr int MSM_MAX_PARTS = 16;  // (2^16 buckets) / (128 threads * 32 buckets)
 static inline unsigned grid_for_groups(size_t n, int k) { return grid_for((n + k - 1) / k); }
 

@@ -18,7 +18,7 @@ using namespace s256;
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
 static std::vector<apt> g_comb, g_ct;
-static constexpr int K = 16;
+static constexpr int K = 32;
 
 static void ensure_tables() {
     if (!g_ct.empty()) return;
