@@ -600,6 +600,17 @@ static void enqueue_dsm(s256_ctx *ctx, const view &v, size_t n, cudaStream_t s) 
 #define S256_INV_K 32
 #endif
 constexpr int INV_K = S256_INV_K;
+// Inversion group size by batch size: K items share one Fermat chain but are processed serially by
+// one thread, so small batches use small groups (n = 4096 with K = 32 would run on 128 threads).
+static inline int inv_k_for(size_t n) { return n >= ((size_t)1 << 19) ? INV_K : (n >= ((size_t)1 << 16) ? 4 : 1); }
+#define DISPATCH_K(n, CALL)               \
+    do {                                  \
+        switch (inv_k_for(n)) {           \
+            case 1: { constexpr int KK = 1; CALL; } break;  \
+            case 4: { constexpr int KK = 4; CALL; } break;  \
+            default: { constexpr int KK = INV_K; CALL; } break; \
+        }                                 \
+    } while (0)
 constexpr int MSM_MAX_PARTS = 16;  // (2^16 buckets) / (128 threads * 32 buckets)
 static inline unsigned grid_for_groups(size_t n, int k) { return grid_for((n + k - 1) / k); }
 
@@ -607,8 +618,8 @@ static inline unsigned grid_for_groups(size_t n, int k) { return grid_for((n + k
 // caller passes a second stream, decode runs there (behind the key copy) and joins through an event.
 static int chunk_ecdsa_verify(s256_ctx *ctx, const view &v, const uint8_t *pk, const uint8_t *dg, const uint8_t *sig, uint32_t flags,
                               size_t n, uint8_t *ok, cudaStream_t s, cudaStream_t s_decode = nullptr) {
-    LAUNCH(ctx, (k_ecdsa_scalars<INV_K, false>), grid_for_groups(n, INV_K), 0, s, dg, sig, n, flags, v.u1, v.dig1,
-           v.dig2, v.sfl);
+    DISPATCH_K(n, LAUNCH(ctx, (k_ecdsa_scalars<KK, false>), grid_for_groups(n, KK), 0, s, dg, sig, n, flags, v.u1,
+                         v.dig1, v.dig2, v.sfl));
     if (s_decode && s_decode != s) {
         LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s_decode, pk, n, v.aff, v.pvalid);
         cudaEventRecord(ctx->ev_decode, s_decode);
@@ -623,11 +634,11 @@ static int chunk_ecdsa_verify(s256_ctx *ctx, const view &v, const uint8_t *pk, c
 static int chunk_ecdsa_recover(s256_ctx *ctx, const view &v, const uint8_t *dg, const uint8_t *sig65, size_t n, uint8_t *pk65,
                                uint8_t *status, cudaStream_t s) {
     LAUNCH(ctx, k_decode_recover, grid_for(n), 0, s, sig65, n, v.aff, v.pvalid);
-    LAUNCH(ctx, (k_ecdsa_scalars<INV_K, true>), grid_for_groups(n, INV_K), 0, s, dg, sig65, n, 0u, v.u1, v.dig1,
-           v.dig2, v.sfl);
+    DISPATCH_K(n, LAUNCH(ctx, (k_ecdsa_scalars<KK, true>), grid_for_groups(n, KK), 0, s, dg, sig65, n, 0u, v.u1,
+                         v.dig1, v.dig2, v.sfl));
     enqueue_dsm(ctx, v, n, s);
-    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, v.res, v.pvalid, v.sfl, v.cstat,
-           3, pk65, status, (const uint8_t *)nullptr);
+    DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, v.res, v.pvalid, v.sfl, v.cstat,
+           3, pk65, status, (const uint8_t *)nullptr));
     return S256_SUCCESS;
 }
 static int chunk_schnorr_verify(s256_ctx *ctx, const view &v, const uint8_t *pkx, const uint8_t *msg, size_t msg_len,
@@ -636,8 +647,8 @@ static int chunk_schnorr_verify(s256_ctx *ctx, const view &v, const uint8_t *pkx
     LAUNCH(ctx, k_schnorr_scalars, grid_for(n), 0, s, pkx, msg, msg_len, sig, n, v.u1, v.dig1, v.dig2,
            v.sfl);
     enqueue_dsm(ctx, v, n, s);
-    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, v.res, v.pvalid, v.sfl, v.cstat,
-           2, (uint8_t *)nullptr, ok, sig);
+    DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, v.res, v.pvalid, v.sfl, v.cstat,
+           2, (uint8_t *)nullptr, ok, sig));
     return S256_SUCCESS;
 }
 static int chunk_dsm(s256_ctx *ctx, const view &v, const uint8_t *u1, const uint8_t *u2, const uint8_t *pt65, size_t n,
@@ -645,16 +656,16 @@ static int chunk_dsm(s256_ctx *ctx, const view &v, const uint8_t *u1, const uint
     LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pt65, n, v.aff, v.pvalid);
     LAUNCH(ctx, k_plain_scalars, grid_for(n), 0, s, u1, u2, n, v.u1, v.dig1, v.dig2, v.sfl);
     enqueue_dsm(ctx, v, n, s);
-    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, v.res, v.pvalid,
-           (const uint8_t *)nullptr, v.cstat, 0, out65, status, (const uint8_t *)nullptr);
+    DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, v.res, v.pvalid,
+           (const uint8_t *)nullptr, v.cstat, 0, out65, status, (const uint8_t *)nullptr));
     return S256_SUCCESS;
 }
 static int chunk_base_mult(s256_ctx *ctx, const view &v, const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status,
                            cudaStream_t s) {
     s256_launch_base_mult_ct(k32, n, ctx->ct_tab, v.res, s);
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, v.res, (const uint8_t *)nullptr,
-           (const uint8_t *)nullptr, v.cstat, 0, out65, status, (const uint8_t *)nullptr);
+    DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, v.res, (const uint8_t *)nullptr,
+           (const uint8_t *)nullptr, v.cstat, 0, out65, status, (const uint8_t *)nullptr));
     return S256_SUCCESS;
 }
 
@@ -664,8 +675,8 @@ static int chunk_scalar_mult(s256_ctx *ctx, const view &v, const uint8_t *k32, c
     LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pt65, n, v.aff, v.pvalid);
     s256_launch_scalar_mult_ct(n, v.aff, k32, v.tbl, v.res, s);
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    LAUNCH(ctx, k_finish_affine<INV_K>, grid_for_groups(n, INV_K), 0, s, n, v.res, v.pvalid,
-           (const uint8_t *)nullptr, v.cstat, mode, out, status, (const uint8_t *)nullptr);
+    DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, v.res, v.pvalid,
+           (const uint8_t *)nullptr, v.cstat, mode, out, status, (const uint8_t *)nullptr));
     return S256_SUCCESS;
 }
 

@@ -32,7 +32,43 @@ __global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
 }
 
 
+// T lanes per scalar (T divides 32): partial sums, then a shuffle tree of complete additions
+template <int T>
+__global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
+    k_base_mult_ct_split(const uint8_t *k32, size_t n, const apt *tab_g, pt *res) {
+    extern __shared__ uint4 smem_raw[];
+    apt *tab = reinterpret_cast<apt *>(smem_raw);
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(tab_g);
+        const int nvec = CT_NW * CT_SZ * (int)sizeof(apt) / 16;
+        for (int v = threadIdx.x; v < nvec; v += blockDim.x) smem_raw[v] = src[v];
+    }
+    __syncthreads();
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t item = gid / T;
+    int part = (int)(gid % T);
+    bool live = item < n;  // uniform inside each group of T lanes
+    sc k;
+    sc_from_be32(k, k32 + 32 * (live ? item : 0));
+    pt acc;
+    item_base_mult_ct_part(acc, k, tab, part, T);
+#pragma unroll
+    for (int off = T / 2; off >= 1; off >>= 1) {
+        pt o;
+        uint32_t *dst = o.x.v;
+        const uint32_t *src = acc.x.v;
+#pragma unroll
+        for (int q = 0; q < 24; q++) dst[q] = __shfl_down_sync(0xffffffffu, src[q], off, T);
+        pt_add(acc, acc, o);
+    }
+    if (live && part == 0) res[item] = acc;
+}
+
 void s256_ct_kernels_init() {
+    cudaFuncSetAttribute(k_base_mult_ct_split<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(CT_NW * CT_SZ * sizeof(apt)));
+    cudaFuncSetAttribute(k_base_mult_ct_split<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(CT_NW * CT_SZ * sizeof(apt)));
     cudaFuncSetAttribute(k_base_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)(CT_NW * CT_SZ * sizeof(apt)));
 }
@@ -41,5 +77,15 @@ void s256_launch_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_g, pt
     unsigned maxg = 148u * S256_BM_MINB;
     if (grid > maxg) grid = maxg;
     if (grid == 0) return;
-    k_base_mult_ct<<<grid, S256_TPB, CT_NW * CT_SZ * sizeof(apt), s>>>(k32, n, tab_g, res);
+    const size_t smem = CT_NW * CT_SZ * sizeof(apt);
+    // small batches are latency bound: deal the windows of each scalar to 8 / 4 lanes
+    if (n <= 8192) {
+        k_base_mult_ct_split<8><<<(unsigned)((n * 8 + S256_TPB - 1) / S256_TPB), S256_TPB, smem, s>>>(k32, n, tab_g, res);
+        return;
+    }
+    if (n <= 32768) {
+        k_base_mult_ct_split<4><<<(unsigned)((n * 4 + S256_TPB - 1) / S256_TPB), S256_TPB, smem, s>>>(k32, n, tab_g, res);
+        return;
+    }
+    k_base_mult_ct<<<grid, S256_TPB, smem, s>>>(k32, n, tab_g, res);
 }

@@ -593,6 +593,58 @@ S256_HD void item_base_mult_ct(pt &acc, const sc &k, const apt *tab /* [CT_NW][C
     }
 }
 
+// Small batches: the 65 windows of one scalar are dealt round-robin to T lanes (window j*T + part in
+// iteration j, so the whole warp stays in lockstep); the caller folds the T partial points with
+// complete additions.  Digits are recoded first (carry chain) into a local array that is then read
+// at an index depending only on the lane number.  Same table, same masks, same selects as above.
+S256_HD void item_base_mult_ct_part(pt &acc, const sc &k, const apt *tab, int part, int T) {
+    int8_t dig[CT_NW];
+    uint32_t carry = 0;
+#pragma unroll 1
+    for (int w = 0; w < CT_NW; w++) {
+        uint32_t v = (w < 64 ? (k.v[(w >> 3) & 7] >> ((w & 7) * 4)) & 0xFu : 0u) + carry;
+        carry = (v + 7u) >> 4;
+        dig[w] = (int8_t)((int32_t)v - (int32_t)(carry << 4));
+    }
+    pt_set_identity(acc);
+    const int iters = (CT_NW + T - 1) / T;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j = 0; j < iters; j++) {
+        int w = j * T + part;
+        uint32_t inrange = (uint32_t)(w < CT_NW);
+        int wc = inrange ? w : 0;
+        int32_t d = inrange ? (int32_t)dig[wc] : 0;
+        uint32_t sign = (uint32_t)d >> 31;
+        uint32_t mag = (uint32_t)((d ^ -(int32_t)sign) + (int32_t)sign);
+        apt sel;
+        sel.x = fe_zero();
+        sel.y = fe_zero();
+        const apt *row = tab + wc * CT_SZ;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
+        for (uint32_t e = 1; e <= (uint32_t)CT_SZ; e++) {
+            uint32_t m = 0u - (uint32_t)(e == mag);
+            apt t = row[e - 1];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                sel.x.v[q] |= t.x.v[q] & m;
+                sel.y.v[q] |= t.y.v[q] & m;
+            }
+        }
+        uint32_t zero = (uint32_t)(mag == 0);
+        apt e1 = row[0];
+        fe_cmov(sel.x, sel.x, e1.x, zero);
+        fe_cmov(sel.y, sel.y, e1.y, zero);
+        fe_cneg(sel.y, sel.y, sign);
+        pt sum;
+        pt_add_mixed(sum, acc, sel.x, sel.y);
+        pt_cmov(acc, sum, acc, zero);
+    }
+}
+
 // Table storage policies for the ct ladder: per-item rows in global memory (host simulation, or
 // when shared memory is not used) and per-thread columns in shared memory ([entry][limb group][thread],
 // LDS.128 / STS.128 conflict-free).  Either way the address stream depends only on public values.

@@ -125,7 +125,16 @@ EXPORT void sim_scalar_base_mult(const uint8_t *k32, size_t n, uint8_t *out65, u
     for (size_t i = 0; i < n; i++) {
         sc k;
         sc_from_be32(k, k32 + 32 * i);
-        item_base_mult_ct(s.res[i], k, g_ct.data());
+        if (n <= 8) {  // exercise the lane-split form (T = 8 then T = 4) the way the kernel folds it
+            int T = (i & 1) ? 4 : 8;
+            pt part[8];
+            for (int p = 0; p < T; p++) item_base_mult_ct_part(part[p], k, g_ct.data(), p, T);
+            for (int off = T / 2; off >= 1; off >>= 1)
+                for (int p = 0; p < off; p++) pt_add(part[p], part[p], part[p + off]);
+            s.res[i] = part[0];
+        } else {
+            item_base_mult_ct(s.res[i], k, g_ct.data());
+        }
     }
     run_finish(s, n, false, false, 0, out65, status, nullptr);
 }
