@@ -110,6 +110,22 @@ int s256_ecdsa_verify(s256_ctx *ctx, const uint8_t *pk65, const uint8_t *digest3
 int s256_ecdsa_verify_dev(s256_ctx *ctx, const uint8_t *d_pk65, const uint8_t *d_digest32, const uint8_t *d_sig64,
                           uint32_t flags, size_t n, uint8_t *d_ok, void *stream);
 
+/* --- host-side codecs in front of the batch (byte parsing only, no arithmetic) ----------------
+ * Signatures arrive concatenated in `der`, row i being der[offsets[i] .. offsets[i+1]) (n + 1 offsets).
+ *   s256_parse_asn1_signatures: secec.ParseASN1Signature (secec/s11n.go:83): strict DER
+ *     SEQUENCE{r,s}, both in [1, n) -> r||s rows; ok[i] = 0 (row zeroed) when rejected.
+ *   s256_is_valid_signature_encoding_bip0066: bitcoin.IsValidSignatureEncodingBIP0066
+ *     (secec/bitcoin/asn1_shitcoin.go:13), rows INCLUDE the trailing sighash byte.
+ *   s256_ecdsa_verify_asn1: PublicKey.Verify with EncodingASN1 (secec/ecdsa.go:171-228).
+ *   s256_bitcoin_verify_asn1: bitcoin.VerifyASN1 (secec/bitcoin/ecdsa_shitcoin.go:29): BIP-66
+ *     check, sighash byte stripped, s <= n/2 enforced. */
+int s256_parse_asn1_signatures(const uint8_t *der, const size_t *offsets, size_t n, uint8_t *sig64, uint8_t *ok);
+int s256_is_valid_signature_encoding_bip0066(const uint8_t *der, const size_t *offsets, size_t n, uint8_t *ok);
+int s256_ecdsa_verify_asn1(s256_ctx *ctx, const uint8_t *pk65, const uint8_t *digest32, const uint8_t *der,
+                           const size_t *offsets, uint32_t flags, size_t n, uint8_t *ok);
+int s256_bitcoin_verify_asn1(s256_ctx *ctx, const uint8_t *pk65, const uint8_t *digest32, const uint8_t *der,
+                             const size_t *offsets, size_t n, uint8_t *ok);
+
 /* --- secec.RecoverPublicKey (secec/ecdsa.go:244) on r||s||v
  *     (secec/s11n.go:156). */
 int s256_ecdsa_recover(s256_ctx *ctx, const uint8_t *digest32, const uint8_t *sig65, size_t n, uint8_t *pk65,

@@ -32,6 +32,8 @@ EXPORTED_SYMBOLS = [
     "s256_ecdh", "s256_ecdh_dev", "s256_point_decompress",
     "s256_double_scalar_mult_basepoint_vartime", "s256_double_scalar_mult_basepoint_vartime_dev",
     "s256_ecdsa_verify", "s256_ecdsa_verify_dev",
+    "s256_parse_asn1_signatures", "s256_is_valid_signature_encoding_bip0066",
+    "s256_ecdsa_verify_asn1", "s256_bitcoin_verify_asn1",
     "s256_ecdsa_recover", "s256_ecdsa_recover_dev",
     "s256_schnorr_verify", "s256_schnorr_verify_dev",
     "s256_msm", "s256_msm_partial", "s256_msm_combine",
@@ -79,6 +81,42 @@ def load_library():
 
 def mac32_per_item(entry_point):
     return load_library().s256_mac32_per_item(entry_point.encode())
+
+
+def _pack_rows(rows):
+    """list of byte strings -> (concatenated uint8 array, size_t offsets array)"""
+    rows = [bytes(r) for r in rows]
+    offs = np.zeros(len(rows) + 1, dtype=np.uintp)
+    np.cumsum([len(r) for r in rows], out=offs[1:])
+    data = np.frombuffer(b"".join(rows) or b"\x00", dtype=np.uint8).copy()
+    return data, offs
+
+
+def parse_asn1_signatures(rows):
+    """secec.ParseASN1Signature over a list of DER signatures -> (sig64 rows, ok). Host-side, no GPU needed."""
+    lib = load_library()
+    data, offs = _pack_rows(rows)
+    n = len(rows)
+    sig = np.zeros((n, 64), np.uint8)
+    ok = np.zeros(n, np.uint8)
+    rc = lib.s256_parse_asn1_signatures(data.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), C.c_size_t(n),
+                                        sig.ctypes.data_as(C.c_void_p), ok.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise S256Error(f"parse_asn1_signatures rc={rc}")
+    return sig, ok
+
+
+def is_valid_signature_encoding_bip0066(rows):
+    """bitcoin.IsValidSignatureEncodingBIP0066 over a list of signatures (with the sighash byte)."""
+    lib = load_library()
+    data, offs = _pack_rows(rows)
+    n = len(rows)
+    ok = np.zeros(n, np.uint8)
+    rc = lib.s256_is_valid_signature_encoding_bip0066(data.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p),
+                                                      C.c_size_t(n), ok.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise S256Error(f"is_valid_signature_encoding_bip0066 rc={rc}")
+    return ok
 
 
 def _is_torch_cuda(x):
@@ -255,6 +293,29 @@ class Engine:
         ok = np.zeros(n, np.uint8)
         self._check(self._lib.s256_ecdsa_verify(self._ctx, self._hp(pk), self._hp(dg), self._hp(sg), C.c_uint32(flags),
                                                 C.c_size_t(n), self._hp(ok)), "ecdsa_verify")
+        return ok
+
+    # -- PublicKey.Verify, EncodingASN1 (secec/ecdsa.go:171) and bitcoin.VerifyASN1 ----------
+    def ecdsa_verify_asn1(self, pk65, digest32, der_rows, flags=0):
+        pk, dg = _host(pk65, 65), _host(digest32, 32)
+        data, offs = _pack_rows(der_rows)
+        n = len(der_rows)
+        if len(pk) != n or len(dg) != n:
+            raise ValueError("length mismatch")
+        ok = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_ecdsa_verify_asn1(self._ctx, self._hp(pk), self._hp(dg), self._hp(data), self._hp(offs),
+                                                     C.c_uint32(flags), C.c_size_t(n), self._hp(ok)), "ecdsa_verify_asn1")
+        return ok
+
+    def bitcoin_verify_asn1(self, pk65, digest32, der_rows_with_sighash):
+        pk, dg = _host(pk65, 65), _host(digest32, 32)
+        data, offs = _pack_rows(der_rows_with_sighash)
+        n = len(der_rows_with_sighash)
+        if len(pk) != n or len(dg) != n:
+            raise ValueError("length mismatch")
+        ok = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_bitcoin_verify_asn1(self._ctx, self._hp(pk), self._hp(dg), self._hp(data), self._hp(offs),
+                                                       C.c_size_t(n), self._hp(ok)), "bitcoin_verify_asn1")
         return ok
 
     # -- secec.RecoverPublicKey (secec/ecdsa.go:244) ---------------------------

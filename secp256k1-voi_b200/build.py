@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 # S256_LIB=<path> selects a prebuilt variant (tuning experiments); it is never rebuilt.
 LIB = os.environ.get("S256_LIB") or os.path.join(LIBDIR, "libsecp256k1_b200.so")
-SOURCES = ["api.cu", "kern_ct.cu"]
+SOURCES = ["api.cu", "kern_ct.cu", "codecs.cpp"]
 HEADERS = ["fe.cuh", "sc.cuh", "point.cuh", "sha256.cuh", "kernels.cuh", "microbench.cuh", "launchers.h", "msm.cuh", "vm.cuh", "fe_sqr_gen.cuh"]
 
 

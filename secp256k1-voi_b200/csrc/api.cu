@@ -935,6 +935,42 @@ extern "C" int s256_point_decompress(s256_ctx *ctx, const uint8_t *pt33, size_t 
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
 
+// PublicKey.Verify with EncodingASN1 (secec/ecdsa.go:171-228): parse on the host (codecs.cpp), then the
+// same batch as the compact path; rows the parser rejects come back false.
+extern "C" int s256_ecdsa_verify_asn1(s256_ctx *ctx, const uint8_t *pk65, const uint8_t *digest32, const uint8_t *der,
+                                      const size_t *offsets, uint32_t flags, size_t n, uint8_t *ok) {
+    if (!ctx || (n && (!pk65 || !digest32 || !der || !offsets || !ok))) return S256_ERR_ARG;
+    std::vector<uint8_t> sig(64 * n), parsed(n);
+    int rc = s256_parse_asn1_signatures(der, offsets, n, sig.data(), parsed.data());
+    if (rc != S256_SUCCESS) return rc;
+    rc = s256_ecdsa_verify(ctx, pk65, digest32, sig.data(), flags, n, ok);
+    if (rc != S256_SUCCESS) return rc;
+    for (size_t i = 0; i < n; i++) ok[i] &= parsed[i];
+    return S256_SUCCESS;
+}
+// bitcoin.VerifyASN1 (secec/bitcoin/ecdsa_shitcoin.go:29-35)
+extern "C" int s256_bitcoin_verify_asn1(s256_ctx *ctx, const uint8_t *pk65, const uint8_t *digest32, const uint8_t *der,
+                                        const size_t *offsets, size_t n, uint8_t *ok) {
+    if (!ctx || (n && (!pk65 || !digest32 || !der || !offsets || !ok))) return S256_ERR_ARG;
+    std::vector<uint8_t> bip(n);
+    int rc = s256_is_valid_signature_encoding_bip0066(der, offsets, n, bip.data());
+    if (rc != S256_SUCCESS) return rc;
+    // strip the sighash byte of the rows that passed; rejected rows become empty (and fail to parse)
+    std::vector<size_t> off2(n + 1);
+    std::vector<uint8_t> der2;
+    der2.reserve(offsets[n] - offsets[0]);
+    for (size_t i = 0; i < n; i++) {
+        off2[i] = der2.size();
+        if (bip[i]) der2.insert(der2.end(), der + offsets[i], der + offsets[i + 1] - 1);
+    }
+    off2[n] = der2.size();
+    if (der2.empty()) der2.push_back(0);
+    rc = s256_ecdsa_verify_asn1(ctx, pk65, digest32, der2.data(), off2.data(), S256_FLAG_REJECT_MALLEABLE, n, ok);
+    if (rc != S256_SUCCESS) return rc;
+    for (size_t i = 0; i < n; i++) ok[i] &= bip[i];
+    return S256_SUCCESS;
+}
+
 // ---------------------------------------------------------------------------
 // MSM
 // ---------------------------------------------------------------------------

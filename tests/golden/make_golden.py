@@ -191,6 +191,27 @@ def rfc6979():
     return rows
 
 
+def wycheproof_ecdsa_der():
+    """EVERY Wycheproof ECDSA case with the raw DER signature: pins ParseASN1Signature + verify end to end
+    (secec/wycheproof_test.go:317-336: Verify(hBytes, sigBytes, nil) must equal result == valid)."""
+    cases = []
+    for fn, hname in (("ecdsa_secp256k1_sha256_test.json", "sha256"), ("ecdsa_secp256k1_sha512_test.json", "sha512")):
+        doc = json.load(open(f"{REF}/secec/testdata/wycheproof/{fn}"))
+        for g in doc["testGroups"]:
+            pk = g["publicKey"]["uncompressed"]
+            for tc in g["tests"]:
+                digest = hashlib.new(hname, bytes.fromhex(tc["msg"])).digest()
+                cases.append({"src": fn, "tcId": tc["tcId"], "pk": pk, "digest": digest.hex(), "sig": tc["sig"],
+                              "valid": tc["result"] == "valid"})
+    return cases
+
+
+def bip66():
+    doc = json.load(open(f"{REF}/secec/bitcoin/testdata/bip-0066-test-vectors.json"))
+    return {"valid": [{"der": v["DER"], "r": v["r"], "s": v["s"]} for v in doc["valid"]],
+            "invalid": [{"der": v["DER"], "exception": v.get("exception", "")} for v in doc["invalid"]["decode"]]}
+
+
 def in_source_kats():
     pt = open(f"{REF}/point_test.go").read()
     glv = open(f"{REF}/point_mul_glv_test.go").read()
@@ -232,6 +253,14 @@ def main():
     json.dump({"provenance": "secec/testdata/secp256k1_rfc6979_sha256.csv", "rows": rows},
               open(f"{OUT}/rfc6979.json", "w"), indent=0)
     print("rfc6979:", len(rows))
+    der = wycheproof_ecdsa_der()
+    json.dump({"provenance": "secec/testdata/wycheproof/ecdsa_secp256k1_sha{256,512}_test.json, every case, raw DER",
+               "cases": der}, open(f"{OUT}/wycheproof_ecdsa_der.json", "w"), indent=0)
+    print("wycheproof ecdsa (raw DER):", len(der), "cases,", sum(c["valid"] for c in der), "valid")
+    b66 = bip66()
+    json.dump({"provenance": "secec/bitcoin/testdata/bip-0066-test-vectors.json", **b66},
+              open(f"{OUT}/bip66.json", "w"), indent=0)
+    print("bip66:", len(b66["valid"]), "valid,", len(b66["invalid"]), "invalid")
     k = in_source_kats()
     json.dump({"provenance": "point_test.go:39,49,244-253; point_mul_glv_test.go:18-45; internal/gentable/point_mul_table.bin",
                **k}, open(f"{OUT}/kats.json", "w"), indent=0)
