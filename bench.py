@@ -268,7 +268,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 161), "d2h_bytes_per_step": int(n)},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "int32-mac (IMAD.WIDE.U32 issue; not hbm/tensor: 161 B per verify)",
+            "roofline": {"bound": "int-mul",
+                         "bound_note": "32x32->64 multiply issue (IMAD.WIDE.U32, half rate on sm_100); not hbm/tensor: "
+                                       "161 B and ~142k multiply-accumulates per verification",
                          "kernel": "k_dsm", "achieved": achieved / 1e12 if achieved else None,
                          "peak": imad_peak / 1e12, "unit": "TMAC32/s",
                          "frac": (achieved / imad_peak) if achieved else None,
