@@ -126,6 +126,15 @@ int s256_ecdsa_verify_asn1(s256_ctx *ctx, const uint8_t *pk65, const uint8_t *di
 int s256_bitcoin_verify_asn1(s256_ctx *ctx, const uint8_t *pk65, const uint8_t *digest32, const uint8_t *der,
                              const size_t *offsets, size_t n, uint8_t *ok);
 
+/* --- PrivateKey.Sign with RFC6979SHA256() as the entropy source (secec/ecdsa.go:92-135,284-390;
+ *     nonce: secec/ecdsa_k_rfc6979.go): deterministic, constant time.  priv32 must be a canonical
+ *     non-zero scalar (NewPrivateKey, secec/secec.go:141).  Outputs: compact r||s (low-s normalised),
+ *     the recovery id (0..3), status. */
+int s256_ecdsa_sign_rfc6979(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *digest32, size_t n, uint8_t *sig64,
+                            uint8_t *recid, uint8_t *status);
+int s256_ecdsa_sign_rfc6979_dev(s256_ctx *ctx, const uint8_t *d_priv32, const uint8_t *d_digest32, size_t n,
+                                uint8_t *d_sig64, uint8_t *d_recid, uint8_t *d_status, void *stream);
+
 /* --- secec.RecoverPublicKey (secec/ecdsa.go:244) on r||s||v
  *     (secec/s11n.go:156). */
 int s256_ecdsa_recover(s256_ctx *ctx, const uint8_t *digest32, const uint8_t *sig65, size_t n, uint8_t *pk65,

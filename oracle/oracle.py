@@ -155,6 +155,16 @@ def ecdsa_recover(digest32, sig65):
     o = _out(65); st = lib().orc_ecdsa_recover(_buf(digest32, 32), _buf(sig65, 65), o); return o.raw, st
 
 
+def ecdsa_sign_rfc6979(priv32, digest32):
+    sig = _out(64); rec = C.c_uint8(0)
+    st = lib().orc_ecdsa_sign_rfc6979(_buf(priv32, 32), _buf(digest32, 32), sig, C.byref(rec))
+    return sig.raw, rec.value, st
+
+
+def hmac_sha256(key32, msg):
+    o = _out(32); msg = bytes(msg); lib().orc_hmac_sha256(_buf(key32, 32), msg, C.c_size_t(len(msg)), o); return o.raw
+
+
 def schnorr_verify(pkx32, msg, sig64):
     msg = bytes(msg)
     return lib().orc_schnorr_verify(_buf(pkx32, 32), msg, C.c_size_t(len(msg)), _buf(sig64, 64))
@@ -222,3 +232,10 @@ def batch_schnorr_verify(pkx, msg, sig, threads=None):
     ok = np.zeros(n, np.uint8)
     lib().orc_batch_schnorr_verify(_p(pkx), _p(msg), C.c_size_t(msg.shape[1]), _p(sig), C.c_size_t(n), _p(ok), threads or default_threads())
     return ok
+
+
+def batch_ecdsa_sign_rfc6979(priv, digest, threads=None):
+    priv = _np(priv, 32); digest = _np(digest, 32); n = len(priv)
+    sig = np.zeros((n, 64), np.uint8); rec = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8)
+    lib().orc_batch_ecdsa_sign_rfc6979(_p(priv), _p(digest), C.c_size_t(n), _p(sig), _p(rec), _p(st), threads or default_threads())
+    return sig, rec, st

@@ -804,6 +804,85 @@ static int schnorr_verify_one(const u8 pkx32[32], const u8 *msg, size_t msg_len,
     return memcmp(ub + 1, sig64, 32) == 0;
 }
 
+/* secec/ecdsa_k_rfc6979.go:36-145 -- HMAC_DRBG(SHA-256) keyed with int2octets(x) || bits2octets(h1);
+ * every Read returns one 32-byte T = V after V = HMAC_K(V); a rejected T is followed by
+ * K = HMAC_K(V || 0x00), V = HMAC_K(V) (delayed to the next Read). */
+static void hmac_sha256(u8 out[32], const u8 key[32], const u8 *msg, size_t len) {
+    u8 pad[64], inner[32];
+    sha256_ctx c;
+    memset(pad, 0x36, 64);
+    for (int i = 0; i < 32; i++) pad[i] ^= key[i];
+    sha256_init(&c); sha256_update(&c, pad, 64); sha256_update(&c, msg, len); sha256_final(&c, inner);
+    memset(pad, 0x5c, 64);
+    for (int i = 0; i < 32; i++) pad[i] ^= key[i];
+    sha256_init(&c); sha256_update(&c, pad, 64); sha256_update(&c, inner, 32); sha256_final(&c, out);
+}
+typedef struct { u8 v[32], k[32]; int need_update; } drbg6979;
+static void drbg_init(drbg6979 *g, const u8 x32[32], const u8 h32[32]) {
+    u8 m[97];
+    memset(g->v, 0x01, 32);
+    memset(g->k, 0x00, 32);
+    g->need_update = 0;
+    for (int oct = 0; oct < 2; oct++) {
+        memcpy(m, g->v, 32); m[32] = (u8)oct; memcpy(m + 33, x32, 32); memcpy(m + 65, h32, 32);
+        hmac_sha256(g->k, g->k, m, 97);
+        hmac_sha256(g->v, g->k, g->v, 32);
+    }
+}
+static void drbg_read(drbg6979 *g, u8 out[32]) {
+    if (g->need_update) {
+        u8 m[33];
+        memcpy(m, g->v, 32); m[32] = 0;
+        hmac_sha256(g->k, g->k, m, 33);
+        hmac_sha256(g->v, g->k, g->v, 32);
+    }
+    hmac_sha256(g->v, g->k, g->v, 32);
+    memcpy(out, g->v, 32);
+    g->need_update = 1;
+}
+/* secec/ecdsa.go:284-390 with rand = RFC6979SHA256() (:505-506): e = leftmost 32 digest bytes mod n,
+ * k from the DRBG by rejection (sampleRandomScalar :523-545), R = k*G, r = x(R) mod n,
+ * s = (r*d + e)/k, low-s normalisation, recovery id = (didReduce << 1 | yOdd) ^ negated.
+ * priv32 must be canonical and non-zero (NewPrivateKey, secec/secec.go:141-160). */
+static int ecdsa_sign_rfc6979_one(const u8 priv32[32], const u8 digest32[32], u8 sig64[64], u8 *recid) {
+    sc d, e, k, r, s, kinv;
+    memset(sig64, 0, 64);
+    *recid = 0;
+    if (!sc_set_canonical_bytes(&d, priv32) || sc_is_zero(&d)) return ST_INVALID;
+    sc_set_bytes(&e, digest32);
+    u8 db[32], eb[32], t[32];
+    sc_bytes(db, &d);
+    sc_bytes(eb, &e);
+    drbg6979 g;
+    drbg_init(&g, db, eb);
+    for (;;) {
+        int ok = 0;
+        for (int i = 0; i < 8 && !ok; i++) {
+            drbg_read(&g, t);
+            ok = (sc_set_bytes(&k, t) == 0) && !sc_is_zero(&k);
+        }
+        if (!ok) return ST_INVALID;
+        pt R, sR;
+        pt_scalar_base_mult(&R, &k);
+        pt_rescale(&sR, &R);
+        u8 xb[32];
+        fe_bytes(xb, &sR.x);
+        int did_reduce = sc_set_bytes(&r, xb);
+        if (sc_is_zero(&r)) continue;
+        sc_invert(&kinv, &k);
+        sc_mul(&s, &r, &d);
+        sc_add(&s, &s, &e);
+        sc_mul(&s, &s, &kinv);
+        if (sc_is_zero(&s)) continue;
+        int neg = sc_is_gt_half_n(&s);
+        if (neg) sc_neg(&s, &s);
+        *recid = (u8)(((did_reduce << 1) | fe_is_odd(&sR.y)) ^ neg);
+        sc_bytes(sig64, &r);
+        sc_bytes(sig64 + 32, &s);
+        return ST_OK;
+    }
+}
+
 /* ------------------------------------------------------------------------- */
 /* Exported single-item entry points (ctypes)                                 */
 /* ------------------------------------------------------------------------- */
@@ -952,6 +1031,11 @@ EXPORT int orc_ecdsa_recover(const u8 digest32[32], const u8 sig65[65], u8 pk65[
     orc_init();
     return ecdsa_recover_one(digest32, sig65, pk65);
 }
+EXPORT int orc_ecdsa_sign_rfc6979(const u8 priv32[32], const u8 digest32[32], u8 sig64[64], u8 *recid) {
+    orc_init();
+    return ecdsa_sign_rfc6979_one(priv32, digest32, sig64, recid);
+}
+EXPORT void orc_hmac_sha256(const u8 key[32], const u8 *msg, size_t len, u8 out[32]) { hmac_sha256(out, key, msg, len); }
 EXPORT int orc_schnorr_verify(const u8 pkx32[32], const u8 *msg, size_t msg_len, const u8 sig64[64]) {
     orc_init();
     return schnorr_verify_one(pkx32, msg, msg_len, sig64);
@@ -962,7 +1046,7 @@ EXPORT int orc_schnorr_verify(const u8 pkx32[32], const u8 *msg, size_t msg_len,
 /* Items are split into contiguous slices, one per thread.                    */
 /* ------------------------------------------------------------------------- */
 
-enum { OP_SBM, OP_SBM_VT, OP_SMUL, OP_ECDH, OP_DSM, OP_VERIFY, OP_RECOVER, OP_SCHNORR };
+enum { OP_SBM, OP_SBM_VT, OP_SMUL, OP_ECDH, OP_DSM, OP_VERIFY, OP_RECOVER, OP_SCHNORR, OP_SIGN };
 typedef struct {
     int op; size_t lo, hi;
     const u8 *a, *b, *c; size_t msg_len; uint32_t flags;
@@ -979,6 +1063,7 @@ static void *job_run(void *arg) {
         case OP_DSM: j->status[i] = (u8)orc_double_scalar_mult_basepoint_vartime(j->a + 32 * i, j->b + 32 * i, j->c + 65 * i, j->out + 65 * i); break;
         case OP_VERIFY: j->status[i] = (u8)ecdsa_verify_one(j->a + 65 * i, j->b + 32 * i, j->c + 64 * i, j->flags); break;
         case OP_RECOVER: j->status[i] = (u8)ecdsa_recover_one(j->a + 32 * i, j->b + 65 * i, j->out + 65 * i); break;
+        case OP_SIGN: j->status[i] = (u8)ecdsa_sign_rfc6979_one(j->a + 32 * i, j->b + 32 * i, j->out + 64 * i, (u8 *)j->c + i); break;
         case OP_SCHNORR: j->status[i] = (u8)schnorr_verify_one(j->a + 32 * i, j->b + j->msg_len * i, j->msg_len, j->c + 64 * i); break;
         }
     }
@@ -1025,5 +1110,9 @@ EXPORT void orc_batch_ecdsa_recover(const u8 *digest32, const u8 *sig65, size_t 
 }
 EXPORT void orc_batch_schnorr_verify(const u8 *pkx32, const u8 *msg, size_t msg_len, const u8 *sig64, size_t n, u8 *ok, int nthreads) {
     job_t j = {0}; j.op = OP_SCHNORR; j.a = pkx32; j.b = msg; j.msg_len = msg_len; j.c = sig64; j.status = ok;
+    run_batch(j, n, nthreads);
+}
+EXPORT void orc_batch_ecdsa_sign_rfc6979(const u8 *priv32, const u8 *digest32, size_t n, u8 *sig64, u8 *recid, u8 *status, int nthreads) {
+    job_t j = {0}; j.op = OP_SIGN; j.a = priv32; j.b = digest32; j.c = recid; j.out = sig64; j.status = status;
     run_batch(j, n, nthreads);
 }

@@ -35,6 +35,7 @@ EXPORTED_SYMBOLS = [
     "s256_parse_asn1_signatures", "s256_is_valid_signature_encoding_bip0066",
     "s256_ecdsa_verify_asn1", "s256_bitcoin_verify_asn1",
     "s256_ecdsa_recover", "s256_ecdsa_recover_dev",
+    "s256_ecdsa_sign_rfc6979", "s256_ecdsa_sign_rfc6979_dev",
     "s256_schnorr_verify", "s256_schnorr_verify_dev",
     "s256_msm", "s256_msm_partial", "s256_msm_combine",
     "s256_debug_gen_table", "s256_debug_field_op", "s256_microbench_imad",
@@ -317,6 +318,30 @@ class Engine:
         self._check(self._lib.s256_bitcoin_verify_asn1(self._ctx, self._hp(pk), self._hp(dg), self._hp(data), self._hp(offs),
                                                        C.c_size_t(n), self._hp(ok)), "bitcoin_verify_asn1")
         return ok
+
+    # -- PrivateKey.Sign(RFC6979SHA256(), digest) (secec/ecdsa.go:92,284) -------------------
+    def ecdsa_sign_rfc6979(self, priv32, digest32):
+        """-> (sig64 rows r||s low-s, recovery ids, status)"""
+        if _is_torch_cuda(priv32):
+            import torch
+            n = priv32.numel() // 32
+            sig = torch.empty((n, 64), dtype=torch.uint8, device=priv32.device)
+            rec = torch.empty(n, dtype=torch.uint8, device=priv32.device)
+            st = torch.empty(n, dtype=torch.uint8, device=priv32.device)
+            a = self._dev_args(priv32, digest32, sig, rec, st)
+            self._check(self._lib.s256_ecdsa_sign_rfc6979_dev(self._ctx, a[0], a[1], C.c_size_t(n), a[2], a[3], a[4],
+                                                              self._stream()), "ecdsa_sign_rfc6979_dev")
+            return sig, rec, st
+        d, dg = _host(priv32, 32), _host(digest32, 32)
+        n = len(d)
+        if len(dg) != n:
+            raise ValueError("length mismatch")
+        sig = np.zeros((n, 64), np.uint8)
+        rec = np.zeros(n, np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_ecdsa_sign_rfc6979(self._ctx, self._hp(d), self._hp(dg), C.c_size_t(n), self._hp(sig),
+                                                      self._hp(rec), self._hp(st)), "ecdsa_sign_rfc6979")
+        return sig, rec, st
 
     # -- secec.RecoverPublicKey (secec/ecdsa.go:244) ---------------------------
     def ecdsa_recover(self, digest32, sig65):

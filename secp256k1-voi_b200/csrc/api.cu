@@ -199,6 +199,23 @@ __global__ void __launch_bounds__(S256_TPB) k_finish_affine(size_t n, const pt *
     group_finish<K>(t, stride, n, res, pvalid, sfl, comb_status, mode, out, status, sig64);
 }
 
+// ---- deterministic signing (kernels.cuh) ----
+__global__ void __launch_bounds__(S256_TPB) k_rfc6979_nonce(const uint8_t *priv32, const uint8_t *digest32, size_t n,
+                                                            uint8_t *kbuf, uint8_t *valid) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    valid[i] = item_rfc6979_nonce(kbuf + 32 * i, priv32 + 32 * i, digest32 + 32 * i);
+}
+template <int K>
+__global__ void __launch_bounds__(S256_TPB) k_sign_finish(size_t n, const uint8_t *priv32, const uint8_t *digest32,
+                                                          const uint8_t *kbuf, const uint8_t *valid, const uint8_t *r65,
+                                                          uint8_t *sig64, uint8_t *recid, uint8_t *status) {
+    size_t stride = (n + K - 1) / K;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= stride) return;
+    group_sign_finish<K>(t, stride, n, priv32, digest32, kbuf, valid, r65, sig64, recid, status);
+}
+
 // ---- Pippenger MSM (msm.cuh) -------------------------------------------------
 template <bool SCATTER>
 __global__ void __launch_bounds__(S256_TPB) k_msm_digits(const uint8_t *k32, size_t n, msm_plan plan, uint32_t *counts,
@@ -680,6 +697,23 @@ static int chunk_scalar_mult(s256_ctx *ctx, const view &v, const uint8_t *k32, c
     return S256_SUCCESS;
 }
 
+// PrivateKey.Sign(RFC6979SHA256(), digest): nonce -> k*G (ct) -> affine -> (r, s, v).  Scratch use: k in
+// v.u1 (32 B/item), R in v.out (65 B/item), validity in v.pvalid; the nonce buffer is wiped afterwards.
+static int chunk_sign(s256_ctx *ctx, const view &v, const uint8_t *priv32, const uint8_t *digest32, size_t n,
+                      uint8_t *sig64, uint8_t *recid, uint8_t *status, cudaStream_t s) {
+    uint8_t *kbuf = reinterpret_cast<uint8_t *>(v.u1);
+    LAUNCH(ctx, k_rfc6979_nonce, grid_for(n), 0, s, priv32, digest32, n, kbuf, v.pvalid);
+    s256_launch_base_mult_ct(kbuf, n, ctx->ct_tab, v.res, s);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, v.res, (const uint8_t *)nullptr,
+                         (const uint8_t *)nullptr, v.cstat, 0, v.out, v.sfl, (const uint8_t *)nullptr));
+    DISPATCH_K(n, LAUNCH(ctx, k_sign_finish<KK>, grid_for_groups(n, KK), 0, s, n, priv32, digest32, kbuf, v.pvalid, v.out,
+                         sig64, recid, status));
+    CK(cudaMemsetAsync(kbuf, 0, 32 * n, s));
+    CK(cudaMemsetAsync(v.res, 0, sizeof(pt) * n, s));
+    return S256_SUCCESS;
+}
+
 // Runs `body(offset, count)` over chunks of at most cap items.
 template <typename F>
 static int for_chunks(s256_ctx *ctx, size_t n, F body) {
@@ -930,6 +964,37 @@ extern "C" int s256_point_decompress(s256_ctx *ctx, const uint8_t *pt33, size_t 
         CK(cudaMemcpyAsync(out65 + 65 * off, ctx->out, 65 * c, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
+        return S256_SUCCESS;
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+
+extern "C" int s256_ecdsa_sign_rfc6979_dev(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *digest32, size_t n,
+                                           uint8_t *sig64, uint8_t *recid, uint8_t *status, void *stream) {
+    ENTER(ctx);
+    if (n && (!priv32 || !digest32 || !sig64 || !recid || !status)) return S256_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        return chunk_sign(ctx, view_at(ctx, 0), priv32 + 32 * off, digest32 + 32 * off, c, sig64 + 64 * off, recid + off,
+                          status + off, s);
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+extern "C" int s256_ecdsa_sign_rfc6979(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *digest32, size_t n,
+                                       uint8_t *sig64, uint8_t *recid, uint8_t *status) {
+    ENTER(ctx);
+    if (n && (!priv32 || !digest32 || !sig64 || !recid || !status)) return S256_ERR_ARG;
+    int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t s) {
+        CK(cudaMemcpyAsync(v.in_a, priv32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(v.in_b, digest32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        // outputs staged in v.in_c (sig64), v.cstat is busy inside finish_affine -> recid in v.in_a + 32*cap? use tail of in_c
+        uint8_t *d_sig = v.in_c, *d_rec = v.in_c + 64 * c, *d_st = v.st;
+        int r = chunk_sign(ctx, v, v.in_a, v.in_b, c, d_sig, d_rec, d_st, s);
+        if (r != S256_SUCCESS) return r;
+        CK(cudaMemcpyAsync(sig64 + 64 * off, d_sig, 64 * c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(recid + off, d_rec, c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + off, d_st, c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemsetAsync(v.in_a, 0, 32 * c, s));  // wipe the staged private keys
         return S256_SUCCESS;
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
@@ -1283,6 +1348,7 @@ extern "C" double s256_mac32_per_item(const char *name) {
     if (s == "schnorr_verify") return sqrt_fe + (ZN + split) + dsm + affine;
     if (s == "double_scalar_mult_basepoint_vartime") return oncurve + split + dsm + affine;
     if (s == "scalar_base_mult") return CT_NW * mix + affine;
+    if (s == "ecdsa_sign_rfc6979") return CT_NW * mix + affine + (5 * ZN + inv_sc / INV_K);  // + 22 SHA-256 blocks
     if (s == "scalar_mult" || s == "ecdh") {
         const double tab = (CTM_TS / 2) * dbl + (CTM_TS / 2 - 1) * mix;
         const double lad = (CTM_ND - 1) * CTM_W * dbl + 2 * CTM_ND * add + CTM_ND * M;

@@ -760,4 +760,107 @@ S256_HD uint8_t item_decode_compressed(apt &out, const uint8_t *b) {
     return item_decompress(out, x, ok, (uint32_t)(b[0] & 1u));
 }
 
+// ---------------------------------------------------------------------------
+// Deterministic ECDSA signing: PrivateKey.Sign(RFC6979SHA256(), digest)
+// (secec/ecdsa.go:284-390 with the DRBG of secec/ecdsa_k_rfc6979.go).  Everything
+// here handles secrets: no branch or address depends on d or k, except the
+// rejection of an out-of-range DRBG output (probability 2^-128, the reference
+// short-circuits there too, ecdsa.go:537-540).
+//   nonce kernel : d canonical & non-zero (NewPrivateKey, secec/secec.go:141-160),
+//                  e = digest mod n, k = first DRBG output in [1, n)
+//   R = k*G      : the constant-time fixed-base kernel + batched affine conversion
+//   finish       : r = x(R) mod n, s = (r*d + e)/k with one shared k^-1 chain per group,
+//                  low-s normalisation, recovery id = (didReduce << 1 | yOdd) ^ negated
+// An item whose r or s comes out zero (the reference would draw another k; not reachable in
+// practice) is reported as S256_ST_INVALID rather than retried.
+// ---------------------------------------------------------------------------
+S256_HD uint8_t item_rfc6979_nonce(uint8_t kout[32], const uint8_t *priv32, const uint8_t *digest32) {
+    sc d, e;
+    uint32_t d_ok = (1u - sc_from_be32(d, priv32)) & (1u - sc_is_zero(d));
+    sc_from_be32(e, digest32);
+    uint8_t m[97], K[32], V[32];
+    for (int i = 0; i < 32; i++) {
+        V[i] = 0x01;
+        K[i] = 0x00;
+    }
+    uint8_t xb[32], hb[32];
+    sc_to_be32(xb, d);
+    sc_to_be32(hb, e);
+    for (int oct = 0; oct < 2; oct++) {
+        for (int i = 0; i < 32; i++) {
+            m[i] = V[i];
+            m[33 + i] = xb[i];
+            m[65 + i] = hb[i];
+        }
+        m[32] = (uint8_t)oct;
+        hmac_sha256_k32(K, K, m, 97);
+        hmac_sha256_k32(V, K, V, 32);
+    }
+    uint32_t ok = 0;
+    for (int attempt = 0; attempt < 8 && !ok; attempt++) {
+        if (attempt) {
+            for (int i = 0; i < 32; i++) m[i] = V[i];
+            m[32] = 0x00;
+            hmac_sha256_k32(K, K, m, 33);
+            hmac_sha256_k32(V, K, V, 32);
+        }
+        hmac_sha256_k32(V, K, V, 32);
+        sc k;
+        ok = (1u - sc_from_be32(k, V)) & (1u - sc_is_zero(k));
+    }
+    // an invalid key still runs the pipeline on a harmless nonce (k = 1)
+    uint32_t good = ok & d_ok;
+    for (int i = 0; i < 32; i++) kout[i] = good ? V[i] : (uint8_t)(i == 31);
+    return (uint8_t)good;
+}
+
+template <int K>
+S256_HD void group_sign_finish(size_t t, size_t stride, size_t n, const uint8_t *priv32, const uint8_t *digest32,
+                               const uint8_t *kbuf, const uint8_t *valid, const uint8_t *r65, uint8_t *sig64,
+                               uint8_t *recid, uint8_t *status) {
+    sc pre[K];
+    sc run = sc_one();
+    for (int m = 0; m < K; m++) {
+        size_t i = t + (size_t)m * stride;
+        pre[m] = run;
+        if (i < n) {
+            sc k;
+            sc_from_be32(k, kbuf + 32 * i);  // in [1, n) by construction
+            sc_mul(run, run, k);
+        }
+    }
+    sc inv;
+    sc_invert(inv, run);
+    for (int m = K - 1; m >= 0; m--) {
+        size_t i = t + (size_t)m * stride;
+        if (i >= n) continue;
+        sc k, kinv, d, e, r, s, ns;
+        sc_from_be32(k, kbuf + 32 * i);
+        sc_mul(kinv, inv, pre[m]);
+        sc_mul(inv, inv, k);
+        sc_from_be32(d, priv32 + 32 * i);
+        sc_from_be32(e, digest32 + 32 * i);
+        const uint8_t *R = r65 + 65 * i;
+        uint32_t did_reduce = sc_from_be32(r, R + 1);
+        uint32_t y_odd = R[64] & 1u;
+        sc_mul(s, r, d);
+        sc_add(s, s, e);
+        sc_mul(s, s, kinv);
+        uint32_t neg = sc_is_gt_half_n(s);
+        sc_neg(ns, s);
+        sc_cmov(s, s, ns, neg);
+        uint32_t ok = (uint32_t)(valid[i] != 0) & (1u - sc_is_zero(r)) & (1u - sc_is_zero(s));
+        uint32_t km = 0u - ok;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            r.v[q] &= km;
+            s.v[q] &= km;
+        }
+        sc_to_be32(sig64 + 64 * i, r);
+        sc_to_be32(sig64 + 64 * i + 32, s);
+        recid[i] = (uint8_t)((((did_reduce << 1) | y_odd) ^ neg) & km);
+        status[i] = (uint8_t)(ok ? ST_OK : ST_INVALID);
+    }
+}
+
 }  // namespace s256

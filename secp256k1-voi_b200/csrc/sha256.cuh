@@ -92,4 +92,68 @@ S256_HD void bip340_challenge(uint8_t out32[32], const uint8_t *r32, const uint8
     }
 }
 
+// ---------------------------------------------------------------------------
+// byte-stream SHA-256 and HMAC-SHA256 with a 32-byte key: the HMAC_DRBG of the
+// reference's deterministic nonces (secec/ecdsa_k_rfc6979.go:36-145; Go's
+// crypto/hmac + crypto/sha256).  Branch-free in the data.
+// ---------------------------------------------------------------------------
+struct sha_stream {
+    uint32_t h[8];
+    uint8_t buf[64];
+    uint32_t fill;
+    uint64_t total;
+};
+S256_HD void sha_init(sha_stream &c) {
+    const uint32_t iv[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    for (int i = 0; i < 8; i++) c.h[i] = iv[i];
+    c.fill = 0;
+    c.total = 0;
+}
+S256_HD void sha_block_from_buf(sha_stream &c) {
+    uint32_t w[16];
+    for (int i = 0; i < 16; i++)
+        w[i] = ((uint32_t)c.buf[4 * i] << 24) | ((uint32_t)c.buf[4 * i + 1] << 16) | ((uint32_t)c.buf[4 * i + 2] << 8) | c.buf[4 * i + 3];
+    sha256_compress(c.h, w);
+    c.fill = 0;
+}
+S256_HD void sha_update(sha_stream &c, const uint8_t *d, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        c.buf[c.fill++] = d[i];
+        if (c.fill == 64) sha_block_from_buf(c);
+    }
+    c.total += n;
+}
+S256_HD void sha_final(sha_stream &c, uint8_t out[32]) {
+    uint64_t bits = c.total * 8;
+    c.buf[c.fill++] = 0x80;
+    if (c.fill > 56) {
+        while (c.fill < 64) c.buf[c.fill++] = 0;
+        sha_block_from_buf(c);
+    }
+    while (c.fill < 56) c.buf[c.fill++] = 0;
+    for (int i = 0; i < 8; i++) c.buf[56 + i] = (uint8_t)(bits >> (56 - 8 * i));
+    sha_block_from_buf(c);
+    for (int i = 0; i < 8; i++) {
+        out[4 * i] = (uint8_t)(c.h[i] >> 24);
+        out[4 * i + 1] = (uint8_t)(c.h[i] >> 16);
+        out[4 * i + 2] = (uint8_t)(c.h[i] >> 8);
+        out[4 * i + 3] = (uint8_t)c.h[i];
+    }
+}
+// out may alias key or msg
+S256_HD void hmac_sha256_k32(uint8_t out[32], const uint8_t key[32], const uint8_t *msg, size_t len) {
+    uint8_t pad[64], inner[32];
+    sha_stream c;
+    for (int i = 0; i < 64; i++) pad[i] = (uint8_t)(0x36 ^ (i < 32 ? key[i] : 0));
+    sha_init(c);
+    sha_update(c, pad, 64);
+    sha_update(c, msg, len);
+    sha_final(c, inner);
+    for (int i = 0; i < 64; i++) pad[i] = (uint8_t)(0x5c ^ (i < 32 ? key[i] : 0));
+    sha_init(c);
+    sha_update(c, pad, 64);
+    sha_update(c, inner, 32);
+    sha_final(c, out);
+}
+
 }  // namespace s256

@@ -90,6 +90,18 @@ func (e *Engine) RecoverPublicKeyBatch(digest32, sig65 []byte) (pk65 []byte, sta
 	return
 }
 
+// SignRFC6979Batch is PrivateKey.Sign(secec.RFC6979SHA256(), digest, EncodingCompactRecoverable) over rows of
+// private scalars (32 B) and digests (32 B): returns r||s rows (low-s), recovery ids and per-row status.
+func (e *Engine) SignRFC6979Batch(priv32, digest32 []byte) (sig64, recid, status []byte, err error) {
+	n := len(priv32) / 32
+	if len(digest32) != 32*n {
+		panic("secp256k1b200: SignRFC6979Batch: length mismatch")
+	}
+	sig64, recid, status = make([]byte, 64*n), make([]byte, n), make([]byte, n)
+	err = e.err(C.s256_ecdsa_sign_rfc6979(e.ctx, ptr(priv32), ptr(digest32), C.size_t(n), ptr(sig64), ptr(recid), ptr(status)))
+	return
+}
+
 // SchnorrVerifyBatch is bitcoin.SchnorrPublicKey.Verify (incl. lift_x) over x-only keys.
 func (e *Engine) SchnorrVerifyBatch(pkx32, msgs []byte, msgLen int, sig64 []byte) ([]bool, error) {
 	n := len(pkx32) / 32

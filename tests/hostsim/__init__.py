@@ -123,3 +123,10 @@ def msm_combine(parts):
     parts = _a(parts, 96); out = np.zeros(65, np.uint8); st = C.c_uint8(0)
     lib().sim_msm_combine(_p(parts), C.c_size_t(len(parts)), _p(out), C.byref(st))
     return out, st.value
+
+
+def ecdsa_sign_rfc6979(priv, digest):
+    priv, digest = _a(priv, 32), _a(digest, 32); n = len(priv)
+    sig = np.zeros((n, 64), np.uint8); rec = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8)
+    lib().sim_ecdsa_sign_rfc6979(_p(priv), _p(digest), C.c_size_t(n), _p(sig), _p(rec), _p(st))
+    return sig, rec, st

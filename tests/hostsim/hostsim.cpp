@@ -262,6 +262,22 @@ EXPORT void sim_msm_combine(const uint8_t *partials96, size_t m, uint8_t *out65,
     f.res[0] = acc;
     run_finish(f, 1, false, false, 0, out65, status, nullptr);
 }
+EXPORT void sim_ecdsa_sign_rfc6979(const uint8_t *priv32, const uint8_t *digest32, size_t n, uint8_t *sig64, uint8_t *recid,
+                                   uint8_t *status) {
+    ensure_tables();
+    scratch s(n);
+    std::vector<uint8_t> kbuf(32 * n), valid(n), r65(65 * n), rst(n);
+    for (size_t i = 0; i < n; i++) valid[i] = item_rfc6979_nonce(kbuf.data() + 32 * i, priv32 + 32 * i, digest32 + 32 * i);
+    for (size_t i = 0; i < n; i++) {
+        sc k;
+        sc_from_be32(k, kbuf.data() + 32 * i);
+        item_base_mult_ct(s.res[i], k, g_ct.data());
+    }
+    run_finish(s, n, false, false, 0, r65.data(), rst.data(), nullptr);
+    size_t stride = (n + K - 1) / K;
+    for (size_t t = 0; t < stride; t++)
+        group_sign_finish<K>(t, stride, n, priv32, digest32, kbuf.data(), valid.data(), r65.data(), sig64, recid, status);
+}
 EXPORT void sim_gen_table(int wbits, int nwin, uint8_t *out) {
     for (int w = 0; w < nwin; w++)
         for (uint32_t d = 1; d < (1u << wbits); d++) {

@@ -406,3 +406,30 @@ def check_msm_sharded(be, o, n=256, shards=4):
     assert st == 0
     got, st = be.msm_combine(np.zeros((0, 96), np.uint8))
     assert st == 2
+
+
+def check_sign_rfc6979(be, o, n=64):
+    """PrivateKey.Sign(RFC6979SHA256(), digest): the 20 sign KATs of the reference
+    (secec/ecdsa_k_test.go:244-278), then seeded keys/digests against the oracle, then the
+    sign -> verify and sign -> recover round trips."""
+    doc = load_golden("rfc6979.json")["rows"]
+    priv = rows([H(r["priv"]) for r in doc], 32)
+    dg = rows([H(r["digest"]) for r in doc], 32)
+    sig, rec, st = be.ecdsa_sign_rfc6979(priv, dg)
+    assert st.tolist() == [1] * len(doc)
+    for r, s_ in zip(doc, sig):
+        assert s_.tobytes().hex() == r["r"] + r["s"], r
+    ks = synth.base_mult_scalars(n, start=1000)           # arbitrary 32-byte strings
+    ks[0] = 0; ks[1] = np.frombuffer(b32(N), np.uint8); ks[2] = 0xFF        # invalid private keys
+    ks[3] = np.frombuffer(b32(1), np.uint8); ks[4] = np.frombuffer(b32(N - 1), np.uint8)
+    dgs = synth.base_mult_scalars(n, start=5000)
+    dgs[5] = 0; dgs[6] = 0xFF; dgs[7] = np.frombuffer(b32(N), np.uint8)
+    sig, rec, st = be.ecdsa_sign_rfc6979(ks, dgs)
+    esig, erec, est = o.batch_ecdsa_sign_rfc6979(ks, dgs)
+    assert np.array_equal(st, est) and np.array_equal(sig, esig) and np.array_equal(rec, erec)
+    assert st[:3].tolist() == [0, 0, 0] and not sig[:3].any()
+    good = st == 1
+    pk, pst = o.batch_scalar_base_mult(ks[good])
+    assert o.batch_ecdsa_verify(pk, dgs[good], sig[good], 1).all()   # low-s signatures verify
+    q, qst = o.batch_ecdsa_recover(dgs[good], np.concatenate([sig[good], rec[good, None]], axis=1))
+    assert (qst == 1).all() and np.array_equal(q, pk)

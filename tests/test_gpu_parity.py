@@ -75,6 +75,21 @@ def test_msm_sharded(engine, oracle):
     ps.check_msm_sharded(engine, oracle, n=4096, shards=8)
 
 
+def test_sign_rfc6979(engine, oracle):
+    ps.check_sign_rfc6979(engine, oracle, n=2048)
+    # sign on the GPU, verify on the GPU, at a size where every kernel runs full waves
+    n = 1 << 16
+    priv = ps.synth.base_mult_scalars(n, start=77)
+    priv[:, 0] &= 0x7F  # keep every key below n
+    dg = ps.synth.base_mult_scalars(n, start=99)
+    sig, rec, st = engine.ecdsa_sign_rfc6979(priv, dg)
+    assert (st == 1).all()
+    pk, _ = engine.scalar_base_mult(priv)
+    assert engine.ecdsa_verify(pk, dg, sig, 1).all()
+    q, qst = engine.ecdsa_recover(dg, np.concatenate([sig, rec[:, None]], axis=1))
+    assert (qst == 1).all() and np.array_equal(q, pk)
+
+
 def test_empty_and_ragged(engine):
     z = np.zeros((0, 32), np.uint8)
     out, st = engine.scalar_base_mult(z)

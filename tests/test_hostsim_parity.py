@@ -21,6 +21,7 @@ class Backend:
     msm = staticmethod(hs.msm)
     msm_partial = staticmethod(hs.msm_partial)
     msm_combine = staticmethod(hs.msm_combine)
+    ecdsa_sign_rfc6979 = staticmethod(hs.ecdsa_sign_rfc6979)
     debug_field_op = staticmethod(hs.field_op)
     debug_gen_table = staticmethod(hs.gen_table)
 
@@ -100,3 +101,7 @@ def test_msm_window_sizes(oracle):
 
 def test_msm_sharded(oracle):
     ps.check_msm_sharded(be, oracle, n=128, shards=4)
+
+
+def test_sign_rfc6979(oracle):
+    ps.check_sign_rfc6979(be, oracle, n=24)

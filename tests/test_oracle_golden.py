@@ -172,3 +172,19 @@ def test_nonce_reuse_pairs(oracle):
     assert oracle.ecdsa_verify(pk, m2, r + s2) == 1
     assert oracle.ecdsa_verify(pk, m1, r + s1) == 1
     assert oracle.ecdsa_verify(pk, m1, r + s1, 1) == 0  # s1 > n/2 (RejectMalleable)
+
+
+def test_rfc6979_sign_kats(oracle):
+    # secec/ecdsa_k_test.go:244-278: Sign(RFC6979SHA256(), sha256(msg)) must reproduce the vector's signature
+    import hmac as pyhmac
+    doc = load_golden("rfc6979.json")
+    for r in doc["rows"]:
+        sig, rec, st = oracle.ecdsa_sign_rfc6979(H(r["priv"]), H(r["digest"]))
+        assert st == 1 and sig.hex() == r["r"] + r["s"], r
+        pk, _ = oracle.scalar_base_mult(H(r["priv"]))
+        q, qst = oracle.ecdsa_recover(H(r["digest"]), sig + bytes([rec]))
+        assert qst == 1 and q == pk  # the recovery id is right
+    k, m = bytes(range(32)), b"abc" * 41
+    assert oracle.hmac_sha256(k, m) == pyhmac.new(k, m, hashlib.sha256).digest()
+    for bad in (bytes(32), b"\xff" * 32, N.to_bytes(32, "big")):
+        assert oracle.ecdsa_sign_rfc6979(bad, bytes(32))[2] == 0
