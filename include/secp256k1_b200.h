@@ -149,6 +149,14 @@ int s256_schnorr_verify(s256_ctx *ctx, const uint8_t *pkx32, const uint8_t *msg,
 int s256_schnorr_verify_dev(s256_ctx *ctx, const uint8_t *d_pkx32, const uint8_t *d_msg, size_t msg_len,
                             const uint8_t *d_sig64, size_t n, uint8_t *d_ok, void *stream);
 
+/* --- bitcoin.SchnorrPrivateKey.Sign (secec/bitcoin/schnorr.go:111-147 -> signSchnorr :322): BIP-340
+ *     signing with caller-supplied auxiliary randomness (32 B per row; the reference draws it from
+ *     its entropy source, :130-141).  priv32 as for NewPrivateKey; constant time. */
+int s256_schnorr_sign(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *msg, size_t msg_len, const uint8_t *aux32,
+                      size_t n, uint8_t *sig64, uint8_t *status);
+int s256_schnorr_sign_dev(s256_ctx *ctx, const uint8_t *d_priv32, const uint8_t *d_msg, size_t msg_len,
+                          const uint8_t *d_aux32, size_t n, uint8_t *d_sig64, uint8_t *d_status, void *stream);
+
 /* --- Point.MultiScalarMult[Vartime] (point_mul_multi.go:25,73): sum k_i*P_i
  *     over this context's items -> one 65-byte point.  n == 0 gives the
  *     identity.  *status: S256_ST_OK / S256_ST_IDENTITY / S256_ST_INVALID (a

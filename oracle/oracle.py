@@ -165,6 +165,12 @@ def hmac_sha256(key32, msg):
     o = _out(32); msg = bytes(msg); lib().orc_hmac_sha256(_buf(key32, 32), msg, C.c_size_t(len(msg)), o); return o.raw
 
 
+def schnorr_sign(priv32, msg, aux32):
+    sig = _out(64); msg = bytes(msg)
+    st = lib().orc_schnorr_sign(_buf(priv32, 32), msg, C.c_size_t(len(msg)), _buf(aux32, 32), sig)
+    return sig.raw, st
+
+
 def schnorr_verify(pkx32, msg, sig64):
     msg = bytes(msg)
     return lib().orc_schnorr_verify(_buf(pkx32, 32), msg, C.c_size_t(len(msg)), _buf(sig64, 64))

@@ -883,6 +883,53 @@ static int ecdsa_sign_rfc6979_one(const u8 priv32[32], const u8 digest32[32], u8
     }
 }
 
+/* secec/bitcoin/schnorr.go:309-320 */
+static void tagged_hash3(u8 out[32], const char *tag, const u8 *a, size_t al, const u8 *b, size_t bl, const u8 *c, size_t cl) {
+    u8 th[32];
+    sha256_ctx x;
+    orc_sha256((const u8 *)tag, strlen(tag), th);
+    sha256_init(&x);
+    sha256_update(&x, th, 32); sha256_update(&x, th, 32);
+    if (al) sha256_update(&x, a, al);
+    if (bl) sha256_update(&x, b, bl);
+    if (cl) sha256_update(&x, c, cl);
+    sha256_final(&x, out);
+}
+/* secec/bitcoin/schnorr.go:322-400 signSchnorr (+ NewSchnorrPrivateKeyFromECDSA :161-180 for d and P):
+ * d' canonical non-zero; P = d'G; d = d' or n - d' (even y); t = d xor H_aux(aux);
+ * k' = H_nonce(t || Px || m) mod n (zero is an error); R = k'G; k = k' or n - k';
+ * e = H_challenge(Rx || Px || m) mod n; sig = Rx || (k + e d). */
+static int schnorr_sign_one(const u8 priv32[32], const u8 *msg, size_t msg_len, const u8 aux32[32], u8 sig64[64]) {
+    sc dp, d, kp, k, e, sum;
+    memset(sig64, 0, 64);
+    if (!sc_set_canonical_bytes(&dp, priv32) || sc_is_zero(&dp)) return ST_INVALID;
+    pt P, R, sP, sR;
+    pt_scalar_base_mult(&P, &dp);
+    pt_rescale(&sP, &P);
+    u8 px[32], rx[32], db[32], t[32], rnd[32], eb[32];
+    fe_bytes(px, &sP.x);
+    d = dp;
+    if (fe_is_odd(&sP.y)) sc_neg(&d, &dp);
+    sc_bytes(db, &d);
+    tagged_hash3(t, "BIP0340/aux", aux32, 32, NULL, 0, NULL, 0);
+    for (int i = 0; i < 32; i++) t[i] ^= db[i];
+    tagged_hash3(rnd, "BIP0340/nonce", t, 32, px, 32, msg, msg_len);
+    sc_set_bytes(&kp, rnd);
+    if (sc_is_zero(&kp)) return ST_INVALID;
+    pt_scalar_base_mult(&R, &kp);
+    pt_rescale(&sR, &R);
+    fe_bytes(rx, &sR.x);
+    k = kp;
+    if (fe_is_odd(&sR.y)) sc_neg(&k, &kp);
+    tagged_hash3(eb, "BIP0340/challenge", rx, 32, px, 32, msg, msg_len);
+    sc_set_bytes(&e, eb);
+    sc_mul(&sum, &e, &d);
+    sc_add(&sum, &k, &sum);
+    memcpy(sig64, rx, 32);
+    sc_bytes(sig64 + 32, &sum);
+    return ST_OK;
+}
+
 /* ------------------------------------------------------------------------- */
 /* Exported single-item entry points (ctypes)                                 */
 /* ------------------------------------------------------------------------- */
@@ -1036,6 +1083,10 @@ EXPORT int orc_ecdsa_sign_rfc6979(const u8 priv32[32], const u8 digest32[32], u8
     return ecdsa_sign_rfc6979_one(priv32, digest32, sig64, recid);
 }
 EXPORT void orc_hmac_sha256(const u8 key[32], const u8 *msg, size_t len, u8 out[32]) { hmac_sha256(out, key, msg, len); }
+EXPORT int orc_schnorr_sign(const u8 priv32[32], const u8 *msg, size_t msg_len, const u8 aux32[32], u8 sig64[64]) {
+    orc_init();
+    return schnorr_sign_one(priv32, msg, msg_len, aux32, sig64);
+}
 EXPORT int orc_schnorr_verify(const u8 pkx32[32], const u8 *msg, size_t msg_len, const u8 sig64[64]) {
     orc_init();
     return schnorr_verify_one(pkx32, msg, msg_len, sig64);

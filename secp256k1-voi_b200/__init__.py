@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "s256_ecdsa_verify_asn1", "s256_bitcoin_verify_asn1",
     "s256_ecdsa_recover", "s256_ecdsa_recover_dev",
     "s256_ecdsa_sign_rfc6979", "s256_ecdsa_sign_rfc6979_dev",
-    "s256_schnorr_verify", "s256_schnorr_verify_dev",
+    "s256_schnorr_verify", "s256_schnorr_verify_dev", "s256_schnorr_sign", "s256_schnorr_sign_dev",
     "s256_msm", "s256_msm_partial", "s256_msm_combine",
     "s256_debug_gen_table", "s256_debug_field_op", "s256_microbench_imad",
     "s256_microbench_variant", "s256_profile_enable", "s256_profile_read",
@@ -384,6 +384,29 @@ class Engine:
         self._check(self._lib.s256_schnorr_verify(self._ctx, self._hp(pk), self._hp(m), C.c_size_t(m.shape[1] if n else 0),
                                                   self._hp(sg), C.c_size_t(n), self._hp(ok)), "schnorr_verify")
         return ok
+
+    # -- bitcoin.SchnorrPrivateKey.Sign (secec/bitcoin/schnorr.go:111,322) ---------------------
+    def schnorr_sign(self, priv32, msg, aux32):
+        if _is_torch_cuda(priv32):
+            import torch
+            n = priv32.numel() // 32
+            msg_len = msg.numel() // n if n else 0
+            sig = torch.empty((n, 64), dtype=torch.uint8, device=priv32.device)
+            st = torch.empty(n, dtype=torch.uint8, device=priv32.device)
+            a = self._dev_args(priv32, msg, aux32, sig, st)
+            self._check(self._lib.s256_schnorr_sign_dev(self._ctx, a[0], a[1], C.c_size_t(msg_len), a[2], C.c_size_t(n),
+                                                        a[3], a[4], self._stream()), "schnorr_sign_dev")
+            return sig, st
+        d, ax = _host(priv32, 32), _host(aux32, 32)
+        n = len(d)
+        m = _host(msg, 0).reshape(n, -1) if n else np.zeros((0, 0), np.uint8)
+        if len(ax) != n:
+            raise ValueError("length mismatch")
+        sig = np.zeros((n, 64), np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_schnorr_sign(self._ctx, self._hp(d), self._hp(m), C.c_size_t(m.shape[1] if n else 0),
+                                                self._hp(ax), C.c_size_t(n), self._hp(sig), self._hp(st)), "schnorr_sign")
+        return sig, st
 
     # -- Point.MultiScalarMult[Vartime] (point_mul_multi.go:25,73) -------------
     def msm(self, k32, pt65, vartime=True):

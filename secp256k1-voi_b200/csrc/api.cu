@@ -216,6 +216,24 @@ __global__ void __launch_bounds__(S256_TPB) k_sign_finish(size_t n, const uint8_
     group_sign_finish<K>(t, stride, n, priv32, digest32, kbuf, valid, r65, sig64, recid, status);
 }
 
+__global__ void __launch_bounds__(S256_TPB) k_schnorr_nonce(const uint8_t *priv32, const uint8_t *p65, const uint8_t *msg,
+                                                            size_t msg_len, const uint8_t *aux32, size_t n,
+                                                            uint8_t *kbuf, uint8_t *valid) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    valid[i] = item_schnorr_nonce(kbuf + 32 * i, priv32 + 32 * i, p65 + 65 * i, msg + msg_len * i, msg_len, aux32 + 32 * i);
+}
+__global__ void __launch_bounds__(S256_TPB) k_schnorr_sign_finish(const uint8_t *priv32, const uint8_t *p65,
+                                                                  const uint8_t *r65, const uint8_t *kbuf,
+                                                                  const uint8_t *msg, size_t msg_len,
+                                                                  const uint8_t *valid, size_t n, uint8_t *sig64,
+                                                                  uint8_t *status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    item_schnorr_sign_finish(sig64 + 64 * i, status + i, priv32 + 32 * i, p65 + 65 * i, r65 + 65 * i, kbuf + 32 * i,
+                             msg + msg_len * i, msg_len, valid[i]);
+}
+
 // ---- Pippenger MSM (msm.cuh) -------------------------------------------------
 template <bool SCATTER>
 __global__ void __launch_bounds__(S256_TPB) k_msm_digits(const uint8_t *k32, size_t n, msm_plan plan, uint32_t *counts,
@@ -714,6 +732,27 @@ static int chunk_sign(s256_ctx *ctx, const view &v, const uint8_t *priv32, const
     return S256_SUCCESS;
 }
 
+// SchnorrPrivateKey.Sign: P = d'G -> nonce -> R = k'G -> finish.  Byte scratch: P in v.out, R and k' in the
+// per-item table area (1536 B/item, unused by this path); both secret buffers are wiped afterwards.
+static int chunk_schnorr_sign(s256_ctx *ctx, const view &v, const uint8_t *priv32, const uint8_t *msg, size_t msg_len,
+                              const uint8_t *aux32, size_t n, uint8_t *sig64, uint8_t *status, cudaStream_t s) {
+    uint8_t *arena = reinterpret_cast<uint8_t *>(v.tbl);
+    uint8_t *r65 = arena, *kbuf = arena + 65 * n;
+    s256_launch_base_mult_ct(priv32, n, ctx->ct_tab, v.res, s);
+    DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, v.res, (const uint8_t *)nullptr,
+                         (const uint8_t *)nullptr, v.cstat, 0, v.out, v.sfl, (const uint8_t *)nullptr));
+    LAUNCH(ctx, k_schnorr_nonce, grid_for(n), 0, s, priv32, v.out, msg, msg_len, aux32, n, kbuf, v.pvalid);
+    s256_launch_base_mult_ct(kbuf, n, ctx->ct_tab, v.res, s);
+    ctx->launches.fetch_add(2, std::memory_order_relaxed);
+    DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, v.res, (const uint8_t *)nullptr,
+                         (const uint8_t *)nullptr, v.cstat, 0, r65, v.sfl, (const uint8_t *)nullptr));
+    LAUNCH(ctx, k_schnorr_sign_finish, grid_for(n), 0, s, priv32, v.out, r65, kbuf, msg, msg_len, v.pvalid, n, sig64,
+           status);
+    CK(cudaMemsetAsync(kbuf, 0, 32 * n, s));
+    CK(cudaMemsetAsync(v.res, 0, sizeof(pt) * n, s));
+    return S256_SUCCESS;
+}
+
 // Runs `body(offset, count)` over chunks of at most cap items.
 template <typename F>
 static int for_chunks(s256_ctx *ctx, size_t n, F body) {
@@ -995,6 +1034,47 @@ extern "C" int s256_ecdsa_sign_rfc6979(s256_ctx *ctx, const uint8_t *priv32, con
         CK(cudaMemcpyAsync(recid + off, d_rec, c, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(status + off, d_st, c, cudaMemcpyDeviceToHost, s));
         CK(cudaMemsetAsync(v.in_a, 0, 32 * c, s));  // wipe the staged private keys
+        return S256_SUCCESS;
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+
+extern "C" int s256_schnorr_sign_dev(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *msg, size_t msg_len,
+                                     const uint8_t *aux32, size_t n, uint8_t *sig64, uint8_t *status, void *stream) {
+    ENTER(ctx);
+    if (n && (!priv32 || (!msg && msg_len) || !aux32 || !sig64 || !status)) return S256_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        return chunk_schnorr_sign(ctx, view_at(ctx, 0), priv32 + 32 * off, msg + msg_len * off, msg_len, aux32 + 32 * off,
+                                  c, sig64 + 64 * off, status + off, s);
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+extern "C" int s256_schnorr_sign(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *msg, size_t msg_len,
+                                 const uint8_t *aux32, size_t n, uint8_t *sig64, uint8_t *status) {
+    ENTER(ctx);
+    if (n && (!priv32 || (!msg && msg_len) || !aux32 || !sig64 || !status)) return S256_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    size_t need = (msg_len ? msg_len : 1) * (n < ctx->cap ? n : ctx->cap);
+    if (need > ctx->in_b_bytes) {
+        if (ctx->in_b) cudaFree(ctx->in_b);
+        ctx->in_b = nullptr;
+        ctx->in_b_bytes = 0;
+        CK(cudaMalloc(&ctx->in_b, need));
+        ctx->in_b_bytes = need;
+    }
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        view v = view_at(ctx, 0);
+        CK(cudaMemcpyAsync(ctx->in_a, priv32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        if (msg_len) CK(cudaMemcpyAsync(ctx->in_b, msg + msg_len * off, msg_len * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->in_c, aux32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        uint8_t *d_sig = reinterpret_cast<uint8_t *>(v.aff);  // 64 B per item, unused by this path
+        int r = chunk_schnorr_sign(ctx, v, ctx->in_a, ctx->in_b, msg_len, ctx->in_c, c, d_sig, ctx->st, s);
+        if (r != S256_SUCCESS) return r;
+        CK(cudaMemcpyAsync(sig64 + 64 * off, d_sig, 64 * c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemsetAsync(ctx->in_a, 0, 32 * c, s));
+        CK(cudaStreamSynchronize(s));
         return S256_SUCCESS;
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
@@ -1348,6 +1428,7 @@ extern "C" double s256_mac32_per_item(const char *name) {
     if (s == "schnorr_verify") return sqrt_fe + (ZN + split) + dsm + affine;
     if (s == "double_scalar_mult_basepoint_vartime") return oncurve + split + dsm + affine;
     if (s == "scalar_base_mult") return CT_NW * mix + affine;
+    if (s == "schnorr_sign") return 2 * (CT_NW * mix + affine) + 2 * ZN;  // + ~9 SHA-256 blocks
     if (s == "ecdsa_sign_rfc6979") return CT_NW * mix + affine + (5 * ZN + inv_sc / INV_K);  // + 22 SHA-256 blocks
     if (s == "scalar_mult" || s == "ecdh") {
         const double tab = (CTM_TS / 2) * dbl + (CTM_TS / 2 - 1) * mix;

@@ -863,4 +863,69 @@ S256_HD void group_sign_finish(size_t t, size_t stride, size_t n, const uint8_t 
     }
 }
 
+// ---------------------------------------------------------------------------
+// BIP-340 signing: SchnorrPrivateKey.Sign (secec/bitcoin/schnorr.go:322-400), keys
+// built like NewSchnorrPrivateKeyFromECDSA (:161-180).  Secrets throughout: branch-free.
+//   P = d'*G (ct fixed-base kernel) -> nonce kernel: d = d' or n - d' (even y(P)),
+//   t = d xor H_aux(aux), k' = H_nonce(t || Px || m) mod n  ->  R = k'*G  ->
+//   finish: k = k' or n - k' (even y(R)), e = H_challenge(Rx || Px || m) mod n, sig = Rx || k + e*d.
+// The reference's post-signing self-check (:393, :402-418) recomputes R from (s - d*e)*G; with
+// deterministic arithmetic it cannot fail, and the parity tests verify every signature instead.
+// ---------------------------------------------------------------------------
+S256_HD uint8_t item_schnorr_nonce(uint8_t kout[32], const uint8_t *priv32, const uint8_t *p65, const uint8_t *msg,
+                                   size_t msg_len, const uint8_t *aux32) {
+    sc dp, d, nd;
+    uint32_t ok = (1u - sc_from_be32(dp, priv32)) & (1u - sc_is_zero(dp));
+    sc_neg(nd, dp);
+    sc_cmov(d, dp, nd, (uint32_t)(p65[64] & 1u));
+    uint8_t t[32], db[32], rnd[32];
+    sc_to_be32(db, d);
+    sha_stream c;
+    sha_init_tagged(c, TAG_AUX);
+    sha_update(c, aux32, 32);
+    sha_final(c, t);
+    for (int i = 0; i < 32; i++) t[i] ^= db[i];
+    sha_init_tagged(c, TAG_NONCE);
+    sha_update(c, t, 32);
+    sha_update(c, p65 + 1, 32);
+    sha_update(c, msg, msg_len);
+    sha_final(c, rnd);
+    sc kp;
+    sc_from_be32(kp, rnd);
+    ok &= 1u - sc_is_zero(kp);  // errKPrimeIsZero
+    sc one = sc_one();
+    sc_cmov(kp, one, kp, ok);   // a harmless nonce keeps the pipeline well defined
+    sc_to_be32(kout, kp);
+    return (uint8_t)ok;
+}
+S256_HD void item_schnorr_sign_finish(uint8_t *sig64, uint8_t *status, const uint8_t *priv32, const uint8_t *p65,
+                                      const uint8_t *r65, const uint8_t *kbuf, const uint8_t *msg, size_t msg_len,
+                                      uint32_t valid) {
+    sc dp, d, nd, kp, k, nk, e, sum;
+    sc_from_be32(dp, priv32);
+    sc_neg(nd, dp);
+    sc_cmov(d, dp, nd, (uint32_t)(p65[64] & 1u));
+    sc_from_be32(kp, kbuf);
+    sc_neg(nk, kp);
+    sc_cmov(k, kp, nk, (uint32_t)(r65[64] & 1u));
+    uint8_t eb[32];
+    sha_stream c;
+    sha_init_tagged(c, TAG_CHALLENGE);
+    sha_update(c, r65 + 1, 32);
+    sha_update(c, p65 + 1, 32);
+    sha_update(c, msg, msg_len);
+    sha_final(c, eb);
+    sc_from_be32(e, eb);
+    sc_mul(sum, e, d);
+    sc_add(sum, k, sum);
+    uint8_t m = (uint8_t)(0u - (valid & 1u));
+    uint8_t sb[32];
+    sc_to_be32(sb, sum);
+    for (int i = 0; i < 32; i++) {
+        sig64[i] = r65[1 + i] & m;
+        sig64[32 + i] = sb[i] & m;
+    }
+    *status = (uint8_t)(valid ? ST_OK : ST_INVALID);
+}
+
 }  // namespace s256

@@ -156,4 +156,17 @@ S256_HD void hmac_sha256_k32(uint8_t out[32], const uint8_t key[32], const uint8
     sha_final(c, out);
 }
 
+// BIP-340 tagged hashes (secec/bitcoin/schnorr.go:34-36, 309-320): the state after the 64-byte
+// SHA256(tag) || SHA256(tag) block is a constant per tag.
+enum { TAG_AUX = 0, TAG_NONCE = 1, TAG_CHALLENGE = 2 };
+S256_HD void sha_init_tagged(sha_stream &c, int tag) {
+    const uint32_t mid[3][8] = {
+        {0x24dd3219u, 0x4eba7e70u, 0xca0fabb9u, 0x0fa3166du, 0x3afbe4b1u, 0x4c44df97u, 0x4aac2739u, 0x249e850au},
+        {0x46615b35u, 0xf4bfbff7u, 0x9f8dc671u, 0x83627ab3u, 0x60217180u, 0x57358661u, 0x21a29e54u, 0x68b07b4cu},
+        {0x9cecba11u, 0x23925381u, 0x11679112u, 0xd1627e0fu, 0x97c87550u, 0x003cc765u, 0x90f61164u, 0x33e9b66au}};
+    for (int i = 0; i < 8; i++) c.h[i] = mid[tag][i];
+    c.fill = 0;
+    c.total = 64;
+}
+
 }  // namespace s256

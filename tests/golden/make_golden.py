@@ -167,7 +167,8 @@ def bip340():
     rows = []
     with open(f"{REF}/secec/bitcoin/testdata/bip-0340-test-vectors.csv") as f:
         for row in csv.DictReader(f):
-            rows.append({"index": int(row["index"]), "sk": row["secret key"].lower(), "pk": row["public key"].lower(),
+            rows.append({"index": int(row["index"]), "sk": row["secret key"].lower(), "aux": row["aux_rand"].lower(),
+                         "pk": row["public key"].lower(),
                          "msg": row["message"].lower(), "sig": row["signature"].lower(),
                          "valid": row["verification result"] == "TRUE", "comment": row["comment"]})
     return rows

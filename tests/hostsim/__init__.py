@@ -130,3 +130,11 @@ def ecdsa_sign_rfc6979(priv, digest):
     sig = np.zeros((n, 64), np.uint8); rec = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8)
     lib().sim_ecdsa_sign_rfc6979(_p(priv), _p(digest), C.c_size_t(n), _p(sig), _p(rec), _p(st))
     return sig, rec, st
+
+
+def schnorr_sign(priv, msg, aux):
+    priv, aux = _a(priv, 32), _a(aux, 32); n = len(priv)
+    msg = np.ascontiguousarray(msg, dtype=np.uint8).reshape(n, -1)
+    sig = np.zeros((n, 64), np.uint8); st = np.zeros(n, np.uint8)
+    lib().sim_schnorr_sign(_p(priv), _p(msg), C.c_size_t(msg.shape[1]), _p(aux), C.c_size_t(n), _p(sig), _p(st))
+    return sig, st

@@ -278,6 +278,30 @@ EXPORT void sim_ecdsa_sign_rfc6979(const uint8_t *priv32, const uint8_t *digest3
     for (size_t t = 0; t < stride; t++)
         group_sign_finish<K>(t, stride, n, priv32, digest32, kbuf.data(), valid.data(), r65.data(), sig64, recid, status);
 }
+EXPORT void sim_schnorr_sign(const uint8_t *priv32, const uint8_t *msg, size_t msg_len, const uint8_t *aux32, size_t n,
+                             uint8_t *sig64, uint8_t *status) {
+    ensure_tables();
+    scratch s(n);
+    std::vector<uint8_t> p65(65 * n), r65(65 * n), kbuf(32 * n), valid(n), st(n);
+    for (size_t i = 0; i < n; i++) {
+        sc k;
+        sc_from_be32(k, priv32 + 32 * i);
+        item_base_mult_ct(s.res[i], k, g_ct.data());
+    }
+    run_finish(s, n, false, false, 0, p65.data(), st.data(), nullptr);
+    for (size_t i = 0; i < n; i++)
+        valid[i] = item_schnorr_nonce(kbuf.data() + 32 * i, priv32 + 32 * i, p65.data() + 65 * i, msg + msg_len * i, msg_len,
+                                      aux32 + 32 * i);
+    for (size_t i = 0; i < n; i++) {
+        sc k;
+        sc_from_be32(k, kbuf.data() + 32 * i);
+        item_base_mult_ct(s.res[i], k, g_ct.data());
+    }
+    run_finish(s, n, false, false, 0, r65.data(), st.data(), nullptr);
+    for (size_t i = 0; i < n; i++)
+        item_schnorr_sign_finish(sig64 + 64 * i, status + i, priv32 + 32 * i, p65.data() + 65 * i, r65.data() + 65 * i,
+                                 kbuf.data() + 32 * i, msg + msg_len * i, msg_len, valid[i]);
+}
 EXPORT void sim_gen_table(int wbits, int nwin, uint8_t *out) {
     for (int w = 0; w < nwin; w++)
         for (uint32_t d = 1; d < (1u << wbits); d++) {

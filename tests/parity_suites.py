@@ -433,3 +433,33 @@ def check_sign_rfc6979(be, o, n=64):
     assert o.batch_ecdsa_verify(pk, dgs[good], sig[good], 1).all()   # low-s signatures verify
     q, qst = o.batch_ecdsa_recover(dgs[good], np.concatenate([sig[good], rec[good, None]], axis=1))
     assert (qst == 1).all() and np.array_equal(q, pk)
+
+
+def check_schnorr_sign(be, o, n=48):
+    """SchnorrPrivateKey.Sign: the BIP-340 vector rows that carry a secret key (bit-exact signature),
+    then seeded keys against the oracle and sign -> verify."""
+    doc = [r for r in load_golden("bip340.json")["rows"] if r["sk"]]
+    by_len = {}
+    for r in doc:
+        by_len.setdefault(len(r["msg"]) // 2, []).append(r)
+    for mlen, rs in by_len.items():
+        priv = rows([H(r["sk"]) for r in rs], 32)
+        aux = rows([H(r["aux"]) for r in rs], 32)
+        msg = rows([H(r["msg"]) for r in rs], mlen) if mlen else np.zeros((len(rs), 0), np.uint8)
+        sig, st = be.schnorr_sign(priv, msg, aux)
+        assert st.tolist() == [1] * len(rs)
+        for r, s_ in zip(rs, sig):
+            assert s_.tobytes().hex() == r["sig"], r["index"]
+    priv = synth.base_mult_scalars(n, start=3000)
+    priv[0] = 0; priv[1] = np.frombuffer(b32(N), np.uint8); priv[2] = np.frombuffer(b32(N - 1), np.uint8)
+    priv[3] = np.frombuffer(b32(1), np.uint8)
+    msg = synth.base_mult_scalars(n, start=4000)
+    aux = synth.base_mult_scalars(n, start=6000); aux[4] = 0; aux[5] = 0xFF
+    sig, st = be.schnorr_sign(priv, msg, aux)
+    exp = [o.schnorr_sign(priv[i].tobytes(), msg[i].tobytes(), aux[i].tobytes()) for i in range(n)]
+    assert st.tolist() == [e[1] for e in exp]
+    assert sig.tobytes() == b"".join(e[0] for e in exp)
+    assert st[0] == 0 and st[1] == 0 and st[2] == 1 and not sig[:2].any()
+    good = st == 1
+    pk, _ = o.batch_scalar_base_mult(priv[good])
+    assert o.batch_schnorr_verify(pk[:, 1:33].copy(), msg[good], sig[good]).all()

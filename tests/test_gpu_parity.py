@@ -90,6 +90,18 @@ def test_sign_rfc6979(engine, oracle):
     assert (qst == 1).all() and np.array_equal(q, pk)
 
 
+def test_schnorr_sign(engine, oracle):
+    ps.check_schnorr_sign(engine, oracle, n=1024)
+    n = 1 << 15
+    priv = ps.synth.base_mult_scalars(n, start=11); priv[:, 0] &= 0x7F
+    msg = ps.synth.base_mult_scalars(n, start=12)
+    aux = ps.synth.base_mult_scalars(n, start=13)
+    sig, st = engine.schnorr_sign(priv, msg, aux)
+    assert (st == 1).all()
+    pk, _ = engine.scalar_base_mult(priv)
+    assert engine.schnorr_verify(pk[:, 1:33].copy(), msg, sig).all()
+
+
 def test_empty_and_ragged(engine):
     z = np.zeros((0, 32), np.uint8)
     out, st = engine.scalar_base_mult(z)

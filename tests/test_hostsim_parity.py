@@ -22,6 +22,7 @@ class Backend:
     msm_partial = staticmethod(hs.msm_partial)
     msm_combine = staticmethod(hs.msm_combine)
     ecdsa_sign_rfc6979 = staticmethod(hs.ecdsa_sign_rfc6979)
+    schnorr_sign = staticmethod(hs.schnorr_sign)
     debug_field_op = staticmethod(hs.field_op)
     debug_gen_table = staticmethod(hs.gen_table)
 
@@ -105,3 +106,7 @@ def test_msm_sharded(oracle):
 
 def test_sign_rfc6979(oracle):
     ps.check_sign_rfc6979(be, oracle, n=24)
+
+
+def test_schnorr_sign(oracle):
+    ps.check_schnorr_sign(be, oracle, n=16)

@@ -188,3 +188,20 @@ def test_rfc6979_sign_kats(oracle):
     assert oracle.hmac_sha256(k, m) == pyhmac.new(k, m, hashlib.sha256).digest()
     for bad in (bytes(32), b"\xff" * 32, N.to_bytes(32, "big")):
         assert oracle.ecdsa_sign_rfc6979(bad, bytes(32))[2] == 0
+
+
+def test_bip340_sign_rows(oracle):
+    # secec/bitcoin/schnorr_test.go:149-246: rows carrying a secret key must reproduce the signature
+    doc = load_golden("bip340.json")
+    raw = {}
+    import csv
+    n = 0
+    for r in doc["rows"]:
+        if not r["sk"]:
+            continue
+        aux = r.get("aux")
+        assert aux is not None
+        sig, st = oracle.schnorr_sign(H(r["sk"]), H(r["msg"]), H(aux))
+        assert st == 1 and sig.hex() == r["sig"], r["index"]
+        n += 1
+    assert n >= 8
