@@ -153,3 +153,34 @@ def test_full_size_properties(engine):
     b = engine.ecdsa_verify(w["pk65"], w["digest32"], w["sig64"])
     assert hashlib.sha256(a.tobytes()).digest() == hashlib.sha256(b.tobytes()).digest()
     assert int(a.sum()) == n - n // 16
+
+
+def test_concurrent_callers_share_one_context(engine, oracle):
+    """cgo calls arrive on arbitrary OS threads: one context, many threads, mixed entry points."""
+    import threading
+    w = ps.synth.ecdsa_batch(3000, ps.oracle_base_mult(oracle))
+    ks = ps.synth.base_mult_scalars(2000)
+    exp_pts, exp_st = oracle.batch_scalar_base_mult(ks)
+    errors = []
+
+    def verify_loop():
+        try:
+            for _ in range(6):
+                assert np.array_equal(engine.ecdsa_verify(w["pk65"], w["digest32"], w["sig64"]), w["expected"])
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    def sbm_loop():
+        try:
+            for _ in range(6):
+                out, st = engine.scalar_base_mult(ks)
+                assert np.array_equal(out, exp_pts) and np.array_equal(st, exp_st)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=f) for f in (verify_loop, sbm_loop, verify_loop, sbm_loop)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

@@ -1,0 +1,77 @@
+"""Property tests (hypothesis) over the host-simulated kernel logic, in the spirit of the reference's
+randomised consistency tests (point_test.go:262-347: fast path == bit-serial double-and-add after
+rescale) but seeded and biased towards the values where windowed / GLV / carry code breaks."""
+import numpy as np
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+import hostsim as hs
+import parity_suites as ps
+
+N, P = ps.N, ps.P
+EDGE = [0, 1, 2, 3, 7, 8, 15, 16, 17, 31, 32, N - 1, N - 2, N, N + 1, N // 2, N // 2 + 1, 2**128 - 1, 2**128, 2**128 + 1,
+        2**255, 2**256 - 1, 2**64 - 1, 2**192, 0x5363AD4CC05C30E0A5261C028812645A122E22EA20816678DF02967C1B23BD72,
+        0xAC9C52B33FA3CF1F5AD9E3FD77ED9BA4A880B9FC8EC739C2E0CFC810B51283CF]
+# scalars: edges, sparse / dense bit patterns, runs of identical nibbles (window recoding carries), random
+scalar = st.one_of(
+    st.sampled_from(EDGE),
+    st.integers(0, 2**256 - 1),
+    st.builds(lambda nib, cnt, sh: (int(("%x" % nib) * cnt, 16) << sh) % 2**256, st.integers(1, 15), st.integers(1, 64), st.integers(0, 200)),
+    st.builds(lambda a, b: (1 << a) | (1 << b), st.integers(0, 255), st.integers(0, 255)),
+    st.builds(lambda a: (N - a) % 2**256, st.integers(0, 2**40)),
+)
+SET = dict(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck))
+
+
+def b32(x):
+    return int(x).to_bytes(32, "big")
+
+
+def rows(ints):
+    return np.frombuffer(b"".join(b32(x) for x in ints), np.uint8).reshape(-1, 32).copy()
+
+
+@settings(**SET)
+@given(st.lists(scalar, min_size=1, max_size=6))
+def test_base_mult_matches_trivial(oracle, ks):
+    got, stt = hs.scalar_base_mult(rows(ks))
+    g, _ = oracle.scalar_base_mult(b32(1))
+    for k, o65, s in zip(ks, got, stt):
+        exp, est = oracle.scalar_mult(b32(k), g, 2)  # bit-serial double-and-add
+        assert (s, o65.tobytes()) == (est, exp)
+
+
+@settings(**SET)
+@given(st.lists(st.tuples(scalar, scalar, st.integers(1, 2**64)), min_size=1, max_size=4))
+def test_dsm_and_ct_mult_match_trivial(oracle, items):
+    u1 = [a for a, _, _ in items]; u2 = [b for _, b, _ in items]
+    pts, _ = oracle.batch_scalar_base_mult(rows([d for _, _, d in items]))
+    got, stt = hs.double_scalar_mult(rows(u1), rows(u2), pts)
+    ctg, cts = hs.scalar_mult(rows(u2), pts)
+    g, _ = oracle.scalar_base_mult(b32(1))
+    for i in range(len(items)):
+        a, ast = oracle.scalar_mult(b32(u1[i]), g, 2)
+        b, bst = oracle.scalar_mult(b32(u2[i]), pts[i].tobytes(), 2)
+        exp, est = oracle.point_add(a, ast, b, bst)
+        assert (stt[i], got[i].tobytes()) == (est, exp)
+        assert (cts[i], ctg[i].tobytes()) == (bst, b)   # constant-time ladder == bit-serial too
+
+
+@settings(**SET)
+@given(st.lists(st.tuples(scalar, st.integers(1, 2**64)), min_size=0, max_size=40), st.sampled_from([0, 4, 5, 8, 13, 16]))
+def test_msm_matches_sum_of_products(oracle, items, c):
+    ks = rows([k for k, _ in items]) if items else np.zeros((0, 32), np.uint8)
+    pts = oracle.batch_scalar_base_mult(rows([d for _, d in items]))[0] if items else np.zeros((0, 65), np.uint8)
+    got, s = hs.msm(ks, pts, vartime=True, force_c=c if len(items) else 0)
+    total = sum((k % N) * d for k, d in items) % N
+    exp, est = oracle.scalar_base_mult(b32(total))
+    assert (s, got.tobytes()) == (est, exp)
+
+
+@settings(**SET)
+@given(st.integers(0, 2**256 - 1), st.integers(0, 2**256 - 1))
+def test_field_ops(a, b):
+    A, B = rows([a]), rows([b])
+    assert int.from_bytes(hs.field_op(0, A, B)[0].tobytes(), "big") == a * b % P
+    assert int.from_bytes(hs.field_op(1, A, B)[0].tobytes(), "big") == (a + b) % P
+    assert int.from_bytes(hs.field_op(2, A, B)[0].tobytes(), "big") == (a - b) % P
+    assert int.from_bytes(hs.field_op(16, A, B)[0].tobytes(), "big") == (a % N) * (b % N) % N
