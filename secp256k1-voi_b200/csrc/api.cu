@@ -37,12 +37,12 @@ __global__ void __launch_bounds__(S256_TPB) k_gen_table(apt *out, int wb, size_t
     item_gen_multiple(a, w, d, wb);
     out[idx] = a;
 }
-// the signed constant-time table: out[w][j] = (j + 1) * 16^w * G, j = 0..7, w = 0..64
+// the signed constant-time table: out[w][j] = (j + 1) * 2^(CT_WB*w) * G
 __global__ void __launch_bounds__(S256_TPB) k_gen_ct_table(apt *out) {
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint32_t)(CT_NW * CT_SZ)) return;
     apt a;
-    item_gen_multiple(a, idx / CT_SZ, idx % CT_SZ + 1u, 4);
+    item_gen_multiple(a, idx / CT_SZ, idx % CT_SZ + 1u, CT_WB);
     out[idx] = a;
 }
 

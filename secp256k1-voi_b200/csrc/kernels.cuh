@@ -35,10 +35,24 @@ constexpr int DSM_TS = 1 << (DSM_W - 1);       // table entries 1..TS
 constexpr int COMB_WB = S256_COMB_WB;
 constexpr int COMB_NW = (256 + COMB_WB - 1) / COMB_WB;
 constexpr int COMB_SZ = 1 << COMB_WB;
-// constant-time fixed-base table: signed 4-bit digits in [-7, 8] -> 64 windows + one carry window,
-// entries (j + 1) * 16^w * G for j = 0..7 (33 280 bytes: fits shared memory several times per SM)
-constexpr int CT_NW = 65;
-constexpr int CT_SZ = 8;
+// constant-time fixed-base table: signed CT_WB-bit digits in [-(2^(WB-1) - 1), 2^(WB-1)]; entries
+// (j + 1) * 2^(WB*w) * G for j = 0 .. 2^(WB-1) - 1.  WB = 5: 52 windows x 16 entries = 53 248 bytes
+// (fits shared memory four times per SM); WB = 4: 65 windows (64 + carry) x 8 entries = 33 280 bytes.
+#ifndef S256_CT_WB
+#define S256_CT_WB 5
+#endif
+constexpr int CT_WB = S256_CT_WB;
+constexpr int CT_NW = (257 + CT_WB - 1) / CT_WB;  // 256 scalar bits + the recoding carry
+constexpr int CT_SZ = 1 << (CT_WB - 1);
+// digit w of the recoding: bits [WB*w, WB*w + WB) of k plus the incoming carry
+S256_HD uint32_t ct_window_bits(const sc &k, int w) {
+    int bit = w * CT_WB;
+    if (bit >= 256) return 0u;
+    int limb = bit >> 5, sh = bit & 31;
+    uint32_t v = k.v[limb] >> sh;
+    if (sh + CT_WB > 32 && limb + 1 < 8) v |= k.v[limb + 1] << (32 - sh);
+    return v & ((1u << CT_WB) - 1u);
+}
 // constant-time variable-base ladder (ScalarMult / ECDH): signed window
 #ifndef S256_CTW
 #define S256_CTW 3
@@ -560,9 +574,9 @@ S256_HD void item_base_mult_ct(pt &acc, const sc &k, const apt *tab /* [CT_NW][C
 #pragma unroll 1
 #endif
     for (int w = 0; w < CT_NW; w++) {
-        uint32_t v = (w < 64 ? (k.v[(w >> 3) & 7] >> ((w & 7) * 4)) & 0xFu : 0u) + carry;  // 0 .. 16
-        carry = (v + 7u) >> 4;                                                             // 1 iff v > 8
-        int32_t d = (int32_t)v - (int32_t)(carry << 4);                                    // -7 .. 8
+        uint32_t v = ct_window_bits(k, w) + carry;                       // 0 .. 2^WB
+        carry = (v + (uint32_t)CT_SZ - 1u) >> CT_WB;                      // 1 iff v > 2^(WB-1)
+        int32_t d = (int32_t)v - (int32_t)(carry << CT_WB);               // -(2^(WB-1) - 1) .. 2^(WB-1)
         uint32_t sign = (uint32_t)d >> 31;
         uint32_t mag = (uint32_t)((d ^ -(int32_t)sign) + (int32_t)sign);
         apt sel;
@@ -602,9 +616,9 @@ S256_HD void item_base_mult_ct_part(pt &acc, const sc &k, const apt *tab, int pa
     uint32_t carry = 0;
 #pragma unroll 1
     for (int w = 0; w < CT_NW; w++) {
-        uint32_t v = (w < 64 ? (k.v[(w >> 3) & 7] >> ((w & 7) * 4)) & 0xFu : 0u) + carry;
-        carry = (v + 7u) >> 4;
-        dig[w] = (int8_t)((int32_t)v - (int32_t)(carry << 4));
+        uint32_t v = ct_window_bits(k, w) + carry;
+        carry = (v + (uint32_t)CT_SZ - 1u) >> CT_WB;
+        dig[w] = (int8_t)((int32_t)v - (int32_t)(carry << CT_WB));
     }
     pt_set_identity(acc);
     const int iters = (CT_NW + T - 1) / T;

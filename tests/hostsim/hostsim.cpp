@@ -24,7 +24,7 @@ static void ensure_tables() {
     if (!g_ct.empty()) return;
     g_ct.resize((size_t)CT_NW * CT_SZ);
     for (size_t idx = 0; idx < g_ct.size(); idx++)
-        item_gen_multiple(g_ct[idx], (uint32_t)(idx / CT_SZ), (uint32_t)(idx % CT_SZ) + 1u, 4);
+        item_gen_multiple(g_ct[idx], (uint32_t)(idx / CT_SZ), (uint32_t)(idx % CT_SZ) + 1u, CT_WB);
 }
 // The comb has 2^20 entries; generating it with the bit-serial routine is too
 // slow on one CPU core, so the simulation fills only the entries a batch uses.
