@@ -1,34 +1,15 @@
-// api.cu -- C ABI (include/secp256k1_b200.h) over the sm_100a kernels.
+// api.cu -- C ABI (include/secp256k1_b200.h) over the sm_100a kernels: lifecycle, the verification /
+// multiplication entry points and their kernels.  MSM lives in api_msm.cu, signing in api_sign.cu.
 //
 // Host side only orchestrates: device buffers, copies, launches.  There is no
 // CPU implementation of any curve operation in this library: without a CUDA
 // device every entry point fails with S256_ERR_NO_DEVICE.
-#include <cuda_runtime.h>
-
-#include <atomic>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <mutex>
-#include <new>
-#include <string>
-#include <utility>
-#include <vector>
-
-#include "../../include/secp256k1_b200.h"
-#include "kernels.cuh"
+#include "ctx.h"
 #include "microbench.cuh"
-#include "msm.cuh"
-#include <cub/device/device_scan.cuh>
-#include "launchers.h"
-
-using namespace s256;
 
 // ---------------------------------------------------------------------------
 // __global__ wrappers
 // ---------------------------------------------------------------------------
-#define S256_TPB 128
-
 __global__ void __launch_bounds__(S256_TPB) k_gen_table(apt *out, int wb, size_t total) {
     size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
@@ -173,7 +154,7 @@ constexpr size_t CT_SMEM_BYTES = 0;
 #else
 constexpr size_t CT_SMEM_BYTES = (size_t)CTM_TS * 6 * S256_TPB * sizeof(uint4);
 #endif
-static void s256_launch_scalar_mult_ct(size_t n, const apt *aff, const uint8_t *k32, pt *tbl, pt *res, cudaStream_t s) {
+void s256_launch_scalar_mult_ct(size_t n, const apt *aff, const uint8_t *k32, pt *tbl, pt *res, cudaStream_t s) {
     if (n == 0) return;
     k_scalar_mult_ct<<<(unsigned)((n + S256_TPB - 1) / S256_TPB), S256_TPB, CT_SMEM_BYTES, s>>>(n, aff, k32, tbl, res);
 }
@@ -197,179 +178,6 @@ __global__ void __launch_bounds__(S256_TPB) k_finish_affine(size_t n, const pt *
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= stride) return;
     group_finish<K>(t, stride, n, res, pvalid, sfl, comb_status, mode, out, status, sig64);
-}
-
-// ---- deterministic signing (kernels.cuh) ----
-__global__ void __launch_bounds__(S256_TPB) k_rfc6979_nonce(const uint8_t *priv32, const uint8_t *digest32, size_t n,
-                                                            uint8_t *kbuf, uint8_t *valid) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    valid[i] = item_rfc6979_nonce(kbuf + 32 * i, priv32 + 32 * i, digest32 + 32 * i);
-}
-template <int K>
-__global__ void __launch_bounds__(S256_TPB) k_sign_finish(size_t n, const uint8_t *priv32, const uint8_t *digest32,
-                                                          const uint8_t *kbuf, const uint8_t *valid, const uint8_t *r65,
-                                                          uint8_t *sig64, uint8_t *recid, uint8_t *status) {
-    size_t stride = (n + K - 1) / K;
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= stride) return;
-    group_sign_finish<K>(t, stride, n, priv32, digest32, kbuf, valid, r65, sig64, recid, status);
-}
-
-__global__ void __launch_bounds__(S256_TPB) k_schnorr_nonce(const uint8_t *priv32, const uint8_t *p65, const uint8_t *msg,
-                                                            size_t msg_len, const uint8_t *aux32, size_t n,
-                                                            uint8_t *kbuf, uint8_t *valid) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    valid[i] = item_schnorr_nonce(kbuf + 32 * i, priv32 + 32 * i, p65 + 65 * i, msg + msg_len * i, msg_len, aux32 + 32 * i);
-}
-__global__ void __launch_bounds__(S256_TPB) k_schnorr_sign_finish(const uint8_t *priv32, const uint8_t *p65,
-                                                                  const uint8_t *r65, const uint8_t *kbuf,
-                                                                  const uint8_t *msg, size_t msg_len,
-                                                                  const uint8_t *valid, size_t n, uint8_t *sig64,
-                                                                  uint8_t *status) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    item_schnorr_sign_finish(sig64 + 64 * i, status + i, priv32 + 32 * i, p65 + 65 * i, r65 + 65 * i, kbuf + 32 * i,
-                             msg + msg_len * i, msg_len, valid[i]);
-}
-
-// ---- Pippenger MSM (msm.cuh) -------------------------------------------------
-template <bool SCATTER>
-__global__ void __launch_bounds__(S256_TPB) k_msm_digits(const uint8_t *k32, size_t n, msm_plan plan, uint32_t *counts,
-                                                         uint32_t *cursor, uint32_t *entries) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    sc k;
-    sc_from_be32(k, k32 + 32 * i);
-    int32_t d[MSM_MAX_WIN];
-    msm_digits(d, k, plan);
-    for (int w = 0; w < plan.nwin; w++) {
-        int32_t dw = d[w];
-        if (dw == 0) continue;
-        uint32_t mag = (uint32_t)(dw < 0 ? -dw : dw);
-        uint32_t b = (uint32_t)w * (uint32_t)plan.nb + (mag - 1u);
-        if (!SCATTER) {
-            atomicAdd(&counts[b], 1u);
-        } else {
-            uint32_t pos = atomicAdd(&cursor[b], 1u);
-            entries[pos] = ((uint32_t)i << 1) | (uint32_t)(dw < 0);
-        }
-    }
-}
-// nsl[b] = slices of bucket b (counts -> slice counts), then scanned into sl_off
-__global__ void __launch_bounds__(S256_TPB) k_msm_slice_counts(uint32_t total, const uint32_t *counts, uint32_t *nsl) {
-    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < total) nsl[b] = msm_slices_of(counts[b]);
-    if (b == total) nsl[b] = 0;
-}
-__global__ void __launch_bounds__(S256_TPB) k_msm_slices(uint32_t max_slices, uint32_t total, const uint32_t *sl_off,
-                                                         const uint32_t *offsets, const uint32_t *entries,
-                                                         const apt *aff, pt *slice_sum) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= max_slices || s >= sl_off[total]) return;
-    uint32_t st, en;
-    msm_slice_range(st, en, s, sl_off, offsets, total);
-    pt r;
-    msm_bucket_sum(r, entries, st, en, aff);
-    slice_sum[s] = r;
-}
-#define S256_MSM_WT 128
-// grid (blocks per window, nwin): every thread reduces MSM_SEG buckets, the CTA folds its threads
-__global__ void __launch_bounds__(S256_MSM_WT) k_msm_windows(msm_plan plan, const pt *slice_sum, const uint32_t *sl_off,
-                                                             pt *winpart, int parts) {
-    __shared__ pt sh[S256_MSM_WT];
-    int w = blockIdx.y, t = threadIdx.x;
-    int nbw = msm_window_buckets(plan, w);
-    int seg = msm_seg_for(nbw);
-    int lo = (blockIdx.x * S256_MSM_WT + t) * seg, hi = lo + seg;
-    if (hi > nbw) hi = nbw;
-    pt s;
-    if (lo < hi)
-        msm_segment(s, slice_sum, sl_off, (uint32_t)w * (uint32_t)plan.nb, lo, hi);
-    else
-        pt_set_identity(s);
-    sh[t] = s;
-    __syncthreads();
-    for (int stride = S256_MSM_WT / 2; stride >= 1; stride >>= 1) {
-        if (t < stride) {
-            pt a = sh[t], b = sh[t + stride];
-            pt_add(a, a, b);
-            sh[t] = a;
-        }
-        __syncthreads();
-    }
-    if (t == 0) winpart[w * parts + blockIdx.x] = sh[0];
-}
-// win[w * parts] = sum of the `parts` CTA partials of window w (one thread per window)
-__global__ void k_msm_fold(int nwin, pt *winpart, int parts) {
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nwin) return;
-    pt acc = winpart[w * parts];
-    for (int q = 1; q < parts; q++) {
-        pt t = winpart[w * parts + q];
-        pt_add(acc, acc, t);
-    }
-    winpart[w * parts] = acc;
-}
-// acc (device, projective) += Horner(window partials); first = overwrite
-__global__ void k_msm_final(msm_plan plan, const pt *winpart, int parts, pt *acc, int first) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    pt r;
-    msm_horner(r, winpart, plan, 1, parts);
-    if (!first) {
-        pt a = *acc;
-        pt_add(r, r, a);
-    }
-    *acc = r;
-}
-// out[t] = sum of in[t], in[t + nout], ...   (tree levels of the constant-time MSM)
-__global__ void __launch_bounds__(S256_TPB) k_reduce_points(const pt *in, size_t n, pt *out, size_t nout) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nout) return;
-    pt acc;
-    pt_set_identity(acc);
-    for (size_t i = t; i < n; i += nout) {
-        pt q = in[i];
-        pt_add(acc, acc, q);
-    }
-    out[t] = acc;
-}
-__global__ void k_acc_point(const pt *in, pt *acc, int first) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    pt r = *in;
-    if (!first) {
-        pt a = *acc;
-        pt_add(r, r, a);
-    }
-    *acc = r;
-}
-__global__ void __launch_bounds__(S256_TPB) k_any_invalid(const uint8_t *pvalid, size_t n, uint32_t *flag) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && pvalid[i] == 0) atomicOr(flag, 1u);
-}
-// partial96 rows -> one projective sum; rows must be points on the curve (or the identity)
-__global__ void k_combine_partials(const uint8_t *partials96, size_t m, pt *out, uint32_t *flag) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    pt acc;
-    pt_set_identity(acc);
-    for (size_t j = 0; j < m; j++) {
-        pt q;
-        pt_from_be96(q, partials96 + 96 * j);
-        uint32_t ok = fe_limbs_are_canonical(q.x) & fe_limbs_are_canonical(q.y) & fe_limbs_are_canonical(q.z) &
-                      pt_on_curve(q);
-        if (!ok) {
-            atomicOr(flag, 1u);
-            continue;
-        }
-        pt_add(acc, acc, q);
-    }
-    *out = acc;
-}
-__global__ void k_export_partial(const pt *acc, uint8_t *out96) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    pt a = *acc;
-    pt_to_be96(out96, a);
 }
 
 __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a32, const uint8_t *b32, size_t n,
@@ -405,77 +213,6 @@ __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a3
         sc_to_be32(out32 + 32 * i, r);
     }
 }
-
-// ---------------------------------------------------------------------------
-// context
-// ---------------------------------------------------------------------------
-struct s256_ctx {
-    int device = -1;
-    size_t cap = 0;
-    std::mutex mu;
-    cudaStream_t stream = nullptr, stream2 = nullptr;
-    std::string last_err;
-    std::atomic<uint64_t> launches{0};
-    // constant tables
-    apt *comb = nullptr;    // [COMB_NW][COMB_SZ]
-    apt *ct_tab = nullptr;  // [CT_NW][CT_SZ]
-    // per-chunk scratch
-    apt *aff = nullptr;
-    sc *u1 = nullptr;
-    int8_t *dig1 = nullptr, *dig2 = nullptr;
-    uint8_t *sfl = nullptr, *pvalid = nullptr, *cstat = nullptr;
-    pt *tbl = nullptr, *res = nullptr;
-    // staging for the host-pointer entry points
-    uint8_t *in_a = nullptr, *in_b = nullptr, *in_c = nullptr, *out = nullptr, *st = nullptr;
-    size_t in_b_bytes = 0;
-    unsigned long long *sink = nullptr;
-    // MSM scratch (allocated on first use)
-    size_t msm_cap = 0;
-    uint32_t *msm_counts = nullptr, *msm_offsets = nullptr, *msm_cursor = nullptr, *msm_entries = nullptr;
-    uint32_t *msm_flag = nullptr;
-    uint32_t *msm_nsl = nullptr, *msm_sloff = nullptr;
-    size_t msm_max_slices = 0;
-    pt *msm_buckets = nullptr, *msm_win = nullptr, *msm_acc = nullptr, *msm_tmp = nullptr;
-    void *msm_cub = nullptr;
-    size_t msm_cub_bytes = 0;
-    // optional per-kernel timing of the dominant kernel (bench.py roofline)
-    bool profiling = false;
-    // sub-chunks per host-pointer call (S256_PIPE_PARTS).  Measured (scripts/e2e_parts.py): splitting does not
-    // pay -- the batched-inversion kernel is latency bound, so its cost multiplies with the part count.
-    int pipe_parts = 1;
-    cudaEvent_t ev_decode = nullptr;
-    bool use_reg_ladder = true;  // S256_LADDER=vm selects the frame-form ladder (A/B measurements)
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dsm_events;
-};
-
-#define CK(call)                                                                     \
-    do {                                                                             \
-        cudaError_t e_ = (call);                                                     \
-        if (e_ != cudaSuccess) {                                                     \
-            ctx->last_err = std::string(#call) + ": " + cudaGetErrorString(e_);      \
-            return S256_ERR_CUDA;                                                    \
-        }                                                                            \
-    } while (0)
-
-static inline unsigned grid_for(size_t n) { return (unsigned)((n + S256_TPB - 1) / S256_TPB); }
-#define LAUNCH(ctx, kern, grid, smem, strm, ...)                  \
-    do {                                                          \
-        kern<<<(grid), S256_TPB, (smem), (strm)>>>(__VA_ARGS__);  \
-        (ctx)->launches.fetch_add(1, std::memory_order_relaxed);  \
-    } while (0)
-
-struct dev_guard {
-    int prev = -1;
-    explicit dev_guard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-    }
-    ~dev_guard() {
-        int cur = -1;
-        cudaGetDevice(&cur);
-        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
-    }
-};
 
 extern "C" const char *s256_strerror(int code) {
     switch (code) {
@@ -584,33 +321,15 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
 // ---------------------------------------------------------------------------
 // device-pointer pipelines (one chunk <= cap)
 // ---------------------------------------------------------------------------
-// A window into the per-item scratch arrays starting at item `off`: sub-chunks of one call work on
-// disjoint windows, so they can be in flight on different streams at the same time.
-struct view {
-    apt *aff;
-    sc *u1;
-    int8_t *dig1, *dig2;
-    uint8_t *sfl, *pvalid, *cstat;
-    pt *tbl, *res;
-    uint8_t *in_a, *in_b, *in_c, *out, *st;
-};
-static view view_at(const s256_ctx *ctx, size_t off) {
-    view v;
-    v.aff = ctx->aff + off;
-    v.u1 = ctx->u1 + off;
-    v.dig1 = ctx->dig1 + (size_t)DSM_ND * off;  // [digit][item] inside the window
-    v.dig2 = ctx->dig2 + (size_t)DSM_ND * off;
-    v.sfl = ctx->sfl + off;
-    v.pvalid = ctx->pvalid + off;
-    v.cstat = ctx->cstat + off;
-    v.tbl = ctx->tbl + (size_t)DSM_TS * off;
-    v.res = ctx->res + off;
-    v.in_a = ctx->in_a + 65 * off;
-    v.in_b = ctx->in_b + 32 * off;
-    v.in_c = ctx->in_c + 65 * off;
-    v.out = ctx->out + 65 * off;
-    v.st = ctx->st + off;
-    return v;
+void s256_launch_decode_uncompressed(s256_ctx *ctx, const uint8_t *pt65, size_t n, apt *aff, uint8_t *pvalid,
+                                     cudaStream_t s) {
+    LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pt65, n, aff, pvalid);
+}
+void s256_launch_finish_affine(s256_ctx *ctx, size_t n, const pt *res, const uint8_t *pvalid, const uint8_t *sfl,
+                               uint8_t *cstat, int mode, uint8_t *out, uint8_t *status, const uint8_t *sig64,
+                               cudaStream_t s) {
+    DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, res, pvalid, sfl, cstat, mode, out,
+                         status, sig64));
 }
 
 static void enqueue_dsm(s256_ctx *ctx, const view &v, size_t n, cudaStream_t s) {
@@ -631,23 +350,7 @@ static void enqueue_dsm(s256_ctx *ctx, const view &v, size_t n, cudaStream_t s) 
         ctx->dsm_events.emplace_back(e0, e1);
     }
 }
-#ifndef S256_INV_K
-#define S256_INV_K 32
-#endif
-constexpr int INV_K = S256_INV_K;
-// Inversion group size by batch size: K items share one Fermat chain but are processed serially by
-// one thread, so small batches use small groups (n = 4096 with K = 32 would run on 128 threads).
-static inline int inv_k_for(size_t n) { return n >= ((size_t)1 << 19) ? INV_K : (n >= ((size_t)1 << 16) ? 4 : 1); }
-#define DISPATCH_K(n, CALL)               \
-    do {                                  \
-        switch (inv_k_for(n)) {           \
-            case 1: { constexpr int KK = 1; CALL; } break;  \
-            case 4: { constexpr int KK = 4; CALL; } break;  \
-            default: { constexpr int KK = INV_K; CALL; } break; \
-        }                                 \
-    } while (0)
-constexpr int MSM_MAX_PARTS = 16;  // (2^16 buckets) / (128 threads * 32 buckets)
-static inline unsigned grid_for_groups(size_t n, int k) { return grid_for((n + k - 1) / k); }
+
 
 // The scalar kernel needs digest + signature only and the decode kernel the public keys only: when the
 // caller passes a second stream, decode runs there (behind the key copy) and joins through an event.
@@ -715,94 +418,9 @@ static int chunk_scalar_mult(s256_ctx *ctx, const view &v, const uint8_t *k32, c
     return S256_SUCCESS;
 }
 
-// PrivateKey.Sign(RFC6979SHA256(), digest): nonce -> k*G (ct) -> affine -> (r, s, v).  Scratch use: k in
-// v.u1 (32 B/item), R in v.out (65 B/item), validity in v.pvalid; the nonce buffer is wiped afterwards.
-static int chunk_sign(s256_ctx *ctx, const view &v, const uint8_t *priv32, const uint8_t *digest32, size_t n,
-                      uint8_t *sig64, uint8_t *recid, uint8_t *status, cudaStream_t s) {
-    uint8_t *kbuf = reinterpret_cast<uint8_t *>(v.u1);
-    LAUNCH(ctx, k_rfc6979_nonce, grid_for(n), 0, s, priv32, digest32, n, kbuf, v.pvalid);
-    s256_launch_base_mult_ct(kbuf, n, ctx->ct_tab, v.res, s);
-    ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, v.res, (const uint8_t *)nullptr,
-                         (const uint8_t *)nullptr, v.cstat, 0, v.out, v.sfl, (const uint8_t *)nullptr));
-    DISPATCH_K(n, LAUNCH(ctx, k_sign_finish<KK>, grid_for_groups(n, KK), 0, s, n, priv32, digest32, kbuf, v.pvalid, v.out,
-                         sig64, recid, status));
-    CK(cudaMemsetAsync(kbuf, 0, 32 * n, s));
-    CK(cudaMemsetAsync(v.res, 0, sizeof(pt) * n, s));
-    return S256_SUCCESS;
-}
-
-// SchnorrPrivateKey.Sign: P = d'G -> nonce -> R = k'G -> finish.  Byte scratch: P in v.out, R and k' in the
-// per-item table area (1536 B/item, unused by this path); both secret buffers are wiped afterwards.
-static int chunk_schnorr_sign(s256_ctx *ctx, const view &v, const uint8_t *priv32, const uint8_t *msg, size_t msg_len,
-                              const uint8_t *aux32, size_t n, uint8_t *sig64, uint8_t *status, cudaStream_t s) {
-    uint8_t *arena = reinterpret_cast<uint8_t *>(v.tbl);
-    uint8_t *r65 = arena, *kbuf = arena + 65 * n;
-    s256_launch_base_mult_ct(priv32, n, ctx->ct_tab, v.res, s);
-    DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, v.res, (const uint8_t *)nullptr,
-                         (const uint8_t *)nullptr, v.cstat, 0, v.out, v.sfl, (const uint8_t *)nullptr));
-    LAUNCH(ctx, k_schnorr_nonce, grid_for(n), 0, s, priv32, v.out, msg, msg_len, aux32, n, kbuf, v.pvalid);
-    s256_launch_base_mult_ct(kbuf, n, ctx->ct_tab, v.res, s);
-    ctx->launches.fetch_add(2, std::memory_order_relaxed);
-    DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, v.res, (const uint8_t *)nullptr,
-                         (const uint8_t *)nullptr, v.cstat, 0, r65, v.sfl, (const uint8_t *)nullptr));
-    LAUNCH(ctx, k_schnorr_sign_finish, grid_for(n), 0, s, priv32, v.out, r65, kbuf, msg, msg_len, v.pvalid, n, sig64,
-           status);
-    CK(cudaMemsetAsync(kbuf, 0, 32 * n, s));
-    CK(cudaMemsetAsync(v.res, 0, sizeof(pt) * n, s));
-    return S256_SUCCESS;
-}
-
-// Runs `body(offset, count)` over chunks of at most cap items.
-template <typename F>
-static int for_chunks(s256_ctx *ctx, size_t n, F body) {
-    for (size_t off = 0; off < n; off += ctx->cap) {
-        size_t c = n - off < ctx->cap ? n - off : ctx->cap;
-        int rc = body(off, c);
-        if (rc != S256_SUCCESS) return rc;
-    }
-    return S256_SUCCESS;
-}
-// Host-pointer calls: the chunk is cut into sub-chunks that alternate between two streams, each
-// doing its own H2D -> kernels -> D2H on a disjoint scratch window, so the copies of one sub-chunk
-// overlap the kernels of the other.  body(view, global offset, count, stream).
-template <typename F>
-static int pipelined(s256_ctx *ctx, size_t n, F body) {
-    const size_t min_sub = 65536;
-    for (size_t off = 0; off < n; off += ctx->cap) {
-        size_t c = n - off < ctx->cap ? n - off : ctx->cap;
-        size_t parts = c / min_sub;
-        if (parts > (size_t)ctx->pipe_parts) parts = (size_t)ctx->pipe_parts;
-        if (parts < 1) parts = 1;
-        size_t sub = (c + parts - 1) / parts;
-        sub = (sub + 127) & ~(size_t)127;
-        int k = 0;
-        for (size_t so = 0; so < c; so += sub, k++) {
-            size_t sc_ = c - so < sub ? c - so : sub;
-            int rc = body(view_at(ctx, so), off + so, sc_, (k & 1) ? ctx->stream2 : ctx->stream);
-            if (rc != S256_SUCCESS) return rc;
-        }
-        CK(cudaStreamSynchronize(ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream2));
-    }
-    return S256_SUCCESS;
-}
-static int check_launch(s256_ctx *ctx) {
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        ctx->last_err = std::string("kernel launch: ") + cudaGetErrorString(e);
-        return S256_ERR_CUDA;
-    }
-    return S256_SUCCESS;
-}
-
 // ---------------------------------------------------------------------------
 // exported entry points
 // ---------------------------------------------------------------------------
-#define ENTER(ctx)                       \
-    if (!(ctx)) return S256_ERR_ARG;     \
-    std::lock_guard<std::mutex> lk_((ctx)->mu); \
-    dev_guard dg_((ctx)->device)
 
 extern "C" int s256_ecdsa_verify_dev(s256_ctx *ctx, const uint8_t *pk, const uint8_t *dg, const uint8_t *sig,
                                      uint32_t flags, size_t n, uint8_t *ok, void *stream) {
@@ -1008,78 +626,6 @@ extern "C" int s256_point_decompress(s256_ctx *ctx, const uint8_t *pt33, size_t 
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
 
-extern "C" int s256_ecdsa_sign_rfc6979_dev(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *digest32, size_t n,
-                                           uint8_t *sig64, uint8_t *recid, uint8_t *status, void *stream) {
-    ENTER(ctx);
-    if (n && (!priv32 || !digest32 || !sig64 || !recid || !status)) return S256_ERR_ARG;
-    cudaStream_t s = (cudaStream_t)stream;
-    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        return chunk_sign(ctx, view_at(ctx, 0), priv32 + 32 * off, digest32 + 32 * off, c, sig64 + 64 * off, recid + off,
-                          status + off, s);
-    });
-    return rc != S256_SUCCESS ? rc : check_launch(ctx);
-}
-extern "C" int s256_ecdsa_sign_rfc6979(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *digest32, size_t n,
-                                       uint8_t *sig64, uint8_t *recid, uint8_t *status) {
-    ENTER(ctx);
-    if (n && (!priv32 || !digest32 || !sig64 || !recid || !status)) return S256_ERR_ARG;
-    int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t s) {
-        CK(cudaMemcpyAsync(v.in_a, priv32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(v.in_b, digest32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
-        // outputs staged in v.in_c (sig64), v.cstat is busy inside finish_affine -> recid in v.in_a + 32*cap? use tail of in_c
-        uint8_t *d_sig = v.in_c, *d_rec = v.in_c + 64 * c, *d_st = v.st;
-        int r = chunk_sign(ctx, v, v.in_a, v.in_b, c, d_sig, d_rec, d_st, s);
-        if (r != S256_SUCCESS) return r;
-        CK(cudaMemcpyAsync(sig64 + 64 * off, d_sig, 64 * c, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(recid + off, d_rec, c, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(status + off, d_st, c, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemsetAsync(v.in_a, 0, 32 * c, s));  // wipe the staged private keys
-        return S256_SUCCESS;
-    });
-    return rc != S256_SUCCESS ? rc : check_launch(ctx);
-}
-
-extern "C" int s256_schnorr_sign_dev(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *msg, size_t msg_len,
-                                     const uint8_t *aux32, size_t n, uint8_t *sig64, uint8_t *status, void *stream) {
-    ENTER(ctx);
-    if (n && (!priv32 || (!msg && msg_len) || !aux32 || !sig64 || !status)) return S256_ERR_ARG;
-    cudaStream_t s = (cudaStream_t)stream;
-    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        return chunk_schnorr_sign(ctx, view_at(ctx, 0), priv32 + 32 * off, msg + msg_len * off, msg_len, aux32 + 32 * off,
-                                  c, sig64 + 64 * off, status + off, s);
-    });
-    return rc != S256_SUCCESS ? rc : check_launch(ctx);
-}
-extern "C" int s256_schnorr_sign(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *msg, size_t msg_len,
-                                 const uint8_t *aux32, size_t n, uint8_t *sig64, uint8_t *status) {
-    ENTER(ctx);
-    if (n && (!priv32 || (!msg && msg_len) || !aux32 || !sig64 || !status)) return S256_ERR_ARG;
-    cudaStream_t s = ctx->stream;
-    size_t need = (msg_len ? msg_len : 1) * (n < ctx->cap ? n : ctx->cap);
-    if (need > ctx->in_b_bytes) {
-        if (ctx->in_b) cudaFree(ctx->in_b);
-        ctx->in_b = nullptr;
-        ctx->in_b_bytes = 0;
-        CK(cudaMalloc(&ctx->in_b, need));
-        ctx->in_b_bytes = need;
-    }
-    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        view v = view_at(ctx, 0);
-        CK(cudaMemcpyAsync(ctx->in_a, priv32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
-        if (msg_len) CK(cudaMemcpyAsync(ctx->in_b, msg + msg_len * off, msg_len * c, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->in_c, aux32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
-        uint8_t *d_sig = reinterpret_cast<uint8_t *>(v.aff);  // 64 B per item, unused by this path
-        int r = chunk_schnorr_sign(ctx, v, ctx->in_a, ctx->in_b, msg_len, ctx->in_c, c, d_sig, ctx->st, s);
-        if (r != S256_SUCCESS) return r;
-        CK(cudaMemcpyAsync(sig64 + 64 * off, d_sig, 64 * c, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemsetAsync(ctx->in_a, 0, 32 * c, s));
-        CK(cudaStreamSynchronize(s));
-        return S256_SUCCESS;
-    });
-    return rc != S256_SUCCESS ? rc : check_launch(ctx);
-}
-
 // PublicKey.Verify with EncodingASN1 (secec/ecdsa.go:171-228): parse on the host (codecs.cpp), then the
 // same batch as the compact path; rows the parser rejects come back false.
 extern "C" int s256_ecdsa_verify_asn1(s256_ctx *ctx, const uint8_t *pk65, const uint8_t *digest32, const uint8_t *der,
@@ -1114,187 +660,6 @@ extern "C" int s256_bitcoin_verify_asn1(s256_ctx *ctx, const uint8_t *pk65, cons
     if (rc != S256_SUCCESS) return rc;
     for (size_t i = 0; i < n; i++) ok[i] &= bip[i];
     return S256_SUCCESS;
-}
-
-// ---------------------------------------------------------------------------
-// MSM
-// ---------------------------------------------------------------------------
-static size_t msm_entries_capacity(const s256_ctx *ctx) {
-    // nwin * n entries; the planner uses c >= 12 once n >= 2^16 (nwin <= 22), and c >= 4 (nwin <= 64) below
-    size_t cap = ctx->cap;
-    size_t small = (size_t)MSM_MAX_WIN * (cap < 65536 ? cap : 65536), large = (size_t)22 * cap;
-    return small > large ? small : large;
-}
-static int msm_ensure(s256_ctx *ctx) {
-    if (ctx->msm_cap) return S256_SUCCESS;
-    size_t total = 0;
-    for (int c = 4; c <= MSM_MAX_C; c++) {
-        size_t t = (size_t)msm_plan_for_c(c).total;
-        if (t > total) total = t;
-    }
-    CK(cudaMalloc(&ctx->msm_counts, (total + 1) * 4));
-    CK(cudaMalloc(&ctx->msm_offsets, (total + 1) * 4));
-    CK(cudaMalloc(&ctx->msm_cursor, (total + 1) * 4));
-    CK(cudaMalloc(&ctx->msm_entries, msm_entries_capacity(ctx) * 4));
-    // slice sums: one per bucket at least, plus one per MSM_SLICE entries
-    ctx->msm_max_slices = total + msm_entries_capacity(ctx) / MSM_SLICE + 1;
-    CK(cudaMalloc(&ctx->msm_buckets, ctx->msm_max_slices * sizeof(pt)));
-    CK(cudaMalloc(&ctx->msm_nsl, (total + 1) * 4));
-    CK(cudaMalloc(&ctx->msm_sloff, (total + 1) * 4));
-    CK(cudaMalloc(&ctx->msm_win, (size_t)MSM_MAX_WIN * MSM_MAX_PARTS * sizeof(pt)));
-    CK(cudaMalloc(&ctx->msm_acc, sizeof(pt)));
-    CK(cudaMalloc(&ctx->msm_tmp, 4096 * sizeof(pt)));
-    CK(cudaMalloc(&ctx->msm_flag, 4));
-    size_t bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, bytes, ctx->msm_counts, ctx->msm_offsets, (int)(total + 1));
-    ctx->msm_cub_bytes = bytes;
-    CK(cudaMalloc(&ctx->msm_cub, bytes));
-    ctx->msm_cap = ctx->cap;
-    return S256_SUCCESS;
-}
-
-// one chunk (device pointers): msm_acc (+)= sum k_i P_i
-static int chunk_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, int first,
-                     cudaStream_t s) {
-    LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, s, pt65, n, ctx->aff, ctx->pvalid);
-    LAUNCH(ctx, k_any_invalid, grid_for(n), 0, s, ctx->pvalid, n, ctx->msm_flag);
-    if (!vartime || n < 32) {
-        // constant-time flavour (and tiny inputs): ct ladder per item, then a sum tree
-        s256_launch_scalar_mult_ct(n, ctx->aff, k32, ctx->tbl, ctx->res, s);
-        ctx->launches.fetch_add(1, std::memory_order_relaxed);
-        size_t m = n < 2048 ? (n < 32 ? 1 : 32) : 2048;
-        LAUNCH(ctx, k_reduce_points, grid_for(m), 0, s, ctx->res, n, ctx->msm_tmp, m);
-        if (m > 32) {
-            LAUNCH(ctx, k_reduce_points, grid_for(32), 0, s, ctx->msm_tmp, m, ctx->msm_tmp + 2048, (size_t)32);
-            LAUNCH(ctx, k_reduce_points, 1, 0, s, ctx->msm_tmp + 2048, (size_t)32, ctx->msm_tmp + 2048 + 32, (size_t)1);
-            k_acc_point<<<1, 1, 0, s>>>(ctx->msm_tmp + 2048 + 32, ctx->msm_acc, first);
-        } else if (m > 1) {
-            LAUNCH(ctx, k_reduce_points, 1, 0, s, ctx->msm_tmp, m, ctx->msm_tmp + 2048, (size_t)1);
-            k_acc_point<<<1, 1, 0, s>>>(ctx->msm_tmp + 2048, ctx->msm_acc, first);
-        } else {
-            k_acc_point<<<1, 1, 0, s>>>(ctx->msm_tmp, ctx->msm_acc, first);
-        }
-        ctx->launches.fetch_add(1, std::memory_order_relaxed);
-        return S256_SUCCESS;
-    }
-    msm_plan pl = msm_make_plan(n);
-    while (pl.c < MSM_MAX_C && (size_t)pl.nwin * n > msm_entries_capacity(ctx)) pl = msm_plan_for_c(pl.c + 1);
-    uint32_t total = (uint32_t)pl.total;
-    CK(cudaMemsetAsync(ctx->msm_counts, 0, ((size_t)total + 1) * 4, s));
-    LAUNCH(ctx, k_msm_digits<false>, grid_for(n), 0, s, k32, n, pl, ctx->msm_counts, ctx->msm_cursor, ctx->msm_entries);
-    size_t bytes = ctx->msm_cub_bytes;
-    CK(cub::DeviceScan::ExclusiveSum(ctx->msm_cub, bytes, ctx->msm_counts, ctx->msm_offsets, (int)(total + 1), s));
-    CK(cudaMemcpyAsync(ctx->msm_cursor, ctx->msm_offsets, (size_t)total * 4, cudaMemcpyDeviceToDevice, s));
-    LAUNCH(ctx, k_msm_digits<true>, grid_for(n), 0, s, k32, n, pl, ctx->msm_counts, ctx->msm_cursor, ctx->msm_entries);
-    // buckets -> slices of <= MSM_SLICE entries
-    LAUNCH(ctx, k_msm_slice_counts, grid_for((size_t)total + 1), 0, s, total, ctx->msm_counts, ctx->msm_nsl);
-    CK(cub::DeviceScan::ExclusiveSum(ctx->msm_cub, bytes, ctx->msm_nsl, ctx->msm_sloff, (int)(total + 1), s));
-    size_t max_slices = (size_t)total + ((size_t)pl.nwin * n) / MSM_SLICE + 1;
-    if (max_slices > ctx->msm_max_slices) max_slices = ctx->msm_max_slices;
-    LAUNCH(ctx, k_msm_slices, grid_for(max_slices), 0, s, (uint32_t)max_slices, total, ctx->msm_sloff, ctx->msm_offsets,
-           ctx->msm_entries, ctx->aff, ctx->msm_buckets);
-    int parts = 1;
-    for (int w = 0; w < pl.nwin; w += pl.nwin - 1 > 0 ? pl.nwin - 1 : 1) {  // first and top window cover both sizes
-        int nbw = msm_window_buckets(pl, w);
-        int p = (nbw + S256_MSM_WT * msm_seg_for(nbw) - 1) / (S256_MSM_WT * msm_seg_for(nbw));
-        if (p > parts) parts = p;
-    }
-    k_msm_windows<<<dim3(parts, pl.nwin), S256_MSM_WT, 0, s>>>(pl, ctx->msm_buckets, ctx->msm_sloff, ctx->msm_win, parts);
-    k_msm_fold<<<1, 64, 0, s>>>(pl.nwin, ctx->msm_win, parts);
-    k_msm_final<<<1, 1, 0, s>>>(pl, ctx->msm_win, parts, ctx->msm_acc, first);
-    ctx->launches.fetch_add(3, std::memory_order_relaxed);
-    return S256_SUCCESS;
-}
-
-// host pointers -> msm_acc holds the projective sum; *invalid = 1 if a point failed to decode
-static int msm_run(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, uint32_t *invalid) {
-    int rc = msm_ensure(ctx);
-    if (rc != S256_SUCCESS) return rc;
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemsetAsync(ctx->msm_flag, 0, 4, s));
-    if (n == 0) {
-        pt id;
-        pt_set_identity(id);
-        CK(cudaMemcpyAsync(ctx->msm_acc, &id, sizeof(pt), cudaMemcpyHostToDevice, s));
-        CK(cudaStreamSynchronize(s));
-    }
-    int first = 1;
-    rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        CK(cudaMemcpyAsync(ctx->in_a, pt65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->in_b, k32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
-        int r = chunk_msm(ctx, ctx->in_b, ctx->in_a, c, vartime, first, s);
-        first = 0;
-        return r;
-    });
-    if (rc != S256_SUCCESS) return rc;
-    CK(cudaMemcpyAsync(invalid, ctx->msm_flag, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    return check_launch(ctx);
-}
-// msm_acc -> 65-byte encoding + status
-static int msm_finish(s256_ctx *ctx, uint8_t *out65, uint8_t *status) {
-    cudaStream_t s = ctx->stream;
-    LAUNCH(ctx, k_finish_affine<INV_K>, 1, 0, s, (size_t)1, ctx->msm_acc, (const uint8_t *)nullptr,
-           (const uint8_t *)nullptr, ctx->cstat, 0, ctx->out, ctx->st, (const uint8_t *)nullptr);
-    CK(cudaMemcpyAsync(out65, ctx->out, 65, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(status, ctx->st, 1, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    return check_launch(ctx);
-}
-extern "C" int s256_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, uint8_t *out65,
-                        uint8_t *status) {
-    ENTER(ctx);
-    if (!out65 || !status || (n && (!k32 || !pt65))) return S256_ERR_ARG;
-    uint32_t invalid = 0;
-    int rc = msm_run(ctx, k32, pt65, n, vartime, &invalid);
-    if (rc != S256_SUCCESS) return rc;
-    if (invalid) {
-        memset(out65, 0, 65);
-        *status = S256_ST_INVALID;
-        return S256_SUCCESS;
-    }
-    return msm_finish(ctx, out65, status);
-}
-extern "C" int s256_msm_partial(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime,
-                                uint8_t *partial96, uint8_t *status) {
-    ENTER(ctx);
-    if (!partial96 || !status || (n && (!k32 || !pt65))) return S256_ERR_ARG;
-    uint32_t invalid = 0;
-    int rc = msm_run(ctx, k32, pt65, n, vartime, &invalid);
-    if (rc != S256_SUCCESS) return rc;
-    if (invalid) {
-        memset(partial96, 0, 96);
-        *status = S256_ST_INVALID;
-        return S256_SUCCESS;
-    }
-    cudaStream_t s = ctx->stream;
-    k_export_partial<<<1, 1, 0, s>>>(ctx->msm_acc, ctx->out);
-    ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    CK(cudaMemcpyAsync(partial96, ctx->out, 96, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    *status = S256_ST_OK;
-    return check_launch(ctx);
-}
-extern "C" int s256_msm_combine(s256_ctx *ctx, const uint8_t *partials96, size_t m, uint8_t *out65, uint8_t *status) {
-    ENTER(ctx);
-    if (!out65 || !status || (m && !partials96)) return S256_ERR_ARG;
-    if (96 * m > 65 * ctx->cap) return S256_ERR_ARG;
-    int rc = msm_ensure(ctx);
-    if (rc != S256_SUCCESS) return rc;
-    cudaStream_t s = ctx->stream;
-    CK(cudaMemsetAsync(ctx->msm_flag, 0, 4, s));
-    if (m) CK(cudaMemcpyAsync(ctx->in_a, partials96, 96 * m, cudaMemcpyHostToDevice, s));
-    k_combine_partials<<<1, 1, 0, s>>>(ctx->in_a, m, ctx->msm_acc, ctx->msm_flag);
-    ctx->launches.fetch_add(1, std::memory_order_relaxed);
-    uint32_t invalid = 0;
-    CK(cudaMemcpyAsync(&invalid, ctx->msm_flag, 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    if (invalid) {
-        memset(out65, 0, 65);
-        *status = S256_ST_INVALID;
-        return S256_SUCCESS;
-    }
-    return msm_finish(ctx, out65, status);
 }
 
 // ---------------------------------------------------------------------------

@@ -1,0 +1,324 @@
+// api_msm.cu -- Point.MultiScalarMult[Vartime]: the Pippenger kernels (msm.cuh) and their entry points.
+#include "ctx.h"
+#include "msm.cuh"
+#include <cub/device/device_scan.cuh>
+
+// ---- Pippenger MSM (msm.cuh) -------------------------------------------------
+template <bool SCATTER>
+__global__ void __launch_bounds__(S256_TPB) k_msm_digits(const uint8_t *k32, size_t n, msm_plan plan, uint32_t *counts,
+                                                         uint32_t *cursor, uint32_t *entries) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    sc k;
+    sc_from_be32(k, k32 + 32 * i);
+    int32_t d[MSM_MAX_WIN];
+    msm_digits(d, k, plan);
+    for (int w = 0; w < plan.nwin; w++) {
+        int32_t dw = d[w];
+        if (dw == 0) continue;
+        uint32_t mag = (uint32_t)(dw < 0 ? -dw : dw);
+        uint32_t b = (uint32_t)w * (uint32_t)plan.nb + (mag - 1u);
+        if (!SCATTER) {
+            atomicAdd(&counts[b], 1u);
+        } else {
+            uint32_t pos = atomicAdd(&cursor[b], 1u);
+            entries[pos] = ((uint32_t)i << 1) | (uint32_t)(dw < 0);
+        }
+    }
+}
+// nsl[b] = slices of bucket b (counts -> slice counts), then scanned into sl_off
+__global__ void __launch_bounds__(S256_TPB) k_msm_slice_counts(uint32_t total, const uint32_t *counts, uint32_t *nsl) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < total) nsl[b] = msm_slices_of(counts[b]);
+    if (b == total) nsl[b] = 0;
+}
+__global__ void __launch_bounds__(S256_TPB) k_msm_slices(uint32_t max_slices, uint32_t total, const uint32_t *sl_off,
+                                                         const uint32_t *offsets, const uint32_t *entries,
+                                                         const apt *aff, pt *slice_sum) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= max_slices || s >= sl_off[total]) return;
+    uint32_t st, en;
+    msm_slice_range(st, en, s, sl_off, offsets, total);
+    pt r;
+    msm_bucket_sum(r, entries, st, en, aff);
+    slice_sum[s] = r;
+}
+#define S256_MSM_WT 128
+// grid (blocks per window, nwin): every thread reduces MSM_SEG buckets, the CTA folds its threads
+__global__ void __launch_bounds__(S256_MSM_WT) k_msm_windows(msm_plan plan, const pt *slice_sum, const uint32_t *sl_off,
+                                                             pt *winpart, int parts) {
+    __shared__ pt sh[S256_MSM_WT];
+    int w = blockIdx.y, t = threadIdx.x;
+    int nbw = msm_window_buckets(plan, w);
+    int seg = msm_seg_for(nbw);
+    int lo = (blockIdx.x * S256_MSM_WT + t) * seg, hi = lo + seg;
+    if (hi > nbw) hi = nbw;
+    pt s;
+    if (lo < hi)
+        msm_segment(s, slice_sum, sl_off, (uint32_t)w * (uint32_t)plan.nb, lo, hi);
+    else
+        pt_set_identity(s);
+    sh[t] = s;
+    __syncthreads();
+    for (int stride = S256_MSM_WT / 2; stride >= 1; stride >>= 1) {
+        if (t < stride) {
+            pt a = sh[t], b = sh[t + stride];
+            pt_add(a, a, b);
+            sh[t] = a;
+        }
+        __syncthreads();
+    }
+    if (t == 0) winpart[w * parts + blockIdx.x] = sh[0];
+}
+// win[w * parts] = sum of the `parts` CTA partials of window w (one thread per window)
+__global__ void k_msm_fold(int nwin, pt *winpart, int parts) {
+    int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwin) return;
+    pt acc = winpart[w * parts];
+    for (int q = 1; q < parts; q++) {
+        pt t = winpart[w * parts + q];
+        pt_add(acc, acc, t);
+    }
+    winpart[w * parts] = acc;
+}
+// acc (device, projective) += Horner(window partials); first = overwrite
+__global__ void k_msm_final(msm_plan plan, const pt *winpart, int parts, pt *acc, int first) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    pt r;
+    msm_horner(r, winpart, plan, 1, parts);
+    if (!first) {
+        pt a = *acc;
+        pt_add(r, r, a);
+    }
+    *acc = r;
+}
+// out[t] = sum of in[t], in[t + nout], ...   (tree levels of the constant-time MSM)
+__global__ void __launch_bounds__(S256_TPB) k_reduce_points(const pt *in, size_t n, pt *out, size_t nout) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nout) return;
+    pt acc;
+    pt_set_identity(acc);
+    for (size_t i = t; i < n; i += nout) {
+        pt q = in[i];
+        pt_add(acc, acc, q);
+    }
+    out[t] = acc;
+}
+__global__ void k_acc_point(const pt *in, pt *acc, int first) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    pt r = *in;
+    if (!first) {
+        pt a = *acc;
+        pt_add(r, r, a);
+    }
+    *acc = r;
+}
+__global__ void __launch_bounds__(S256_TPB) k_any_invalid(const uint8_t *pvalid, size_t n, uint32_t *flag) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && pvalid[i] == 0) atomicOr(flag, 1u);
+}
+// partial96 rows -> one projective sum; rows must be points on the curve (or the identity)
+__global__ void k_combine_partials(const uint8_t *partials96, size_t m, pt *out, uint32_t *flag) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    pt acc;
+    pt_set_identity(acc);
+    for (size_t j = 0; j < m; j++) {
+        pt q;
+        pt_from_be96(q, partials96 + 96 * j);
+        uint32_t ok = fe_limbs_are_canonical(q.x) & fe_limbs_are_canonical(q.y) & fe_limbs_are_canonical(q.z) &
+                      pt_on_curve(q);
+        if (!ok) {
+            atomicOr(flag, 1u);
+            continue;
+        }
+        pt_add(acc, acc, q);
+    }
+    *out = acc;
+}
+__global__ void k_export_partial(const pt *acc, uint8_t *out96) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    pt a = *acc;
+    pt_to_be96(out96, a);
+}
+
+
+// ---------------------------------------------------------------------------
+// MSM
+// ---------------------------------------------------------------------------
+static size_t msm_entries_capacity(const s256_ctx *ctx) {
+    // nwin * n entries; the planner uses c >= 12 once n >= 2^16 (nwin <= 22), and c >= 4 (nwin <= 64) below
+    size_t cap = ctx->cap;
+    size_t small = (size_t)MSM_MAX_WIN * (cap < 65536 ? cap : 65536), large = (size_t)22 * cap;
+    return small > large ? small : large;
+}
+static int msm_ensure(s256_ctx *ctx) {
+    if (ctx->msm_cap) return S256_SUCCESS;
+    size_t total = 0;
+    for (int c = 4; c <= MSM_MAX_C; c++) {
+        size_t t = (size_t)msm_plan_for_c(c).total;
+        if (t > total) total = t;
+    }
+    CK(cudaMalloc(&ctx->msm_counts, (total + 1) * 4));
+    CK(cudaMalloc(&ctx->msm_offsets, (total + 1) * 4));
+    CK(cudaMalloc(&ctx->msm_cursor, (total + 1) * 4));
+    CK(cudaMalloc(&ctx->msm_entries, msm_entries_capacity(ctx) * 4));
+    // slice sums: one per bucket at least, plus one per MSM_SLICE entries
+    ctx->msm_max_slices = total + msm_entries_capacity(ctx) / MSM_SLICE + 1;
+    CK(cudaMalloc(&ctx->msm_buckets, ctx->msm_max_slices * sizeof(pt)));
+    CK(cudaMalloc(&ctx->msm_nsl, (total + 1) * 4));
+    CK(cudaMalloc(&ctx->msm_sloff, (total + 1) * 4));
+    CK(cudaMalloc(&ctx->msm_win, (size_t)MSM_MAX_WIN * MSM_MAX_PARTS * sizeof(pt)));
+    CK(cudaMalloc(&ctx->msm_acc, sizeof(pt)));
+    CK(cudaMalloc(&ctx->msm_tmp, 4096 * sizeof(pt)));
+    CK(cudaMalloc(&ctx->msm_flag, 4));
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, ctx->msm_counts, ctx->msm_offsets, (int)(total + 1));
+    ctx->msm_cub_bytes = bytes;
+    CK(cudaMalloc(&ctx->msm_cub, bytes));
+    ctx->msm_cap = ctx->cap;
+    return S256_SUCCESS;
+}
+
+// one chunk (device pointers): msm_acc (+)= sum k_i P_i
+static int chunk_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, int first,
+                     cudaStream_t s) {
+    s256_launch_decode_uncompressed(ctx, pt65, n, ctx->aff, ctx->pvalid, s);
+    LAUNCH(ctx, k_any_invalid, grid_for(n), 0, s, ctx->pvalid, n, ctx->msm_flag);
+    if (!vartime || n < 32) {
+        // constant-time flavour (and tiny inputs): ct ladder per item, then a sum tree
+        s256_launch_scalar_mult_ct(n, ctx->aff, k32, ctx->tbl, ctx->res, s);
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        size_t m = n < 2048 ? (n < 32 ? 1 : 32) : 2048;
+        LAUNCH(ctx, k_reduce_points, grid_for(m), 0, s, ctx->res, n, ctx->msm_tmp, m);
+        if (m > 32) {
+            LAUNCH(ctx, k_reduce_points, grid_for(32), 0, s, ctx->msm_tmp, m, ctx->msm_tmp + 2048, (size_t)32);
+            LAUNCH(ctx, k_reduce_points, 1, 0, s, ctx->msm_tmp + 2048, (size_t)32, ctx->msm_tmp + 2048 + 32, (size_t)1);
+            k_acc_point<<<1, 1, 0, s>>>(ctx->msm_tmp + 2048 + 32, ctx->msm_acc, first);
+        } else if (m > 1) {
+            LAUNCH(ctx, k_reduce_points, 1, 0, s, ctx->msm_tmp, m, ctx->msm_tmp + 2048, (size_t)1);
+            k_acc_point<<<1, 1, 0, s>>>(ctx->msm_tmp + 2048, ctx->msm_acc, first);
+        } else {
+            k_acc_point<<<1, 1, 0, s>>>(ctx->msm_tmp, ctx->msm_acc, first);
+        }
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
+        return S256_SUCCESS;
+    }
+    msm_plan pl = msm_make_plan(n);
+    while (pl.c < MSM_MAX_C && (size_t)pl.nwin * n > msm_entries_capacity(ctx)) pl = msm_plan_for_c(pl.c + 1);
+    uint32_t total = (uint32_t)pl.total;
+    CK(cudaMemsetAsync(ctx->msm_counts, 0, ((size_t)total + 1) * 4, s));
+    LAUNCH(ctx, k_msm_digits<false>, grid_for(n), 0, s, k32, n, pl, ctx->msm_counts, ctx->msm_cursor, ctx->msm_entries);
+    size_t bytes = ctx->msm_cub_bytes;
+    CK(cub::DeviceScan::ExclusiveSum(ctx->msm_cub, bytes, ctx->msm_counts, ctx->msm_offsets, (int)(total + 1), s));
+    CK(cudaMemcpyAsync(ctx->msm_cursor, ctx->msm_offsets, (size_t)total * 4, cudaMemcpyDeviceToDevice, s));
+    LAUNCH(ctx, k_msm_digits<true>, grid_for(n), 0, s, k32, n, pl, ctx->msm_counts, ctx->msm_cursor, ctx->msm_entries);
+    // buckets -> slices of <= MSM_SLICE entries
+    LAUNCH(ctx, k_msm_slice_counts, grid_for((size_t)total + 1), 0, s, total, ctx->msm_counts, ctx->msm_nsl);
+    CK(cub::DeviceScan::ExclusiveSum(ctx->msm_cub, bytes, ctx->msm_nsl, ctx->msm_sloff, (int)(total + 1), s));
+    size_t max_slices = (size_t)total + ((size_t)pl.nwin * n) / MSM_SLICE + 1;
+    if (max_slices > ctx->msm_max_slices) max_slices = ctx->msm_max_slices;
+    LAUNCH(ctx, k_msm_slices, grid_for(max_slices), 0, s, (uint32_t)max_slices, total, ctx->msm_sloff, ctx->msm_offsets,
+           ctx->msm_entries, ctx->aff, ctx->msm_buckets);
+    int parts = 1;
+    for (int w = 0; w < pl.nwin; w += pl.nwin - 1 > 0 ? pl.nwin - 1 : 1) {  // first and top window cover both sizes
+        int nbw = msm_window_buckets(pl, w);
+        int p = (nbw + S256_MSM_WT * msm_seg_for(nbw) - 1) / (S256_MSM_WT * msm_seg_for(nbw));
+        if (p > parts) parts = p;
+    }
+    k_msm_windows<<<dim3(parts, pl.nwin), S256_MSM_WT, 0, s>>>(pl, ctx->msm_buckets, ctx->msm_sloff, ctx->msm_win, parts);
+    k_msm_fold<<<1, 64, 0, s>>>(pl.nwin, ctx->msm_win, parts);
+    k_msm_final<<<1, 1, 0, s>>>(pl, ctx->msm_win, parts, ctx->msm_acc, first);
+    ctx->launches.fetch_add(3, std::memory_order_relaxed);
+    return S256_SUCCESS;
+}
+
+// host pointers -> msm_acc holds the projective sum; *invalid = 1 if a point failed to decode
+static int msm_run(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, uint32_t *invalid) {
+    int rc = msm_ensure(ctx);
+    if (rc != S256_SUCCESS) return rc;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->msm_flag, 0, 4, s));
+    if (n == 0) {
+        pt id;
+        pt_set_identity(id);
+        CK(cudaMemcpyAsync(ctx->msm_acc, &id, sizeof(pt), cudaMemcpyHostToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    int first = 1;
+    rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        CK(cudaMemcpyAsync(ctx->in_a, pt65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->in_b, k32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        int r = chunk_msm(ctx, ctx->in_b, ctx->in_a, c, vartime, first, s);
+        first = 0;
+        return r;
+    });
+    if (rc != S256_SUCCESS) return rc;
+    CK(cudaMemcpyAsync(invalid, ctx->msm_flag, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return check_launch(ctx);
+}
+// msm_acc -> 65-byte encoding + status
+static int msm_finish(s256_ctx *ctx, uint8_t *out65, uint8_t *status) {
+    cudaStream_t s = ctx->stream;
+    s256_launch_finish_affine(ctx, 1, ctx->msm_acc, nullptr, nullptr, ctx->cstat, 0, ctx->out, ctx->st, nullptr, s);
+    CK(cudaMemcpyAsync(out65, ctx->out, 65, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(status, ctx->st, 1, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return check_launch(ctx);
+}
+extern "C" int s256_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, uint8_t *out65,
+                        uint8_t *status) {
+    ENTER(ctx);
+    if (!out65 || !status || (n && (!k32 || !pt65))) return S256_ERR_ARG;
+    uint32_t invalid = 0;
+    int rc = msm_run(ctx, k32, pt65, n, vartime, &invalid);
+    if (rc != S256_SUCCESS) return rc;
+    if (invalid) {
+        memset(out65, 0, 65);
+        *status = S256_ST_INVALID;
+        return S256_SUCCESS;
+    }
+    return msm_finish(ctx, out65, status);
+}
+extern "C" int s256_msm_partial(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime,
+                                uint8_t *partial96, uint8_t *status) {
+    ENTER(ctx);
+    if (!partial96 || !status || (n && (!k32 || !pt65))) return S256_ERR_ARG;
+    uint32_t invalid = 0;
+    int rc = msm_run(ctx, k32, pt65, n, vartime, &invalid);
+    if (rc != S256_SUCCESS) return rc;
+    if (invalid) {
+        memset(partial96, 0, 96);
+        *status = S256_ST_INVALID;
+        return S256_SUCCESS;
+    }
+    cudaStream_t s = ctx->stream;
+    k_export_partial<<<1, 1, 0, s>>>(ctx->msm_acc, ctx->out);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    CK(cudaMemcpyAsync(partial96, ctx->out, 96, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *status = S256_ST_OK;
+    return check_launch(ctx);
+}
+extern "C" int s256_msm_combine(s256_ctx *ctx, const uint8_t *partials96, size_t m, uint8_t *out65, uint8_t *status) {
+    ENTER(ctx);
+    if (!out65 || !status || (m && !partials96)) return S256_ERR_ARG;
+    if (96 * m > 65 * ctx->cap) return S256_ERR_ARG;
+    int rc = msm_ensure(ctx);
+    if (rc != S256_SUCCESS) return rc;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->msm_flag, 0, 4, s));
+    if (m) CK(cudaMemcpyAsync(ctx->in_a, partials96, 96 * m, cudaMemcpyHostToDevice, s));
+    k_combine_partials<<<1, 1, 0, s>>>(ctx->in_a, m, ctx->msm_acc, ctx->msm_flag);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    uint32_t invalid = 0;
+    CK(cudaMemcpyAsync(&invalid, ctx->msm_flag, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (invalid) {
+        memset(out65, 0, 65);
+        *status = S256_ST_INVALID;
+        return S256_SUCCESS;
+    }
+    return msm_finish(ctx, out65, status);
+}
+

@@ -26,8 +26,14 @@ S256_HD uint32_t sha_k(int i) {
     return K[i];
 }
 
-// one compression; w[16] is consumed (used as the rolling schedule)
-S256_HD void sha256_compress(uint32_t h[8], uint32_t w[16]) {
+// one compression; w[16] is consumed (used as the rolling schedule).  Out of line on the device: the
+// 64 unrolled rounds are instantiated once instead of at every call site (HMAC reaches it ~90 times).
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+inline
+#endif
+void sha256_compress(uint32_t h[8], uint32_t w[16]) {
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll
     for (int i = 0; i < 64; i++) {
@@ -141,7 +147,12 @@ S256_HD void sha_final(sha_stream &c, uint8_t out[32]) {
     }
 }
 // out may alias key or msg
-S256_HD void hmac_sha256_k32(uint8_t out[32], const uint8_t key[32], const uint8_t *msg, size_t len) {
+#if defined(__CUDACC__)
+static __host__ __device__ __noinline__
+#else
+inline
+#endif
+void hmac_sha256_k32(uint8_t out[32], const uint8_t key[32], const uint8_t *msg, size_t len) {
     uint8_t pad[64], inner[32];
     sha_stream c;
     for (int i = 0; i < 64; i++) pad[i] = (uint8_t)(0x36 ^ (i < 32 ? key[i] : 0));
