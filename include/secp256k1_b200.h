@@ -157,6 +157,16 @@ int s256_schnorr_sign(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *msg, 
 int s256_schnorr_sign_dev(s256_ctx *ctx, const uint8_t *d_priv32, const uint8_t *d_msg, size_t msg_len,
                           const uint8_t *d_aux32, size_t n, uint8_t *d_sig64, uint8_t *d_status, void *stream);
 
+/* --- h2c.Secp256k1_XMD_SHA256_SSWU_RO / _NU (secec/h2c/h2c.go:25,49): RFC 9380 hash_to_curve
+ *     (random_oracle != 0) or encode_to_curve over n messages of msg_len bytes sharing one domain
+ *     separation tag.  dst_len == 0 is an error (errInvalidDomainSep); a DST longer than 255 bytes is
+ *     hashed as the RFC prescribes.  Constant time.  status: S256_ST_OK / S256_ST_IDENTITY.
+ *     s256_expand_message_xmd exposes expandMessageXMD (h2c_expand_message.go:33) for len_in_bytes <= 96. */
+int s256_hash_to_curve(s256_ctx *ctx, const uint8_t *dst, size_t dst_len, const uint8_t *msg, size_t msg_len, size_t n,
+                       int random_oracle, uint8_t *out65, uint8_t *status);
+int s256_expand_message_xmd(s256_ctx *ctx, const uint8_t *dst, size_t dst_len, const uint8_t *msg, size_t msg_len,
+                            size_t n, size_t len_in_bytes, uint8_t *out);
+
 /* --- Point.MultiScalarMult[Vartime] (point_mul_multi.go:25,73): sum k_i*P_i
  *     over this context's items -> one 65-byte point.  n == 0 gives the
  *     identity.  *status: S256_ST_OK / S256_ST_IDENTITY / S256_ST_INVALID (a

@@ -165,6 +165,22 @@ def hmac_sha256(key32, msg):
     o = _out(32); msg = bytes(msg); lib().orc_hmac_sha256(_buf(key32, 32), msg, C.c_size_t(len(msg)), o); return o.raw
 
 
+def hash_to_curve(dst, msg, random_oracle=True):
+    dst, msg = bytes(dst), bytes(msg); o = _out(65)
+    st = lib().orc_hash_to_curve(dst, C.c_size_t(len(dst)), msg, C.c_size_t(len(msg)), int(random_oracle), o)
+    return o.raw, st
+
+
+def expand_message_xmd(dst, msg, length):
+    dst, msg = bytes(dst), bytes(msg); o = _out(length)
+    ok = lib().orc_expand_message_xmd(dst, C.c_size_t(len(dst)), msg, C.c_size_t(len(msg)), o, C.c_size_t(length))
+    return o.raw if ok else None
+
+
+def map_to_curve(u48):
+    o = _out(65); st = lib().orc_map_to_curve(_buf(u48, 48), o); return o.raw, st
+
+
 def schnorr_sign(priv32, msg, aux32):
     sig = _out(64); msg = bytes(msg)
     st = lib().orc_schnorr_sign(_buf(priv32, 32), msg, C.c_size_t(len(msg)), _buf(aux32, 32), sig)

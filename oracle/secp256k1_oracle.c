@@ -931,6 +931,145 @@ static int schnorr_sign_one(const u8 priv32[32], const u8 *msg, size_t msg_len, 
 }
 
 /* ------------------------------------------------------------------------- */
+/* Hash to curve (RFC 9380): secec/h2c/*.go, point_h2c.go, internal/swu/swu.go  */
+/* ------------------------------------------------------------------------- */
+static void hex_to_limbs(u64 l[4], const char *h);
+static fe H_A, H_B, H_Z, H_C2, H_K[4][4];
+static void fe_from_hex(fe *r, const char *h) { u64 l[4]; hex_to_limbs(l, h); mont_to(r->v, l, &FP); }
+static void h2c_init(void) {
+    fe_from_hex(&H_A, "3f8731abdd661adca08a5558f0f5d272e953d363cb6f0e5d405447c01a444533");  /* swu.go feA */
+    fe_set_u64(&H_B, 1771);
+    fe t; fe_set_u64(&t, 11); fe_neg(&H_Z, &t);
+    fe_from_hex(&H_C2, "31fdf302724013e57ad13fb38f842afeec184f00a74789dd286729c8303c4a59");  /* field_sqrt_ratio.go:10 */
+    static const char *k[4][4] = {
+        {"8e38e38e38e38e38e38e38e38e38e38e38e38e38e38e38e38e38e38daaaaa8c7", "07d3d4c80bc321d5b9f315cea7fd44c5d595d2fc0bf63b92dfff1044f17c6581",
+         "534c328d23f234e6e2a413deca25caece4506144037c40314ecbd0b53d9dd262", "8e38e38e38e38e38e38e38e38e38e38e38e38e38e38e38e38e38e38daaaaa88c"},
+        {"d35771193d94918a9ca34ccbb7b640dd86cd409542f8487d9fe6b745781eb49b", "edadc6f64383dc1df7c4b2d51b54225406d36b641f5e41bbc52a56612a8c6d14", 0, 0},
+        {"4bda12f684bda12f684bda12f684bda12f684bda12f684bda12f684b8e38e23c", "c75e0c32d5cb7c0fa9d0a54b12a0a6d5647ab046d686da6fdffc90fc201d71a3",
+         "29a6194691f91a73715209ef6512e576722830a201be2018a765e85a9ecee931", "2f684bda12f684bda12f684bda12f684bda12f684bda12f684bda12f38e38d84"},
+        {"fffffffffffffffffffffffffffffffffffffffffffffffffffffffefffff93b", "7a06534bb8bdb49fd5e9e6632722c2989467c1bfc8e8d978dfb425d2685c2573",
+         "6484aa716545ca2cf3a70c3fa8fe337e0a3d21162f0d6299a7bf8192bfd2a76f", 0}};
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) if (k[i][j]) fe_from_hex(&H_K[i][j], k[i][j]);
+}
+/* secec/h2c/h2c_expand_message.go:33-139 with SHA-256 */
+static int expand_message_xmd(u8 *out, size_t len, const u8 *dst, size_t dst_len, const u8 *msg, size_t msg_len) {
+    u8 dbuf[32], b0[32], bi[32], zpad[64] = {0}, x[3];
+    if (len == 0 || len > 65535 || dst_len == 0) return 0;
+    if (dst_len > 255) {
+        sha256_ctx c; sha256_init(&c);
+        sha256_update(&c, (const u8 *)"H2C-OVERSIZE-DST-", 17); sha256_update(&c, dst, dst_len); sha256_final(&c, dbuf);
+        dst = dbuf; dst_len = 32;
+    }
+    size_t ell = (len + 31) / 32;
+    if (ell > 255) return 0;
+    u8 dl = (u8)dst_len;
+    sha256_ctx c; sha256_init(&c);
+    sha256_update(&c, zpad, 64); sha256_update(&c, msg, msg_len);
+    x[0] = (u8)(len >> 8); x[1] = (u8)len; x[2] = 0; sha256_update(&c, x, 3);
+    sha256_update(&c, dst, dst_len); sha256_update(&c, &dl, 1); sha256_final(&c, b0);
+    sha256_init(&c); sha256_update(&c, b0, 32); x[0] = 1; sha256_update(&c, x, 1);
+    sha256_update(&c, dst, dst_len); sha256_update(&c, &dl, 1); sha256_final(&c, bi);
+    size_t off = 0;
+    for (size_t i = 1; i <= ell; i++) {
+        if (i > 1) {
+            u8 t[32];
+            for (int k = 0; k < 32; k++) t[k] = b0[k] ^ bi[k];
+            sha256_init(&c); sha256_update(&c, t, 32); x[0] = (u8)i; sha256_update(&c, x, 1);
+            sha256_update(&c, dst, dst_len); sha256_update(&c, &dl, 1); sha256_final(&c, bi);
+        }
+        size_t take = len - off < 32 ? len - off : 32;
+        memcpy(out + off, bi, take);
+        off += take;
+    }
+    return 1;
+}
+/* internal/field/field_reduce.go:24-64 for 48-byte inputs: big-endian integer mod p */
+static void fe_set_wide48(fe *r, const u8 b[48]) {
+    u8 lo[32], hi[32] = {0};
+    memcpy(lo, b + 16, 32);
+    memcpy(hi + 16, b, 16);
+    fe l, h, two256;
+    fe_set_bytes(&l, lo);
+    fe_set_bytes(&h, hi);
+    u64 d[4] = {0x1000003D1ULL, 0, 0, 0};  /* 2^256 mod p */
+    mont_to(two256.v, d, &FP);
+    fe_mul(&h, &h, &two256);
+    fe_add(r, &l, &h);
+}
+/* internal/field/field_sqrt_ratio.go:25-63 (RFC 9380 F.2.1.2, p = 3 mod 4) */
+static int fe_sqrt_ratio(fe *z, const fe *u, const fe *v) {
+    fe tv1, tv2, tv3, y1, y2, x223, x22, x2;
+    fe_sqr(&tv1, v); fe_mul(&tv2, u, v); fe_mul(&tv1, &tv1, &tv2);
+    /* y1 = tv1^((p-3)/4): (p-3)/4 = 2^254 - 2^30 - 245 = 1^223 0 1^22 0000 10 11 */
+    fe_pow_common(&x223, &x22, &x2, &tv1);
+    fe t; fe_pow2k(&t, &x223, 23); fe_mul(&t, &t, &x22);
+    fe_pow2k(&t, &t, 5); fe_mul(&t, &t, &tv1);     /* ...0000 1 */
+    fe_pow2k(&t, &t, 3); fe_mul(&t, &t, &x2);      /* 0 11 */
+    y1 = t;
+    fe_mul(&y1, &y1, &tv2);
+    fe_mul(&y2, &y1, &H_C2);
+    fe_sqr(&tv3, &y1); fe_mul(&tv3, &tv3, v);
+    int qr = fe_eq(&tv3, u);
+    *z = qr ? y1 : y2;
+    return qr;
+}
+/* internal/swu/swu.go:70-147 -- map_to_curve_simple_swu on E' (RFC 9380 F.2) */
+static void swu_map(fe *x, fe *y, const fe *u) {
+    fe tv1, tv2, tv3, tv4, tv5, tv6, y1, nt;
+    fe_sqr(&tv1, u); fe_mul(&tv1, &H_Z, &tv1);
+    fe_sqr(&tv2, &tv1); fe_add(&tv2, &tv2, &tv1);
+    fe_add(&tv3, &tv2, &FE_ONE); fe_mul(&tv3, &H_B, &tv3);
+    int sel = fe_is_zero(&tv2);
+    fe_neg(&nt, &tv2);
+    tv4 = sel ? H_Z : nt;
+    fe_mul(&tv4, &H_A, &tv4);
+    fe_sqr(&tv2, &tv3); fe_sqr(&tv6, &tv4); fe_mul(&tv5, &H_A, &tv6);
+    fe_add(&tv2, &tv2, &tv5); fe_mul(&tv2, &tv2, &tv3);
+    fe_mul(&tv6, &tv6, &tv4); fe_mul(&tv5, &H_B, &tv6); fe_add(&tv2, &tv2, &tv5);
+    fe_mul(x, &tv1, &tv3);
+    int is_sq = fe_sqrt_ratio(&y1, &tv2, &tv6);
+    fe_mul(y, &tv1, u); fe_mul(y, y, &y1);
+    if (is_sq) { *x = tv3; *y = y1; }
+    if (fe_is_odd(u) != fe_is_odd(y)) fe_neg(y, y);
+    fe_invert(&tv4, &tv4);
+    fe_mul(x, x, &tv4);
+}
+/* internal/swu/swu.go:149-199 -- 3-isogeny E' -> E; 0 if a denominator vanishes */
+static int iso_map(fe *xo, fe *yo, const fe *X, const fe *Y) {
+    fe XX, XXX, xn, xd, yn, yd, t;
+    fe_sqr(&XX, X); fe_mul(&XXX, &XX, X);
+    fe_mul(&xn, &H_K[0][3], &XXX); fe_mul(&t, &H_K[0][2], &XX); fe_add(&xn, &xn, &t);
+    fe_mul(&t, &H_K[0][1], X); fe_add(&xn, &xn, &t); fe_add(&xn, &xn, &H_K[0][0]);
+    fe_mul(&xd, &H_K[1][1], X); fe_add(&xd, &xd, &XX); fe_add(&xd, &xd, &H_K[1][0]);
+    int xz = fe_is_zero(&xd);
+    fe_invert(&xd, &xd); fe_mul(xo, &xn, &xd);
+    fe_mul(&yn, &H_K[2][3], &XXX); fe_mul(&t, &H_K[2][2], &XX); fe_add(&yn, &yn, &t);
+    fe_mul(&t, &H_K[2][1], X); fe_add(&yn, &yn, &t); fe_add(&yn, &yn, &H_K[2][0]);
+    fe_mul(&yd, &H_K[3][2], &XX); fe_mul(&t, &H_K[3][1], X); fe_add(&yd, &yd, &t);
+    fe_add(&yd, &yd, &XXX); fe_add(&yd, &yd, &H_K[3][0]);
+    int yz = fe_is_zero(&yd);
+    fe_invert(&yd, &yd); fe_mul(yo, &yn, &yd); fe_mul(yo, Y, yo);
+    return !(xz | yz);
+}
+/* point_h2c.go:23-55 SetUniformBytes (48 bytes) */
+static void pt_set_uniform48(pt *v, const u8 b[48]) {
+    fe u, xp, yp, x, y;
+    fe_set_wide48(&u, b);
+    swu_map(&xp, &yp, &u);
+    if (iso_map(&x, &y, &xp, &yp)) { v->x = x; v->y = y; v->z = FE_ONE; } else pt_identity(v);
+}
+/* secec/h2c/h2c.go:25-63 */
+static int hash_to_curve_one(const u8 *dst, size_t dst_len, const u8 *msg, size_t msg_len, int ro, u8 out65[65]) {
+    u8 ub[96];
+    memset(out65, 0, 65);
+    if (!expand_message_xmd(ub, ro ? 96 : 48, dst, dst_len, msg, msg_len)) return ST_INVALID;
+    pt q0, q1, r;
+    pt_set_uniform48(&q0, ub);
+    if (ro) { pt_set_uniform48(&q1, ub + 48); pt_add(&r, &q0, &q1); } else r = q0;
+    return pt_uncompressed_bytes(out65, &r);
+}
+
+/* ------------------------------------------------------------------------- */
 /* Exported single-item entry points (ctypes)                                 */
 /* ------------------------------------------------------------------------- */
 
@@ -968,6 +1107,7 @@ static void do_init(void) {
     hex_to_limbs(l, "79be667ef9dcbbac55a06295ce870b07029bfcdb2dce28d959f2815b16f81798"); mont_to(PT_G.x.v, l, &FP);
     hex_to_limbs(l, "483ada7726a3c4655da4fbfc0e1108a8fd17b448a68554199c47d08ffb10d4b8"); mont_to(PT_G.y.v, l, &FP);
     PT_G.z = FE_ONE;
+    h2c_init();
     gen_tables();
 }
 EXPORT void orc_init(void) { pthread_once(&g_once, do_init); }
@@ -1083,6 +1223,19 @@ EXPORT int orc_ecdsa_sign_rfc6979(const u8 priv32[32], const u8 digest32[32], u8
     return ecdsa_sign_rfc6979_one(priv32, digest32, sig64, recid);
 }
 EXPORT void orc_hmac_sha256(const u8 key[32], const u8 *msg, size_t len, u8 out[32]) { hmac_sha256(out, key, msg, len); }
+EXPORT int orc_hash_to_curve(const u8 *dst, size_t dst_len, const u8 *msg, size_t msg_len, int ro, u8 out65[65]) {
+    orc_init();
+    return hash_to_curve_one(dst, dst_len, msg, msg_len, ro, out65);
+}
+EXPORT int orc_expand_message_xmd(const u8 *dst, size_t dst_len, const u8 *msg, size_t msg_len, u8 *out, size_t len) {
+    return expand_message_xmd(out, len, dst, dst_len, msg, msg_len);
+}
+EXPORT int orc_map_to_curve(const u8 u48[48], u8 out65[65]) {
+    orc_init();
+    pt q;
+    pt_set_uniform48(&q, u48);
+    return pt_uncompressed_bytes(out65, &q);
+}
 EXPORT int orc_schnorr_sign(const u8 priv32[32], const u8 *msg, size_t msg_len, const u8 aux32[32], u8 sig64[64]) {
     orc_init();
     return schnorr_sign_one(priv32, msg, msg_len, aux32, sig64);

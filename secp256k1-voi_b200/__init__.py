@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = [
     "s256_ecdsa_recover", "s256_ecdsa_recover_dev",
     "s256_ecdsa_sign_rfc6979", "s256_ecdsa_sign_rfc6979_dev",
     "s256_schnorr_verify", "s256_schnorr_verify_dev", "s256_schnorr_sign", "s256_schnorr_sign_dev",
-    "s256_msm", "s256_msm_partial", "s256_msm_combine",
+    "s256_msm", "s256_msm_partial", "s256_msm_combine", "s256_hash_to_curve", "s256_expand_message_xmd",
     "s256_debug_gen_table", "s256_debug_field_op", "s256_microbench_imad",
     "s256_microbench_variant", "s256_profile_enable", "s256_profile_read",
     "s256_launch_count", "s256_mac32_per_item",
@@ -407,6 +407,30 @@ class Engine:
         self._check(self._lib.s256_schnorr_sign(self._ctx, self._hp(d), self._hp(m), C.c_size_t(m.shape[1] if n else 0),
                                                 self._hp(ax), C.c_size_t(n), self._hp(sig), self._hp(st)), "schnorr_sign")
         return sig, st
+
+    # -- h2c.Secp256k1_XMD_SHA256_SSWU_RO / _NU (secec/h2c/h2c.go:25,49) ------------------------
+    def hash_to_curve(self, dst, msgs, random_oracle=True):
+        """msgs: (n, msg_len) uint8 rows (equal length).  -> (out65, status)"""
+        dst = bytes(dst)
+        m = np.ascontiguousarray(msgs, dtype=np.uint8)
+        if m.ndim != 2:
+            raise ValueError("msgs must be a 2-D array of equal-length rows")
+        n, msg_len = m.shape
+        out = np.zeros((n, 65), np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_hash_to_curve(self._ctx, dst, C.c_size_t(len(dst)), self._hp(m), C.c_size_t(msg_len),
+                                                 C.c_size_t(n), int(bool(random_oracle)), self._hp(out), self._hp(st)),
+                    "hash_to_curve")
+        return out, st
+
+    def expand_message_xmd(self, dst, msgs, length):
+        dst = bytes(dst)
+        m = np.ascontiguousarray(msgs, dtype=np.uint8)
+        n, msg_len = m.shape
+        out = np.zeros((n, length), np.uint8)
+        self._check(self._lib.s256_expand_message_xmd(self._ctx, dst, C.c_size_t(len(dst)), self._hp(m), C.c_size_t(msg_len),
+                                                      C.c_size_t(n), C.c_size_t(length), self._hp(out)), "expand_message_xmd")
+        return out
 
     # -- Point.MultiScalarMult[Vartime] (point_mul_multi.go:25,73) -------------
     def msm(self, k32, pt65, vartime=True):

@@ -213,6 +213,23 @@ def bip66():
             "invalid": [{"der": v["DER"], "exception": v.get("exception", "")} for v in doc["invalid"]["decode"]]}
 
 
+def h2c_vectors():
+    """secec/h2c/testdata/*.json (RFC 9380 appendix J.8 / K.1 vectors; loader: secec/h2c/h2c_test.go:35-194)."""
+    out = {"suites": [], "expand": []}
+    for fn in ("secp256k1_XMD_SHA-256_SSWU_RO_.json", "secp256k1_XMD_SHA-256_SSWU_NU_.json"):
+        d = json.load(open(f"{REF}/secec/h2c/testdata/{fn}"))
+        out["suites"].append({"src": fn, "dst": d["dst"], "random_oracle": d["randomOracle"],
+                              "vectors": [{"msg": v["msg"], "u": [x[2:] for x in v["u"]],
+                                           "Px": v["P"]["x"][2:], "Py": v["P"]["y"][2:],
+                                           "Q": [[q["x"][2:], q["y"][2:]] for q in ([v["Q0"], v["Q1"]] if "Q0" in v else [v["Q"]])]}
+                                          for v in d["vectors"]]})
+    for fn in ("expand_message_xmd_SHA256_38.json", "expand_message_xmd_SHA256_256.json"):
+        d = json.load(open(f"{REF}/secec/h2c/testdata/{fn}"))
+        out["expand"].append({"src": fn, "dst": d["DST"], "tests": [{"msg": t["msg"], "len": int(t["len_in_bytes"], 16),
+                                                                     "uniform_bytes": t["uniform_bytes"]} for t in d["tests"]]})
+    return out
+
+
 def in_source_kats():
     pt = open(f"{REF}/point_test.go").read()
     glv = open(f"{REF}/point_mul_glv_test.go").read()
@@ -262,6 +279,9 @@ def main():
     json.dump({"provenance": "secec/bitcoin/testdata/bip-0066-test-vectors.json", **b66},
               open(f"{OUT}/bip66.json", "w"), indent=0)
     print("bip66:", len(b66["valid"]), "valid,", len(b66["invalid"]), "invalid")
+    h2c = h2c_vectors()
+    json.dump({"provenance": "secec/h2c/testdata/*.json (RFC 9380 vectors)", **h2c}, open(f"{OUT}/h2c.json", "w"), indent=0)
+    print("h2c:", sum(len(s["vectors"]) for s in h2c["suites"]), "suite vectors,", sum(len(e["tests"]) for e in h2c["expand"]), "expand vectors")
     k = in_source_kats()
     json.dump({"provenance": "point_test.go:39,49,244-253; point_mul_glv_test.go:18-45; internal/gentable/point_mul_table.bin",
                **k}, open(f"{OUT}/kats.json", "w"), indent=0)

@@ -138,3 +138,28 @@ def schnorr_sign(priv, msg, aux):
     sig = np.zeros((n, 64), np.uint8); st = np.zeros(n, np.uint8)
     lib().sim_schnorr_sign(_p(priv), _p(msg), C.c_size_t(msg.shape[1]), _p(aux), C.c_size_t(n), _p(sig), _p(st))
     return sig, st
+
+
+def hash_to_curve(dst, msgs, random_oracle=True):
+    import hashlib
+    dst = bytes(dst)
+    if len(dst) > 255:  # the library pre-hashes oversize DSTs on the host
+        dst = hashlib.sha256(b"H2C-OVERSIZE-DST-" + dst).digest()
+    m = np.ascontiguousarray(msgs, dtype=np.uint8); n, ml = m.shape
+    out = np.zeros((n, 65), np.uint8); st = np.zeros(n, np.uint8)
+    lib().sim_hash_to_curve(dst, C.c_size_t(len(dst)), _p(m), C.c_size_t(ml), C.c_size_t(n), int(random_oracle), _p(out), _p(st))
+    return out, st
+
+
+def expand_message_xmd(dst, msgs, length):
+    import hashlib
+    dst = bytes(dst)
+    if len(dst) > 255:
+        dst = hashlib.sha256(b"H2C-OVERSIZE-DST-" + dst).digest()
+    m = np.ascontiguousarray(msgs, dtype=np.uint8); n, ml = m.shape
+    out = np.zeros((n, length), np.uint8)
+    for i in range(n):
+        row = np.zeros(length, np.uint8)
+        lib().sim_expand_xmd(dst, C.c_size_t(len(dst)), _p(m[i:i + 1].copy()), C.c_size_t(ml), int(length), _p(row))
+        out[i] = row
+    return out

@@ -13,6 +13,7 @@
 
 #include "../../secp256k1-voi_b200/csrc/kernels.cuh"
 #include "../../secp256k1-voi_b200/csrc/msm.cuh"
+#include "../../secp256k1-voi_b200/csrc/h2c.cuh"
 
 using namespace s256;
 #define EXPORT extern "C" __attribute__((visibility("default")))
@@ -301,6 +302,15 @@ EXPORT void sim_schnorr_sign(const uint8_t *priv32, const uint8_t *msg, size_t m
     for (size_t i = 0; i < n; i++)
         item_schnorr_sign_finish(sig64 + 64 * i, status + i, priv32 + 32 * i, p65.data() + 65 * i, r65.data() + 65 * i,
                                  kbuf.data() + 32 * i, msg + msg_len * i, msg_len, valid[i]);
+}
+EXPORT void sim_hash_to_curve(const uint8_t *dst, size_t dst_len, const uint8_t *msg, size_t msg_len, size_t n, int ro,
+                              uint8_t *out65, uint8_t *status) {
+    scratch s(n ? n : 1);
+    for (size_t i = 0; i < n; i++) item_hash_to_curve(s.res[i], dst, (int)dst_len, msg + msg_len * i, msg_len, ro);
+    run_finish(s, n, false, false, 0, out65, status, nullptr);
+}
+EXPORT void sim_expand_xmd(const uint8_t *dst, size_t dst_len, const uint8_t *msg, size_t msg_len, int len, uint8_t *out) {
+    h2c_expand_xmd(out, len, dst, (int)dst_len, msg, msg_len);
 }
 EXPORT void sim_gen_table(int wbits, int nwin, uint8_t *out) {
     for (int w = 0; w < nwin; w++)

@@ -463,3 +463,37 @@ def check_schnorr_sign(be, o, n=48):
     good = st == 1
     pk, _ = o.batch_scalar_base_mult(priv[good])
     assert o.batch_schnorr_verify(pk[:, 1:33].copy(), msg[good], sig[good]).all()
+
+
+def check_hash_to_curve(be, o, n=32):
+    """RFC 9380 suite vectors (secec/h2c/h2c_test.go:35-120), expander vectors that fit 96 bytes,
+    then seeded messages against the oracle, both suites, odd message lengths, an oversize DST."""
+    doc = load_golden("h2c.json")
+    for s_ in doc["suites"]:
+        by_len = {}
+        for v in s_["vectors"]:
+            by_len.setdefault(len(v["msg"]), []).append(v)
+        for mlen, vs in by_len.items():
+            msgs = rows([v["msg"].encode() for v in vs], mlen) if mlen else np.zeros((len(vs), 0), np.uint8)
+            out, st = be.hash_to_curve(s_["dst"].encode(), msgs, s_["random_oracle"])
+            assert st.tolist() == [1] * len(vs)
+            for v, o65 in zip(vs, out):
+                assert o65[1:].tobytes().hex() == v["Px"] + v["Py"], v["msg"][:20]
+    for e in doc["expand"]:
+        for tc in e["tests"]:
+            if tc["len"] > 96:
+                continue
+            m = np.frombuffer(tc["msg"].encode(), np.uint8).reshape(1, -1) if tc["msg"] else np.zeros((1, 0), np.uint8)
+            got = be.expand_message_xmd(e["dst"].encode(), m, tc["len"])
+            assert got[0].tobytes().hex() == tc["uniform_bytes"], tc["msg"][:20]
+    for mlen in (0, 1, 31, 64, 119):
+        msgs = np.frombuffer(b"".join(synth.D(b"h2c", i)[:1] * mlen if mlen else b"" for i in range(n)), np.uint8).reshape(n, mlen) \
+            if mlen else np.zeros((n, 0), np.uint8)
+        if mlen:
+            msgs = (msgs + np.arange(n, dtype=np.uint8)[:, None] * 7 + np.arange(mlen, dtype=np.uint8)[None, :]).astype(np.uint8)
+        for ro in (True, False):
+            for dst in (b"QUUX-V01-CS02-with-secp256k1_XMD:SHA-256_SSWU_RO_", b"d", b"z" * 300):
+                out, st = be.hash_to_curve(dst, msgs, ro)
+                for i in range(0, n, max(1, n // 8)):
+                    exp, est = o.hash_to_curve(dst, msgs[i].tobytes(), ro)
+                    assert (st[i], out[i].tobytes()) == (est, exp), (mlen, ro, len(dst), i)

@@ -102,6 +102,12 @@ def test_schnorr_sign(engine, oracle):
     assert engine.schnorr_verify(pk[:, 1:33].copy(), msg, sig).all()
 
 
+def test_hash_to_curve(engine, oracle, s256):
+    ps.check_hash_to_curve(engine, oracle, n=512)
+    with pytest.raises(s256.S256Error):
+        engine.hash_to_curve(b"", np.zeros((2, 4), np.uint8))   # errInvalidDomainSep
+
+
 def test_empty_and_ragged(engine):
     z = np.zeros((0, 32), np.uint8)
     out, st = engine.scalar_base_mult(z)

@@ -23,6 +23,8 @@ class Backend:
     msm_combine = staticmethod(hs.msm_combine)
     ecdsa_sign_rfc6979 = staticmethod(hs.ecdsa_sign_rfc6979)
     schnorr_sign = staticmethod(hs.schnorr_sign)
+    hash_to_curve = staticmethod(hs.hash_to_curve)
+    expand_message_xmd = staticmethod(hs.expand_message_xmd)
     debug_field_op = staticmethod(hs.field_op)
     debug_gen_table = staticmethod(hs.gen_table)
 
@@ -110,3 +112,7 @@ def test_sign_rfc6979(oracle):
 
 def test_schnorr_sign(oracle):
     ps.check_schnorr_sign(be, oracle, n=16)
+
+
+def test_hash_to_curve(oracle):
+    ps.check_hash_to_curve(be, oracle, n=8)

@@ -205,3 +205,29 @@ def test_bip340_sign_rows(oracle):
         assert st == 1 and sig.hex() == r["sig"], r["index"]
         n += 1
     assert n >= 8
+
+
+def test_h2c_vectors(oracle):
+    # secec/h2c/h2c_test.go:35-194 -- RFC 9380 suite vectors (u, Q0/Q1, P) and expand_message_xmd vectors
+    doc = load_golden("h2c.json")
+    n = 0
+    for e in doc["expand"]:
+        for tc in e["tests"]:
+            got = oracle.expand_message_xmd(e["dst"].encode(), tc["msg"].encode(), tc["len"])
+            assert got.hex() == tc["uniform_bytes"], tc
+            n += 1
+    assert n == 20
+    for s in doc["suites"]:
+        for v in s["vectors"]:
+            out, st = oracle.hash_to_curve(s["dst"].encode(), v["msg"].encode(), s["random_oracle"])
+            assert st == 1 and out[1:].hex() == v["Px"] + v["Py"], v
+            # hash_to_field and the per-u maps (h2c_test.go checks u and Q too)
+            ub = oracle.expand_message_xmd(s["dst"].encode(), v["msg"].encode(), 96 if s["random_oracle"] else 48)
+            for j, (uhex, q) in enumerate(zip(v["u"], v["Q"])):
+                assert int.from_bytes(ub[48 * j:48 * j + 48], "big") % P == int(uhex, 16)
+                qo, qst = oracle.map_to_curve(ub[48 * j:48 * j + 48])
+                assert qst == 1 and qo[1:].hex() == q[0] + q[1]
+    assert oracle.expand_message_xmd(b"", b"x", 32) is None          # empty DST is an error
+    long_dst = b"a" * 300                                             # oversize DST is hashed
+    assert oracle.expand_message_xmd(long_dst, b"abc", 48) == oracle.expand_message_xmd(
+        hashlib.sha256(b"H2C-OVERSIZE-DST-" + long_dst).digest(), b"abc", 48)
