@@ -240,6 +240,41 @@ def main():
         b.record(); torch.cuda.synchronize()
         sbm[str(nn)] = nn * reps / (a.elapsed_time(b) * 1e-3)
 
+    # ---- the other hot-path entry points at the same batch size (device-resident, rank 0 only) ----
+    other = {}
+    if rank == 0:
+        def timed(fn, reps=3):
+            fn(); torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        priv = torch.from_numpy(pkg.synth.base_mult_scalars(n, start=77))
+        priv[:, 0] &= 0x7F                                   # every key below n
+        d_priv = priv.cuda()
+        d_aux = torch.from_numpy(pkg.synth.base_mult_scalars(n, start=78)).cuda()
+        pub, _ = eng.scalar_base_mult(d_priv)
+        sig, rec, st = eng.ecdsa_sign_rfc6979(d_priv, d_dg)
+        sig65 = torch.cat([sig, rec[:, None]], dim=1).contiguous()
+        ssig, sst = eng.schnorr_sign(d_priv, d_dg, d_aux)
+        pkx = pub[:, 1:33].contiguous()
+        assert bool(eng.ecdsa_verify(pub, d_dg, sig).all()) and bool(eng.schnorr_verify(pkx, d_dg, ssig).all())
+        q, qst = eng.ecdsa_recover(d_dg, sig65)
+        assert bool((qst == 1).all()) and bool((q == pub).all())
+        for name, key, fn in (
+                ("schnorr_verify", "schnorr_verify", lambda: eng.schnorr_verify(pkx, d_dg, ssig)),
+                ("ecdsa_recover", "ecdsa_recover", lambda: eng.ecdsa_recover(d_dg, sig65)),
+                ("ecdh", "ecdh", lambda: eng.ecdh(d_priv, pub)),
+                ("scalar_mult_ct", "scalar_mult", lambda: eng.scalar_mult(d_priv, pub)),
+                ("ecdsa_sign_rfc6979", "ecdsa_sign_rfc6979", lambda: eng.ecdsa_sign_rfc6979(d_priv, d_dg)),
+                ("schnorr_sign", "schnorr_sign", lambda: eng.schnorr_sign(d_priv, d_dg, d_aux))):
+            ms = timed(fn)
+            mac = pkg.mac32_per_item(key)
+            other[name] = {"items_per_s": n / (ms * 1e-3), "ms": ms,
+                           "frac_of_int_mul_peak": n / (ms * 1e-3) * mac / imad_peak if mac else None}
+
     if rank == 0:
         mac_item = pkg.mac32_per_item("ecdsa_verify")
         # dominant kernel: algorithmic MAC32 of one k_dsm launch / its mean duration
@@ -287,6 +322,7 @@ def main():
                          "hbm_frac": (6.549e9 * n / (1 << 20)) / ((dsm_ms / max(dsm_launches, 1)) * 1e-3) / 6548.2e9},
             "cpu_baseline": cpu,
             "scalar_base_mult_ops_per_sec": sbm,
+            "other_paths": other,
             "input_generation_s": t_gen,
         }
         print(json.dumps(line))
