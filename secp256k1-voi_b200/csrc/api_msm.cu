@@ -1,6 +1,7 @@
 // api_msm.cu -- Point.MultiScalarMult[Vartime]: the Pippenger kernels (msm.cuh) and their entry points.
 #include "ctx.h"
 #include "msm.cuh"
+#include "coop.cuh"
 #include <cub/device/device_scan.cuh>
 
 // ---- Pippenger MSM (msm.cuh) -------------------------------------------------
@@ -32,35 +33,90 @@ __global__ void __launch_bounds__(S256_TPB) k_msm_slice_counts(uint32_t total, c
     if (b < total) nsl[b] = msm_slices_of(counts[b]);
     if (b == total) nsl[b] = 0;
 }
-__global__ void __launch_bounds__(S256_TPB) k_msm_slices(uint32_t max_slices, uint32_t total, const uint32_t *sl_off,
-                                                         const uint32_t *offsets, const uint32_t *entries,
-                                                         const apt *aff, pt *slice_sum) {
-    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= max_slices || s >= sl_off[total]) return;
-    uint32_t st, en;
-    msm_slice_range(st, en, s, sl_off, offsets, total);
-    pt r;
-    msm_bucket_sum(r, entries, st, en, aff);
-    slice_sum[s] = r;
-}
-#define S256_MSM_WT 128
-// grid (blocks per window, nwin): every thread reduces MSM_SEG buckets, the CTA folds its threads
-__global__ void __launch_bounds__(S256_MSM_WT) k_msm_windows(msm_plan plan, const pt *slice_sum, const uint32_t *sl_off,
-                                                             pt *winpart, int parts) {
-    __shared__ pt sh[S256_MSM_WT];
-    int w = blockIdx.y, t = threadIdx.x;
-    int nbw = msm_window_buckets(plan, w);
-    int seg = msm_seg_for(nbw);
-    int lo = (blockIdx.x * S256_MSM_WT + t) * seg, hi = lo + seg;
-    if (hi > nbw) hi = nbw;
-    pt s;
-    if (lo < hi)
-        msm_segment(s, slice_sum, sl_off, (uint32_t)w * (uint32_t)plan.nb, lo, hi);
-    else
-        pt_set_identity(s);
-    sh[t] = s;
+// Slice schedule: range[s] = entry range of slice s, hist[MSM_SLICE - len] = slices of that length.
+#define S256_MSM_ST 256
+constexpr int MSM_BINS = MSM_SLICE + 1;
+__global__ void __launch_bounds__(S256_MSM_ST) k_msm_slice_ranges(uint32_t max_slices, uint32_t total, const uint32_t *sl_off,
+                                                                  const uint32_t *offsets, uint2 *range, uint32_t *hist) {
+    __shared__ uint32_t sh[MSM_BINS];
+    for (int i = threadIdx.x; i < MSM_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    for (int stride = S256_MSM_WT / 2; stride >= 1; stride >>= 1) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < max_slices && s < sl_off[total]) {
+        uint32_t st, en;
+        msm_slice_range(st, en, s, sl_off, offsets, total);
+        range[s] = make_uint2(st, en);
+        atomicAdd(&sh[MSM_SLICE - (en - st)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < MSM_BINS; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// perm = slice ids ordered by decreasing length (order inside a length class is arbitrary)
+__global__ void __launch_bounds__(S256_MSM_ST) k_msm_slice_perm(uint32_t max_slices, uint32_t total, const uint32_t *sl_off,
+                                                                const uint2 *range, const uint32_t *hist, uint32_t *cursor,
+                                                                uint32_t *perm) {
+    __shared__ uint32_t cnt[MSM_BINS], base[MSM_BINS];
+    for (int i = threadIdx.x; i < MSM_BINS; i += blockDim.x) cnt[i] = 0;
+    __syncthreads();
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = s < max_slices && s < sl_off[total];
+    uint32_t bin = 0, rank = 0;
+    if (live) {
+        uint2 r = range[s];
+        bin = MSM_SLICE - (r.y - r.x);
+        rank = atomicAdd(&cnt[bin], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < MSM_BINS; i += blockDim.x) {
+        uint32_t c = cnt[i], before = 0;
+        if (c) {
+            for (int k = 0; k < i; k++) before += hist[k];
+            base[i] = before + atomicAdd(&cursor[i], c);
+        }
+    }
+    __syncthreads();
+    if (live) perm[base[bin] + rank] = s;
+}
+__global__ void __launch_bounds__(S256_TPB) k_msm_slices(uint32_t max_slices, uint32_t total, const uint32_t *sl_off,
+                                                         const uint32_t *perm, const uint2 *range, const uint32_t *entries,
+                                                         const apt *aff, pt *slice_sum) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= max_slices || t >= sl_off[total]) return;
+    uint32_t s = perm[t];
+    uint2 r = range[s];
+    pt acc;
+    msm_bucket_sum(acc, entries, r.x, r.y, aff);
+    slice_sum[s] = acc;
+}
+
+// One CTA of MSM_WT threads, thread t holding (run_t, sum_t) with sum_t weighted relative to its own
+// first element: returns (in thread 0)  R = sum_t run_t  and  A = sum_t (sum_t + t * 2^lg * run_t).
+// sum_t t * run_t is the sum over t >= 1 of the suffix sums S_t = sum_{u >= t} run_u.
+__device__ __forceinline__ void msm_cta_weighted(pt &R, pt &A, const pt &run, const pt &sum, int lg, pt *sh) {
+    int t = threadIdx.x;
+    sh[t] = run;
+    __syncthreads();
+    for (int d = 1; d < MSM_WT; d <<= 1) {
+        pt v = sh[t];
+        if (t + d < MSM_WT) {
+            pt o = sh[t + d];
+            pt_add(v, v, o);
+        }
+        __syncthreads();
+        sh[t] = v;
+        __syncthreads();
+    }
+    R = sh[0];
+    pt v = sum;
+    if (t >= 1) {
+        pt st = sh[t];
+        msm_weigh(v, sum, st, lg);
+    }
+    __syncthreads();
+    sh[t] = v;
+    __syncthreads();
+    for (int stride = MSM_WT / 2; stride >= 1; stride >>= 1) {
         if (t < stride) {
             pt a = sh[t], b = sh[t + stride];
             pt_add(a, a, b);
@@ -68,29 +124,66 @@ __global__ void __launch_bounds__(S256_MSM_WT) k_msm_windows(msm_plan plan, cons
         }
         __syncthreads();
     }
-    if (t == 0) winpart[w * parts + blockIdx.x] = sh[0];
+    A = sh[0];
 }
-// win[w * parts] = sum of the `parts` CTA partials of window w (one thread per window)
-__global__ void k_msm_fold(int nwin, pt *winpart, int parts) {
-    int w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nwin) return;
-    pt acc = winpart[w * parts];
-    for (int q = 1; q < parts; q++) {
-        pt t = winpart[w * parts + q];
-        pt_add(acc, acc, t);
+// level 1, grid (parts, nwin): part[(w * parts + blk) * 2 + {0, 1}] = (R, A) of the CTA's MSM_WT * seg buckets
+__global__ void __launch_bounds__(MSM_WT) k_msm_windows(msm_plan plan, const pt *slice_sum, const uint32_t *sl_off, pt *part,
+                                                        int parts) {
+    __shared__ pt sh[MSM_WT];
+    int w = blockIdx.y, t = threadIdx.x;
+    int nbw = msm_window_buckets(plan, w);
+    if ((int)blockIdx.x >= msm_parts_for(nbw)) return;
+    int seg = msm_seg_for(nbw);
+    int lo = (blockIdx.x * MSM_WT + t) * seg, hi = lo + seg;
+    if (hi > nbw) hi = nbw;
+    pt run, sum;
+    if (lo < hi) {
+        msm_segment_pair(run, sum, slice_sum, sl_off, (uint32_t)w * (uint32_t)plan.nb, lo, hi);
+    } else {
+        pt_set_identity(run);
+        pt_set_identity(sum);
     }
-    winpart[w * parts] = acc;
+    pt R, A;
+    msm_cta_weighted(R, A, run, sum, msm_log2(seg), sh);
+    if (t == 0) {
+        part[((size_t)w * parts + blockIdx.x) * 2] = R;
+        part[((size_t)w * parts + blockIdx.x) * 2 + 1] = A;
+    }
 }
-// acc (device, projective) += Horner(window partials); first = overwrite
-__global__ void k_msm_final(msm_plan plan, const pt *winpart, int parts, pt *acc, int first) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// level 2, one CTA per window: win[w] = sum over the window's CTAs q of (A_q + q * MSM_WT * seg * R_q)
+__global__ void __launch_bounds__(MSM_WT) k_msm_windows2(msm_plan plan, const pt *part, int parts, pt *win) {
+    __shared__ pt sh[MSM_WT];
+    int w = blockIdx.x, t = threadIdx.x;
+    int nbw = msm_window_buckets(plan, w);
+    pt run, sum;
+    if (t < msm_parts_for(nbw)) {
+        run = part[((size_t)w * parts + t) * 2];
+        sum = part[((size_t)w * parts + t) * 2 + 1];
+    } else {
+        pt_set_identity(run);
+        pt_set_identity(sum);
+    }
+    pt R, A;
+    msm_cta_weighted(R, A, run, sum, msm_log2(MSM_WT * msm_seg_for(nbw)), sh);
+    if (t == 0) win[w] = A;
+}
+// acc (device, projective) += Horner(windows); first = overwrite.  One warp, 8-lane cooperative group law.
+__global__ void __launch_bounds__(32) k_msm_final(msm_plan plan, const pt *win, pt *acc, int first) {
+    int j = threadIdx.x & 7;
     pt r;
-    msm_horner(r, winpart, plan, 1, parts);
+    pt_set_identity(r);
+    for (int w = plan.nwin - 1; w >= 0; w--) {
+        if (w != plan.nwin - 1)
+            for (int k = 0; k < plan.c; k++) pt_double_coop(r, j);
+        pt t = win[w];
+        pt_add_coop(r, t, j);
+    }
     if (!first) {
         pt a = *acc;
-        pt_add(r, r, a);
+        pt_add_coop(r, a, j);
     }
-    *acc = r;
+    __syncwarp();
+    if (threadIdx.x == 0) *acc = r;
 }
 // out[t] = sum of in[t], in[t + nout], ...   (tree levels of the constant-time MSM)
 __global__ void __launch_bounds__(S256_TPB) k_reduce_points(const pt *in, size_t n, pt *out, size_t nout) {
@@ -167,7 +260,11 @@ static int msm_ensure(s256_ctx *ctx) {
     CK(cudaMalloc(&ctx->msm_buckets, ctx->msm_max_slices * sizeof(pt)));
     CK(cudaMalloc(&ctx->msm_nsl, (total + 1) * 4));
     CK(cudaMalloc(&ctx->msm_sloff, (total + 1) * 4));
-    CK(cudaMalloc(&ctx->msm_win, (size_t)MSM_MAX_WIN * MSM_MAX_PARTS * sizeof(pt)));
+    CK(cudaMalloc(&ctx->msm_range, ctx->msm_max_slices * sizeof(uint2)));
+    CK(cudaMalloc(&ctx->msm_perm, ctx->msm_max_slices * 4));
+    CK(cudaMalloc(&ctx->msm_hist, 2 * MSM_BINS * 4));
+    CK(cudaMalloc(&ctx->msm_part, (size_t)MSM_MAX_WIN * MSM_MAX_PARTS * 2 * sizeof(pt)));
+    CK(cudaMalloc(&ctx->msm_win, (size_t)MSM_MAX_WIN * sizeof(pt)));
     CK(cudaMalloc(&ctx->msm_acc, sizeof(pt)));
     CK(cudaMalloc(&ctx->msm_tmp, 4096 * sizeof(pt)));
     CK(cudaMalloc(&ctx->msm_flag, 4));
@@ -217,18 +314,21 @@ static int chunk_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, siz
     CK(cub::DeviceScan::ExclusiveSum(ctx->msm_cub, bytes, ctx->msm_nsl, ctx->msm_sloff, (int)(total + 1), s));
     size_t max_slices = (size_t)total + ((size_t)pl.nwin * n) / MSM_SLICE + 1;
     if (max_slices > ctx->msm_max_slices) max_slices = ctx->msm_max_slices;
-    LAUNCH(ctx, k_msm_slices, grid_for(max_slices), 0, s, (uint32_t)max_slices, total, ctx->msm_sloff, ctx->msm_offsets,
-           ctx->msm_entries, ctx->aff, ctx->msm_buckets);
-    int parts = 1;
-    for (int w = 0; w < pl.nwin; w += pl.nwin - 1 > 0 ? pl.nwin - 1 : 1) {  // first and top window cover both sizes
-        int nbw = msm_window_buckets(pl, w);
-        int p = (nbw + S256_MSM_WT * msm_seg_for(nbw) - 1) / (S256_MSM_WT * msm_seg_for(nbw));
-        if (p > parts) parts = p;
-    }
-    k_msm_windows<<<dim3(parts, pl.nwin), S256_MSM_WT, 0, s>>>(pl, ctx->msm_buckets, ctx->msm_sloff, ctx->msm_win, parts);
-    k_msm_fold<<<1, 64, 0, s>>>(pl.nwin, ctx->msm_win, parts);
-    k_msm_final<<<1, 1, 0, s>>>(pl, ctx->msm_win, parts, ctx->msm_acc, first);
-    ctx->launches.fetch_add(3, std::memory_order_relaxed);
+    // hand the slices out longest first: every warp then runs (almost) equally long threads
+    CK(cudaMemsetAsync(ctx->msm_hist, 0, 2 * MSM_BINS * 4, s));
+    unsigned sgrid = (unsigned)((max_slices + S256_MSM_ST - 1) / S256_MSM_ST);
+    k_msm_slice_ranges<<<sgrid, S256_MSM_ST, 0, s>>>((uint32_t)max_slices, total, ctx->msm_sloff, ctx->msm_offsets,
+                                                     (uint2 *)ctx->msm_range, ctx->msm_hist);
+    k_msm_slice_perm<<<sgrid, S256_MSM_ST, 0, s>>>((uint32_t)max_slices, total, ctx->msm_sloff, (const uint2 *)ctx->msm_range,
+                                                   ctx->msm_hist, ctx->msm_hist + MSM_BINS, ctx->msm_perm);
+    LAUNCH(ctx, k_msm_slices, grid_for(max_slices), 0, s, (uint32_t)max_slices, total, ctx->msm_sloff, ctx->msm_perm,
+           (const uint2 *)ctx->msm_range, ctx->msm_entries, ctx->aff, ctx->msm_buckets);
+    int parts = msm_parts_for(pl.nb);
+    if (msm_parts_for(pl.nb_top) > parts) parts = msm_parts_for(pl.nb_top);
+    k_msm_windows<<<dim3(parts, pl.nwin), MSM_WT, 0, s>>>(pl, ctx->msm_buckets, ctx->msm_sloff, ctx->msm_part, parts);
+    k_msm_windows2<<<pl.nwin, MSM_WT, 0, s>>>(pl, ctx->msm_part, parts, ctx->msm_win);
+    k_msm_final<<<1, 32, 0, s>>>(pl, ctx->msm_win, ctx->msm_acc, first);
+    ctx->launches.fetch_add(5, std::memory_order_relaxed);
     return S256_SUCCESS;
 }
 

@@ -46,9 +46,10 @@ struct s256_ctx {
     size_t msm_cap = 0;
     uint32_t *msm_counts = nullptr, *msm_offsets = nullptr, *msm_cursor = nullptr, *msm_entries = nullptr;
     uint32_t *msm_flag = nullptr;
-    uint32_t *msm_nsl = nullptr, *msm_sloff = nullptr;
+    uint32_t *msm_nsl = nullptr, *msm_sloff = nullptr, *msm_perm = nullptr, *msm_hist = nullptr;
+    void *msm_range = nullptr;
     size_t msm_max_slices = 0;
-    pt *msm_buckets = nullptr, *msm_win = nullptr, *msm_acc = nullptr, *msm_tmp = nullptr;
+    pt *msm_buckets = nullptr, *msm_win = nullptr, *msm_part = nullptr, *msm_acc = nullptr, *msm_tmp = nullptr;
     void *msm_cub = nullptr;
     size_t msm_cub_bytes = 0;
     // optional per-kernel timing of the dominant kernel (bench.py roofline)
@@ -136,7 +137,7 @@ static inline int inv_k_for(size_t n) { return n >= ((size_t)1 << 19) ? INV_K : 
             default: { constexpr int KK = INV_K; CALL; } break; \
         }                                 \
     } while (0)
-constexpr int MSM_MAX_PARTS = 16;  // (2^16 buckets) / (128 threads * 32 buckets)
+constexpr int MSM_MAX_PARTS = 64;  // (2^16 buckets) / (128 threads * 8 buckets)
 static inline unsigned grid_for_groups(size_t n, int k) { return grid_for((n + k - 1) / k); }
 
 // Runs `body(offset, count)` over chunks of at most cap items.

@@ -13,10 +13,17 @@
 //            harmless because only the group element matters
 //   slices : buckets are cut into slices of <= MSM_SLICE entries; one thread per slice does
 //            mixed complete additions (inputs are affine).  Slicing bounds the serial work of
-//            dense buckets (e.g. the partial top window) and of skewed scalar distributions
-//   windows: R_w = sum_j j * B_{w,j} by segmented running sums (MSM_SEG buckets per thread,
-//            many CTAs per window), a bucket being the sum of its slices
-//   final  : per-window partials are folded, then Horner over the windows (c doublings each)
+//            dense buckets (e.g. the partial top window) and of skewed scalar distributions.
+//            Slices are handed to threads in order of decreasing length (a 65-bin counting
+//            sort), so the lanes of a warp run the same number of additions
+//   windows: R_w = sum_j j * B_{w,j} in two levels, a bucket being the sum of its slices.  Level 1:
+//            a thread owns seg consecutive buckets and forms (run, sum) = (sum B_j,
+//            sum (j-lo+1) B_j); the CTA turns the position weights lo_t = t * seg into a suffix
+//            scan of the runs (sum_t t * run_t = sum_{t>=1} S_t, S_t = sum_{u>=t} run_u): no
+//            scalar multiple of a point is ever computed, only log2(seg) doublings.  Level 2 is
+//            the same step over the CTAs' (run, sum) pairs, one CTA per window
+//   final  : Horner over the windows (c doublings each) with the 8-lane cooperative group law of
+//            coop.cuh, because this chain of 256 - c doublings is the serial tail of the MSM
 #pragma once
 #include "fe.cuh"
 #include "point.cuh"
@@ -26,13 +33,24 @@ namespace s256 {
 
 constexpr int MSM_MAX_C = 16;
 constexpr int MSM_SLICE = 64;   // entries per slice
-constexpr int MSM_SEG = 32;     // most buckets one thread reduces in the window stage
-// buckets per thread for a window of nbw buckets: aim for >= 512 threads per window
+constexpr int MSM_WT = 128;     // threads of a window-stage CTA
+// buckets one thread reduces in the window stage (a power of two, like every window size):
+// small, because the stage is latency bound -- each thread runs 2 * seg dependent additions
 S256_HD int msm_seg_for(int nbw) {
     int seg = nbw >> 9;
-    if (seg < 2) seg = 2;
-    if (seg > MSM_SEG) seg = MSM_SEG;
+    if (seg < 1) seg = 1;
+    if (seg > 8) seg = 8;
     return seg;
+}
+S256_HD int msm_log2(int v) {
+    int l = 0;
+    while ((1 << (l + 1)) <= v) l++;
+    return l;
+}
+// CTAs of MSM_WT threads a window of nbw buckets needs (<= MSM_WT, so one CTA folds them)
+S256_HD int msm_parts_for(int nbw) {
+    int per = MSM_WT * msm_seg_for(nbw);
+    return (nbw + per - 1) / per;
 }
 constexpr int MSM_MAX_WIN = 64;  // c = 4 -> 64 windows
 
@@ -89,11 +107,22 @@ S256_HD void msm_digits(int32_t *d, const sc &k, const msm_plan &p) {
 S256_HD void msm_bucket_sum(pt &out, const uint32_t *entries, uint32_t start, uint32_t end, const apt *aff) {
     pt acc;
     pt_set_identity(acc);
-    for (uint32_t e = start; e < end; e++) {
-        uint32_t v = entries[e];
+    if (start < end) {
+        // the next point is fetched before the current addition: the gather latency hides behind it
+        uint32_t v = entries[start];
         apt a = aff[v >> 1];
-        if (v & 1u) fe_neg(a.y, a.y);
-        pt_add_mixed(acc, acc, a.x, a.y);
+        for (uint32_t e = start; e < end; e++) {
+            uint32_t vn = v;
+            apt an = a;
+            if (e + 1 < end) {
+                vn = entries[e + 1];
+                an = aff[vn >> 1];
+            }
+            if (v & 1u) fe_neg(a.y, a.y);
+            pt_add_mixed(acc, acc, a.x, a.y);
+            v = vn;
+            a = an;
+        }
     }
     out = acc;
 }
@@ -111,29 +140,24 @@ S256_HD void msm_bucket_from_slices(pt &out, const pt *slice_sum, const uint32_t
     }
 }
 
-// sum_{j in (lo, hi]} j * B_j for the window whose first bucket is `base`
-S256_HD void msm_segment(pt &out, const pt *slice_sum, const uint32_t *sl_off, uint32_t base, int lo, int hi) {
-    pt run, sum;
-    pt_set_identity(run);
-    pt_set_identity(sum);
-    for (int j = hi; j > lo; j--) {
+// run = sum_{j in [lo, hi)} B_j and sum = sum_j (j - lo + 1) * B_j for the window whose first
+// bucket is `base` (lo < hi).  The weights are relative to lo: the caller scales by position.
+S256_HD void msm_segment_pair(pt &run, pt &sum, const pt *slice_sum, const uint32_t *sl_off, uint32_t base, int lo,
+                              int hi) {
+    msm_bucket_from_slices(run, slice_sum, sl_off, base + (uint32_t)(hi - 1));
+    sum = run;
+    for (int j = hi - 1; j > lo; j--) {
         pt b;
         msm_bucket_from_slices(b, slice_sum, sl_off, base + (uint32_t)(j - 1));
         pt_add(run, run, b);
         pt_add(sum, sum, run);
     }
-    // sum = sum_j (j - lo) B_j ; add lo * run (double-and-add from the top set bit of lo)
-    if (lo > 0) {
-        int top = 0;
-        while ((lo >> (top + 1)) != 0) top++;
-        pt m = run;
-        for (int b = top - 1; b >= 0; b--) {
-            pt_double(m, m);
-            if ((lo >> b) & 1) pt_add(m, m, run);
-        }
-        pt_add(sum, sum, m);
-    }
-    out = sum;
+}
+// v = sum + 2^log2w * s   (the position weight of a thread's / CTA's run total)
+S256_HD void msm_weigh(pt &v, const pt &sum, const pt &s, int log2w) {
+    pt m = s;
+    for (int k = 0; k < log2w; k++) pt_double(m, m);
+    pt_add(v, sum, m);
 }
 
 // Horner over window results, highest first; window w is the sum of `parts` partials at win[w * stride ..]

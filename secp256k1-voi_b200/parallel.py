@@ -32,9 +32,10 @@ def gather_bytes(local_row, group=None, device=None):
     t = torch.from_numpy(np.ascontiguousarray(local_row, dtype=np.uint8))
     if device is not None:
         t = t.to(device)
-    out = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(out, t, group=group)
-    return np.stack([o.cpu().numpy() for o in out])
+    t = t.reshape(-1)
+    out = torch.empty(world * t.numel(), dtype=t.dtype, device=t.device)  # flat: the layout gloo accepts too
+    dist.all_gather_into_tensor(out, t, group=group)   # one collective, one copy back
+    return out.cpu().numpy().reshape(world, -1)
 
 
 def msm_sharded(engine, k32_local, pt65_local, vartime=True, group=None, device=None):

@@ -6,6 +6,7 @@
 // the build container has no GPU: kernel logic (recoding, ladders, batched
 // inversion, encodings) is debugged here against the oracle before GPU time
 // is spent.  It is never linked into, or called by, the product library.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -211,32 +212,47 @@ EXPORT void sim_msm(const uint8_t *k32, const uint8_t *pt65, size_t n, int varti
             msm_slice_range(st, en, sidx, sl_off.data(), offsets.data(), (uint32_t)total);
             msm_bucket_sum(slice_sum[sidx], entries.data(), st, en, s.aff.data());
         }
-        const int T = 128;
-        int parts = 1;
+        // window stage exactly as k_msm_windows / k_msm_windows2 run it: (run, sum) per thread, suffix
+        // scan of the runs across the CTA, position weights as doublings, tree sum
+        const int T = MSM_WT;
+        auto cta_weighted = [&](std::vector<pt> &run, std::vector<pt> &sum, int lg, pt &R, pt &A) {
+            std::vector<pt> sh = run;
+            for (int d = 1; d < T; d <<= 1) {
+                std::vector<pt> nx = sh;
+                for (int t = 0; t + d < T; t++) pt_add(nx[t], sh[t], sh[t + d]);
+                sh = nx;
+            }
+            R = sh[0];
+            std::vector<pt> v(T);
+            v[0] = sum[0];
+            for (int t = 1; t < T; t++) msm_weigh(v[t], sum[t], sh[t], lg);
+            for (int stride = T / 2; stride >= 1; stride >>= 1)
+                for (int t = 0; t < stride; t++) pt_add(v[t], v[t], v[t + stride]);
+            A = v[0];
+        };
+        int parts = std::max(msm_parts_for(pl.nb), msm_parts_for(pl.nb_top));
+        std::vector<pt> part((size_t)pl.nwin * parts * 2), win(pl.nwin);
         for (int w = 0; w < pl.nwin; w++) {
-            int nbw = msm_window_buckets(pl, w);
-            int p_ = (nbw + T * msm_seg_for(nbw) - 1) / (T * msm_seg_for(nbw));
-            if (p_ > parts) parts = p_;
-        }
-        std::vector<pt> win((size_t)pl.nwin * parts);
-        for (int w = 0; w < pl.nwin; w++) {
-            int nbw = msm_window_buckets(pl, w);
-            for (int blk = 0; blk < parts; blk++) {
-                std::vector<pt> sh(T);
-                int seg = msm_seg_for(nbw);
+            int nbw = msm_window_buckets(pl, w), seg = msm_seg_for(nbw), pw = msm_parts_for(nbw);
+            for (int blk = 0; blk < pw; blk++) {
+                std::vector<pt> run(T), sum(T);
                 for (int t = 0; t < T; t++) {
                     int lo = (blk * T + t) * seg, hi = lo + seg;
                     if (hi > nbw) hi = nbw;
-                    if (lo < hi) msm_segment(sh[t], slice_sum.data(), sl_off.data(), (uint32_t)w * (uint32_t)pl.nb, lo, hi);
-                    else pt_set_identity(sh[t]);
+                    if (lo < hi) msm_segment_pair(run[t], sum[t], slice_sum.data(), sl_off.data(), (uint32_t)w * (uint32_t)pl.nb, lo, hi);
+                    else { pt_set_identity(run[t]); pt_set_identity(sum[t]); }
                 }
-                for (int stride = T / 2; stride >= 1; stride >>= 1)
-                    for (int t = 0; t < stride; t++) pt_add(sh[t], sh[t], sh[t + stride]);
-                win[(size_t)w * parts + blk] = sh[0];
+                cta_weighted(run, sum, msm_log2(seg), part[((size_t)w * parts + blk) * 2], part[((size_t)w * parts + blk) * 2 + 1]);
             }
+            std::vector<pt> run(T), sum(T);
+            for (int t = 0; t < T; t++) {
+                if (t < pw) { run[t] = part[((size_t)w * parts + t) * 2]; sum[t] = part[((size_t)w * parts + t) * 2 + 1]; }
+                else { pt_set_identity(run[t]); pt_set_identity(sum[t]); }
+            }
+            pt R;
+            cta_weighted(run, sum, msm_log2(T * seg), R, win[w]);
         }
-        for (int w = 0; w < pl.nwin; w++)
-            for (int q = 1; q < parts; q++) pt_add(win[(size_t)w * parts], win[(size_t)w * parts], win[(size_t)w * parts + q]);
+        parts = 1;
         msm_horner(acc, win.data(), pl, 1, parts);
     }
     memset(out65, 0, 65);

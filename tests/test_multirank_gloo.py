@@ -58,6 +58,9 @@ def _worker(rank, world, port, q):
         lo, hi = par.shard_range(48, rank, world)
         ok_ver = np.array_equal(mine, v["expected"][lo:hi])
         q.put((rank, bool(ok_msm), bool(ok_poison), bool(ok_ver)))
+    except Exception as e:  # report instead of leaving the parent to time out on an empty queue
+        q.put((rank, repr(e)))
+        raise
     finally:
         dist.destroy_process_group()
 
@@ -82,7 +85,8 @@ def test_world_size_2_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
+    res = [q.get(timeout=300) for _ in procs]
+    assert all(len(r) == 4 for r in res), res
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
