@@ -37,14 +37,15 @@ __global__ void __launch_bounds__(S256_TPB) k_msm_slice_counts(uint32_t total, c
 #define S256_MSM_ST 256
 constexpr int MSM_BINS = MSM_SLICE + 1;
 __global__ void __launch_bounds__(S256_MSM_ST) k_msm_slice_ranges(uint32_t max_slices, uint32_t total, const uint32_t *sl_off,
-                                                                  const uint32_t *offsets, uint2 *range, uint32_t *hist) {
+                                                                  const uint32_t *offsets, uint2 *range, uint32_t *bucket_of,
+                                                                  uint32_t *hist) {
     __shared__ uint32_t sh[MSM_BINS];
     for (int i = threadIdx.x; i < MSM_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < max_slices && s < sl_off[total]) {
         uint32_t st, en;
-        msm_slice_range(st, en, s, sl_off, offsets, total);
+        bucket_of[s] = msm_slice_range(st, en, s, sl_off, offsets, total);
         range[s] = make_uint2(st, en);
         atomicAdd(&sh[MSM_SLICE - (en - st)], 1u);
     }
@@ -88,6 +89,14 @@ __global__ void __launch_bounds__(S256_TPB) k_msm_slices(uint32_t max_slices, ui
     pt acc;
     msm_bucket_sum(acc, entries, r.x, r.y, aff);
     slice_sum[s] = acc;
+}
+// second level for buckets of more than MSM_SUPER slices (msm.cuh); a no-op thread otherwise
+__global__ void __launch_bounds__(S256_TPB) k_msm_superslices(uint32_t max_slices, uint32_t total, const uint32_t *sl_off,
+                                                              const uint32_t *bucket_of, pt *slice_sum) {
+    uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= max_slices || s >= sl_off[total]) return;
+    uint32_t b = bucket_of[s];
+    msm_superslice_fold(slice_sum, s, sl_off[b], sl_off[b + 1]);
 }
 
 // One CTA of MSM_WT threads, thread t holding (run_t, sum_t) with sum_t weighted relative to its own
@@ -262,6 +271,7 @@ static int msm_ensure(s256_ctx *ctx) {
     CK(cudaMalloc(&ctx->msm_sloff, (total + 1) * 4));
     CK(cudaMalloc(&ctx->msm_range, ctx->msm_max_slices * sizeof(uint2)));
     CK(cudaMalloc(&ctx->msm_perm, ctx->msm_max_slices * 4));
+    CK(cudaMalloc(&ctx->msm_sbkt, ctx->msm_max_slices * 4));
     CK(cudaMalloc(&ctx->msm_hist, 2 * MSM_BINS * 4));
     CK(cudaMalloc(&ctx->msm_part, (size_t)MSM_MAX_WIN * MSM_MAX_PARTS * 2 * sizeof(pt)));
     CK(cudaMalloc(&ctx->msm_win, (size_t)MSM_MAX_WIN * sizeof(pt)));
@@ -318,11 +328,13 @@ static int chunk_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, siz
     CK(cudaMemsetAsync(ctx->msm_hist, 0, 2 * MSM_BINS * 4, s));
     unsigned sgrid = (unsigned)((max_slices + S256_MSM_ST - 1) / S256_MSM_ST);
     k_msm_slice_ranges<<<sgrid, S256_MSM_ST, 0, s>>>((uint32_t)max_slices, total, ctx->msm_sloff, ctx->msm_offsets,
-                                                     (uint2 *)ctx->msm_range, ctx->msm_hist);
+                                                     (uint2 *)ctx->msm_range, ctx->msm_sbkt, ctx->msm_hist);
     k_msm_slice_perm<<<sgrid, S256_MSM_ST, 0, s>>>((uint32_t)max_slices, total, ctx->msm_sloff, (const uint2 *)ctx->msm_range,
                                                    ctx->msm_hist, ctx->msm_hist + MSM_BINS, ctx->msm_perm);
     LAUNCH(ctx, k_msm_slices, grid_for(max_slices), 0, s, (uint32_t)max_slices, total, ctx->msm_sloff, ctx->msm_perm,
            (const uint2 *)ctx->msm_range, ctx->msm_entries, ctx->aff, ctx->msm_buckets);
+    LAUNCH(ctx, k_msm_superslices, grid_for(max_slices), 0, s, (uint32_t)max_slices, total, ctx->msm_sloff, ctx->msm_sbkt,
+           ctx->msm_buckets);
     int parts = msm_parts_for(pl.nb);
     if (msm_parts_for(pl.nb_top) > parts) parts = msm_parts_for(pl.nb_top);
     k_msm_windows<<<dim3(parts, pl.nwin), MSM_WT, 0, s>>>(pl, ctx->msm_buckets, ctx->msm_sloff, ctx->msm_part, parts);

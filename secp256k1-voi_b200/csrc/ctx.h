@@ -46,7 +46,7 @@ struct s256_ctx {
     size_t msm_cap = 0;
     uint32_t *msm_counts = nullptr, *msm_offsets = nullptr, *msm_cursor = nullptr, *msm_entries = nullptr;
     uint32_t *msm_flag = nullptr;
-    uint32_t *msm_nsl = nullptr, *msm_sloff = nullptr, *msm_perm = nullptr, *msm_hist = nullptr;
+    uint32_t *msm_nsl = nullptr, *msm_sloff = nullptr, *msm_perm = nullptr, *msm_hist = nullptr, *msm_sbkt = nullptr;
     void *msm_range = nullptr;
     size_t msm_max_slices = 0;
     pt *msm_buckets = nullptr, *msm_win = nullptr, *msm_part = nullptr, *msm_acc = nullptr, *msm_tmp = nullptr;

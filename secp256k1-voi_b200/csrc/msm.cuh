@@ -33,6 +33,7 @@ namespace s256 {
 
 constexpr int MSM_MAX_C = 16;
 constexpr int MSM_SLICE = 64;   // entries per slice
+constexpr int MSM_SUPER = 64;   // slices per super-slice (buckets of more than MSM_SUPER slices only)
 constexpr int MSM_WT = 128;     // threads of a window-stage CTA
 // buckets one thread reduces in the window stage (a power of two, like every window size):
 // small, because the stage is latency bound -- each thread runs 2 * seg dependent additions
@@ -130,11 +131,27 @@ S256_HD void msm_bucket_sum(pt &out, const uint32_t *entries, uint32_t start, ui
 // slices of bucket b: max(1, ceil(count / MSM_SLICE))
 S256_HD uint32_t msm_slices_of(uint32_t count) { return count == 0 ? 1u : (count + MSM_SLICE - 1) / MSM_SLICE; }
 
-// bucket b = sum of its slices (almost always exactly one)
+// A bucket of more than MSM_SUPER slices (> 4096 entries: equal or adversarial scalars) gets a second
+// level: the thread of every MSM_SUPER-th slice folds the next MSM_SUPER slice sums into its own slot.
+// [s0, s1) = the slices of the bucket that owns slice s.
+S256_HD void msm_superslice_fold(pt *slice_sum, uint32_t s, uint32_t s0, uint32_t s1) {
+    if (s1 - s0 <= (uint32_t)MSM_SUPER || ((s - s0) % (uint32_t)MSM_SUPER) != 0) return;
+    uint32_t e = s + (uint32_t)MSM_SUPER;
+    if (e > s1) e = s1;
+    pt acc = slice_sum[s];
+    for (uint32_t q = s + 1; q < e; q++) {
+        pt t = slice_sum[q];
+        pt_add(acc, acc, t);
+    }
+    slice_sum[s] = acc;
+}
+
+// bucket b = sum of its slices (almost always exactly one), or of its super-slices
 S256_HD void msm_bucket_from_slices(pt &out, const pt *slice_sum, const uint32_t *sl_off, uint32_t b) {
     uint32_t s0 = sl_off[b], s1 = sl_off[b + 1];
+    uint32_t step = s1 - s0 > (uint32_t)MSM_SUPER ? (uint32_t)MSM_SUPER : 1u;
     out = slice_sum[s0];
-    for (uint32_t s = s0 + 1; s < s1; s++) {
+    for (uint32_t s = s0 + step; s < s1; s += step) {
         pt q = slice_sum[s];
         pt_add(out, out, q);
     }
@@ -174,9 +191,9 @@ S256_HD void msm_horner(pt &out, const pt *win, const msm_plan &p, int parts, in
     }
     out = acc;
 }
-// which slice range does slice s cover?  binary search for the bucket, then the entry range
-S256_HD void msm_slice_range(uint32_t &start, uint32_t &end, uint32_t s, const uint32_t *sl_off, const uint32_t *offsets,
-                             uint32_t total_buckets) {
+// which entry range does slice s cover?  binary search for the bucket (returned), then the range
+S256_HD uint32_t msm_slice_range(uint32_t &start, uint32_t &end, uint32_t s, const uint32_t *sl_off,
+                                 const uint32_t *offsets, uint32_t total_buckets) {
     uint32_t lo = 0, hi = total_buckets;  // invariant: sl_off[lo] <= s < sl_off[hi]
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
@@ -187,6 +204,7 @@ S256_HD void msm_slice_range(uint32_t &start, uint32_t &end, uint32_t s, const u
     end = start + MSM_SLICE;
     if (end > offsets[lo + 1]) end = offsets[lo + 1];
     if (start > end) start = end;
+    return lo;  // the bucket
 }
 
 // projective point <-> 96-byte big-endian X || Y || Z (the cross-GPU partial)

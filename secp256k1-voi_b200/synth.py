@@ -190,4 +190,4 @@ def msm_batch(n, base_mult, start=0, seed=SEED):
     pts, st = base_mult(_be32_rows(d))
     total = sum(a * b for a, b in zip(d, s)) % N
     return {"k32": _be32_rows(s), "pt65": np.asarray(pts, np.uint8).reshape(n, 65),
-            "closed_form_scalar": total.to_bytes(32, "big")}
+            "closed_form_scalar": total.to_bytes(32, "big"), "key_sum": sum(d) % N}

@@ -207,11 +207,14 @@ EXPORT void sim_msm(const uint8_t *k32, const uint8_t *pt65, size_t n, int varti
         std::vector<uint32_t> sl_off(total + 1, 0);
         for (size_t b = 0; b < total; b++) sl_off[b + 1] = sl_off[b] + msm_slices_of(counts[b]);
         std::vector<pt> slice_sum(sl_off[total]);
+        std::vector<uint32_t> bucket_of(sl_off[total]);
         for (uint32_t sidx = 0; sidx < sl_off[total]; sidx++) {
             uint32_t st, en;
-            msm_slice_range(st, en, sidx, sl_off.data(), offsets.data(), (uint32_t)total);
+            bucket_of[sidx] = msm_slice_range(st, en, sidx, sl_off.data(), offsets.data(), (uint32_t)total);
             msm_bucket_sum(slice_sum[sidx], entries.data(), st, en, s.aff.data());
         }
+        for (uint32_t sidx = 0; sidx < sl_off[total]; sidx++)
+            msm_superslice_fold(slice_sum.data(), sidx, sl_off[bucket_of[sidx]], sl_off[bucket_of[sidx] + 1]);
         // window stage exactly as k_msm_windows / k_msm_windows2 run it: (run, sum) per thread, suffix
         // scan of the runs across the CTA, position weights as doublings, tree sum
         const int T = MSM_WT;

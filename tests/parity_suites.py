@@ -337,7 +337,7 @@ def check_point_decompress(be, o, n=64):
     assert st[0] == 1 and out[0].tobytes().hex() == kats["g_uncompressed"]
 
 
-def check_msm(be, o, sizes=(0, 1, 2, 31, 32, 33, 64, 300), big=None):
+def check_msm(be, o, sizes=(0, 1, 2, 31, 32, 33, 64, 300), big=None, heavy=None):
     """point_mul_multi_test.go:14-70 (sizes 0, 1, 32, 64 vs sum of ScalarMult) and
     the closed form of config 5: sum s_i * (d_i G) == (sum s_i d_i mod n) G."""
     w = synth.msm_batch(max(sizes), oracle_base_mult(o))
@@ -381,6 +381,15 @@ def check_msm(be, o, sizes=(0, 1, 2, 31, 32, 33, 64, 300), big=None):
     got, st = be.msm(ks, w["pt65"][:ns])
     exp, est = o.msm(ks.tobytes(), w["pt65"][:ns].tobytes())
     assert (st, got.tobytes()) == (est, exp)
+    if heavy:
+        # one bucket per window holds every point (> 64 slices of 64: the super-slice level);
+        # k * sum P_i = (k * sum d_i mod n) * G
+        wh = synth.msm_batch(heavy, oracle_base_mult(o))
+        kv = 0x0123456789ABCDEF0FEDCBA987654321_1122334455667788_99AABBCCDDEEFF00
+        kh = np.tile(np.frombuffer(b32(kv), np.uint8), (heavy, 1))
+        got, st = be.msm(kh, wh["pt65"])
+        exp, est = o.scalar_base_mult(b32(kv * wh["key_sum"] % N))
+        assert st == est and got.tobytes() == exp
     if big:
         wb = synth.msm_batch(big, oracle_base_mult(o))
         got, st = be.msm(wb["k32"], wb["pt65"])

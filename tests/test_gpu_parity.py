@@ -68,7 +68,7 @@ def test_point_decompress(engine, oracle):
 
 
 def test_msm(engine, oracle):
-    ps.check_msm(engine, oracle, sizes=(0, 1, 2, 31, 32, 33, 64, 300, 1000, 4096), big=1 << 17)
+    ps.check_msm(engine, oracle, sizes=(0, 1, 2, 31, 32, 33, 64, 300, 1000, 4096), big=1 << 17, heavy=20000)
 
 
 def test_msm_sharded(engine, oracle):

@@ -90,7 +90,7 @@ def test_point_decompress(oracle):
 
 
 def test_msm(oracle):
-    ps.check_msm(be, oracle, sizes=(0, 1, 2, 31, 32, 33, 64, 200))
+    ps.check_msm(be, oracle, sizes=(0, 1, 2, 31, 32, 33, 64, 200), heavy=4500)
 
 
 def test_msm_window_sizes(oracle):
