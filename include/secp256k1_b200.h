@@ -53,6 +53,8 @@ typedef struct s256_ctx s256_ctx;
 #define S256_ST_IDENTITY 2  /* result is the point at infinity (output bytes zeroed);
                                the reference encodes it as the single byte 0x00
                                (point_s11n.go:75-77) or returns an error (XBytes, :123-125) */
+#define S256_ST_BAD_ALGORITHM 3 /* ParseASN1PublicKey: algorithm is not ecPublicKey (secec/s11n.go:31) */
+#define S256_ST_BAD_CURVE 4     /* ParseASN1PublicKey: named curve is not secp256k1 (secec/s11n.go:32) */
 
 /* flags */
 #define S256_FLAG_REJECT_MALLEABLE 1u /* ECDSAOptions.RejectMalleable, secec/ecdsa.go:72-75,212 */
@@ -118,7 +120,27 @@ int s256_ecdsa_verify_dev(s256_ctx *ctx, const uint8_t *d_pk65, const uint8_t *d
  *     (secec/bitcoin/asn1_shitcoin.go:13), rows INCLUDE the trailing sighash byte.
  *   s256_ecdsa_verify_asn1: PublicKey.Verify with EncodingASN1 (secec/ecdsa.go:171-228).
  *   s256_bitcoin_verify_asn1: bitcoin.VerifyASN1 (secec/bitcoin/ecdsa_shitcoin.go:29): BIP-66
- *     check, sighash byte stripped, s <= n/2 enforced. */
+ *     check, sighash byte stripped, s <= n/2 enforced.
+ *   s256_parse_asn1_public_keys: secec.ParseASN1PublicKey (secec/s11n.go:38-76) up to the call of
+ *     NewPublicKey: strict SubjectPublicKeyInfo with the ecPublicKey / secp256k1 OIDs; yields the
+ *     SEC 1 point bytes (row stride 65, left-aligned, point_len[i] in {1, 33, 65}) and a status
+ *     (S256_ST_OK / S256_ST_INVALID / S256_ST_BAD_ALGORITHM / S256_ST_BAD_CURVE).  Feed the rows
+ *     to s256_new_public_keys for the curve checks.
+ *   s256_build_asn1_public_keys: PublicKey.ASN1Bytes (secec/secec.go:109, s11n.go:190): 88 bytes.
+ *   s256_build_asn1_signatures: secec.BuildASN1Signature (secec/s11n.go:110): rows of stride 72,
+ *     out_len[i] bytes used. */
+int s256_parse_asn1_public_keys(const uint8_t *der, const size_t *offsets, size_t n, uint8_t *point65,
+                                uint8_t *point_len, uint8_t *status);
+int s256_build_asn1_public_keys(const uint8_t *pk65, size_t n, uint8_t *out88);
+/* secec.NewPublicKey (secec/secec.go:183-199) over rows of mixed SEC 1 encodings (stride 65, enc_len[i] in
+ * {1, 33, 65} bytes used): validated uncompressed bytes out; status S256_ST_OK / S256_ST_INVALID /
+ * S256_ST_IDENTITY (a valid encoding, but not a public key: errAIsInfinity). */
+int s256_new_public_keys(s256_ctx *ctx, const uint8_t *enc65, const uint8_t *enc_len, size_t n, uint8_t *out65,
+                         uint8_t *status);
+/* secec.ParseASN1PublicKey end to end: host SPKI parse, then s256_new_public_keys. */
+int s256_parse_asn1_public_keys_checked(s256_ctx *ctx, const uint8_t *der, const size_t *offsets, size_t n,
+                                        uint8_t *out65, uint8_t *status);
+int s256_build_asn1_signatures(const uint8_t *sig64, size_t n, uint8_t *out72, uint8_t *out_len);
 int s256_parse_asn1_signatures(const uint8_t *der, const size_t *offsets, size_t n, uint8_t *sig64, uint8_t *ok);
 int s256_is_valid_signature_encoding_bip0066(const uint8_t *der, const size_t *offsets, size_t n, uint8_t *ok);
 int s256_ecdsa_verify_asn1(s256_ctx *ctx, const uint8_t *pk65, const uint8_t *digest32, const uint8_t *der,

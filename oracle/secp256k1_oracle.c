@@ -1136,6 +1136,7 @@ EXPORT int orc_point_decode(const u8 *in, size_t len, u8 out65[65]) {
     orc_init();
     pt p;
     memset(out65, 0, 65);
+    if (len == 1) return in[0] == 0x00 ? ST_IDENTITY : ST_INVALID; /* point_s11n.go:211-217 */
     if (!decode_point(&p, in, len)) return ST_INVALID;
     return pt_uncompressed_bytes(out65, &p);
 }

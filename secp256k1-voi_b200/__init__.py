@@ -33,6 +33,8 @@ EXPORTED_SYMBOLS = [
     "s256_double_scalar_mult_basepoint_vartime", "s256_double_scalar_mult_basepoint_vartime_dev",
     "s256_ecdsa_verify", "s256_ecdsa_verify_dev",
     "s256_parse_asn1_signatures", "s256_is_valid_signature_encoding_bip0066",
+    "s256_parse_asn1_public_keys", "s256_build_asn1_public_keys", "s256_build_asn1_signatures",
+    "s256_new_public_keys", "s256_parse_asn1_public_keys_checked",
     "s256_ecdsa_verify_asn1", "s256_bitcoin_verify_asn1",
     "s256_ecdsa_recover", "s256_ecdsa_recover_dev",
     "s256_ecdsa_sign_rfc6979", "s256_ecdsa_sign_rfc6979_dev",
@@ -105,6 +107,47 @@ def parse_asn1_signatures(rows):
     if rc != 0:
         raise S256Error(f"parse_asn1_signatures rc={rc}")
     return sig, ok
+
+
+def parse_asn1_public_keys(rows):
+    """secec.ParseASN1PublicKey up to NewPublicKey, over a list of DER SubjectPublicKeyInfo blobs ->
+    (point rows of stride 65, point_len, status).  Host-side, no GPU needed; feed Engine.new_public_keys."""
+    lib = load_library()
+    data, offs = _pack_rows(rows)
+    n = len(rows)
+    pts = np.zeros((n, 65), np.uint8)
+    ln = np.zeros(n, np.uint8)
+    st = np.zeros(n, np.uint8)
+    rc = lib.s256_parse_asn1_public_keys(data.ctypes.data_as(C.c_void_p), offs.ctypes.data_as(C.c_void_p), C.c_size_t(n),
+                                         pts.ctypes.data_as(C.c_void_p), ln.ctypes.data_as(C.c_void_p),
+                                         st.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise S256Error(f"parse_asn1_public_keys rc={rc}")
+    return pts, ln, st
+
+
+def build_asn1_public_keys(pk65):
+    """PublicKey.ASN1Bytes over validated uncompressed keys -> (n, 88) rows."""
+    lib = load_library()
+    p = _host(pk65, 65)
+    out = np.zeros((len(p), 88), np.uint8)
+    rc = lib.s256_build_asn1_public_keys(p.ctypes.data_as(C.c_void_p), C.c_size_t(len(p)), out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise S256Error(f"build_asn1_public_keys rc={rc}")
+    return out
+
+
+def build_asn1_signatures(sig64):
+    """secec.BuildASN1Signature over compact r||s rows -> list of DER byte strings."""
+    lib = load_library()
+    g = _host(sig64, 64)
+    out = np.zeros((len(g), 72), np.uint8)
+    ln = np.zeros(len(g), np.uint8)
+    rc = lib.s256_build_asn1_signatures(g.ctypes.data_as(C.c_void_p), C.c_size_t(len(g)), out.ctypes.data_as(C.c_void_p),
+                                        ln.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise S256Error(f"build_asn1_signatures rc={rc}")
+    return [out[i, :ln[i]].tobytes() for i in range(len(g))]
 
 
 def is_valid_signature_encoding_bip0066(rows):
@@ -253,6 +296,34 @@ class Engine:
         st = np.zeros(n, np.uint8)
         self._check(self._lib.s256_point_decompress(self._ctx, self._hp(p), C.c_size_t(n), self._hp(out), self._hp(st)),
                     "point_decompress")
+        return out, st
+
+    # -- secec.NewPublicKey / ParseASN1PublicKey (secec/secec.go:183, secec/s11n.go:38) ----
+    def new_public_keys(self, enc, enc_len=None):
+        """Rows of SEC 1 encodings: a list of byte strings of mixed length, or (stride-65 rows, lengths)."""
+        if enc_len is None:
+            rows = [bytes(r) for r in enc]
+            enc_len = np.array([len(r) if len(r) <= 65 else 0 for r in rows], np.uint8)
+            enc = np.zeros((len(rows), 65), np.uint8)
+            for i, r in enumerate(rows):
+                if len(r) <= 65:
+                    enc[i, :len(r)] = np.frombuffer(r, np.uint8)
+        e, ln = _host(enc, 65), _host(enc_len, 0).reshape(-1)
+        n = len(e)
+        out = np.zeros((n, 65), np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_new_public_keys(self._ctx, self._hp(e), self._hp(ln), C.c_size_t(n), self._hp(out),
+                                                   self._hp(st)), "new_public_keys")
+        return out, st
+
+    def parse_asn1_public_keys(self, rows):
+        data, offs = _pack_rows(rows)
+        n = len(rows)
+        out = np.zeros((n, 65), np.uint8)
+        st = np.zeros(n, np.uint8)
+        self._check(self._lib.s256_parse_asn1_public_keys_checked(self._ctx, self._hp(data), offs.ctypes.data_as(C.c_void_p),
+                                                                  C.c_size_t(n), self._hp(out), self._hp(st)),
+                    "parse_asn1_public_keys")
         return out, st
 
     # -- Point.DoubleScalarMultBasepointVartime (point_mul_glv.go:307) --------

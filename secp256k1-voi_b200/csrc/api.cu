@@ -44,7 +44,28 @@ __global__ void __launch_bounds__(S256_TPB) k_decode_compressed(const uint8_t *p
     pvalid[i] = item_decode_compressed(a, pt33 + 33 * i);
     aff[i] = a;
 }
-// affine (validated) -> 65-byte encoding; invalid -> zeros
+// secec.NewPublicKey (secec/secec.go:183-199) over rows of mixed SEC 1 encodings (stride 65, len[i] bytes
+// used): Point.SetBytes (point_s11n.go:209-228) dispatches on the length; the identity encoding is a
+// valid point but not a public key (errAIsInfinity).  pvalid: 1 ok, 0 invalid, 2 identity.
+__global__ void __launch_bounds__(S256_TPB) k_decode_sec1(const uint8_t *enc65, const uint8_t *len, size_t n, apt *aff,
+                                                          uint8_t *pvalid) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t *e = enc65 + 65 * i;
+    apt a;
+    a.x = fe_zero();
+    a.y = fe_zero();
+    uint8_t st = ST_INVALID;
+    if (len[i] == 65)
+        st = item_decode_uncompressed(a, e) ? ST_OK : ST_INVALID;
+    else if (len[i] == 33)
+        st = item_decode_compressed(a, e) ? ST_OK : ST_INVALID;
+    else if (len[i] == 1 && e[0] == 0x00)
+        st = ST_IDENTITY;
+    pvalid[i] = st;
+    aff[i] = a;
+}
+// affine (validated) -> 65-byte encoding; invalid -> zeros, status = the decoder's code
 __global__ void __launch_bounds__(S256_TPB) k_encode_affine(const apt *aff, const uint8_t *pvalid, size_t n,
                                                             uint8_t *out65, uint8_t *status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,6 +81,21 @@ __global__ void __launch_bounds__(S256_TPB) k_encode_affine(const apt *aff, cons
         for (int b = 0; b < 65; b++) o[b] = 0;
     }
     status[i] = ok ? ST_OK : ST_INVALID;
+}
+__global__ void __launch_bounds__(S256_TPB) k_encode_public_key(const apt *aff, const uint8_t *pvalid, size_t n,
+                                                                uint8_t *out65, uint8_t *status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    apt a = aff[i];
+    uint8_t *o = out65 + 65 * i;
+    if (pvalid[i] == ST_OK) {
+        o[0] = 0x04;
+        fe_to_be32(o + 1, a.x);
+        fe_to_be32(o + 33, a.y);
+    } else {
+        for (int b = 0; b < 65; b++) o[b] = 0;
+    }
+    status[i] = pvalid[i];
 }
 
 // BIP-340 lift_x: x-only key, even y (secec/bitcoin/schnorr.go:257-275)
@@ -625,6 +661,41 @@ extern "C" int s256_point_decompress(s256_ctx *ctx, const uint8_t *pt33, size_t 
         return S256_SUCCESS;
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+// secec.NewPublicKey over mixed SEC 1 encodings -> the uncompressed bytes PublicKey caches (secec/secec.go:84)
+extern "C" int s256_new_public_keys(s256_ctx *ctx, const uint8_t *enc65, const uint8_t *enc_len, size_t n, uint8_t *out65,
+                                    uint8_t *status) {
+    ENTER(ctx);
+    if (n && (!enc65 || !enc_len || !out65 || !status)) return S256_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        CK(cudaMemcpyAsync(ctx->in_a, enc65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->in_b, enc_len + off, c, cudaMemcpyHostToDevice, s));
+        LAUNCH(ctx, k_decode_sec1, grid_for(c), 0, s, ctx->in_a, ctx->in_b, c, ctx->aff, ctx->pvalid);
+        LAUNCH(ctx, k_encode_public_key, grid_for(c), 0, s, ctx->aff, ctx->pvalid, c, ctx->out, ctx->st);
+        CK(cudaMemcpyAsync(out65 + 65 * off, ctx->out, 65 * c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return S256_SUCCESS;
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+// secec.ParseASN1PublicKey (secec/s11n.go:38-76): SubjectPublicKeyInfo on the host (codecs.cpp), NewPublicKey
+// on the device.  status: the parser's code, else the decoder's.
+extern "C" int s256_parse_asn1_public_keys_checked(s256_ctx *ctx, const uint8_t *der, const size_t *offsets, size_t n,
+                                                   uint8_t *out65, uint8_t *status) {
+    if (!ctx || (n && (!der || !offsets || !out65 || !status))) return S256_ERR_ARG;
+    std::vector<uint8_t> enc(65 * n), len(n), pst(n);
+    int rc = s256_parse_asn1_public_keys(der, offsets, n, enc.data(), len.data(), pst.data());
+    if (rc != S256_SUCCESS) return rc;
+    rc = s256_new_public_keys(ctx, enc.data(), len.data(), n, out65, status);
+    if (rc != S256_SUCCESS) return rc;
+    for (size_t i = 0; i < n; i++)
+        if (pst[i] != S256_ST_OK) {
+            status[i] = pst[i];
+            memset(out65 + 65 * i, 0, 65);
+        }
+    return S256_SUCCESS;
 }
 
 // PublicKey.Verify with EncodingASN1 (secec/ecdsa.go:171-228): parse on the host (codecs.cpp), then the

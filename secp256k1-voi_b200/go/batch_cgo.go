@@ -208,6 +208,53 @@ func (e *Engine) ECDHBatch(k32, pt65 []byte) (x32 []byte, status []byte, err err
 	return
 }
 
+// packRows concatenates variable-length rows and returns the n + 1 offsets the C ABI expects.
+func packRows(rows [][]byte) ([]byte, []C.size_t) {
+	offs := make([]C.size_t, len(rows)+1)
+	var data []byte
+	for i, r := range rows {
+		data = append(data, r...)
+		offs[i+1] = C.size_t(len(data))
+	}
+	if len(data) == 0 {
+		data = []byte{0}
+	}
+	return data, offs
+}
+
+// ParseASN1PublicKeyBatch is secec.ParseASN1PublicKey over DER SubjectPublicKeyInfo blobs: the strict
+// SPKI parse runs on the host, NewPublicKey's curve checks on the GPU.  status[i] is S256_ST_OK or the
+// reason (invalid / not ecPublicKey / not secp256k1 / identity); accepted rows hold the 65-byte key.
+func (e *Engine) ParseASN1PublicKeyBatch(der [][]byte) (pk65 []byte, status []byte, err error) {
+	n := len(der)
+	data, offs := packRows(der)
+	pk65, status = make([]byte, 65*n), make([]byte, n)
+	err = e.err(C.s256_parse_asn1_public_keys_checked(e.ctx, ptr(data), &offs[0], C.size_t(n), ptr(pk65), ptr(status)))
+	return
+}
+
+// VerifyASN1Batch is secec.PublicKey.Verify with EncodingASN1 (the default encoding) over n rows.
+func (e *Engine) VerifyASN1Batch(pk65, digest32 []byte, sigs [][]byte, opts *secec.ECDSAOptions) ([]bool, error) {
+	n := len(sigs)
+	if len(pk65) != 65*n || len(digest32) != 32*n {
+		panic("secp256k1b200: VerifyASN1Batch: length mismatch")
+	}
+	var flags C.uint32_t
+	if opts != nil && opts.RejectMalleable {
+		flags = C.S256_FLAG_REJECT_MALLEABLE
+	}
+	data, offs := packRows(sigs)
+	ok := make([]byte, n)
+	if err := e.err(C.s256_ecdsa_verify_asn1(e.ctx, ptr(pk65), ptr(digest32), ptr(data), &offs[0], flags, C.size_t(n), ptr(ok))); err != nil {
+		return nil, err
+	}
+	res := make([]bool, n)
+	for i, b := range ok {
+		res[i] = b == 1
+	}
+	return res, nil
+}
+
 var errInvalid = errors.New("secp256k1b200: invalid input row")
 
 // decodePoints rebuilds reference Points from the engine's rows; the identity comes back as the

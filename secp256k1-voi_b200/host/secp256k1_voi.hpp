@@ -5,8 +5,10 @@
 // argument meaning and error behaviour as the Go packages it mirrors:
 //   secp256k1.Scalar  (scalar.go:52-261)      -> secp256k1::Scalar
 //   secp256k1.Point   (point.go:42-224, point_s11n.go, point_mul_*.go) -> secp256k1::Point
-//   secec.PublicKey.Verify / RecoverPublicKey / PrivateKey.ECDH (secec/ecdsa.go, secec.go)
-//   bitcoin.SchnorrPublicKey.Verify (secec/bitcoin/schnorr.go:221)
+//   secec.PublicKey.Verify (all three encodings) / RecoverPublicKey / PrivateKey.ECDH / PrivateKey.Sign with
+//   RFC6979SHA256() / ParseASN1PublicKey / ASN1Bytes / Parse- and BuildASN1Signature (secec/*.go)
+//   bitcoin.SchnorrPublicKey.Verify, SchnorrPrivateKey.Sign, VerifyASN1 (secec/bitcoin/*.go)
+//   h2c.Secp256k1_XMD_SHA256_SSWU_RO / _NU (secec/h2c/h2c.go)
 // plus the batch entry points the engine adds (…Batch).  Single-item methods are
 // batches of one: correct, but the GPU only pays off on the batch forms.
 // Misuse that panics in Go throws std::logic_error; data errors that return
@@ -294,10 +296,33 @@ inline void DoubleScalarMultBasepointVartimeBatch(const uint8_t *u1, const uint8
 
 namespace secec {
 
-struct ECDSAOptions {  // secec/ecdsa.go:55-75 (EncodingCompact path)
+// secec/ecdsa.go:38-50
+enum SignatureEncoding { EncodingASN1 = 0, EncodingCompact = 1, EncodingCompactRecoverable = 2 };
+// secec/ecdsa.go:52-77.  Go's `Hash crypto.Hash` only validates the digest length; here it is that length
+// in bytes (0: SHA-256, 32).
+struct ECDSAOptions {
+    size_t HashSize = 0;
+    SignatureEncoding Encoding = EncodingASN1;
+    bool SelfVerify = false;
     bool RejectMalleable = false;
 };
 constexpr size_t CompactSignatureSize = 64, CompactRecoverableSignatureSize = 65;
+
+// secec/s11n.go:83 ParseASN1Signature: strict DER SEQUENCE { r, s }, both in [1, n) -> r || s
+inline std::array<uint8_t, 64> ParseASN1Signature(const uint8_t *data, size_t len) {
+    std::array<uint8_t, 64> sig{};
+    size_t offs[2] = {0, len};
+    uint8_t ok = 0, dummy = 0;
+    if (s256_parse_asn1_signatures(len ? data : &dummy, offs, 1, sig.data(), &ok) != S256_SUCCESS || !ok)
+        throw Error("secp256k1/secec: invalid ASN.1 signature");
+    return sig;
+}
+// secec/s11n.go:112 BuildASN1Signature
+inline std::vector<uint8_t> BuildASN1Signature(const uint8_t sig64[64]) {
+    uint8_t out[72], n = 0;
+    if (s256_build_asn1_signatures(sig64, 1, out, &n) != S256_SUCCESS) throw Error("BuildASN1Signature");
+    return std::vector<uint8_t>(out, out + n);
+}
 
 class PublicKey {
   public:
@@ -309,23 +334,128 @@ class PublicKey {
         k.point_ = p;
         return k;
     }
+    // secec/s11n.go:45 ParseASN1PublicKey: SubjectPublicKeyInfo, named curve only
+    static PublicKey ParseASN1PublicKey(const uint8_t *data, size_t len, Engine &e = Engine::Default()) {
+        size_t offs[2] = {0, len};
+        uint8_t pt[65], plen = 0, st = 0, dummy = 0;
+        if (s256_parse_asn1_public_keys(len ? data : &dummy, offs, 1, pt, &plen, &st) != S256_SUCCESS)
+            throw Error("ParseASN1PublicKey");
+        if (st == S256_ST_BAD_ALGORITHM) throw Error("secp256k1/secec: algorithm is not ecPublicKey");
+        if (st == S256_ST_BAD_CURVE) throw Error("secp256k1/secec: named curve is not secp256k1");
+        if (st != S256_ST_OK) throw Error("secp256k1/secec: invalid ASN.1 Subject Public Key Info");
+        return NewPublicKey(pt, plen, e);
+    }
     const Point &point() const { return point_; }
     std::vector<uint8_t> Bytes() const { return point_.UncompressedBytes(); }
-    // secec/ecdsa.go:171 Verify, compact r||s encoding; digest: leftmost 32 bytes are used (ecdsa.go:477)
+    // secec/secec.go:109 ASN1Bytes
+    std::vector<uint8_t> ASN1Bytes() const {
+        std::vector<uint8_t> out(88);
+        if (s256_build_asn1_public_keys(point_.raw().data(), 1, out.data()) != S256_SUCCESS) throw Error("ASN1Bytes");
+        return out;
+    }
+    // secec/ecdsa.go:171 Verify.  opts == nullptr: EncodingASN1, any s in [1, n), digest of any length >= 32
+    // (the leftmost 32 bytes are used, ecdsa.go:477).
     bool Verify(const uint8_t *digest, size_t digest_len, const uint8_t *sig, size_t sig_len, const ECDSAOptions *opts = nullptr,
                 Engine &e = Engine::Default()) const {
-        if (digest_len < 32 || sig_len != CompactSignatureSize) return false;
-        uint8_t ok = 0;
-        e.check(s256_ecdsa_verify(e.ctx(), point_.raw().data(), digest, sig,
-                                  (opts && opts->RejectMalleable) ? S256_FLAG_REJECT_MALLEABLE : 0u, 1, &ok),
-                "Verify");
-        return ok == 1;
+        SignatureEncoding enc = EncodingASN1;
+        uint32_t flags = 0;
+        if (opts) {
+            enc = opts->Encoding;
+            if (opts->RejectMalleable) flags = S256_FLAG_REJECT_MALLEABLE;
+            if (digest_len != (opts->HashSize ? opts->HashSize : 32)) return false;
+        }
+        if (digest_len < 32) return false;
+        uint8_t ok = 0, dummy = 0;
+        switch (enc) {
+        case EncodingASN1: {
+            size_t offs[2] = {0, sig_len};
+            e.check(s256_ecdsa_verify_asn1(e.ctx(), point_.raw().data(), digest, sig_len ? sig : &dummy, offs, flags, 1, &ok),
+                    "Verify");
+            return ok == 1;
+        }
+        case EncodingCompact:
+            if (sig_len != CompactSignatureSize) return false;
+            e.check(s256_ecdsa_verify(e.ctx(), point_.raw().data(), digest, sig, flags, 1, &ok), "Verify");
+            return ok == 1;
+        case EncodingCompactRecoverable: {
+            // ecdsa.go:221-227: recover with (r, s, v) and compare keys
+            if (sig_len != CompactRecoverableSignatureSize) return false;
+            if (flags && Scalar::NewScalarFromBytes(sig + 32).IsGreaterThanHalfN()) return false;
+            uint8_t pk[65], st = 0;
+            e.check(s256_ecdsa_recover(e.ctx(), digest, sig, 1, pk, &st), "Verify");
+            return st == S256_ST_OK && std::memcmp(pk, point_.raw().data(), 65) == 0;
+        }
+        }
+        return false;  // errInvalidEncoding
     }
     bool Equal(const PublicKey &o) const { return point_.Equal(o.point_); }
 
   private:
     Point point_;
 };
+
+// secec/secec.go:149 NewPrivateKey + Sign with RFC6979SHA256() as the entropy source (secec/ecdsa.go:92,
+// ecdsa_k_rfc6979.go:38).  The engine implements the deterministic path only; randomised nonces with the
+// reference's TupleHash hardening stay on the host library.
+class PrivateKey {
+  public:
+    static PrivateKey NewPrivateKey(const uint8_t *key, size_t len, Engine &e = Engine::Default()) {
+        if (len != ScalarSize) throw Error("secp256k1/secec: invalid private key");
+        if (std::memcmp(key, detail::N_BE, 32) >= 0) throw Error("secp256k1/secec: invalid private key");
+        uint8_t acc = 0;
+        for (size_t i = 0; i < 32; i++) acc |= key[i];
+        if (!acc) throw Error("secp256k1/secec: invalid private key");
+        PrivateKey k;
+        std::memcpy(k.d_.data(), key, 32);
+        uint8_t pk[65], st = 0;
+        e.check(s256_scalar_base_mult(e.ctx(), key, 1, pk, &st), "NewPrivateKey");
+        k.pub_ = PublicKey::NewPublicKey(pk, 65, e);
+        return k;
+    }
+    const std::array<uint8_t, 32> &Bytes() const { return d_; }
+    const PublicKey &PublicKeyRef() const { return pub_; }
+    // Sign(RFC6979SHA256(), digest, opts): opts == nullptr -> EncodingASN1, digest of any length >= 32
+    std::vector<uint8_t> Sign(const uint8_t *digest, size_t digest_len, const ECDSAOptions *opts = nullptr,
+                              Engine &e = Engine::Default()) const {
+        SignatureEncoding enc = opts ? opts->Encoding : EncodingASN1;
+        if (opts && digest_len != (opts->HashSize ? opts->HashSize : 32)) throw Error("secp256k1/secec: invalid digest");
+        if (digest_len < 32) throw Error("secp256k1/secec: invalid digest");
+        uint8_t sig[65], st = 0;
+        e.check(s256_ecdsa_sign_rfc6979(e.ctx(), d_.data(), digest, 1, sig, sig + 64, &st), "Sign");
+        if (st != S256_ST_OK) throw Error("secp256k1/secec: signing failed");
+        if (opts && opts->SelfVerify) {
+            ECDSAOptions v;
+            v.Encoding = EncodingCompact;
+            v.HashSize = digest_len;
+            if (!pub_.Verify(digest, digest_len, sig, 64, &v, e) || (sig[64] & 3) != sig[64])
+                throw Error("secp256k1/secec: failed to verify freshly generated signature");
+        }
+        switch (enc) {
+        case EncodingASN1: return BuildASN1Signature(sig);
+        case EncodingCompact: return std::vector<uint8_t>(sig, sig + 64);
+        case EncodingCompactRecoverable: return std::vector<uint8_t>(sig, sig + 65);
+        }
+        throw Error("secp256k1/secec: invalid signature encoding");
+    }
+
+  private:
+    std::array<uint8_t, 32> d_{};
+    PublicKey pub_;
+};
+// batch forms of the above
+inline void SignRFC6979Batch(const uint8_t *priv32, const uint8_t *digest32, size_t n, uint8_t *sig64, uint8_t *recid,
+                             uint8_t *status, Engine &e = Engine::Default()) {
+    e.check(s256_ecdsa_sign_rfc6979(e.ctx(), priv32, digest32, n, sig64, recid, status), "SignRFC6979Batch");
+}
+inline void VerifyASN1Batch(const uint8_t *pk65, const uint8_t *digest32, const uint8_t *der, const size_t *offsets, size_t n,
+                            bool reject_malleable, uint8_t *ok, Engine &e = Engine::Default()) {
+    e.check(s256_ecdsa_verify_asn1(e.ctx(), pk65, digest32, der, offsets, reject_malleable ? S256_FLAG_REJECT_MALLEABLE : 0u, n, ok),
+            "VerifyASN1Batch");
+}
+inline void ParseASN1PublicKeyBatch(const uint8_t *der, const size_t *offsets, size_t n, uint8_t *pk65, uint8_t *status,
+                                    Engine &e = Engine::Default()) {
+    e.check(s256_parse_asn1_public_keys_checked(e.ctx(), der, offsets, n, pk65, status), "ParseASN1PublicKeyBatch");
+}
 
 // secec/ecdsa.go:244 RecoverPublicKey on r || s || v
 inline PublicKey RecoverPublicKey(const uint8_t digest32[32], const uint8_t sig65[65], Engine &e = Engine::Default()) {
@@ -383,10 +513,69 @@ class SchnorrPublicKey {
   private:
     std::array<uint8_t, 32> x_{};
 };
+// secec/bitcoin/ecdsa_shitcoin.go:29 VerifyASN1: BIP-66 syntax, trailing sighash byte, s <= n/2
+inline bool VerifyASN1(const PublicKey &k, const uint8_t *digest, size_t digest_len, const uint8_t *sig, size_t sig_len,
+                       Engine &e = Engine::Default()) {
+    if (digest_len != 32) return false;
+    size_t offs[2] = {0, sig_len};
+    uint8_t ok = 0, dummy = 0;
+    e.check(s256_bitcoin_verify_asn1(e.ctx(), k.point().raw().data(), digest, sig_len ? sig : &dummy, offs, 1, &ok), "VerifyASN1");
+    return ok == 1;
+}
+// secec/bitcoin/asn1_shitcoin.go:13
+inline bool IsValidSignatureEncodingBIP0066(const uint8_t *data, size_t len) {
+    size_t offs[2] = {0, len};
+    uint8_t ok = 0, dummy = 0;
+    return s256_is_valid_signature_encoding_bip0066(len ? data : &dummy, offs, 1, &ok) == S256_SUCCESS && ok == 1;
+}
+// secec/bitcoin/schnorr.go:140 NewSchnorrPrivateKey + :111 Sign with caller-supplied auxiliary randomness
+class SchnorrPrivateKey {
+  public:
+    static SchnorrPrivateKey NewSchnorrPrivateKey(const uint8_t *key, size_t len) {
+        if (len != ScalarSize || std::memcmp(key, detail::N_BE, 32) >= 0) throw Error("secp256k1/secec/bitcoin: invalid private key");
+        uint8_t acc = 0;
+        for (size_t i = 0; i < 32; i++) acc |= key[i];
+        if (!acc) throw Error("secp256k1/secec/bitcoin: invalid private key");
+        SchnorrPrivateKey k;
+        std::memcpy(k.d_.data(), key, 32);
+        return k;
+    }
+    std::array<uint8_t, 64> Sign(const uint8_t aux32[32], const uint8_t *msg, size_t msg_len, Engine &e = Engine::Default()) const {
+        std::array<uint8_t, 64> sig{};
+        uint8_t st = 0, dummy = 0;
+        e.check(s256_schnorr_sign(e.ctx(), d_.data(), msg_len ? msg : &dummy, msg_len, aux32, 1, sig.data(), &st), "SchnorrPrivateKey.Sign");
+        if (st != S256_ST_OK) throw Error("secp256k1/secec/bitcoin: signing failed");
+        return sig;
+    }
+
+  private:
+    std::array<uint8_t, 32> d_{};
+};
 inline void SchnorrVerifyBatch(const uint8_t *pkx32, const uint8_t *msg, size_t msg_len, const uint8_t *sig64, size_t n,
                                uint8_t *ok, Engine &e = Engine::Default()) {
     e.check(s256_schnorr_verify(e.ctx(), pkx32, msg, msg_len, sig64, n, ok), "SchnorrVerifyBatch");
 }
 }  // namespace bitcoin
+
+namespace h2c {
+// secec/h2c/h2c.go:25,49: RFC 9380 secp256k1_XMD:SHA-256_SSWU_RO_ / _NU_
+inline Point Secp256k1_XMD_SHA256_SSWU(bool random_oracle, const uint8_t *dst, size_t dst_len, const uint8_t *msg, size_t msg_len,
+                                       Engine &e) {
+    if (dst_len == 0) throw Error("secp256k1/secec/h2c: invalid domain separator");
+    uint8_t out[65], st = 0, dummy = 0;
+    e.check(s256_hash_to_curve(e.ctx(), dst, dst_len, msg_len ? msg : &dummy, msg_len, 1, random_oracle ? 1 : 0, out, &st),
+            "hash_to_curve");
+    if (st == S256_ST_IDENTITY) return Point::NewIdentityPoint();
+    return Point::NewPointFromBytes(out, 65, e);
+}
+inline Point Secp256k1_XMD_SHA256_SSWU_RO(const uint8_t *dst, size_t dst_len, const uint8_t *msg, size_t msg_len,
+                                          Engine &e = Engine::Default()) {
+    return Secp256k1_XMD_SHA256_SSWU(true, dst, dst_len, msg, msg_len, e);
+}
+inline Point Secp256k1_XMD_SHA256_SSWU_NU(const uint8_t *dst, size_t dst_len, const uint8_t *msg, size_t msg_len,
+                                          Engine &e = Engine::Default()) {
+    return Secp256k1_XMD_SHA256_SSWU(false, dst, dst_len, msg, msg_len, e);
+}
+}  // namespace h2c
 }  // namespace secec
 }  // namespace secp256k1

@@ -23,7 +23,7 @@ static std::vector<uint8_t> unhex(const std::string &h) {
     } while (0)
 
 int main(int argc, char **argv) {
-    if (argc < 8) return 2;
+    if (argc < 16) return 2;
     auto gU = unhex(argv[1]), gC = unhex(argv[2]), a = unhex(argv[3]), xn = unhex(argv[4]), b = unhex(argv[5]);
     auto bipPk = unhex(argv[6]), bipSig = unhex(argv[7]);
     // G round trips (point_test.go:38-57)
@@ -76,6 +76,63 @@ int main(int argc, char **argv) {
     auto pkA = secec::PublicKey::NewPublicKey(A.UncompressedBytes().data(), 65);
     auto pkB = secec::PublicKey::NewPublicKey(B.UncompressedBytes().data(), 65);
     REQUIRE(secec::ECDH(ka, pkB) == secec::ECDH(kb, pkA));
+    // Sign with RFC6979SHA256() (secec/ecdsa_k_test.go:244-278 row 0) in the three encodings, then Verify
+    auto sPriv = unhex(argv[8]), sDigest = unhex(argv[9]), sRS = unhex(argv[10]);
+    auto sk = secec::PrivateKey::NewPrivateKey(sPriv.data(), sPriv.size());
+    secec::ECDSAOptions compact, recoverable, selfv;
+    compact.Encoding = secec::EncodingCompact;
+    recoverable.Encoding = secec::EncodingCompactRecoverable;
+    selfv.SelfVerify = true;
+    auto sigC = sk.Sign(sDigest.data(), sDigest.size(), &compact);
+    REQUIRE(sigC == sRS);
+    auto sigA = sk.Sign(sDigest.data(), sDigest.size());  // opts == nil -> ASN.1
+    REQUIRE(sigA == secec::BuildASN1Signature(sRS.data()));
+    REQUIRE(sk.Sign(sDigest.data(), sDigest.size(), &selfv) == sigA);
+    auto back = secec::ParseASN1Signature(sigA.data(), sigA.size());
+    REQUIRE(std::vector<uint8_t>(back.begin(), back.end()) == sRS);
+    auto sigR = sk.Sign(sDigest.data(), sDigest.size(), &recoverable);
+    REQUIRE(sigR.size() == 65 && sigR[64] < 4);
+    const auto &vk = sk.PublicKeyRef();
+    REQUIRE(vk.Verify(sDigest.data(), sDigest.size(), sigA.data(), sigA.size()));
+    REQUIRE(vk.Verify(sDigest.data(), sDigest.size(), sigC.data(), sigC.size(), &compact));
+    REQUIRE(vk.Verify(sDigest.data(), sDigest.size(), sigR.data(), sigR.size(), &recoverable));
+    REQUIRE(!vk.Verify(sDigest.data(), sDigest.size(), sigC.data(), sigC.size()));       // compact bytes are not DER
+    REQUIRE(!vk.Verify(sDigest.data(), sDigest.size() - 1, sigC.data(), sigC.size(), &compact));  // digest length
+    sigR[64] ^= 1;
+    REQUIRE(!vk.Verify(sDigest.data(), sDigest.size(), sigR.data(), sigR.size(), &recoverable));
+    REQUIRE(secec::RecoverPublicKey(sDigest.data(), sk.Sign(sDigest.data(), 32, &recoverable).data()).Equal(vk));
+    threw = false;
+    try { secec::ParseASN1Signature(sigC.data(), sigC.size()); } catch (const Error &) { threw = true; }
+    REQUIRE(threw);
+    // bitcoin.VerifyASN1: BIP-66 + sighash byte + low s (the signer already normalises s)
+    auto withHash = sigA;
+    withHash.push_back(0x01);
+    REQUIRE(secec::bitcoin::IsValidSignatureEncodingBIP0066(withHash.data(), withHash.size()));
+    REQUIRE(secec::bitcoin::VerifyASN1(vk, sDigest.data(), 32, withHash.data(), withHash.size()));
+    REQUIRE(!secec::bitcoin::VerifyASN1(vk, sDigest.data(), 32, sigA.data(), sigA.size()));
+    // ParseASN1PublicKey <-> ASN1Bytes (secec/wycheproof_test.go:245-254)
+    auto spki = vk.ASN1Bytes();
+    REQUIRE(spki.size() == 88);
+    REQUIRE(secec::PublicKey::ParseASN1PublicKey(spki.data(), spki.size()).Equal(vk));
+    spki[10] ^= 1;  // inside the ecPublicKey OID
+    threw = false;
+    try { secec::PublicKey::ParseASN1PublicKey(spki.data(), spki.size()); } catch (const Error &) { threw = true; }
+    REQUIRE(threw);
+    // BIP-340 signing, row 0 (schnorr_test.go:149-246)
+    auto bSk = unhex(argv[11]), bAux = unhex(argv[12]);
+    auto ssk = secec::bitcoin::SchnorrPrivateKey::NewSchnorrPrivateKey(bSk.data(), bSk.size());
+    bipSig[40] ^= 1;
+    auto ssig = ssk.Sign(bAux.data(), msg, 32);
+    REQUIRE(std::vector<uint8_t>(ssig.begin(), ssig.end()) == bipSig);
+    // RFC 9380 vector "abc" (secec/h2c/h2c_test.go)
+    std::string dst = argv[13], hmsg = argv[14];
+    auto hXY = unhex(argv[15]);
+    Point hp = secec::h2c::Secp256k1_XMD_SHA256_SSWU_RO((const uint8_t *)dst.data(), dst.size(), (const uint8_t *)hmsg.data(), hmsg.size());
+    auto hb = hp.UncompressedBytes();
+    REQUIRE(hb.size() == 65 && std::vector<uint8_t>(hb.begin() + 1, hb.end()) == hXY);
+    threw = false;
+    try { secec::h2c::Secp256k1_XMD_SHA256_SSWU_NU(nullptr, 0, (const uint8_t *)hmsg.data(), hmsg.size()); } catch (const Error &) { threw = true; }
+    REQUIRE(threw);
     printf("host mirror ok\n");
     return 0;
 }

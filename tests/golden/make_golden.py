@@ -163,6 +163,35 @@ def wycheproof_ecdh():
     return cases
 
 
+DH_FLAGS_BAD_PUBLIC = {"InvalidCompressedPublic", "InvalidCurveAttack", "InvalidEncoding", "InvalidPublic",
+                       "WrongCurve", "UnnamedCurve", "InvalidAsn"}   # secec/wycheproof_test.go:42-53
+DH_FLAGS_COMPRESSED = {"CompressedPublic", "CompressedPoint"}        # :55-58
+
+
+def wycheproof_ecdh_spki():
+    """EVERY case of ecdh_secp256k1_test.json with its raw DER SubjectPublicKeyInfo, and the verdict the
+    reference's own harness requires of ParseASN1PublicKey (secec/wycheproof_test.go:212-253): a case with
+    an empty shared secret or a bad-public flag must be rejected; every other case must parse (and, unless
+    compressed, PublicKey.ASN1Bytes must reproduce the input byte for byte, :251-254)."""
+    doc = json.load(open(f"{REF}/secec/testdata/wycheproof/ecdh_secp256k1_test.json"))
+    cases = []
+    for g in doc["testGroups"]:
+        assert g["encoding"] == "asn" and g["curve"] == "secp256k1"
+        for tc in g["tests"]:
+            bad = tc["shared"] == "" or any(f in DH_FLAGS_BAD_PUBLIC for f in tc["flags"])
+            compressed = any(f in DH_FLAGS_COMPRESSED for f in tc["flags"])
+            must_fail = tc["result"] != "valid"
+            if tc["tcId"] == 2 and tc["result"] == "acceptable" and compressed:
+                must_fail = False
+            # the harness asserts !mustFail for every case that parses (:283)
+            assert bad or not must_fail, tc["tcId"]
+            priv = int(tc["private"], 16)
+            cases.append({"tcId": tc["tcId"], "flags": tc["flags"], "public": tc["public"], "must_parse": not bad,
+                          "compressed": compressed, "priv": (priv % (1 << 256)).to_bytes(32, "big").hex() if not bad else "",
+                          "shared": tc["shared"] if not bad else ""})
+    return cases
+
+
 def bip340():
     rows = []
     with open(f"{REF}/secec/bitcoin/testdata/bip-0340-test-vectors.csv") as f:
@@ -263,6 +292,11 @@ def main():
     json.dump({"provenance": "secec/testdata/wycheproof/ecdh_secp256k1{,_webcrypto}_test.json (Wycheproof v0.9rc5, Apache-2.0)",
                "cases": ecdh}, open(f"{OUT}/wycheproof_ecdh.json", "w"), indent=0)
     print("wycheproof ecdh:", len(ecdh), "exported,", sum(1 for c in ecdh if c["shared"]), "with shared secret")
+    spki = wycheproof_ecdh_spki()
+    json.dump({"provenance": "secec/testdata/wycheproof/ecdh_secp256k1_test.json, every case, raw DER public key; "
+                             "verdicts as required by secec/wycheproof_test.go:212-253", "cases": spki},
+              open(f"{OUT}/wycheproof_ecdh_spki.json", "w"), indent=0)
+    print("wycheproof ecdh (raw SPKI):", len(spki), "cases,", sum(c["must_parse"] for c in spki), "must parse")
     b = bip340()
     json.dump({"provenance": "secec/bitcoin/testdata/bip-0340-test-vectors.csv", "rows": b},
               open(f"{OUT}/bip340.json", "w"), indent=0)

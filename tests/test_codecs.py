@@ -85,3 +85,99 @@ def test_bitcoin_verify_asn1(engine, oracle, s256):
     exp = bip & ok & low
     assert np.array_equal(got, exp)
     assert 0 < int(exp.sum()) < int(np.array([c["valid"] for c in der]).sum())  # high-s valid cases are refused
+
+
+def test_parse_asn1_public_keys_wycheproof(s256, oracle):
+    """secec.ParseASN1PublicKey against the verdicts the reference's own harness demands for all 752
+    ASN.1-encoded Wycheproof ECDH keys (secec/wycheproof_test.go:212-253): host SPKI parser, then the
+    oracle standing in for NewPublicKey's curve checks; ASN1Bytes must reproduce the input."""
+    cases = load_golden("wycheproof_ecdh_spki.json")["cases"]
+    assert len(cases) == 752
+    pts, ln, st = s256.parse_asn1_public_keys([H(c["public"]) for c in cases])
+    n_ok = 0
+    for c, p, l, s in zip(cases, pts, ln, st):
+        accepted, enc = False, None
+        if s == 1:
+            enc, pst = oracle.point_decode(p[:l].tobytes())
+            accepted = pst == 1  # a finite point on the curve; the identity is not a public key
+        assert accepted == c["must_parse"], (c, int(s), int(l))
+        if not accepted:
+            continue
+        n_ok += 1
+        if not c["compressed"]:
+            assert s256.build_asn1_public_keys(np.frombuffer(enc, np.uint8))[0].tobytes() == H(c["public"]), c
+        shared, est = oracle.ecdh(H(c["priv"]), enc)
+        assert est == 1 and shared.hex() == c["shared"], c
+    assert n_ok == 474
+
+
+def test_parse_asn1_public_keys_hand_cases(s256):
+    head = H("3056301006072a8648ce3d020106052b8104000a034200")
+    g = H("0479be667ef9dcbbac55a06295ce870b07029bfcdb2dce28d959f2815b16f81798"
+          "483ada7726a3c4655da4fbfc0e1108a8fd17b448a68554199c47d08ffb10d4b8")
+    good = head + g
+    rows = [good,
+            good + b"\x00",                                              # trailing byte
+            good[:-1],                                                   # truncated
+            good.replace(H("2a8648ce3d0201"), H("2a8648ce3d0202")),      # not ecPublicKey
+            good.replace(H("2b8104000a"), H("2b81040022")),              # secp384r1
+            H("3057301006072a8648ce3d020106052b8104000a034300") + g + b"\x00",   # 66-byte bit string
+            H("3016301006072a8648ce3d020106052b8104000a03020000"),              # the identity encoding
+            good[:22] + b"\x01" + g[:-1] + bytes([g[-1] & 0xFE]),        # one padding bit (shifted on read)
+            H("30818f") + good[2:]]                                      # wrong outer length
+    pts, ln, st = s256.parse_asn1_public_keys(rows)
+    assert st.tolist() == [1, 0, 0, 3, 4, 0, 1, 1, 0]
+    assert pts[0].tobytes() == g and ln[0] == 65 and ln[6] == 1 and pts[6, 0] == 0
+    shifted = int.from_bytes(g[:-1] + bytes([g[-1] & 0xFE]), "big") >> 1
+    assert pts[7].tobytes() == shifted.to_bytes(65, "big")
+
+
+def test_build_asn1_signatures(s256):
+    """secec.BuildASN1Signature: what the strict parser accepts round-trips byte for byte (every Wycheproof
+    signature that parses is DER, so rebuilding from (r, s) must give the original)."""
+    der = load_golden("wycheproof_ecdsa_der.json")["cases"]
+    rows = [H(c["sig"]) for c in der]
+    sig, ok = s256.parse_asn1_signatures(rows)
+    keep = [i for i in range(len(rows)) if ok[i]]
+    built = s256.build_asn1_signatures(sig[keep])
+    assert [built[j] for j in range(len(keep))] == [rows[i] for i in keep]
+    small = np.zeros((2, 64), np.uint8); small[0, 31] = 1; small[0, 63] = 0x80; small[1, :] = 0xFF
+    b = s256.build_asn1_signatures(small)
+    assert b[0] == H("3007020101020200 80".replace(" ", "")) and len(b[1]) == 72 and b[1][:4] == H("30460221")
+
+
+@pytest.mark.gpu
+def test_parse_asn1_public_keys_on_device(engine):
+    """ParseASN1PublicKey end to end (host SPKI parse + NewPublicKey on the GPU), then ECDH with the parsed key."""
+    cases = load_golden("wycheproof_ecdh_spki.json")["cases"]
+    out, st = engine.parse_asn1_public_keys([H(c["public"]) for c in cases])
+    assert [int(s == 1) for s in st] == [int(c["must_parse"]) for c in cases]
+    keep = [i for i, c in enumerate(cases) if c["must_parse"]]
+    priv = np.frombuffer(b"".join(H(cases[i]["priv"]) for i in keep), np.uint8).reshape(-1, 32)
+    x, xst = engine.ecdh(priv, out[keep])
+    assert xst.tolist() == [1] * len(keep)
+    assert [x[j].tobytes().hex() for j in range(len(keep))] == [cases[i]["shared"] for i in keep]
+    assert not out[[i for i, c in enumerate(cases) if not c["must_parse"]]].any()
+
+
+@pytest.mark.gpu
+def test_new_public_keys_mixed_encodings(engine, oracle):
+    """secec.NewPublicKey: compressed, uncompressed, identity and malformed rows in one batch."""
+    ks = np.zeros((8, 32), np.uint8)
+    ks[:, 31] = np.arange(1, 9)
+    w = engine.scalar_base_mult(ks)[0]
+    rows = []
+    for i in range(8):
+        full = w[i].tobytes()
+        comp = bytes([2 + (full[64] & 1)]) + full[1:33]
+        rows += [full, comp]
+    rows += [b"\x00", b"\x01", b"", b"\x04" + b"\x00" * 64, rows[0][:64], b"\x05" + rows[0][1:],
+             bytes([rows[1][0] ^ 1]) + rows[1][1:], b"\x02" + (2**256 - 2**32 - 977).to_bytes(32, "big")]
+    out, st = engine.new_public_keys(rows)
+    for r, o, s in zip(rows, out, st):
+        exp, est = oracle.point_decode(r) if len(r) in (1, 33, 65) else (bytes(65), 0)
+        assert int(s) == est, (r.hex(), int(s), est)
+        assert o.tobytes() == (exp if est == 1 else bytes(65))
+    assert st[:16].tolist() == [1] * 16 and st[16] == 2 and st[17] == 0
+    # the flipped-parity compressed row decodes to the negated point
+    assert st[22] == 1 and out[22, 1:33].tobytes() == out[0, 1:33].tobytes() and out[22, 33:].tobytes() != out[0, 33:].tobytes()

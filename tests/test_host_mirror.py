@@ -29,7 +29,11 @@ def test_mirror_runs_reference_style_checks(s256):
     exe = build(s256)
     k = load_golden("kats.json")
     row0 = load_golden("bip340.json")["rows"][0]
+    rfc = load_golden("rfc6979.json")["rows"][0]
+    suite = [s for s in load_golden("h2c.json")["suites"] if s["random_oracle"]][0]
+    vec = [v for v in suite["vectors"] if v["msg"] == "abc"][0]
     r = subprocess.run([exe, k["g_uncompressed"], k["g_compressed"], k["libsecp_a"], k["libsecp_xn"], k["libsecp_b"],
-                        row0["pk"], row0["sig"]], capture_output=True, text=True, timeout=300)
+                        row0["pk"], row0["sig"], rfc["priv"], rfc["digest"], rfc["r"] + rfc["s"], row0["sk"], row0["aux"],
+                        suite["dst"], vec["msg"], vec["Px"] + vec["Py"]], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "host mirror ok" in r.stdout
