@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(S256_TPB) k_decode_recover(const uint8_t *sig6
 }
 
 template <int K, bool RECOVER>
-__global__ void __launch_bounds__(S256_TPB) k_ecdsa_scalars(const uint8_t *digest32, const uint8_t *sig, size_t n,
+__global__ void __launch_bounds__(S256_TPB, 4) k_ecdsa_scalars(const uint8_t *digest32, const uint8_t *sig, size_t n,
                                                             uint32_t flags, sc *u1, int8_t *dig1, int8_t *dig2,
                                                             uint8_t *sfl) {
     size_t stride = (n + K - 1) / K;
@@ -280,6 +280,9 @@ extern "C" void s256_free(s256_ctx *ctx) {
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
         if (ctx->ev_decode) cudaEventDestroy(ctx->ev_decode);
+        for (cudaEvent_t e : ctx->ev_pipe)
+            if (e) cudaEventDestroy(e);
+        if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
     }
     delete ctx;
 }
@@ -323,11 +326,17 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
     ctx->cap = max_batch ? max_batch : ((size_t)1 << 20);
     dev_guard g(device);
     int rc = ctx_alloc(ctx);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // stream2 feeds stream: its short kernels go first
     if (rc == S256_SUCCESS && (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-                               cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess))
+                               cudaStreamCreateWithPriority(&ctx->stream2, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+                               cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi) != cudaSuccess))
         rc = S256_ERR_CUDA;
-    if (rc == S256_SUCCESS && cudaEventCreateWithFlags(&ctx->ev_decode, cudaEventDisableTiming) != cudaSuccess)
+    if (rc == S256_SUCCESS && (cudaEventCreateWithFlags(&ctx->ev_decode, cudaEventDisableTiming) != cudaSuccess ||
+                               false))
         rc = S256_ERR_CUDA;
+    for (cudaEvent_t &e : ctx->ev_pipe)
+        if (rc == S256_SUCCESS && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = S256_ERR_CUDA;
     if (rc == S256_SUCCESS) {
         // generator tables (reference: package init, point_mul_table.go:75-100,147-160)
         size_t total = (size_t)COMB_NW * COMB_SZ;
@@ -469,10 +478,106 @@ extern "C" int s256_ecdsa_verify_dev(s256_ctx *ctx, const uint8_t *pk, const uin
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
+// Host-pointer verification as a pipeline over three sub-chunks of 1/16, 3/16 and 12/16 of the chunk.
+// Two feeder streams (high priority) carry the inputs in -- digests + signatures then the scalar kernel
+// on one, public keys then the decode kernel on the other -- and the main stream runs the ladder and
+// the final check of each sub-chunk as soon as both of its events have fired.  The ladder therefore
+// starts after 1/16 of the copy, its first sub-chunk is a single wave that leaves SM slots free for
+// the next scalar kernel, and the remaining 3 ms of PCIe traffic (2^20 items) hide under ladders.
+// Equal parts lose: the batched-inversion kernel is latency bound (~1 ms whatever its size) and would
+// sit in front of every ladder.
+// S256_TRACE=1: device timestamps of the pipeline stages, printed per call (debug aid, off by default)
+struct stage_trace {
+    bool on;
+    std::vector<std::pair<const char *, cudaEvent_t>> ev;
+    cudaEvent_t t0 = nullptr;
+    explicit stage_trace(cudaStream_t s) : on(getenv("S256_TRACE") != nullptr) {
+        if (on) {
+            cudaEventCreate(&t0);
+            cudaEventRecord(t0, s);
+        }
+    }
+    void mark(const char *what, cudaStream_t s) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        ev.emplace_back(what, e);
+    }
+    void dump() {
+        if (!on) return;
+        for (auto &p : ev) {
+            float ms = 0;
+            cudaEventSynchronize(p.second);
+            cudaEventElapsedTime(&ms, t0, p.second);
+            fprintf(stderr, "[s256 trace] %-12s %8.3f ms\n", p.first, ms);
+            cudaEventDestroy(p.second);
+        }
+        cudaEventDestroy(t0);
+    }
+};
+static int verify_pipelined(s256_ctx *ctx, const uint8_t *pk, const uint8_t *dg, const uint8_t *sig, uint32_t flags,
+                            size_t off, size_t c, uint8_t *ok) {
+    cudaStream_t feed = ctx->stream2, feed_pk = ctx->stream3, mainst = ctx->stream;
+    const int P = 3;
+    size_t cut[P + 1] = {0, (c / 16 + 127) & ~(size_t)127, (c / 4 + 127) & ~(size_t)127, c};
+    stage_trace tr(feed);
+    static const char *const names[3][4] = {{"sig+dg A", "scalars A", "decode A", "ladder A"},
+                                            {"sig+dg B", "scalars B", "decode B", "ladder B"},
+                                            {"sig+dg C", "scalars C", "decode C", "ladder C"}};
+    for (int k = 0; k < P; k++) {
+        size_t so = cut[k], n = cut[k + 1] - cut[k];
+        view v = view_at(ctx, so);
+        size_t g = off + so;
+        CK(cudaMemcpyAsync(v.in_b, dg + 32 * g, 32 * n, cudaMemcpyHostToDevice, feed));
+        CK(cudaMemcpyAsync(v.in_c, sig + 64 * g, 64 * n, cudaMemcpyHostToDevice, feed));
+        tr.mark(names[k][0], feed);
+        CK(cudaMemcpyAsync(v.in_a, pk + 65 * g, 65 * n, cudaMemcpyHostToDevice, feed_pk));
+        DISPATCH_K(n, LAUNCH(ctx, (k_ecdsa_scalars<KK, false>), grid_for_groups(n, KK), 0, feed, v.in_b, v.in_c, n, flags, v.u1,
+                             v.dig1, v.dig2, v.sfl));
+        tr.mark(names[k][1], feed);
+        CK(cudaEventRecord(ctx->ev_pipe[2 * k], feed));
+        LAUNCH(ctx, k_decode_uncompressed, grid_for(n), 0, feed_pk, v.in_a, n, v.aff, v.pvalid);
+        tr.mark(names[k][2], feed_pk);
+        CK(cudaEventRecord(ctx->ev_pipe[2 * k + 1], feed_pk));
+    }
+    for (int k = 0; k < P; k++) {
+        size_t so = cut[k], n = cut[k + 1] - cut[k];
+        view v = view_at(ctx, so);
+        CK(cudaStreamWaitEvent(mainst, ctx->ev_pipe[2 * k], 0));
+        CK(cudaStreamWaitEvent(mainst, ctx->ev_pipe[2 * k + 1], 0));
+        enqueue_dsm(ctx, v, n, mainst);
+        tr.mark(names[k][3], mainst);
+        LAUNCH(ctx, k_ecdsa_finish, grid_for(n), 0, mainst, n, v.res, v.in_c, v.pvalid, v.sfl, v.st);
+    }
+    CK(cudaMemcpyAsync(ok + off, ctx->st, c, cudaMemcpyDeviceToHost, mainst));
+    tr.mark("d2h", mainst);
+    CK(cudaStreamSynchronize(mainst));
+    tr.dump();
+    return S256_SUCCESS;
+}
 extern "C" int s256_ecdsa_verify(s256_ctx *ctx, const uint8_t *pk, const uint8_t *dg, const uint8_t *sig,
                                  uint32_t flags, size_t n, uint8_t *ok) {
     ENTER(ctx);
     if (n && (!pk || !dg || !sig || !ok)) return S256_ERR_ARG;
+    if (ctx->pipe_parts == 1 && n >= ((size_t)1 << 18)) {
+        int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+            if (c < ((size_t)1 << 16)) {  // a short tail chunk: plain path
+                view v = view_at(ctx, 0);
+                cudaStream_t s = ctx->stream;
+                CK(cudaMemcpyAsync(v.in_b, dg + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync(v.in_c, sig + 64 * off, 64 * c, cudaMemcpyHostToDevice, s));
+                CK(cudaMemcpyAsync(v.in_a, pk + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
+                int r = chunk_ecdsa_verify(ctx, v, v.in_a, v.in_b, v.in_c, flags, c, v.st, s);
+                if (r != S256_SUCCESS) return r;
+                CK(cudaMemcpyAsync(ok + off, v.st, c, cudaMemcpyDeviceToHost, s));
+                CK(cudaStreamSynchronize(s));
+                return S256_SUCCESS;
+            }
+            return verify_pipelined(ctx, pk, dg, sig, flags, off, c, ok);
+        });
+        return rc != S256_SUCCESS ? rc : check_launch(ctx);
+    }
     int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t s) {
         // digest + signature first: the batched inversion starts while the keys are still in flight
         cudaStream_t s2 = (s == ctx->stream) ? ctx->stream2 : ctx->stream;

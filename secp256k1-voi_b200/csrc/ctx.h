@@ -26,7 +26,7 @@ struct s256_ctx {
     int device = -1;
     size_t cap = 0;
     std::mutex mu;
-    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr, stream3 = nullptr;
     std::string last_err;
     std::atomic<uint64_t> launches{0};
     // constant tables
@@ -57,7 +57,7 @@ struct s256_ctx {
     // sub-chunks per host-pointer call (S256_PIPE_PARTS).  Measured (scripts/e2e_parts.py): splitting does not
     // pay -- the batched-inversion kernel is latency bound, so its cost multiplies with the part count.
     int pipe_parts = 1;
-    cudaEvent_t ev_decode = nullptr;
+    cudaEvent_t ev_decode = nullptr, ev_pipe[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool use_reg_ladder = true;  // S256_LADDER=vm selects the frame-form ladder (A/B measurements)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dsm_events;
 };

@@ -97,6 +97,17 @@ S256_HD uint32_t sc_reduce_once(sc &r, const uint32_t a[8], uint32_t carry_in) {
 // scalar.go:123-131 SetBytes: big-endian bytes, reduced once; returns didReduce
 S256_HD uint32_t sc_from_be32(sc &r, const uint8_t *b) {
     uint32_t l[8];
+#if S256_PTX
+    // rows of the batch buffers are 16-byte aligned: two 128-bit loads instead of 32 byte loads
+    if ((((size_t)b) & 15u) == 0) {
+        const uint4 hi = *reinterpret_cast<const uint4 *>(b), lo = *reinterpret_cast<const uint4 *>(b + 16);
+        l[7] = __byte_perm(hi.x, 0, 0x0123); l[6] = __byte_perm(hi.y, 0, 0x0123);
+        l[5] = __byte_perm(hi.z, 0, 0x0123); l[4] = __byte_perm(hi.w, 0, 0x0123);
+        l[3] = __byte_perm(lo.x, 0, 0x0123); l[2] = __byte_perm(lo.y, 0, 0x0123);
+        l[1] = __byte_perm(lo.z, 0, 0x0123); l[0] = __byte_perm(lo.w, 0, 0x0123);
+        return sc_reduce_once(r, l, 0);
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const uint8_t *q = b + 4 * (7 - i);
@@ -203,6 +214,92 @@ S256_HD void sc_mul_wide(uint32_t w[16], const uint32_t a[8], const uint32_t b[8
         w[i + 8] = (uint32_t)carry;
     }
 }
+#if S256_PTX
+// Device form of the product and of the first two folds: the same even/odd mad.cc carry chains as
+// fe_mul_wide (fe.cuh) instead of 64-bit C arithmetic, whose dependent IMAD / IADD3 / IADD3.X triples
+// made one sc_mul ~3100 cycles of latency -- and the batched-inversion kernel, 600 dependent sc_mul
+// per thread on few threads, is latency bound.
+// out[0..12] = lo[0..7] + hi[0..7] * (2^256 - n),  2^256 - n = NC[0..3] + 2^128
+S256_D void sc_fold_ptx(uint32_t out[13], const uint32_t lo[8], const uint32_t hi[8]) {
+    const uint32_t c0 = 0x2FC9BEBFu, c1 = 0x402DA173u, c2 = 0x50B75FC4u, c3 = 0x45512319u;
+    uint32_t e[12], o[11];
+    // hi * NC[0..3]: rows 0..3 of the schoolbook product
+    S256_MULW(e[0], e[1], hi[0], c0);
+    S256_MULW(e[2], e[3], hi[2], c0);
+    S256_MULW(e[4], e[5], hi[4], c0);
+    S256_MULW(e[6], e[7], hi[6], c0);
+    S256_MULW(o[0], o[1], hi[1], c0);
+    S256_MULW(o[2], o[3], hi[3], c0);
+    S256_MULW(o[4], o[5], hi[5], c0);
+    S256_MULW(o[6], o[7], hi[7], c0);
+    S256_CHAIN_C(o[0], o[1], o[2], o[3], o[4], o[5], o[6], o[7], o[8], hi[0], hi[2], hi[4], hi[6], c1);
+    S256_CHAIN_X2(e[2], e[3], e[4], e[5], e[6], e[7], e[8], e[9], hi[1], hi[3], hi[5], hi[7], c1);
+    S256_CHAIN_C(e[2], e[3], e[4], e[5], e[6], e[7], e[8], e[9], e[10], hi[0], hi[2], hi[4], hi[6], c2);
+    S256_CHAIN_X1(o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], hi[1], hi[3], hi[5], hi[7], c2);
+    S256_CHAIN_C(o[2], o[3], o[4], o[5], o[6], o[7], o[8], o[9], o[10], hi[0], hi[2], hi[4], hi[6], c3);
+    S256_CHAIN_X1(e[4], e[5], e[6], e[7], e[8], e[9], e[10], e[11], hi[1], hi[3], hi[5], hi[7], c3);
+    // P = e + (o << 32): 12 limbs, no carry out (P < 2^384)
+    asm("add.cc.u32 %0,%0,%11; addc.cc.u32 %1,%1,%12; addc.cc.u32 %2,%2,%13; addc.cc.u32 %3,%3,%14;"
+        "addc.cc.u32 %4,%4,%15; addc.cc.u32 %5,%5,%16; addc.cc.u32 %6,%6,%17; addc.cc.u32 %7,%7,%18;"
+        "addc.cc.u32 %8,%8,%19; addc.cc.u32 %9,%9,%20; addc.u32 %10,%10,%21;"
+        : "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9]),
+          "+r"(e[10]), "+r"(e[11])
+        : "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]),
+          "r"(o[10]));
+    // + lo (limbs 0..7), carry rippling through limbs 8..11 into limb 12
+    asm("add.cc.u32 %0,%0,%13; addc.cc.u32 %1,%1,%14; addc.cc.u32 %2,%2,%15; addc.cc.u32 %3,%3,%16;"
+        "addc.cc.u32 %4,%4,%17; addc.cc.u32 %5,%5,%18; addc.cc.u32 %6,%6,%19; addc.cc.u32 %7,%7,%20;"
+        "addc.cc.u32 %8,%8,0; addc.cc.u32 %9,%9,0; addc.cc.u32 %10,%10,0; addc.cc.u32 %11,%11,0; addc.u32 %12,0,0;"
+        : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]),
+          "+r"(e[9]), "+r"(e[10]), "+r"(e[11]), "=r"(out[12])
+        : "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]), "r"(lo[4]), "r"(lo[5]), "r"(lo[6]), "r"(lo[7]));
+    // + hi << 128 (limbs 4..11)
+    asm("add.cc.u32 %0,%0,%9; addc.cc.u32 %1,%1,%10; addc.cc.u32 %2,%2,%11; addc.cc.u32 %3,%3,%12;"
+        "addc.cc.u32 %4,%4,%13; addc.cc.u32 %5,%5,%14; addc.cc.u32 %6,%6,%15; addc.cc.u32 %7,%7,%16; addc.u32 %8,%8,0;"
+        : "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "+r"(e[8]), "+r"(e[9]), "+r"(e[10]), "+r"(e[11]), "+r"(out[12])
+        : "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]), "r"(hi[4]), "r"(hi[5]), "r"(hi[6]), "r"(hi[7]));
+#pragma unroll
+    for (int i = 0; i < 12; i++) out[i] = e[i];
+}
+S256_D void sc_reduce512_ptx(sc &r, const uint32_t w[16]) {
+    uint32_t x[13], y[13], z[9], h2[8];
+    sc_fold_ptx(x, w, w + 8);  // < 2^386: limbs 0..12, x[12] <= 2
+#pragma unroll
+    for (int i = 0; i < 8; i++) h2[i] = i < 5 ? x[8 + i] : 0u;
+    sc_fold_ptx(y, x, h2);     // x >> 256 < 2^130  ->  y < 2^260: y[8] < 16, y[9..12] = 0
+    sc_fold<1, 9>(z, y, y + 8);
+    uint32_t c = z[8];
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        acc = (acc >> 32) + z[i] + ((i < 5) ? (uint64_t)(S256_K(SC_NC)[i] & (0u - c)) : 0u);
+        z[i] = (uint32_t)acc;
+    }
+    sc_reduce_once(r, z, 0);
+}
+#endif
+
+#if S256_PTX
+// out of line (one body for ~60 call sites), operands and result in registers: passing references
+// would pin every scalar to the local-memory stack
+static __device__ __noinline__ sc sc_mul_call(sc a, sc b) {
+    uint32_t w[16];
+    sc r;
+    fe_mul_wide(w, a.v, b.v);
+    sc_reduce512_ptx(r, w);
+    return r;
+}
+S256_D void sc_mul(sc &r, const sc &a, const sc &b) { r = sc_mul_call(a, b); }
+// 36 instead of 64 products (fe_sqr_gen.cuh): the inversion chain is 253 squarings
+static __device__ __noinline__ sc sc_sqr_call(sc a) {
+    uint32_t w[16];
+    sc r;
+    fe_sqr_wide(w, a.v);
+    sc_reduce512_ptx(r, w);
+    return r;
+}
+S256_D void sc_sqr(sc &r, const sc &a) { r = sc_sqr_call(a); }
+#else
 #if defined(__CUDACC__)
 static __host__ __device__ S256_NOINLINE
 #else
@@ -214,6 +311,7 @@ void sc_mul(sc &r, const sc &a, const sc &b) {
     sc_reduce512(r, w);
 }
 S256_HD void sc_sqr(sc &r, const sc &a) { sc_mul(r, a, a); }
+#endif
 
 // scalar_invert.go:11-303 -- x^(n-2), Invert(0) = 0.  The top 127 exponent
 // bits are ones (run-of-ones chain), the low 129 go through a 4-bit window.

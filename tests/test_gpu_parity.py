@@ -161,6 +161,27 @@ def test_full_size_properties(engine):
     assert int(a.sum()) == n - n // 16
 
 
+def test_host_pipeline_chunk_shapes(s256):
+    """The host-pointer verify path is a two-stage pipeline per chunk (api.cu verify_pipelined): exercise a
+    chunk cut in 1/8 + 7/8, a second pipelined chunk of odd size, and a short tail chunk on the plain path."""
+    eng = s256.Engine(device=0, max_batch=1 << 18)
+    try:
+        n = (1 << 18) + (1 << 16) + 777
+        w = ps.synth.ecdsa_batch(n, eng.scalar_base_mult)
+        for m in (n, (1 << 18) + 1000, 1 << 18):
+            got = eng.ecdsa_verify(w["pk65"][:m], w["digest32"][:m], w["sig64"][:m])
+            assert np.array_equal(got, w["expected"][:m]), m
+        d = [torch_cuda(w[k]) for k in ("pk65", "digest32", "sig64")]
+        assert np.array_equal(eng.ecdsa_verify(*d).cpu().numpy(), w["expected"])
+    finally:
+        eng.close()
+
+
+def torch_cuda(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
 def test_concurrent_callers_share_one_context(engine, oracle):
     """cgo calls arrive on arbitrary OS threads: one context, many threads, mixed entry points."""
     import threading
