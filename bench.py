@@ -57,7 +57,7 @@ def workload_config(n_gpus, batch):
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
@@ -72,7 +72,9 @@ class ClockSampler:
         except OSError:
             self.p = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """The sampler is started BEFORE the warm-up (nvidia-smi needs ~0.1 s to produce its first line,
+        longer with one instance per rank); only samples stamped inside [t_begin, t_end] are kept."""
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -82,23 +84,37 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, smax, reasons, power = [], [], set(), []
+        import datetime
+        rows = []
         for line in self.f.read().splitlines():
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1])); smax.append(float(c[2])); power.append(float(c[3]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = None
+            try:
+                rows.append((ts, float(c[1]), float(c[2]), float(c[3]), c[5:9]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+        os.unlink(self.f.name)
+        window = "timed region"
+        if t_begin is not None:
+            inside = [r for r in rows if r[0] is not None and t_begin - 0.02 <= r[0] <= t_end + 0.02]
+            if inside:
+                rows = inside
+            elif rows:  # region shorter than the sampling period, or an unparsed timestamp: nearest samples
+                rows, window = rows[-3:], "last samples before the region ended"
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        reasons = set()
+        for r in rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        os.unlink(self.f.name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(smax), "power_w_max": max(power),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": max(r[2] for r in rows),
+                "power_w_max": max(r[3] for r in rows), "samples": len(rows), "window": window, "reasons": sorted(reasons)}
 
 
 def cpu_reference_arm(args):
@@ -186,23 +202,26 @@ def main():
     imad_peak = max(imad_peak, eng.microbench_imad(8192)[0])
 
     # ---- device-resident timing ------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         ok = eng.ecdsa_verify(d_pk, d_dg, d_sg)
     torch.cuda.synchronize()
     assert np.array_equal(ok.cpu().numpy(), expected), "verify booleans differ from the construction"
-    sampler = ClockSampler(local)
     launches0 = eng.launch_count
     eng.profile_enable(True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(); torch.cuda.synchronize()
-    sampler.start()
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         ok = eng.ecdsa_verify(d_pk, d_dg, d_sg)
     e1.record()
-    torch.cuda.synchronize(); barrier()
+    torch.cuda.synchronize()
+    t_end = time.time()
+    barrier()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     dsm_ms, dsm_launches = eng.profile_read()
     eng.profile_enable(False)
     launches = eng.launch_count - launches0

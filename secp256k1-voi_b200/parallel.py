@@ -29,7 +29,7 @@ def gather_bytes(local_row, group=None, device=None):
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    t = torch.from_numpy(np.ascontiguousarray(local_row, dtype=np.uint8))
+    t = torch.from_numpy(np.array(local_row, dtype=np.uint8, copy=True))
     if device is not None:
         t = t.to(device)
     t = t.reshape(-1)
