@@ -206,7 +206,8 @@ int s256_msm_combine(s256_ctx *ctx, const uint8_t *partials96, size_t m, uint8_t
  * as X||Y (64 B each), window-major: with wbits = 8, nwin = 32 this is byte for
  * byte internal/gentable/point_mul_table.bin. */
 int s256_debug_gen_table(s256_ctx *ctx, int wbits, int nwin, uint8_t *out);
-/* out32[i] = a32[i] (op) b32[i] in F_p (op 0 mul, 1 add, 2 sub, 3 inv(a), 4 sqrt(a) or zeros)
+/* out32[i] = a32[i] (op) b32[i] in F_p (op 0 mul, 1 add, 2 sub, 3 inv(a), 4 sqrt(a) or zeros, 5 a*21,
+ * 6 a^2; 8 + op for the variable-time flavour of mul / add / sub / a*21 / a^2 used by the vartime paths)
  * or Z_n (op 16 mul, 17 add, 18 inv(a)); inputs are reduced like SetBytes. */
 int s256_debug_field_op(s256_ctx *ctx, int op, const uint8_t *a32, const uint8_t *b32, size_t n, uint8_t *out32);
 /* Integer-multiply peak: runs independent IMAD.WIDE.U32 chains on every SM and

@@ -232,6 +232,12 @@ __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a3
             case 4: fe_sqrt(r, a); break;
             case 5: fe_mul_small(r, a, 21u); break;
             case 6: fe_sqr(r, a); break;
+            // 8 + op: the variable-time flavour (fe_vt.cuh) of the same operation
+            case 8: fe_mul_vt(r, a, b); break;
+            case 9: fe_add_vt(r, a, b); break;
+            case 10: fe_sub_vt(r, a, b); break;
+            case 13: fe_mul_small_vt(r, a, 21u); break;
+            case 14: fe_sqr_vt(r, a); break;
             default: r = fe_zero();
         }
         fe_normalize(r, r);

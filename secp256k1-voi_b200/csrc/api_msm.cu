@@ -110,7 +110,7 @@ __device__ __forceinline__ void msm_cta_weighted(pt &R, pt &A, const pt &run, co
         pt v = sh[t];
         if (t + d < MSM_WT) {
             pt o = sh[t + d];
-            pt_add(v, v, o);
+            pt_add<true>(v, v, o);
         }
         __syncthreads();
         sh[t] = v;
@@ -128,7 +128,7 @@ __device__ __forceinline__ void msm_cta_weighted(pt &R, pt &A, const pt &run, co
     for (int stride = MSM_WT / 2; stride >= 1; stride >>= 1) {
         if (t < stride) {
             pt a = sh[t], b = sh[t + stride];
-            pt_add(a, a, b);
+            pt_add<true>(a, a, b);
             sh[t] = a;
         }
         __syncthreads();

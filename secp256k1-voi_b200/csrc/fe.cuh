@@ -80,7 +80,8 @@ S256_D void fe_fold_carry(fe &r, uint32_t c) {
     }
 }
 
-S256_D void fe_add(fe &r, const fe &a, const fe &b) {
+// r = a + b mod 2^256, returns the carry
+S256_D uint32_t fe_add_raw(fe &r, const fe &a, const fe &b) {
     uint32_t c;
     asm("add.cc.u32 %0,%9,%17; addc.cc.u32 %1,%10,%18; addc.cc.u32 %2,%11,%19; addc.cc.u32 %3,%12,%20;"
         "addc.cc.u32 %4,%13,%21; addc.cc.u32 %5,%14,%22; addc.cc.u32 %6,%15,%23; addc.cc.u32 %7,%16,%24;"
@@ -89,11 +90,16 @@ S256_D void fe_add(fe &r, const fe &a, const fe &b) {
           "=r"(r.v[7]), "=r"(c)
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
           "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
+    return c;
+}
+S256_D void fe_add(fe &r, const fe &a, const fe &b) {
+    uint32_t c = fe_add_raw(r, a, b);
     fe_fold_carry(r, c);
 }
 
-S256_D void fe_sub(fe &r, const fe &a, const fe &b) {
-    uint32_t bw, bw2;
+// r = a - b mod 2^256, returns the borrow as 0 / 0xFFFFFFFF
+S256_D uint32_t fe_sub_raw(fe &r, const fe &a, const fe &b) {
+    uint32_t bw;
     asm("sub.cc.u32 %0,%9,%17; subc.cc.u32 %1,%10,%18; subc.cc.u32 %2,%11,%19; subc.cc.u32 %3,%12,%20;"
         "subc.cc.u32 %4,%13,%21; subc.cc.u32 %5,%14,%22; subc.cc.u32 %6,%15,%23; subc.cc.u32 %7,%16,%24;"
         "subc.u32 %8,0,0;"
@@ -101,7 +107,11 @@ S256_D void fe_sub(fe &r, const fe &a, const fe &b) {
           "=r"(r.v[7]), "=r"(bw)
         : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
           "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]), "r"(b.v[7]));
-    // bw is 0 or 0xFFFFFFFF; on borrow the true value is r - 2^256 = r - delta (mod p)
+    return bw;
+}
+// on borrow the true value is r - 2^256 = r - delta (mod p)
+S256_D void fe_fold_borrow(fe &r, uint32_t bw) {
+    uint32_t bw2;
     uint32_t one = bw & 1u;
     uint32_t t = bw & S256_DELTA_LO;
     asm("sub.cc.u32 %0,%0,%9; subc.cc.u32 %1,%1,%10; subc.cc.u32 %2,%2,0; subc.cc.u32 %3,%3,0;"
@@ -116,6 +126,10 @@ S256_D void fe_sub(fe &r, const fe &a, const fe &b) {
               "+r"(r.v[7])
             : "r"(S256_DELTA_LO));
     }
+}
+S256_D void fe_sub(fe &r, const fe &a, const fe &b) {
+    uint32_t bw = fe_sub_raw(r, a, b);
+    fe_fold_borrow(r, bw);
 }
 
 #else  // portable
@@ -247,14 +261,17 @@ S256_D void fe_mul_wide(uint32_t r[16], const uint32_t a[8], const uint32_t b[8]
 }
 
 // out = (t[0..7] + 2^256 * (t8 + 2^32 * t9)) mod-p-folded into [0, 2^256); t9 in {0,1}
-S256_D void fe_fold_top(fe &out, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4, uint32_t t5,
-                        uint32_t t6, uint32_t t7, uint32_t t8, uint32_t t9) {
-    // u = T * (2^32 + 977), T = t8 + t9 * 2^32 < 2^33 + 1  ->  u < 2^66
-    uint32_t u0, u1, u2, c;
+// u = T * (2^32 + 977), T = t8 + t9 * 2^32 < 2^33 + 1  ->  u < 2^66
+S256_D void fe_top_times_delta(uint32_t &u0, uint32_t &u1, uint32_t &u2, uint32_t t8, uint32_t t9) {
     S256_MULW(u0, u1, t8, S256_DELTA_LO);
     uint32_t t9d = t9 * S256_DELTA_LO;
     asm("add.cc.u32 %0,%0,%2; addc.u32 %1,%3,0;" : "+r"(u1), "=r"(u2) : "r"(t8), "r"(t9));
     asm("add.cc.u32 %0,%0,%2; addc.u32 %1,%1,0;" : "+r"(u1), "+r"(u2) : "r"(t9d));
+}
+S256_D void fe_fold_top(fe &out, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4, uint32_t t5,
+                        uint32_t t6, uint32_t t7, uint32_t t8, uint32_t t9) {
+    uint32_t u0, u1, u2, c;
+    fe_top_times_delta(u0, u1, u2, t8, t9);
     asm("add.cc.u32 %0,%9,%17; addc.cc.u32 %1,%10,%18; addc.cc.u32 %2,%11,%19; addc.cc.u32 %3,%12,0;"
         "addc.cc.u32 %4,%13,0; addc.cc.u32 %5,%14,0; addc.cc.u32 %6,%15,0; addc.cc.u32 %7,%16,0; addc.u32 %8,0,0;"
         : "=r"(out.v[0]), "=r"(out.v[1]), "=r"(out.v[2]), "=r"(out.v[3]), "=r"(out.v[4]), "=r"(out.v[5]),
@@ -268,8 +285,9 @@ S256_D void fe_fold_top(fe &out, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t
 }
 
 // out = r[0..15] mod p (weak)
-S256_D void fe_reduce_wide(fe &out, uint32_t r[16]) {
-    uint32_t t8, t9, o[8];
+// r[0..7] + 2^256 * (t8 + 2^32 * t9) = r[0..15] folded once
+S256_D void fe_reduce_wide_pre(uint32_t r[16], uint32_t &t8, uint32_t &t9) {
+    uint32_t o[8];
     const uint32_t d = S256_DELTA_LO;
     // lo += hi_even * 977 (carry -> t8)
     S256_CHAIN_C(r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], t8, r[8], r[10], r[12], r[14], d);
@@ -289,6 +307,10 @@ S256_D void fe_reduce_wide(fe &out, uint32_t r[16]) {
         "addc.u32 %8,0,0;"
         : "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(t8), "=r"(t9)
         : "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]));
+}
+S256_D void fe_reduce_wide(fe &out, uint32_t r[16]) {
+    uint32_t t8, t9;
+    fe_reduce_wide_pre(r, t8, t9);
     fe_fold_top(out, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], t8, t9);
 }
 
@@ -360,8 +382,8 @@ S256_D void fe_sqr(fe &r, const fe &a) { fe_sqr_inline(r, a); }
 #endif
 
 // r = a * k for a small constant k (< 2^16): 8 IMAD.WIDE + one fold
-S256_D void fe_mul_small(fe &r, const fe &a, uint32_t k) {
-    uint32_t e[8], o[8], t8;
+S256_D void fe_mul_small_pre(uint32_t e[8], uint32_t &t8, const fe &a, uint32_t k) {
+    uint32_t o[8];
     S256_MULW(e[0], e[1], a.v[0], k);
     S256_MULW(e[2], e[3], a.v[2], k);
     S256_MULW(e[4], e[5], a.v[4], k);
@@ -374,6 +396,10 @@ S256_D void fe_mul_small(fe &r, const fe &a, uint32_t k) {
         "addc.cc.u32 %4,%4,%12; addc.cc.u32 %5,%5,%13; addc.cc.u32 %6,%6,%14; addc.u32 %7,%15,0;"
         : "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "=r"(t8)
         : "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
+}
+S256_D void fe_mul_small(fe &r, const fe &a, uint32_t k) {
+    uint32_t e[8], t8;
+    fe_mul_small_pre(e, t8, a, k);
     fe_fold_top(r, e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], t8, 0u);
 }
 

@@ -1,0 +1,152 @@
+// fe_vt.cuh -- variable-time flavour of the F_p operations, for PUBLIC data only.
+//
+// The constant-time code (fe.cuh) finishes every addition, subtraction and reduction with a full
+// 8-limb ripple of the 2^256 = delta fold, because a shortcut would branch on the data.  The
+// verification ladder (DoubleScalarMultBasepointVartime, point_mul_glv.go:307) and the vartime MSM
+// (point_mul_multi.go:73) handle public values and are variable time in the reference too, so here
+// the ripple stops after limb 2 and continues behind a branch only if a carry really leaves that limb
+// (probability 2^-32 per operation for random data; any input stays correct).  That removes 5 of the
+// ~21 instructions of an addition and 5 of a reduction; the ladder kernel is sensitive to its
+// instruction count, not only to its multiplier work.
+//
+// fe_ops<false> is the constant-time set, fe_ops<true> this one; the group law (point.cuh) is a
+// template over it.  Off the device both are the same portable code.
+#pragma once
+#include "fe.cuh"
+
+namespace s256 {
+
+#if S256_PTX
+
+S256_D void fe_fold_carry_vt(fe &r, uint32_t c) {
+    uint32_t c3;
+    uint32_t t = c * S256_DELTA_LO;
+    asm("add.cc.u32 %0,%0,%4; addc.cc.u32 %1,%1,%5; addc.cc.u32 %2,%2,0; addc.u32 %3,0,0;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "=r"(c3)
+        : "r"(t), "r"(c));
+    if (c3) {
+        uint32_t c2;
+        asm("add.cc.u32 %0,%0,1; addc.cc.u32 %1,%1,0; addc.cc.u32 %2,%2,0; addc.cc.u32 %3,%3,0; addc.cc.u32 %4,%4,0;"
+            "addc.u32 %5,0,0;"
+            : "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(c2));
+        if (c2) {  // wrapped: r < delta now, add delta once more, no further carry possible
+            asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,1; addc.u32 %2,%2,0;"
+                : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2])
+                : "r"(S256_DELTA_LO));
+        }
+    }
+}
+S256_D void fe_add_vt(fe &r, const fe &a, const fe &b) {
+    uint32_t c = fe_add_raw(r, a, b);
+    fe_fold_carry_vt(r, c);
+}
+S256_D void fe_sub_vt(fe &r, const fe &a, const fe &b) {
+    uint32_t bw = fe_sub_raw(r, a, b);
+    uint32_t one = bw & 1u, t = bw & S256_DELTA_LO, b3;
+    asm("sub.cc.u32 %0,%0,%4; subc.cc.u32 %1,%1,%5; subc.cc.u32 %2,%2,0; subc.u32 %3,0,0;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "=r"(b3)
+        : "r"(t), "r"(one));
+    if (b3) {
+        uint32_t bw2;
+        asm("sub.cc.u32 %0,%0,1; subc.cc.u32 %1,%1,0; subc.cc.u32 %2,%2,0; subc.cc.u32 %3,%3,0; subc.cc.u32 %4,%4,0;"
+            "subc.u32 %5,0,0;"
+            : "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(bw2));
+        if (bw2) {  // wrapped again: r >= 2^256 - delta now, subtracting delta cannot borrow
+            asm("sub.cc.u32 %0,%0,%8; subc.cc.u32 %1,%1,1; subc.cc.u32 %2,%2,0; subc.cc.u32 %3,%3,0;"
+                "subc.cc.u32 %4,%4,0; subc.cc.u32 %5,%5,0; subc.cc.u32 %6,%6,0; subc.u32 %7,%7,0;"
+                : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]),
+                  "+r"(r.v[7])
+                : "r"(S256_DELTA_LO));
+        }
+    }
+}
+// u < 2^66 lands on limbs 0..2; the carry leaves limb 2 with probability ~2^-30
+S256_D void fe_fold_top_vt(fe &out, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4, uint32_t t5,
+                           uint32_t t6, uint32_t t7, uint32_t t8, uint32_t t9) {
+    uint32_t u0, u1, u2, c3;
+    fe_top_times_delta(u0, u1, u2, t8, t9);
+    asm("add.cc.u32 %0,%4,%7; addc.cc.u32 %1,%5,%8; addc.cc.u32 %2,%6,%9; addc.u32 %3,0,0;"
+        : "=r"(out.v[0]), "=r"(out.v[1]), "=r"(out.v[2]), "=r"(c3)
+        : "r"(t0), "r"(t1), "r"(t2), "r"(u0), "r"(u1), "r"(u2));
+    out.v[3] = t3; out.v[4] = t4; out.v[5] = t5; out.v[6] = t6; out.v[7] = t7;
+    if (c3) {
+        uint32_t c;
+        asm("add.cc.u32 %0,%0,1; addc.cc.u32 %1,%1,0; addc.cc.u32 %2,%2,0; addc.cc.u32 %3,%3,0; addc.cc.u32 %4,%4,0;"
+            "addc.u32 %5,0,0;"
+            : "+r"(out.v[3]), "+r"(out.v[4]), "+r"(out.v[5]), "+r"(out.v[6]), "+r"(out.v[7]), "=r"(c));
+        if (c) {  // out < 2^66 now; one more delta, no carry possible
+            asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,1; addc.u32 %2,%2,0;"
+                : "+r"(out.v[0]), "+r"(out.v[1]), "+r"(out.v[2])
+                : "r"(S256_DELTA_LO));
+        }
+    }
+}
+S256_D void fe_mul_inline_vt(fe &r, const fe &a, const fe &b) {
+    uint32_t w[16], t8, t9;
+    fe_mul_wide(w, a.v, b.v);
+    fe_reduce_wide_pre(w, t8, t9);
+    fe_fold_top_vt(r, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], t8, t9);
+}
+S256_D void fe_sqr_inline_vt(fe &r, const fe &a) {
+#ifndef S256_NO_SQR
+    uint32_t w[16], t8, t9;
+    fe_sqr_wide(w, a.v);
+    fe_reduce_wide_pre(w, t8, t9);
+    fe_fold_top_vt(r, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], t8, t9);
+#else
+    fe_mul_inline_vt(r, a, a);
+#endif
+}
+#ifndef S256_MUL_INLINE
+static __device__ __noinline__ fe fe_mul_call_vt(fe a, fe b) {
+    fe r;
+    fe_mul_inline_vt(r, a, b);
+    return r;
+}
+static __device__ __noinline__ fe fe_sqr_call_vt(fe a) {
+    fe r;
+    fe_sqr_inline_vt(r, a);
+    return r;
+}
+S256_D void fe_mul_vt(fe &r, const fe &a, const fe &b) { r = fe_mul_call_vt(a, b); }
+S256_D void fe_sqr_vt(fe &r, const fe &a) { r = fe_sqr_call_vt(a); }
+#else
+S256_D void fe_mul_vt(fe &r, const fe &a, const fe &b) { fe_mul_inline_vt(r, a, b); }
+S256_D void fe_sqr_vt(fe &r, const fe &a) { fe_sqr_inline_vt(r, a); }
+#endif
+S256_D void fe_mul_small_vt(fe &r, const fe &a, uint32_t k) {
+    uint32_t e[8], t8;
+    fe_mul_small_pre(e, t8, a, k);
+    fe_fold_top_vt(r, e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], t8, 0u);
+}
+
+#else  // portable: one implementation serves both flavours
+
+S256_HD void fe_add_vt(fe &r, const fe &a, const fe &b) { fe_add(r, a, b); }
+S256_HD void fe_sub_vt(fe &r, const fe &a, const fe &b) { fe_sub(r, a, b); }
+S256_HD void fe_mul_vt(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
+S256_HD void fe_sqr_vt(fe &r, const fe &a) { fe_sqr(r, a); }
+S256_HD void fe_mul_small_vt(fe &r, const fe &a, uint32_t k) { fe_mul_small(r, a, k); }
+
+#endif
+
+template <bool VT>
+struct fe_ops;
+template <>
+struct fe_ops<false> {
+    S256_HD static void add(fe &r, const fe &a, const fe &b) { fe_add(r, a, b); }
+    S256_HD static void sub(fe &r, const fe &a, const fe &b) { fe_sub(r, a, b); }
+    S256_HD static void mul(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
+    S256_HD static void sqr(fe &r, const fe &a) { fe_sqr(r, a); }
+    S256_HD static void mul_small(fe &r, const fe &a, uint32_t k) { fe_mul_small(r, a, k); }
+};
+template <>
+struct fe_ops<true> {
+    S256_HD static void add(fe &r, const fe &a, const fe &b) { fe_add_vt(r, a, b); }
+    S256_HD static void sub(fe &r, const fe &a, const fe &b) { fe_sub_vt(r, a, b); }
+    S256_HD static void mul(fe &r, const fe &a, const fe &b) { fe_mul_vt(r, a, b); }
+    S256_HD static void sqr(fe &r, const fe &a) { fe_sqr_vt(r, a); }
+    S256_HD static void mul_small(fe &r, const fe &a, uint32_t k) { fe_mul_small_vt(r, a, k); }
+};
+
+}  // namespace s256

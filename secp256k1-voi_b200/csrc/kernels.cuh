@@ -300,6 +300,7 @@ S256_HD void item_schnorr_scalars(size_t i, size_t n, const uint8_t *pkx32, cons
 //   ladder: ND steps of W doublings + two complete additions, the lambda half
 //           reusing the same table through x -> beta*x
 //   G half: COMB_NW mixed additions from the precomputed comb, no doublings
+// Public data, variable time as in the reference: the group law runs on fe_ops<true> (fe_vt.cuh).
 // ---------------------------------------------------------------------------
 S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
                       const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
@@ -314,10 +315,10 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
 #endif
         for (int k = 2; k <= DSM_TS; k += 2) {
             pt h = T[k / 2 - 1];
-            pt_double(cur, h);
+            pt_double<true>(cur, h);
             T[k - 1] = cur;
             if (k < DSM_TS) {
-                pt_add_mixed(cur, cur, P.x, P.y);
+                pt_add_mixed<true>(cur, cur, P.x, P.y);
                 T[k] = cur;
             }
         }
@@ -334,7 +335,7 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-            for (int k = 0; k < DSM_W; k++) pt_double(acc, acc);
+            for (int k = 0; k < DSM_W; k++) pt_double<true>(acc, acc);
         }
         int da = dig1[(size_t)s * n + i];
         int db = dig2[(size_t)s * n + i];
@@ -347,9 +348,12 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
                 uint32_t neg = (uint32_t)(d < 0) ^ ((fl >> (1 + h)) & 1u);
                 int mag = d < 0 ? -d : d;
                 pt q = T[mag - 1];
-                if (h) fe_mul(q.x, q.x, beta);
-                if (neg) fe_neg(q.y, q.y);
-                pt_add(acc, acc, q);
+                if (h) fe_mul_vt(q.x, q.x, beta);
+                if (neg) {
+                    fe z = fe_zero();
+                    fe_sub_vt(q.y, z, q.y);
+                }
+                pt_add<true>(acc, acc, q);
             }
         }
     }
@@ -364,7 +368,7 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
         d &= (uint32_t)COMB_SZ - 1u;
         if (d != 0) {
             apt g = comb[(size_t)w * COMB_SZ + d];
-            pt_add_mixed(acc, acc, g.x, g.y);
+            pt_add_mixed<true>(acc, acc, g.x, g.y);
         }
     }
     res[i] = acc;

@@ -119,8 +119,11 @@ S256_HD void msm_bucket_sum(pt &out, const uint32_t *entries, uint32_t start, ui
                 vn = entries[e + 1];
                 an = aff[vn >> 1];
             }
-            if (v & 1u) fe_neg(a.y, a.y);
-            pt_add_mixed(acc, acc, a.x, a.y);
+            if (v & 1u) {
+                fe z = fe_zero();
+                fe_sub_vt(a.y, z, a.y);
+            }
+            pt_add_mixed<true>(acc, acc, a.x, a.y);
             v = vn;
             a = an;
         }
@@ -141,7 +144,7 @@ S256_HD void msm_superslice_fold(pt *slice_sum, uint32_t s, uint32_t s0, uint32_
     pt acc = slice_sum[s];
     for (uint32_t q = s + 1; q < e; q++) {
         pt t = slice_sum[q];
-        pt_add(acc, acc, t);
+        pt_add<true>(acc, acc, t);
     }
     slice_sum[s] = acc;
 }
@@ -153,7 +156,7 @@ S256_HD void msm_bucket_from_slices(pt &out, const pt *slice_sum, const uint32_t
     out = slice_sum[s0];
     for (uint32_t s = s0 + step; s < s1; s += step) {
         pt q = slice_sum[s];
-        pt_add(out, out, q);
+        pt_add<true>(out, out, q);
     }
 }
 
@@ -166,15 +169,15 @@ S256_HD void msm_segment_pair(pt &run, pt &sum, const pt *slice_sum, const uint3
     for (int j = hi - 1; j > lo; j--) {
         pt b;
         msm_bucket_from_slices(b, slice_sum, sl_off, base + (uint32_t)(j - 1));
-        pt_add(run, run, b);
-        pt_add(sum, sum, run);
+        pt_add<true>(run, run, b);
+        pt_add<true>(sum, sum, run);
     }
 }
 // v = sum + 2^log2w * s   (the position weight of a thread's / CTA's run total)
 S256_HD void msm_weigh(pt &v, const pt &sum, const pt &s, int log2w) {
     pt m = s;
-    for (int k = 0; k < log2w; k++) pt_double(m, m);
-    pt_add(v, sum, m);
+    for (int k = 0; k < log2w; k++) pt_double<true>(m, m);
+    pt_add<true>(v, sum, m);
 }
 
 // Horner over window results, highest first; window w is the sum of `parts` partials at win[w * stride ..]
@@ -183,10 +186,10 @@ S256_HD void msm_horner(pt &out, const pt *win, const msm_plan &p, int parts, in
     pt_set_identity(acc);
     for (int w = p.nwin - 1; w >= 0; w--) {
         if (w != p.nwin - 1)
-            for (int k = 0; k < p.c; k++) pt_double(acc, acc);
+            for (int k = 0; k < p.c; k++) pt_double<true>(acc, acc);
         for (int q = 0; q < parts; q++) {
             pt t = win[w * stride + q];
-            pt_add(acc, acc, t);
+            pt_add<true>(acc, acc, t);
         }
     }
     out = acc;

@@ -6,8 +6,12 @@
 // (0 : 1 : 0) (point.go:42-49).  Multiplications by b3 go through
 // fe_mul_small (8 MAC32 instead of 73).  Only affine values are observable
 // (point_test.go:359-390), so temporaries / scheduling differ freely.
+// Each formula is a template over the field-operation set: <false> (default) is the constant-time
+// one, <true> the variable-time one of fe_vt.cuh for the paths that are variable time in the
+// reference as well (verification ladder, vartime MSM).
 #pragma once
 #include "fe.cuh"
+#include "fe_vt.cuh"
 
 namespace s256 {
 
@@ -44,41 +48,43 @@ S256_HD void fe_cneg(fe &r, const fe &a, uint32_t ctrl) {
 }
 
 // v = p + q, complete (12 M + 2 m3b + 19 a).
+template <bool VT = false>
 S256_HD void pt_add(pt &v, const pt &p, const pt &q) {
+    typedef fe_ops<VT> F;
     fe t0, t1, t2, t3, t4, x3, y3, z3;
-    fe_mul(t0, p.x, q.x);
-    fe_mul(t1, p.y, q.y);
-    fe_mul(t2, p.z, q.z);
-    fe_add(t3, p.x, p.y);
-    fe_add(t4, q.x, q.y);
-    fe_mul(t3, t3, t4);
-    fe_add(t4, t0, t1);
-    fe_sub(t3, t3, t4);
-    fe_add(t4, p.y, p.z);
-    fe_add(x3, q.y, q.z);
-    fe_mul(t4, t4, x3);
-    fe_add(x3, t1, t2);
-    fe_sub(t4, t4, x3);
-    fe_add(x3, p.x, p.z);
-    fe_add(y3, q.x, q.z);
-    fe_mul(x3, x3, y3);
-    fe_add(y3, t0, t2);
-    fe_sub(y3, x3, y3);
-    fe_add(x3, t0, t0);
-    fe_add(t0, x3, t0);
-    fe_mul_small(t2, t2, S256_B3);
-    fe_add(z3, t1, t2);
-    fe_sub(t1, t1, t2);
-    fe_mul_small(y3, y3, S256_B3);
-    fe_mul(x3, t4, y3);
-    fe_mul(t2, t3, t1);
-    fe_sub(x3, t2, x3);
-    fe_mul(y3, y3, t0);
-    fe_mul(t1, t1, z3);
-    fe_add(y3, t1, y3);
-    fe_mul(t0, t0, t3);
-    fe_mul(z3, z3, t4);
-    fe_add(z3, z3, t0);
+    F::mul(t0, p.x, q.x);
+    F::mul(t1, p.y, q.y);
+    F::mul(t2, p.z, q.z);
+    F::add(t3, p.x, p.y);
+    F::add(t4, q.x, q.y);
+    F::mul(t3, t3, t4);
+    F::add(t4, t0, t1);
+    F::sub(t3, t3, t4);
+    F::add(t4, p.y, p.z);
+    F::add(x3, q.y, q.z);
+    F::mul(t4, t4, x3);
+    F::add(x3, t1, t2);
+    F::sub(t4, t4, x3);
+    F::add(x3, p.x, p.z);
+    F::add(y3, q.x, q.z);
+    F::mul(x3, x3, y3);
+    F::add(y3, t0, t2);
+    F::sub(y3, x3, y3);
+    F::add(x3, t0, t0);
+    F::add(t0, x3, t0);
+    F::mul_small(t2, t2, S256_B3);
+    F::add(z3, t1, t2);
+    F::sub(t1, t1, t2);
+    F::mul_small(y3, y3, S256_B3);
+    F::mul(x3, t4, y3);
+    F::mul(t2, t3, t1);
+    F::sub(x3, t2, x3);
+    F::mul(y3, y3, t0);
+    F::mul(t1, t1, z3);
+    F::add(y3, t1, y3);
+    F::mul(t0, t0, t3);
+    F::mul(z3, z3, t4);
+    F::add(z3, z3, t0);
     v.x = x3;
     v.y = y3;
     v.z = z3;
@@ -86,67 +92,64 @@ S256_HD void pt_add(pt &v, const pt &p, const pt &q) {
 
 // v = p + (x2, y2, 1); complete for every p, addend must not be the identity
 // (11 M + 2 m3b + 13 a).
+template <bool VT = false>
 S256_HD void pt_add_mixed(pt &v, const pt &p, const fe &x2, const fe &y2) {
+    typedef fe_ops<VT> F;
     fe t0, t1, t2, t3, t4, x3, y3, z3;
-    fe_mul(t0, p.x, x2);
-    fe_mul(t1, p.y, y2);
-    fe_add(t3, x2, y2);
-    fe_add(t4, p.x, p.y);
-    fe_mul(t3, t3, t4);
-    fe_add(t4, t0, t1);
-    fe_sub(t3, t3, t4);
-    fe_mul(t4, y2, p.z);
-    fe_add(t4, t4, p.y);
-    fe_mul(y3, x2, p.z);
-    fe_add(y3, y3, p.x);
-    fe_add(x3, t0, t0);
-    fe_add(t0, x3, t0);
-    fe_mul_small(t2, p.z, S256_B3);
-    fe_add(z3, t1, t2);
-    fe_sub(t1, t1, t2);
-    fe_mul_small(y3, y3, S256_B3);
-    fe_mul(x3, t4, y3);
-    fe_mul(t2, t3, t1);
-    fe_sub(x3, t2, x3);
-    fe_mul(y3, y3, t0);
-    fe_mul(t1, t1, z3);
-    fe_add(y3, t1, y3);
-    fe_mul(t0, t0, t3);
-    fe_mul(z3, z3, t4);
-    fe_add(z3, z3, t0);
+    F::mul(t0, p.x, x2);
+    F::mul(t1, p.y, y2);
+    F::add(t3, x2, y2);
+    F::add(t4, p.x, p.y);
+    F::mul(t3, t3, t4);
+    F::add(t4, t0, t1);
+    F::sub(t3, t3, t4);
+    F::mul(t4, y2, p.z);
+    F::add(t4, t4, p.y);
+    F::mul(y3, x2, p.z);
+    F::add(y3, y3, p.x);
+    F::add(x3, t0, t0);
+    F::add(t0, x3, t0);
+    F::mul_small(t2, p.z, S256_B3);
+    F::add(z3, t1, t2);
+    F::sub(t1, t1, t2);
+    F::mul_small(y3, y3, S256_B3);
+    F::mul(x3, t4, y3);
+    F::mul(t2, t3, t1);
+    F::sub(x3, t2, x3);
+    F::mul(y3, y3, t0);
+    F::mul(t1, t1, z3);
+    F::add(y3, t1, y3);
+    F::mul(t0, t0, t3);
+    F::mul(z3, z3, t4);
+    F::add(z3, z3, t0);
     v.x = x3;
     v.y = y3;
     v.z = z3;
 }
 
 // v = 2p, complete (6 M + 2 S + 1 m3b + 9 a).
-#if defined(S256_DBL_INLINE) && S256_PTX
-#define S256_DMUL fe_mul_inline
-#define S256_DSQR fe_sqr_inline
-#else
-#define S256_DMUL fe_mul
-#define S256_DSQR fe_sqr
-#endif
+template <bool VT = false>
 S256_HD void pt_double(pt &v, const pt &p) {
+    typedef fe_ops<VT> F;
     fe t0, t1, t2, x3, y3, z3;
-    S256_DSQR(t0, p.y);
-    fe_add(z3, t0, t0);
-    fe_add(z3, z3, z3);
-    fe_add(z3, z3, z3);
-    S256_DMUL(t1, p.y, p.z);
-    S256_DSQR(t2, p.z);
-    fe_mul_small(t2, t2, S256_B3);
-    S256_DMUL(x3, t2, z3);
-    fe_add(y3, t0, t2);
-    S256_DMUL(z3, t1, z3);
-    fe_add(t1, t2, t2);
-    fe_add(t2, t1, t2);
-    fe_sub(t0, t0, t2);
-    S256_DMUL(y3, t0, y3);
-    fe_add(y3, x3, y3);
-    S256_DMUL(t1, p.x, p.y);
-    S256_DMUL(x3, t0, t1);
-    fe_add(x3, x3, x3);
+    F::sqr(t0, p.y);
+    F::add(z3, t0, t0);
+    F::add(z3, z3, z3);
+    F::add(z3, z3, z3);
+    F::mul(t1, p.y, p.z);
+    F::sqr(t2, p.z);
+    F::mul_small(t2, t2, S256_B3);
+    F::mul(x3, t2, z3);
+    F::add(y3, t0, t2);
+    F::mul(z3, t1, z3);
+    F::add(t1, t2, t2);
+    F::add(t2, t1, t2);
+    F::sub(t0, t0, t2);
+    F::mul(y3, t0, y3);
+    F::add(y3, x3, y3);
+    F::mul(t1, p.x, p.y);
+    F::mul(x3, t0, t1);
+    F::add(x3, x3, x3);
     v.x = x3;
     v.y = y3;
     v.z = z3;

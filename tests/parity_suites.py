@@ -36,11 +36,43 @@ def check_field_ops(be, rng_seed=7, n=256):
     # worst cases for the folds: products / sums that land just below 2^256
     A += [2**256 - 1] * 4 + [P - 1, P - 1]
     B += [2**256 - 1, P, P - 1, 2, P - 1, 2]
+    # rare carry paths of the folds (fe.cuh / fe_vt.cuh): after the first pass the low limbs are
+    # ff..f0 | ffffffff | ffffffff, so adding delta = 2^32 + 977 ripples past limb 2 (shallow: stops
+    # at limb 3; deep: runs off the top and wraps a second time); likewise for borrows
+    D = 2**32 + 977
+    X3 = 2**96 - 16
+    A += [P - 1, 2**256 - 1, 2**256 - 2, 1, 1, 7 * 2**96 + 5]
+    B += [X3 + D + 1, 2**96, 2**256 - 1, 2**256 + 1 - (7 * 2**96 + 5), 2**256 - 4, 2**256 - 3]
+    for r in range(21):  # a * 21 = 2^256 + t, t = X3 + r * 2^96: the top fold of mul_small ripples past limb 2
+        if (2**256 + X3 + r * 2**96) % 21 == 0:
+            A.append((2**256 + X3 + r * 2**96) // 21)
+            B.append(3)
+            break
+    # a * b whose once-folded value lo + hi * delta equals 2^256 + t with t = X3 + (random high limbs):
+    # the top fold of the multiplication ripples past limb 2
+    made = 0
+    for trial in range(200):
+        t = X3 + (int.from_bytes(rng.bytes(1), "big") << 96)
+        a_ = int.from_bytes(rng.bytes(10), "big") | (1 << 79) | 1
+        hi = (-(2**256 + t) * pow(P, -1, a_)) % a_      # makes hi * p + 2^256 + t divisible by a_
+        if hi * D <= t:
+            continue
+        prod = hi * P + 2**256 + t                        # = hi * 2^256 + lo with lo + hi * delta = 2^256 + t
+        if prod % a_:
+            continue
+        b_ = prod // a_
+        if b_ < 2**256 and (prod % 2**256) + (prod >> 256) * D == 2**256 + t:
+            A.append(a_); B.append(b_); made += 1
+            if made == 4:
+                break
+    assert made == 4
     a, b = rows([b32(x) for x in A], 32), rows([b32(x) for x in B], 32)
-    ops = [(0, lambda x, y: x * y % P), (1, lambda x, y: (x + y) % P), (2, lambda x, y: (x - y) % P),
-           (3, lambda x, y: pow(x % P, P - 2, P)), (5, lambda x, y: x * 21 % P), (6, lambda x, y: x * x % P),
-           (16, lambda x, y: (x % N) * (y % N) % N), (17, lambda x, y: (x % N + y % N) % N),
-           (18, lambda x, y: pow(x % N, N - 2, N))]
+    fe_ops = [(0, lambda x, y: x * y % P), (1, lambda x, y: (x + y) % P), (2, lambda x, y: (x - y) % P),
+              (5, lambda x, y: x * 21 % P), (6, lambda x, y: x * x % P)]
+    ops = fe_ops + [(8 + op, f) for op, f in fe_ops] + [
+        (3, lambda x, y: pow(x % P, P - 2, P)),
+        (16, lambda x, y: (x % N) * (y % N) % N), (17, lambda x, y: (x % N + y % N) % N),
+        (18, lambda x, y: pow(x % N, N - 2, N))]
     for op, f in ops:
         got = be.debug_field_op(op, a, b)
         for i, (x, y) in enumerate(zip(A, B)):
