@@ -293,6 +293,30 @@ def main():
             mac = pkg.mac32_per_item(key)
             other[name] = {"items_per_s": n / (ms * 1e-3), "ms": ms,
                            "frac_of_int_mul_peak": n / (ms * 1e-3) * mac / imad_peak if mac else None}
+        # the same calls end to end: pinned host buffers in AND out through the host-pointer entry points
+        eng_h = pkg.Engine(device=local, max_batch=n, pinned_outputs=True)
+        pin = lambda t_: t_.cpu().pin_memory().numpy()
+        h_priv, h_aux, h_pub, h_pkx, h_sig65, h_ssig = pin(d_priv), pin(d_aux), pin(pub), pin(pkx), pin(sig65), pin(ssig)
+
+        def wall(fn, reps=3):
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return (time.perf_counter() - t0) / reps * 1e3
+        for name, fn in (
+                ("schnorr_verify", lambda: eng_h.schnorr_verify(h_pkx, np_dg, h_ssig)),
+                ("ecdsa_recover", lambda: eng_h.ecdsa_recover(np_dg, h_sig65)),
+                ("ecdh", lambda: eng_h.ecdh(h_priv, h_pub)),
+                ("scalar_mult_ct", lambda: eng_h.scalar_mult(h_priv, h_pub)),
+                ("ecdsa_sign_rfc6979", lambda: eng_h.ecdsa_sign_rfc6979(h_priv, np_dg)),
+                ("schnorr_sign", lambda: eng_h.schnorr_sign(h_priv, np_dg, h_aux))):
+            ms = wall(fn)
+            other[name]["e2e_items_per_s"] = n / (ms * 1e-3)
+            other[name]["e2e_ms"] = ms
+        ms = wall(lambda: eng_h.scalar_base_mult(h_priv))
+        sbm["1048576_e2e"] = n / (ms * 1e-3)
+        eng_h.close()
 
     if rank == 0:
         mac_item = pkg.mac32_per_item("ecdsa_verify")

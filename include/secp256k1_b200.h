@@ -201,6 +201,13 @@ int s256_msm_partial(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, siz
                      uint8_t *partial96, uint8_t *status);
 int s256_msm_combine(s256_ctx *ctx, const uint8_t *partials96, size_t m, uint8_t *out65, uint8_t *status);
 
+/* --- page-locked host buffers.  The host-pointer entry points accept any memory, but copies from and
+ *     to pageable memory are staged by the driver at a fraction of the PCIe rate; batch buffers
+ *     allocated here (the cgo shim can wrap them as Go slices) move at full speed and let the
+ *     sub-chunk pipeline overlap them with the kernels.  NULL on failure. */
+void *s256_host_alloc(size_t bytes);
+void s256_host_free(void *p);
+
 /* --- measurement / debug hooks (not part of the reference surface) -------- */
 /* Regenerates multiples d * 2^(wbits*w) * G, d in [1, 2^wbits), w in [0, nwin)
  * as X||Y (64 B each), window-major: with wbits = 8, nwin = 32 this is byte for

@@ -42,7 +42,7 @@ EXPORTED_SYMBOLS = [
     "s256_msm", "s256_msm_partial", "s256_msm_combine", "s256_hash_to_curve", "s256_expand_message_xmd",
     "s256_debug_gen_table", "s256_debug_field_op", "s256_microbench_imad",
     "s256_microbench_variant", "s256_profile_enable", "s256_profile_read",
-    "s256_launch_count", "s256_mac32_per_item",
+    "s256_launch_count", "s256_mac32_per_item", "s256_host_alloc", "s256_host_free",
 ]
 
 _lib = None
@@ -78,6 +78,10 @@ def load_library():
     lib.s256_mac32_per_item.argtypes = [C.c_char_p]
     lib.s256_free.argtypes = [C.c_void_p]
     lib.s256_free.restype = None
+    lib.s256_host_alloc.restype = C.c_void_p
+    lib.s256_host_alloc.argtypes = [C.c_size_t]
+    lib.s256_host_free.argtypes = [C.c_void_p]
+    lib.s256_host_free.restype = None
     _lib = lib
     return lib
 
@@ -179,7 +183,12 @@ def _host(x, width):
 class Engine:
     """One context on one GPU (s256_init).  Use one Engine per process/GPU."""
 
-    def __init__(self, device=-1, max_batch=0):
+    def __init__(self, device=-1, max_batch=0, pinned_outputs=False):
+        """pinned_outputs=True: host results are returned as views into page-locked buffers owned by the
+        engine (s256_host_alloc) -- D2H at full PCIe speed instead of a staged copy into pageable
+        memory -- and stay valid only until the next call of the same method."""
+        self._pinned = bool(pinned_outputs)
+        self._pool = {}
         self._lib = load_library()
         self._ctx = C.c_void_p()
         rc = self._lib.s256_init(C.byref(self._ctx), int(device), C.c_size_t(max_batch))
@@ -189,6 +198,9 @@ class Engine:
 
     # -- plumbing -----------------------------------------------------------
     def close(self):
+        for ptr, _ in getattr(self, "_pool", {}).values():
+            self._lib.s256_host_free(C.c_void_p(ptr))
+        self._pool = {}
         if getattr(self, "_ctx", None) and self._ctx.value:
             self._lib.s256_free(self._ctx)
             self._ctx = C.c_void_p()
@@ -211,6 +223,34 @@ class Engine:
     @property
     def launch_count(self):
         return int(self._lib.s256_launch_count(self._ctx))
+
+    def _out(self, key, shape):
+        if isinstance(shape, int):
+            shape = (shape,)
+        if not self._pinned:
+            return np.zeros(shape, np.uint8)
+        size = int(np.prod(shape))
+        ent = self._pool.get(key)
+        if ent is None or ent[1] < size:
+            if ent is not None:
+                self._lib.s256_host_free(C.c_void_p(ent[0]))
+            cap = max(size, 1)
+            ptr = self._lib.s256_host_alloc(C.c_size_t(cap))
+            if not ptr:
+                raise S256Error("s256_host_alloc failed")
+            ent = (ptr, cap)
+            self._pool[key] = ent
+        arr = np.ctypeslib.as_array((C.c_uint8 * ent[1]).from_address(ent[0]))
+        return arr[:size].reshape(shape)
+
+    def pinned_empty(self, shape):
+        """A page-locked uint8 array for INPUT batches (freed with the engine)."""
+        self._pin_seq = getattr(self, "_pin_seq", 0) + 1
+        keep, self._pinned = self._pinned, True
+        try:
+            return self._out(("in", self._pin_seq), shape)
+        finally:
+            self._pinned = keep
 
     @staticmethod
     def _hp(a):
@@ -242,8 +282,8 @@ class Engine:
             return out, st
         k = _host(k32, 32)
         n = len(k)
-        out = np.zeros((n, 65), np.uint8)
-        st = np.zeros(n, np.uint8)
+        out = self._out(1, (n, 65))
+        st = self._out(2, n)
         self._check(self._lib.s256_scalar_base_mult(self._ctx, self._hp(k), C.c_size_t(n), self._hp(out), self._hp(st)),
                     "scalar_base_mult")
         return out, st
@@ -263,8 +303,8 @@ class Engine:
         n = len(k)
         if len(p) != n:
             raise ValueError("len(scalars) != len(points)")
-        out = np.zeros((n, 65), np.uint8)
-        st = np.zeros(n, np.uint8)
+        out = self._out(3, (n, 65))
+        st = self._out(4, n)
         self._check(self._lib.s256_scalar_mult(self._ctx, self._hp(k), self._hp(p), C.c_size_t(n), self._hp(out), self._hp(st)),
                     "scalar_mult")
         return out, st
@@ -283,8 +323,8 @@ class Engine:
         n = len(k)
         if len(p) != n:
             raise ValueError("len(scalars) != len(points)")
-        out = np.zeros((n, 32), np.uint8)
-        st = np.zeros(n, np.uint8)
+        out = self._out(5, (n, 32))
+        st = self._out(6, n)
         self._check(self._lib.s256_ecdh(self._ctx, self._hp(k), self._hp(p), C.c_size_t(n), self._hp(out), self._hp(st)), "ecdh")
         return out, st
 
@@ -292,8 +332,8 @@ class Engine:
     def point_decompress(self, pt33):
         p = _host(pt33, 33)
         n = len(p)
-        out = np.zeros((n, 65), np.uint8)
-        st = np.zeros(n, np.uint8)
+        out = self._out(7, (n, 65))
+        st = self._out(8, n)
         self._check(self._lib.s256_point_decompress(self._ctx, self._hp(p), C.c_size_t(n), self._hp(out), self._hp(st)),
                     "point_decompress")
         return out, st
@@ -304,14 +344,14 @@ class Engine:
         if enc_len is None:
             rows = [bytes(r) for r in enc]
             enc_len = np.array([len(r) if len(r) <= 65 else 0 for r in rows], np.uint8)
-            enc = np.zeros((len(rows), 65), np.uint8)
+            enc = self._out(9, (len(rows), 65))
             for i, r in enumerate(rows):
                 if len(r) <= 65:
                     enc[i, :len(r)] = np.frombuffer(r, np.uint8)
         e, ln = _host(enc, 65), _host(enc_len, 0).reshape(-1)
         n = len(e)
-        out = np.zeros((n, 65), np.uint8)
-        st = np.zeros(n, np.uint8)
+        out = self._out(10, (n, 65))
+        st = self._out(11, n)
         self._check(self._lib.s256_new_public_keys(self._ctx, self._hp(e), self._hp(ln), C.c_size_t(n), self._hp(out),
                                                    self._hp(st)), "new_public_keys")
         return out, st
@@ -319,8 +359,8 @@ class Engine:
     def parse_asn1_public_keys(self, rows):
         data, offs = _pack_rows(rows)
         n = len(rows)
-        out = np.zeros((n, 65), np.uint8)
-        st = np.zeros(n, np.uint8)
+        out = self._out(12, (n, 65))
+        st = self._out(13, n)
         self._check(self._lib.s256_parse_asn1_public_keys_checked(self._ctx, self._hp(data), offs.ctypes.data_as(C.c_void_p),
                                                                   C.c_size_t(n), self._hp(out), self._hp(st)),
                     "parse_asn1_public_keys")
@@ -341,8 +381,8 @@ class Engine:
         n = len(a1)
         if len(a2) != n or len(p) != n:
             raise ValueError("length mismatch")
-        out = np.zeros((n, 65), np.uint8)
-        st = np.zeros(n, np.uint8)
+        out = self._out(14, (n, 65))
+        st = self._out(15, n)
         self._check(self._lib.s256_double_scalar_mult_basepoint_vartime(
             self._ctx, self._hp(a1), self._hp(a2), self._hp(p), C.c_size_t(n), self._hp(out), self._hp(st)),
             "double_scalar_mult_basepoint_vartime")
@@ -362,7 +402,7 @@ class Engine:
         n = len(pk)
         if len(dg) != n or len(sg) != n:
             raise ValueError("length mismatch")
-        ok = np.zeros(n, np.uint8)
+        ok = self._out(16, n)
         self._check(self._lib.s256_ecdsa_verify(self._ctx, self._hp(pk), self._hp(dg), self._hp(sg), C.c_uint32(flags),
                                                 C.c_size_t(n), self._hp(ok)), "ecdsa_verify")
         return ok
@@ -374,7 +414,7 @@ class Engine:
         n = len(der_rows)
         if len(pk) != n or len(dg) != n:
             raise ValueError("length mismatch")
-        ok = np.zeros(n, np.uint8)
+        ok = self._out(17, n)
         self._check(self._lib.s256_ecdsa_verify_asn1(self._ctx, self._hp(pk), self._hp(dg), self._hp(data), self._hp(offs),
                                                      C.c_uint32(flags), C.c_size_t(n), self._hp(ok)), "ecdsa_verify_asn1")
         return ok
@@ -385,7 +425,7 @@ class Engine:
         n = len(der_rows_with_sighash)
         if len(pk) != n or len(dg) != n:
             raise ValueError("length mismatch")
-        ok = np.zeros(n, np.uint8)
+        ok = self._out(18, n)
         self._check(self._lib.s256_bitcoin_verify_asn1(self._ctx, self._hp(pk), self._hp(dg), self._hp(data), self._hp(offs),
                                                        C.c_size_t(n), self._hp(ok)), "bitcoin_verify_asn1")
         return ok
@@ -407,9 +447,9 @@ class Engine:
         n = len(d)
         if len(dg) != n:
             raise ValueError("length mismatch")
-        sig = np.zeros((n, 64), np.uint8)
-        rec = np.zeros(n, np.uint8)
-        st = np.zeros(n, np.uint8)
+        sig = self._out(19, (n, 64))
+        rec = self._out(20, n)
+        st = self._out(21, n)
         self._check(self._lib.s256_ecdsa_sign_rfc6979(self._ctx, self._hp(d), self._hp(dg), C.c_size_t(n), self._hp(sig),
                                                       self._hp(rec), self._hp(st)), "ecdsa_sign_rfc6979")
         return sig, rec, st
@@ -429,8 +469,8 @@ class Engine:
         n = len(dg)
         if len(sg) != n:
             raise ValueError("length mismatch")
-        out = np.zeros((n, 65), np.uint8)
-        st = np.zeros(n, np.uint8)
+        out = self._out(22, (n, 65))
+        st = self._out(23, n)
         self._check(self._lib.s256_ecdsa_recover(self._ctx, self._hp(dg), self._hp(sg), C.c_size_t(n), self._hp(out), self._hp(st)),
                     "ecdsa_recover")
         return out, st
@@ -451,7 +491,7 @@ class Engine:
         m = _host(msg, 0).reshape(n, -1) if n else np.zeros((0, 0), np.uint8)
         if len(sg) != n:
             raise ValueError("length mismatch")
-        ok = np.zeros(n, np.uint8)
+        ok = self._out(24, n)
         self._check(self._lib.s256_schnorr_verify(self._ctx, self._hp(pk), self._hp(m), C.c_size_t(m.shape[1] if n else 0),
                                                   self._hp(sg), C.c_size_t(n), self._hp(ok)), "schnorr_verify")
         return ok
@@ -473,8 +513,8 @@ class Engine:
         m = _host(msg, 0).reshape(n, -1) if n else np.zeros((0, 0), np.uint8)
         if len(ax) != n:
             raise ValueError("length mismatch")
-        sig = np.zeros((n, 64), np.uint8)
-        st = np.zeros(n, np.uint8)
+        sig = self._out(25, (n, 64))
+        st = self._out(26, n)
         self._check(self._lib.s256_schnorr_sign(self._ctx, self._hp(d), self._hp(m), C.c_size_t(m.shape[1] if n else 0),
                                                 self._hp(ax), C.c_size_t(n), self._hp(sig), self._hp(st)), "schnorr_sign")
         return sig, st
@@ -487,8 +527,8 @@ class Engine:
         if m.ndim != 2:
             raise ValueError("msgs must be a 2-D array of equal-length rows")
         n, msg_len = m.shape
-        out = np.zeros((n, 65), np.uint8)
-        st = np.zeros(n, np.uint8)
+        out = self._out(27, (n, 65))
+        st = self._out(28, n)
         self._check(self._lib.s256_hash_to_curve(self._ctx, dst, C.c_size_t(len(dst)), self._hp(m), C.c_size_t(msg_len),
                                                  C.c_size_t(n), int(bool(random_oracle)), self._hp(out), self._hp(st)),
                     "hash_to_curve")
@@ -498,7 +538,7 @@ class Engine:
         dst = bytes(dst)
         m = np.ascontiguousarray(msgs, dtype=np.uint8)
         n, msg_len = m.shape
-        out = np.zeros((n, length), np.uint8)
+        out = self._out(29, (n, length))
         self._check(self._lib.s256_expand_message_xmd(self._ctx, dst, C.c_size_t(len(dst)), self._hp(m), C.c_size_t(msg_len),
                                                       C.c_size_t(n), C.c_size_t(length), self._hp(out)), "expand_message_xmd")
         return out
@@ -510,7 +550,7 @@ class Engine:
         if len(p) != n:
             # the reference panics: point_mul_multi.go:27-29
             raise ValueError("secp256k1: len(scalars) != len(points)")
-        out = np.zeros(65, np.uint8)
+        out = self._out(30, 65)
         st = C.c_uint8(0)
         self._check(self._lib.s256_msm(self._ctx, self._hp(k), self._hp(p), C.c_size_t(n), int(vartime), self._hp(out),
                                        C.byref(st)), "msm")
@@ -521,7 +561,7 @@ class Engine:
         n = len(k)
         if len(p) != n:
             raise ValueError("secp256k1: len(scalars) != len(points)")
-        out = np.zeros(96, np.uint8)
+        out = self._out(31, 96)
         st = C.c_uint8(0)
         self._check(self._lib.s256_msm_partial(self._ctx, self._hp(k), self._hp(p), C.c_size_t(n), int(vartime),
                                                self._hp(out), C.byref(st)), "msm_partial")
@@ -529,7 +569,7 @@ class Engine:
 
     def msm_combine(self, partials96):
         p = _host(partials96, 96)
-        out = np.zeros(65, np.uint8)
+        out = self._out(32, 65)
         st = C.c_uint8(0)
         self._check(self._lib.s256_msm_combine(self._ctx, self._hp(p), C.c_size_t(len(p)), self._hp(out), C.byref(st)),
                     "msm_combine")
@@ -537,13 +577,13 @@ class Engine:
 
     # -- measurement / debug ----------------------------------------------------
     def debug_gen_table(self, wbits, nwin):
-        out = np.zeros(((2 ** wbits - 1) * nwin, 64), np.uint8)
+        out = self._out(33, ((2 ** wbits - 1) * nwin, 64))
         self._check(self._lib.s256_debug_gen_table(self._ctx, int(wbits), int(nwin), self._hp(out)), "debug_gen_table")
         return out
 
     def debug_field_op(self, op, a32, b32):
         a, b = _host(a32, 32), _host(b32, 32)
-        out = np.zeros((len(a), 32), np.uint8)
+        out = self._out(34, (len(a), 32))
         self._check(self._lib.s256_debug_field_op(self._ctx, int(op), self._hp(a), self._hp(b), C.c_size_t(len(a)),
                                                   self._hp(out)), "debug_field_op")
         return out

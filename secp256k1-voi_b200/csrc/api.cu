@@ -256,6 +256,19 @@ __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a3
     }
 }
 
+// page-locked host memory for callers that want full-speed copies (cudaHostAllocPortable: any device)
+extern "C" void *s256_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void s256_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" const char *s256_strerror(int code) {
     switch (code) {
         case S256_SUCCESS: return "success";
@@ -353,7 +366,7 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
             cudaFuncSetAttribute(k_scalar_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM_BYTES);
         cudaFuncSetAttribute(k_dsm_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM_BYTES);
         const char *pp = getenv("S256_PIPE_PARTS");
-        if (pp && atoi(pp) >= 1 && atoi(pp) <= 16) ctx->pipe_parts = atoi(pp);
+        if (pp && atoi(pp) >= 0 && atoi(pp) <= 16) ctx->pipe_parts = atoi(pp);
         const char *lad = getenv("S256_LADDER");
         ctx->use_reg_ladder = !(lad && std::string(lad) == "vm");  // register form is the faster one (profiles/)
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -639,7 +652,6 @@ extern "C" int s256_schnorr_verify(s256_ctx *ctx, const uint8_t *pkx, const uint
                                    const uint8_t *sig, size_t n, uint8_t *ok) {
     ENTER(ctx);
     if (n && (!pkx || (!msg && msg_len) || !sig || !ok)) return S256_ERR_ARG;
-    cudaStream_t s = ctx->stream;
     size_t need = (msg_len ? msg_len : 1) * (n < ctx->cap ? n : ctx->cap);
     if (need > ctx->in_b_bytes) {
         if (ctx->in_b) cudaFree(ctx->in_b);
@@ -648,14 +660,14 @@ extern "C" int s256_schnorr_verify(s256_ctx *ctx, const uint8_t *pkx, const uint
         CK(cudaMalloc(&ctx->in_b, need));
         ctx->in_b_bytes = need;
     }
-    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        CK(cudaMemcpyAsync(ctx->in_a, pkx + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
-        if (msg_len) CK(cudaMemcpyAsync(ctx->in_b, msg + msg_len * off, msg_len * c, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->in_c, sig + 64 * off, 64 * c, cudaMemcpyHostToDevice, s));
-        int r = chunk_schnorr_verify(ctx, view_at(ctx, 0), ctx->in_a, ctx->in_b, msg_len, ctx->in_c, c, ctx->st, s);
+    int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t ps) {
+        uint8_t *dmsg = ctx->in_b + msg_len * (size_t)(v.st - ctx->st);  // messages are msg_len apart, not 32
+        CK(cudaMemcpyAsync(v.in_a, pkx + 32 * off, 32 * c, cudaMemcpyHostToDevice, ps));
+        if (msg_len) CK(cudaMemcpyAsync(dmsg, msg + msg_len * off, msg_len * c, cudaMemcpyHostToDevice, ps));
+        CK(cudaMemcpyAsync(v.in_c, sig + 64 * off, 64 * c, cudaMemcpyHostToDevice, ps));
+        int r = chunk_schnorr_verify(ctx, v, v.in_a, dmsg, msg_len, v.in_c, c, v.st, ps);
         if (r != S256_SUCCESS) return r;
-        CK(cudaMemcpyAsync(ok + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
+        CK(cudaMemcpyAsync(ok + off, v.st, c, cudaMemcpyDeviceToHost, ps));
         return S256_SUCCESS;
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);

@@ -119,7 +119,6 @@ extern "C" int s256_schnorr_sign(s256_ctx *ctx, const uint8_t *priv32, const uin
                                  const uint8_t *aux32, size_t n, uint8_t *sig64, uint8_t *status) {
     ENTER(ctx);
     if (n && (!priv32 || (!msg && msg_len) || !aux32 || !sig64 || !status)) return S256_ERR_ARG;
-    cudaStream_t s = ctx->stream;
     size_t need = (msg_len ? msg_len : 1) * (n < ctx->cap ? n : ctx->cap);
     if (need > ctx->in_b_bytes) {
         if (ctx->in_b) cudaFree(ctx->in_b);
@@ -128,20 +127,18 @@ extern "C" int s256_schnorr_sign(s256_ctx *ctx, const uint8_t *priv32, const uin
         CK(cudaMalloc(&ctx->in_b, need));
         ctx->in_b_bytes = need;
     }
-    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        view v = view_at(ctx, 0);
-        CK(cudaMemcpyAsync(ctx->in_a, priv32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
-        if (msg_len) CK(cudaMemcpyAsync(ctx->in_b, msg + msg_len * off, msg_len * c, cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->in_c, aux32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+    int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t ps) {
+        uint8_t *dmsg = ctx->in_b + msg_len * (size_t)(v.st - ctx->st);  // messages are msg_len apart, not 32
+        CK(cudaMemcpyAsync(v.in_a, priv32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, ps));
+        if (msg_len) CK(cudaMemcpyAsync(dmsg, msg + msg_len * off, msg_len * c, cudaMemcpyHostToDevice, ps));
+        CK(cudaMemcpyAsync(v.in_c, aux32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, ps));
         uint8_t *d_sig = reinterpret_cast<uint8_t *>(v.aff);  // 64 B per item, unused by this path
-        int r = chunk_schnorr_sign(ctx, v, ctx->in_a, ctx->in_b, msg_len, ctx->in_c, c, d_sig, ctx->st, s);
+        int r = chunk_schnorr_sign(ctx, v, v.in_a, dmsg, msg_len, v.in_c, c, d_sig, v.st, ps);
         if (r != S256_SUCCESS) return r;
-        CK(cudaMemcpyAsync(sig64 + 64 * off, d_sig, 64 * c, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemsetAsync(ctx->in_a, 0, 32 * c, s));
-        CK(cudaStreamSynchronize(s));
+        CK(cudaMemcpyAsync(sig64 + 64 * off, d_sig, 64 * c, cudaMemcpyDeviceToHost, ps));
+        CK(cudaMemcpyAsync(status + off, v.st, c, cudaMemcpyDeviceToHost, ps));
+        CK(cudaMemsetAsync(v.in_a, 0, 32 * c, ps));  // wipe the staged private keys
         return S256_SUCCESS;
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
-

@@ -153,19 +153,36 @@ static int for_chunks(s256_ctx *ctx, size_t n, F body) {
 // Host-pointer calls: the chunk is cut into sub-chunks that alternate between two streams, each
 // doing its own H2D -> kernels -> D2H on a disjoint scratch window, so the copies of one sub-chunk
 // overlap the kernels of the other.  body(view, global offset, count, stream).
+// Default (pipe_parts == 1, "auto"): chunks of >= 2^18 items are cut at 1/16, 4/16 and 10/16 -- a small
+// first part so that the main kernel starts early, growing parts so that the copies and the short
+// latency-bound preparation kernels of part k+1 hide under the main kernel of part k, and a last part
+// small enough that its trailing D2H stays short.  S256_PIPE_PARTS=n > 1 forces n equal parts
+// (measured slower); S256_PIPE_PARTS=0 disables the split.
 template <typename F>
 static int pipelined(s256_ctx *ctx, size_t n, F body) {
     const size_t min_sub = 65536;
     for (size_t off = 0; off < n; off += ctx->cap) {
         size_t c = n - off < ctx->cap ? n - off : ctx->cap;
-        size_t parts = c / min_sub;
-        if (parts > (size_t)ctx->pipe_parts) parts = (size_t)ctx->pipe_parts;
-        if (parts < 1) parts = 1;
-        size_t sub = (c + parts - 1) / parts;
-        sub = (sub + 127) & ~(size_t)127;
-        int k = 0;
-        for (size_t so = 0; so < c; so += sub, k++) {
-            size_t sc_ = c - so < sub ? c - so : sub;
+        size_t cut[17];
+        int np = 1;
+        cut[0] = 0;
+        if (ctx->pipe_parts == 1 && c >= ((size_t)1 << 18)) {
+            np = 4;
+            cut[1] = (c / 16 + 127) & ~(size_t)127;
+            cut[2] = (c / 4 + 127) & ~(size_t)127;
+            cut[3] = (c / 8 * 5 + 127) & ~(size_t)127;
+        } else if (ctx->pipe_parts > 1) {
+            size_t parts = c / min_sub;
+            if (parts > (size_t)ctx->pipe_parts) parts = (size_t)ctx->pipe_parts;
+            if (parts < 1) parts = 1;
+            size_t sub = (c + parts - 1) / parts;
+            sub = (sub + 127) & ~(size_t)127;
+            np = 0;
+            for (size_t so = 0; so < c; so += sub) cut[np++] = so;
+        }
+        cut[np] = c;
+        for (int k = 0; k < np; k++) {
+            size_t so = cut[k], sc_ = cut[k + 1] - cut[k];
             int rc = body(view_at(ctx, so), off + so, sc_, (k & 1) ? ctx->stream2 : ctx->stream);
             if (rc != S256_SUCCESS) return rc;
         }

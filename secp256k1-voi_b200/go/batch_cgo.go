@@ -208,6 +208,24 @@ func (e *Engine) ECDHBatch(k32, pt65 []byte) (x32 []byte, status []byte, err err
 	return
 }
 
+// PinnedBytes returns a page-locked byte slice of length n for batch inputs / outputs: copies from and to
+// such memory run at PCIe speed and overlap the kernels, while ordinary Go heap memory is staged by the
+// driver.  The slice is C memory (not moved or freed by the Go GC); release it with FreePinned.
+func PinnedBytes(n int) []byte {
+	p := C.s256_host_alloc(C.size_t(n))
+	if p == nil {
+		return nil
+	}
+	return unsafe.Slice((*byte)(p), n)
+}
+
+// FreePinned releases a slice obtained from PinnedBytes.
+func FreePinned(b []byte) {
+	if len(b) > 0 {
+		C.s256_host_free(unsafe.Pointer(&b[0]))
+	}
+}
+
 // packRows concatenates variable-length rows and returns the n + 1 offsets the C ABI expects.
 func packRows(rows [][]byte) ([]byte, []C.size_t) {
 	offs := make([]C.size_t, len(rows)+1)
