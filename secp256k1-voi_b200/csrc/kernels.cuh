@@ -796,39 +796,51 @@ S256_HD uint8_t item_rfc6979_nonce(uint8_t kout[32], const uint8_t *priv32, cons
     sc d, e;
     uint32_t d_ok = (1u - sc_from_be32(d, priv32)) & (1u - sc_is_zero(d));
     sc_from_be32(e, digest32);
-    uint8_t m[97], K[32], V[32];
-    for (int i = 0; i < 32; i++) {
-        V[i] = 0x01;
-        K[i] = 0x00;
+    // K, V, int2octets(x) and bits2octets(h) as big-endian words (ecdsa_k_rfc6979.go:108-145)
+    uint32_t K[8], V[8], xw[8], hw[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        V[i] = 0x01010101u;
+        K[i] = 0;
+        xw[i] = d.v[7 - i];
+        hw[i] = e.v[7 - i];
     }
-    uint8_t xb[32], hb[32];
-    sc_to_be32(xb, d);
-    sc_to_be32(hb, e);
-    for (int oct = 0; oct < 2; oct++) {
-        for (int i = 0; i < 32; i++) {
-            m[i] = V[i];
-            m[33 + i] = xb[i];
-            m[65 + i] = hb[i];
-        }
-        m[32] = (uint8_t)oct;
-        hmac_sha256_k32(K, K, m, 97);
-        hmac_sha256_k32(V, K, V, 32);
+    for (uint32_t oct = 0; oct < 2; oct++) {
+        hmac_k32_m97(K, K, V, oct, xw, hw);
+        hmac_k32_m32(V, K, V);
     }
     uint32_t ok = 0;
+    sc k;
     for (int attempt = 0; attempt < 8 && !ok; attempt++) {
-        if (attempt) {
-            for (int i = 0; i < 32; i++) m[i] = V[i];
+        if (attempt) {  // out-of-range candidate (probability 2^-128): K = HMAC(K, V || 00), byte-stream form
+            uint8_t m[33], Kb[32], Vb[32];
+            for (int i = 0; i < 8; i++)
+                for (int b = 0; b < 4; b++) {
+                    m[4 * i + b] = Vb[4 * i + b] = (uint8_t)(V[i] >> (24 - 8 * b));
+                    Kb[4 * i + b] = (uint8_t)(K[i] >> (24 - 8 * b));
+                }
             m[32] = 0x00;
-            hmac_sha256_k32(K, K, m, 33);
-            hmac_sha256_k32(V, K, V, 32);
+            hmac_sha256_k32(Kb, Kb, m, 33);
+            for (int i = 0; i < 8; i++)
+                K[i] = ((uint32_t)Kb[4 * i] << 24) | ((uint32_t)Kb[4 * i + 1] << 16) | ((uint32_t)Kb[4 * i + 2] << 8) | Kb[4 * i + 3];
+            hmac_k32_m32(V, K, V);
         }
-        hmac_sha256_k32(V, K, V, 32);
-        sc k;
-        ok = (1u - sc_from_be32(k, V)) & (1u - sc_is_zero(k));
+        hmac_k32_m32(V, K, V);
+        uint32_t l[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) l[i] = V[7 - i];
+        ok = (1u - sc_reduce_once(k, l, 0)) & (1u - sc_is_zero(k));
     }
     // an invalid key still runs the pipeline on a harmless nonce (k = 1)
     uint32_t good = ok & d_ok;
-    for (int i = 0; i < 32; i++) kout[i] = good ? V[i] : (uint8_t)(i == 31);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t wv = good ? V[i] : (uint32_t)(i == 7);
+        kout[4 * i] = (uint8_t)(wv >> 24);
+        kout[4 * i + 1] = (uint8_t)(wv >> 16);
+        kout[4 * i + 2] = (uint8_t)(wv >> 8);
+        kout[4 * i + 3] = (uint8_t)wv;
+    }
     return (uint8_t)good;
 }
 

@@ -26,14 +26,8 @@ S256_HD uint32_t sha_k(int i) {
     return K[i];
 }
 
-// one compression; w[16] is consumed (used as the rolling schedule).  Out of line on the device: the
-// 64 unrolled rounds are instantiated once instead of at every call site (HMAC reaches it ~90 times).
-#if defined(__CUDACC__)
-static __host__ __device__ __noinline__
-#else
-inline
-#endif
-void sha256_compress(uint32_t h[8], uint32_t w[16]) {
+// one compression; w[16] is consumed (used as the rolling schedule)
+S256_HD void sha256_rounds(uint32_t h[8], uint32_t w[16]) {
     uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
 #pragma unroll
     for (int i = 0; i < 64; i++) {
@@ -53,6 +47,30 @@ void sha256_compress(uint32_t h[8], uint32_t w[16]) {
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
+#if defined(__CUDA_ARCH__)
+// Out of line on the device: the 64 unrolled rounds are instantiated once instead of at every call
+// site (HMAC reaches them ~90 times).  State and block travel BY VALUE, i.e. in registers: pointer
+// arguments would pin both arrays to the local-memory stack of every caller.
+struct sha_regs_h { uint32_t v[8]; };
+struct sha_regs_w { uint32_t v[16]; };
+static __device__ __noinline__ sha_regs_h sha256_compress_call(sha_regs_h h, sha_regs_w w) {
+    sha256_rounds(h.v, w.v);
+    return h;
+}
+__device__ __forceinline__ void sha256_compress(uint32_t h[8], uint32_t w[16]) {
+    sha_regs_h hs;
+    sha_regs_w ws;
+#pragma unroll
+    for (int i = 0; i < 8; i++) hs.v[i] = h[i];
+#pragma unroll
+    for (int i = 0; i < 16; i++) ws.v[i] = w[i];
+    hs = sha256_compress_call(hs, ws);
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = hs.v[i];
+}
+#else
+inline void sha256_compress(uint32_t h[8], uint32_t w[16]) { sha256_rounds(h, w); }
+#endif
 
 // out32 = BIP-340 challenge hash of (r32 || px32 || msg[0..msg_len))
 S256_HD void bip340_challenge(uint8_t out32[32], const uint8_t *r32, const uint8_t *px32, const uint8_t *msg,
@@ -165,6 +183,74 @@ void hmac_sha256_k32(uint8_t out[32], const uint8_t key[32], const uint8_t *msg,
     sha_update(c, pad, 64);
     sha_update(c, inner, 32);
     sha_final(c, out);
+}
+
+// Word-oriented HMAC-SHA256 for the two fixed message layouts of the RFC 6979 generator
+// (secec/ecdsa_k_rfc6979.go:49-145): a 32-byte key, and as message either V (32 bytes) or
+// V || oct || x || h (97 bytes).  Everything stays in 32-bit big-endian words in registers; the byte-stream
+// form above costs ~3x as many instructions on its per-byte buffer handling.
+S256_HD void sha_iv(uint32_t h[8]) {
+    h[0] = 0x6a09e667u; h[1] = 0xbb67ae85u; h[2] = 0x3c6ef372u; h[3] = 0xa54ff53au;
+    h[4] = 0x510e527fu; h[5] = 0x9b05688cu; h[6] = 0x1f83d9abu; h[7] = 0x5be0cd19u;
+}
+// state after the one-block key pad (key ^ pad byte repeated)
+S256_HD void hmac_pad_state(uint32_t st[8], const uint32_t key[8], uint32_t pad) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        w[i] = key[i] ^ pad;
+        w[8 + i] = pad;
+    }
+    sha_iv(st);
+    sha256_compress(st, w);
+}
+// out = H(opad block || inner digest): the outer half of every HMAC
+S256_HD void hmac_outer(uint32_t out[8], const uint32_t key[8], const uint32_t inner[8]) {
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = inner[i];
+    w[8] = 0x80000000u;
+#pragma unroll
+    for (int i = 9; i < 15; i++) w[i] = 0;
+    w[15] = (64 + 32) * 8;
+    hmac_pad_state(out, key, 0x5c5c5c5cu);
+    sha256_compress(out, w);
+}
+// out = HMAC(key, v), |v| = 32.  out may alias key or v.
+S256_HD void hmac_k32_m32(uint32_t out[8], const uint32_t key[8], const uint32_t v[8]) {
+    uint32_t st[8], w[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = v[i];
+    w[8] = 0x80000000u;
+#pragma unroll
+    for (int i = 9; i < 15; i++) w[i] = 0;
+    w[15] = (64 + 32) * 8;
+    hmac_pad_state(st, key, 0x36363636u);
+    sha256_compress(st, w);
+    hmac_outer(out, key, st);
+}
+// out = HMAC(key, v || oct || x || h), 32 + 1 + 32 + 32 bytes.  out may alias key.
+S256_HD void hmac_k32_m97(uint32_t out[8], const uint32_t key[8], const uint32_t v[8], uint32_t oct, const uint32_t x[8],
+                          const uint32_t h[8]) {
+    uint32_t st[8], w[16];
+    hmac_pad_state(st, key, 0x36363636u);
+    // bytes 0..63: v, then oct and the first 31 bytes of x (everything after v is shifted by one byte)
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = v[i];
+    w[8] = (oct << 24) | (x[0] >> 8);
+#pragma unroll
+    for (int i = 1; i < 8; i++) w[8 + i] = (x[i - 1] << 24) | (x[i] >> 8);
+    sha256_compress(st, w);
+    // bytes 64..96: last byte of x, h; then the 0x80 pad, zeros and the bit length of 64 + 97 bytes
+    w[0] = (x[7] << 24) | (h[0] >> 8);
+#pragma unroll
+    for (int i = 1; i < 8; i++) w[i] = (h[i - 1] << 24) | (h[i] >> 8);
+    w[8] = (h[7] << 24) | 0x00800000u;
+#pragma unroll
+    for (int i = 9; i < 15; i++) w[i] = 0;
+    w[15] = (64 + 97) * 8;
+    sha256_compress(st, w);
+    hmac_outer(out, key, st);
 }
 
 // BIP-340 tagged hashes (secec/bitcoin/schnorr.go:34-36, 309-320): the state after the 64-byte

@@ -177,6 +177,26 @@ def test_host_pipeline_chunk_shapes(s256):
         eng.close()
 
 
+def test_pinned_buffers(s256, oracle):
+    """s256_host_alloc: page-locked inputs and engine-owned page-locked results give the same bytes as the
+    pageable path; a result view is only reused by the next call of the same method."""
+    eng = s256.Engine(device=0, max_batch=4096, pinned_outputs=True)
+    try:
+        ks = ps.synth.base_mult_scalars(3000)
+        pk = eng.pinned_empty((3000, 32))
+        pk[:] = ks
+        out, st = eng.scalar_base_mult(pk)
+        exp, est = oracle.batch_scalar_base_mult(ks)
+        assert np.array_equal(out, exp) and np.array_equal(st, est)
+        keep = out.copy()
+        out2, _ = eng.scalar_base_mult(pk[:100])
+        assert np.array_equal(out2, keep[:100])
+        x, xst = eng.ecdh(pk[8:3000], keep[8:3000])   # another method: its own buffers
+        assert np.array_equal(out2, keep[:100]) and (xst == 1).all()
+    finally:
+        eng.close()
+
+
 def torch_cuda(a):
     import torch
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
