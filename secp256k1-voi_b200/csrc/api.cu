@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a3
             case 10: fe_sub_vt(r, a, b); break;
             case 13: fe_mul_small_vt(r, a, 21u); break;
             case 14: fe_sqr_vt(r, a); break;
+            case 15: fe_mul8_vt(r, a); break;
             default: r = fe_zero();
         }
         fe_normalize(r, r);

@@ -133,9 +133,7 @@ S256_HD void pt_double(pt &v, const pt &p) {
     typedef fe_ops<VT> F;
     fe t0, t1, t2, x3, y3, z3;
     F::sqr(t0, p.y);
-    F::add(z3, t0, t0);
-    F::add(z3, z3, z3);
-    F::add(z3, z3, z3);
+    F::mul8(z3, t0);
     F::mul(t1, p.y, p.z);
     F::sqr(t2, p.z);
     F::mul_small(t2, t2, S256_B3);

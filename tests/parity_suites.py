@@ -69,7 +69,11 @@ def check_field_ops(be, rng_seed=7, n=256):
     a, b = rows([b32(x) for x in A], 32), rows([b32(x) for x in B], 32)
     fe_ops = [(0, lambda x, y: x * y % P), (1, lambda x, y: (x + y) % P), (2, lambda x, y: (x - y) % P),
               (5, lambda x, y: x * 21 % P), (6, lambda x, y: x * x % P)]
-    ops = fe_ops + [(8 + op, f) for op, f in fe_ops] + [
+    # 8a: the bits shifted out fold back as (a >> 253) * delta; inputs chosen so that the fold ripples
+    A += [2**256 - 1, (7 << 253) | (2**93 - 1 << 0), (1 << 253) | (2**93 - 2)]
+    B += [0, 0, 0]
+    a, b = rows([b32(x) for x in A], 32), rows([b32(x) for x in B], 32)
+    ops = fe_ops + [(8 + op, f) for op, f in fe_ops] + [(15, lambda x, y: x * 8 % P)] + [
         (3, lambda x, y: pow(x % P, P - 2, P)),
         (16, lambda x, y: (x % N) * (y % N) % N), (17, lambda x, y: (x % N + y % N) % N),
         (18, lambda x, y: pow(x % N, N - 2, N))]
