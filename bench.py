@@ -157,6 +157,9 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch-log2", type=int, default=BATCH_LOG2)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true",
+                    help="only the device-resident headline steps (for the ncu launch list in profiles/): "
+                         "no end-to-end leg, no other paths")
     args = ap.parse_args()
     if args.impl == "reference":
         return cpu_reference_arm(args)
@@ -232,21 +235,23 @@ def main():
 
     # ---- end to end through the C ABI with host buffers --------------------------
     np_pk, np_dg, np_sg = h_pk.numpy(), h_dg.numpy(), h_sg.numpy()
-    for _ in range(2):
-        ok_h = eng.ecdsa_verify(np_pk, np_dg, np_sg)
-    barrier(); torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ok_h = eng.ecdsa_verify(np_pk, np_dg, np_sg)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    assert np.array_equal(ok_h, expected)
-    e2e_value = n * world * args.steps / e2e_s
+    e2e_value = None
+    if not args.headline_only:
+        for _ in range(2):
+            ok_h = eng.ecdsa_verify(np_pk, np_dg, np_sg)
+        barrier(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ok_h = eng.ecdsa_verify(np_pk, np_dg, np_sg)
+        torch.cuda.synchronize()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        assert np.array_equal(ok_h, expected)
+        e2e_value = n * world * args.steps / e2e_s
 
     # ---- ScalarBaseMult ops/s (BASELINE configs[0] and at 2^20) -------------------
     sbm = {}
-    for nn in (4096, n):
+    for nn in (() if args.headline_only else (4096, n)):
         ks = torch.from_numpy(pkg.synth.base_mult_scalars(nn)).cuda()
         for _ in range(3):
             eng.scalar_base_mult(ks)
@@ -261,7 +266,7 @@ def main():
 
     # ---- the other hot-path entry points at the same batch size (device-resident, rank 0 only) ----
     other = {}
-    if rank == 0:
+    if rank == 0 and not args.headline_only:
         def timed(fn, reps=3):
             fn(); torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -21,4 +21,21 @@ for n in (1, 33, 1500):
         eng.msm(we["k32"], we["pt65"], vartime=vt)
     comp = np.concatenate([2 + (we["pt65"][:, 64:] & 1), we["pt65"][:, 1:33]], axis=1)
     eng.point_decompress(comp)
+    priv = ks.copy(); priv[:, 0] &= 0x7F; priv[:, 31] |= 1
+    sig, rec, st = eng.ecdsa_sign_rfc6979(priv, w["digest32"])
+    eng.schnorr_sign(priv, w["digest32"], ks)
+    eng.hash_to_curve(b"QUUX-V01-CS02-with-secp256k1_XMD:SHA-256_SSWU_RO_", w["digest32"], random_oracle=True)
+    eng.new_public_keys([bytes(r) for r in pk[:8]] + [b"\x00", b"\x02" + bytes(pk[1][1:33])])
+# the sort / slice / super-slice / window stages of the MSM: random scalars, then one heavy bucket per window
+wm = pkg.synth.msm_batch(6000, eng.scalar_base_mult)
+eng.msm(wm["k32"], wm["pt65"])
+eng.msm(np.tile(wm["k32"][:1], (6000, 1)), wm["pt65"])
+eng.close()
+if os.environ.get("SANITIZE_BIG", "1") == "1":
+    # the three-part host pipeline of ecdsa_verify and the four-part one of the other entry points
+    n = 1 << 18
+    big = pkg.Engine(device=0, max_batch=n)
+    w = pkg.synth.ecdsa_batch(n, big.scalar_base_mult)
+    assert np.array_equal(big.ecdsa_verify(w["pk65"], w["digest32"], w["sig64"]), w["expected"])
+    big.close()
 print("sanitize_all ok")
