@@ -25,7 +25,7 @@ for n in (1, 33, 1500):
     sig, rec, st = eng.ecdsa_sign_rfc6979(priv, w["digest32"])
     eng.schnorr_sign(priv, w["digest32"], ks)
     eng.hash_to_curve(b"QUUX-V01-CS02-with-secp256k1_XMD:SHA-256_SSWU_RO_", w["digest32"], random_oracle=True)
-    eng.new_public_keys([bytes(r) for r in pk[:8]] + [b"\x00", b"\x02" + bytes(pk[1][1:33])])
+    eng.new_public_keys([bytes(r) for r in pk[:8]] + [b"\x00", b"\x02" + bytes(pk[-1][1:33])])
 # the sort / slice / super-slice / window stages of the MSM: random scalars, then one heavy bucket per window
 wm = pkg.synth.msm_batch(6000, eng.scalar_base_mult)
 eng.msm(wm["k32"], wm["pt65"])
