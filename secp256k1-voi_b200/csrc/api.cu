@@ -210,10 +210,14 @@ template <int K>
 __global__ void __launch_bounds__(S256_TPB) k_finish_affine(size_t n, const pt *res, const uint8_t *pvalid,
                                                             const uint8_t *sfl, uint8_t *comb_status, int mode,
                                                             uint8_t *out, uint8_t *status, const uint8_t *sig64) {
-    size_t stride = (n + K - 1) / K;
+    __shared__ uint4 stage[S256_TPB / 32][130];  // 2080 bytes per warp: 32 rows of 65 bytes (kernels.cuh)
+    // a multiple of 32, so that the items a warp converts together start at a multiple of 32 (the
+    // staged 2080-byte block is then 16-byte aligned in `out`)
+    size_t stride = (((n + K - 1) / K) + 31) & ~(size_t)31;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= stride) return;
-    group_finish<K>(t, stride, n, res, pvalid, sfl, comb_status, mode, out, status, sig64);
+    group_finish<K>(t, stride, n, res, pvalid, sfl, comb_status, mode, out, status, sig64,
+                    reinterpret_cast<uint8_t *>(stage[threadIdx.x / 32]));
 }
 
 __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a32, const uint8_t *b32, size_t n,

@@ -514,6 +514,16 @@ S256_HD uint32_t fe_limbs_are_canonical(const fe &a) {
 
 // big-endian 32 bytes <-> limbs (internal/helpers/helpers.go:47-65)
 S256_HD void fe_from_be32(fe &r, const uint8_t *b) {
+#if defined(__CUDA_ARCH__)
+    if ((((size_t)b) & 15u) == 0) {  // aligned rows (x-only keys, signatures): two 128-bit loads
+        const uint4 hi = *reinterpret_cast<const uint4 *>(b), lo = *reinterpret_cast<const uint4 *>(b + 16);
+        r.v[7] = __byte_perm(hi.x, 0, 0x0123); r.v[6] = __byte_perm(hi.y, 0, 0x0123);
+        r.v[5] = __byte_perm(hi.z, 0, 0x0123); r.v[4] = __byte_perm(hi.w, 0, 0x0123);
+        r.v[3] = __byte_perm(lo.x, 0, 0x0123); r.v[2] = __byte_perm(lo.y, 0, 0x0123);
+        r.v[1] = __byte_perm(lo.z, 0, 0x0123); r.v[0] = __byte_perm(lo.w, 0, 0x0123);
+        return;
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const uint8_t *q = b + 4 * (7 - i);
@@ -522,6 +532,19 @@ S256_HD void fe_from_be32(fe &r, const uint8_t *b) {
 }
 // caller passes a canonical element
 S256_HD void fe_to_be32(uint8_t *b, const fe &a) {
+#if defined(__CUDA_ARCH__)
+    // a 16-byte aligned destination (32- and 64-byte rows of the batch buffers): two 128-bit stores
+    if ((((size_t)b) & 15u) == 0) {
+        uint4 hi, lo;
+        hi.x = __byte_perm(a.v[7], 0, 0x0123); hi.y = __byte_perm(a.v[6], 0, 0x0123);
+        hi.z = __byte_perm(a.v[5], 0, 0x0123); hi.w = __byte_perm(a.v[4], 0, 0x0123);
+        lo.x = __byte_perm(a.v[3], 0, 0x0123); lo.y = __byte_perm(a.v[2], 0, 0x0123);
+        lo.z = __byte_perm(a.v[1], 0, 0x0123); lo.w = __byte_perm(a.v[0], 0, 0x0123);
+        reinterpret_cast<uint4 *>(b)[0] = hi;
+        reinterpret_cast<uint4 *>(b)[1] = lo;
+        return;
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         uint8_t *q = b + 4 * (7 - i);

@@ -477,9 +477,41 @@ S256_HD uint8_t item_ecdsa_finish(const pt &R, const uint8_t *sig64, uint32_t va
 // secec/secec.go:53-56: identity is an error); mode 2: BIP-340 acceptance
 // (schnorr.go:451-478): not identity, y even, x == sig[0:32].
 // ---------------------------------------------------------------------------
+// Row access for the conversion kernel.  On the device a point is fetched with six 128-bit loads
+// (the rows are 96 bytes apart, 16-byte aligned) instead of 24 word loads.
+S256_HD void pt_fetch(pt &r, const pt *p) {
+#if defined(__CUDA_ARCH__)
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4], a5 = q[5];
+    r.x.v[0] = a0.x; r.x.v[1] = a0.y; r.x.v[2] = a0.z; r.x.v[3] = a0.w;
+    r.x.v[4] = a1.x; r.x.v[5] = a1.y; r.x.v[6] = a1.z; r.x.v[7] = a1.w;
+    r.y.v[0] = a2.x; r.y.v[1] = a2.y; r.y.v[2] = a2.z; r.y.v[3] = a2.w;
+    r.y.v[4] = a3.x; r.y.v[5] = a3.y; r.y.v[6] = a3.z; r.y.v[7] = a3.w;
+    r.z.v[0] = a4.x; r.z.v[1] = a4.y; r.z.v[2] = a4.z; r.z.v[3] = a4.w;
+    r.z.v[4] = a5.x; r.z.v[5] = a5.y; r.z.v[6] = a5.z; r.z.v[7] = a5.w;
+#else
+    r = *p;
+#endif
+}
+S256_HD void fe_fetch(fe &r, const fe *p) {
+#if defined(__CUDA_ARCH__)
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a0 = q[0], a1 = q[1];
+    r.v[0] = a0.x; r.v[1] = a0.y; r.v[2] = a0.z; r.v[3] = a0.w;
+    r.v[4] = a1.x; r.v[5] = a1.y; r.v[6] = a1.z; r.v[7] = a1.w;
+#else
+    r = *p;
+#endif
+}
+
+// Batched projective -> affine + encode.  `stage` (device only, may be null): 2080 bytes of shared
+// memory per warp.  The 65-byte rows of the 32 consecutive items a warp converts at a time form one
+// contiguous, 16-byte aligned 2080-byte block; written row by row they are byte stores 65 bytes apart
+// (every store instruction touches 32 sectors), so they are assembled in shared memory and leave as
+// 130 coalesced 128-bit stores.
 template <int K>
 S256_HD void group_finish_affine(size_t t, size_t stride, size_t n, const pt *res, const uint8_t *in_status, int mode,
-                                 uint8_t *out, uint8_t *status, const uint8_t *sig64) {
+                                 uint8_t *out, uint8_t *status, const uint8_t *sig64, uint8_t *stage = nullptr) {
     fe pre[K];
     fe run = fe_one();
     const fe one = fe_one();
@@ -487,17 +519,23 @@ S256_HD void group_finish_affine(size_t t, size_t stride, size_t n, const pt *re
         size_t i = t + (size_t)m * stride;
         pre[m] = run;
         if (i < n) {
-            fe z = res[i].z;
+            fe z;
+            fe_fetch(z, &res[i].z);
             fe_cmov(z, z, one, fe_is_zero(z));
             fe_mul(run, run, z);
         }
     }
     fe inv;
     fe_invert(inv, run);
+#if defined(__CUDA_ARCH__)
+    const unsigned lane = threadIdx.x & 31u;
+    const bool full_warp = stage != nullptr && (t - lane) + 32 <= stride;  // every lane of the warp is alive
+#endif
     for (int m = K - 1; m >= 0; m--) {
         size_t i = t + (size_t)m * stride;
         if (i >= n) continue;
-        pt R = res[i];
+        pt R;
+        pt_fetch(R, &res[i]);
         uint32_t ident = fe_is_zero(R.z);
         fe z;
         fe_cmov(z, R.z, one, ident);
@@ -518,6 +556,22 @@ S256_HD void group_finish_affine(size_t t, size_t stride, size_t n, const pt *re
         }
         uint8_t st = (uint8_t)(in_ok ? (ident ? ST_IDENTITY : ST_OK) : ST_INVALID);
         if (mode == 0) {
+#if defined(__CUDA_ARCH__)
+            const size_t i0 = i - lane;  // first item of this warp's block of rows
+            if (full_warp && i0 + 32 <= n && (i0 & 15) == 0) {
+                uint8_t *o = stage + 65 * lane;
+                o[0] = (uint8_t)(keep ? 0x04 : 0x00);
+                fe_to_be32(o + 1, x);
+                fe_to_be32(o + 33, y);
+                __syncwarp();
+                const uint4 *src = reinterpret_cast<const uint4 *>(stage);
+                uint4 *dst = reinterpret_cast<uint4 *>(out + 65 * i0);
+                for (unsigned j = lane; j < 130; j += 32) dst[j] = src[j];
+                __syncwarp();
+                status[i] = st;
+                continue;
+            }
+#endif
             uint8_t *o = out + 65 * i;
             o[0] = (uint8_t)(keep ? 0x04 : 0x00);
             fe_to_be32(o + 1, x);
@@ -542,7 +596,8 @@ S256_HD void group_finish_affine(size_t t, size_t stride, size_t n, const pt *re
 // identity result into an error (secec/secec.go:206-209).
 template <int K>
 S256_HD void group_finish(size_t t, size_t stride, size_t n, const pt *res, const uint8_t *pvalid, const uint8_t *sfl,
-                          uint8_t *cstat, int mode, uint8_t *out, uint8_t *status, const uint8_t *sig64) {
+                          uint8_t *cstat, int mode, uint8_t *out, uint8_t *status, const uint8_t *sig64,
+                          uint8_t *stage = nullptr) {
     for (int m = 0; m < K; m++) {
         size_t i = t + (size_t)m * stride;
         if (i < n) {
@@ -552,7 +607,7 @@ S256_HD void group_finish(size_t t, size_t stride, size_t n, const pt *res, cons
             cstat[i] = (uint8_t)v;
         }
     }
-    group_finish_affine<K>(t, stride, n, res, cstat, mode == 3 ? 0 : mode, out, status, sig64);
+    group_finish_affine<K>(t, stride, n, res, cstat, mode == 3 ? 0 : mode, out, status, sig64, stage);
     if (mode == 3) {
         for (int m = 0; m < K; m++) {
             size_t i = t + (size_t)m * stride;

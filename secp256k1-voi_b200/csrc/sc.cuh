@@ -116,6 +116,18 @@ S256_HD uint32_t sc_from_be32(sc &r, const uint8_t *b) {
     return sc_reduce_once(r, l, 0);
 }
 S256_HD void sc_to_be32(uint8_t *b, const sc &a) {
+#if defined(__CUDA_ARCH__)
+    if ((((size_t)b) & 15u) == 0) {  // aligned rows: two 128-bit stores
+        uint4 hi, lo;
+        hi.x = __byte_perm(a.v[7], 0, 0x0123); hi.y = __byte_perm(a.v[6], 0, 0x0123);
+        hi.z = __byte_perm(a.v[5], 0, 0x0123); hi.w = __byte_perm(a.v[4], 0, 0x0123);
+        lo.x = __byte_perm(a.v[3], 0, 0x0123); lo.y = __byte_perm(a.v[2], 0, 0x0123);
+        lo.z = __byte_perm(a.v[1], 0, 0x0123); lo.w = __byte_perm(a.v[0], 0, 0x0123);
+        reinterpret_cast<uint4 *>(b)[0] = hi;
+        reinterpret_cast<uint4 *>(b)[1] = lo;
+        return;
+    }
+#endif
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         uint8_t *q = b + 4 * (7 - i);
