@@ -19,7 +19,9 @@ __global__ void __launch_bounds__(S256_TPB) k_gen_table(apt *out, int wb, size_t
     out[idx] = a;
 }
 // the signed constant-time table: out[w][j] = (j + 1) * 2^(CT_WB*w) * G
+template <int WB>
 __global__ void __launch_bounds__(S256_TPB) k_gen_ct_table(apt *out) {
+    constexpr int CT_SZ = ct_cfg<WB>::SZ, CT_NW = ct_cfg<WB>::NW, CT_WB = WB;
     uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (uint32_t)(CT_NW * CT_SZ)) return;
     apt a;
@@ -294,7 +296,7 @@ extern "C" void s256_free(s256_ctx *ctx) {
     if (!ctx) return;
     {
         dev_guard g(ctx->device);
-        void *ptrs[] = {ctx->comb, ctx->ct_tab, ctx->aff, ctx->u1,   ctx->dig1, ctx->dig2, ctx->sfl, ctx->pvalid,
+        void *ptrs[] = {ctx->comb, ctx->ct_tab, ctx->ct_tab_small, ctx->aff, ctx->u1,   ctx->dig1, ctx->dig2, ctx->sfl, ctx->pvalid,
                         ctx->cstat, ctx->tbl,   ctx->res, ctx->in_a, ctx->in_b, ctx->in_c, ctx->out, ctx->st,
                         ctx->sink, ctx->msm_counts, ctx->msm_offsets, ctx->msm_cursor, ctx->msm_entries, ctx->msm_flag,
                         ctx->msm_buckets, ctx->msm_win, ctx->msm_acc, ctx->msm_tmp, ctx->msm_cub, ctx->msm_nsl, ctx->msm_sloff,
@@ -314,7 +316,8 @@ extern "C" void s256_free(s256_ctx *ctx) {
 static int ctx_alloc(s256_ctx *ctx) {
     size_t cap = ctx->cap;
     CK(cudaMalloc(&ctx->comb, sizeof(apt) * COMB_NW * COMB_SZ));
-    CK(cudaMalloc(&ctx->ct_tab, sizeof(apt) * CT_NW * CT_SZ));
+    CK(cudaMalloc(&ctx->ct_tab, sizeof(apt) * ct_cfg<CT_WB>::NW * ct_cfg<CT_WB>::SZ));
+    CK(cudaMalloc(&ctx->ct_tab_small, sizeof(apt) * ct_cfg<CT_WB_SMALL>::NW * ct_cfg<CT_WB_SMALL>::SZ));
     CK(cudaMalloc(&ctx->aff, sizeof(apt) * cap));
     CK(cudaMalloc(&ctx->u1, sizeof(sc) * cap));
     CK(cudaMalloc(&ctx->dig1, (size_t)DSM_ND * cap));
@@ -365,7 +368,10 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
         // generator tables (reference: package init, point_mul_table.go:75-100,147-160)
         size_t total = (size_t)COMB_NW * COMB_SZ;
         LAUNCH(ctx, k_gen_table, grid_for(total), 0, ctx->stream, ctx->comb, COMB_WB, total);
-        LAUNCH(ctx, k_gen_ct_table, grid_for((size_t)CT_NW * CT_SZ), 0, ctx->stream, ctx->ct_tab);
+        LAUNCH(ctx, k_gen_ct_table<CT_WB>, grid_for((size_t)ct_cfg<CT_WB>::NW * ct_cfg<CT_WB>::SZ), 0, ctx->stream,
+               ctx->ct_tab);
+        LAUNCH(ctx, k_gen_ct_table<CT_WB_SMALL>, grid_for((size_t)ct_cfg<CT_WB_SMALL>::NW * ct_cfg<CT_WB_SMALL>::SZ), 0,
+               ctx->stream, ctx->ct_tab_small);
         s256_ct_kernels_init();
         if (CT_SMEM_BYTES)
             cudaFuncSetAttribute(k_scalar_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM_BYTES);
@@ -470,7 +476,7 @@ static int chunk_dsm(s256_ctx *ctx, const view &v, const uint8_t *u1, const uint
 }
 static int chunk_base_mult(s256_ctx *ctx, const view &v, const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status,
                            cudaStream_t s) {
-    s256_launch_base_mult_ct(k32, n, ctx->ct_tab, v.res, s);
+    s256_launch_base_mult_ct(k32, n, ctx->ct_tab, ctx->ct_tab_small, v.res, s);
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, v.res, (const uint8_t *)nullptr,
            (const uint8_t *)nullptr, v.cstat, 0, out65, status, (const uint8_t *)nullptr));

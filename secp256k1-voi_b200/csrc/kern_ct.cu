@@ -6,19 +6,24 @@
 #include "launchers.h"
 
 using namespace s256;
-#define S256_TPB 128
-
+// 16 warps per SM in both configurations; the table (NW * SZ * 64 bytes of shared memory per CTA) decides
+// how many CTAs fit: 88 KB (6-bit windows) twice with 256 threads, 53 KB (5-bit) four times with 128.
+#define S256_TPB 128       // the lane-split kernels
+#define S256_TPB_BIG 256   // the throughput kernel
 #ifndef S256_BM_MINB
 #define S256_BM_MINB 4
 #endif
+#define S256_BM_MINB_BIG 2
+constexpr size_t CT_BYTES_BIG = (size_t)ct_cfg<CT_WB>::NW * ct_cfg<CT_WB>::SZ * sizeof(apt);
+constexpr size_t CT_BYTES_SMALL = (size_t)ct_cfg<CT_WB_SMALL>::NW * ct_cfg<CT_WB_SMALL>::SZ * sizeof(apt);
 
-__global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
+__global__ void __launch_bounds__(S256_TPB_BIG, S256_BM_MINB_BIG)
     k_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_g, pt *res) {
     extern __shared__ uint4 smem_raw[];
     apt *tab = reinterpret_cast<apt *>(smem_raw);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(tab_g);
-        const int nvec = CT_NW * CT_SZ * (int)sizeof(apt) / 16;
+        const int nvec = (int)(CT_BYTES_BIG / 16);
         for (int v = threadIdx.x; v < nvec; v += blockDim.x) smem_raw[v] = src[v];
     }
     __syncthreads();
@@ -26,7 +31,7 @@ __global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
         sc k;
         sc_from_be32(k, k32 + 32 * i);
         pt acc;
-        item_base_mult_ct(acc, k, tab);
+        item_base_mult_ct<CT_WB>(acc, k, tab);
         res[i] = acc;
     }
 }
@@ -40,7 +45,7 @@ __global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
     apt *tab = reinterpret_cast<apt *>(smem_raw);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(tab_g);
-        const int nvec = CT_NW * CT_SZ * (int)sizeof(apt) / 16;
+        const int nvec = (int)(CT_BYTES_SMALL / 16);
         for (int v = threadIdx.x; v < nvec; v += blockDim.x) smem_raw[v] = src[v];
     }
     __syncthreads();
@@ -51,7 +56,7 @@ __global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
     sc k;
     sc_from_be32(k, k32 + 32 * (live ? item : 0));
     pt acc;
-    item_base_mult_ct_part(acc, k, tab, part, T);
+    item_base_mult_ct_part<CT_WB_SMALL>(acc, k, tab, part, T);
 #pragma unroll
     for (int off = T / 2; off >= 1; off >>= 1) {
         pt o;
@@ -65,27 +70,25 @@ __global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
 }
 
 void s256_ct_kernels_init() {
-    cudaFuncSetAttribute(k_base_mult_ct_split<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(CT_NW * CT_SZ * sizeof(apt)));
-    cudaFuncSetAttribute(k_base_mult_ct_split<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(CT_NW * CT_SZ * sizeof(apt)));
-    cudaFuncSetAttribute(k_base_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)(CT_NW * CT_SZ * sizeof(apt)));
+    cudaFuncSetAttribute(k_base_mult_ct_split<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_SMALL);
+    cudaFuncSetAttribute(k_base_mult_ct_split<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_SMALL);
+    cudaFuncSetAttribute(k_base_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_BIG);
 }
-void s256_launch_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_g, pt *res, cudaStream_t s) {
-    unsigned grid = (unsigned)((n + S256_TPB - 1) / S256_TPB);
-    unsigned maxg = 148u * S256_BM_MINB;
-    if (grid > maxg) grid = maxg;
-    if (grid == 0) return;
-    const size_t smem = CT_NW * CT_SZ * sizeof(apt);
+// tab_big: [NW(6)][SZ(6)], tab_small: [NW(5)][SZ(5)] (ctx->ct_tab, ctx->ct_tab_small)
+void s256_launch_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_big, const apt *tab_small, pt *res,
+                              cudaStream_t s) {
+    if (n == 0) return;
     // small batches are latency bound: deal the windows of each scalar to 8 / 4 lanes
     if (n <= 8192) {
-        k_base_mult_ct_split<8><<<(unsigned)((n * 8 + S256_TPB - 1) / S256_TPB), S256_TPB, smem, s>>>(k32, n, tab_g, res);
+        k_base_mult_ct_split<8><<<(unsigned)((n * 8 + S256_TPB - 1) / S256_TPB), S256_TPB, CT_BYTES_SMALL, s>>>(k32, n, tab_small, res);
         return;
     }
     if (n <= 32768) {
-        k_base_mult_ct_split<4><<<(unsigned)((n * 4 + S256_TPB - 1) / S256_TPB), S256_TPB, smem, s>>>(k32, n, tab_g, res);
+        k_base_mult_ct_split<4><<<(unsigned)((n * 4 + S256_TPB - 1) / S256_TPB), S256_TPB, CT_BYTES_SMALL, s>>>(k32, n, tab_small, res);
         return;
     }
-    k_base_mult_ct<<<grid, S256_TPB, smem, s>>>(k32, n, tab_g, res);
+    unsigned grid = (unsigned)((n + S256_TPB_BIG - 1) / S256_TPB_BIG);
+    unsigned maxg = 148u * S256_BM_MINB_BIG;
+    if (grid > maxg) grid = maxg;
+    k_base_mult_ct<<<grid, S256_TPB_BIG, CT_BYTES_BIG, s>>>(k32, n, tab_big, res);
 }

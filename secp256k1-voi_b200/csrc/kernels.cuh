@@ -35,16 +35,26 @@ constexpr int DSM_TS = 1 << (DSM_W - 1);       // table entries 1..TS
 constexpr int COMB_WB = S256_COMB_WB;
 constexpr int COMB_NW = (256 + COMB_WB - 1) / COMB_WB;
 constexpr int COMB_SZ = 1 << COMB_WB;
-// constant-time fixed-base table: signed CT_WB-bit digits in [-(2^(WB-1) - 1), 2^(WB-1)]; entries
-// (j + 1) * 2^(WB*w) * G for j = 0 .. 2^(WB-1) - 1.  WB = 5: 52 windows x 16 entries = 53 248 bytes
-// (fits shared memory four times per SM); WB = 4: 65 windows (64 + carry) x 8 entries = 33 280 bytes.
+// constant-time fixed-base tables: signed WB-bit digits in [-(2^(WB-1) - 1), 2^(WB-1)]; entries
+// (j + 1) * 2^(WB*w) * G for j = 0 .. 2^(WB-1) - 1.  Two window sizes are resident: WB = 6
+// (43 windows x 32 entries = 88 064 bytes, twice per SM) for the throughput kernel, and WB = 5
+// (52 x 16 = 53 248 bytes) for the lane-split small-batch kernels, where every CTA stages its own copy
+// of the table and a smaller one starts sooner.  WB = 7 is 3 % faster at 2^20 and 2x slower at 4096.
+template <int WB>
+struct ct_cfg {
+    static constexpr int NW = (257 + WB - 1) / WB;  // 256 scalar bits + the recoding carry
+    static constexpr int SZ = 1 << (WB - 1);
+};
 #ifndef S256_CT_WB
-#define S256_CT_WB 5
+#define S256_CT_WB 6
 #endif
-constexpr int CT_WB = S256_CT_WB;
-constexpr int CT_NW = (257 + CT_WB - 1) / CT_WB;  // 256 scalar bits + the recoding carry
-constexpr int CT_SZ = 1 << (CT_WB - 1);
+#ifndef S256_CT_WB_SMALL
+#define S256_CT_WB_SMALL 5
+#endif
+constexpr int CT_WB = S256_CT_WB, CT_WB_SMALL = S256_CT_WB_SMALL;
+constexpr int CT_NW = ct_cfg<CT_WB>::NW;  // for the work model (s256_mac32_per_item)
 // digit w of the recoding: bits [WB*w, WB*w + WB) of k plus the incoming carry
+template <int CT_WB>
 S256_HD uint32_t ct_window_bits(const sc &k, int w) {
     int bit = w * CT_WB;
     if (bit >= 256) return 0u;
@@ -626,14 +636,16 @@ S256_HD void group_finish(size_t t, size_t stride, size_t n, const pt *res, cons
 // bank pattern depends on the scalar -- the sign is applied by select, and
 // digit 0 is resolved by select after a dummy add (point_mul_table.go:118-129).
 // ---------------------------------------------------------------------------
-S256_HD void item_base_mult_ct(pt &acc, const sc &k, const apt *tab /* [CT_NW][CT_SZ] */) {
+template <int CT_WB = S256_CT_WB>
+S256_HD void item_base_mult_ct(pt &acc, const sc &k, const apt *tab /* [NW][SZ] */) {
+    constexpr int CT_NW = ct_cfg<CT_WB>::NW, CT_SZ = ct_cfg<CT_WB>::SZ;
     pt_set_identity(acc);
     uint32_t carry = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int w = 0; w < CT_NW; w++) {
-        uint32_t v = ct_window_bits(k, w) + carry;                       // 0 .. 2^WB
+        uint32_t v = ct_window_bits<CT_WB>(k, w) + carry;                       // 0 .. 2^WB
         carry = (v + (uint32_t)CT_SZ - 1u) >> CT_WB;                      // 1 iff v > 2^(WB-1)
         int32_t d = (int32_t)v - (int32_t)(carry << CT_WB);               // -(2^(WB-1) - 1) .. 2^(WB-1)
         uint32_t sign = (uint32_t)d >> 31;
@@ -646,12 +658,13 @@ S256_HD void item_base_mult_ct(pt &acc, const sc &k, const apt *tab /* [CT_NW][C
 #pragma unroll 2
 #endif
         for (uint32_t j = 1; j <= (uint32_t)CT_SZ; j++) {
-            uint32_t m = 0u - (uint32_t)(j == mag);
+            // a register select per word (SEL on the device: no branch, no address depends on mag)
+            const bool hit = j == mag;
             apt e = row[j - 1];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                sel.x.v[q] |= e.x.v[q] & m;
-                sel.y.v[q] |= e.y.v[q] & m;
+                sel.x.v[q] = hit ? e.x.v[q] : sel.x.v[q];
+                sel.y.v[q] = hit ? e.y.v[q] : sel.y.v[q];
             }
         }
         // mag == 0 selected nothing: add a well-formed dummy (entry 1) and discard the sum
@@ -670,12 +683,14 @@ S256_HD void item_base_mult_ct(pt &acc, const sc &k, const apt *tab /* [CT_NW][C
 // iteration j, so the whole warp stays in lockstep); the caller folds the T partial points with
 // complete additions.  Digits are recoded first (carry chain) into a local array that is then read
 // at an index depending only on the lane number.  Same table, same masks, same selects as above.
+template <int CT_WB = S256_CT_WB_SMALL>
 S256_HD void item_base_mult_ct_part(pt &acc, const sc &k, const apt *tab, int part, int T) {
+    constexpr int CT_NW = ct_cfg<CT_WB>::NW, CT_SZ = ct_cfg<CT_WB>::SZ;
     int8_t dig[CT_NW];
     uint32_t carry = 0;
 #pragma unroll 1
     for (int w = 0; w < CT_NW; w++) {
-        uint32_t v = ct_window_bits(k, w) + carry;
+        uint32_t v = ct_window_bits<CT_WB>(k, w) + carry;
         carry = (v + (uint32_t)CT_SZ - 1u) >> CT_WB;
         dig[w] = (int8_t)((int32_t)v - (int32_t)(carry << CT_WB));
     }
@@ -699,12 +714,12 @@ S256_HD void item_base_mult_ct_part(pt &acc, const sc &k, const apt *tab, int pa
 #pragma unroll 2
 #endif
         for (uint32_t e = 1; e <= (uint32_t)CT_SZ; e++) {
-            uint32_t m = 0u - (uint32_t)(e == mag);
+            const bool hit = e == mag;
             apt t = row[e - 1];
 #pragma unroll
             for (int q = 0; q < 8; q++) {
-                sel.x.v[q] |= t.x.v[q] & m;
-                sel.y.v[q] |= t.y.v[q] & m;
+                sel.x.v[q] = hit ? t.x.v[q] : sel.x.v[q];
+                sel.y.v[q] = hit ? t.y.v[q] : sel.y.v[q];
             }
         }
         uint32_t zero = (uint32_t)(mag == 0);

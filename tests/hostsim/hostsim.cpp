@@ -19,14 +19,19 @@
 using namespace s256;
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
-static std::vector<apt> g_comb, g_ct;
+static std::vector<apt> g_comb, g_ct, g_ct_small;
 static constexpr int K = 32;
 
 static void ensure_tables() {
     if (!g_ct.empty()) return;
-    g_ct.resize((size_t)CT_NW * CT_SZ);
+    // both resident tables, as s256_init builds them: 6-bit windows (throughput kernel), 5-bit (lane-split kernels)
+    constexpr int SZB = ct_cfg<CT_WB>::SZ, SZS = ct_cfg<CT_WB_SMALL>::SZ;
+    g_ct.resize((size_t)ct_cfg<CT_WB>::NW * SZB);
     for (size_t idx = 0; idx < g_ct.size(); idx++)
-        item_gen_multiple(g_ct[idx], (uint32_t)(idx / CT_SZ), (uint32_t)(idx % CT_SZ) + 1u, CT_WB);
+        item_gen_multiple(g_ct[idx], (uint32_t)(idx / SZB), (uint32_t)(idx % SZB) + 1u, CT_WB);
+    g_ct_small.resize((size_t)ct_cfg<CT_WB_SMALL>::NW * SZS);
+    for (size_t idx = 0; idx < g_ct_small.size(); idx++)
+        item_gen_multiple(g_ct_small[idx], (uint32_t)(idx / SZS), (uint32_t)(idx % SZS) + 1u, CT_WB_SMALL);
 }
 // The comb has 2^20 entries; generating it with the bit-serial routine is too
 // slow on one CPU core, so the simulation fills only the entries a batch uses.
@@ -130,7 +135,7 @@ EXPORT void sim_scalar_base_mult(const uint8_t *k32, size_t n, uint8_t *out65, u
         if (n <= 8) {  // exercise the lane-split form (T = 8 then T = 4) the way the kernel folds it
             int T = (i & 1) ? 4 : 8;
             pt part[8];
-            for (int p = 0; p < T; p++) item_base_mult_ct_part(part[p], k, g_ct.data(), p, T);
+            for (int p = 0; p < T; p++) item_base_mult_ct_part<CT_WB_SMALL>(part[p], k, g_ct_small.data(), p, T);
             for (int off = T / 2; off >= 1; off >>= 1)
                 for (int p = 0; p < off; p++) pt_add(part[p], part[p], part[p + off]);
             s.res[i] = part[0];
