@@ -19,5 +19,16 @@ elif which == "ecdh":
 elif which == "sbm":
     ks = cu(pkg.synth.base_mult_scalars(n))
     for _ in range(3): eng.scalar_base_mult(ks)
+elif which == "h2c":
+    import time
+    engp = pkg.Engine(device=0, max_batch=n, pinned_outputs=True)
+    msgs = np.frombuffer(b"".join(pkg.synth.D(b"h2c", i) for i in range(n)), np.uint8).reshape(n, 32)
+    hm = torch.from_numpy(msgs.copy()).pin_memory().numpy()
+    dst = b"QUUX-V01-CS02-with-secp256k1_XMD:SHA-256_SSWU_RO_"
+    for ro in (True, False):
+        for _ in range(2): engp.hash_to_curve(dst, hm, random_oracle=ro)
+        t0 = time.perf_counter()
+        for _ in range(3): engp.hash_to_curve(dst, hm, random_oracle=ro)
+        print("h2c ro=%s: %.3f ms per 2^%d call, %.1f M/s" % (ro, (time.perf_counter() - t0) / 3 * 1e3, int(np.log2(n)), n * 3 / (time.perf_counter() - t0) / 1e6))
 torch.cuda.synchronize()
 print("ok")
