@@ -18,6 +18,55 @@ __global__ void __launch_bounds__(S256_TPB) k_gen_table(apt *out, int wb, size_t
     item_gen_multiple(a, w, d, wb);
     out[idx] = a;
 }
+// The signed comb of the verification ladder (kernels.cuh): out[w][j] = (j + 1) * B_w, B_w = 2^(COMB_WB*w) * G.
+// 25 M entries, so not one bit-serial multiple and one inversion each (k_gen_table): a thread owns COMB_RUN
+// consecutive entries of one window, reaches the first by double-and-add over B_w, walks the rest with
+// mixed additions of B_w, and converts all of them with one shared inversion.
+__global__ void k_comb_bases(apt *bases) {
+    uint32_t w = threadIdx.x;
+    if (w < (uint32_t)COMB_NW) item_gen_multiple(bases[w], w, 1u, COMB_WB);
+}
+constexpr int COMB_RUN = 32;
+static_assert(COMB_SZ % COMB_RUN == 0, "a run never straddles two windows");
+__global__ void __launch_bounds__(S256_TPB) k_gen_comb(const apt *bases, size_t total, apt *out) {
+    size_t e0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * COMB_RUN;
+    if (e0 >= total) return;
+    const apt B = bases[e0 / COMB_SZ];
+    const uint32_t m = (uint32_t)(e0 % COMB_SZ) + 1u;  // first multiplier of the run, <= 2^(WB-1)
+    pt buf[COMB_RUN];
+    pt acc;
+    pt_set_identity(acc);
+#pragma unroll 1
+    for (int b = COMB_WB - 1; b >= 0; b--) {
+        pt_double(acc, acc);
+        if ((m >> b) & 1u) pt_add_mixed(acc, acc, B.x, B.y);
+    }
+    buf[0] = acc;
+#pragma unroll 1
+    for (int i = 1; i < COMB_RUN; i++) {
+        pt_add_mixed(acc, acc, B.x, B.y);
+        buf[i] = acc;
+    }
+    fe pre[COMB_RUN], run = fe_one(), inv;
+#pragma unroll 1
+    for (int i = 0; i < COMB_RUN; i++) {
+        pre[i] = run;
+        fe_mul(run, run, buf[i].z);  // never zero: (j + 1) * 2^(WB*w) < n
+    }
+    fe_invert(inv, run);
+#pragma unroll 1
+    for (int i = COMB_RUN - 1; i >= 0; i--) {
+        fe zi;
+        apt a;
+        fe_mul(zi, inv, pre[i]);
+        fe_mul(inv, inv, buf[i].z);
+        fe_mul(a.x, buf[i].x, zi);
+        fe_mul(a.y, buf[i].y, zi);
+        fe_normalize(a.x, a.x);
+        fe_normalize(a.y, a.y);
+        out[e0 + i] = a;
+    }
+}
 // the signed constant-time table: out[w][j] = (j + 1) * 2^(CT_WB*w) * G
 template <int WB>
 __global__ void __launch_bounds__(S256_TPB) k_gen_ct_table(apt *out) {
@@ -160,18 +209,6 @@ __global__ void __launch_bounds__(S256_TPB, S256_DSM_MINB)
     item_dsm(i, n, aff, u1, dig1, dig2, sfl, tbl, res, comb);
 }
 
-#ifndef S256_VM_MINB
-#define S256_VM_MINB 4
-#endif
-__global__ void __launch_bounds__(S256_TPB, S256_VM_MINB)
-    k_dsm_vm(size_t n, const apt *aff, const sc *u1, const int8_t *dig1, const int8_t *dig2, const uint8_t *sfl, pt *tbl,
-             pt *res, const apt *comb) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    DevFrame<S256_TPB> f{threadIdx.x};
-    item_dsm_vm(f, i, n, aff, u1, dig1, dig2, sfl, tbl, res, comb);
-}
-constexpr size_t VM_SMEM_BYTES = (size_t)VM_SLOTS * 2 * S256_TPB * sizeof(uint4);
 
 #ifndef S256_SM_MINB
 #define S256_SM_MINB 4
@@ -315,7 +352,7 @@ extern "C" void s256_free(s256_ctx *ctx) {
 
 static int ctx_alloc(s256_ctx *ctx) {
     size_t cap = ctx->cap;
-    CK(cudaMalloc(&ctx->comb, sizeof(apt) * COMB_NW * COMB_SZ));
+    CK(cudaMalloc(&ctx->comb, sizeof(apt) * ((size_t)COMB_NW * COMB_SZ + COMB_NW)));  // + the window bases B_w
     CK(cudaMalloc(&ctx->ct_tab, sizeof(apt) * ct_cfg<CT_WB>::NW * ct_cfg<CT_WB>::SZ));
     CK(cudaMalloc(&ctx->ct_tab_small, sizeof(apt) * ct_cfg<CT_WB_SMALL>::NW * ct_cfg<CT_WB_SMALL>::SZ));
     CK(cudaMalloc(&ctx->aff, sizeof(apt) * cap));
@@ -367,7 +404,9 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
     if (rc == S256_SUCCESS) {
         // generator tables (reference: package init, point_mul_table.go:75-100,147-160)
         size_t total = (size_t)COMB_NW * COMB_SZ;
-        LAUNCH(ctx, k_gen_table, grid_for(total), 0, ctx->stream, ctx->comb, COMB_WB, total);
+        apt *bases = ctx->comb + total;
+        k_comb_bases<<<1, 32, 0, ctx->stream>>>(bases);
+        LAUNCH(ctx, k_gen_comb, grid_for(total / COMB_RUN), 0, ctx->stream, bases, total, ctx->comb);
         LAUNCH(ctx, k_gen_ct_table<CT_WB>, grid_for((size_t)ct_cfg<CT_WB>::NW * ct_cfg<CT_WB>::SZ), 0, ctx->stream,
                ctx->ct_tab);
         LAUNCH(ctx, k_gen_ct_table<CT_WB_SMALL>, grid_for((size_t)ct_cfg<CT_WB_SMALL>::NW * ct_cfg<CT_WB_SMALL>::SZ), 0,
@@ -375,11 +414,8 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
         s256_ct_kernels_init();
         if (CT_SMEM_BYTES)
             cudaFuncSetAttribute(k_scalar_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM_BYTES);
-        cudaFuncSetAttribute(k_dsm_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VM_SMEM_BYTES);
         const char *pp = getenv("S256_PIPE_PARTS");
         if (pp && atoi(pp) >= 0 && atoi(pp) <= 16) ctx->pipe_parts = atoi(pp);
-        const char *lad = getenv("S256_LADDER");
-        ctx->use_reg_ladder = !(lad && std::string(lad) == "vm");  // register form is the faster one (profiles/)
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) {
             fprintf(stderr, "s256_init: table generation failed: %s\n", cudaGetErrorString(e));
@@ -415,12 +451,7 @@ static void enqueue_dsm(s256_ctx *ctx, const view &v, size_t n, cudaStream_t s) 
         cudaEventCreate(&e1);
         cudaEventRecord(e0, s);
     }
-    if (ctx->use_reg_ladder)
-        LAUNCH(ctx, k_dsm, grid_for(n), 0, s, n, v.aff, v.u1, v.dig1, v.dig2, v.sfl, v.tbl, v.res,
-               ctx->comb);
-    else
-        LAUNCH(ctx, k_dsm_vm, grid_for(n), VM_SMEM_BYTES, s, n, v.aff, v.u1, v.dig1, v.dig2, v.sfl,
-               v.tbl, v.res, ctx->comb);
+    LAUNCH(ctx, k_dsm, grid_for(n), 0, s, n, v.aff, v.u1, v.dig1, v.dig2, v.sfl, v.tbl, v.res, ctx->comb);
     if (ctx->profiling) {
         cudaEventRecord(e1, s);
         ctx->dsm_events.emplace_back(e0, e1);

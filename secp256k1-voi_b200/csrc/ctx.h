@@ -58,7 +58,6 @@ struct s256_ctx {
     // pay -- the batched-inversion kernel is latency bound, so its cost multiplies with the part count.
     int pipe_parts = 1;
     cudaEvent_t ev_decode = nullptr, ev_pipe[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool use_reg_ladder = true;  // S256_LADDER=vm selects the frame-form ladder (A/B measurements)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dsm_events;
 };
 

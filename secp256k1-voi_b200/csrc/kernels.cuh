@@ -17,7 +17,6 @@
 #include "point.cuh"
 #include "sc.cuh"
 #include "sha256.cuh"
-#include "vm.cuh"
 
 namespace s256 {
 
@@ -28,13 +27,30 @@ namespace s256 {
 constexpr int DSM_W = S256_W;
 constexpr int DSM_ND = glv_recode<DSM_W>::ND;  // digits per 128-bit half
 constexpr int DSM_TS = 1 << (DSM_W - 1);       // table entries 1..TS
-// fixed-base comb for the G half: COMB_NW windows of COMB_WB bits
+// fixed-base comb for the G half of the verification ladder: COMB_NW windows of COMB_WB bits, SIGNED
+// digits in [-(2^(WB-1) - 1), 2^(WB-1)], entries (j + 1) * 2^(WB*w) * G for j = 0 .. 2^(WB-1) - 1.
+// No doublings, one mixed addition per window, so wider windows are fewer additions and the only
+// price is table memory -- which this GPU has: WB = 22 is 12 windows of 2^21 entries = 1.5 GiB of the
+// 180 GB (WB = 16: 16 windows, 32 MiB), one 64-byte gather per window, public data.
 #ifndef S256_COMB_WB
-#define S256_COMB_WB 16
+#define S256_COMB_WB 22
 #endif
 constexpr int COMB_WB = S256_COMB_WB;
-constexpr int COMB_NW = (256 + COMB_WB - 1) / COMB_WB;
-constexpr int COMB_SZ = 1 << COMB_WB;
+constexpr int COMB_NW = (257 + COMB_WB - 1) / COMB_WB;  // 256 scalar bits + the recoding carry
+constexpr int COMB_SZ = 1 << (COMB_WB - 1);
+// signed digit w of u1 (carry in / out); the top window absorbs the last carry
+S256_HD int32_t comb_digit(const sc &u1, int w, uint32_t &carry) {
+    int bit = w * COMB_WB;
+    uint32_t v = 0;
+    if (bit < 256) {
+        v = u1.v[bit >> 5] >> (bit & 31);
+        if ((bit & 31) + COMB_WB > 32 && (bit >> 5) + 1 < 8) v |= u1.v[(bit >> 5) + 1] << (32 - (bit & 31));
+        v &= (1u << COMB_WB) - 1u;
+    }
+    v += carry;                                         // 0 .. 2^WB
+    carry = (v + (uint32_t)COMB_SZ - 1u) >> COMB_WB;    // 1 iff v > 2^(WB-1)
+    return (int32_t)v - (int32_t)(carry << COMB_WB);
+}
 // constant-time fixed-base tables: signed WB-bit digits in [-(2^(WB-1) - 1), 2^(WB-1)]; entries
 // (j + 1) * 2^(WB*w) * G for j = 0 .. 2^(WB-1) - 1.  Two window sizes are resident: WB = 6
 // (43 windows x 32 entries = 88 064 bytes, twice per SM) for the throughput kernel, and WB = 5
@@ -368,90 +384,23 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
         }
     }
     sc u1 = u1s[i];
+    uint32_t carry = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int w = 0; w < COMB_NW; w++) {
-        int bit = w * COMB_WB;
-        uint32_t d = u1.v[bit >> 5] >> (bit & 31);
-        if ((bit & 31) + COMB_WB > 32 && (bit >> 5) + 1 < 8) d |= u1.v[(bit >> 5) + 1] << (32 - (bit & 31));
-        d &= (uint32_t)COMB_SZ - 1u;
+        int32_t d = comb_digit(u1, w, carry);
         if (d != 0) {
-            apt g = comb[(size_t)w * COMB_SZ + d];
+            uint32_t mag = (uint32_t)(d < 0 ? -d : d);
+            apt g = comb[(size_t)w * COMB_SZ + (mag - 1u)];
+            if (d < 0) {
+                fe z = fe_zero();
+                fe_sub_vt(g.y, z, g.y);
+            }
             pt_add_mixed<true>(acc, acc, g.x, g.y);
         }
     }
     res[i] = acc;
-}
-
-// The same computation in frame form (vm.cuh): field elements live in per-thread
-// slots (shared memory on the device) and every operation is an out-of-line
-// worker taking slot addresses.  This is the version the product launches; the
-// register form above is kept for A/B measurements.
-template <class F>
-S256_HD void item_dsm_vm(F &f, size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1,
-                         const int8_t *dig2, const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
-    pt *T = tbl + i * (size_t)DSM_TS;
-    f.load_apt(AX, &aff[i]);  // the addend stays P for the whole table build
-    f.load_apt(SX, &aff[i]);
-    f.set(SZ, fe_one());
-    f.store_pt(&T[0], SX);
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-    for (int k = 2; k <= DSM_TS; k += 2) {
-        f.load_pt(SX, &T[k / 2 - 1]);
-        vm_pt_double(f);
-        f.store_pt(&T[k - 1], SX);
-        if (k < DSM_TS) {
-            vm_pt_add_mixed(f);
-            f.store_pt(&T[k], SX);
-        }
-    }
-    uint32_t fl = sfl[i];
-    vm_set_identity(f);
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-    for (int s = DSM_ND - 1; s >= 0; s--) {
-        if (s != DSM_ND - 1) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-            for (int k = 0; k < DSM_W; k++) vm_pt_double(f);
-        }
-        int da = dig1[(size_t)s * n + i];
-        int db = dig2[(size_t)s * n + i];
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-        for (int h = 0; h < 2; h++) {
-            int d = h ? db : da;
-            if (d != 0) {
-                uint32_t neg = (uint32_t)(d < 0) ^ ((fl >> (1 + h)) & 1u);
-                int mag = d < 0 ? -d : d;
-                f.load_pt(AX, &T[mag - 1]);
-                if (h) f.mul_beta(AX, AX);
-                if (neg) f.neg(AY, AY);
-                vm_pt_add(f);
-            }
-        }
-    }
-    sc u1 = u1s[i];
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-    for (int w = 0; w < COMB_NW; w++) {
-        int bit = w * COMB_WB;
-        uint32_t d = u1.v[bit >> 5] >> (bit & 31);
-        if ((bit & 31) + COMB_WB > 32 && (bit >> 5) + 1 < 8) d |= u1.v[(bit >> 5) + 1] << (32 - (bit & 31));
-        d &= (uint32_t)COMB_SZ - 1u;
-        if (d != 0) {
-            f.load_apt(AX, &comb[(size_t)w * COMB_SZ + d]);
-            vm_pt_add_mixed(f);
-        }
-    }
-    f.store_pt(&res[i], SX);
 }
 
 // ---------------------------------------------------------------------------

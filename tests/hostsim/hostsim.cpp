@@ -19,7 +19,7 @@
 using namespace s256;
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
-static std::vector<apt> g_comb, g_ct, g_ct_small;
+static std::vector<apt> g_ct, g_ct_small;
 static constexpr int K = 32;
 
 static void ensure_tables() {
@@ -33,17 +33,18 @@ static void ensure_tables() {
     for (size_t idx = 0; idx < g_ct_small.size(); idx++)
         item_gen_multiple(g_ct_small[idx], (uint32_t)(idx / SZS), (uint32_t)(idx % SZS) + 1u, CT_WB_SMALL);
 }
-// The comb has 2^20 entries; generating it with the bit-serial routine is too
-// slow on one CPU core, so the simulation fills only the entries a batch uses.
-static std::vector<uint8_t> g_comb_have;
-static void ensure_comb_entry(uint32_t w, uint32_t d) {
-    if (g_comb.empty()) {
-        g_comb.resize((size_t)COMB_NW * COMB_SZ);
-        g_comb_have.assign(g_comb.size(), 0);
+// The comb has 12 * 2^21 entries (1.5 GiB); the simulation fills only the entries a batch uses, in
+// lazily zeroed memory (calloc: untouched pages cost nothing).
+static apt *g_comb_tab = nullptr;
+static uint8_t *g_comb_have = nullptr;
+static void ensure_comb_entry(uint32_t w, uint32_t mag) {  // entry mag * 2^(WB*w) * G, mag in [1, 2^(WB-1)]
+    if (!g_comb_tab) {
+        g_comb_tab = (apt *)calloc((size_t)COMB_NW * COMB_SZ, sizeof(apt));
+        g_comb_have = (uint8_t *)calloc((size_t)COMB_NW * COMB_SZ, 1);
     }
-    size_t idx = (size_t)w * COMB_SZ + d;
+    size_t idx = (size_t)w * COMB_SZ + (mag - 1u);
     if (!g_comb_have[idx]) {
-        item_gen_multiple(g_comb[idx], w, d, COMB_WB);
+        item_gen_multiple(g_comb_tab[idx], w, mag, COMB_WB);
         g_comb_have[idx] = 1;
     }
 }
@@ -59,28 +60,17 @@ struct scratch {
 };
 
 static void run_dsm(scratch &s, size_t n) {
-    for (size_t i = 0; i < n; i++)
-        for (int w = 0; w < COMB_NW; w++) {
-            int bit = w * COMB_WB;
-            uint32_t d = s.u1[i].v[bit >> 5] >> (bit & 31);
-            if ((bit & 31) + COMB_WB > 32 && (bit >> 5) + 1 < 8) d |= s.u1[i].v[(bit >> 5) + 1] << (32 - (bit & 31));
-            d &= (uint32_t)COMB_SZ - 1u;
-            if (d) ensure_comb_entry((uint32_t)w, d);
-        }
-    if (g_comb.empty()) ensure_comb_entry(0, 1);
-    // the frame-form ladder is what the product launches; S256_SIM_LADDER=reg runs the register form
-    const char *lad = getenv("S256_SIM_LADDER");
-    bool reg = lad && std::string(lad) == "reg";
     for (size_t i = 0; i < n; i++) {
-        if (reg) {
-            item_dsm(i, n, s.aff.data(), s.u1.data(), s.dig1.data(), s.dig2.data(), s.sfl.data(), s.tbl.data(),
-                     s.res.data(), g_comb.data());
-        } else {
-            HostFrame f;
-            item_dsm_vm(f, i, n, s.aff.data(), s.u1.data(), s.dig1.data(), s.dig2.data(), s.sfl.data(), s.tbl.data(),
-                        s.res.data(), g_comb.data());
+        uint32_t carry = 0;
+        for (int w = 0; w < COMB_NW; w++) {
+            int32_t d = comb_digit(s.u1[i], w, carry);
+            if (d) ensure_comb_entry((uint32_t)w, (uint32_t)(d < 0 ? -d : d));
         }
     }
+    if (!g_comb_tab) ensure_comb_entry(0, 1);
+    for (size_t i = 0; i < n; i++)
+        item_dsm(i, n, s.aff.data(), s.u1.data(), s.dig1.data(), s.dig2.data(), s.sfl.data(), s.tbl.data(), s.res.data(),
+                 g_comb_tab);
 }
 static void run_finish(scratch &s, size_t n, bool use_pvalid, bool use_sfl, int mode, uint8_t *out, uint8_t *status,
                        const uint8_t *sig) {
