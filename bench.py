@@ -363,11 +363,11 @@ def main():
                          "kernel_ms": dsm_ms / max(dsm_launches, 1), "kernel_share_of_step": dsm_ms / ms_total if world == 1 else None,
                          "whole_step_frac": value / world * mac_item / imad_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_dsm launch at 2^20 items, from the
-                         # committed capture profiles/r01_ncu_final_dsm.txt (4.80 GB + 1.75 GB); scaled if --batch-log2 differs
-                         "traffic": 6.549e9 * n / (1 << 20), "traffic_unit": "bytes per launch",
-                         "traffic_note": "ncu --set full, profiles/r01_ncu_final_dsm.txt: ~6.2 KB per item (per-item table "
-                                         "write + gathers) = 0.28 TB/s, 4 % of the measured HBM copy peak; not the bound",
-                         "hbm_frac": (6.549e9 * n / (1 << 20)) / ((dsm_ms / max(dsm_launches, 1)) * 1e-3) / 6548.2e9},
+                         # committed capture profiles/r01_ncu_final_dsm.txt (4.752 GB + 1.850 GB); scaled if --batch-log2 differs
+                         "traffic": 6.602e9 * n / (1 << 20), "traffic_unit": "bytes per launch",
+                         "traffic_note": "ncu --set full, profiles/r01_ncu_final_dsm.txt: ~6.3 KB per item (per-item table "
+                                         "write + reads, comb gathers) = 0.29 TB/s, 4.5 % of the measured HBM copy peak; not the bound",
+                         "hbm_frac": (6.602e9 * n / (1 << 20)) / ((dsm_ms / max(dsm_launches, 1)) * 1e-3) / 6548.2e9},
             "cpu_baseline": cpu,
             "scalar_base_mult_ops_per_sec": sbm,
             "other_paths": other,
