@@ -771,13 +771,14 @@ S256_HD void item_scalar_mult_ct(size_t i, const apt *aff, const uint8_t *k32, c
 #pragma unroll 2
 #endif
             for (uint32_t j = 1; j <= (uint32_t)CTM_TS; j++) {
-                uint32_t m = 0u - (uint32_t)(j == mag);
+                // one register select per word (SEL): every entry is read, no branch, no address depends on mag
+                const bool hit = j == mag;
                 pt e = T.load((int)j - 1);
 #pragma unroll
                 for (int w = 0; w < 8; w++) {
-                    q.x.v[w] |= e.x.v[w] & m;
-                    q.y.v[w] |= e.y.v[w] & m;
-                    q.z.v[w] |= e.z.v[w] & m;
+                    q.x.v[w] = hit ? e.x.v[w] : q.x.v[w];
+                    q.y.v[w] = hit ? e.y.v[w] : q.y.v[w];
+                    q.z.v[w] = hit ? e.z.v[w] : q.z.v[w];
                 }
             }
             q.y.v[0] |= (uint32_t)(mag == 0);  // digit 0 -> (0 : 1 : 0)
