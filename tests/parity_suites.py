@@ -270,6 +270,13 @@ def check_double_scalar_mult(be, o, n=96):
     for j, s in enumerate(load_golden("kats.json")["glv_split_scalars"]):
         if 9 + j < n:
             u2[9 + j] = int(s, 16)
+    # boundaries of the signed 22-bit comb recoding of u1 (kernels.cuh comb_digit): a digit of exactly
+    # 2^21 (last table entry), 2^21 + 1 (-> -(2^21 - 1) with a carry), a run of carries, the top window
+    edge_u1 = [2**21, 2**21 + 1, 2**22 - 1, 2**22, (2**21 + 1) * sum(2**(22 * w) for w in range(11)),
+               sum((2**22 - 1) << (22 * w) for w in range(11)), N - 1, N - 2**21, 2**242, 2**255 + 2**21 + 1]
+    for j, v in enumerate(edge_u1):
+        if 40 + j < n:
+            u1[40 + j] = v
     pts, _ = o.batch_scalar_base_mult(rows([b32(x) for x in d], 32))
     U1, U2 = rows([b32(x) for x in u1], 32), rows([b32(x) for x in u2], 32)
     got, st = be.double_scalar_mult_basepoint_vartime(U1, U2, pts)
