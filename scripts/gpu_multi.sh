@@ -4,7 +4,7 @@ N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/gpus_$N.txt
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
-    bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench rc=$?"
+    bench.py --gpus $N --skip-cpu-baseline > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench rc=$?"
 cat gpurun_out/bench_n$N.json | cut -c1-900; tail -3 gpurun_out/bench_n$N.err
 LOG2N=20 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 \
     scripts/msm_nccl.py > gpurun_out/msm_n$N.json 2> gpurun_out/msm_n$N.err; echo "msm rc=$?"
