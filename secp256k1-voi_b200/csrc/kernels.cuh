@@ -517,7 +517,7 @@ S256_HD void group_finish_affine(size_t t, size_t stride, size_t n, const pt *re
         if (mode == 0) {
 #if defined(__CUDA_ARCH__)
             const size_t i0 = i - lane;  // first item of this warp's block of rows
-            if (full_warp && i0 + 32 <= n && (i0 & 15) == 0) {
+            if (full_warp && i0 + 32 <= n && (((size_t)(out + 65 * i0)) & 15u) == 0) {
                 uint8_t *o = stage + 65 * lane;
                 o[0] = (uint8_t)(keep ? 0x04 : 0x00);
                 fe_to_be32(o + 1, x);

@@ -197,6 +197,31 @@ def test_pinned_buffers(s256, oracle):
         eng.close()
 
 
+def test_misaligned_device_inputs(engine, oracle):
+    """The kernels use 128-bit loads when a row is 16-byte aligned and must fall back to byte loads when the
+    caller's device pointer is not (a tensor view at an odd offset)."""
+    import torch
+
+    def odd(a):
+        a = np.ascontiguousarray(a)
+        buf = torch.empty(a.size + 1, dtype=torch.uint8, device="cuda")
+        v = buf[1:].view(a.shape)
+        v.copy_(torch.from_numpy(a))
+        assert v.data_ptr() % 2 == 1 and v.is_contiguous()
+        return v
+    n = 700
+    w = ps.synth.ecdsa_batch(n, ps.oracle_base_mult(oracle))
+    ok = engine.ecdsa_verify(odd(w["pk65"]), odd(w["digest32"]), odd(w["sig64"]))
+    assert np.array_equal(ok.cpu().numpy(), w["expected"])
+    ks = ps.synth.base_mult_scalars(n)
+    out, st = engine.scalar_base_mult(odd(ks))
+    exp, est = oracle.batch_scalar_base_mult(ks)
+    assert np.array_equal(out.cpu().numpy(), exp) and np.array_equal(st.cpu().numpy(), est)
+    ws = ps.synth.schnorr_batch(n, ps.oracle_base_mult(oracle))
+    ok = engine.schnorr_verify(odd(ws["pkx32"]), odd(ws["msg"]), odd(ws["sig64"]))
+    assert np.array_equal(ok.cpu().numpy(), ws["expected"])
+
+
 def torch_cuda(a):
     import torch
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
