@@ -577,10 +577,10 @@ S256_HD void group_finish(size_t t, size_t stride, size_t n, const pt *res, cons
 
 // ---------------------------------------------------------------------------
 // constant-time fixed-base multiplication (point_mul_table.go:168-194): no
-// doublings, one mixed addition per 4-bit window.  The scalar is recoded
-// branch-free into signed digits d_w in [-7, 8] (65 windows), every window
-// scans all 8 table entries with masks (the GPU counterpart of
-// point_mul_table_amd64.s:81-130) -- the table is staged in shared memory and
+// doublings, one mixed addition per WB-bit window.  The scalar is recoded
+// branch-free into signed digits d_w in [-(2^(WB-1) - 1), 2^(WB-1)], every window
+// reads all 2^(WB-1) table entries and keeps one by register select (the GPU
+// counterpart of point_mul_table_amd64.s:81-130) -- the table is staged in shared memory and
 // every lane reads the same address, so neither the address stream nor the
 // bank pattern depends on the scalar -- the sign is applied by select, and
 // digit 0 is resolved by select after a dummy add (point_mul_table.go:118-129).
@@ -628,10 +628,10 @@ S256_HD void item_base_mult_ct(pt &acc, const sc &k, const apt *tab /* [NW][SZ] 
     }
 }
 
-// Small batches: the 65 windows of one scalar are dealt round-robin to T lanes (window j*T + part in
+// Small batches: the windows of one scalar are dealt round-robin to T lanes (window j*T + part in
 // iteration j, so the whole warp stays in lockstep); the caller folds the T partial points with
 // complete additions.  Digits are recoded first (carry chain) into a local array that is then read
-// at an index depending only on the lane number.  Same table, same masks, same selects as above.
+// at an index depending only on the lane number.  Same selects as above, over the 5-bit table.
 template <int CT_WB = S256_CT_WB_SMALL>
 S256_HD void item_base_mult_ct_part(pt &acc, const sc &k, const apt *tab, int part, int T) {
     constexpr int CT_NW = ct_cfg<CT_WB>::NW, CT_SZ = ct_cfg<CT_WB>::SZ;
