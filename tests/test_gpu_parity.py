@@ -177,6 +177,49 @@ def test_host_pipeline_chunk_shapes(s256):
         eng.close()
 
 
+def test_host_pipeline_other_paths(s256, oracle):
+    """The four-part host pipeline (ctx.h pipelined) of the other entry points: a pipelined chunk of 2^18
+    plus a short second chunk, checked by closed forms / round trips on everything and by the oracle on a
+    sample that straddles every sub-chunk boundary."""
+    cap = 1 << 18
+    eng = s256.Engine(device=0, max_batch=cap)
+    try:
+        n = cap + 5000
+        cuts = [0, cap // 16, cap // 4, cap // 8 * 5, cap, n]
+        sample = sorted({min(max(c + d, 0), n - 1) for c in cuts for d in (-2, -1, 0, 1, 127, 128)})
+        ks = ps.synth.base_mult_scalars(n)
+        pts, st = eng.scalar_base_mult(ks)
+        eo, es = oracle.batch_scalar_base_mult(ks[sample])
+        assert np.array_equal(pts[sample], eo) and np.array_equal(st[sample], es)
+        we = ps.synth.ecdh_batch(n, eng.scalar_base_mult)
+        x, xst = eng.ecdh(we["k32"], we["pt65"])
+        exp, _ = eng.scalar_base_mult(we["closed_form_scalar"])
+        assert np.array_equal(x, exp[:, 1:33]) and (xst == 1).all()
+        full, fst = eng.scalar_mult(we["k32"], we["pt65"])
+        assert np.array_equal(full, exp) and (fst == 1).all()
+        ws = ps.synth.schnorr_batch(n, eng.scalar_base_mult)
+        assert np.array_equal(eng.schnorr_verify(ws["pkx32"], ws["msg"], ws["sig64"]), ws["expected"])
+        w = ps.synth.ecdsa_batch(n, eng.scalar_base_mult, corrupt_every=0)
+        priv = np.frombuffer(b"".join(ps.synth._nonzero_mod_n(v).to_bytes(32, "big")
+                                      for v in ps.synth._stream_ints(b"key", 0, n, ps.synth.SEED)), np.uint8).reshape(n, 32)
+        sig, rec, sst = eng.ecdsa_sign_rfc6979(priv, w["digest32"])
+        assert (sst == 1).all()
+        es_, er_, est_ = oracle.batch_ecdsa_sign_rfc6979(priv[sample], w["digest32"][sample])
+        assert np.array_equal(sig[sample], es_) and np.array_equal(rec[sample], er_)
+        assert eng.ecdsa_verify(w["pk65"], w["digest32"], sig).all()
+        pk, pst = eng.ecdsa_recover(w["digest32"], np.concatenate([sig, rec.reshape(-1, 1)], axis=1))
+        assert np.array_equal(pk, w["pk65"]) and (pst == 1).all()
+        ssig, sst2 = eng.schnorr_sign(priv, w["digest32"], ks)
+        pub, _ = eng.scalar_base_mult(priv)
+        assert (sst2 == 1).all() and eng.schnorr_verify(pub[:, 1:33].copy(), w["digest32"], ssig).all()
+        u1 = ps.synth.base_mult_scalars(n, start=5)
+        d, dst_ = eng.double_scalar_mult_basepoint_vartime(u1, we["k32"], we["pt65"])
+        do, dso = oracle.batch_double_scalar_mult(u1[sample], we["k32"][sample], we["pt65"][sample])
+        assert np.array_equal(d[sample], do) and np.array_equal(dst_[sample], dso)
+    finally:
+        eng.close()
+
+
 def test_pinned_buffers(s256, oracle):
     """s256_host_alloc: page-locked inputs and engine-owned page-locked results give the same bytes as the
     pageable path; a result view is only reused by the next call of the same method."""
