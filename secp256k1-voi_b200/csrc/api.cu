@@ -414,6 +414,7 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
         s256_ct_kernels_init();
         if (CT_SMEM_BYTES)
             cudaFuncSetAttribute(k_scalar_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM_BYTES);
+        cudaFuncSetAttribute(k_scalar_mult_ct, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         const char *pp = getenv("S256_PIPE_PARTS");
         if (pp && atoi(pp) >= 0 && atoi(pp) <= 16) ctx->pipe_parts = atoi(pp);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);

@@ -4,6 +4,8 @@
 #endif
 #include "kernels.cuh"
 #include "launchers.h"
+#include <cstdio>
+#include <cstdlib>
 
 using namespace s256;
 // 16 warps per SM in both configurations; the table (NW * SZ * 64 bytes of shared memory per CTA) decides
@@ -14,6 +16,9 @@ using namespace s256;
 #define S256_BM_MINB 4
 #endif
 #define S256_BM_MINB_BIG 2
+#ifndef S256_BM_SPLIT4_MAX
+#define S256_BM_SPLIT4_MAX 16384
+#endif
 constexpr size_t CT_BYTES_BIG = (size_t)ct_cfg<CT_WB>::NW * ct_cfg<CT_WB>::SZ * sizeof(apt);
 constexpr size_t CT_BYTES_SMALL = (size_t)ct_cfg<CT_WB_SMALL>::NW * ct_cfg<CT_WB_SMALL>::SZ * sizeof(apt);
 
@@ -27,7 +32,12 @@ __global__ void __launch_bounds__(S256_TPB_BIG, S256_BM_MINB_BIG)
         for (int v = threadIdx.x; v < nvec; v += blockDim.x) smem_raw[v] = src[v];
     }
     __syncthreads();
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // warps of 32 consecutive items are dealt round-robin over the CTAs (warp g -> CTA g % grid), so that a
+    // batch that does not fill every resident CTA still loads all SMs evenly
+    const size_t G = gridDim.x, wpb = blockDim.x / 32, lane = threadIdx.x & 31;
+    for (size_t g = blockIdx.x + G * (threadIdx.x / 32); g * 32 < n; g += G * wpb) {
+        size_t i = g * 32 + lane;
+        if (i >= n) break;
         sc k;
         sc_from_be32(k, k32 + 32 * i);
         pt acc;
@@ -73,22 +83,37 @@ void s256_ct_kernels_init() {
     cudaFuncSetAttribute(k_base_mult_ct_split<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_SMALL);
     cudaFuncSetAttribute(k_base_mult_ct_split<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_SMALL);
     cudaFuncSetAttribute(k_base_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_BIG);
+    // ask for the largest shared-memory carve-out: without the hint the driver sizes it for ONE CTA and the
+    // second (fourth) CTA of an SM waits for the first to retire
+    cudaFuncSetAttribute(k_base_mult_ct, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_base_mult_ct_split<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_base_mult_ct_split<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (getenv("S256_TRACE")) {
+        int a = 0, b = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_base_mult_ct, S256_TPB_BIG, CT_BYTES_BIG);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_base_mult_ct_split<8>, S256_TPB, CT_BYTES_SMALL);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, k_base_mult_ct);
+        fprintf(stderr, "[s256 trace] k_base_mult_ct: %d CTAs/SM (regs %d, static smem %zu, dyn %zu); split<8>: %d CTAs/SM\n", a,
+                fa.numRegs, fa.sharedSizeBytes, CT_BYTES_BIG, b);
+    }
 }
 // tab_big: [NW(6)][SZ(6)], tab_small: [NW(5)][SZ(5)] (ctx->ct_tab, ctx->ct_tab_small)
 void s256_launch_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_big, const apt *tab_small, pt *res,
                               cudaStream_t s) {
     if (n == 0) return;
-    // small batches are latency bound: deal the windows of each scalar to 8 / 4 lanes
+    // small batches are latency bound: deal the windows of each scalar to 8 / 4 lanes (16 lanes measured
+    // slower at n = 4096: 0.227 against 0.198 ms)
     if (n <= 8192) {
         k_base_mult_ct_split<8><<<(unsigned)((n * 8 + S256_TPB - 1) / S256_TPB), S256_TPB, CT_BYTES_SMALL, s>>>(k32, n, tab_small, res);
         return;
     }
-    if (n <= 32768) {
+    if (n <= (size_t)S256_BM_SPLIT4_MAX) {
         k_base_mult_ct_split<4><<<(unsigned)((n * 4 + S256_TPB - 1) / S256_TPB), S256_TPB, CT_BYTES_SMALL, s>>>(k32, n, tab_small, res);
         return;
     }
-    unsigned grid = (unsigned)((n + S256_TPB_BIG - 1) / S256_TPB_BIG);
+    size_t warps = (n + 31) / 32;
     unsigned maxg = 148u * S256_BM_MINB_BIG;
-    if (grid > maxg) grid = maxg;
+    unsigned grid = warps < maxg ? (unsigned)warps : maxg;
     k_base_mult_ct<<<grid, S256_TPB_BIG, CT_BYTES_BIG, s>>>(k32, n, tab_big, res);
 }
