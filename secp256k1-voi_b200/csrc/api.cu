@@ -390,6 +390,7 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
     ctx->cap = max_batch ? max_batch : ((size_t)1 << 20);
     dev_guard g(device);
     int rc = ctx_alloc(ctx);
+    if (rc != S256_SUCCESS && cudaGetLastError() == cudaErrorMemoryAllocation) rc = S256_ERR_NOMEM;  // also clears the error
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // stream2 feeds stream: its short kernels go first
     if (rc == S256_SUCCESS && (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||

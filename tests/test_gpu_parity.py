@@ -220,6 +220,22 @@ def test_host_pipeline_other_paths(s256, oracle):
         eng.close()
 
 
+def test_init_out_of_memory_is_an_error_code(s256, oracle):
+    """A context too large for the device comes back as an error (no abort, nothing leaked), and the
+    next context works."""
+    with pytest.raises(s256.S256Error) as ei:
+        s256.Engine(device=0, max_batch=1 << 28)   # 2^28 items x 1.7 KB of scratch > 180 GB
+    assert "out of memory" in str(ei.value) or "rc=-4" in str(ei.value)
+    eng = s256.Engine(device=0, max_batch=1024)
+    try:
+        ks = ps.synth.base_mult_scalars(16)
+        out, st = eng.scalar_base_mult(ks)
+        exp, est = oracle.batch_scalar_base_mult(ks)
+        assert np.array_equal(out, exp) and np.array_equal(st, est)
+    finally:
+        eng.close()
+
+
 def test_pinned_buffers(s256, oracle):
     """s256_host_alloc: page-locked inputs and engine-owned page-locked results give the same bytes as the
     pageable path; a result view is only reused by the next call of the same method."""
