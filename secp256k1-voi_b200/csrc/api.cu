@@ -275,6 +275,7 @@ __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a3
             case 4: fe_sqrt(r, a); break;
             case 5: fe_mul_small(r, a, 21u); break;
             case 6: fe_sqr(r, a); break;
+            case 7: fe_invert_fermat(r, a); break;
             // 8 + op: the variable-time flavour (fe_vt.cuh) of the same operation
             case 8: fe_mul_vt(r, a, b); break;
             case 9: fe_add_vt(r, a, b); break;
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a3
             case 16: sc_mul(r, a, b); break;
             case 17: sc_add(r, a, b); break;
             case 18: sc_invert(r, a); break;
+            case 19: sc_invert_fermat(r, a); break;
             default: r = sc_zero();
         }
         sc_to_be32(out32 + 32 * i, r);
@@ -1017,7 +1019,8 @@ extern "C" int s256_microbench_imad(s256_ctx *ctx, int iters, double *mac32_per_
 extern "C" double s256_mac32_per_item(const char *name) {
     const double M = 73, S = 45, SM = 9, ZN = 139;
     const double dbl = 6 * M + 2 * S + SM, add = 12 * M + 2 * SM, mix = 11 * M + 2 * SM;
-    const double inv_fe = 255 * S + 15 * M, sqrt_fe = 254 * S + 13 * M + 2 * S + M, inv_sc = 330 * ZN;
+    // inversions are safegcd (modinv.cuh): 20 batches x (54 + 36) 32x32->64 products, whatever the modulus
+    const double inv_fe = 20 * 90, sqrt_fe = 254 * S + 13 * M + 2 * S + M, inv_sc = 20 * 90;
     const double oncurve = 2 * S + M;
     const double table = (DSM_TS / 2) * dbl + (DSM_TS / 2 - 1) * mix;
     const double ladder = (DSM_ND - 1) * DSM_W * dbl + 2 * DSM_ND * add + DSM_ND * M;

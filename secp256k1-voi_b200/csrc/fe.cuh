@@ -580,7 +580,8 @@ S256_HD void fe_pow_x223(fe &x223, fe &x22, fe &x2, fe &x3, const fe &a) {
     fe_sqr_n(t, x176, 44); fe_mul(t, t, x44);
     fe_sqr_n(t, t, 3); fe_mul(x223, t, x3);
 }
-S256_HD void fe_invert(fe &r, const fe &a) {
+// x^(p-2) by the reference's addition chain (field_invert.go:11): kept as the cross-check of fe_invert
+S256_HD void fe_invert_fermat(fe &r, const fe &a) {
     fe x223, x22, x2, x3, t;
     fe_pow_x223(x223, x22, x2, x3, a);
     fe_sqr_n(t, x223, 23); fe_mul(t, t, x22);
@@ -602,4 +603,15 @@ S256_HD uint32_t fe_sqrt(fe &r, const fe &a) {
     return ok;
 }
 
+}  // namespace s256
+
+#include "modinv.cuh"
+
+namespace s256 {
+// a^-1 mod p, Invert(0) = 0 (field_invert.go:11): safegcd (modinv.cuh), constant time
+S256_HD void fe_invert(fe &r, const fe &a) {
+    fe t;
+    fe_normalize(t, a);
+    mi_invert(r.v, t.v, mi_modulus_p());
+}
 }  // namespace s256

@@ -332,7 +332,7 @@ static __host__ __device__ S256_NOINLINE
 #else
 inline
 #endif
-void sc_invert(sc &r, const sc &a) {
+void sc_invert_fermat(sc &r, const sc &a) {
     sc tbl[16];
     tbl[0] = sc_one();
     tbl[1] = a;
@@ -384,6 +384,15 @@ void sc_invert(sc &r, const sc &a) {
         if (nib) sc_mul(x, x, tbl[nib]);  // exponent is public
     }
     r = x;
+}
+// a^-1 mod n, Invert(0) = 0 (scalar_invert.go:11): safegcd (modinv.cuh), constant time; a is canonical
+#if defined(__CUDACC__)
+static __host__ __device__ S256_NOINLINE
+#else
+inline
+#endif
+void sc_invert(sc &r, const sc &a) {
+    mi_invert(r.v, a.v, mi_modulus_n());
 }
 
 // point_mul_glv.go:119-189 -- round(k * g / 2^384): limbs 12..15 of the

@@ -350,6 +350,7 @@ EXPORT void sim_field_op(int op, const uint8_t *a32, const uint8_t *b32, size_t 
                 case 4: fe_sqrt(r, a); break;
                 case 5: fe_mul_small(r, a, 21u); break;
                 case 6: fe_sqr(r, a); break;
+                case 7: fe_invert_fermat(r, a); break;
                 case 8: fe_mul_vt(r, a, b); break;
                 case 9: fe_add_vt(r, a, b); break;
                 case 10: fe_sub_vt(r, a, b); break;
@@ -368,6 +369,7 @@ EXPORT void sim_field_op(int op, const uint8_t *a32, const uint8_t *b32, size_t 
                 case 16: sc_mul(r, a, b); break;
                 case 17: sc_add(r, a, b); break;
                 case 18: sc_invert(r, a); break;
+                case 19: sc_invert_fermat(r, a); break;
                 default: r = sc_zero();
             }
             sc_to_be32(out32 + 32 * i, r);
