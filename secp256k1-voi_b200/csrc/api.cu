@@ -543,14 +543,15 @@ extern "C" int s256_ecdsa_verify_dev(s256_ctx *ctx, const uint8_t *pk, const uin
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
-// Host-pointer verification as a pipeline over three sub-chunks of 1/16, 3/16 and 12/16 of the chunk.
+// Host-pointer verification as a pipeline over two sub-chunks, 3/32 and 29/32 of the chunk.
 // Two feeder streams (high priority) carry the inputs in -- digests + signatures then the scalar kernel
 // on one, public keys then the decode kernel on the other -- and the main stream runs the ladder and
 // the final check of each sub-chunk as soon as both of its events have fired.  The ladder therefore
-// starts after 1/16 of the copy, its first sub-chunk is a single wave that leaves SM slots free for
-// the next scalar kernel, and the remaining 3 ms of PCIe traffic (2^20 items) hide under ladders.
-// Equal parts lose: the batched-inversion kernel is latency bound (~1 ms whatever its size) and would
-// sit in front of every ladder.
+// starts after 3/32 of the copy, and the remaining 2.8 ms of PCIe traffic (2^20 items) and the second
+// scalar kernel hide under the first ladder.  Measured schedules (ms per 2^20 call, S256_VERIFY_CUTS in
+// 64ths): 6 -> 23.86, 8 -> 24.10, 12 -> 23.98, 16 -> 24.29, 4 -> 24.31, 4,16 -> 24.27, 2,8,32 -> 24.56,
+// 2,6,16,36 -> 25.33: every extra part costs a latency-bound scalar kernel that takes SM slots from a
+// ladder, and equal parts lose for the same reason.
 // S256_TRACE=1: device timestamps of the pipeline stages, printed per call (debug aid, off by default)
 struct stage_trace {
     bool on;
@@ -584,12 +585,28 @@ struct stage_trace {
 static int verify_pipelined(s256_ctx *ctx, const uint8_t *pk, const uint8_t *dg, const uint8_t *sig, uint32_t flags,
                             size_t off, size_t c, uint8_t *ok) {
     cudaStream_t feed = ctx->stream2, feed_pk = ctx->stream3, mainst = ctx->stream;
-    const int P = 3;
-    size_t cut[P + 1] = {0, (c / 16 + 127) & ~(size_t)127, (c / 4 + 127) & ~(size_t)127, c};
+    // cut points in 64ths of the chunk; S256_VERIFY_CUTS="a,b,.." (each in 1..63, increasing) overrides them
+    int P = 2;
+    size_t cut[6] = {0, (c / 64 * 6 + 127) & ~(size_t)127, c, c, c, c};
+    if (const char *cs = getenv("S256_VERIFY_CUTS")) {
+        int k = 1, prev = 0;
+        for (const char *q = cs; *q && k < 5;) {
+            int v = atoi(q);
+            if (v <= prev || v >= 64) break;
+            cut[k++] = (c / 64 * (size_t)v + 127) & ~(size_t)127;
+            prev = v;
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+        cut[k] = c;
+        P = k;
+    }
     stage_trace tr(feed);
-    static const char *const names[3][4] = {{"sig+dg A", "scalars A", "decode A", "ladder A"},
+    static const char *const names[5][4] = {{"sig+dg A", "scalars A", "decode A", "ladder A"},
                                             {"sig+dg B", "scalars B", "decode B", "ladder B"},
-                                            {"sig+dg C", "scalars C", "decode C", "ladder C"}};
+                                            {"sig+dg C", "scalars C", "decode C", "ladder C"},
+                                            {"sig+dg D", "scalars D", "decode D", "ladder D"},
+                                            {"sig+dg E", "scalars E", "decode E", "ladder E"}};
     for (int k = 0; k < P; k++) {
         size_t so = cut[k], n = cut[k + 1] - cut[k];
         view v = view_at(ctx, so);

@@ -57,7 +57,7 @@ struct s256_ctx {
     // sub-chunks per host-pointer call (S256_PIPE_PARTS).  Measured (scripts/e2e_parts.py): splitting does not
     // pay -- the batched-inversion kernel is latency bound, so its cost multiplies with the part count.
     int pipe_parts = 1;
-    cudaEvent_t ev_decode = nullptr, ev_pipe[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_decode = nullptr, ev_pipe[10] = {};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dsm_events;
 };
 
