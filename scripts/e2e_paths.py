@@ -36,7 +36,7 @@ ms, (pk, st) = t(lambda: eng.ecdsa_recover(dg, sig65)); out["ecdsa_recover"] = m
 assert np.array_equal(pk, w["pk65"]) and (st == 1).all()
 print(json.dumps({k_: round(v, 3) for k_, v in out.items()}))
 ''' % ROOT
-for parts in ("0", "1"):
-    env = dict(os.environ, S256_PIPE_PARTS=parts)
+for cuts in os.environ.get("CUTS_LIST", "4,16,40").split(";"):
+    env = dict(os.environ, S256_PIPE_CUTS=cuts)
     p = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=1200)
-    print("S256_PIPE_PARTS=" + parts, p.stdout.strip().splitlines()[-1] if p.stdout.strip() else p.stderr[-600:], flush=True)
+    print("S256_PIPE_CUTS=" + cuts, p.stdout.strip().splitlines()[-1] if p.stdout.strip() else p.stderr[-600:], flush=True)

@@ -732,7 +732,7 @@ extern "C" int s256_schnorr_verify(s256_ctx *ctx, const uint8_t *pkx, const uint
         if (r != S256_SUCCESS) return r;
         CK(cudaMemcpyAsync(ok + off, v.st, c, cudaMemcpyDeviceToHost, ps));
         return S256_SUCCESS;
-    });
+    }, /*small_output=*/true);
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
 

@@ -152,13 +152,14 @@ static int for_chunks(s256_ctx *ctx, size_t n, F body) {
 // Host-pointer calls: the chunk is cut into sub-chunks that alternate between two streams, each
 // doing its own H2D -> kernels -> D2H on a disjoint scratch window, so the copies of one sub-chunk
 // overlap the kernels of the other.  body(view, global offset, count, stream).
-// Default (pipe_parts == 1, "auto"): chunks of >= 2^18 items are cut at 1/16, 4/16 and 10/16 -- a small
+// Default (pipe_parts == 1, "auto"): chunks of >= 2^18 items are cut at 6/64, 24/64 and 44/64 -- a small
 // first part so that the main kernel starts early, growing parts so that the copies and the short
 // latency-bound preparation kernels of part k+1 hide under the main kernel of part k, and a last part
-// small enough that its trailing D2H stays short.  S256_PIPE_PARTS=n > 1 forces n equal parts
+// small enough that its trailing D2H stays short; entry points that return one byte per item use two
+// parts (1/8, 7/8).  Measured in DESIGN.md section 5; S256_PIPE_CUTS overrides the cut points.  S256_PIPE_PARTS=n > 1 forces n equal parts
 // (measured slower); S256_PIPE_PARTS=0 disables the split.
 template <typename F>
-static int pipelined(s256_ctx *ctx, size_t n, F body) {
+static int pipelined(s256_ctx *ctx, size_t n, F body, bool small_output = false) {
     const size_t min_sub = 65536;
     for (size_t off = 0; off < n; off += ctx->cap) {
         size_t c = n - off < ctx->cap ? n - off : ctx->cap;
@@ -166,10 +167,27 @@ static int pipelined(s256_ctx *ctx, size_t n, F body) {
         int np = 1;
         cut[0] = 0;
         if (ctx->pipe_parts == 1 && c >= ((size_t)1 << 18)) {
-            np = 4;
-            cut[1] = (c / 16 + 127) & ~(size_t)127;
-            cut[2] = (c / 4 + 127) & ~(size_t)127;
-            cut[3] = (c / 8 * 5 + 127) & ~(size_t)127;
+            if (small_output) {  // one byte per item comes back: no trailing D2H to keep short
+                np = 2;
+                cut[1] = (c / 8 + 127) & ~(size_t)127;
+            } else {
+                np = 4;
+                cut[1] = (c / 64 * 6 + 127) & ~(size_t)127;
+                cut[2] = (c / 64 * 24 + 127) & ~(size_t)127;
+                cut[3] = (c / 64 * 44 + 127) & ~(size_t)127;
+            }
+            if (const char *cs = getenv("S256_PIPE_CUTS")) {  // tuning knob: cut points in 64ths, increasing
+                int k = 1, prev = 0;
+                for (const char *q = cs; *q && k < 8;) {
+                    int v = atoi(q);
+                    if (v <= prev || v >= 64) break;
+                    cut[k++] = (c / 64 * (size_t)v + 127) & ~(size_t)127;
+                    prev = v;
+                    while (*q && *q != ',') q++;
+                    if (*q == ',') q++;
+                }
+                np = k;
+            }
         } else if (ctx->pipe_parts > 1) {
             size_t parts = c / min_sub;
             if (parts > (size_t)ctx->pipe_parts) parts = (size_t)ctx->pipe_parts;
