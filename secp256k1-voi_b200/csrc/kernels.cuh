@@ -825,9 +825,14 @@ S256_HD uint8_t item_rfc6979_nonce(uint8_t kout[32], const uint8_t *priv32, cons
         xw[i] = d.v[7 - i];
         hw[i] = e.v[7 - i];
     }
+    // every HMAC under one key shares the key's two pad states; those of the initial all-zero K are constants
+    uint32_t ist[8], ost[8];
+    hmac_zero_key_states(ist, ost);
     for (uint32_t oct = 0; oct < 2; oct++) {
-        hmac_k32_m97(K, K, V, oct, xw, hw);
-        hmac_k32_m32(V, K, V);
+        hmac_st_m97(K, ist, ost, V, oct, xw, hw);
+        hmac_pad_state(ist, K, 0x36363636u);
+        hmac_pad_state(ost, K, 0x5c5c5c5cu);
+        hmac_st_m32(V, ist, ost, V);
     }
     uint32_t ok = 0;
     sc k;
@@ -843,9 +848,11 @@ S256_HD uint8_t item_rfc6979_nonce(uint8_t kout[32], const uint8_t *priv32, cons
             hmac_sha256_k32(Kb, Kb, m, 33);
             for (int i = 0; i < 8; i++)
                 K[i] = ((uint32_t)Kb[4 * i] << 24) | ((uint32_t)Kb[4 * i + 1] << 16) | ((uint32_t)Kb[4 * i + 2] << 8) | Kb[4 * i + 3];
-            hmac_k32_m32(V, K, V);
+            hmac_pad_state(ist, K, 0x36363636u);
+            hmac_pad_state(ost, K, 0x5c5c5c5cu);
+            hmac_st_m32(V, ist, ost, V);
         }
-        hmac_k32_m32(V, K, V);
+        hmac_st_m32(V, ist, ost, V);
         uint32_t l[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) l[i] = V[7 - i];

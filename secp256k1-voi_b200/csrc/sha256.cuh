@@ -204,8 +204,8 @@ S256_HD void hmac_pad_state(uint32_t st[8], const uint32_t key[8], uint32_t pad)
     sha_iv(st);
     sha256_compress(st, w);
 }
-// out = H(opad block || inner digest): the outer half of every HMAC
-S256_HD void hmac_outer(uint32_t out[8], const uint32_t key[8], const uint32_t inner[8]) {
+// out = H(opad block || inner digest): the outer half of every HMAC; ost = state after the opad block
+S256_HD void hmac_outer_st(uint32_t out[8], const uint32_t ost[8], const uint32_t inner[8]) {
     uint32_t w[16];
 #pragma unroll
     for (int i = 0; i < 8; i++) w[i] = inner[i];
@@ -213,27 +213,34 @@ S256_HD void hmac_outer(uint32_t out[8], const uint32_t key[8], const uint32_t i
 #pragma unroll
     for (int i = 9; i < 15; i++) w[i] = 0;
     w[15] = (64 + 32) * 8;
-    hmac_pad_state(out, key, 0x5c5c5c5cu);
-    sha256_compress(out, w);
+    uint32_t h[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = ost[i];
+    sha256_compress(h, w);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = h[i];
 }
-// out = HMAC(key, v), |v| = 32.  out may alias key or v.
-S256_HD void hmac_k32_m32(uint32_t out[8], const uint32_t key[8], const uint32_t v[8]) {
+// out = HMAC(key, v), |v| = 32, given the two pad states of the key.  out may alias v.
+S256_HD void hmac_st_m32(uint32_t out[8], const uint32_t ist[8], const uint32_t ost[8], const uint32_t v[8]) {
     uint32_t st[8], w[16];
 #pragma unroll
-    for (int i = 0; i < 8; i++) w[i] = v[i];
+    for (int i = 0; i < 8; i++) {
+        w[i] = v[i];
+        st[i] = ist[i];
+    }
     w[8] = 0x80000000u;
 #pragma unroll
     for (int i = 9; i < 15; i++) w[i] = 0;
     w[15] = (64 + 32) * 8;
-    hmac_pad_state(st, key, 0x36363636u);
     sha256_compress(st, w);
-    hmac_outer(out, key, st);
+    hmac_outer_st(out, ost, st);
 }
-// out = HMAC(key, v || oct || x || h), 32 + 1 + 32 + 32 bytes.  out may alias key.
-S256_HD void hmac_k32_m97(uint32_t out[8], const uint32_t key[8], const uint32_t v[8], uint32_t oct, const uint32_t x[8],
-                          const uint32_t h[8]) {
+// out = HMAC(key, v || oct || x || h), 32 + 1 + 32 + 32 bytes, given the two pad states of the key
+S256_HD void hmac_st_m97(uint32_t out[8], const uint32_t ist[8], const uint32_t ost[8], const uint32_t v[8], uint32_t oct,
+                         const uint32_t x[8], const uint32_t h[8]) {
     uint32_t st[8], w[16];
-    hmac_pad_state(st, key, 0x36363636u);
+#pragma unroll
+    for (int i = 0; i < 8; i++) st[i] = ist[i];
     // bytes 0..63: v, then oct and the first 31 bytes of x (everything after v is shifted by one byte)
 #pragma unroll
     for (int i = 0; i < 8; i++) w[i] = v[i];
@@ -250,7 +257,28 @@ S256_HD void hmac_k32_m97(uint32_t out[8], const uint32_t key[8], const uint32_t
     for (int i = 9; i < 15; i++) w[i] = 0;
     w[15] = (64 + 97) * 8;
     sha256_compress(st, w);
-    hmac_outer(out, key, st);
+    hmac_outer_st(out, ost, st);
+}
+// the same with the pad states derived from the key (2 more compressions)
+S256_HD void hmac_k32_m32(uint32_t out[8], const uint32_t key[8], const uint32_t v[8]) {
+    uint32_t ist[8], ost[8];
+    hmac_pad_state(ist, key, 0x36363636u);
+    hmac_pad_state(ost, key, 0x5c5c5c5cu);
+    hmac_st_m32(out, ist, ost, v);
+}
+S256_HD void hmac_k32_m97(uint32_t out[8], const uint32_t key[8], const uint32_t v[8], uint32_t oct, const uint32_t x[8],
+                          const uint32_t h[8]) {
+    uint32_t ist[8], ost[8];
+    hmac_pad_state(ist, key, 0x36363636u);
+    hmac_pad_state(ost, key, 0x5c5c5c5cu);
+    hmac_st_m97(out, ist, ost, v, oct, x, h);
+}
+// pad states of the all-zero key, the generator's initial K (SHA-256 of 64 bytes 0x36 / 0x5c from the IV)
+S256_HD void hmac_zero_key_states(uint32_t ist[8], uint32_t ost[8]) {
+    ist[0] = 0xf454deadu; ist[1] = 0x9725214fu; ist[2] = 0x90daf2a0u; ist[3] = 0xdf1228eau;
+    ist[4] = 0x64e5750fu; ist[5] = 0xa3924181u; ist[6] = 0x824a932bu; ist[7] = 0xf8e04e32u;
+    ost[0] = 0xd385480fu; ost[1] = 0x7abb6477u; ost[2] = 0x37c9c538u; ost[3] = 0x5dd82467u;
+    ost[4] = 0x8e043a72u; ost[5] = 0x753434b0u; ost[6] = 0xdeb82818u; ost[7] = 0x361d45a6u;
 }
 
 // BIP-340 tagged hashes (secec/bitcoin/schnorr.go:34-36, 309-320): the state after the 64-byte
