@@ -140,7 +140,7 @@ EXPORT void sim_scalar_mult(const uint8_t *k32, const uint8_t *pt65, size_t n, i
     for (size_t i = 0; i < n; i++) s.pvalid[i] = item_decode_uncompressed(s.aff[i], pt65 + 65 * i);
     for (size_t i = 0; i < n; i++) {
         CtTableGlobal T{s.tbl.data() + i * (size_t)DSM_TS};
-        item_scalar_mult_ct(i, s.aff.data(), k32, T, s.res.data());
+        item_scalar_mult_ct_affine(i, s.aff.data(), k32, T, s.tbl.data() + i * (size_t)DSM_TS, s.res.data());
     }
     run_finish(s, n, true, false, mode, out, status, nullptr);
 }
@@ -172,7 +172,7 @@ EXPORT void sim_msm(const uint8_t *k32, const uint8_t *pt65, size_t n, int varti
     if (n && (!vartime || n < 32) && force_c == 0) {
         for (size_t i = 0; i < n; i++) {
             CtTableGlobal T{s.tbl.data() + i * (size_t)DSM_TS};
-            item_scalar_mult_ct(i, s.aff.data(), k32, T, s.res.data());
+            item_scalar_mult_ct_affine(i, s.aff.data(), k32, T, s.tbl.data() + i * (size_t)DSM_TS, s.res.data());
         }
         for (size_t i = 0; i < n; i++) pt_add(acc, acc, s.res[i]);
     } else if (n) {
