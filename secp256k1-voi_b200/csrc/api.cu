@@ -223,16 +223,10 @@ __global__ void __launch_bounds__(S256_TPB, S256_SM_MINB)
 #else
     CtTableShared<S256_TPB> T{threadIdx.x};
 #endif
-#ifdef S256_CT_PROJ_TABLE
-    item_scalar_mult_ct(i, aff, k32, T, res);
-#else
     item_scalar_mult_ct_affine(i, aff, k32, T, tbl + i * (size_t)DSM_TS, res);
-#endif
 }
 #ifdef S256_CT_TABLE_GLOBAL
 constexpr size_t CT_SMEM_BYTES = 0;
-#elif defined(S256_CT_PROJ_TABLE)
-constexpr size_t CT_SMEM_BYTES = (size_t)CTM_TS * 6 * S256_TPB * sizeof(uint4);
 #else
 constexpr size_t CT_SMEM_BYTES = (size_t)CTM_TS * 4 * S256_TPB * sizeof(uint4);
 #endif
@@ -1062,13 +1056,8 @@ extern "C" double s256_mac32_per_item(const char *name) {
     if (s == "schnorr_sign") return 2 * (CT_NW * mix + affine) + 2 * ZN;  // + ~9 SHA-256 blocks
     if (s == "ecdsa_sign_rfc6979") return CT_NW * mix + affine + (5 * ZN + inv_sc / INV_K);  // + 22 SHA-256 blocks
     if (s == "scalar_mult" || s == "ecdh") {
-#ifdef S256_CT_PROJ_TABLE
-        const double tab = (CTM_TS / 2) * dbl + (CTM_TS / 2 - 1) * mix;
-        const double lad = (CTM_ND - 1) * CTM_W * dbl + 2 * CTM_ND * add + CTM_ND * M;
-#else
         const double tab = (CTM_TS / 2) * dbl + (CTM_TS / 2 - 1) * mix + 5 * (CTM_TS - 1) * M + inv_fe;  // + normalisation
         const double lad = (CTM_ND - 1) * CTM_W * dbl + 2 * CTM_ND * mix + CTM_ND * M;
-#endif
         return oncurve + split + tab + lad + affine;
     }
     return 0.0;

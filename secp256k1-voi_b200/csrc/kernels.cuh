@@ -682,13 +682,12 @@ S256_HD void item_base_mult_ct_part(pt &acc, const sc &k, const apt *tab, int pa
     }
 }
 
-// Table storage policies for the ct ladder: per-item rows in global memory (host simulation, or
-// when shared memory is not used) and per-thread columns in shared memory ([entry][limb group][thread],
-// LDS.128 / STS.128 conflict-free).  Either way the address stream depends only on public values.
+// Table storage policies for the ct ladder's affine table: per-item rows in global memory (host
+// simulation, or when shared memory is not used) and per-thread columns in shared memory
+// ([entry][limb group][thread], LDS.128 / STS.128 conflict-free).  Either way the address stream depends
+// only on public values.
 struct CtTableGlobal {
     pt *T;
-    S256_HD void store(int j, const pt &p) const { T[j] = p; }
-    S256_HD pt load(int j) const { return T[j]; }
     // affine entries live behind the projective scratch rows of the same per-item region
     S256_HD void store_affine(int j, const apt &a) const { reinterpret_cast<apt *>(T + CTM_TS)[j] = a; }
     S256_HD apt load_affine(int j) const { return reinterpret_cast<const apt *>(T + CTM_TS)[j]; }
@@ -697,24 +696,6 @@ struct CtTableGlobal {
 template <int TPB>
 struct CtTableShared {
     uint32_t t;
-    __device__ __forceinline__ void store(int j, const pt &p) const {
-        extern __shared__ uint4 ct_smem[];
-        const uint32_t *w = p.x.v;  // x, y, z are contiguous: 24 words
-#pragma unroll
-        for (int g = 0; g < 6; g++)
-            ct_smem[(uint32_t)(j * 6 + g) * TPB + t] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
-    }
-    __device__ __forceinline__ pt load(int j) const {
-        extern __shared__ uint4 ct_smem[];
-        pt p;
-        uint32_t *w = p.x.v;
-#pragma unroll
-        for (int g = 0; g < 6; g++) {
-            uint4 q = ct_smem[(uint32_t)(j * 6 + g) * TPB + t];
-            w[4 * g] = q.x; w[4 * g + 1] = q.y; w[4 * g + 2] = q.z; w[4 * g + 3] = q.w;
-        }
-        return p;
-    }
     // affine entries: 16 words = 4 x uint4 per entry, same conflict-free column layout
     __device__ __forceinline__ void store_affine(int j, const apt &a) const {
         extern __shared__ uint4 ct_smem[];
@@ -835,81 +816,6 @@ S256_HD void item_scalar_mult_ct_affine(size_t i, const apt *aff, const uint8_t 
             pt sum;
             pt_add_mixed(sum, acc, q.x, q.y);
             pt_cmov(acc, sum, acc, zero);
-        }
-    }
-    res[i] = acc;
-}
-
-template <class TAB>
-S256_HD void item_scalar_mult_ct(size_t i, const apt *aff, const uint8_t *k32, const TAB &T, pt *res) {
-    {
-        apt P = aff[i];
-        pt cur;
-        pt_from_affine(cur, P);
-        T.store(0, cur);
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-        for (int k = 2; k <= CTM_TS; k += 2) {
-            pt h = T.load(k / 2 - 1);
-            pt_double(cur, h);
-            T.store(k - 1, cur);
-            if (k < CTM_TS) {
-                pt_add_mixed(cur, cur, P.x, P.y);
-                T.store(k, cur);
-            }
-        }
-    }
-    sc k;
-    sc_from_be32(k, k32 + 32 * i);
-    uint32_t m1[4], m2[4], neg1, neg2;
-    sc_split_glv_abs(m1, neg1, m2, neg2, k);
-    int8_t d1[CTM_ND], d2[CTM_ND];
-    glv_recode<CTM_W>::run(d1, m1);
-    glv_recode<CTM_W>::run(d2, m2);
-    pt acc;
-    pt_set_identity(acc);
-    const fe beta = fe_beta();
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-    for (int s = CTM_ND - 1; s >= 0; s--) {
-        if (s != CTM_ND - 1) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-            for (int q = 0; q < CTM_W; q++) pt_double(acc, acc);
-        }
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-        for (int h = 0; h < 2; h++) {
-            int32_t d = h ? (int32_t)d2[s] : (int32_t)d1[s];
-            uint32_t sign = (uint32_t)d >> 31;                                // 1 iff d < 0
-            uint32_t mag = (uint32_t)((d ^ -(int32_t)sign) + (int32_t)sign);  // |d|, branch-free
-            uint32_t neg = sign ^ (h ? neg2 : neg1);
-            pt q;
-            q.x = fe_zero();
-            q.y = fe_zero();
-            q.z = fe_zero();
-#if defined(__CUDA_ARCH__)
-#pragma unroll 2
-#endif
-            for (uint32_t j = 1; j <= (uint32_t)CTM_TS; j++) {
-                // one register select per word (SEL): every entry is read, no branch, no address depends on mag
-                const bool hit = j == mag;
-                pt e = T.load((int)j - 1);
-#pragma unroll
-                for (int w = 0; w < 8; w++) {
-                    q.x.v[w] = hit ? e.x.v[w] : q.x.v[w];
-                    q.y.v[w] = hit ? e.y.v[w] : q.y.v[w];
-                    q.z.v[w] = hit ? e.z.v[w] : q.z.v[w];
-                }
-            }
-            q.y.v[0] |= (uint32_t)(mag == 0);  // digit 0 -> (0 : 1 : 0)
-            if (h) fe_mul(q.x, q.x, beta);     // h is the (public) half index, not a secret
-            fe_cneg(q.y, q.y, neg);
-            pt_add(acc, acc, q);
         }
     }
     res[i] = acc;
