@@ -544,15 +544,17 @@ extern "C" int s256_ecdsa_verify_dev(s256_ctx *ctx, const uint8_t *pk, const uin
     });
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
-// Host-pointer verification as a pipeline over two sub-chunks, 3/32 and 29/32 of the chunk.
+// Host-pointer verification as a pipeline over two sub-chunks, 3/16 and 13/16 of the chunk.
 // Two feeder streams (high priority) carry the inputs in -- digests + signatures then the scalar kernel
 // on one, public keys then the decode kernel on the other -- and the main stream runs the ladder and
 // the final check of each sub-chunk as soon as both of its events have fired.  The ladder therefore
-// starts after 3/32 of the copy, and the remaining 2.8 ms of PCIe traffic (2^20 items) and the second
-// scalar kernel hide under the first ladder.  Measured schedules (ms per 2^20 call, S256_VERIFY_CUTS in
-// 64ths): 6 -> 23.86, 8 -> 24.10, 12 -> 23.98, 16 -> 24.29, 4 -> 24.31, 4,16 -> 24.27, 2,8,32 -> 24.56,
-// 2,6,16,36 -> 25.33: every extra part costs a latency-bound scalar kernel that takes SM slots from a
-// ladder, and equal parts lose for the same reason.
+// starts after 3/16 of the copy, and the rest of the PCIe traffic and the second scalar kernel hide
+// under the first ladder as long as the link sustains ~32 GB/s (a ladder consumes its 161 B/item at
+// 7.5 GB/s).  Measured schedules (ms per 2^20 call on one GPU, S256_VERIFY_CUTS in 64ths): 6 -> 23.86,
+// 8 -> 24.10, 12 -> 23.98, 16 -> 24.29, 4 -> 24.31, 4,16 -> 24.27, 2,8,32 -> 24.56, 2,6,16,36 -> 25.33:
+// every extra part costs a latency-bound scalar kernel that takes SM slots from a ladder.  With eight
+// GPUs copying at once each link gave ~34 GB/s and the 6/64 cut left a 2 ms bubble (26.1 ms per call),
+// hence 12/64.
 // S256_TRACE=1: device timestamps of the pipeline stages, printed per call (debug aid, off by default)
 struct stage_trace {
     bool on;
@@ -588,7 +590,7 @@ static int verify_pipelined(s256_ctx *ctx, const uint8_t *pk, const uint8_t *dg,
     cudaStream_t feed = ctx->stream2, feed_pk = ctx->stream3, mainst = ctx->stream;
     // cut points in 64ths of the chunk; S256_VERIFY_CUTS="a,b,.." (each in 1..63, increasing) overrides them
     int P = 2;
-    size_t cut[6] = {0, (c / 64 * 6 + 127) & ~(size_t)127, c, c, c, c};
+    size_t cut[6] = {0, (c / 64 * 12 + 127) & ~(size_t)127, c, c, c, c};
     if (const char *cs = getenv("S256_VERIFY_CUTS")) {
         int k = 1, prev = 0;
         for (const char *q = cs; *q && k < 5;) {
