@@ -75,3 +75,23 @@ def test_field_ops(a, b):
     assert int.from_bytes(hs.field_op(1, A, B)[0].tobytes(), "big") == (a + b) % P
     assert int.from_bytes(hs.field_op(2, A, B)[0].tobytes(), "big") == (a - b) % P
     assert int.from_bytes(hs.field_op(16, A, B)[0].tobytes(), "big") == (a % N) * (b % N) % N
+
+
+def test_safegcd_inversion_matches_fermat_and_pow():
+    """modinv.cuh (Bernstein-Yang divsteps) against Python's pow and against the reference's Fermat chains
+    (field_invert.go:11, scalar_invert.go:11) kept as fe_invert_fermat / sc_invert_fermat: random values plus
+    the structured ones a limb-boundary or sign bug would trip over (powers of two, all-ones runs, values
+    next to the moduli, non-canonical field inputs), and Invert(0) = 0."""
+    rng = np.random.default_rng(2024)
+    vals = [int.from_bytes(rng.bytes(32), "big") for _ in range(1500)]
+    vals += [2**k for k in range(256)] + [2**k - 1 for k in range(1, 257)]
+    vals += [P - 1 - k for k in range(32)] + [N - 1 - k for k in range(32)] + list(range(32)) + [P + k for k in range(32)]
+    vals += [(2**30) ** k for k in range(9)] + [(2**30) ** k - 1 for k in range(1, 9)]
+    a = rows(vals)
+    inv_p, fer_p = hs.field_op(3, a, a), hs.field_op(7, a, a)
+    inv_n, fer_n = hs.field_op(18, a, a), hs.field_op(19, a, a)
+    for v, ip, fp, i_n, fn in zip(vals, inv_p, fer_p, inv_n, fer_n):
+        assert int.from_bytes(ip.tobytes(), "big") == pow(v % P, P - 2, P), hex(v)
+        assert ip.tobytes() == fp.tobytes(), hex(v)
+        assert int.from_bytes(i_n.tobytes(), "big") == pow(v % N, N - 2, N), hex(v)
+        assert i_n.tobytes() == fn.tobytes(), hex(v)
