@@ -347,34 +347,7 @@ static __device__ __noinline__ fe fe_sqr_call(fe a) {
     fe_sqr_inline(r, a);
     return r;
 }
-#ifdef S256_MUL_SMEM_ARGS
-// Operands travel through a per-thread shared-memory argument buffer (STS.128 in the caller, LDS.128
-// in the callee: the LSU pipe is idle) instead of 16 registers marshalled with IMAD.MOV on the FMA
-// pipe; the product still returns in registers.  [4][S256_ARG_TPB] uint4, conflict-free.
-#ifndef S256_ARG_TPB
-#define S256_ARG_TPB 128
-#endif
-static __shared__ uint4 s256_argbuf[4 * S256_ARG_TPB];
-static __device__ __noinline__ fe fe_mul_call_sm() {
-    fe a, b, r;
-    uint4 q;
-    q = s256_argbuf[threadIdx.x]; a.v[0] = q.x; a.v[1] = q.y; a.v[2] = q.z; a.v[3] = q.w;
-    q = s256_argbuf[S256_ARG_TPB + threadIdx.x]; a.v[4] = q.x; a.v[5] = q.y; a.v[6] = q.z; a.v[7] = q.w;
-    q = s256_argbuf[2 * S256_ARG_TPB + threadIdx.x]; b.v[0] = q.x; b.v[1] = q.y; b.v[2] = q.z; b.v[3] = q.w;
-    q = s256_argbuf[3 * S256_ARG_TPB + threadIdx.x]; b.v[4] = q.x; b.v[5] = q.y; b.v[6] = q.z; b.v[7] = q.w;
-    fe_mul_inline(r, a, b);
-    return r;
-}
-S256_D void fe_mul(fe &r, const fe &a, const fe &b) {
-    s256_argbuf[threadIdx.x] = make_uint4(a.v[0], a.v[1], a.v[2], a.v[3]);
-    s256_argbuf[S256_ARG_TPB + threadIdx.x] = make_uint4(a.v[4], a.v[5], a.v[6], a.v[7]);
-    s256_argbuf[2 * S256_ARG_TPB + threadIdx.x] = make_uint4(b.v[0], b.v[1], b.v[2], b.v[3]);
-    s256_argbuf[3 * S256_ARG_TPB + threadIdx.x] = make_uint4(b.v[4], b.v[5], b.v[6], b.v[7]);
-    r = fe_mul_call_sm();
-}
-#else
 S256_D void fe_mul(fe &r, const fe &a, const fe &b) { r = fe_mul_call(a, b); }
-#endif
 S256_D void fe_sqr(fe &r, const fe &a) { r = fe_sqr_call(a); }
 #else
 S256_D void fe_mul(fe &r, const fe &a, const fe &b) { fe_mul_inline(r, a, b); }
