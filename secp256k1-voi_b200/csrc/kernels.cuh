@@ -312,7 +312,16 @@ S256_HD void item_schnorr_scalars(size_t i, size_t n, const uint8_t *pkx32, cons
     sc s, e, ne;
     uint32_t ok = fe_limbs_are_canonical(r) & (1u - sc_from_be32(s, sg + 32));
     uint8_t eb[32];
-    bip340_challenge(eb, sg, pkx32 + 32 * i, msg + msg_len * i, msg_len);
+    if (msg_len == 32) {  // fixed layout: the tag midstate plus two compressions, all in words
+        uint32_t rw[8], pw[8], mw[8], ew[8];
+        be32_words(rw, sg);
+        be32_words(pw, pkx32 + 32 * i);
+        be32_words(mw, msg + 32 * i);
+        bip340_tagged_96(ew, TAG_CHALLENGE, rw, pw, mw);
+        words_be32(eb, ew);
+    } else {
+        bip340_challenge(eb, sg, pkx32 + 32 * i, msg + msg_len * i, msg_len);
+    }
     sc_from_be32(e, eb);
     sc_neg(ne, e);
     item_store_scalars(s, ne, ok, i, n, u1_out, dig1, dig2, sfl);
@@ -966,18 +975,28 @@ S256_HD uint8_t item_schnorr_nonce(uint8_t kout[32], const uint8_t *priv32, cons
     uint32_t ok = (1u - sc_from_be32(dp, priv32)) & (1u - sc_is_zero(dp));
     sc_neg(nd, dp);
     sc_cmov(d, dp, nd, (uint32_t)(p65[64] & 1u));
-    uint8_t t[32], db[32], rnd[32];
-    sc_to_be32(db, d);
-    sha_stream c;
-    sha_init_tagged(c, TAG_AUX);
-    sha_update(c, aux32, 32);
-    sha_final(c, t);
-    for (int i = 0; i < 32; i++) t[i] ^= db[i];
-    sha_init_tagged(c, TAG_NONCE);
-    sha_update(c, t, 32);
-    sha_update(c, p65 + 1, 32);
-    sha_update(c, msg, msg_len);
-    sha_final(c, rnd);
+    uint8_t rnd[32];
+    uint32_t tw[8], aw[8], pw[8], rw[8];
+    be32_words(aw, aux32);
+    bip340_tagged_32(tw, TAG_AUX, aw);
+#pragma unroll
+    for (int i = 0; i < 8; i++) tw[i] ^= d.v[7 - i];  // t = bytes(d) xor hash_aux(a)
+    be32_words(pw, p65 + 1);
+    if (msg_len == 32) {  // fixed layout: two compressions from the tag midstate
+        uint32_t mw[8];
+        be32_words(mw, msg);
+        bip340_tagged_96(rw, TAG_NONCE, tw, pw, mw);
+        words_be32(rnd, rw);
+    } else {
+        uint8_t t[32];
+        words_be32(t, tw);
+        sha_stream c;
+        sha_init_tagged(c, TAG_NONCE);
+        sha_update(c, t, 32);
+        sha_update(c, p65 + 1, 32);
+        sha_update(c, msg, msg_len);
+        sha_final(c, rnd);
+    }
     sc kp;
     sc_from_be32(kp, rnd);
     ok &= 1u - sc_is_zero(kp);  // errKPrimeIsZero
@@ -997,12 +1016,21 @@ S256_HD void item_schnorr_sign_finish(uint8_t *sig64, uint8_t *status, const uin
     sc_neg(nk, kp);
     sc_cmov(k, kp, nk, (uint32_t)(r65[64] & 1u));
     uint8_t eb[32];
-    sha_stream c;
-    sha_init_tagged(c, TAG_CHALLENGE);
-    sha_update(c, r65 + 1, 32);
-    sha_update(c, p65 + 1, 32);
-    sha_update(c, msg, msg_len);
-    sha_final(c, eb);
+    if (msg_len == 32) {
+        uint32_t rw[8], pw[8], mw[8], ew[8];
+        be32_words(rw, r65 + 1);
+        be32_words(pw, p65 + 1);
+        be32_words(mw, msg);
+        bip340_tagged_96(ew, TAG_CHALLENGE, rw, pw, mw);
+        words_be32(eb, ew);
+    } else {
+        sha_stream c;
+        sha_init_tagged(c, TAG_CHALLENGE);
+        sha_update(c, r65 + 1, 32);
+        sha_update(c, p65 + 1, 32);
+        sha_update(c, msg, msg_len);
+        sha_final(c, eb);
+    }
     sc_from_be32(e, eb);
     sc_mul(sum, e, d);
     sc_add(sum, k, sum);

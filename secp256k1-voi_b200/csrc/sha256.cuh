@@ -294,4 +294,59 @@ S256_HD void sha_init_tagged(sha_stream &c, int tag) {
     c.total = 64;
 }
 
+
+// Word-oriented tagged hashes for the fixed 32-byte layouts of BIP-340 (schnorr.go:309-400): with 32-byte
+// messages -- the common case, and the benchmark's -- the nonce and challenge hashes are the tag midstate
+// plus exactly two compressions, the aux hash one; no byte buffer is involved.
+S256_HD void be32_words(uint32_t w[8], const uint8_t *p) {
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        w[i] = ((uint32_t)p[4 * i] << 24) | ((uint32_t)p[4 * i + 1] << 16) | ((uint32_t)p[4 * i + 2] << 8) | p[4 * i + 3];
+}
+S256_HD void words_be32(uint8_t *p, const uint32_t w[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        p[4 * i] = (uint8_t)(w[i] >> 24);
+        p[4 * i + 1] = (uint8_t)(w[i] >> 16);
+        p[4 * i + 2] = (uint8_t)(w[i] >> 8);
+        p[4 * i + 3] = (uint8_t)w[i];
+    }
+}
+S256_HD void sha_tag_midstate(uint32_t h[8], int tag) {
+    sha_stream c;
+    sha_init_tagged(c, tag);
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = c.h[i];
+}
+// out = tagged_hash(tag, a), |a| = 32
+S256_HD void bip340_tagged_32(uint32_t out[8], int tag, const uint32_t a[8]) {
+    uint32_t w[16];
+    sha_tag_midstate(out, tag);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = a[i];
+    w[8] = 0x80000000u;
+#pragma unroll
+    for (int i = 9; i < 15; i++) w[i] = 0;
+    w[15] = (64 + 32) * 8;
+    sha256_compress(out, w);
+}
+// out = tagged_hash(tag, a || b || m), |a| = |b| = |m| = 32
+S256_HD void bip340_tagged_96(uint32_t out[8], int tag, const uint32_t a[8], const uint32_t b[8], const uint32_t m[8]) {
+    uint32_t w[16];
+    sha_tag_midstate(out, tag);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        w[i] = a[i];
+        w[8 + i] = b[i];
+    }
+    sha256_compress(out, w);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = m[i];
+    w[8] = 0x80000000u;
+#pragma unroll
+    for (int i = 9; i < 15; i++) w[i] = 0;
+    w[15] = (64 + 96) * 8;
+    sha256_compress(out, w);
+}
+
 }  // namespace s256
