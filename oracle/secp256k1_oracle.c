@@ -931,7 +931,7 @@ static int schnorr_sign_one(const u8 priv32[32], const u8 *msg, size_t msg_len, 
 }
 
 /* ------------------------------------------------------------------------- */
-/* Hash to curve (RFC 9380): secec/h2c/*.go, point_h2c.go, internal/swu/swu.go  */
+/* Hash to curve (RFC 9380): secec/h2c/ (all .go files), point_h2c.go, internal/swu/swu.go  */
 /* ------------------------------------------------------------------------- */
 static void hex_to_limbs(u64 l[4], const char *h);
 static fe H_A, H_B, H_Z, H_C2, H_K[4][4];
