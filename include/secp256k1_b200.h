@@ -225,6 +225,10 @@ int s256_microbench_imad(s256_ctx *ctx, int iters, double *mac32_per_s, double *
 /* Other probes of the integer pipes (variant ids in csrc/microbench.cuh): carry-chained
  * IMAD.WIDE.X, 32-bit IMAD, IMAD.HI, IADD3.X chains, mixed issue. */
 int s256_microbench_variant(s256_ctx *ctx, int variant, int iters, double *ops_per_s, double *ms);
+/* Field-multiplication probe: dependent F_p products per second over all SMs.  form 0 = the ladders'
+ * out-of-line 8x32-limb IMAD.WIDE multiplier, 1 = the same inlined, 2 = the 5x52-limb FP64-pipe
+ * experiment (csrc/fe52.cuh; not used by any entry point). */
+int s256_microbench_fe_mul(s256_ctx *ctx, int form, int iters, double *muls_per_s, double *ms);
 /* CUDA-event timing of the dominant kernel (the u1*G + u2*P ladder) on the stream
  * it is launched on: enable, run steps, read the summed device time. */
 int s256_profile_enable(s256_ctx *ctx, int enable);

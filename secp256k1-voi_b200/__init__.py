@@ -41,7 +41,7 @@ EXPORTED_SYMBOLS = [
     "s256_schnorr_verify", "s256_schnorr_verify_dev", "s256_schnorr_sign", "s256_schnorr_sign_dev",
     "s256_msm", "s256_msm_partial", "s256_msm_combine", "s256_hash_to_curve", "s256_expand_message_xmd",
     "s256_debug_gen_table", "s256_debug_field_op", "s256_microbench_imad",
-    "s256_microbench_variant", "s256_profile_enable", "s256_profile_read",
+    "s256_microbench_variant", "s256_microbench_fe_mul", "s256_profile_enable", "s256_profile_read",
     "s256_launch_count", "s256_mac32_per_item", "s256_host_alloc", "s256_host_free",
 ]
 
@@ -601,6 +601,12 @@ class Engine:
         rate, ms = C.c_double(0), C.c_double(0)
         self._check(self._lib.s256_microbench_variant(self._ctx, int(variant), int(iters), C.byref(rate), C.byref(ms)),
                     "microbench_variant")
+        return rate.value, ms.value
+
+    def microbench_fe_mul(self, form, iters=2048):
+        rate, ms = C.c_double(), C.c_double()
+        self._check(self._lib.s256_microbench_fe_mul(self._ctx, int(form), int(iters), C.byref(rate), C.byref(ms)),
+                    "microbench_fe_mul")
         return rate.value, ms.value
 
     def microbench_imad(self, iters=4096):

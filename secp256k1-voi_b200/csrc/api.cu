@@ -6,6 +6,7 @@
 // device every entry point fails with S256_ERR_NO_DEVICE.
 #include "ctx.h"
 #include "microbench.cuh"
+#include "fe52.cuh"
 
 // ---------------------------------------------------------------------------
 // __global__ wrappers
@@ -1009,7 +1010,8 @@ extern "C" int s256_microbench_variant(s256_ctx *ctx, int variant, int iters, do
     if (iters < 1 || variant < 0 || variant >= MB_NVARIANTS) return S256_ERR_ARG;
     typedef void (*fn_t)(int, int, cudaStream_t, unsigned long long *);
     static const fn_t fns[MB_NVARIANTS] = {launch_probe<0>, launch_probe<1>, launch_probe<2>, launch_probe<3>,
-                                           launch_probe<4>, launch_probe<5>, launch_probe<6>};
+                                           launch_probe<4>, launch_probe<5>, launch_probe<6>, launch_probe<7>,
+                                           launch_probe<8>, launch_probe<9>, launch_probe<10>};
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -1032,6 +1034,93 @@ extern "C" int s256_microbench_variant(s256_ctx *ctx, int variant, int iters, do
 extern "C" int s256_microbench_imad(s256_ctx *ctx, int iters, double *mac32_per_s, double *ms) {
     // the carry-chained form is the one the field multiplier issues, and the fastest MAC32 form measured
     return s256_microbench_variant(ctx, MB_MADC_CHAIN, iters, mac32_per_s, ms);
+}
+
+// Field-multiplication probes: dependent products in two interleaved chains, the
+// instruction-level parallelism a point formula offers.  form 0: fe_mul as the ladders call it (8x32 limbs,
+// IMAD.WIDE carry chains, out of line); 1: the same inlined; 2: fe52_mul (5x52 limbs on the FP64 pipe, fe52.cuh).
+template <int FORM>
+__global__ void __launch_bounds__(128, 4) k_femul_probe(uint32_t seed, int iters, unsigned long long *sink) {
+    uint32_t a = seed ^ (threadIdx.x * 2654435761u), b = seed + blockIdx.x * 40503u + 1u;
+    unsigned long long acc = 0;
+    if (FORM == 2) {
+        fe52 x1, y1, x2, y2;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            x1.v[k] = (double)(a + 7u * k);
+            y1.v[k] = (double)(b + 11u * k);
+            x2.v[k] = (double)(a ^ (0x9e3779b9u * (k + 1)));
+            y2.v[k] = (double)(b ^ (0x85ebca6bu * (k + 1)));
+        }
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                fe52_mul(x1, x1, y1);
+                fe52_mul(x2, x2, y2);
+                fe52_mul(y1, y1, x2);
+                fe52_mul(y2, y2, x1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) acc ^= fe52_bits(x1.v[k]) ^ fe52_bits(y1.v[k]) ^ fe52_bits(x2.v[k]) ^ fe52_bits(y2.v[k]);
+    } else {
+        fe x1, y1, x2, y2;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            x1.v[k] = a + 7u * k;
+            y1.v[k] = b + 11u * k;
+            x2.v[k] = a ^ (0x9e3779b9u * (k + 1));
+            y2.v[k] = b ^ (0x85ebca6bu * (k + 1));
+        }
+#pragma unroll 1
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                if (FORM == 0) {
+                    fe_mul(x1, x1, y1);
+                    fe_mul(x2, x2, y2);
+                    fe_mul(y1, y1, x2);
+                    fe_mul(y2, y2, x1);
+                } else {
+                    fe_mul_inline(x1, x1, y1);
+                    fe_mul_inline(x2, x2, y2);
+                    fe_mul_inline(y1, y1, x2);
+                    fe_mul_inline(y2, y2, x1);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc ^= (unsigned long long)(x1.v[k] ^ y1.v[k]) << 32 | (x2.v[k] ^ y2.v[k]);
+    }
+    if (acc == 0x123456789abcdefull) sink[0] = acc;
+}
+template <int FORM>
+static void launch_femul_probe(int blocks, int iters, cudaStream_t s, unsigned long long *sink) {
+    k_femul_probe<FORM><<<blocks, 128, 0, s>>>(12345u, iters, sink);
+}
+extern "C" int s256_microbench_fe_mul(s256_ctx *ctx, int form, int iters, double *muls_per_s, double *ms_out) {
+    ENTER(ctx);
+    if (iters < 1 || form < 0 || form > 2) return S256_ERR_ARG;
+    typedef void (*fn_t)(int, int, cudaStream_t, unsigned long long *);
+    static const fn_t fns[3] = {launch_femul_probe<0>, launch_femul_probe<1>, launch_femul_probe<2>};
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int blocks = 148 * 16;
+    fns[form](blocks, 4, ctx->stream, ctx->sink);
+    CK(cudaEventRecord(e0, ctx->stream));
+    fns[form](blocks, iters, ctx->stream, ctx->sink);
+    CK(cudaEventRecord(e1, ctx->stream));
+    ctx->launches.fetch_add(2);
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (muls_per_s) *muls_per_s = (double)blocks * 128 * (double)iters * 8.0 / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return check_launch(ctx);
 }
 
 // MAC32 per item actually executed (DESIGN.md "work per item"): F_p mul = 73 (64 + 9),

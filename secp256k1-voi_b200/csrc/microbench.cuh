@@ -16,7 +16,11 @@ enum {
     MB_ADDC_CHAIN = 4,  // add.cc/addc.cc chains of 8                      -> IADD3 / IADD3.X
     MB_MADC_PAIR = 5,   // mad.lo.cc + madc.hi.cc + addc (carry OUT only)
     MB_MIX = 6,         // mad.wide interleaved with add.cc chains (dual-pipe issue)
-    MB_NVARIANTS = 7
+    MB_DFMA = 7,        // fma.rz.f64, eight independent chains                           -> DFMA (FP64 pipe)
+    MB_DFMA_IMAD = 8,   // 8 DFMA + 4 carry-chained wide MADs per repeat (2 : 1, the ratio of the pipe rates): do the two pipes overlap?
+    MB_DFMA_PROD = 9,   // one 52x52-bit product the FP64 way: 2 DFMA + 1 DADD + two 64-bit integer adds
+    MB_DFMA_PROD_IMAD = 10,  // MB_DFMA_PROD and a carry-chained wide MAD side by side (1 : 1)
+    MB_NVARIANTS = 11
 };
 
 template <int V>
@@ -25,6 +29,13 @@ __global__ void __launch_bounds__(256) k_int_probe(uint32_t seed, int iters, uns
     uint32_t r0 = a, r1 = b, r2 = a + 1, r3 = b + 2, r4 = a + 3, r5 = b + 4, r6 = a + 5, r7 = b + 6;
     uint32_t s0 = b, s1 = a, s2 = b + 1, s3 = a + 2, s4 = b + 3, s5 = a + 4, s6 = b + 5, s7 = a + 6, t = 0, u = 0;
     unsigned long long c0 = a, c1 = b, c2 = a + 1, c3 = b + 2, c4 = a + 3, c5 = b + 4, c6 = a + 5, c7 = b + 6;
+    // FP64 probes: operands below 2^52 held as doubles, the splitting constants of the
+    // 52-bit-limb product (hi = fma_rz(a, b, 2^104) - 2^104, lo = fma_rz(a, b, 2^104 + 2^52 - hi') - 2^52)
+    double d0 = (double)(a & 0xfffff) + 1.0, d1 = d0 + 3.0, d2 = d0 + 5.0, d3 = d0 + 7.0, d4 = d0 + 11.0, d5 = d0 + 13.0, d6 = d0 + 17.0,
+           d7 = d0 + 19.0;
+    const double dm = 0.99999904632568359375 + (double)(b & 7) * 1.1102230246251565e-16, dy = 1.0 + (double)(a & 3);
+    const double C1 = 20282409603651670423947251286016.0 /* 2^104 */, C2 = C1 + 4503599627370496.0 /* + 2^52 */;
+    const double db = 4503599627370495.0 - (double)(b & 0xffff);
 #pragma unroll 1
     for (int it = 0; it < iters; it++) {
 #pragma unroll
@@ -90,9 +101,40 @@ __global__ void __launch_bounds__(256) k_int_probe(uint32_t seed, int iters, uns
                     : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(s0), "+r"(s1),
                       "+r"(s2), "+r"(s3), "+r"(s4), "+r"(s5), "+r"(s6), "+r"(s7)
                     : "r"(b));
+            } else if (V == MB_DFMA || V == MB_DFMA_IMAD) {
+                asm volatile(
+                    "fma.rz.f64 %0,%0,%8,%9; fma.rz.f64 %1,%1,%8,%9; fma.rz.f64 %2,%2,%8,%9; fma.rz.f64 %3,%3,%8,%9;"
+                    "fma.rz.f64 %4,%4,%8,%9; fma.rz.f64 %5,%5,%8,%9; fma.rz.f64 %6,%6,%8,%9; fma.rz.f64 %7,%7,%8,%9;"
+                    : "+d"(d0), "+d"(d1), "+d"(d2), "+d"(d3), "+d"(d4), "+d"(d5), "+d"(d6), "+d"(d7) : "d"(dm), "d"(dy));
+                if (V == MB_DFMA_IMAD) {
+                    asm volatile(
+                        "mad.lo.cc.u32 %0,%9,%13,%0; madc.hi.cc.u32 %1,%9,%13,%1; madc.lo.cc.u32 %2,%10,%13,%2; madc.hi.cc.u32 %3,%10,%13,%3;"
+                        "madc.lo.cc.u32 %4,%11,%13,%4; madc.hi.cc.u32 %5,%11,%13,%5; madc.lo.cc.u32 %6,%12,%13,%6; madc.hi.cc.u32 %7,%12,%13,%7;"
+                        "addc.u32 %8,%8,0;"
+                        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(t)
+                        : "r"(s0), "r"(s2), "r"(s4), "r"(s6), "r"(s1));
+                    s0 += r1; s2 += r3; s4 += r5; s6 += r7; s1 ^= r0;
+                }
+            } else if (V == MB_DFMA_PROD || V == MB_DFMA_PROD_IMAD) {
+                // four products per repeat; the next multiplicand is the low half just computed
+#define S256_MB_PROD(D, ACC_HI, ACC_LO)                                                                              \
+    asm volatile("{ .reg .f64 h, l, sb; .reg .u64 x;\n"                                                              \
+                 "fma.rz.f64 h,%0,%3,%4; sub.rz.f64 sb,%5,h; fma.rz.f64 l,%0,%3,sb;\n"                                \
+                 "mov.b64 x,h; add.u64 %1,%1,x; mov.b64 x,l; add.u64 %2,%2,x; sub.rz.f64 %0,l,%6; }\n"                \
+                 : "+d"(D), "+l"(ACC_HI), "+l"(ACC_LO) : "d"(db), "d"(C1), "d"(C2), "d"(4503599627370496.0));
+                S256_MB_PROD(d0, c0, c1) S256_MB_PROD(d1, c2, c3) S256_MB_PROD(d2, c4, c5) S256_MB_PROD(d3, c6, c7)
+                if (V == MB_DFMA_PROD_IMAD) {
+                    asm volatile(
+                        "mad.lo.cc.u32 %0,%5,%7,%0; madc.hi.cc.u32 %1,%5,%7,%1; madc.lo.cc.u32 %2,%6,%7,%2; madc.hi.cc.u32 %3,%6,%7,%3;"
+                        "addc.u32 %4,%4,0;"
+                        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(t) : "r"(s0), "r"(s2), "r"(s1));
+                    s0 += r1; s2 += r3; s1 ^= r0;
+                }
             }
         }
     }
+    c0 ^= (unsigned long long)__double_as_longlong(d0) ^ __double_as_longlong(d1) ^ __double_as_longlong(d2) ^ __double_as_longlong(d3);
+    c1 ^= (unsigned long long)__double_as_longlong(d4) ^ __double_as_longlong(d5) ^ __double_as_longlong(d6) ^ __double_as_longlong(d7);
     unsigned long long cc = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
     uint32_t s = (uint32_t)cc ^ (uint32_t)(cc >> 32) ^ r0 ^ r1 ^ r2 ^ r3 ^ r4 ^ r5 ^ r6 ^ r7 ^ s0 ^ s1 ^ s2 ^ s3 ^ s4 ^ s5 ^ s6 ^ s7 ^ t ^ u;
     if (s == 0x12345678u) sink[0] = s;
@@ -108,6 +150,10 @@ static inline double mb_ops_per_trip(int v) {
         case MB_ADDC_CHAIN: return 16 * 8;
         case MB_MADC_PAIR: return 4 * 8;
         case MB_MIX: return 4 * 8;
+        case MB_DFMA: return 8 * 8;           // DFMAs
+        case MB_DFMA_IMAD: return 12 * 8;     // 8 DFMAs + 4 wide MADs
+        case MB_DFMA_PROD: return 4 * 8;      // 52x52-bit products
+        case MB_DFMA_PROD_IMAD: return 6 * 8; // 4 FP64 products + 2 wide MADs
         default: return 0;
     }
 }
