@@ -60,6 +60,8 @@ class Engine {
 namespace detail {
 static const uint8_t N_BE[32] = {0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFE,
                                  0xBA, 0xAE, 0xDC, 0xE6, 0xAF, 0x48, 0xA0, 0x3B, 0xBF, 0xD2, 0x5E, 0x8C, 0xD0, 0x36, 0x41, 0x41};
+static const uint8_t P_BE[32] = {0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF,
+                                 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFF, 0xFE, 0xFF, 0xFF, 0xFC, 0x2F};
 inline int cmp_be(const uint8_t *a, const uint8_t *b) { return std::memcmp(a, b, 32); }
 inline void sub_be(uint8_t *r, const uint8_t *a, const uint8_t *b) {
     int borrow = 0;
@@ -71,8 +73,8 @@ inline void sub_be(uint8_t *r, const uint8_t *a, const uint8_t *b) {
 }
 }  // namespace detail
 
-// scalar.go: an integer mod n.  Only what the batch path needs lives on the host
-// (decode / encode / range predicates); arithmetic on scalars happens on the GPU.
+// scalar.go: an integer mod n.  Decode / encode / range predicates / negation / selection are byte
+// operations on the host; products, sums and inverses mod n happen on the GPU.
 class Scalar {
   public:
     Scalar() { b_.fill(0); }  // NewScalar(): zero
@@ -106,6 +108,51 @@ class Scalar {
         return s;
     }
     const std::array<uint8_t, 32> &Bytes() const { return b_; }  // scalar.go:148, canonical big-endian
+    // scalar.go:52-121 and scalar_invert.go:11 -- receiver = result, arguments may alias the receiver.
+    // The mod-n products, sums and inverses run on the device (the Z_n kernels of the verification path,
+    // through s256_debug_field_op); negation and selection are byte operations on canonical values.
+    Scalar &Zero() { b_.fill(0); return *this; }
+    Scalar &One() { b_.fill(0); b_[31] = 1; return *this; }
+    Scalar &Set(const Scalar &a) { b_ = a.b_; return *this; }
+    Scalar &Add(const Scalar &a, const Scalar &b, Engine &e = Engine::Default()) { return devOp(17, a, b, e); }
+    Scalar &Multiply(const Scalar &a, const Scalar &b, Engine &e = Engine::Default()) { return devOp(16, a, b, e); }
+    Scalar &Square(const Scalar &a, Engine &e = Engine::Default()) { return devOp(16, a, a, e); }
+    Scalar &Invert(const Scalar &a, Engine &e = Engine::Default()) { return devOp(18, a, a, e); }  // Invert(0) = 0
+    Scalar &Negate(const Scalar &a) {
+        if (a.IsZero()) return Zero();
+        std::array<uint8_t, 32> t;
+        detail::sub_be(t.data(), detail::N_BE, a.b_.data());
+        b_ = t;
+        return *this;
+    }
+    Scalar &Subtract(const Scalar &a, const Scalar &b, Engine &e = Engine::Default()) {
+        Scalar nb;
+        nb.Negate(b);
+        return Add(a, nb, e);
+    }
+    template <class It>
+    Scalar &Sum(It first, It last, Engine &e = Engine::Default()) {  // scalar.go:96
+        Scalar acc;
+        for (; first != last; ++first) acc.Add(acc, *first, e);
+        return Set(acc);
+    }
+    template <class It>
+    Scalar &Product(It first, It last, Engine &e = Engine::Default()) {  // scalar.go:106
+        Scalar acc;
+        acc.One();
+        for (; first != last; ++first) acc.Multiply(acc, *first, e);
+        return Set(acc);
+    }
+    Scalar &ConditionalNegate(const Scalar &a, uint64_t ctrl) {  // scalar.go:162
+        Scalar n;
+        n.Negate(a);
+        return ConditionalSelect(a, n, ctrl);
+    }
+    Scalar &ConditionalSelect(const Scalar &a, const Scalar &b, uint64_t ctrl) {  // scalar.go:170: a iff ctrl == 0
+        const uint8_t m = (uint8_t)(0 - (uint8_t)(ctrl != 0));
+        for (int i = 0; i < 32; i++) b_[i] = (uint8_t)((a.b_[i] & ~m) | (b.b_[i] & m));
+        return *this;
+    }
     uint64_t IsZero() const {
         uint8_t acc = 0;
         for (uint8_t x : b_) acc |= x;
@@ -120,6 +167,12 @@ class Scalar {
     }
 
   private:
+    Scalar &devOp(int op, const Scalar &a, const Scalar &b, Engine &e) {
+        std::array<uint8_t, 32> out;
+        e.check(s256_debug_field_op(e.ctx(), op, a.b_.data(), b.b_.data(), 1, out.data()), "Scalar arithmetic");
+        b_ = out;
+        return *this;
+    }
     std::array<uint8_t, 32> b_;
 };
 
@@ -255,6 +308,50 @@ class Point {
         q.toPartial(parts + 96);
         e.check(s256_msm_combine(e.ctx(), parts, 2, enc_.data(), &st), "Add");
         return set(st);
+    }
+    // point.go:42-59,73-131,164-224
+    Point &Identity() { return Set(NewIdentityPoint()); }
+    Point &Generator() { return Set(NewGeneratorPoint()); }
+    Point &Set(const Point &p) {
+        p.assertValid();
+        enc_ = p.enc_;
+        valid_ = true;
+        identity_ = p.identity_;
+        return *this;
+    }
+    static Point NewPointFrom(const Point &p) {
+        Point r;
+        r.Set(p);
+        return r;
+    }
+    // point.go:203 -- (x, y) big-endian; rejects non-canonical coordinates and points off the curve
+    static Point NewPointFromCoords(const uint8_t x[32], const uint8_t y[32], Engine &e = Engine::Default()) {
+        uint8_t buf[65];
+        buf[0] = 0x04;
+        std::memcpy(buf + 1, x, 32);
+        std::memcpy(buf + 33, y, 32);
+        return NewPointFromBytes(buf, 65, e);
+    }
+    Point &Double(const Point &p, Engine &e = Engine::Default()) { return Add(p, p, e); }  // the combine's addition is complete
+    Point &Negate(const Point &p) {  // (x, y) -> (x, p - y); y is never 0 on this curve (no points of order 2)
+        Set(p);
+        if (!identity_) detail::sub_be(enc_.data() + 33, detail::P_BE, enc_.data() + 33);
+        return *this;
+    }
+    Point &Subtract(const Point &p, const Point &q, Engine &e = Engine::Default()) {
+        Point nq;
+        nq.Negate(q);
+        return Add(p, nq, e);
+    }
+    Point &ConditionalNegate(const Point &p, uint64_t ctrl) {
+        Point n;
+        n.Negate(p);
+        return ConditionalSelect(p, n, ctrl);
+    }
+    Point &ConditionalSelect(const Point &a, const Point &b, uint64_t ctrl) {  // point.go:116: a iff ctrl == 0
+        a.assertValid();
+        b.assertValid();
+        return Set(ctrl != 0 ? b : a);
     }
     const std::array<uint8_t, 65> &raw() const { return enc_; }
 

@@ -61,6 +61,52 @@ int main(int argc, char **argv) {
     threw = false;
     try { Scalar::NewScalarFromCanonicalBytes(nb); } catch (const Error &) { threw = true; }
     REQUIRE(threw);
+    // the rest of the Point / Scalar surface (point.go:62-131, scalar.go:52-121, scalar_invert.go:11)
+    {
+        Point t, u, n;
+        REQUIRE(t.Double(g).Equal(two));
+        REQUIRE(u.Subtract(two, g).Equal(g));
+        REQUIRE(u.Subtract(g, g).IsIdentity() == 1);
+        n.Negate(g);
+        REQUIRE(n.IsYOdd() != g.IsYOdd() && n.XBytes() == g.XBytes());
+        REQUIRE(u.Add(g, n).IsIdentity() == 1);
+        REQUIRE(u.Negate(Point::NewIdentityPoint()).IsIdentity() == 1);
+        REQUIRE(u.ConditionalNegate(g, 1).Equal(n) && u.ConditionalNegate(g, 0).Equal(g));
+        REQUIRE(u.ConditionalSelect(g, two, 0).Equal(g) && u.ConditionalSelect(g, two, 1).Equal(two));
+        REQUIRE(u.Identity().IsIdentity() == 1 && u.Generator().Equal(g));
+        REQUIRE(Point::NewPointFrom(two).Equal(two));
+        REQUIRE(Point::NewPointFromCoords(gU.data() + 1, gU.data() + 33).Equal(g));
+        bool bad = false;
+        try { Point::NewPointFromCoords(gU.data() + 1, gU.data() + 1); } catch (const Error &) { bad = true; }
+        REQUIRE(bad);  // (Gx, Gx) is not on the curve
+        // (n - 1) * G = -G, and k * G + (n - k) * G = identity
+        Scalar one, m1, k = sxn, nk, sum, prod, inv, sq;
+        one.One();
+        m1.Negate(one);
+        REQUIRE(t.ScalarBaseMult(m1).Equal(n));
+        nk.Negate(k);
+        REQUIRE(sum.Add(k, nk).IsZero() == 1);
+        REQUIRE(sum.Subtract(k, k).IsZero() == 1);
+        REQUIRE(sum.Subtract(Scalar(), one).Equal(m1));
+        REQUIRE(prod.Multiply(m1, m1).Equal(one));          // (-1)^2 = 1
+        REQUIRE(sq.Square(k).Equal(prod.Multiply(k, k)));
+        REQUIRE(prod.Multiply(k, inv.Invert(k)).Equal(one));
+        REQUIRE(inv.Invert(Scalar()).IsZero() == 1);         // scalar_invert.go:9-10
+        std::vector<Scalar> v = {k, one, m1, k};
+        Scalar two_k;
+        two_k.Add(k, k);
+        REQUIRE(sum.Sum(v.begin(), v.end()).Equal(two_k));
+        REQUIRE(prod.Product(v.begin(), v.end()).Equal(Scalar().Negate(sq)));
+        REQUIRE(sum.ConditionalNegate(k, 1).Equal(nk) && sum.ConditionalNegate(k, 0).Equal(k));
+        REQUIRE(sum.ConditionalSelect(k, one, 0).Equal(k) && sum.ConditionalSelect(k, one, 1).Equal(one));
+        // (a * b) * G == a * (b * G)
+        Scalar ab;
+        ab.Multiply(k, m1);
+        Point bg, abg, abg2;
+        bg.ScalarBaseMult(m1);
+        abg.ScalarMult(k, bg);
+        REQUIRE(abg2.ScalarBaseMult(ab).Equal(abg));
+    }
     // ECDSA: sign-free check -- recover then verify must agree (secec/wycheproof_test.go:421-438 shape)
     // BIP-340 row 0 (schnorr_test.go:149-246)
     auto spk = secec::bitcoin::SchnorrPublicKey::NewSchnorrPublicKey(bipPk.data(), bipPk.size());
