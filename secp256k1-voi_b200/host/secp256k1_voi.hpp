@@ -421,6 +421,40 @@ inline std::vector<uint8_t> BuildASN1Signature(const uint8_t sig64[64]) {
     return std::vector<uint8_t>(out, out + n);
 }
 
+// secec/s11n.go:129-176 -- compact [R | S] and recoverable [R | S | V] signatures: r, s in [1, n)
+struct RawSignature {
+    Scalar r, s;
+    uint8_t v = 0;
+};
+inline RawSignature ParseCompactSignature(const uint8_t *data, size_t len) {
+    if (len != CompactSignatureSize) throw Error("secp256k1/secec: invalid compact signature");
+    RawSignature sig;
+    try {
+        sig.r.SetCanonicalBytes(data);
+        sig.s.SetCanonicalBytes(data + 32);
+    } catch (const Error &) {
+        throw Error("secp256k1/secec: invalid scalar");
+    }
+    if (sig.r.IsZero() || sig.s.IsZero()) throw Error("secp256k1/secec: invalid scalar");
+    return sig;
+}
+inline std::vector<uint8_t> BuildCompactSignature(const Scalar &r, const Scalar &s) {
+    std::vector<uint8_t> out(r.Bytes().begin(), r.Bytes().end());
+    out.insert(out.end(), s.Bytes().begin(), s.Bytes().end());
+    return out;
+}
+inline RawSignature ParseCompactRecoverableSignature(const uint8_t *data, size_t len) {
+    if (len != CompactRecoverableSignatureSize) throw Error("secp256k1/secec: invalid compact signature");
+    RawSignature sig = ParseCompactSignature(data, CompactSignatureSize);
+    sig.v = data[64];  // not range-checked here, as in the reference: RecoverPublicKey refuses v > 3
+    return sig;
+}
+inline std::vector<uint8_t> BuildCompactRecoverableSignature(const Scalar &r, const Scalar &s, uint8_t v) {
+    std::vector<uint8_t> out = BuildCompactSignature(r, s);
+    out.push_back(v);
+    return out;
+}
+
 class PublicKey {
   public:
     // secec/secec.go:188 NewPublicKey: any SEC 1 encoding, identity rejected
@@ -486,6 +520,25 @@ class PublicKey {
         return false;  // errInvalidEncoding
     }
     bool Equal(const PublicKey &o) const { return point_.Equal(o.point_); }
+    // secec/secec.go:98,114,202
+    std::vector<uint8_t> CompressedBytes() const { return point_.CompressedBytes(); }
+    Point PointCopy() const { return Point::NewPointFrom(point_); }  // Go: Point() returns a copy
+    uint64_t IsYOdd() const { return point_.IsYOdd(); }
+    static PublicKey NewPublicKeyFromPoint(const Point &p) {
+        if (p.IsIdentity()) throw Error("secp256k1/secec: public key is the point at infinity");
+        PublicKey k;
+        k.point_ = Point::NewPointFrom(p);
+        return k;
+    }
+    // secec/ecdsa.go:234 VerifyRaw: (r, s) as scalars; zero r or s fails inside the kernel as in verify()
+    bool VerifyRaw(const uint8_t *digest, size_t digest_len, const Scalar &r, const Scalar &s, Engine &e = Engine::Default()) const {
+        if (digest_len < 32) return false;
+        uint8_t sig[64], ok = 0;
+        std::memcpy(sig, r.Bytes().data(), 32);
+        std::memcpy(sig + 32, s.Bytes().data(), 32);
+        e.check(s256_ecdsa_verify(e.ctx(), point_.raw().data(), digest, sig, 0, 1, &ok), "VerifyRaw");
+        return ok == 1;
+    }
 
   private:
     Point point_;
@@ -511,6 +564,32 @@ class PrivateKey {
     }
     const std::array<uint8_t, 32> &Bytes() const { return d_; }
     const PublicKey &PublicKeyRef() const { return pub_; }
+    // secec/secec.go:45,53,61,75,164
+    // (Go: Scalar() and PublicKey(); a C++ member cannot share its name with the type it returns)
+    secp256k1::Scalar ScalarCopy() const { return secp256k1::Scalar::NewScalarFromCanonicalBytes(d_.data()); }
+    bool Equal(const PrivateKey &o) const {
+        uint8_t acc = 0;
+        for (size_t i = 0; i < 32; i++) acc |= (uint8_t)(d_[i] ^ o.d_[i]);
+        return acc == 0;
+    }
+    static PrivateKey NewPrivateKeyFromScalar(const secp256k1::Scalar &s, Engine &e = Engine::Default()) {
+        return NewPrivateKey(s.Bytes().data(), ScalarSize, e);  // zero is refused there
+    }
+    std::array<uint8_t, 32> ECDH(const PublicKey &remote, Engine &e = Engine::Default()) const {
+        std::array<uint8_t, 32> x;
+        uint8_t st = 0;
+        e.check(s256_ecdh(e.ctx(), d_.data(), remote.point().raw().data(), 1, x.data(), &st), "ECDH");
+        if (st != S256_ST_OK) throw Error("secp256k1/secec: ECDH failed");
+        return x;
+    }
+    // secec/ecdsa.go:161 SignRaw with RFC6979SHA256(): (r, s, recovery id)
+    RawSignature SignRaw(const uint8_t *digest, size_t digest_len, Engine &e = Engine::Default()) const {
+        ECDSAOptions o;
+        o.Encoding = EncodingCompactRecoverable;
+        o.HashSize = digest_len;
+        std::vector<uint8_t> sig = Sign(digest, digest_len, &o, e);
+        return ParseCompactRecoverableSignature(sig.data(), sig.size());
+    }
     // Sign(RFC6979SHA256(), digest, opts): opts == nullptr -> EncodingASN1, digest of any length >= 32
     std::vector<uint8_t> Sign(const uint8_t *digest, size_t digest_len, const ECDSAOptions *opts = nullptr,
                               Engine &e = Engine::Default()) const {
@@ -555,6 +634,13 @@ inline void ParseASN1PublicKeyBatch(const uint8_t *der, const size_t *offsets, s
 }
 
 // secec/ecdsa.go:244 RecoverPublicKey on r || s || v
+inline PublicKey RecoverPublicKey(const uint8_t digest32[32], const uint8_t sig65[65], Engine &e);
+// secec/ecdsa.go:244 RecoverPublicKey(digest, r, s, recoveryID)
+inline PublicKey RecoverPublicKey(const uint8_t digest32[32], const Scalar &r, const Scalar &s, uint8_t recoveryID,
+                                  Engine &e = Engine::Default()) {
+    std::vector<uint8_t> sig = BuildCompactRecoverableSignature(r, s, recoveryID);
+    return RecoverPublicKey(digest32, sig.data(), e);
+}
 inline PublicKey RecoverPublicKey(const uint8_t digest32[32], const uint8_t sig65[65], Engine &e = Engine::Default()) {
     uint8_t pk[65], st = 0;
     e.check(s256_ecdsa_recover(e.ctx(), digest32, sig65, 1, pk, &st), "RecoverPublicKey");

@@ -138,6 +138,46 @@ int main(int argc, char **argv) {
     REQUIRE(std::vector<uint8_t>(back.begin(), back.end()) == sRS);
     auto sigR = sk.Sign(sDigest.data(), sDigest.size(), &recoverable);
     REQUIRE(sigR.size() == 65 && sigR[64] < 4);
+    {   // the raw forms (secec/ecdsa.go:161,234,244; secec/s11n.go:129-176; secec/secec.go:45-121,164,202)
+        auto raw = sk.SignRaw(sDigest.data(), sDigest.size());
+        REQUIRE(secec::BuildCompactSignature(raw.r, raw.s) == sRS && raw.v == sigR[64]);
+        REQUIRE(secec::BuildCompactRecoverableSignature(raw.r, raw.s, raw.v) == sigR);
+        REQUIRE(sk.PublicKeyRef().VerifyRaw(sDigest.data(), sDigest.size(), raw.r, raw.s));
+        REQUIRE(!sk.PublicKeyRef().VerifyRaw(sDigest.data(), sDigest.size(), raw.s, raw.r));
+        REQUIRE(!sk.PublicKeyRef().VerifyRaw(sDigest.data(), sDigest.size(), Scalar(), raw.s));
+        REQUIRE(secec::RecoverPublicKey(sDigest.data(), raw.r, raw.s, raw.v).Equal(sk.PublicKeyRef()));
+        auto parsed = secec::ParseCompactRecoverableSignature(sigR.data(), sigR.size());
+        REQUIRE(parsed.r.Equal(raw.r) && parsed.s.Equal(raw.s) && parsed.v == raw.v);
+        bool bad = false;
+        std::vector<uint8_t> zeroR(64, 0);
+        std::memcpy(zeroR.data() + 32, sRS.data() + 32, 32);
+        try { secec::ParseCompactSignature(zeroR.data(), 64); } catch (const Error &) { bad = true; }
+        REQUIRE(bad);  // r = 0
+        bad = false;
+        std::vector<uint8_t> bigS(sRS);
+        std::memcpy(bigS.data() + 32, detail::N_BE, 32);
+        try { secec::ParseCompactSignature(bigS.data(), 64); } catch (const Error &) { bad = true; }
+        REQUIRE(bad);  // s = n
+        bad = false;
+        sigR[64] = 4;
+        REQUIRE(secec::ParseCompactRecoverableSignature(sigR.data(), 65).v == 4);  // parsed as is (secec/s11n.go:156-170) ...
+        try { secec::RecoverPublicKey(sDigest.data(), raw.r, raw.s, 4); } catch (const Error &) { bad = true; }
+        REQUIRE(bad);  // ... and refused by the recovery (secec/ecdsa.go:245-247)
+        sigR[64] = raw.v;
+        auto sk2 = secec::PrivateKey::NewPrivateKeyFromScalar(sk.ScalarCopy());
+        REQUIRE(sk2.Equal(sk) && sk2.PublicKeyRef().Equal(sk.PublicKeyRef()));
+        bad = false;
+        try { secec::PrivateKey::NewPrivateKeyFromScalar(Scalar()); } catch (const Error &) { bad = true; }
+        REQUIRE(bad);
+        auto pub2 = secec::PublicKey::NewPublicKeyFromPoint(sk.PublicKeyRef().PointCopy());
+        REQUIRE(pub2.Equal(sk.PublicKeyRef()) && pub2.CompressedBytes().size() == 33);
+        REQUIRE(secec::PublicKey::NewPublicKey(pub2.CompressedBytes().data(), 33).Equal(pub2));
+        bad = false;
+        try { secec::PublicKey::NewPublicKeyFromPoint(Point::NewIdentityPoint()); } catch (const Error &) { bad = true; }
+        REQUIRE(bad);
+        auto skA = secec::PrivateKey::NewPrivateKeyFromScalar(ka), skB = secec::PrivateKey::NewPrivateKeyFromScalar(kb);
+        REQUIRE(skA.ECDH(skB.PublicKeyRef()) == skB.ECDH(skA.PublicKeyRef()) && skA.ECDH(pkB) == secec::ECDH(ka, pkB));
+    }
     const auto &vk = sk.PublicKeyRef();
     REQUIRE(vk.Verify(sDigest.data(), sDigest.size(), sigA.data(), sigA.size()));
     REQUIRE(vk.Verify(sDigest.data(), sDigest.size(), sigC.data(), sigC.size(), &compact));
