@@ -675,15 +675,31 @@ class SchnorrPublicKey {
     // secec/bitcoin/schnorr.go:257 NewSchnorrPublicKey (lift_x is validated here, as in Go)
     static SchnorrPublicKey NewSchnorrPublicKey(const uint8_t *key, size_t len, Engine &e = Engine::Default()) {
         if (len != SchnorrPublicKeySize) throw Error("secp256k1/secec/bitcoin: invalid public key");
-        uint8_t cp[33], out[65], st = 0;
-        cp[0] = 0x02;
+        uint8_t cp[33];
+        cp[0] = 0x02;  // lift_x: the point with even y
         std::memcpy(cp + 1, key, 32);
-        e.check(s256_point_decompress(e.ctx(), cp, 1, out, &st), "lift_x");
-        if (st != S256_ST_OK) throw Error("secp256k1/secec/bitcoin: failed to decompress public key");
         SchnorrPublicKey k;
+        try {
+            k.point_ = Point::NewPointFromBytes(cp, 33, e);
+        } catch (const Error &) {
+            throw Error("secp256k1/secec/bitcoin: failed to decompress public key");
+        }
         std::memcpy(k.x_.data(), key, 32);
         return k;
     }
+    // secec/bitcoin/schnorr.go:282 -- any point but the identity; the y coordinate is made even
+    static SchnorrPublicKey NewSchnorrPublicKeyFromPoint(const Point &point) {
+        if (point.IsIdentity()) throw Error("secp256k1/secec/bitcoin: public key is the point at infinity");
+        SchnorrPublicKey k;
+        k.point_.ConditionalNegate(point, point.IsYOdd());
+        std::vector<uint8_t> x = k.point_.XBytes();
+        std::memcpy(k.x_.data(), x.data(), 32);
+        return k;
+    }
+    // secec/bitcoin/schnorr.go:303
+    static SchnorrPublicKey NewSchnorrPublicKeyFromECDSA(const PublicKey &pk) { return NewSchnorrPublicKeyFromPoint(pk.point()); }
+    Point PointCopy() const { return Point::NewPointFrom(point_); }  // Go: Point() returns a copy
+    bool Equal(const SchnorrPublicKey &o) const { return x_ == o.x_; }
     // secec/bitcoin/schnorr.go:221 Verify
     bool Verify(const uint8_t *msg, size_t msg_len, const uint8_t *sig, size_t sig_len, Engine &e = Engine::Default()) const {
         if (sig_len != SchnorrSignatureSize) return false;
@@ -694,6 +710,7 @@ class SchnorrPublicKey {
     const std::array<uint8_t, 32> &Bytes() const { return x_; }
 
   private:
+    Point point_;  // never the identity, y even
     std::array<uint8_t, 32> x_{};
 };
 // secec/bitcoin/ecdsa_shitcoin.go:29 VerifyASN1: BIP-66 syntax, trailing sighash byte, s <= n/2
@@ -714,14 +731,27 @@ inline bool IsValidSignatureEncodingBIP0066(const uint8_t *data, size_t len) {
 // secec/bitcoin/schnorr.go:140 NewSchnorrPrivateKey + :111 Sign with caller-supplied auxiliary randomness
 class SchnorrPrivateKey {
   public:
-    static SchnorrPrivateKey NewSchnorrPrivateKey(const uint8_t *key, size_t len) {
-        if (len != ScalarSize || std::memcmp(key, detail::N_BE, 32) >= 0) throw Error("secp256k1/secec/bitcoin: invalid private key");
-        uint8_t acc = 0;
-        for (size_t i = 0; i < 32; i++) acc |= key[i];
-        if (!acc) throw Error("secp256k1/secec/bitcoin: invalid private key");
+    static SchnorrPrivateKey NewSchnorrPrivateKey(const uint8_t *key, size_t len, Engine &e = Engine::Default()) {
+        try {
+            return NewSchnorrPrivateKeyFromECDSA(PrivateKey::NewPrivateKey(key, len, e));
+        } catch (const Error &) {
+            throw Error("secp256k1/secec/bitcoin: invalid private key");
+        }
+    }
+    // secec/bitcoin/schnorr.go:162
+    static SchnorrPrivateKey NewSchnorrPrivateKeyFromECDSA(const PrivateKey &sk) {
         SchnorrPrivateKey k;
-        std::memcpy(k.d_.data(), key, 32);
+        k.d_ = sk.Bytes();
+        k.pub_ = SchnorrPublicKey::NewSchnorrPublicKeyFromECDSA(sk.PublicKeyRef());
         return k;
+    }
+    const std::array<uint8_t, 32> &Bytes() const { return d_; }  // d', the scalar as given (schnorr.go:76)
+    secp256k1::Scalar ScalarCopy() const { return secp256k1::Scalar::NewScalarFromCanonicalBytes(d_.data()); }
+    const SchnorrPublicKey &PublicKeyRef() const { return pub_; }
+    bool Equal(const SchnorrPrivateKey &o) const {
+        uint8_t acc = 0;
+        for (size_t i = 0; i < 32; i++) acc |= (uint8_t)(d_[i] ^ o.d_[i]);
+        return acc == 0;
     }
     std::array<uint8_t, 64> Sign(const uint8_t aux32[32], const uint8_t *msg, size_t msg_len, Engine &e = Engine::Default()) const {
         std::array<uint8_t, 64> sig{};
@@ -733,6 +763,7 @@ class SchnorrPrivateKey {
 
   private:
     std::array<uint8_t, 32> d_{};
+    SchnorrPublicKey pub_;
 };
 inline void SchnorrVerifyBatch(const uint8_t *pkx32, const uint8_t *msg, size_t msg_len, const uint8_t *sig64, size_t n,
                                uint8_t *ok, Engine &e = Engine::Default()) {

@@ -210,6 +210,32 @@ int main(int argc, char **argv) {
     bipSig[40] ^= 1;
     auto ssig = ssk.Sign(bAux.data(), msg, 32);
     REQUIRE(std::vector<uint8_t>(ssig.begin(), ssig.end()) == bipSig);
+    {   // key conversions (secec/bitcoin/schnorr.go:76-108,162-186,200-307): row 0 has d' = 3 and the listed x-only key
+        namespace btc = secec::bitcoin;
+        REQUIRE(ssk.PublicKeyRef().Equal(spk) && ssk.PublicKeyRef().Bytes() == spk.Bytes());
+        REQUIRE(ssk.ScalarCopy().Equal(Scalar::NewScalarFromUint64(3)) && std::vector<uint8_t>(ssk.Bytes().begin(), ssk.Bytes().end()) == bSk);
+        auto esk = secec::PrivateKey::NewPrivateKey(bSk.data(), bSk.size());
+        auto fromEcdsa = btc::SchnorrPrivateKey::NewSchnorrPrivateKeyFromECDSA(esk);
+        REQUIRE(fromEcdsa.Equal(ssk) && fromEcdsa.PublicKeyRef().Equal(spk));
+        REQUIRE(btc::SchnorrPublicKey::NewSchnorrPublicKeyFromECDSA(esk.PublicKeyRef()).Equal(spk));
+        // a point with odd y and its negation give the same x-only key, whose point has even y
+        Point odd = esk.PublicKeyRef().PointCopy(), even;
+        if (!odd.IsYOdd()) odd.Negate(odd);
+        even.Negate(odd);
+        auto kOdd = btc::SchnorrPublicKey::NewSchnorrPublicKeyFromPoint(odd), kEven = btc::SchnorrPublicKey::NewSchnorrPublicKeyFromPoint(even);
+        REQUIRE(kOdd.Equal(kEven) && kOdd.Equal(spk) && kOdd.PointCopy().Equal(even) && kOdd.PointCopy().IsYOdd() == 0);
+        REQUIRE(spk.PointCopy().Equal(even));
+        bool bad = false;
+        try { btc::SchnorrPublicKey::NewSchnorrPublicKeyFromPoint(Point::NewIdentityPoint()); } catch (const Error &) { bad = true; }
+        REQUIRE(bad);
+        bad = false;
+        uint8_t zero32[32] = {0};
+        try { btc::SchnorrPrivateKey::NewSchnorrPrivateKey(zero32, 32); } catch (const Error &) { bad = true; }
+        REQUIRE(bad);
+        bad = false;
+        try { btc::SchnorrPrivateKey::NewSchnorrPrivateKey(detail::N_BE, 32); } catch (const Error &) { bad = true; }
+        REQUIRE(bad);
+    }
     // RFC 9380 vector "abc" (secec/h2c/h2c_test.go)
     std::string dst = argv[13], hmsg = argv[14];
     auto hXY = unhex(argv[15]);
