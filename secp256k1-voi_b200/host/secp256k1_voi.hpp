@@ -670,6 +670,83 @@ inline void ECDHBatch(const uint8_t *k32, const uint8_t *pt65, size_t n, uint8_t
 
 namespace bitcoin {
 constexpr size_t SchnorrPublicKeySize = 32, SchnorrSignatureSize = 64;
+// secec/bitcoin/schnorr.go:56 PreHashSchnorrMessage: SHA-256(SHA-256(name) || SHA-256(name) || msg), the tagged
+// hash of BIP-340 with the caller's domain separator.  `name` must be non-empty valid UTF-8 (Go refuses a string
+// that strings.ToValidUTF8 would change).  Message pre-hashing is byte hashing on the host, as in the reference
+// (Go's crypto/sha256); the challenge / nonce / aux hashes of signing and verification run on the device.
+namespace hashing {
+inline void sha256_block(uint32_t h[8], const uint8_t *p) {
+    static const uint32_t K[64] = {
+        0x428a2f98, 0x71374491, 0xb5c0fbcf, 0xe9b5dba5, 0x3956c25b, 0x59f111f1, 0x923f82a4, 0xab1c5ed5, 0xd807aa98, 0x12835b01, 0x243185be,
+        0x550c7dc3, 0x72be5d74, 0x80deb1fe, 0x9bdc06a7, 0xc19bf174, 0xe49b69c1, 0xefbe4786, 0x0fc19dc6, 0x240ca1cc, 0x2de92c6f, 0x4a7484aa,
+        0x5cb0a9dc, 0x76f988da, 0x983e5152, 0xa831c66d, 0xb00327c8, 0xbf597fc7, 0xc6e00bf3, 0xd5a79147, 0x06ca6351, 0x14292967, 0x27b70a85,
+        0x2e1b2138, 0x4d2c6dfc, 0x53380d13, 0x650a7354, 0x766a0abb, 0x81c2c92e, 0x92722c85, 0xa2bfe8a1, 0xa81a664b, 0xc24b8b70, 0xc76c51a3,
+        0xd192e819, 0xd6990624, 0xf40e3585, 0x106aa070, 0x19a4c116, 0x1e376c08, 0x2748774c, 0x34b0bcb5, 0x391c0cb3, 0x4ed8aa4a, 0x5b9cca4f,
+        0x682e6ff3, 0x748f82ee, 0x78a5636f, 0x84c87814, 0x8cc70208, 0x90befffa, 0xa4506ceb, 0xbef9a3f7, 0xc67178f2};
+    auto rotr = [](uint32_t x, int n) { return (x >> n) | (x << (32 - n)); };
+    uint32_t w[64];
+    for (int i = 0; i < 16; i++) w[i] = (uint32_t)p[4 * i] << 24 | (uint32_t)p[4 * i + 1] << 16 | (uint32_t)p[4 * i + 2] << 8 | p[4 * i + 3];
+    for (int i = 16; i < 64; i++) {
+        uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3);
+        uint32_t s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+        w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+    }
+    uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+    for (int i = 0; i < 64; i++) {
+        uint32_t t1 = hh + (rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25)) + ((e & f) ^ (~e & g)) + K[i] + w[i];
+        uint32_t t2 = (rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22)) + ((a & b) ^ (a & c) ^ (b & c));
+        hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    }
+    h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+}
+inline std::array<uint8_t, 32> sha256(const std::vector<uint8_t> &m) {
+    uint32_t h[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    std::vector<uint8_t> p(m);
+    p.push_back(0x80);
+    while (p.size() % 64 != 56) p.push_back(0);
+    const uint64_t bits = (uint64_t)m.size() * 8;
+    for (int i = 7; i >= 0; i--) p.push_back((uint8_t)(bits >> (8 * i)));
+    for (size_t o = 0; o < p.size(); o += 64) sha256_block(h, p.data() + o);
+    std::array<uint8_t, 32> out;
+    for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 4; j++) out[4 * i + j] = (uint8_t)(h[i] >> (24 - 8 * j));
+    return out;
+}
+// RFC 3629 well-formedness as Go's utf8 package decides it: no overlongs, no surrogates, nothing above U+10FFFF
+inline bool valid_utf8(const std::string &s) {
+    size_t i = 0, n = s.size();
+    while (i < n) {
+        const uint8_t c = (uint8_t)s[i];
+        size_t len;
+        uint8_t lo = 0x80, hi = 0xBF;
+        if (c < 0x80) { i++; continue; }
+        else if (c >= 0xC2 && c <= 0xDF) len = 2;
+        else if (c == 0xE0) { len = 3; lo = 0xA0; }
+        else if (c == 0xED) { len = 3; hi = 0x9F; }
+        else if (c >= 0xE1 && c <= 0xEF) len = 3;
+        else if (c == 0xF0) { len = 4; lo = 0x90; }
+        else if (c >= 0xF1 && c <= 0xF3) len = 4;
+        else if (c == 0xF4) { len = 4; hi = 0x8F; }
+        else return false;
+        if (i + len > n) return false;
+        const uint8_t c1 = (uint8_t)s[i + 1];
+        if (c1 < lo || c1 > hi) return false;
+        for (size_t k = 2; k < len; k++)
+            if (((uint8_t)s[i + k] & 0xC0) != 0x80) return false;
+        i += len;
+    }
+    return true;
+}
+}  // namespace hashing
+inline std::array<uint8_t, 32> PreHashSchnorrMessage(const std::string &name, const uint8_t *msg, size_t msg_len) {
+    if (name.empty() || !hashing::valid_utf8(name)) throw Error("secp256k1/secec/bitcoin: invalid domain separator");
+    const std::array<uint8_t, 32> tag = hashing::sha256(std::vector<uint8_t>(name.begin(), name.end()));
+    std::vector<uint8_t> buf(tag.begin(), tag.end());
+    buf.insert(buf.end(), tag.begin(), tag.end());
+    buf.insert(buf.end(), msg, msg + msg_len);
+    return hashing::sha256(buf);
+}
+
 class SchnorrPublicKey {
   public:
     // secec/bitcoin/schnorr.go:257 NewSchnorrPublicKey (lift_x is validated here, as in Go)
