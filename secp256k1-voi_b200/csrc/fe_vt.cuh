@@ -158,6 +158,22 @@ S256_HD void fe_mul8_vt(fe &r, const fe &a) {
 
 #endif
 
+#if defined(__CUDA_ARCH__) && defined(S256_DBL_CLONES) && !defined(S256_MUL_INLINE)
+// experiment: one out-of-line copy of the multiplier per call position of the doubling, so that the
+// register convention of each copy can follow the registers its operands already live in
+template <int TAG>
+static __device__ __noinline__ fe fe_mul_clone_vt(fe a, fe b) {
+    fe r;
+    fe_mul_inline_vt(r, a, b);
+    return r;
+}
+template <int TAG>
+static __device__ __noinline__ fe fe_sqr_clone_vt(fe a) {
+    fe r;
+    fe_sqr_inline_vt(r, a);
+    return r;
+}
+#endif
 template <bool VT>
 struct fe_ops;
 template <>
@@ -166,6 +182,8 @@ struct fe_ops<false> {
     S256_HD static void sub(fe &r, const fe &a, const fe &b) { fe_sub(r, a, b); }
     S256_HD static void mul(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
     S256_HD static void sqr(fe &r, const fe &a) { fe_sqr(r, a); }
+    template <int TAG> S256_HD static void mul_t(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
+    template <int TAG> S256_HD static void sqr_t(fe &r, const fe &a) { fe_sqr(r, a); }
     S256_HD static void mul_small(fe &r, const fe &a, uint32_t k) { fe_mul_small(r, a, k); }
     S256_HD static void mul8(fe &r, const fe &a) {
         fe t;
@@ -180,6 +198,13 @@ struct fe_ops<true> {
     S256_HD static void sub(fe &r, const fe &a, const fe &b) { fe_sub_vt(r, a, b); }
     S256_HD static void mul(fe &r, const fe &a, const fe &b) { fe_mul_vt(r, a, b); }
     S256_HD static void sqr(fe &r, const fe &a) { fe_sqr_vt(r, a); }
+#if defined(__CUDA_ARCH__) && defined(S256_DBL_CLONES) && !defined(S256_MUL_INLINE)
+    template <int TAG> S256_HD static void mul_t(fe &r, const fe &a, const fe &b) { r = fe_mul_clone_vt<TAG>(a, b); }
+    template <int TAG> S256_HD static void sqr_t(fe &r, const fe &a) { r = fe_sqr_clone_vt<TAG>(a); }
+#else
+    template <int TAG> S256_HD static void mul_t(fe &r, const fe &a, const fe &b) { fe_mul_vt(r, a, b); }
+    template <int TAG> S256_HD static void sqr_t(fe &r, const fe &a) { fe_sqr_vt(r, a); }
+#endif
     S256_HD static void mul_small(fe &r, const fe &a, uint32_t k) { fe_mul_small_vt(r, a, k); }
     S256_HD static void mul8(fe &r, const fe &a) { fe_mul8_vt(r, a); }
 };
