@@ -63,21 +63,20 @@ S256_HD fe fe_one() { return fe_from_u32(1); }
 // ---------------------------------------------------------------------------
 #if S256_PTX
 
-// r += c * delta where c in {0,1}; returns the carry out (only possible when r
-// was within delta of 2^256, after which r is < delta and cannot carry again).
+// r += c * delta where c in {0,1}.  A carry out is only possible when r was within delta of 2^256, after which r is
+// < delta and delta is added once more (no further carry possible).  Branch-free: the second addition is masked,
+// because the constant-time kernels run on these (point_mul_table.go:168, point_mul_glv.go:257 are branch-free too).
 S256_D void fe_fold_carry(fe &r, uint32_t c) {
     uint32_t c2;
-    uint32_t t = c * S256_DELTA_LO;
+    uint32_t t = (0u - c) & S256_DELTA_LO;
     asm("add.cc.u32 %0,%0,%9; addc.cc.u32 %1,%1,%10; addc.cc.u32 %2,%2,0; addc.cc.u32 %3,%3,0;"
         "addc.cc.u32 %4,%4,0; addc.cc.u32 %5,%5,0; addc.cc.u32 %6,%6,0; addc.cc.u32 %7,%7,0; addc.u32 %8,0,0;"
         : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]),
           "+r"(r.v[7]), "=r"(c2)
         : "r"(t), "r"(c));
-    if (c2) {  // r < delta now: add delta once more, no further carry possible
-        asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,1; addc.u32 %2,%2,0;"
-            : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2])
-            : "r"(S256_DELTA_LO));
-    }
+    asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,%4; addc.u32 %2,%2,0;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2])
+        : "r"((0u - c2) & S256_DELTA_LO), "r"(c2));
 }
 
 // r = a + b mod 2^256, returns the carry
@@ -119,13 +118,13 @@ S256_D void fe_fold_borrow(fe &r, uint32_t bw) {
         : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]),
           "+r"(r.v[7]), "=r"(bw2)
         : "r"(t), "r"(one));
-    if (bw2) {  // wrapped again: r >= 2^256 - delta now, subtracting delta cannot borrow
-        asm("sub.cc.u32 %0,%0,%8; subc.cc.u32 %1,%1,1; subc.cc.u32 %2,%2,0; subc.cc.u32 %3,%3,0;"
-            "subc.cc.u32 %4,%4,0; subc.cc.u32 %5,%5,0; subc.cc.u32 %6,%6,0; subc.u32 %7,%7,0;"
-            : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]),
-              "+r"(r.v[7])
-            : "r"(S256_DELTA_LO));
-    }
+    // wrapped again (bw2 = ~0): r >= 2^256 - delta now, subtracting delta once more cannot borrow; masked, not
+    // branched, for the constant-time kernels
+    asm("sub.cc.u32 %0,%0,%8; subc.cc.u32 %1,%1,%9; subc.cc.u32 %2,%2,0; subc.cc.u32 %3,%3,0;"
+        "subc.cc.u32 %4,%4,0; subc.cc.u32 %5,%5,0; subc.cc.u32 %6,%6,0; subc.u32 %7,%7,0;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]),
+          "+r"(r.v[7])
+        : "r"(bw2 & S256_DELTA_LO), "r"(bw2 & 1u));
 }
 S256_D void fe_sub(fe &r, const fe &a, const fe &b) {
     uint32_t bw = fe_sub_raw(r, a, b);
@@ -264,7 +263,7 @@ S256_D void fe_mul_wide(uint32_t r[16], const uint32_t a[8], const uint32_t b[8]
 // u = T * (2^32 + 977), T = t8 + t9 * 2^32 < 2^33 + 1  ->  u < 2^66
 S256_D void fe_top_times_delta(uint32_t &u0, uint32_t &u1, uint32_t &u2, uint32_t t8, uint32_t t9) {
     S256_MULW(u0, u1, t8, S256_DELTA_LO);
-    uint32_t t9d = t9 * S256_DELTA_LO;
+    uint32_t t9d = (0u - t9) & S256_DELTA_LO;  // t9 in {0, 1}
     asm("add.cc.u32 %0,%0,%2; addc.u32 %1,%3,0;" : "+r"(u1), "=r"(u2) : "r"(t8), "r"(t9));
     asm("add.cc.u32 %0,%0,%2; addc.u32 %1,%1,0;" : "+r"(u1), "+r"(u2) : "r"(t9d));
 }
@@ -277,11 +276,10 @@ S256_D void fe_fold_top(fe &out, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t
         : "=r"(out.v[0]), "=r"(out.v[1]), "=r"(out.v[2]), "=r"(out.v[3]), "=r"(out.v[4]), "=r"(out.v[5]),
           "=r"(out.v[6]), "=r"(out.v[7]), "=r"(c)
         : "r"(t0), "r"(t1), "r"(t2), "r"(t3), "r"(t4), "r"(t5), "r"(t6), "r"(t7), "r"(u0), "r"(u1), "r"(u2));
-    if (c) {  // out < 2^66 now; one more delta, no carry possible
-        asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,1; addc.u32 %2,%2,0;"
-            : "+r"(out.v[0]), "+r"(out.v[1]), "+r"(out.v[2])
-            : "r"(S256_DELTA_LO));
-    }
+    // on carry out < 2^66 now: one more delta, no carry possible; masked, not branched (constant-time kernels)
+    asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,%4; addc.u32 %2,%2,0;"
+        : "+r"(out.v[0]), "+r"(out.v[1]), "+r"(out.v[2])
+        : "r"((0u - c) & S256_DELTA_LO), "r"(c));
 }
 
 // out = r[0..15] mod p (weak)
@@ -314,20 +312,38 @@ S256_D void fe_reduce_wide(fe &out, uint32_t r[16]) {
     fe_fold_top(out, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7], t8, t9);
 }
 
+}  // namespace s256
+#include "fe_mul_gen.cuh"
+namespace s256 {
+// The multiplier the curve code uses: the split-form core of fe_mul_gen.cuh (no register re-pairing, see
+// tools/gen_fe_mul.py).  -DS256_MUL_MERGED selects the first form (merge the accumulators, then reduce) for A/B runs;
+// fe_mul_wide itself stays in use as the 8x8 product of the Z_n arithmetic (sc.cuh).
 S256_D void fe_mul_inline(fe &r, const fe &a, const fe &b) {
+#ifndef S256_MUL_MERGED
+    uint32_t w[9], t9;
+    fe_mul_core(w, t9, a.v, b.v);
+    fe_fold_top(r, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w[8], t9);
+#else
     uint32_t w[16];
     fe_mul_wide(w, a.v, b.v);
     fe_reduce_wide(r, w);
+#endif
 }
 #ifndef S256_NO_SQR
 }  // namespace s256
 #include "fe_sqr_gen.cuh"
 namespace s256 {
-// dedicated squaring: 36 + 9 MAC32 (tools/gen_fe_sqr.py)
+// dedicated squaring: 36 + 9 MAC32 (tools/gen_fe_sqr.py, tools/gen_fe_mul.py)
 S256_D void fe_sqr_inline(fe &r, const fe &a) {
+#ifndef S256_MUL_MERGED
+    uint32_t w[9], t9;
+    fe_sqr_core(w, t9, a.v);
+    fe_fold_top(r, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w[8], t9);
+#else
     uint32_t w[16];
     fe_sqr_wide(w, a.v);
     fe_reduce_wide(r, w);
+#endif
 }
 #else
 S256_D void fe_sqr_inline(fe &r, const fe &a) { fe_mul_inline(r, a, a); }

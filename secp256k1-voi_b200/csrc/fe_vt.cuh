@@ -20,7 +20,7 @@ namespace s256 {
 
 S256_D void fe_fold_carry_vt(fe &r, uint32_t c) {
     uint32_t c3;
-    uint32_t t = c * S256_DELTA_LO;
+    uint32_t t = c ? S256_DELTA_LO : 0u;  // c in {0, 1}; a product or a negation here would issue on the multiplier's pipe
     asm("add.cc.u32 %0,%0,%4; addc.cc.u32 %1,%1,%5; addc.cc.u32 %2,%2,0; addc.u32 %3,0,0;"
         : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "=r"(c3)
         : "r"(t), "r"(c));
@@ -60,21 +60,28 @@ S256_D void fe_sub_vt(fe &r, const fe &a, const fe &b) {
         }
     }
 }
-// u < 2^66 lands on limbs 0..2; the carry leaves limb 2 with probability ~2^-30
+// out = t[0..7] + (t8 + 2^32 * t9) * delta.  The common case is three instructions on limbs 0..2 after the one wide
+// multiplication: (out0, out1) = t8 * 977 + (t1 : t0) with the carry into limb 2, then "+ t8 << 32".  Anything
+// else -- a carry leaving limb 2 (probability ~2^-30) or t9 = 1 (the high half within 2^-22 of 2^256) -- takes the
+// slow path behind one branch.  No multiplication by t9, no zero register for a 64-bit addend: nothing here issues
+// on the multiplier's pipe except the one product.
 S256_D void fe_fold_top_vt(fe &out, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4, uint32_t t5,
                            uint32_t t6, uint32_t t7, uint32_t t8, uint32_t t9) {
-    uint32_t u0, u1, u2, c3;
-    fe_top_times_delta(u0, u1, u2, t8, t9);
-    asm("add.cc.u32 %0,%4,%7; addc.cc.u32 %1,%5,%8; addc.cc.u32 %2,%6,%9; addc.u32 %3,0,0;"
-        : "=r"(out.v[0]), "=r"(out.v[1]), "=r"(out.v[2]), "=r"(c3)
-        : "r"(t0), "r"(t1), "r"(t2), "r"(u0), "r"(u1), "r"(u2));
+    uint32_t c3, c3b;  // both carries are captured (never "c3 += carry": a final add issues as IMAD.X)
+    asm("mad.lo.cc.u32 %0,%4,%5,%6; madc.hi.cc.u32 %1,%4,%5,%7; addc.cc.u32 %2,%8,0; addc.u32 %3,0,0;"
+        : "=&r"(out.v[0]), "=&r"(out.v[1]), "=&r"(out.v[2]), "=&r"(c3)
+        : "r"(t8), "r"(S256_DELTA_LO), "r"(t0), "r"(t1), "r"(t2));
+    asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,0; addc.u32 %2,0,0;" : "+r"(out.v[1]), "+r"(out.v[2]), "=r"(c3b) : "r"(t8));
     out.v[3] = t3; out.v[4] = t4; out.v[5] = t5; out.v[6] = t6; out.v[7] = t7;
-    if (c3) {
+    if (c3 | c3b | t9) {  // rare: + t9 * (977 << 32) + (t9 << 64) + ((c3 + c3b) << 96), then the wrap of a carry out of limb 7
         uint32_t c;
-        asm("add.cc.u32 %0,%0,1; addc.cc.u32 %1,%1,0; addc.cc.u32 %2,%2,0; addc.cc.u32 %3,%3,0; addc.cc.u32 %4,%4,0;"
-            "addc.u32 %5,0,0;"
-            : "+r"(out.v[3]), "+r"(out.v[4]), "+r"(out.v[5]), "+r"(out.v[6]), "+r"(out.v[7]), "=r"(c));
-        if (c) {  // out < 2^66 now; one more delta, no carry possible
+        c3 += c3b;
+        asm("add.cc.u32 %0,%0,%8; addc.cc.u32 %1,%1,%9; addc.cc.u32 %2,%2,%10; addc.cc.u32 %3,%3,0; addc.cc.u32 %4,%4,0;"
+            "addc.cc.u32 %5,%5,0; addc.cc.u32 %6,%6,0; addc.u32 %7,0,0;"
+            : "+r"(out.v[1]), "+r"(out.v[2]), "+r"(out.v[3]), "+r"(out.v[4]), "+r"(out.v[5]), "+r"(out.v[6]), "+r"(out.v[7]),
+              "=r"(c)
+            : "r"((0u - t9) & S256_DELTA_LO), "r"(t9), "r"(c3));
+        if (c) {  // out < 2^67 now; one more delta, no carry possible
             asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,1; addc.u32 %2,%2,0;"
                 : "+r"(out.v[0]), "+r"(out.v[1]), "+r"(out.v[2])
                 : "r"(S256_DELTA_LO));
@@ -82,13 +89,23 @@ S256_D void fe_fold_top_vt(fe &out, uint32_t t0, uint32_t t1, uint32_t t2, uint3
     }
 }
 S256_D void fe_mul_inline_vt(fe &r, const fe &a, const fe &b) {
+#if !defined(S256_MUL_MERGED)
+    uint32_t w[9], t9;
+    fe_mul_core_w(w, t9, a.v, b.v);
+    fe_fold_top_vt(r, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w[8], t9);
+#else
     uint32_t w[16], t8, t9;
     fe_mul_wide(w, a.v, b.v);
     fe_reduce_wide_pre(w, t8, t9);
     fe_fold_top_vt(r, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], t8, t9);
+#endif
 }
 S256_D void fe_sqr_inline_vt(fe &r, const fe &a) {
-#ifndef S256_NO_SQR
+#if !defined(S256_NO_SQR) && !defined(S256_MUL_MERGED)
+    uint32_t w[9], t9;
+    fe_sqr_core_w(w, t9, a.v);
+    fe_fold_top_vt(r, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w[8], t9);
+#elif !defined(S256_NO_SQR)
     uint32_t w[16], t8, t9;
     fe_sqr_wide(w, a.v);
     fe_reduce_wide_pre(w, t8, t9);
@@ -118,6 +135,55 @@ S256_D void fe_mul_small_vt(fe &r, const fe &a, uint32_t k) {
     uint32_t e[8], t8;
     fe_mul_small_pre(e, t8, a, k);
     fe_fold_top_vt(r, e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], t8, 0u);
+}
+// r = 21a = a + 4a + 16a (b3 of the complete formulas) WITHOUT the multiplier: two funnel-shift passes and two add
+// chains on the ALU pipe, which has headroom in the ladders, instead of 8 wide multiplications plus the register
+// pairing ptxas wraps around them on the pipe that bounds the kernel.  Returns limbs + top (< 32) for the fold.
+S256_D void fe_mul21_pre(uint32_t e[8], uint32_t &t8, const fe &a) {
+    uint32_t x[8], c1, c2;
+#pragma unroll
+    for (int i = 7; i >= 1; i--) x[i] = __funnelshift_l(a.v[i - 1], a.v[i], 2);
+    x[0] = __funnelshift_l(0u, a.v[0], 2);
+    asm("add.cc.u32 %0,%9,%17; addc.cc.u32 %1,%10,%18; addc.cc.u32 %2,%11,%19; addc.cc.u32 %3,%12,%20;"
+        "addc.cc.u32 %4,%13,%21; addc.cc.u32 %5,%14,%22; addc.cc.u32 %6,%15,%23; addc.cc.u32 %7,%16,%24;"
+        "addc.u32 %8,0,0;"
+        : "=r"(e[0]), "=r"(e[1]), "=r"(e[2]), "=r"(e[3]), "=r"(e[4]), "=r"(e[5]), "=r"(e[6]), "=r"(e[7]), "=r"(c1)
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
+#pragma unroll
+    for (int i = 7; i >= 1; i--) x[i] = __funnelshift_l(a.v[i - 1], a.v[i], 4);
+    x[0] = __funnelshift_l(0u, a.v[0], 4);
+    asm("add.cc.u32 %0,%0,%9; addc.cc.u32 %1,%1,%10; addc.cc.u32 %2,%2,%11; addc.cc.u32 %3,%3,%12;"
+        "addc.cc.u32 %4,%4,%13; addc.cc.u32 %5,%5,%14; addc.cc.u32 %6,%6,%15; addc.cc.u32 %7,%7,%16;"
+        "addc.u32 %8,0,0;"
+        : "+r"(e[0]), "+r"(e[1]), "+r"(e[2]), "+r"(e[3]), "+r"(e[4]), "+r"(e[5]), "+r"(e[6]), "+r"(e[7]), "=r"(c2)
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]));
+    t8 = (a.v[7] >> 30) + (a.v[7] >> 28) + c1 + c2;
+}
+// out = e[0..7] + t * delta for a small t (< 2^16): t * 977 fits one word, so the fold is three adds on limbs 0..2
+S256_D void fe_fold_small_vt(fe &out, const uint32_t e[8], uint32_t t) {
+    uint32_t c3;
+    uint32_t u = t * S256_DELTA_LO;
+    asm("add.cc.u32 %0,%4,%7; addc.cc.u32 %1,%5,%8; addc.cc.u32 %2,%6,0; addc.u32 %3,0,0;"
+        : "=r"(out.v[0]), "=r"(out.v[1]), "=r"(out.v[2]), "=r"(c3)
+        : "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(u), "r"(t));
+    out.v[3] = e[3]; out.v[4] = e[4]; out.v[5] = e[5]; out.v[6] = e[6]; out.v[7] = e[7];
+    if (c3) {
+        uint32_t c2;
+        asm("add.cc.u32 %0,%0,1; addc.cc.u32 %1,%1,0; addc.cc.u32 %2,%2,0; addc.cc.u32 %3,%3,0; addc.cc.u32 %4,%4,0;"
+            "addc.u32 %5,0,0;"
+            : "+r"(out.v[3]), "+r"(out.v[4]), "+r"(out.v[5]), "+r"(out.v[6]), "+r"(out.v[7]), "=r"(c2));
+        if (c2) {  // wrapped: out is tiny now, one more delta cannot carry
+            asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,1; addc.u32 %2,%2,0;"
+                : "+r"(out.v[0]), "+r"(out.v[1]), "+r"(out.v[2])
+                : "r"(S256_DELTA_LO));
+        }
+    }
+}
+S256_D void fe_mul21_vt(fe &r, const fe &a) {
+    uint32_t e[8], t8;
+    fe_mul21_pre(e, t8, a);
+    fe_fold_small_vt(r, e, t8);
 }
 // r = 8a: one funnel-shift pass and a fold of the three bits shifted out, instead of three additions
 S256_D void fe_mul8_vt(fe &r, const fe &a) {
@@ -158,22 +224,6 @@ S256_HD void fe_mul8_vt(fe &r, const fe &a) {
 
 #endif
 
-#if defined(__CUDA_ARCH__) && defined(S256_DBL_CLONES) && !defined(S256_MUL_INLINE)
-// experiment: one out-of-line copy of the multiplier per call position of the doubling, so that the
-// register convention of each copy can follow the registers its operands already live in
-template <int TAG>
-static __device__ __noinline__ fe fe_mul_clone_vt(fe a, fe b) {
-    fe r;
-    fe_mul_inline_vt(r, a, b);
-    return r;
-}
-template <int TAG>
-static __device__ __noinline__ fe fe_sqr_clone_vt(fe a) {
-    fe r;
-    fe_sqr_inline_vt(r, a);
-    return r;
-}
-#endif
 template <bool VT>
 struct fe_ops;
 template <>
@@ -182,8 +232,25 @@ struct fe_ops<false> {
     S256_HD static void sub(fe &r, const fe &a, const fe &b) { fe_sub(r, a, b); }
     S256_HD static void mul(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
     S256_HD static void sqr(fe &r, const fe &a) { fe_sqr(r, a); }
-    template <int TAG> S256_HD static void mul_t(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
-    template <int TAG> S256_HD static void sqr_t(fe &r, const fe &a) { fe_sqr(r, a); }
+#if S256_PTX && !defined(S256_B3_MULT)
+    // 21a and 8a by shifts and adds with the branch-free fold (the constant-time flavour of fe_mul21_vt / fe_mul8_vt)
+    S256_HD static void mul_small(fe &r, const fe &a, uint32_t k) {
+        if (k == 21u) {
+            uint32_t e[8], t8;
+            fe_mul21_pre(e, t8, a);
+            fe_fold_top(r, e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], t8, 0u);
+        } else {
+            fe_mul_small(r, a, k);
+        }
+    }
+    S256_HD static void mul8(fe &r, const fe &a) {
+        uint32_t e[8];
+#pragma unroll
+        for (int i = 7; i >= 1; i--) e[i] = __funnelshift_l(a.v[i - 1], a.v[i], 3);
+        e[0] = a.v[0] << 3;
+        fe_fold_top(r, e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7], a.v[7] >> 29, 0u);
+    }
+#else
     S256_HD static void mul_small(fe &r, const fe &a, uint32_t k) { fe_mul_small(r, a, k); }
     S256_HD static void mul8(fe &r, const fe &a) {
         fe t;
@@ -191,6 +258,7 @@ struct fe_ops<false> {
         fe_add(t, t, t);
         fe_add(r, t, t);
     }
+#endif
 };
 template <>
 struct fe_ops<true> {
@@ -198,14 +266,13 @@ struct fe_ops<true> {
     S256_HD static void sub(fe &r, const fe &a, const fe &b) { fe_sub_vt(r, a, b); }
     S256_HD static void mul(fe &r, const fe &a, const fe &b) { fe_mul_vt(r, a, b); }
     S256_HD static void sqr(fe &r, const fe &a) { fe_sqr_vt(r, a); }
-#if defined(__CUDA_ARCH__) && defined(S256_DBL_CLONES) && !defined(S256_MUL_INLINE)
-    template <int TAG> S256_HD static void mul_t(fe &r, const fe &a, const fe &b) { r = fe_mul_clone_vt<TAG>(a, b); }
-    template <int TAG> S256_HD static void sqr_t(fe &r, const fe &a) { r = fe_sqr_clone_vt<TAG>(a); }
+#if S256_PTX && !defined(S256_B3_MULT)
+    S256_HD static void mul_small(fe &r, const fe &a, uint32_t k) {
+        if (k == 21u) fe_mul21_vt(r, a); else fe_mul_small_vt(r, a, k);
+    }
 #else
-    template <int TAG> S256_HD static void mul_t(fe &r, const fe &a, const fe &b) { fe_mul_vt(r, a, b); }
-    template <int TAG> S256_HD static void sqr_t(fe &r, const fe &a) { fe_sqr_vt(r, a); }
-#endif
     S256_HD static void mul_small(fe &r, const fe &a, uint32_t k) { fe_mul_small_vt(r, a, k); }
+#endif
     S256_HD static void mul8(fe &r, const fe &a) { fe_mul8_vt(r, a); }
 };
 

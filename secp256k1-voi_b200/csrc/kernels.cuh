@@ -337,6 +337,25 @@ S256_HD void item_schnorr_scalars(size_t i, size_t n, const uint8_t *pkx32, cons
 //   G half: COMB_NW mixed additions from the precomputed comb, no doublings
 // Public data, variable time as in the reference: the group law runs on fe_ops<true> (fe_vt.cuh).
 // ---------------------------------------------------------------------------
+// a table row as twelve 64-bit loads (register pairs are what the multiplier wants anyway; 128-bit loads would force
+// 4-register alignment, which cost more in moves than it saved -- DESIGN.md section 5)
+S256_HD void pt_fetch64(pt &r, const pt *p) {
+#if defined(__CUDA_ARCH__) && !defined(S256_DSM_LD32)
+    const uint2 *q = reinterpret_cast<const uint2 *>(p);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint2 a = q[k], b = q[4 + k], c = q[8 + k];
+        r.x.v[2 * k] = a.x; r.x.v[2 * k + 1] = a.y;
+        r.y.v[2 * k] = b.x; r.y.v[2 * k + 1] = b.y;
+        r.z.v[2 * k] = c.x; r.z.v[2 * k + 1] = c.y;
+    }
+#else
+    r = *p;
+#endif
+}
+// public data, variable time as in the reference: the short-ripple field operations of fe_vt.cuh.  (The branch-free
+// set in this ladder: 22.74 ms against 21.55, k_dsm at 2^20 -- profiles/r02_variants.json.)
+constexpr bool DSM_VT = true;
 S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
                       const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
     pt *T = tbl + i * (size_t)DSM_TS;
@@ -350,10 +369,10 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
 #endif
         for (int k = 2; k <= DSM_TS; k += 2) {
             pt h = T[k / 2 - 1];
-            pt_double<true>(cur, h);
+            pt_double<DSM_VT>(cur, h);
             T[k - 1] = cur;
             if (k < DSM_TS) {
-                pt_add_mixed<true>(cur, cur, P.x, P.y);
+                pt_add_mixed<DSM_VT>(cur, cur, P.x, P.y);
                 T[k] = cur;
             }
         }
@@ -366,14 +385,30 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
 #pragma unroll 1
 #endif
     for (int s = DSM_ND - 1; s >= 0; s--) {
+        // digits first: their loads and the table rows' trip from L2 overlap the doublings
+        int da = dig1[(size_t)s * n + i];
+        int db = dig2[(size_t)s * n + i];
+#if defined(__CUDA_ARCH__) && !defined(S256_DSM_NO_PREFETCH)
+        {
+            int ma = da < 0 ? -da : da, mb = db < 0 ? -db : db;
+            if (ma) {
+                const char *r = reinterpret_cast<const char *>(T + (ma - 1));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(r));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(r + 64));
+            }
+            if (mb) {
+                const char *r = reinterpret_cast<const char *>(T + (mb - 1));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(r));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(r + 64));
+            }
+        }
+#endif
         if (s != DSM_ND - 1) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-            for (int k = 0; k < DSM_W; k++) pt_double<true>(acc, acc);
+            for (int k = 0; k < DSM_W; k++) pt_double<DSM_VT>(acc, acc);
         }
-        int da = dig1[(size_t)s * n + i];
-        int db = dig2[(size_t)s * n + i];
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -382,13 +417,14 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
             if (d != 0) {
                 uint32_t neg = (uint32_t)(d < 0) ^ ((fl >> (1 + h)) & 1u);
                 int mag = d < 0 ? -d : d;
-                pt q = T[mag - 1];
-                if (h) fe_mul_vt(q.x, q.x, beta);
+                pt q;
+                pt_fetch64(q, T + (mag - 1));
+                if (h) fe_ops<DSM_VT>::mul(q.x, q.x, beta);
                 if (neg) {
                     fe z = fe_zero();
-                    fe_sub_vt(q.y, z, q.y);
+                    fe_ops<DSM_VT>::sub(q.y, z, q.y);
                 }
-                pt_add<true>(acc, acc, q);
+                pt_add<DSM_VT>(acc, acc, q);
             }
         }
     }
@@ -404,9 +440,9 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
             apt g = comb[(size_t)w * COMB_SZ + (mag - 1u)];
             if (d < 0) {
                 fe z = fe_zero();
-                fe_sub_vt(g.y, z, g.y);
+                fe_ops<DSM_VT>::sub(g.y, z, g.y);
             }
-            pt_add_mixed<true>(acc, acc, g.x, g.y);
+            pt_add_mixed<DSM_VT>(acc, acc, g.x, g.y);
         }
     }
     res[i] = acc;

@@ -132,21 +132,21 @@ template <bool VT = false>
 S256_HD void pt_double(pt &v, const pt &p) {
     typedef fe_ops<VT> F;
     fe t0, t1, t2, x3, y3, z3;
-    F::template sqr_t<7>(t0, p.y);
+    F::sqr(t0, p.y);
     F::mul8(z3, t0);
-    F::template mul_t<1>(t1, p.y, p.z);
-    F::template sqr_t<8>(t2, p.z);
+    F::mul(t1, p.y, p.z);
+    F::sqr(t2, p.z);
     F::mul_small(t2, t2, S256_B3);
-    F::template mul_t<2>(x3, t2, z3);
+    F::mul(x3, t2, z3);
     F::add(y3, t0, t2);
-    F::template mul_t<3>(z3, t1, z3);
+    F::mul(z3, t1, z3);
     F::add(t1, t2, t2);
     F::add(t2, t1, t2);
     F::sub(t0, t0, t2);
-    F::template mul_t<4>(y3, t0, y3);
+    F::mul(y3, t0, y3);
     F::add(y3, x3, y3);
-    F::template mul_t<5>(t1, p.x, p.y);
-    F::template mul_t<6>(x3, t0, t1);
+    F::mul(t1, p.x, p.y);
+    F::mul(x3, t0, t1);
     F::add(x3, x3, x3);
     v.x = x3;
     v.y = y3;
