@@ -21,7 +21,11 @@
  *
  * The *_dev twins take device pointers and a cudaStream_t (as void*; NULL =
  * default stream), enqueue the work and return without synchronising; they
- * are what bench.py times with inputs resident in HBM.
+ * are what bench.py times with inputs resident in HBM.  All calls on one
+ * context share its scratch memory, so they are also ordered ON THE DEVICE:
+ * the work of a call starts only after the work of the previous call on the
+ * same context has finished, whatever streams the two calls used (an event
+ * recorded at the end of every call).  Two contexts on one device overlap freely.
  */
 #ifndef SECP256K1_B200_H
 #define SECP256K1_B200_H
@@ -202,6 +206,30 @@ int s256_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, i
 int s256_msm_partial(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime,
                      uint8_t *partial96, uint8_t *status);
 int s256_msm_combine(s256_ctx *ctx, const uint8_t *partials96, size_t m, uint8_t *out65, uint8_t *status);
+/* device-resident twin: k32 / pt65 / out65 / status are device pointers, nothing is synchronised */
+int s256_msm_dev(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, uint8_t *out65,
+                 uint8_t *status, void *stream);
+
+/* --- Point.MultiScalarMult over a batch SHARDED across GPUs (BASELINE.json configs[4]; the operation is
+ *     point_mul_multi.go:25-117, the sharding is this engine's).  One process and one context per GPU; rank g
+ *     passes its own contiguous slice (n_local items, possibly 0).  Every rank reduces its slice to one projective
+ *     partial, ONE ncclAllGather of 112 bytes per rank brings the partials together on every GPU, they are folded
+ *     and encoded there: all ranks return the same 65-byte point and status.  The partials never visit the host;
+ *     the host-pointer form synchronises once per call, the _dev form not at all.
+ *       s256_comm_unique_id : rank 0 calls it and hands the 128 bytes to the other ranks (any channel);
+ *       s256_comm_init      : every rank, collectively (ncclCommInitRank on the context's device);
+ *       s256_comm_free      : optional, s256_free releases the communicator too.
+ *     NCCL is loaded with dlopen on first use (the copy already in the process if there is one); a context without a
+ *     communicator, or a communicator of one rank, computes the plain MSM.  S256_ERR_NCCL: library missing or a
+ *     collective failed (s256_last_cuda_error has the text). */
+int s256_msm_plan(size_t n, int *window_bits, int *windows); /* the Pippenger plan for n points (measurement aid) */
+int s256_comm_unique_id(uint8_t id128[128]);
+int s256_comm_init(s256_ctx *ctx, const uint8_t id128[128], int rank, int nranks);
+int s256_comm_free(s256_ctx *ctx);
+int s256_msm_sharded(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n_local, int vartime, uint8_t *out65,
+                     uint8_t *status);
+int s256_msm_sharded_dev(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n_local, int vartime,
+                         uint8_t *out65, uint8_t *status, void *stream);
 
 /* --- page-locked host buffers.  The host-pointer entry points accept any memory, but copies from and
  *     to pageable memory are staged by the driver at a fraction of the PCIe rate; batch buffers
@@ -238,6 +266,11 @@ uint64_t s256_launch_count(const s256_ctx *ctx);
 /* MAC32 (32x32->64 multiply-accumulates) executed per item by each path,
  * derived from the modmul counts in DESIGN.md; key is an entry point name. */
 double s256_mac32_per_item(const char *entry_point);
+/* Measurement aids for the roofline (bench.py): the ladder additions the last verification-type call really executed
+ * for the first n items of its last chunk (zero digits are skipped), and the executed MAC32 of one k_dsm item given
+ * those counts per item. */
+int s256_debug_ladder_add_count(s256_ctx *ctx, size_t n, uint64_t *adds_first_half, uint64_t *adds_lambda_half);
+double s256_mac32_k_dsm(double adds_per_item, double beta_muls_per_item);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -261,3 +261,27 @@ def batch_ecdsa_sign_rfc6979(priv, digest, threads=None):
     sig = np.zeros((n, 64), np.uint8); rec = np.zeros(n, np.uint8); st = np.zeros(n, np.uint8)
     lib().orc_batch_ecdsa_sign_rfc6979(_p(priv), _p(digest), C.c_size_t(n), _p(sig), _p(rec), _p(st), threads or default_threads())
     return sig, rec, st
+
+
+# ---- OpenSSL sanity anchor (oracle/openssl_baseline.c): measurement only -------------------------------------------
+def openssl_ecdsa_verify(pk, digest, sig, reps=1, threads=None):
+    """(ok bytes, seconds for `reps` passes of ECDSA_do_verify on `threads` threads), or None when libcrypto / its headers
+    are not there to build against."""
+    so = os.path.join(_HERE, "_build", "libosslbase.so")
+    src = os.path.join(_HERE, "openssl_baseline.c")
+    try:
+        if (not os.path.exists(so)) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _HERE, "-B", "_build/libosslbase.so"], stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL)
+        L = C.CDLL(so)
+    except (OSError, subprocess.CalledProcessError):
+        return None
+    pk, digest, sig = _np(pk, 65), _np(digest, 32), _np(sig, 64)
+    n = len(pk)
+    ok = np.zeros(n, np.uint8)
+    secs = C.c_double(0)
+    rc = L.ossl_batch_ecdsa_verify(_p(pk), _p(digest), _p(sig), C.c_size_t(n), int(reps), int(threads or default_threads()),
+                                   _p(ok), C.byref(secs))
+    if rc != 0:
+        return None
+    return ok, secs.value

@@ -39,7 +39,9 @@ EXPORTED_SYMBOLS = [
     "s256_ecdsa_recover", "s256_ecdsa_recover_dev",
     "s256_ecdsa_sign_rfc6979", "s256_ecdsa_sign_rfc6979_dev",
     "s256_schnorr_verify", "s256_schnorr_verify_dev", "s256_schnorr_sign", "s256_schnorr_sign_dev",
-    "s256_msm", "s256_msm_partial", "s256_msm_combine", "s256_hash_to_curve", "s256_expand_message_xmd",
+    "s256_msm", "s256_msm_partial", "s256_msm_combine", "s256_msm_dev", "s256_msm_sharded", "s256_msm_sharded_dev",
+    "s256_comm_unique_id", "s256_comm_init", "s256_comm_free", "s256_msm_plan", "s256_hash_to_curve", "s256_expand_message_xmd",
+    "s256_debug_ladder_add_count", "s256_mac32_k_dsm",
     "s256_debug_gen_table", "s256_debug_field_op", "s256_microbench_imad",
     "s256_microbench_variant", "s256_microbench_fe_mul", "s256_profile_enable", "s256_profile_read",
     "s256_launch_count", "s256_mac32_per_item", "s256_host_alloc", "s256_host_free",
@@ -76,6 +78,8 @@ def load_library():
     lib.s256_launch_count.argtypes = [C.c_void_p]
     lib.s256_mac32_per_item.restype = C.c_double
     lib.s256_mac32_per_item.argtypes = [C.c_char_p]
+    lib.s256_mac32_k_dsm.restype = C.c_double
+    lib.s256_mac32_k_dsm.argtypes = [C.c_double, C.c_double]
     lib.s256_free.argtypes = [C.c_void_p]
     lib.s256_free.restype = None
     lib.s256_host_alloc.restype = C.c_void_p
@@ -84,6 +88,13 @@ def load_library():
     lib.s256_host_free.restype = None
     _lib = lib
     return lib
+
+
+def msm_plan(n):
+    """(window bits, windows) of the Pippenger plan for n points on one GPU."""
+    c, w = C.c_int(0), C.c_int(0)
+    load_library().s256_msm_plan(C.c_size_t(n), C.byref(c), C.byref(w))
+    return c.value, w.value
 
 
 def mac32_per_item(entry_point):
@@ -545,6 +556,17 @@ class Engine:
 
     # -- Point.MultiScalarMult[Vartime] (point_mul_multi.go:25,73) -------------
     def msm(self, k32, pt65, vartime=True):
+        if _is_torch_cuda(k32):  # device-resident: (65,) and (1,) uint8 tensors, nothing synchronised
+            import torch
+            n = k32.numel() // 32
+            if pt65.numel() // 65 != n:
+                raise ValueError("secp256k1: len(scalars) != len(points)")
+            out = torch.empty(65, dtype=torch.uint8, device=k32.device)
+            st = torch.empty(1, dtype=torch.uint8, device=k32.device)
+            a = self._dev_args(k32, pt65, out, st)
+            self._check(self._lib.s256_msm_dev(self._ctx, a[0], a[1], C.c_size_t(n), int(vartime), a[2], a[3], self._stream()),
+                        "msm_dev")
+            return out, st
         k, p = _host(k32, 32), _host(pt65, 65)
         n = len(k)
         if len(p) != n:
@@ -555,6 +577,58 @@ class Engine:
         self._check(self._lib.s256_msm(self._ctx, self._hp(k), self._hp(p), C.c_size_t(n), int(vartime), self._hp(out),
                                        C.byref(st)), "msm")
         return out, st.value
+
+    # -- the same product over a batch sharded across GPUs (BASELINE configs[4]) ------------
+    @staticmethod
+    def comm_unique_id():
+        """Rank 0: the 128 bytes (ncclUniqueId) every rank passes to comm_init."""
+        buf = (C.c_uint8 * 128)()
+        rc = load_library().s256_comm_unique_id(buf)
+        if rc != 0:
+            raise S256Error(f"comm_unique_id: {load_library().s256_strerror(rc).decode()} (rc={rc})")
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, nranks):
+        """Collective: builds this context's NCCL communicator (one rank per GPU)."""
+        if len(unique_id) != 128:
+            raise ValueError("unique id must be 128 bytes")
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._lib.s256_comm_init(self._ctx, buf, int(rank), int(nranks)), "comm_init")
+        self.comm_size = int(nranks)
+
+    def comm_free(self):
+        self._check(self._lib.s256_comm_free(self._ctx), "comm_free")
+        self.comm_size = 0
+
+    def msm_sharded(self, k32_local, pt65_local, vartime=True):
+        """This rank's slice in, the whole product out (on every rank): local Pippenger, ONE ncclAllGather of 112 bytes
+        per rank inside the library, fold, encode.  Device tensors: nothing is synchronised; host arrays: one sync."""
+        if _is_torch_cuda(k32_local):
+            import torch
+            n = k32_local.numel() // 32
+            if pt65_local.numel() // 65 != n:
+                raise ValueError("secp256k1: len(scalars) != len(points)")
+            out = torch.empty(65, dtype=torch.uint8, device=k32_local.device)
+            st = torch.empty(1, dtype=torch.uint8, device=k32_local.device)
+            a = self._dev_args(k32_local, pt65_local, out, st)
+            self._check(self._lib.s256_msm_sharded_dev(self._ctx, a[0], a[1], C.c_size_t(n), int(vartime), a[2], a[3],
+                                                       self._stream()), "msm_sharded_dev")
+            return out, st
+        k, p = _host(k32_local, 32), _host(pt65_local, 65)
+        n = len(k)
+        if len(p) != n:
+            raise ValueError("secp256k1: len(scalars) != len(points)")
+        out = self._out(34, 65)
+        st = C.c_uint8(0)
+        self._check(self._lib.s256_msm_sharded(self._ctx, self._hp(k), self._hp(p), C.c_size_t(n), int(vartime),
+                                               self._hp(out), C.byref(st)), "msm_sharded")
+        return out, st.value
+
+    def ladder_add_count(self, n):
+        """(additions of the first half, of the lambda half) the last verification-type call executed for its first n items."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._lib.s256_debug_ladder_add_count(self._ctx, C.c_size_t(n), C.byref(a), C.byref(b)), "ladder_add_count")
+        return a.value, b.value
 
     def msm_partial(self, k32, pt65, vartime=True):
         k, p = _host(k32, 32), _host(pt65, 65)

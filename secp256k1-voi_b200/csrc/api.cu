@@ -337,16 +337,18 @@ extern "C" void s256_free(s256_ctx *ctx) {
     if (!ctx) return;
     {
         dev_guard g(ctx->device);
+        s256_internal_comm_release(ctx);
         void *ptrs[] = {ctx->comb, ctx->ct_tab, ctx->ct_tab_small, ctx->aff, ctx->u1,   ctx->dig1, ctx->dig2, ctx->sfl, ctx->pvalid,
                         ctx->cstat, ctx->tbl,   ctx->res, ctx->in_a, ctx->in_b, ctx->in_c, ctx->out, ctx->st,
                         ctx->sink, ctx->msm_counts, ctx->msm_offsets, ctx->msm_cursor, ctx->msm_entries, ctx->msm_flag,
                         ctx->msm_buckets, ctx->msm_win, ctx->msm_acc, ctx->msm_tmp, ctx->msm_cub, ctx->msm_nsl, ctx->msm_sloff,
-                        ctx->msm_perm, ctx->msm_hist, ctx->msm_range, ctx->msm_part, ctx->msm_sbkt};
+                        ctx->msm_perm, ctx->msm_hist, ctx->msm_range, ctx->msm_part, ctx->msm_sbkt, ctx->comm_buf};
         for (void *p : ptrs)
             if (p) cudaFree(p);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
         if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
         if (ctx->ev_decode) cudaEventDestroy(ctx->ev_decode);
+        if (ctx->ev_idle) cudaEventDestroy(ctx->ev_idle);
         for (cudaEvent_t e : ctx->ev_pipe)
             if (e) cudaEventDestroy(e);
         if (ctx->stream3) cudaStreamDestroy(ctx->stream3);
@@ -374,7 +376,7 @@ static int ctx_alloc(s256_ctx *ctx) {
     ctx->in_b_bytes = 32 * cap;
     CK(cudaMalloc(&ctx->out, 65 * cap));
     CK(cudaMalloc(&ctx->st, cap));
-    CK(cudaMalloc(&ctx->sink, 8));
+    CK(cudaMalloc(&ctx->sink, 16));
     return S256_SUCCESS;
 }
 
@@ -402,7 +404,7 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
                                cudaStreamCreateWithPriority(&ctx->stream3, cudaStreamNonBlocking, prio_hi) != cudaSuccess))
         rc = S256_ERR_CUDA;
     if (rc == S256_SUCCESS && (cudaEventCreateWithFlags(&ctx->ev_decode, cudaEventDisableTiming) != cudaSuccess ||
-                               false))
+                               cudaEventCreateWithFlags(&ctx->ev_idle, cudaEventDisableTiming) != cudaSuccess))
         rc = S256_ERR_CUDA;
     for (cudaEvent_t &e : ctx->ev_pipe)
         if (rc == S256_SUCCESS && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = S256_ERR_CUDA;
@@ -540,6 +542,7 @@ extern "C" int s256_ecdsa_verify_dev(s256_ctx *ctx, const uint8_t *pk, const uin
     ENTER(ctx);
     if (n && (!pk || !dg || !sig || !ok)) return S256_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    scratch_guard sg_(ctx, s, false);
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
         return chunk_ecdsa_verify(ctx, view_at(ctx, 0), pk + 65 * off, dg + 32 * off, sig + 64 * off, flags, c, ok + off, s);
     });
@@ -645,6 +648,7 @@ static int verify_pipelined(s256_ctx *ctx, const uint8_t *pk, const uint8_t *dg,
 extern "C" int s256_ecdsa_verify(s256_ctx *ctx, const uint8_t *pk, const uint8_t *dg, const uint8_t *sig,
                                  uint32_t flags, size_t n, uint8_t *ok) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (n && (!pk || !dg || !sig || !ok)) return S256_ERR_ARG;
     if (ctx->pipe_parts == 1 && n >= ((size_t)1 << 18)) {
         int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
@@ -684,6 +688,7 @@ extern "C" int s256_ecdsa_recover_dev(s256_ctx *ctx, const uint8_t *dg, const ui
     ENTER(ctx);
     if (n && (!dg || !sig65 || !pk65 || !status)) return S256_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    scratch_guard sg_(ctx, s, false);
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
         return chunk_ecdsa_recover(ctx, view_at(ctx, 0), dg + 32 * off, sig65 + 65 * off, c, pk65 + 65 * off, status + off, s);
     });
@@ -692,6 +697,7 @@ extern "C" int s256_ecdsa_recover_dev(s256_ctx *ctx, const uint8_t *dg, const ui
 extern "C" int s256_ecdsa_recover(s256_ctx *ctx, const uint8_t *dg, const uint8_t *sig65, size_t n, uint8_t *pk65,
                                   uint8_t *status) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (n && (!dg || !sig65 || !pk65 || !status)) return S256_ERR_ARG;
     int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t s) {
         CK(cudaMemcpyAsync(v.in_b, dg + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
@@ -710,6 +716,7 @@ extern "C" int s256_schnorr_verify_dev(s256_ctx *ctx, const uint8_t *pkx, const 
     ENTER(ctx);
     if (n && (!pkx || (!msg && msg_len) || !sig || !ok)) return S256_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    scratch_guard sg_(ctx, s, false);
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
         return chunk_schnorr_verify(ctx, view_at(ctx, 0), pkx + 32 * off, msg + msg_len * off, msg_len, sig + 64 * off, c, ok + off, s);
     });
@@ -718,6 +725,7 @@ extern "C" int s256_schnorr_verify_dev(s256_ctx *ctx, const uint8_t *pkx, const 
 extern "C" int s256_schnorr_verify(s256_ctx *ctx, const uint8_t *pkx, const uint8_t *msg, size_t msg_len,
                                    const uint8_t *sig, size_t n, uint8_t *ok) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (n && (!pkx || (!msg && msg_len) || !sig || !ok)) return S256_ERR_ARG;
     size_t need = (msg_len ? msg_len : 1) * (n < ctx->cap ? n : ctx->cap);
     if (need > ctx->in_b_bytes) {
@@ -746,6 +754,7 @@ extern "C" int s256_double_scalar_mult_basepoint_vartime_dev(s256_ctx *ctx, cons
     ENTER(ctx);
     if (n && (!u1 || !u2 || !pt65 || !out65 || !status)) return S256_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    scratch_guard sg_(ctx, s, false);
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
         return chunk_dsm(ctx, view_at(ctx, 0), u1 + 32 * off, u2 + 32 * off, pt65 + 65 * off, c, out65 + 65 * off, status + off, s);
     });
@@ -755,6 +764,7 @@ extern "C" int s256_double_scalar_mult_basepoint_vartime(s256_ctx *ctx, const ui
                                                          const uint8_t *pt65, size_t n, uint8_t *out65,
                                                          uint8_t *status) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (n && (!u1 || !u2 || !pt65 || !out65 || !status)) return S256_ERR_ARG;
     int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t s) {
         CK(cudaMemcpyAsync(v.in_a, pt65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
@@ -774,6 +784,7 @@ extern "C" int s256_scalar_base_mult_dev(s256_ctx *ctx, const uint8_t *k32, size
     ENTER(ctx);
     if (n && (!k32 || !out65 || !status)) return S256_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    scratch_guard sg_(ctx, s, false);
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
         return chunk_base_mult(ctx, view_at(ctx, 0), k32 + 32 * off, c, out65 + 65 * off, status + off, s);
     });
@@ -781,6 +792,7 @@ extern "C" int s256_scalar_base_mult_dev(s256_ctx *ctx, const uint8_t *k32, size
 }
 extern "C" int s256_scalar_base_mult(s256_ctx *ctx, const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (n && (!k32 || !out65 || !status)) return S256_ERR_ARG;
     int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t s) {
         CK(cudaMemcpyAsync(v.in_b, k32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
@@ -798,6 +810,7 @@ static int scalar_mult_common_dev(s256_ctx *ctx, const uint8_t *k32, const uint8
     ENTER(ctx);
     if (n && (!k32 || !pt65 || !out || !status)) return S256_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    scratch_guard sg_(ctx, s, false);
     size_t w = mode == 1 ? 32 : 65;
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
         return chunk_scalar_mult(ctx, view_at(ctx, 0), k32 + 32 * off, pt65 + 65 * off, c, mode, out + w * off, status + off, s);
@@ -807,6 +820,7 @@ static int scalar_mult_common_dev(s256_ctx *ctx, const uint8_t *k32, const uint8
 static int scalar_mult_common_host(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int mode,
                                    uint8_t *out, uint8_t *status) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (n && (!k32 || !pt65 || !out || !status)) return S256_ERR_ARG;
     size_t w = mode == 1 ? 32 : 65;
     int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t s) {
@@ -839,6 +853,7 @@ extern "C" int s256_ecdh_dev(s256_ctx *ctx, const uint8_t *k32, const uint8_t *p
 // NewPointFromBytes on compressed encodings (point_s11n.go:140): 33 B -> 65 B + status
 extern "C" int s256_point_decompress(s256_ctx *ctx, const uint8_t *pt33, size_t n, uint8_t *out65, uint8_t *status) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (n && (!pt33 || !out65 || !status)) return S256_ERR_ARG;
     cudaStream_t s = ctx->stream;
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
@@ -856,6 +871,7 @@ extern "C" int s256_point_decompress(s256_ctx *ctx, const uint8_t *pt33, size_t 
 extern "C" int s256_new_public_keys(s256_ctx *ctx, const uint8_t *enc65, const uint8_t *enc_len, size_t n, uint8_t *out65,
                                     uint8_t *status) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (n && (!enc65 || !enc_len || !out65 || !status)) return S256_ERR_ARG;
     cudaStream_t s = ctx->stream;
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
@@ -929,6 +945,7 @@ extern "C" int s256_bitcoin_verify_asn1(s256_ctx *ctx, const uint8_t *pk65, cons
 // ---------------------------------------------------------------------------
 extern "C" int s256_debug_gen_table(s256_ctx *ctx, int wbits, int nwin, uint8_t *out) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (!out || wbits < 1 || wbits > 16 || nwin < 1 || wbits * nwin > 256) return S256_ERR_ARG;
     size_t total = (size_t)nwin << wbits;
     apt *d = nullptr;
@@ -958,6 +975,7 @@ extern "C" int s256_debug_gen_table(s256_ctx *ctx, int wbits, int nwin, uint8_t 
 extern "C" int s256_debug_field_op(s256_ctx *ctx, int op, const uint8_t *a32, const uint8_t *b32, size_t n,
                                    uint8_t *out32) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (n && (!a32 || !b32 || !out32)) return S256_ERR_ARG;
     if (n > ctx->cap) return S256_ERR_ARG;
     cudaStream_t s = ctx->stream;
@@ -1123,16 +1141,63 @@ extern "C" int s256_microbench_fe_mul(s256_ctx *ctx, int form, int iters, double
     return check_launch(ctx);
 }
 
-// MAC32 per item actually executed (DESIGN.md "work per item"): F_p mul = 73 (64 + 9),
-// F_p square = 45 (36 + 9), small-constant mul = 9, Z_n modmul = 139 (64 + 40 + 30 + 5).
+// Measured, not modelled: the number of ladder additions the last verification-type call on this context really
+// executed (non-zero digits of its two recoded halves), for the first `n` items of its last chunk.  bench.py turns it
+// into the executed MAC32 of that k_dsm launch: additions with a zero digit are skipped, and the lambda half costs one
+// more multiplication (x -> beta x) per executed addition.
+__global__ void __launch_bounds__(S256_TPB) k_count_nonzero_digits(const int8_t *d1, const int8_t *d2, size_t total,
+                                                                  unsigned long long *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    unsigned a = 0, b = 0;
+    for (; i < total; i += stride) {
+        a += d1[i] != 0;
+        b += d2[i] != 0;
+    }
+    a = __reduce_add_sync(0xffffffffu, a);
+    b = __reduce_add_sync(0xffffffffu, b);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(out, (unsigned long long)a);
+        atomicAdd(out + 1, (unsigned long long)b);
+    }
+}
+extern "C" int s256_debug_ladder_add_count(s256_ctx *ctx, size_t n, uint64_t *adds_g_half, uint64_t *adds_lambda_half) {
+    ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
+    if (!adds_g_half || !adds_lambda_half || n > ctx->cap) return S256_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->sink, 0, 16, s));
+    if (n) LAUNCH(ctx, k_count_nonzero_digits, 148 * 8, 0, s, ctx->dig1, ctx->dig2, (size_t)DSM_ND * n, ctx->sink);
+    unsigned long long h[2] = {0, 0};
+    CK(cudaMemcpyAsync(h, ctx->sink, 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *adds_g_half = h[0];
+    *adds_lambda_half = h[1];
+    return check_launch(ctx);
+}
+// executed MAC32 of one k_dsm item given its measured number of ladder additions (both halves) and beta multiplications
+extern "C" double s256_mac32_k_dsm(double adds_per_item, double beta_muls_per_item) {
+    const double M = 73, S = 45;
+    const double dbl = 6 * M + 2 * S, add = 12 * M, mix = 11 * M;
+    return (DSM_TS / 2) * dbl + (DSM_TS / 2 - 1) * mix + (DSM_ND - 1) * DSM_W * dbl + adds_per_item * add +
+           beta_muls_per_item * M + COMB_NW * mix;
+}
+
+// MAC32 (32x32->64 multiply-accumulates, i.e. IMAD.WIDE issues) per item as EXECUTED:
+// F_p mul = 73 (64 + 8 + the fold's one), F_p square = 45 (28 + 8 + 8 + 1), Z_n modmul = 133.  Multiplication by
+// b3 = 21 and by 8 are shifts and adds now (fe_vt.cuh): no multiplier work in the variable-time flavour, one
+// product (the fold) in the constant-time one.  Ladder steps with a zero digit are skipped, so the model charges the
+// EXPECTED number of executed additions for uniformly random scalars: a signed 5-bit digit is zero with probability
+// 2^-5, the top digit of a 128-bit half (3 bits + carry) with probability 1/8.
 extern "C" double s256_mac32_per_item(const char *name) {
-    const double M = 73, S = 45, SM = 9, ZN = 139;
-    const double dbl = 6 * M + 2 * S + SM, add = 12 * M + 2 * SM, mix = 11 * M + 2 * SM;
+    const double M = 73, S = 45, ZN = 133;
+    const double dbl = 6 * M + 2 * S, add = 12 * M, mix = 11 * M;              // variable-time flavour (k_dsm, MSM)
+    const double dbl_ct = dbl + 2, mix_ct = mix + 2;                              // + the folds of 21a and 8a / 21a twice
     // inversions are safegcd (modinv.cuh): 20 batches x (54 + 36) 32x32->64 products, whatever the modulus
     const double inv_fe = 20 * 90, sqrt_fe = 254 * S + 13 * M + 2 * S + M, inv_sc = 20 * 90;
     const double oncurve = 2 * S + M;
     const double table = (DSM_TS / 2) * dbl + (DSM_TS / 2 - 1) * mix;
-    const double ladder = (DSM_ND - 1) * DSM_W * dbl + 2 * DSM_ND * add + DSM_ND * M;
+    const double adds_per_half = (DSM_ND - 1) * (1.0 - 1.0 / (1 << DSM_W)) + 7.0 / 8.0;
+    const double ladder = (DSM_ND - 1) * DSM_W * dbl + 2 * adds_per_half * add + adds_per_half * M;
     const double comb = COMB_NW * mix;
     const double dsm = table + ladder + comb;
     const double split = 3 * ZN + 2 * 64;
@@ -1143,13 +1208,14 @@ extern "C" double s256_mac32_per_item(const char *name) {
     if (s == "ecdsa_recover") return sqrt_fe + (6 * ZN + inv_sc / INV_K + split) + dsm + affine;
     if (s == "schnorr_verify") return sqrt_fe + (ZN + split) + dsm + affine;
     if (s == "double_scalar_mult_basepoint_vartime") return oncurve + split + dsm + affine;
-    if (s == "scalar_base_mult") return CT_NW * mix + affine;
-    if (s == "schnorr_sign") return 2 * (CT_NW * mix + affine) + 2 * ZN;  // + ~9 SHA-256 blocks
-    if (s == "ecdsa_sign_rfc6979") return CT_NW * mix + affine + (5 * ZN + inv_sc / INV_K);  // + 22 SHA-256 blocks
+    if (s == "scalar_base_mult") return CT_NW * mix_ct + affine;
+    if (s == "schnorr_sign") return 2 * (CT_NW * mix_ct + affine) + 2 * ZN;  // + ~9 SHA-256 blocks
+    if (s == "ecdsa_sign_rfc6979") return CT_NW * mix_ct + affine + (5 * ZN + inv_sc / INV_K);  // + 22 SHA-256 blocks
     if (s == "scalar_mult" || s == "ecdh") {
-        const double tab = (CTM_TS / 2) * dbl + (CTM_TS / 2 - 1) * mix + 5 * (CTM_TS - 1) * M + inv_fe;  // + normalisation
-        const double lad = (CTM_ND - 1) * CTM_W * dbl + 2 * CTM_ND * mix + CTM_ND * M;
+        const double tab = (CTM_TS / 2) * dbl_ct + (CTM_TS / 2 - 1) * mix_ct + 5 * (CTM_TS - 1) * M + inv_fe;  // + normalisation
+        const double lad = (CTM_ND - 1) * CTM_W * dbl_ct + 2 * CTM_ND * mix_ct + CTM_ND * M;
         return oncurve + split + tab + lad + affine;
     }
+    if (s == "msm_mixed_add") return mix;  // one bucket accumulation step of the Pippenger MSM (k_msm_slices)
     return 0.0;
 }

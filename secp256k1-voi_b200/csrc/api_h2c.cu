@@ -50,6 +50,7 @@ static int ensure_msg_staging(s256_ctx *ctx, size_t msg_len, size_t n) {
 extern "C" int s256_hash_to_curve(s256_ctx *ctx, const uint8_t *dst, size_t dst_len, const uint8_t *msg, size_t msg_len,
                                   size_t n, int random_oracle, uint8_t *out65, uint8_t *status) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (n && ((!msg && msg_len) || !out65 || !status)) return S256_ERR_ARG;
     uint8_t dbuf[H2C_MAX_DST];
     int dl = 0;
@@ -75,6 +76,7 @@ extern "C" int s256_hash_to_curve(s256_ctx *ctx, const uint8_t *dst, size_t dst_
 extern "C" int s256_expand_message_xmd(s256_ctx *ctx, const uint8_t *dst, size_t dst_len, const uint8_t *msg,
                                        size_t msg_len, size_t n, size_t len_in_bytes, uint8_t *out) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (n && ((!msg && msg_len) || !out)) return S256_ERR_ARG;
     if (len_in_bytes == 0 || len_in_bytes > 96) return S256_ERR_ARG;  // the suites here need 48 or 96
     uint8_t dbuf[H2C_MAX_DST];

@@ -3,6 +3,8 @@
 #include "msm.cuh"
 #include "coop.cuh"
 #include <cub/device/device_scan.cuh>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is resolved at run time (no link-time dependency on NCCL)
 
 // ---- Pippenger MSM (msm.cuh) -------------------------------------------------
 template <bool SCATTER>
@@ -381,6 +383,7 @@ static int msm_finish(s256_ctx *ctx, uint8_t *out65, uint8_t *status) {
 extern "C" int s256_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, uint8_t *out65,
                         uint8_t *status) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (!out65 || !status || (n && (!k32 || !pt65))) return S256_ERR_ARG;
     uint32_t invalid = 0;
     int rc = msm_run(ctx, k32, pt65, n, vartime, &invalid);
@@ -395,6 +398,7 @@ extern "C" int s256_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, 
 extern "C" int s256_msm_partial(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime,
                                 uint8_t *partial96, uint8_t *status) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (!partial96 || !status || (n && (!k32 || !pt65))) return S256_ERR_ARG;
     uint32_t invalid = 0;
     int rc = msm_run(ctx, k32, pt65, n, vartime, &invalid);
@@ -414,6 +418,7 @@ extern "C" int s256_msm_partial(s256_ctx *ctx, const uint8_t *k32, const uint8_t
 }
 extern "C" int s256_msm_combine(s256_ctx *ctx, const uint8_t *partials96, size_t m, uint8_t *out65, uint8_t *status) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (!out65 || !status || (m && !partials96)) return S256_ERR_ARG;
     if (96 * m > 65 * ctx->cap) return S256_ERR_ARG;
     int rc = msm_ensure(ctx);
@@ -434,3 +439,231 @@ extern "C" int s256_msm_combine(s256_ctx *ctx, const uint8_t *partials96, size_t
     return msm_finish(ctx, out65, status);
 }
 
+
+
+// ---------------------------------------------------------------------------
+// Device-resident and multi-GPU MSM.
+//
+// s256_msm_dev: inputs and outputs in HBM, everything enqueued on the caller's stream, no host synchronisation.
+//
+// s256_msm_sharded[_dev]: config 5 of BASELINE.json.  One process per GPU; rank g passes ITS contiguous slice of the
+// batch.  Each rank reduces its slice to a projective partial (Pippenger), ONE ncclAllGather of 112 bytes per rank
+// brings the partials together on every GPU, one warp folds them (8-lane cooperative additions) and the shared
+// batched-affine kernel encodes the sum.  The partials never leave the device; the host-pointer form synchronises once,
+// to read 66 bytes.  NCCL is resolved with dlopen at the first s256_comm_* call: in a process that already uses NCCL
+// (torch.distributed) that is the copy already loaded, otherwise libnccl.so.2 from the loader path; a context that
+// never shards never touches it.  The communicator is built from an ncclUniqueId that rank 0 obtains with
+// s256_comm_unique_id and the application hands to the other ranks (any channel: MPI, torch.distributed, a file).
+// ---------------------------------------------------------------------------
+namespace {
+struct nccl_api {
+    void *h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+nccl_api &nccl() {
+    static nccl_api api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the copy the process already uses, if any
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return;
+        api.h = h;
+        api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+        api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+        api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(h, "ncclAllGather"));
+        api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+    });
+    return api;
+}
+#define NCCLCK(call)                                                                             \
+    do {                                                                                         \
+        ncclResult_t r_ = (call);                                                                \
+        if (r_ != ncclSuccess) {                                                                 \
+            ctx->last_err = std::string(#call) + ": " + nccl().GetErrorString(r_);               \
+            return S256_ERR_NCCL;                                                                \
+        }                                                                                        \
+    } while (0)
+
+// what one rank contributes to the gather: its projective partial in limb form and its "a point failed to decode" flag
+struct msm_wire {
+    pt p;
+    uint32_t invalid, pad[3];
+};
+static_assert(sizeof(msm_wire) == 112, "wire format");
+}  // namespace
+
+__global__ void k_msm_pack(const pt *acc, const uint32_t *flag, msm_wire *out) {
+    if (threadIdx.x == 0) {
+        out->p = *acc;
+        out->invalid = *flag;
+        out->pad[0] = out->pad[1] = out->pad[2] = 0;
+    }
+}
+// acc = sum of the m gathered partials (one warp, 8-lane cooperative additions); flag |= any rank's flag
+__global__ void __launch_bounds__(32) k_msm_fold_wire(const msm_wire *in, int m, pt *acc, uint32_t *flag) {
+    int j = threadIdx.x & 7;
+    pt r;
+    pt_set_identity(r);
+    uint32_t bad = 0;
+    for (int g = 0; g < m; g++) {
+        pt q = in[g].p;
+        bad |= in[g].invalid;
+        pt_add_coop(r, q, j);
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        *acc = r;
+        if (bad) atomicOr(flag, 1u);
+    }
+}
+// after the encode: a failed decode anywhere turns the result into (all zero, S256_ST_INVALID), on the device
+__global__ void k_msm_publish(const uint32_t *flag, uint8_t *out65, uint8_t *status) {
+    if (*flag) {
+        for (int i = threadIdx.x; i < 65; i += blockDim.x) out65[i] = 0;
+        if (threadIdx.x == 0) *status = S256_ST_INVALID;
+    }
+}
+
+// device pointers, any n: msm_acc / msm_flag hold the local sum afterwards (nothing synchronised)
+static int msm_run_dev(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, cudaStream_t s) {
+    int rc = msm_ensure(ctx);
+    if (rc != S256_SUCCESS) return rc;
+    CK(cudaMemsetAsync(ctx->msm_flag, 0, 4, s));
+    if (n == 0) {
+        static const pt id = [] { pt p; pt_set_identity(p); return p; }();
+        CK(cudaMemcpyAsync(ctx->msm_acc, &id, sizeof(pt), cudaMemcpyHostToDevice, s));
+    }
+    int first = 1;
+    return for_chunks(ctx, n, [&](size_t off, size_t c) {
+        int r = chunk_msm(ctx, k32 + 32 * off, pt65 + 65 * off, c, vartime, first, s);
+        first = 0;
+        return r;
+    });
+}
+// msm_acc -> out65 / status (device pointers), flag honoured, nothing synchronised
+static int msm_finish_dev(s256_ctx *ctx, uint8_t *out65, uint8_t *status, cudaStream_t s) {
+    s256_launch_finish_affine(ctx, 1, ctx->msm_acc, nullptr, nullptr, ctx->cstat, 0, out65, status, nullptr, s);
+    k_msm_publish<<<1, 96, 0, s>>>(ctx->msm_flag, out65, status);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
+    return check_launch(ctx);
+}
+extern "C" int s256_msm_dev(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int vartime, uint8_t *out65,
+                            uint8_t *status, void *stream) {
+    ENTER(ctx);
+    if (!out65 || !status || (n && (!k32 || !pt65))) return S256_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    scratch_guard sg_(ctx, s, false);
+    int rc = msm_run_dev(ctx, k32, pt65, n, vartime, s);
+    if (rc != S256_SUCCESS) return rc;
+    return msm_finish_dev(ctx, out65, status, s);
+}
+
+// the Pippenger plan for n points on one GPU (window bits, windows): what bench.py's work model needs
+extern "C" int s256_msm_plan(size_t n, int *window_bits, int *windows) {
+    if (!window_bits || !windows) return S256_ERR_ARG;
+    msm_plan pl = msm_make_plan(n);
+    *window_bits = pl.c;
+    *windows = pl.nwin;
+    return S256_SUCCESS;
+}
+extern "C" int s256_comm_unique_id(uint8_t id128[128]) {
+    if (!id128) return S256_ERR_ARG;
+    if (!nccl().ok) return S256_ERR_NCCL;
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId");
+    if (nccl().GetUniqueId(&id) != ncclSuccess) return S256_ERR_NCCL;
+    memcpy(id128, &id, 128);
+    return S256_SUCCESS;
+}
+extern "C" int s256_comm_init(s256_ctx *ctx, const uint8_t id128[128], int rank, int nranks) {
+    ENTER(ctx);
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks || nranks > S256_COMM_MAX_RANKS) return S256_ERR_ARG;
+    if (!nccl().ok) {
+        ctx->last_err = "libnccl.so.2 not found (dlopen)";
+        return S256_ERR_NCCL;
+    }
+    if (ctx->comm) {
+        nccl().CommDestroy((ncclComm_t)ctx->comm);
+        ctx->comm = nullptr;
+    }
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclComm_t comm = nullptr;
+    NCCLCK(nccl().CommInitRank(&comm, nranks, id, rank));
+    ctx->comm = comm;
+    ctx->comm_rank = rank;
+    ctx->comm_size = nranks;
+    if (!ctx->comm_buf) CK(cudaMalloc(&ctx->comm_buf, sizeof(msm_wire) * (S256_COMM_MAX_RANKS + 1)));
+    return S256_SUCCESS;
+}
+void s256_internal_comm_release(s256_ctx *ctx) {
+    if (ctx->comm && nccl().ok) nccl().CommDestroy((ncclComm_t)ctx->comm);
+    ctx->comm = nullptr;
+    ctx->comm_size = 0;
+}
+extern "C" int s256_comm_free(s256_ctx *ctx) {
+    ENTER(ctx);
+    s256_internal_comm_release(ctx);
+    return S256_SUCCESS;
+}
+// local partial (already in msm_acc / msm_flag) -> gathered and folded on every rank
+static int msm_exchange(s256_ctx *ctx, cudaStream_t s) {
+    if (!ctx->comm) return S256_SUCCESS;  // no communicator: the partial is the sum
+    msm_wire *send = reinterpret_cast<msm_wire *>(ctx->comm_buf), *recv = send + 1;
+    k_msm_pack<<<1, 32, 0, s>>>(ctx->msm_acc, ctx->msm_flag, send);
+    NCCLCK(nccl().AllGather(send, recv, sizeof(msm_wire), ncclUint8, (ncclComm_t)ctx->comm, s));
+    k_msm_fold_wire<<<1, 32, 0, s>>>(recv, ctx->comm_size, ctx->msm_acc, ctx->msm_flag);
+    ctx->launches.fetch_add(2, std::memory_order_relaxed);
+    return S256_SUCCESS;
+}
+extern "C" int s256_msm_sharded_dev(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n_local, int vartime,
+                                    uint8_t *out65, uint8_t *status, void *stream) {
+    ENTER(ctx);
+    if (!out65 || !status || (n_local && (!k32 || !pt65))) return S256_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    scratch_guard sg_(ctx, s, false);
+    int rc = msm_run_dev(ctx, k32, pt65, n_local, vartime, s);
+    if (rc != S256_SUCCESS) return rc;
+    rc = msm_exchange(ctx, s);
+    if (rc != S256_SUCCESS) return rc;
+    return msm_finish_dev(ctx, out65, status, s);
+}
+extern "C" int s256_msm_sharded(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n_local, int vartime,
+                                uint8_t *out65, uint8_t *status) {
+    ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
+    if (!out65 || !status || (n_local && (!k32 || !pt65))) return S256_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    int rc = msm_ensure(ctx);
+    if (rc != S256_SUCCESS) return rc;
+    CK(cudaMemsetAsync(ctx->msm_flag, 0, 4, s));
+    if (n_local == 0) {
+        static const pt id = [] { pt p; pt_set_identity(p); return p; }();
+        CK(cudaMemcpyAsync(ctx->msm_acc, &id, sizeof(pt), cudaMemcpyHostToDevice, s));
+    }
+    int first = 1;
+    rc = for_chunks(ctx, n_local, [&](size_t off, size_t c) {
+        CK(cudaMemcpyAsync(ctx->in_a, pt65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->in_b, k32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
+        int r = chunk_msm(ctx, ctx->in_b, ctx->in_a, c, vartime, first, s);
+        first = 0;
+        return r;
+    });
+    if (rc != S256_SUCCESS) return rc;
+    rc = msm_exchange(ctx, s);
+    if (rc != S256_SUCCESS) return rc;
+    rc = msm_finish_dev(ctx, ctx->out, ctx->st, s);
+    if (rc != S256_SUCCESS) return rc;
+    CK(cudaMemcpyAsync(out65, ctx->out, 65, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(status, ctx->st, 1, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));  // the one host synchronisation of the call
+    return check_launch(ctx);
+}

@@ -78,6 +78,7 @@ extern "C" int s256_ecdsa_sign_rfc6979_dev(s256_ctx *ctx, const uint8_t *priv32,
     ENTER(ctx);
     if (n && (!priv32 || !digest32 || !sig64 || !recid || !status)) return S256_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    scratch_guard sg_(ctx, s, false);
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
         return chunk_sign(ctx, view_at(ctx, 0), priv32 + 32 * off, digest32 + 32 * off, c, sig64 + 64 * off, recid + off,
                           status + off, s);
@@ -87,6 +88,7 @@ extern "C" int s256_ecdsa_sign_rfc6979_dev(s256_ctx *ctx, const uint8_t *priv32,
 extern "C" int s256_ecdsa_sign_rfc6979(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *digest32, size_t n,
                                        uint8_t *sig64, uint8_t *recid, uint8_t *status) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (n && (!priv32 || !digest32 || !sig64 || !recid || !status)) return S256_ERR_ARG;
     int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t s) {
         CK(cudaMemcpyAsync(v.in_a, priv32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, s));
@@ -109,6 +111,7 @@ extern "C" int s256_schnorr_sign_dev(s256_ctx *ctx, const uint8_t *priv32, const
     ENTER(ctx);
     if (n && (!priv32 || (!msg && msg_len) || !aux32 || !sig64 || !status)) return S256_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    scratch_guard sg_(ctx, s, false);
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
         return chunk_schnorr_sign(ctx, view_at(ctx, 0), priv32 + 32 * off, msg + msg_len * off, msg_len, aux32 + 32 * off,
                                   c, sig64 + 64 * off, status + off, s);
@@ -118,6 +121,7 @@ extern "C" int s256_schnorr_sign_dev(s256_ctx *ctx, const uint8_t *priv32, const
 extern "C" int s256_schnorr_sign(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *msg, size_t msg_len,
                                  const uint8_t *aux32, size_t n, uint8_t *sig64, uint8_t *status) {
     ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
     if (n && (!priv32 || (!msg && msg_len) || !aux32 || !sig64 || !status)) return S256_ERR_ARG;
     size_t need = (msg_len ? msg_len : 1) * (n < ctx->cap ? n : ctx->cap);
     if (need > ctx->in_b_bytes) {

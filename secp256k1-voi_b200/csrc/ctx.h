@@ -58,8 +58,15 @@ struct s256_ctx {
     // pay -- the batched-inversion kernel is latency bound, so its cost multiplies with the part count.
     int pipe_parts = 1;
     cudaEvent_t ev_decode = nullptr, ev_pipe[10] = {};
+    // recorded when a call has enqueued its last work; the next call's streams wait on it (scratch_guard below)
+    cudaEvent_t ev_idle = nullptr;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> dsm_events;
+    // multi-GPU MSM (api_msm.cu): an ncclComm_t built by s256_comm_init, and the 112-byte rows of the gather
+    void *comm = nullptr;
+    int comm_rank = 0, comm_size = 0;
+    void *comm_buf = nullptr;
 };
+#define S256_COMM_MAX_RANKS 72
 
 #define CK(call)                                                                     \
     do {                                                                             \
@@ -224,9 +231,33 @@ static inline int check_launch(s256_ctx *ctx) {
     dev_guard dg_((ctx)->device)
 
 
+// Device-side ordering between calls.  Every entry point works in the one per-context scratch, and a *_dev call returns
+// as soon as its kernels are enqueued on the CALLER's stream; the mutex (ENTER) only orders the enqueueing.  Without more,
+// a second call on another stream -- or a host-pointer call on the context's own streams -- could overwrite scratch the
+// first one is still using (verdicts silently wrong; in the signing path the nonce k shares a buffer with u1, so a clash
+// between k*G and the finishing kernel would sign with a different k than the one behind r and leak the key).  So the
+// streams a call uses first wait on ev_idle, and the call records ev_idle on its stream when it is done enqueueing.
+// (Waiting on an event that was never recorded is a no-op.)
+struct scratch_guard {
+    s256_ctx *c;
+    cudaStream_t s;
+    scratch_guard(s256_ctx *c_, cudaStream_t s_, bool internal_streams) : c(c_), s(s_) {
+        cudaStreamWaitEvent(s, c->ev_idle, 0);
+        if (internal_streams) {
+            if (c->stream != s) cudaStreamWaitEvent(c->stream, c->ev_idle, 0);
+            cudaStreamWaitEvent(c->stream2, c->ev_idle, 0);
+            cudaStreamWaitEvent(c->stream3, c->ev_idle, 0);
+        }
+    }
+    ~scratch_guard() { cudaEventRecord(c->ev_idle, s); }
+    scratch_guard(const scratch_guard &) = delete;
+    scratch_guard &operator=(const scratch_guard &) = delete;
+};
+
 // launchers of kernels that live in api.cu but are needed by the other units
 void s256_launch_decode_uncompressed(s256_ctx *ctx, const uint8_t *pt65, size_t n, apt *aff, uint8_t *pvalid, cudaStream_t s);
 void s256_launch_finish_affine(s256_ctx *ctx, size_t n, const pt *res, const uint8_t *pvalid, const uint8_t *sfl,
                                uint8_t *cstat, int mode, uint8_t *out, uint8_t *status, const uint8_t *sig64,
                                cudaStream_t s);
+void s256_internal_comm_release(s256_ctx *ctx);  // api_msm.cu: destroys the NCCL communicator, if any
 void s256_launch_scalar_mult_ct(size_t n, const apt *aff, const uint8_t *k32, pt *tbl, pt *res, cudaStream_t s);

@@ -38,9 +38,30 @@ def gather_bytes(local_row, group=None, device=None):
     return out.cpu().numpy().reshape(world, -1)
 
 
+def init_comm(engine, group=None):
+    """Builds the engine's own NCCL communicator (s256_comm_init) over the ranks of `group`: rank 0 draws the
+    ncclUniqueId, torch.distributed carries its 128 bytes to the others (the one thing the application has to do),
+    every rank joins.  Afterwards engine.msm_sharded runs the gather INSIDE the C ABI."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(engine.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    engine.comm_init(bytes(t.cpu().numpy().tobytes()), rank, world)
+
+
 def msm_sharded(engine, k32_local, pt65_local, vartime=True, group=None, device=None):
     """Point.MultiScalarMult over a batch sharded across ranks: each rank passes ITS slice.
-    Returns (out65, status) on every rank.  Invalid points anywhere poison the result."""
+    Returns (out65, status) on every rank.  Invalid points anywhere poison the result.
+    An engine with a communicator (init_comm) does everything behind the C ABI (s256_msm_sharded: the partials stay on
+    the device, one NCCL all-gather).  Without one -- the gloo tests on CPU, where NCCL does not exist -- the partials
+    travel through torch.distributed as 97-byte rows and are folded with msm_combine."""
+    if getattr(engine, "comm_size", 0) >= 1:
+        return engine.msm_sharded(k32_local, pt65_local, vartime=vartime)
     part, st = engine.msm_partial(k32_local, pt65_local, vartime=vartime)
     row = np.concatenate([np.asarray(part, np.uint8).reshape(96), np.array([st], np.uint8)])
     rows = gather_bytes(row, group=group, device=device)

@@ -161,6 +161,169 @@ def test_full_size_properties(engine):
     assert int(a.sum()) == n - n // 16
 
 
+def _sample_indices(n, expected, count=1 << 14):
+    """Every corrupted item plus `count` valid ones spread over the batch."""
+    bad = np.nonzero(np.asarray(expected) == 0)[0]
+    good = np.nonzero(np.asarray(expected) == 1)[0]
+    good = good[:: max(1, len(good) // count)][:count]
+    return np.sort(np.concatenate([bad, good]))
+
+
+def _checked_base_mult(engine, oracle, sample_of):
+    """base_mult callable for synth.*_batch: the engine computes all n multiples, the ORACLE recomputes the ones at
+    `sample_of(n)` (so that the sampled inputs do not depend on the product), and both must agree there."""
+    def f(k32):
+        out, st = engine.scalar_base_mult(k32)
+        out, st = np.array(out, np.uint8), np.array(st, np.uint8)
+        idx = sample_of(len(out))
+        eo, es = oracle.batch_scalar_base_mult(np.ascontiguousarray(k32[idx]))
+        assert np.array_equal(out[idx], eo) and np.array_equal(st[idx], es)
+        out[idx], st[idx] = eo, es
+        return out, st
+    return f
+
+
+def _spread(count):
+    # the corruption cycle hits i % 16 == 15; this stride also lands on every residue mod 16
+    return lambda n: np.unique(np.concatenate([np.arange(15, n, 16), np.arange(0, n, max(1, n // count))]))
+
+
+def test_full_size_ecdsa_oracle_sampled(engine, oracle):
+    """Config 2 at 2^20 as SURVEY.md 8(d) specifies it: all 65 536 corrupted items and 2^14 valid ones go through the
+    oracle (multi-threaded), with keys and nonce points for those items taken from the oracle's own base mult."""
+    n = 1 << 20
+    w = ps.synth.ecdsa_batch(n, _checked_base_mult(engine, oracle, _spread(1 << 14)))
+    got = engine.ecdsa_verify(w["pk65"], w["digest32"], w["sig64"])
+    assert np.array_equal(got, w["expected"])
+    idx = _sample_indices(n, w["expected"])
+    assert len(idx) >= (1 << 16) + (1 << 14) - 16
+    exp = oracle.batch_ecdsa_verify(np.ascontiguousarray(w["pk65"][idx]), np.ascontiguousarray(w["digest32"][idx]),
+                                    np.ascontiguousarray(w["sig64"][idx]))
+    assert np.array_equal(got[idx], exp)
+
+
+def test_full_size_schnorr_oracle_sampled(engine, oracle):
+    """Config 3 at 2^20 (BIP-340 incl. lift_x): by construction on everything, the oracle on all corrupted + 2^14 valid."""
+    n = 1 << 20
+    w = ps.synth.schnorr_batch(n, _checked_base_mult(engine, oracle, _spread(1 << 14)))
+    got = engine.schnorr_verify(w["pkx32"], w["msg"], w["sig64"])
+    assert np.array_equal(got, w["expected"])
+    idx = _sample_indices(n, w["expected"])
+    exp = oracle.batch_schnorr_verify(np.ascontiguousarray(w["pkx32"][idx]), np.ascontiguousarray(w["msg"][idx]),
+                                      np.ascontiguousarray(w["sig64"][idx]))
+    assert np.array_equal(got[idx], exp)
+
+
+def test_full_size_ecdh_oracle_sampled(engine, oracle):
+    """Config 4 at 2^20 (constant-time GLV ScalarMult / ECDH): the closed form (k d) G on everything, the oracle's own
+    ScalarMult on 2^14 items."""
+    n = 1 << 20
+    w = ps.synth.ecdh_batch(n, _checked_base_mult(engine, oracle, _spread(1 << 14)))
+    x, st = engine.ecdh(w["k32"], w["pt65"])
+    full, fst = engine.scalar_mult(w["k32"], w["pt65"])
+    exp, est = engine.scalar_base_mult(w["closed_form_scalar"])
+    assert (np.asarray(st) == 1).all() and (np.asarray(fst) == 1).all()
+    assert np.array_equal(full, exp) and np.array_equal(x, np.asarray(exp)[:, 1:33])
+    idx = np.arange(0, n, n >> 14)
+    ox, ost = oracle.batch_ecdh(np.ascontiguousarray(w["k32"][idx]), np.ascontiguousarray(w["pt65"][idx]))
+    assert np.array_equal(np.asarray(x)[idx], ox) and (ost == 1).all()
+    of, ofst = oracle.batch_scalar_mult(np.ascontiguousarray(w["k32"][idx[:2048]]), np.ascontiguousarray(w["pt65"][idx[:2048]]))
+    assert np.array_equal(np.asarray(full)[idx[:2048]], of)
+
+
+def test_full_size_msm(engine, oracle):
+    """Config 5 at 2^20 on one GPU: the closed form (sum s_i d_i) G for the whole product, the oracle's Straus on a
+    2^12 prefix, the sharded shape (8 partials -> combine) and the constant-time flavour at n = 4096."""
+    n = 1 << 20
+    w = ps.synth.msm_batch(n, _checked_base_mult(engine, oracle, lambda m: np.arange(0, m, max(1, m >> 12))))
+    got, st = engine.msm(w["k32"], w["pt65"])
+    exp, est = oracle.scalar_base_mult(w["closed_form_scalar"])
+    assert st == est and got.tobytes() == exp
+    m = 1 << 12
+    got, st = engine.msm(w["k32"][:m], w["pt65"][:m])
+    exp, est = oracle.msm(w["k32"][:m].tobytes(), w["pt65"][:m].tobytes())
+    assert (st, got.tobytes()) == (est, exp)
+    got, st = engine.msm(w["k32"][:m], w["pt65"][:m], vartime=False)
+    assert (st, got.tobytes()) == (est, exp)
+    per = n // 8
+    parts = []
+    for g in range(8):
+        p, pst = engine.msm_partial(w["k32"][g * per:(g + 1) * per], w["pt65"][g * per:(g + 1) * per])
+        assert pst == 1
+        parts.append(p)
+    got, st = engine.msm_combine(np.stack(parts))
+    exp, est = oracle.scalar_base_mult(w["closed_form_scalar"])
+    assert st == est and got.tobytes() == exp
+
+
+def test_msm_device_resident_and_sharded_entry_points(s256, oracle):
+    """s256_msm_dev (inputs and result in HBM, no host sync) and s256_msm_sharded[_dev] against the host-pointer MSM and
+    the oracle; the sharded forms run here with a communicator of ONE rank, which still goes through the library's
+    pack -> ncclAllGather -> fold path (two ranks need two GPUs: tests/test_multi_gpu.py)."""
+    eng = s256.Engine(device=0, max_batch=1 << 16)
+    try:
+        w = ps.synth.msm_batch(5000, ps.oracle_base_mult(oracle))
+        exp, est = oracle.msm(w["k32"].tobytes(), w["pt65"].tobytes())
+        dk, dp = torch_cuda(w["k32"]), torch_cuda(w["pt65"])
+        for vt in (True, False):
+            if not vt:
+                dk, dp = dk[:64].contiguous(), dp[:64].contiguous()
+                exp, est = oracle.msm(w["k32"][:64].tobytes(), w["pt65"][:64].tobytes(), vartime=False)
+            out, st = eng.msm(dk, dp, vartime=vt)
+            assert int(st.cpu()[0]) == est and out.cpu().numpy().tobytes() == exp
+        # more items than the context's capacity: chunks accumulate on the device
+        big = ps.synth.msm_batch((1 << 16) + 777, eng.scalar_base_mult)
+        e2, s2 = oracle.scalar_base_mult(big["closed_form_scalar"])
+        out, st = eng.msm(torch_cuda(big["k32"]), torch_cuda(big["pt65"]))
+        assert int(st.cpu()[0]) == s2 and out.cpu().numpy().tobytes() == e2
+        # an undecodable point poisons the result on the device too
+        bad = w["pt65"].copy(); bad[9, 64] ^= 1
+        out, st = eng.msm(torch_cuda(w["k32"]), torch_cuda(bad))
+        assert int(st.cpu()[0]) == 0 and not out.cpu().numpy().any()
+        out, st = eng.msm(torch_cuda(w["k32"][:0]), torch_cuda(w["pt65"][:0]))
+        assert int(st.cpu()[0]) == 2 and not out.cpu().numpy().any()
+        # sharded entry points: no communicator = plain MSM; then a one-rank communicator through NCCL
+        exp, est = oracle.msm(w["k32"].tobytes(), w["pt65"].tobytes())
+        out, st = eng.msm_sharded(w["k32"], w["pt65"])
+        assert (st, out.tobytes()) == (est, exp)
+        eng.comm_init(s256.Engine.comm_unique_id(), 0, 1)
+        out, st = eng.msm_sharded(w["k32"], w["pt65"])
+        assert (st, out.tobytes()) == (est, exp)
+        out, st = eng.msm_sharded(torch_cuda(w["k32"]), torch_cuda(w["pt65"]))
+        assert int(st.cpu()[0]) == est and out.cpu().numpy().tobytes() == exp
+        out, st = eng.msm_sharded(w["k32"], bad)
+        assert st == 0 and not out.any()
+        eng.comm_free()
+    finally:
+        eng.close()
+
+
+def test_calls_on_different_streams_are_ordered_on_the_device(engine):
+    """A *_dev call returns once its kernels are enqueued; the next call (another stream, or a host-pointer call) works in
+    the same per-context scratch.  The library orders them on the device (ctx.h scratch_guard); without that the first
+    call's ladder would read scalars and tables the second one is already overwriting."""
+    import torch
+    n = 1 << 17
+    wa = ps.synth.ecdsa_batch(n, engine.scalar_base_mult, start=0)
+    wb = ps.synth.ecdsa_batch(n, engine.scalar_base_mult, start=5 * n + 3, corrupt_every=7)
+    da = [torch_cuda(wa[k]) for k in ("pk65", "digest32", "sig64")]
+    db = [torch_cuda(wb[k]) for k in ("pk65", "digest32", "sig64")]
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        with torch.cuda.stream(sa):
+            oka = engine.ecdsa_verify(*da)
+        with torch.cuda.stream(sb):
+            okb = engine.ecdsa_verify(*db)
+        okc = engine.ecdsa_verify(wa["pk65"][:4096], wa["digest32"][:4096], wa["sig64"][:4096])   # host-pointer call
+        with torch.cuda.stream(sa):
+            pk, st = engine.scalar_base_mult(torch_cuda(ps.synth.base_mult_scalars(4096)))
+        torch.cuda.synchronize()
+        assert np.array_equal(oka.cpu().numpy(), wa["expected"])
+        assert np.array_equal(okb.cpu().numpy(), wb["expected"])
+        assert np.array_equal(okc, wa["expected"][:4096])
+
+
 def test_host_pipeline_chunk_shapes(s256):
     """The host-pointer verify path is a two-stage pipeline per chunk (api.cu verify_pipelined): exercise a
     chunk cut in 1/8 + 7/8, a second pipelined chunk of odd size, and a short tail chunk on the plain path."""
