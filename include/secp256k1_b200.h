@@ -157,7 +157,12 @@ int s256_bitcoin_verify_asn1(s256_ctx *ctx, const uint8_t *pk65, const uint8_t *
 /* --- PrivateKey.Sign with RFC6979SHA256() as the entropy source (secec/ecdsa.go:92-135,284-390;
  *     nonce: secec/ecdsa_k_rfc6979.go): deterministic, constant time.  priv32 must be a canonical
  *     non-zero scalar (NewPrivateKey, secec/secec.go:141).  Outputs: compact r||s (low-s normalised),
- *     the recovery id (0..3), status. */
+ *     the recovery id (0..3), status.
+ *     Two deliberate differences from the reference, neither observable on valid inputs: (1) a nonce that gives r = 0
+ *     or s = 0 (probability ~2^-256) is reported as S256_ST_INVALID where the reference draws the next DRBG output
+ *     (secec/ecdsa.go's loop); (2) the reference re-verifies a BIP-340 signature before returning it (schnorr.go:393)
+ *     and this library does not -- a caller that wants that fault check runs s256_schnorr_verify / s256_ecdsa_verify on
+ *     the batch it just signed (same context, ~2.5x the signing time). */
 int s256_ecdsa_sign_rfc6979(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *digest32, size_t n, uint8_t *sig64,
                             uint8_t *recid, uint8_t *status);
 int s256_ecdsa_sign_rfc6979_dev(s256_ctx *ctx, const uint8_t *d_priv32, const uint8_t *d_digest32, size_t n,

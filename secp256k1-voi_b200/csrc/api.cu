@@ -342,7 +342,7 @@ extern "C" void s256_free(s256_ctx *ctx) {
                         ctx->cstat, ctx->tbl,   ctx->res, ctx->in_a, ctx->in_b, ctx->in_c, ctx->out, ctx->st,
                         ctx->sink, ctx->msm_counts, ctx->msm_offsets, ctx->msm_cursor, ctx->msm_entries, ctx->msm_flag,
                         ctx->msm_buckets, ctx->msm_win, ctx->msm_acc, ctx->msm_tmp, ctx->msm_cub, ctx->msm_nsl, ctx->msm_sloff,
-                        ctx->msm_perm, ctx->msm_hist, ctx->msm_range, ctx->msm_part, ctx->msm_sbkt, ctx->comm_buf};
+                        ctx->msm_perm, ctx->msm_hist, ctx->msm_range, ctx->msm_part, ctx->msm_sbkt, ctx->comm_buf, ctx->msm_aff2, ctx->msm_half, ctx->msm_bsum};
         for (void *p : ptrs)
             if (p) cudaFree(p);
         if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -728,13 +728,7 @@ extern "C" int s256_schnorr_verify(s256_ctx *ctx, const uint8_t *pkx, const uint
     scratch_guard sg_(ctx, ctx->stream, true);
     if (n && (!pkx || (!msg && msg_len) || !sig || !ok)) return S256_ERR_ARG;
     size_t need = (msg_len ? msg_len : 1) * (n < ctx->cap ? n : ctx->cap);
-    if (need > ctx->in_b_bytes) {
-        if (ctx->in_b) cudaFree(ctx->in_b);
-        ctx->in_b = nullptr;
-        ctx->in_b_bytes = 0;
-        CK(cudaMalloc(&ctx->in_b, need));
-        ctx->in_b_bytes = need;
-    }
+    if (int grc = grow_in_b(ctx, need)) return grc;
     int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t ps) {
         uint8_t *dmsg = ctx->in_b + msg_len * (size_t)(v.st - ctx->st);  // messages are msg_len apart, not 32
         CK(cudaMemcpyAsync(v.in_a, pkx + 32 * off, 32 * c, cudaMemcpyHostToDevice, ps));
@@ -813,8 +807,11 @@ static int scalar_mult_common_dev(s256_ctx *ctx, const uint8_t *k32, const uint8
     scratch_guard sg_(ctx, s, false);
     size_t w = mode == 1 ? 32 : 65;
     int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
-        return chunk_scalar_mult(ctx, view_at(ctx, 0), k32 + 32 * off, pt65 + 65 * off, c, mode, out + w * off, status + off, s);
+        int r = chunk_scalar_mult(ctx, view_at(ctx, 0), k32 + 32 * off, pt65 + 65 * off, c, mode, out + w * off, status + off, s);
+        if (r == S256_SUCCESS) CK(cudaMemsetAsync(ctx->res, 0, sizeof(pt) * c, s));  // k*P in projective form
+        return r;
     });
+    if (rc != S256_SUCCESS) wipe_secret_scratch(ctx);
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
 static int scalar_mult_common_host(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, int mode,
@@ -830,8 +827,13 @@ static int scalar_mult_common_host(s256_ctx *ctx, const uint8_t *k32, const uint
         if (r != S256_SUCCESS) return r;
         CK(cudaMemcpyAsync(out + w * off, v.out, w * c, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(status + off, v.st, c, cudaMemcpyDeviceToHost, s));
+        // the staged private scalars, k*P in projective form and the shared x do not outlive the call
+        CK(cudaMemsetAsync(v.in_b, 0, 32 * c, s));
+        CK(cudaMemsetAsync(v.res, 0, sizeof(pt) * c, s));
+        CK(cudaMemsetAsync(v.out, 0, w * c, s));
         return S256_SUCCESS;
     });
+    if (rc != S256_SUCCESS) wipe_secret_scratch(ctx);
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
 extern "C" int s256_scalar_mult(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, size_t n, uint8_t *out65,
@@ -891,17 +893,22 @@ extern "C" int s256_new_public_keys(s256_ctx *ctx, const uint8_t *enc65, const u
 extern "C" int s256_parse_asn1_public_keys_checked(s256_ctx *ctx, const uint8_t *der, const size_t *offsets, size_t n,
                                                    uint8_t *out65, uint8_t *status) {
     if (!ctx || (n && (!der || !offsets || !out65 || !status))) return S256_ERR_ARG;
-    std::vector<uint8_t> enc(65 * n), len(n), pst(n);
-    int rc = s256_parse_asn1_public_keys(der, offsets, n, enc.data(), len.data(), pst.data());
-    if (rc != S256_SUCCESS) return rc;
-    rc = s256_new_public_keys(ctx, enc.data(), len.data(), n, out65, status);
-    if (rc != S256_SUCCESS) return rc;
-    for (size_t i = 0; i < n; i++)
-        if (pst[i] != S256_ST_OK) {
-            status[i] = pst[i];
-            memset(out65 + 65 * i, 0, 65);
-        }
-    return S256_SUCCESS;
+    if (n == 0) return S256_SUCCESS;
+    try {  // no exception may cross the C ABI (and cgo): a failed host allocation is an error code
+        std::vector<uint8_t> enc(65 * n), len(n), pst(n);
+        int rc = s256_parse_asn1_public_keys(der, offsets, n, enc.data(), len.data(), pst.data());
+        if (rc != S256_SUCCESS) return rc;
+        rc = s256_new_public_keys(ctx, enc.data(), len.data(), n, out65, status);
+        if (rc != S256_SUCCESS) return rc;
+        for (size_t i = 0; i < n; i++)
+            if (pst[i] != S256_ST_OK) {
+                status[i] = pst[i];
+                memset(out65 + 65 * i, 0, 65);
+            }
+        return S256_SUCCESS;
+    } catch (const std::bad_alloc &) {
+        return S256_ERR_NOMEM;
+    }
 }
 
 // PublicKey.Verify with EncodingASN1 (secec/ecdsa.go:171-228): parse on the host (codecs.cpp), then the
@@ -909,35 +916,45 @@ extern "C" int s256_parse_asn1_public_keys_checked(s256_ctx *ctx, const uint8_t 
 extern "C" int s256_ecdsa_verify_asn1(s256_ctx *ctx, const uint8_t *pk65, const uint8_t *digest32, const uint8_t *der,
                                       const size_t *offsets, uint32_t flags, size_t n, uint8_t *ok) {
     if (!ctx || (n && (!pk65 || !digest32 || !der || !offsets || !ok))) return S256_ERR_ARG;
-    std::vector<uint8_t> sig(64 * n), parsed(n);
-    int rc = s256_parse_asn1_signatures(der, offsets, n, sig.data(), parsed.data());
-    if (rc != S256_SUCCESS) return rc;
-    rc = s256_ecdsa_verify(ctx, pk65, digest32, sig.data(), flags, n, ok);
-    if (rc != S256_SUCCESS) return rc;
-    for (size_t i = 0; i < n; i++) ok[i] &= parsed[i];
-    return S256_SUCCESS;
+    if (n == 0) return S256_SUCCESS;
+    try {
+        std::vector<uint8_t> sig(64 * n), parsed(n);
+        int rc = s256_parse_asn1_signatures(der, offsets, n, sig.data(), parsed.data());
+        if (rc != S256_SUCCESS) return rc;
+        rc = s256_ecdsa_verify(ctx, pk65, digest32, sig.data(), flags, n, ok);
+        if (rc != S256_SUCCESS) return rc;
+        for (size_t i = 0; i < n; i++) ok[i] &= parsed[i];
+        return S256_SUCCESS;
+    } catch (const std::bad_alloc &) {
+        return S256_ERR_NOMEM;
+    }
 }
 // bitcoin.VerifyASN1 (secec/bitcoin/ecdsa_shitcoin.go:29-35)
 extern "C" int s256_bitcoin_verify_asn1(s256_ctx *ctx, const uint8_t *pk65, const uint8_t *digest32, const uint8_t *der,
                                         const size_t *offsets, size_t n, uint8_t *ok) {
     if (!ctx || (n && (!pk65 || !digest32 || !der || !offsets || !ok))) return S256_ERR_ARG;
-    std::vector<uint8_t> bip(n);
-    int rc = s256_is_valid_signature_encoding_bip0066(der, offsets, n, bip.data());
-    if (rc != S256_SUCCESS) return rc;
-    // strip the sighash byte of the rows that passed; rejected rows become empty (and fail to parse)
-    std::vector<size_t> off2(n + 1);
-    std::vector<uint8_t> der2;
-    der2.reserve(offsets[n] - offsets[0]);
-    for (size_t i = 0; i < n; i++) {
-        off2[i] = der2.size();
-        if (bip[i]) der2.insert(der2.end(), der + offsets[i], der + offsets[i + 1] - 1);
+    if (n == 0) return S256_SUCCESS;  // (offsets may be NULL then)
+    try {
+        std::vector<uint8_t> bip(n);
+        int rc = s256_is_valid_signature_encoding_bip0066(der, offsets, n, bip.data());
+        if (rc != S256_SUCCESS) return rc;
+        // strip the sighash byte of the rows that passed; rejected rows become empty (and fail to parse)
+        std::vector<size_t> off2(n + 1);
+        std::vector<uint8_t> der2;
+        der2.reserve(offsets[n] - offsets[0]);
+        for (size_t i = 0; i < n; i++) {
+            off2[i] = der2.size();
+            if (bip[i]) der2.insert(der2.end(), der + offsets[i], der + offsets[i + 1] - 1);
+        }
+        off2[n] = der2.size();
+        if (der2.empty()) der2.push_back(0);
+        rc = s256_ecdsa_verify_asn1(ctx, pk65, digest32, der2.data(), off2.data(), S256_FLAG_REJECT_MALLEABLE, n, ok);
+        if (rc != S256_SUCCESS) return rc;
+        for (size_t i = 0; i < n; i++) ok[i] &= bip[i];
+        return S256_SUCCESS;
+    } catch (const std::bad_alloc &) {
+        return S256_ERR_NOMEM;
     }
-    off2[n] = der2.size();
-    if (der2.empty()) der2.push_back(0);
-    rc = s256_ecdsa_verify_asn1(ctx, pk65, digest32, der2.data(), off2.data(), S256_FLAG_REJECT_MALLEABLE, n, ok);
-    if (rc != S256_SUCCESS) return rc;
-    for (size_t i = 0; i < n; i++) ok[i] &= bip[i];
-    return S256_SUCCESS;
 }
 
 // ---------------------------------------------------------------------------

@@ -37,13 +37,7 @@ static int prepare_dst(const uint8_t *dst, size_t dst_len, uint8_t buf[H2C_MAX_D
 // grows the message staging buffer (ctx->in_b) like the Schnorr entry points do
 static int ensure_msg_staging(s256_ctx *ctx, size_t msg_len, size_t n) {
     size_t need = (msg_len ? msg_len : 1) * (n < ctx->cap ? n : ctx->cap);
-    if (need > ctx->in_b_bytes) {
-        if (ctx->in_b) cudaFree(ctx->in_b);
-        ctx->in_b = nullptr;
-        ctx->in_b_bytes = 0;
-        CK(cudaMalloc(&ctx->in_b, need));
-        ctx->in_b_bytes = need;
-    }
+    if (int grc = grow_in_b(ctx, need)) return grc;
     return S256_SUCCESS;
 }
 

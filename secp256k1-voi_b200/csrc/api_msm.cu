@@ -7,32 +7,54 @@
 #include <nccl.h>  // types only: the library is resolved at run time (no link-time dependency on NCCL)
 
 // ---- Pippenger MSM (msm.cuh) -------------------------------------------------
-template <bool SCATTER>
-__global__ void __launch_bounds__(S256_TPB) k_msm_digits(const uint8_t *k32, size_t n, msm_plan plan, uint32_t *counts,
-                                                         uint32_t *cursor, uint32_t *entries) {
+// Pass 1, one thread per point: split the scalar with the endomorphism (once: the halves are kept for pass 2), write the
+// two virtual points (x, y), (beta x, y), count the digits of both halves into their buckets.
+__global__ void __launch_bounds__(S256_TPB) k_msm_prepare(const uint8_t *k32, const apt *aff, size_t n, msm_plan plan,
+                                                          uint4 *half, uint8_t *hsign, apt *aff2, uint32_t *counts) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    sc k;
+    sc k, m[2];
     sc_from_be32(k, k32 + 32 * i);
+    uint32_t neg[2];
+    msm_glv_halves(m[0], neg[0], m[1], neg[1], k);
+    half[2 * i] = make_uint4(m[0].v[0], m[0].v[1], m[0].v[2], m[0].v[3]);
+    half[2 * i + 1] = make_uint4(m[1].v[0], m[1].v[1], m[1].v[2], m[1].v[3]);
+    hsign[i] = (uint8_t)(neg[0] | (neg[1] << 1));
+    apt p = aff[i], p0, p1;
+    msm_glv_points(p0, p1, p);
+    aff2[2 * i] = p0;
+    aff2[2 * i + 1] = p1;
+    for (int h = 0; h < 2; h++) {
+        int32_t d[MSM_MAX_WIN];
+        msm_digits(d, m[h], plan);
+        for (int w = 0; w < plan.nwin; w++)
+            if (d[w] != 0) atomicAdd(&counts[(uint32_t)w * (uint32_t)plan.nb + ((uint32_t)(d[w] < 0 ? -d[w] : d[w]) - 1u)], 1u);
+    }
+}
+// Pass 2: the same digits again, scattered into the bucket-sorted entry list as (virtual point << 1) | negate
+__global__ void __launch_bounds__(S256_TPB) k_msm_scatter(size_t n, msm_plan plan, const uint4 *half, const uint8_t *hsign,
+                                                          uint32_t *cursor, uint32_t *entries) {
+    size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // virtual point
+    if (v >= 2 * n) return;
+    uint4 q = half[v];
+    sc m;
+    m.v[0] = q.x; m.v[1] = q.y; m.v[2] = q.z; m.v[3] = q.w;
+    m.v[4] = m.v[5] = m.v[6] = m.v[7] = 0u;
+    uint32_t hneg = (hsign[v >> 1] >> (v & 1)) & 1u;
     int32_t d[MSM_MAX_WIN];
-    msm_digits(d, k, plan);
+    msm_digits(d, m, plan);
     for (int w = 0; w < plan.nwin; w++) {
         int32_t dw = d[w];
         if (dw == 0) continue;
         uint32_t mag = (uint32_t)(dw < 0 ? -dw : dw);
-        uint32_t b = (uint32_t)w * (uint32_t)plan.nb + (mag - 1u);
-        if (!SCATTER) {
-            atomicAdd(&counts[b], 1u);
-        } else {
-            uint32_t pos = atomicAdd(&cursor[b], 1u);
-            entries[pos] = ((uint32_t)i << 1) | (uint32_t)(dw < 0);
-        }
+        uint32_t pos = atomicAdd(&cursor[(uint32_t)w * (uint32_t)plan.nb + (mag - 1u)], 1u);
+        entries[pos] = ((uint32_t)v << 1) | ((uint32_t)(dw < 0) ^ hneg);
     }
 }
 // nsl[b] = slices of bucket b (counts -> slice counts), then scanned into sl_off
-__global__ void __launch_bounds__(S256_TPB) k_msm_slice_counts(uint32_t total, const uint32_t *counts, uint32_t *nsl) {
+__global__ void __launch_bounds__(S256_TPB) k_msm_slice_counts(uint32_t total, const uint32_t *counts, uint32_t *nsl, int slice) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < total) nsl[b] = msm_slices_of(counts[b]);
+    if (b < total) nsl[b] = msm_slices_of(counts[b], slice);
     if (b == total) nsl[b] = 0;
 }
 // Slice schedule: range[s] = entry range of slice s, hist[MSM_SLICE - len] = slices of that length.
@@ -40,14 +62,14 @@ __global__ void __launch_bounds__(S256_TPB) k_msm_slice_counts(uint32_t total, c
 constexpr int MSM_BINS = MSM_SLICE + 1;
 __global__ void __launch_bounds__(S256_MSM_ST) k_msm_slice_ranges(uint32_t max_slices, uint32_t total, const uint32_t *sl_off,
                                                                   const uint32_t *offsets, uint2 *range, uint32_t *bucket_of,
-                                                                  uint32_t *hist) {
+                                                                  uint32_t *hist, int slice) {
     __shared__ uint32_t sh[MSM_BINS];
     for (int i = threadIdx.x; i < MSM_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < max_slices && s < sl_off[total]) {
         uint32_t st, en;
-        bucket_of[s] = msm_slice_range(st, en, s, sl_off, offsets, total);
+        bucket_of[s] = msm_slice_range(st, en, s, sl_off, offsets, total, slice);
         range[s] = make_uint2(st, en);
         atomicAdd(&sh[MSM_SLICE - (en - st)], 1u);
     }
@@ -99,6 +121,20 @@ __global__ void __launch_bounds__(S256_TPB) k_msm_superslices(uint32_t max_slice
     if (s >= max_slices || s >= sl_off[total]) return;
     uint32_t b = bucket_of[s];
     msm_superslice_fold(slice_sum, s, sl_off[b], sl_off[b + 1]);
+}
+
+// bucket b = the sum of its slice sums, one thread per bucket, written densely (bsum[b]) together with the identity
+// slice map the window stage then reads it through: with short slices a bucket has several slice sums, and folding
+// them inside the window stage would put those additions on its serial chains (measured: k_msm_windows 0.20 -> 0.50 ms
+// at n = 2^17 with 16-entry slices).
+__global__ void __launch_bounds__(S256_TPB) k_msm_fold_buckets(uint32_t total, const pt *slice_sum, const uint32_t *sl_off,
+                                                               pt *bsum, uint32_t *ident) {
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b <= total) ident[b] = b;
+    if (b >= total) return;
+    pt acc;
+    msm_bucket_from_slices(acc, slice_sum, sl_off, b);
+    bsum[b] = acc;
 }
 
 // One CTA of MSM_WT threads, thread t holding (run_t, sum_t) with sum_t weighted relative to its own
@@ -250,24 +286,28 @@ __global__ void k_export_partial(const pt *acc, uint8_t *out96) {
 // MSM
 // ---------------------------------------------------------------------------
 static size_t msm_entries_capacity(const s256_ctx *ctx) {
-    // nwin * n entries; the planner uses c >= 12 once n >= 2^16 (nwin <= 22), and c >= 4 (nwin <= 64) below
+    // nwin * 2n entries (two 128-bit halves per scalar): c = 4 gives 32 windows, i.e. 64 n; the planner is at
+    // c >= 10 (26 n) once n >= 2^14 and chunk_msm widens the windows until the entries fit
     size_t cap = ctx->cap;
-    size_t small = (size_t)MSM_MAX_WIN * (cap < 65536 ? cap : 65536), large = (size_t)22 * cap;
+    size_t small = (size_t)MSM_MAX_WIN * (cap < 65536 ? cap : 65536), large = (size_t)26 * cap;
     return small > large ? small : large;
 }
 static int msm_ensure(s256_ctx *ctx) {
     if (ctx->msm_cap) return S256_SUCCESS;
     size_t total = 0;
     for (int c = 4; c <= MSM_MAX_C; c++) {
-        size_t t = (size_t)msm_plan_for_c(c).total;
+        size_t t = (size_t)msm_plan_for_c(c, 128).total;
         if (t > total) total = t;
     }
+    CK(cudaMalloc(&ctx->msm_bsum, (total + 1) * sizeof(pt)));
+    CK(cudaMalloc(&ctx->msm_aff2, 2 * ctx->cap * sizeof(apt)));
+    CK(cudaMalloc(&ctx->msm_half, 2 * ctx->cap * sizeof(uint4)));
     CK(cudaMalloc(&ctx->msm_counts, (total + 1) * 4));
     CK(cudaMalloc(&ctx->msm_offsets, (total + 1) * 4));
     CK(cudaMalloc(&ctx->msm_cursor, (total + 1) * 4));
     CK(cudaMalloc(&ctx->msm_entries, msm_entries_capacity(ctx) * 4));
     // slice sums: one per bucket at least, plus one per MSM_SLICE entries
-    ctx->msm_max_slices = total + msm_entries_capacity(ctx) / MSM_SLICE + 1;
+    ctx->msm_max_slices = total + msm_entries_capacity(ctx) / (MSM_SLICE / 4) + 1;  // the shortest slice length (msm.cuh)
     CK(cudaMalloc(&ctx->msm_buckets, ctx->msm_max_slices * sizeof(pt)));
     CK(cudaMalloc(&ctx->msm_nsl, (total + 1) * 4));
     CK(cudaMalloc(&ctx->msm_sloff, (total + 1) * 4));
@@ -312,34 +352,46 @@ static int chunk_msm(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt65, siz
         ctx->launches.fetch_add(1, std::memory_order_relaxed);
         return S256_SUCCESS;
     }
-    msm_plan pl = msm_make_plan(n);
-    while (pl.c < MSM_MAX_C && (size_t)pl.nwin * n > msm_entries_capacity(ctx)) pl = msm_plan_for_c(pl.c + 1);
+    // endomorphism form: 2n virtual points with 128-bit scalars (msm.cuh)
+    const size_t nv = 2 * n;
+    msm_plan pl = msm_make_plan(nv, 128);
+    while (pl.c < MSM_MAX_C && (size_t)pl.nwin * nv > msm_entries_capacity(ctx)) pl = msm_plan_for_c(pl.c + 1, 128);
     uint32_t total = (uint32_t)pl.total;
     CK(cudaMemsetAsync(ctx->msm_counts, 0, ((size_t)total + 1) * 4, s));
-    LAUNCH(ctx, k_msm_digits<false>, grid_for(n), 0, s, k32, n, pl, ctx->msm_counts, ctx->msm_cursor, ctx->msm_entries);
+    LAUNCH(ctx, k_msm_prepare, grid_for(n), 0, s, k32, ctx->aff, n, pl, (uint4 *)ctx->msm_half, ctx->sfl, ctx->msm_aff2,
+           ctx->msm_counts);
     size_t bytes = ctx->msm_cub_bytes;
     CK(cub::DeviceScan::ExclusiveSum(ctx->msm_cub, bytes, ctx->msm_counts, ctx->msm_offsets, (int)(total + 1), s));
     CK(cudaMemcpyAsync(ctx->msm_cursor, ctx->msm_offsets, (size_t)total * 4, cudaMemcpyDeviceToDevice, s));
-    LAUNCH(ctx, k_msm_digits<true>, grid_for(n), 0, s, k32, n, pl, ctx->msm_counts, ctx->msm_cursor, ctx->msm_entries);
+    LAUNCH(ctx, k_msm_scatter, grid_for(nv), 0, s, n, pl, (const uint4 *)ctx->msm_half, ctx->sfl, ctx->msm_cursor,
+           ctx->msm_entries);
     // buckets -> slices of <= MSM_SLICE entries
-    LAUNCH(ctx, k_msm_slice_counts, grid_for((size_t)total + 1), 0, s, total, ctx->msm_counts, ctx->msm_nsl);
+    LAUNCH(ctx, k_msm_slice_counts, grid_for((size_t)total + 1), 0, s, total, ctx->msm_counts, ctx->msm_nsl, pl.slice);
     CK(cub::DeviceScan::ExclusiveSum(ctx->msm_cub, bytes, ctx->msm_nsl, ctx->msm_sloff, (int)(total + 1), s));
-    size_t max_slices = (size_t)total + ((size_t)pl.nwin * n) / MSM_SLICE + 1;
+    size_t max_slices = (size_t)total + ((size_t)pl.nwin * nv) / (size_t)pl.slice + 1;
     if (max_slices > ctx->msm_max_slices) max_slices = ctx->msm_max_slices;
     // hand the slices out longest first: every warp then runs (almost) equally long threads
     CK(cudaMemsetAsync(ctx->msm_hist, 0, 2 * MSM_BINS * 4, s));
     unsigned sgrid = (unsigned)((max_slices + S256_MSM_ST - 1) / S256_MSM_ST);
     k_msm_slice_ranges<<<sgrid, S256_MSM_ST, 0, s>>>((uint32_t)max_slices, total, ctx->msm_sloff, ctx->msm_offsets,
-                                                     (uint2 *)ctx->msm_range, ctx->msm_sbkt, ctx->msm_hist);
+                                                     (uint2 *)ctx->msm_range, ctx->msm_sbkt, ctx->msm_hist, pl.slice);
     k_msm_slice_perm<<<sgrid, S256_MSM_ST, 0, s>>>((uint32_t)max_slices, total, ctx->msm_sloff, (const uint2 *)ctx->msm_range,
                                                    ctx->msm_hist, ctx->msm_hist + MSM_BINS, ctx->msm_perm);
     LAUNCH(ctx, k_msm_slices, grid_for(max_slices), 0, s, (uint32_t)max_slices, total, ctx->msm_sloff, ctx->msm_perm,
-           (const uint2 *)ctx->msm_range, ctx->msm_entries, ctx->aff, ctx->msm_buckets);
+           (const uint2 *)ctx->msm_range, ctx->msm_entries, ctx->msm_aff2, ctx->msm_buckets);
     LAUNCH(ctx, k_msm_superslices, grid_for(max_slices), 0, s, (uint32_t)max_slices, total, ctx->msm_sloff, ctx->msm_sbkt,
            ctx->msm_buckets);
     int parts = msm_parts_for(pl.nb);
     if (msm_parts_for(pl.nb_top) > parts) parts = msm_parts_for(pl.nb_top);
-    k_msm_windows<<<dim3(parts, pl.nwin), MSM_WT, 0, s>>>(pl, ctx->msm_buckets, ctx->msm_sloff, ctx->msm_part, parts);
+    const pt *bucket_sums = ctx->msm_buckets;
+    const uint32_t *bucket_map = ctx->msm_sloff;
+    if (pl.slice < MSM_SLICE) {  // several slices per bucket: fold them first, all buckets in parallel
+        LAUNCH(ctx, k_msm_fold_buckets, grid_for((size_t)total + 1), 0, s, total, ctx->msm_buckets, ctx->msm_sloff,
+               ctx->msm_bsum, ctx->msm_nsl);  // msm_nsl (the per-bucket slice counts) is free again: reused as the map
+        bucket_sums = ctx->msm_bsum;
+        bucket_map = ctx->msm_nsl;
+    }
+    k_msm_windows<<<dim3(parts, pl.nwin), MSM_WT, 0, s>>>(pl, bucket_sums, bucket_map, ctx->msm_part, parts);
     k_msm_windows2<<<pl.nwin, MSM_WT, 0, s>>>(pl, ctx->msm_part, parts, ctx->msm_win);
     k_msm_final<<<1, 32, 0, s>>>(pl, ctx->msm_win, ctx->msm_acc, first);
     ctx->launches.fetch_add(5, std::memory_order_relaxed);
@@ -569,7 +621,7 @@ extern "C" int s256_msm_dev(s256_ctx *ctx, const uint8_t *k32, const uint8_t *pt
 // the Pippenger plan for n points on one GPU (window bits, windows): what bench.py's work model needs
 extern "C" int s256_msm_plan(size_t n, int *window_bits, int *windows) {
     if (!window_bits || !windows) return S256_ERR_ARG;
-    msm_plan pl = msm_make_plan(n);
+    msm_plan pl = msm_make_plan(2 * n, 128);
     *window_bits = pl.c;
     *windows = pl.nwin;
     return S256_SUCCESS;

@@ -83,6 +83,7 @@ extern "C" int s256_ecdsa_sign_rfc6979_dev(s256_ctx *ctx, const uint8_t *priv32,
         return chunk_sign(ctx, view_at(ctx, 0), priv32 + 32 * off, digest32 + 32 * off, c, sig64 + 64 * off, recid + off,
                           status + off, s);
     });
+    if (rc != S256_SUCCESS) wipe_secret_scratch(ctx);  // the chunk code returned before its own wipes
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
 extern "C" int s256_ecdsa_sign_rfc6979(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *digest32, size_t n,
@@ -103,6 +104,7 @@ extern "C" int s256_ecdsa_sign_rfc6979(s256_ctx *ctx, const uint8_t *priv32, con
         CK(cudaMemsetAsync(v.in_a, 0, 32 * c, s));  // wipe the staged private keys
         return S256_SUCCESS;
     });
+    if (rc != S256_SUCCESS) wipe_secret_scratch(ctx);  // the chunk code returned before its own wipes
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
 
@@ -116,6 +118,7 @@ extern "C" int s256_schnorr_sign_dev(s256_ctx *ctx, const uint8_t *priv32, const
         return chunk_schnorr_sign(ctx, view_at(ctx, 0), priv32 + 32 * off, msg + msg_len * off, msg_len, aux32 + 32 * off,
                                   c, sig64 + 64 * off, status + off, s);
     });
+    if (rc != S256_SUCCESS) wipe_secret_scratch(ctx);  // the chunk code returned before its own wipes
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }
 extern "C" int s256_schnorr_sign(s256_ctx *ctx, const uint8_t *priv32, const uint8_t *msg, size_t msg_len,
@@ -124,13 +127,7 @@ extern "C" int s256_schnorr_sign(s256_ctx *ctx, const uint8_t *priv32, const uin
     scratch_guard sg_(ctx, ctx->stream, true);
     if (n && (!priv32 || (!msg && msg_len) || !aux32 || !sig64 || !status)) return S256_ERR_ARG;
     size_t need = (msg_len ? msg_len : 1) * (n < ctx->cap ? n : ctx->cap);
-    if (need > ctx->in_b_bytes) {
-        if (ctx->in_b) cudaFree(ctx->in_b);
-        ctx->in_b = nullptr;
-        ctx->in_b_bytes = 0;
-        CK(cudaMalloc(&ctx->in_b, need));
-        ctx->in_b_bytes = need;
-    }
+    if (int grc = grow_in_b(ctx, need)) return grc;
     int rc = pipelined(ctx, n, [&](const view &v, size_t off, size_t c, cudaStream_t ps) {
         uint8_t *dmsg = ctx->in_b + msg_len * (size_t)(v.st - ctx->st);  // messages are msg_len apart, not 32
         CK(cudaMemcpyAsync(v.in_a, priv32 + 32 * off, 32 * c, cudaMemcpyHostToDevice, ps));
@@ -144,5 +141,6 @@ extern "C" int s256_schnorr_sign(s256_ctx *ctx, const uint8_t *priv32, const uin
         CK(cudaMemsetAsync(v.in_a, 0, 32 * c, ps));  // wipe the staged private keys
         return S256_SUCCESS;
     });
+    if (rc != S256_SUCCESS) wipe_secret_scratch(ctx);  // the chunk code returned before its own wipes
     return rc != S256_SUCCESS ? rc : check_launch(ctx);
 }

@@ -50,6 +50,9 @@ struct s256_ctx {
     void *msm_range = nullptr;
     size_t msm_max_slices = 0;
     pt *msm_buckets = nullptr, *msm_win = nullptr, *msm_part = nullptr, *msm_acc = nullptr, *msm_tmp = nullptr;
+    apt *msm_aff2 = nullptr;  // the 2n virtual points of the endomorphism form
+    pt *msm_bsum = nullptr;   // dense per-bucket sums (short-slice plans)
+    void *msm_half = nullptr; // the 2n 128-bit scalar halves
     void *msm_cub = nullptr;
     size_t msm_cub_bytes = 0;
     // optional per-kernel timing of the dominant kernel (bench.py roofline)
@@ -224,6 +227,44 @@ static inline int check_launch(s256_ctx *ctx) {
     return S256_SUCCESS;
 }
 
+
+// Grows the variable-width staging buffer in_b: the new buffer is allocated FIRST and swapped in only on success, so a
+// failed allocation leaves the context exactly as it was (never with in_b == NULL).
+static inline int grow_in_b(s256_ctx *ctx, size_t need) {
+    if (need <= ctx->in_b_bytes) return S256_SUCCESS;
+    uint8_t *fresh = nullptr;
+    if (cudaMalloc(&fresh, need) != cudaSuccess) {
+        cudaGetLastError();
+        ctx->last_err = "cudaMalloc(staging buffer)";
+        return S256_ERR_NOMEM;
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream2);
+    cudaStreamSynchronize(ctx->stream3);
+    if (ctx->in_b) cudaFree(ctx->in_b);
+    ctx->in_b = fresh;
+    ctx->in_b_bytes = need;
+    return S256_SUCCESS;
+}
+
+// Error-path hygiene for the entry points that handle secrets (signing, ScalarMult / ECDH): a CUDA failure makes the
+// normal code return before its own targeted wipes, so the caller of this helper clears every scratch array that can
+// hold a private scalar, a nonce, k*P in projective form or a shared x, for the whole context capacity.
+static inline void wipe_secret_scratch(s256_ctx *ctx) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream2);
+    cudaStreamSynchronize(ctx->stream3);
+    cudaGetLastError();
+    const size_t m = ctx->cap;
+    cudaMemsetAsync(ctx->u1, 0, sizeof(sc) * m, ctx->stream);
+    cudaMemsetAsync(ctx->res, 0, sizeof(pt) * m, ctx->stream);
+    cudaMemsetAsync(ctx->tbl, 0, 97 * m, ctx->stream);  // BIP-340 signing keeps R and k' at the start of this area
+    cudaMemsetAsync(ctx->in_a, 0, 65 * m, ctx->stream);
+    cudaMemsetAsync(ctx->in_b, 0, ctx->in_b_bytes, ctx->stream);
+    cudaMemsetAsync(ctx->in_c, 0, 65 * m, ctx->stream);
+    cudaMemsetAsync(ctx->out, 0, 65 * m, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+}
 
 #define ENTER(ctx)                       \
     if (!(ctx)) return S256_ERR_ARG;     \

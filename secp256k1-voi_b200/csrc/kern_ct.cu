@@ -20,7 +20,9 @@ using namespace s256;
 #define S256_BM_SPLIT4_MAX 16384
 #endif
 constexpr size_t CT_BYTES_BIG = (size_t)ct_cfg<CT_WB>::NW * ct_cfg<CT_WB>::SZ * sizeof(apt);
-constexpr size_t CT_BYTES_SMALL = (size_t)ct_cfg<CT_WB_SMALL>::NW * ct_cfg<CT_WB_SMALL>::SZ * sizeof(apt);
+// lane-split kernels: every window's row is followed by 16 bytes of padding (bank spreading, kernels.cuh)
+constexpr size_t CT_ROW_SMALL = (size_t)ct_cfg<CT_WB_SMALL>::SZ * sizeof(apt), CT_ROW_SMALL_PAD = CT_ROW_SMALL + 16;
+constexpr size_t CT_BYTES_SMALL = (size_t)ct_cfg<CT_WB_SMALL>::NW * CT_ROW_SMALL_PAD;
 
 __global__ void __launch_bounds__(S256_TPB_BIG, S256_BM_MINB_BIG)
     k_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_g, pt *res) {
@@ -55,8 +57,8 @@ __global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
     apt *tab = reinterpret_cast<apt *>(smem_raw);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(tab_g);
-        const int nvec = (int)(CT_BYTES_SMALL / 16);
-        for (int v = threadIdx.x; v < nvec; v += blockDim.x) smem_raw[v] = src[v];
+        constexpr int per_row = (int)(CT_ROW_SMALL / 16), nvec = ct_cfg<CT_WB_SMALL>::NW * per_row;
+        for (int v = threadIdx.x; v < nvec; v += blockDim.x) smem_raw[v + v / per_row] = src[v];   // + one uint4 per row
     }
     __syncthreads();
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,7 +68,7 @@ __global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
     sc k;
     sc_from_be32(k, k32 + 32 * (live ? item : 0));
     pt acc;
-    item_base_mult_ct_part<CT_WB_SMALL>(acc, k, tab, part, T);
+    item_base_mult_ct_part<CT_WB_SMALL>(acc, k, tab, part, T, CT_ROW_SMALL_PAD);
 #pragma unroll
     for (int off = T / 2; off >= 1; off >>= 1) {
         pt o;
@@ -82,6 +84,10 @@ __global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
 void s256_ct_kernels_init() {
     cudaFuncSetAttribute(k_base_mult_ct_split<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_SMALL);
     cudaFuncSetAttribute(k_base_mult_ct_split<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_SMALL);
+    cudaFuncSetAttribute(k_base_mult_ct_split<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_SMALL);
+    cudaFuncSetAttribute(k_base_mult_ct_split<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_SMALL);
+    cudaFuncSetAttribute(k_base_mult_ct_split<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(k_base_mult_ct_split<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_base_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_BIG);
     // ask for the largest shared-memory carve-out: without the hint the driver sizes it for ONE CTA and the
     // second (fourth) CTA of an SM waits for the first to retire
@@ -104,6 +110,14 @@ void s256_launch_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_big, 
     if (n == 0) return;
     // small batches are latency bound: deal the windows of each scalar to 8 / 4 lanes (16 lanes measured
     // slower at n = 4096: 0.227 against 0.198 ms)
+    static const int force_t = getenv("S256_BM_T") ? atoi(getenv("S256_BM_T")) : 0;  // tuning knob: lanes per scalar
+    if (force_t == 16 || force_t == 32) {
+        if (force_t == 16)
+            k_base_mult_ct_split<16><<<(unsigned)((n * 16 + S256_TPB - 1) / S256_TPB), S256_TPB, CT_BYTES_SMALL, s>>>(k32, n, tab_small, res);
+        else
+            k_base_mult_ct_split<32><<<(unsigned)((n * 32 + S256_TPB - 1) / S256_TPB), S256_TPB, CT_BYTES_SMALL, s>>>(k32, n, tab_small, res);
+        return;
+    }
     if (n <= 8192) {
         k_base_mult_ct_split<8><<<(unsigned)((n * 8 + S256_TPB - 1) / S256_TPB), S256_TPB, CT_BYTES_SMALL, s>>>(k32, n, tab_small, res);
         return;

@@ -677,8 +677,14 @@ S256_HD void item_base_mult_ct(pt &acc, const sc &k, const apt *tab /* [NW][SZ] 
 // iteration j, so the whole warp stays in lockstep); the caller folds the T partial points with
 // complete additions.  Digits are recoded first (carry chain) into a local array that is then read
 // at an index depending only on the lane number.  Same selects as above, over the 5-bit table.
+// `row_bytes`: distance between the rows of two consecutive windows.  The lanes of a group read the SAME entry index of
+// DIFFERENT windows at the same time; with the natural stride (16 entries x 64 B = 1024 B) all of them hit the same
+// four banks -- an 8-way conflict on every shared load of the kernel (ncu: 12.8 M of 14.8 M wavefronts were conflicts,
+// profiles/r02_ct_counters.txt).  The kernel stages the table with 16 bytes of padding per row, which spreads the
+// eight lanes over the eight 16-byte bank groups.  (Public addressing either way: lane number and loop counters.)
 template <int CT_WB = S256_CT_WB_SMALL>
-S256_HD void item_base_mult_ct_part(pt &acc, const sc &k, const apt *tab, int part, int T) {
+S256_HD void item_base_mult_ct_part(pt &acc, const sc &k, const apt *tab, int part, int T,
+                                    size_t row_bytes = (size_t)ct_cfg<CT_WB>::SZ * sizeof(apt)) {
     constexpr int CT_NW = ct_cfg<CT_WB>::NW, CT_SZ = ct_cfg<CT_WB>::SZ;
     int8_t dig[CT_NW];
     uint32_t carry = 0;
@@ -703,7 +709,7 @@ S256_HD void item_base_mult_ct_part(pt &acc, const sc &k, const apt *tab, int pa
         apt sel;
         sel.x = fe_zero();
         sel.y = fe_zero();
-        const apt *row = tab + wc * CT_SZ;
+        const apt *row = reinterpret_cast<const apt *>(reinterpret_cast<const char *>(tab) + (size_t)wc * row_bytes);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 2
 #endif

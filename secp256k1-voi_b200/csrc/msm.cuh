@@ -60,32 +60,39 @@ constexpr int MSM_MAX_WIN = 64;  // c = 4 -> 64 windows
 // window exists: such a window would put half of all points into one bucket.
 struct msm_plan {
     int c;         // window bits
-    int nwin;      // windows = ceil(256 / c)
+    int nwin;      // windows = ceil(bits / c)
     int nb;        // buckets per signed window = 2^(c-1)
-    int nb_top;    // buckets of the top window = 2^top_bits, top_bits = 256 - c*(nwin-1)
+    int nb_top;    // buckets of the top window = 2^top_bits, top_bits = bits - c*(nwin-1)
     int total;     // all buckets
+    int slice;     // entries per slice (<= MSM_SLICE): one thread folds one slice
 };
 
-S256_HD msm_plan msm_plan_for_c(int c) {
+// bits = 128: the variable-time MSM splits every scalar with the lambda endomorphism (k = k1 + k2 lambda, |k1|, |k2| <
+// 2^128, point_mul_glv.go:59-117) and runs Pippenger over 2n points (P_i, lambda P_i = (beta x_i, y_i)) with 128-bit
+// scalars: the same number of bucket accumulations, but HALF the buckets and half the doublings of the serial Horner
+// tail (k_msm_final: (nwin - 1) c = 112 instead of 240), which is what a small per-GPU share of a sharded MSM waits for.
+S256_HD msm_plan msm_plan_for_c(int c, int bits = 256) {
     msm_plan p;
     p.c = c;
-    p.nwin = (256 + c - 1) / c;
+    p.nwin = (bits + c - 1) / c;
     p.nb = 1 << (c - 1);
-    p.nb_top = 1 << (256 - c * (p.nwin - 1));
+    p.nb_top = 1 << (bits - c * (p.nwin - 1));
     p.total = (p.nwin - 1) * p.nb + p.nb_top;
+    p.slice = MSM_SLICE;
     return p;
 }
 // Window width by a cost model instead of the round-1 rule c = floor(log2 n) - 4: one bucket accumulation per point and
 // window, about eight of those per bucket for the window stage (measured: 0.13-0.17 ns per accumulated entry, 0.8-2 ns
-// per bucket), and NO width whose unsigned top window is only a few bits wide -- with c = 15 the top window has 2^1
-// buckets, half of all points land in one of them, and that bucket's 4096 slices are folded by a lone thread
-// (k_msm_superslices 0.41 ms, the digit kernels' atomics on one counter: n = 2^19 took 3.17 ms against 3.62 ms for 2^20).
-S256_HD msm_plan msm_make_plan(size_t n) {
+// per bucket), and NO width whose unsigned top window is only a few bits wide -- with c = 15 and 256-bit scalars the top
+// window has 2^1 buckets, half of all points land in one of them, and that bucket's 4096 slices are folded by a lone
+// thread (k_msm_superslices 0.41 ms, the digit kernels' atomics on one counter: n = 2^19 took 3.17 ms against 3.62 ms
+// for 2^20).  n = the number of (virtual) points that carry a `bits`-bit scalar.
+S256_HD msm_plan msm_make_plan(size_t n, int bits = 256) {
     int best = 4;
     double best_cost = -1.0;
     for (int c = 4; c <= MSM_MAX_C; c++) {
-        msm_plan p = msm_plan_for_c(c);
-        int top_bits = 256 - c * (p.nwin - 1);
+        msm_plan p = msm_plan_for_c(c, bits);
+        int top_bits = bits - c * (p.nwin - 1);
         if ((n >> top_bits) > 2048 && c != MSM_MAX_C) continue;  // a top bucket of more than 32 slices
         double cost = (double)n * p.nwin + 8.0 * (double)p.total;
         if (best_cost < 0 || cost < best_cost) {
@@ -93,7 +100,14 @@ S256_HD msm_plan msm_make_plan(size_t n) {
             best = c;
         }
     }
-    return msm_plan_for_c(best);
+    msm_plan p = msm_plan_for_c(best, bits);
+    // A slice is folded by ONE thread, one dependent mixed addition after the other (~4 us each for a lone warp): with
+    // few entries there are not enough slices to fill the GPU and the kernel lasts as long as its longest chain
+    // (n = 2^17: 41 k slices of 64, 0.53 ms).  Shorter slices for smaller inputs: more threads, shorter chains; the
+    // extra slice sums of a bucket are folded in the window stage.
+    double entries = (double)n * p.nwin;
+    p.slice = entries >= 8.0e6 ? MSM_SLICE : (entries >= 4.0e6 ? MSM_SLICE / 2 : MSM_SLICE / 4);
+    return p;
 }
 S256_HD int msm_window_buckets(const msm_plan &p, int w) { return w == p.nwin - 1 ? p.nb_top : p.nb; }
 
@@ -114,6 +128,24 @@ S256_HD void msm_digits(int32_t *d, const sc &k, const msm_plan &p) {
             d[w] = (int32_t)v - (int32_t)(carry << p.c);
         }
     }
+}
+
+// The two halves of a scalar for the endomorphism form: magnitudes below 2^128 (zero-extended to 8 limbs, so that
+// msm_digits reads them like any scalar) and their signs.  Virtual point 2i is P_i with k1, 2i + 1 is lambda P_i with k2.
+S256_HD void msm_glv_halves(sc &m1, uint32_t &neg1, sc &m2, uint32_t &neg2, const sc &k) {
+    uint32_t a[4], b[4];
+    sc_split_glv_abs(a, neg1, b, neg2, k);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        m1.v[i] = i < 4 ? a[i] : 0u;
+        m2.v[i] = i < 4 ? b[i] : 0u;
+    }
+}
+// the virtual points of P: (x, y) and (beta x, y)
+S256_HD void msm_glv_points(apt &p0, apt &p1, const apt &p) {
+    p0 = p;
+    fe_mul(p1.x, p.x, fe_beta());
+    p1.y = p.y;
 }
 
 // slice / bucket accumulation: entries hold (point index << 1) | negate
@@ -144,7 +176,9 @@ S256_HD void msm_bucket_sum(pt &out, const uint32_t *entries, uint32_t start, ui
 }
 
 // slices of bucket b: max(1, ceil(count / MSM_SLICE))
-S256_HD uint32_t msm_slices_of(uint32_t count) { return count == 0 ? 1u : (count + MSM_SLICE - 1) / MSM_SLICE; }
+S256_HD uint32_t msm_slices_of(uint32_t count, int slice) {
+    return count == 0 ? 1u : (count + (uint32_t)slice - 1u) / (uint32_t)slice;
+}
 
 // A bucket of more than MSM_SUPER slices (> 4096 entries: equal or adversarial scalars) gets a second
 // level: the thread of every MSM_SUPER-th slice folds the next MSM_SUPER slice sums into its own slot.
@@ -208,15 +242,15 @@ S256_HD void msm_horner(pt &out, const pt *win, const msm_plan &p, int parts, in
 }
 // which entry range does slice s cover?  binary search for the bucket (returned), then the range
 S256_HD uint32_t msm_slice_range(uint32_t &start, uint32_t &end, uint32_t s, const uint32_t *sl_off,
-                                 const uint32_t *offsets, uint32_t total_buckets) {
+                                 const uint32_t *offsets, uint32_t total_buckets, int slice) {
     uint32_t lo = 0, hi = total_buckets;  // invariant: sl_off[lo] <= s < sl_off[hi]
     while (hi - lo > 1) {
         uint32_t mid = (lo + hi) >> 1;
         if (sl_off[mid] <= s) lo = mid; else hi = mid;
     }
     uint32_t k = s - sl_off[lo];
-    start = offsets[lo] + k * MSM_SLICE;
-    end = start + MSM_SLICE;
+    start = offsets[lo] + k * (uint32_t)slice;
+    end = start + (uint32_t)slice;
     if (end > offsets[lo + 1]) end = offsets[lo + 1];
     if (start > end) start = end;
     return lo;  // the bucket

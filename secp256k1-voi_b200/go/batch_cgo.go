@@ -139,16 +139,24 @@ func (e *Engine) ScalarMultBatch(scalars []*secp256k1.Scalar, points []*secp256k
 		panic("secp256k1: len(scalars) != len(points)")
 	}
 	n := len(scalars)
+	// The identity has a 1-byte encoding (point_s11n.go:73-76), the C ABI takes 65-byte rows: identity operands are
+	// answered here (k * identity = identity, as Point.ScalarMult does) and only the other rows travel.
 	k, p := make([]byte, 0, 32*n), make([]byte, 0, 65*n)
+	rows := make([]int, 0, n)
 	for i := range scalars {
+		if points[i].IsIdentity() == 1 {
+			continue
+		}
 		k = append(k, scalars[i].Bytes()...)
-		p = append(p, points[i].UncompressedBytes()...) // identity inputs must be filtered by the caller
+		p = appendPoint65(p, points[i])
+		rows = append(rows, i)
 	}
-	out, st := make([]byte, 65*n), make([]byte, n)
-	if err := e.err(C.s256_scalar_mult(e.ctx, ptr(k), ptr(p), C.size_t(n), ptr(out), ptr(st))); err != nil {
+	m := len(rows)
+	out, st := make([]byte, 65*m), make([]byte, m)
+	if err := e.err(C.s256_scalar_mult(e.ctx, ptr(k), ptr(p), C.size_t(m), ptr(out), ptr(st))); err != nil {
 		return nil, err
 	}
-	return decodePoints(out, st)
+	return scatterPoints(n, rows, out, st, nil)
 }
 
 // DoubleScalarMultBasepointVartimeBatch is Point.DoubleScalarMultBasepointVartime.
@@ -157,17 +165,42 @@ func (e *Engine) DoubleScalarMultBasepointVartimeBatch(u1, u2 []*secp256k1.Scala
 	if len(u2) != n || len(points) != n {
 		panic("secp256k1: length mismatch")
 	}
+	// u1*G + u2*identity = u1*G: identity rows go through ScalarBaseMultBatch (the reference accepts them,
+	// point_mul_glv.go:307-317), the others through the ladder.
 	a, b, p := make([]byte, 0, 32*n), make([]byte, 0, 32*n), make([]byte, 0, 65*n)
+	rows, idRows := make([]int, 0, n), make([]int, 0)
+	idScalars := make([]*secp256k1.Scalar, 0)
 	for i := 0; i < n; i++ {
+		if points[i].IsIdentity() == 1 {
+			idRows = append(idRows, i)
+			idScalars = append(idScalars, u1[i])
+			continue
+		}
 		a = append(a, u1[i].Bytes()...)
 		b = append(b, u2[i].Bytes()...)
-		p = append(p, points[i].UncompressedBytes()...)
+		p = appendPoint65(p, points[i])
+		rows = append(rows, i)
 	}
-	out, st := make([]byte, 65*n), make([]byte, n)
-	if err := e.err(C.s256_double_scalar_mult_basepoint_vartime(e.ctx, ptr(a), ptr(b), ptr(p), C.size_t(n), ptr(out), ptr(st))); err != nil {
+	m := len(rows)
+	out, st := make([]byte, 65*m), make([]byte, m)
+	if err := e.err(C.s256_double_scalar_mult_basepoint_vartime(e.ctx, ptr(a), ptr(b), ptr(p), C.size_t(m), ptr(out), ptr(st))); err != nil {
 		return nil, err
 	}
-	return decodePoints(out, st)
+	var idPts []*secp256k1.Point
+	if len(idRows) > 0 {
+		var err error
+		if idPts, err = e.ScalarBaseMultBatch(idScalars); err != nil {
+			return nil, err
+		}
+	}
+	res, err := scatterPoints(n, rows, out, st, nil)
+	if err != nil {
+		return nil, err
+	}
+	for j, i := range idRows {
+		res[i] = idPts[j]
+	}
+	return res, nil
 }
 
 // MultiScalarMult is Point.MultiScalarMult[Vartime]: sum scalars[i] * points[i].
@@ -175,11 +208,15 @@ func (e *Engine) MultiScalarMult(scalars []*secp256k1.Scalar, points []*secp256k
 	if len(scalars) != len(points) {
 		panic("secp256k1: len(scalars) != len(points)")
 	}
-	n := len(scalars)
-	k, p := make([]byte, 0, 32*n), make([]byte, 0, 65*n)
+	n := 0
+	k, p := make([]byte, 0, 32*len(scalars)), make([]byte, 0, 65*len(scalars))
 	for i := range scalars {
+		if points[i].IsIdentity() == 1 { // contributes nothing to the sum (point_mul_multi.go accepts it)
+			continue
+		}
 		k = append(k, scalars[i].Bytes()...)
-		p = append(p, points[i].UncompressedBytes()...)
+		p = appendPoint65(p, points[i])
+		n++
 	}
 	out := make([]byte, 65)
 	var st C.uint8_t
@@ -277,6 +314,37 @@ var errInvalid = errors.New("secp256k1b200: invalid input row")
 
 // decodePoints rebuilds reference Points from the engine's rows; the identity comes back as the
 // status byte because the reference's identity encoding is the 1-byte 0x00 (point_s11n.go:75-77).
+// appendPoint65 appends the 65-byte SEC 1 encoding of a non-identity point; anything else would shift every later
+// row of the batch and make the C side read past the slice, so it panics instead.
+func appendPoint65(dst []byte, p *secp256k1.Point) []byte {
+	enc := p.UncompressedBytes()
+	if len(enc) != 65 {
+		panic("secp256k1b200: point without a 65-byte encoding in a batch row")
+	}
+	return append(dst, enc...)
+}
+
+// scatterPoints decodes the m computed rows into a result of n points; rows[j] is the position of computed row j, every
+// other position is the identity (fill == nil) .
+func scatterPoints(n int, rows []int, out, st []byte, fill *secp256k1.Point) ([]*secp256k1.Point, error) {
+	got, err := decodePoints(out, st)
+	if err != nil {
+		return nil, err
+	}
+	res := make([]*secp256k1.Point, n)
+	for i := range res {
+		if fill != nil {
+			res[i] = fill
+		} else {
+			res[i] = secp256k1.NewIdentityPoint()
+		}
+	}
+	for j, i := range rows {
+		res[i] = got[j]
+	}
+	return res, nil
+}
+
 func decodePoints(out, st []byte) ([]*secp256k1.Point, error) {
 	pts := make([]*secp256k1.Point, len(st))
 	for i, s := range st {

@@ -176,37 +176,48 @@ EXPORT void sim_msm(const uint8_t *k32, const uint8_t *pt65, size_t n, int varti
         }
         for (size_t i = 0; i < n; i++) pt_add(acc, acc, s.res[i]);
     } else if (n) {
-        msm_plan pl = msm_make_plan(n);
-        if (force_c) pl = msm_plan_for_c(force_c);
+        // endomorphism form, as chunk_msm runs it: 2n virtual points (P, lambda P) with the 128-bit halves of the scalars
+        const size_t nv = 2 * n;
+        msm_plan pl = msm_make_plan(nv, 128);
+        if (force_c) pl = msm_plan_for_c(force_c, 128);
         size_t total = (size_t)pl.total;
-        std::vector<uint32_t> counts(total + 1, 0), offsets(total + 1, 0), cursor(total + 1, 0), entries((size_t)pl.nwin * n);
-        std::vector<int32_t> dig((size_t)pl.nwin * n);
+        std::vector<uint32_t> counts(total + 1, 0), offsets(total + 1, 0), cursor(total + 1, 0), entries((size_t)pl.nwin * nv);
+        std::vector<int32_t> dig((size_t)pl.nwin * nv);
+        std::vector<apt> aff2(nv);
+        std::vector<uint32_t> hneg(nv);
         for (size_t i = 0; i < n; i++) {
-            sc k;
+            sc k, m[2];
             sc_from_be32(k, k32 + 32 * i);
-            int32_t d[MSM_MAX_WIN];
-            msm_digits(d, k, pl);
-            for (int w = 0; w < pl.nwin; w++) {
-                dig[(size_t)w * n + i] = d[w];
-                if (d[w]) counts[(size_t)w * pl.nb + (size_t)(std::abs(d[w]) - 1)]++;
+            uint32_t ng[2];
+            msm_glv_halves(m[0], ng[0], m[1], ng[1], k);
+            msm_glv_points(aff2[2 * i], aff2[2 * i + 1], s.aff[i]);
+            for (int h = 0; h < 2; h++) {
+                size_t v = 2 * i + h;
+                hneg[v] = ng[h];
+                int32_t d[MSM_MAX_WIN];
+                msm_digits(d, m[h], pl);
+                for (int w = 0; w < pl.nwin; w++) {
+                    dig[(size_t)w * nv + v] = d[w];
+                    if (d[w]) counts[(size_t)w * pl.nb + (size_t)(std::abs(d[w]) - 1)]++;
+                }
             }
         }
         for (size_t b = 0; b < total; b++) offsets[b + 1] = offsets[b] + counts[b];
         cursor = offsets;
-        for (size_t i = n; i-- > 0;)  // reverse order: bucket order must not matter
+        for (size_t v = nv; v-- > 0;)  // reverse order: bucket order must not matter
             for (int w = 0; w < pl.nwin; w++) {
-                int32_t d = dig[(size_t)w * n + i];
-                if (d) entries[cursor[(size_t)w * pl.nb + (size_t)(std::abs(d) - 1)]++] = ((uint32_t)i << 1) | (uint32_t)(d < 0);
+                int32_t d = dig[(size_t)w * nv + v];
+                if (d) entries[cursor[(size_t)w * pl.nb + (size_t)(std::abs(d) - 1)]++] = ((uint32_t)v << 1) | ((uint32_t)(d < 0) ^ hneg[v]);
             }
         // slices of <= MSM_SLICE entries, exactly as the kernels cut them
         std::vector<uint32_t> sl_off(total + 1, 0);
-        for (size_t b = 0; b < total; b++) sl_off[b + 1] = sl_off[b] + msm_slices_of(counts[b]);
+        for (size_t b = 0; b < total; b++) sl_off[b + 1] = sl_off[b] + msm_slices_of(counts[b], pl.slice);
         std::vector<pt> slice_sum(sl_off[total]);
         std::vector<uint32_t> bucket_of(sl_off[total]);
         for (uint32_t sidx = 0; sidx < sl_off[total]; sidx++) {
             uint32_t st, en;
-            bucket_of[sidx] = msm_slice_range(st, en, sidx, sl_off.data(), offsets.data(), (uint32_t)total);
-            msm_bucket_sum(slice_sum[sidx], entries.data(), st, en, s.aff.data());
+            bucket_of[sidx] = msm_slice_range(st, en, sidx, sl_off.data(), offsets.data(), (uint32_t)total, pl.slice);
+            msm_bucket_sum(slice_sum[sidx], entries.data(), st, en, aff2.data());
         }
         for (uint32_t sidx = 0; sidx < sl_off[total]; sidx++)
             msm_superslice_fold(slice_sum.data(), sidx, sl_off[bucket_of[sidx]], sl_off[bucket_of[sidx] + 1]);
