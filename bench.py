@@ -291,6 +291,7 @@ def main():
     # ---- end to end through the C ABI with host buffers --------------------------
     np_pk, np_dg, np_sg = h_pk.numpy(), h_dg.numpy(), h_sg.numpy()
     e2e_value = None
+    h2d_gbs = None
     if not args.headline_only:
         for _ in range(2):
             ok_h = eng.ecdsa_verify(np_pk, np_dg, np_sg)
@@ -303,6 +304,17 @@ def main():
         barrier()
         assert np.array_equal(ok_h, expected)
         e2e_value = n * world * args.steps / e2e_s
+        # what the PCIe link of every rank gives while ALL ranks copy at once (the e2e pipeline needs ~32 GB/s per link to
+        # hide the copies under the ladder; on these boxes every GPU reports CPU affinity 0-31 / NUMA node 0, so there is
+        # no NUMA placement to choose)
+        barrier(); torch.cuda.synchronize()
+        ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ca.record()
+        for _ in range(5):
+            d_pk.copy_(h_pk, non_blocking=True); d_dg.copy_(h_dg, non_blocking=True); d_sg.copy_(h_sg, non_blocking=True)
+        cb.record(); torch.cuda.synchronize()
+        h2d_gbs = all_ranks(5 * n * 161 / (ca.elapsed_time(cb) * 1e-3) / 1e9)
+        barrier()
 
     # ---- ScalarBaseMult ops/s (BASELINE configs[0] and at 2^20) -------------------
     sbm = {}
@@ -428,8 +440,9 @@ def main():
                               if world > 1 else "none (one GPU)"),
                "h2d_bytes_per_call_per_rank": int((hi - lo) * 97), "d2h_bytes_per_call": 66,
                # bucket accumulation only: one mixed addition per point and window with a non-zero digit
-               "mac32_bucket_accumulation": float((hi - lo) * nwin * (1 - 2.0 ** -c_win) * pkg.mac32_per_item("msm_mixed_add")),
-               "frac_of_int_mul_peak_whole_call": float((hi - lo) * nwin * (1 - 2.0 ** -c_win) * pkg.mac32_per_item("msm_mixed_add")
+               # (2 (hi - lo) virtual points: every scalar is split in two 128-bit halves by the endomorphism)
+               "mac32_bucket_accumulation": float(2 * (hi - lo) * nwin * (1 - 2.0 ** -c_win) * pkg.mac32_per_item("msm_mixed_add")),
+               "frac_of_int_mul_peak_whole_call": float(2 * (hi - lo) * nwin * (1 - 2.0 ** -c_win) * pkg.mac32_per_item("msm_mixed_add")
                                                         / (msm_ms * 1e-3) / imad_peak)}
 
     if rank == 0:
@@ -471,7 +484,8 @@ def main():
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32 limbs (8x32, IMAD.WIDE.U32 carry chains)", "data": "synthetic",
             "config": workload_config(world, n),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 161), "d2h_bytes_per_step": int(n)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 161), "d2h_bytes_per_step": int(n),
+                    "h2d_gbs_per_rank_all_ranks_copying": h2d_gbs},
             "gpu_launches": int(launches),
             "clocks": dict(clocks, per_rank_sm_mhz=rank_sm_mhz), "per_rank_ms_per_step": per_rank_ms,
             "roofline": {"bound": "int-mul",

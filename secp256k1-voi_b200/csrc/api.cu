@@ -1162,13 +1162,13 @@ extern "C" int s256_microbench_fe_mul(s256_ctx *ctx, int form, int iters, double
 // executed (non-zero digits of its two recoded halves), for the first `n` items of its last chunk.  bench.py turns it
 // into the executed MAC32 of that k_dsm launch: additions with a zero digit are skipped, and the lambda half costs one
 // more multiplication (x -> beta x) per executed addition.
-__global__ void __launch_bounds__(S256_TPB) k_count_nonzero_digits(const int8_t *d1, const int8_t *d2, size_t total,
-                                                                  unsigned long long *out) {
+__global__ void __launch_bounds__(S256_TPB) k_count_nonzero_digits(const int8_t *d1, const int8_t *d2, size_t total1,
+                                                                  size_t total2, unsigned long long *out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     unsigned a = 0, b = 0;
-    for (; i < total; i += stride) {
-        a += d1[i] != 0;
-        b += d2[i] != 0;
+    for (; i < total2; i += stride) {
+        a += (i < total1) && d1[i] != 0;   // digits are stored [digit][item]: the top digit of the first half is the
+        b += d2[i] != 0;                   // assignment that starts the ladder, not an addition
     }
     a = __reduce_add_sync(0xffffffffu, a);
     b = __reduce_add_sync(0xffffffffu, b);
@@ -1183,7 +1183,7 @@ extern "C" int s256_debug_ladder_add_count(s256_ctx *ctx, size_t n, uint64_t *ad
     if (!adds_g_half || !adds_lambda_half || n > ctx->cap) return S256_ERR_ARG;
     cudaStream_t s = ctx->stream;
     CK(cudaMemsetAsync(ctx->sink, 0, 16, s));
-    if (n) LAUNCH(ctx, k_count_nonzero_digits, 148 * 8, 0, s, ctx->dig1, ctx->dig2, (size_t)DSM_ND * n, ctx->sink);
+    if (n) LAUNCH(ctx, k_count_nonzero_digits, 148 * 8, 0, s, ctx->dig1, ctx->dig2, (size_t)(DSM_ND - 1) * n, (size_t)DSM_ND * n, ctx->sink);
     unsigned long long h[2] = {0, 0};
     CK(cudaMemcpyAsync(h, ctx->sink, 16, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -1194,7 +1194,13 @@ extern "C" int s256_debug_ladder_add_count(s256_ctx *ctx, size_t n, uint64_t *ad
 // executed MAC32 of one k_dsm item given its measured number of ladder additions (both halves) and beta multiplications
 extern "C" double s256_mac32_k_dsm(double adds_per_item, double beta_muls_per_item) {
     const double M = 73, S = 45;
+#ifndef S256_NO_FUSED
+    const double F2 = 137;  // a b + c d with one reduction: 128 + 8 + 1
+    const double dbl = 4 * M + 2 * S + F2, add = 6 * M + 3 * F2, mix = 5 * M + 3 * F2;
+#else
     const double dbl = 6 * M + 2 * S, add = 12 * M, mix = 11 * M;
+#endif
+    // (the very first addition of the ladder is an assignment; bench.py subtracts it from the measured count)
     return (DSM_TS / 2) * dbl + (DSM_TS / 2 - 1) * mix + (DSM_ND - 1) * DSM_W * dbl + adds_per_item * add +
            beta_muls_per_item * M + COMB_NW * mix;
 }
@@ -1207,14 +1213,20 @@ extern "C" double s256_mac32_k_dsm(double adds_per_item, double beta_muls_per_it
 // 2^-5, the top digit of a 128-bit half (3 bits + carry) with probability 1/8.
 extern "C" double s256_mac32_per_item(const char *name) {
     const double M = 73, S = 45, ZN = 133;
-    const double dbl = 6 * M + 2 * S, add = 12 * M, mix = 11 * M;              // variable-time flavour (k_dsm, MSM)
-    const double dbl_ct = dbl + 2, mix_ct = mix + 2;                              // + the folds of 21a and 8a / 21a twice
+#ifndef S256_NO_FUSED
+    const double F2 = 137;  // a b + c d with one reduction (variable-time flavour only)
+    const double dbl = 4 * M + 2 * S + F2, add = 6 * M + 3 * F2, mix = 5 * M + 3 * F2;   // k_dsm, MSM
+#else
+    const double dbl = 6 * M + 2 * S, add = 12 * M, mix = 11 * M;
+#endif
+    const double dbl_ct = 6 * M + 2 * S + 2, mix_ct = 11 * M + 2;                 // + the folds of 21a and 8a / 21a twice
     // inversions are safegcd (modinv.cuh): 20 batches x (54 + 36) 32x32->64 products, whatever the modulus
     const double inv_fe = 20 * 90, sqrt_fe = 254 * S + 13 * M + 2 * S + M, inv_sc = 20 * 90;
     const double oncurve = 2 * S + M;
     const double table = (DSM_TS / 2) * dbl + (DSM_TS / 2 - 1) * mix;
-    const double adds_per_half = (DSM_ND - 1) * (1.0 - 1.0 / (1 << DSM_W)) + 7.0 / 8.0;
-    const double ladder = (DSM_ND - 1) * DSM_W * dbl + 2 * adds_per_half * add + adds_per_half * M;
+    const double adds_per_half = (DSM_ND - 1) * (1.0 - 1.0 / (1 << DSM_W)) + 15.0 / 16.0;
+    // (the first addition of the first half is an assignment: the accumulator is still the identity)
+    const double ladder = (DSM_ND - 1) * DSM_W * dbl + (2 * adds_per_half - 15.0 / 16.0) * add + adds_per_half * M;
     const double comb = COMB_NW * mix;
     const double dsm = table + ladder + comb;
     const double split = 3 * ZN + 2 * 64;

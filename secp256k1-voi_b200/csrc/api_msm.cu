@@ -103,7 +103,10 @@ __global__ void __launch_bounds__(S256_MSM_ST) k_msm_slice_perm(uint32_t max_sli
     __syncthreads();
     if (live) perm[base[bin] + rank] = s;
 }
-__global__ void __launch_bounds__(S256_TPB) k_msm_slices(uint32_t max_slices, uint32_t total, const uint32_t *sl_off,
+#ifndef S256_MSM_SLICES_MINB
+#define S256_MSM_SLICES_MINB 4   // 128 registers: four CTAs per SM instead of the three that 130 registers allowed
+#endif
+__global__ void __launch_bounds__(S256_TPB, S256_MSM_SLICES_MINB) k_msm_slices(uint32_t max_slices, uint32_t total, const uint32_t *sl_off,
                                                          const uint32_t *perm, const uint2 *range, const uint32_t *entries,
                                                          const apt *aff, pt *slice_sum) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;

@@ -88,6 +88,38 @@ S256_D void fe_fold_top_vt(fe &out, uint32_t t0, uint32_t t1, uint32_t t2, uint3
         }
     }
 }
+// The same fold for a top word pair with a small t9 (<= 7): what the sum of two products leaves (fe_mul2add_core_w).  The
+// fast path adds t8 * delta + t9 * (977 << 32) + (t9 << 64) on limbs 0..2; a carry leaving limb 2 takes the slow path.
+S256_D void fe_fold_top2_vt(fe &out, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4, uint32_t t5,
+                            uint32_t t6, uint32_t t7, uint32_t t8, uint32_t t9) {
+    uint32_t c3, c3b, c3c;
+    uint32_t t9m = t9 * S256_DELTA_LO;
+    asm("mad.lo.cc.u32 %0,%4,%5,%6; madc.hi.cc.u32 %1,%4,%5,%7; addc.cc.u32 %2,%8,0; addc.u32 %3,0,0;"
+        : "=&r"(out.v[0]), "=&r"(out.v[1]), "=&r"(out.v[2]), "=&r"(c3)
+        : "r"(t8), "r"(S256_DELTA_LO), "r"(t0), "r"(t1), "r"(t2));
+    asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,%4; addc.u32 %2,0,0;" : "+r"(out.v[1]), "+r"(out.v[2]), "=r"(c3b) : "r"(t8), "r"(t9));
+    asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,0; addc.u32 %2,0,0;" : "+r"(out.v[1]), "+r"(out.v[2]), "=r"(c3c) : "r"(t9m));
+    out.v[3] = t3; out.v[4] = t4; out.v[5] = t5; out.v[6] = t6; out.v[7] = t7;
+    if (c3 | c3b | c3c) {  // rare: ripple the carries out of limb 2, then the wrap of a carry out of limb 7
+        uint32_t c;
+        c3 += c3b + c3c;
+        asm("add.cc.u32 %0,%0,%6; addc.cc.u32 %1,%1,0; addc.cc.u32 %2,%2,0; addc.cc.u32 %3,%3,0; addc.cc.u32 %4,%4,0;"
+            "addc.u32 %5,0,0;"
+            : "+r"(out.v[3]), "+r"(out.v[4]), "+r"(out.v[5]), "+r"(out.v[6]), "+r"(out.v[7]), "=r"(c)
+            : "r"(c3));
+        if (c) {  // out < 2^70 now; one more delta, no carry possible
+            asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,1; addc.u32 %2,%2,0;"
+                : "+r"(out.v[0]), "+r"(out.v[1]), "+r"(out.v[2])
+                : "r"(S256_DELTA_LO));
+        }
+    }
+}
+// r = a * b + c * d with one reduction
+S256_D void fe_mul2add_inline_vt(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) {
+    uint32_t w[9], t9;
+    fe_mul2add_core_w(w, t9, a.v, b.v, c.v, d.v);
+    fe_fold_top2_vt(r, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w[8], t9);
+}
 S256_D void fe_mul_inline_vt(fe &r, const fe &a, const fe &b) {
 #if !defined(S256_MUL_MERGED)
     uint32_t w[9], t9;
@@ -127,7 +159,23 @@ static __device__ __noinline__ fe fe_sqr_call_vt(fe a) {
 }
 S256_D void fe_mul_vt(fe &r, const fe &a, const fe &b) { r = fe_mul_call_vt(a, b); }
 S256_D void fe_sqr_vt(fe &r, const fe &a) { r = fe_sqr_call_vt(a); }
+#ifndef S256_NO_FUSED
+static __device__ __noinline__ fe fe_mul2add_call_vt(fe a, fe b, fe c, fe d) {
+    fe r;
+    fe_mul2add_inline_vt(r, a, b, c, d);
+    return r;
+}
+S256_D void fe_mul2add_vt(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) { r = fe_mul2add_call_vt(a, b, c, d); }
 #else
+S256_D void fe_mul2add_vt(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) {
+    fe t, u;
+    fe_mul_vt(t, a, b);
+    fe_mul_vt(u, c, d);
+    fe_add_vt(r, t, u);
+}
+#endif
+#else
+S256_D void fe_mul2add_vt(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) { fe_mul2add_inline_vt(r, a, b, c, d); }
 S256_D void fe_mul_vt(fe &r, const fe &a, const fe &b) { fe_mul_inline_vt(r, a, b); }
 S256_D void fe_sqr_vt(fe &r, const fe &a) { fe_sqr_inline_vt(r, a); }
 #endif
@@ -214,6 +262,12 @@ S256_HD void fe_add_vt(fe &r, const fe &a, const fe &b) { fe_add(r, a, b); }
 S256_HD void fe_sub_vt(fe &r, const fe &a, const fe &b) { fe_sub(r, a, b); }
 S256_HD void fe_mul_vt(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
 S256_HD void fe_sqr_vt(fe &r, const fe &a) { fe_sqr(r, a); }
+S256_HD void fe_mul2add_vt(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) {
+    fe t, u;
+    fe_mul(t, a, b);
+    fe_mul(u, c, d);
+    fe_add(r, t, u);
+}
 S256_HD void fe_mul_small_vt(fe &r, const fe &a, uint32_t k) { fe_mul_small(r, a, k); }
 S256_HD void fe_mul8_vt(fe &r, const fe &a) {
     fe t;
@@ -232,6 +286,19 @@ struct fe_ops<false> {
     S256_HD static void sub(fe &r, const fe &a, const fe &b) { fe_sub(r, a, b); }
     S256_HD static void mul(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
     S256_HD static void sqr(fe &r, const fe &a) { fe_sqr(r, a); }
+    // a b + c d and a b - c d: two products and an addition here; one fused call in the variable-time flavour
+    S256_HD static void mul2add(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) {
+        fe t, u;
+        fe_mul(t, a, b);
+        fe_mul(u, c, d);
+        fe_add(r, t, u);
+    }
+    S256_HD static void mul2sub(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) {
+        fe t, u;
+        fe_mul(t, a, b);
+        fe_mul(u, c, d);
+        fe_sub(r, t, u);
+    }
 #if S256_PTX && !defined(S256_B3_MULT)
     // 21a and 8a by shifts and adds with the branch-free fold (the constant-time flavour of fe_mul21_vt / fe_mul8_vt)
     S256_HD static void mul_small(fe &r, const fe &a, uint32_t k) {
@@ -266,6 +333,12 @@ struct fe_ops<true> {
     S256_HD static void sub(fe &r, const fe &a, const fe &b) { fe_sub_vt(r, a, b); }
     S256_HD static void mul(fe &r, const fe &a, const fe &b) { fe_mul_vt(r, a, b); }
     S256_HD static void sqr(fe &r, const fe &a) { fe_sqr_vt(r, a); }
+    S256_HD static void mul2add(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) { fe_mul2add_vt(r, a, b, c, d); }
+    S256_HD static void mul2sub(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) {
+        fe z = fe_zero(), nd;
+        fe_sub_vt(nd, z, d);
+        fe_mul2add_vt(r, a, b, c, nd);
+    }
 #if S256_PTX && !defined(S256_B3_MULT)
     S256_HD static void mul_small(fe &r, const fe &a, uint32_t k) {
         if (k == 21u) fe_mul21_vt(r, a); else fe_mul_small_vt(r, a, k);

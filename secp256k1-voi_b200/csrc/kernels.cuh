@@ -356,6 +356,10 @@ S256_HD void pt_fetch64(pt &r, const pt *p) {
 // public data, variable time as in the reference: the short-ripple field operations of fe_vt.cuh.  (The branch-free
 // set in this ladder: 22.74 ms against 21.55, k_dsm at 2^20 -- profiles/r02_variants.json.)
 constexpr bool DSM_VT = true;
+// (Tried and measured, k_dsm at 2^20: the two table rows of a step copied to shared memory with cp.async during the
+// doublings, the digits loaded one step ahead and the comb entry of the next window requested before the current
+// addition -- the long-scoreboard waits they remove are 6.9 % of the stall samples, but the extra live values spill
+// (236 -> 400 bytes of spill stores under the 128-register cap): 21.34 ms against 21.22-21.39 without.  Not kept.)
 S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
                       const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
     pt *T = tbl + i * (size_t)DSM_TS;
@@ -424,7 +428,10 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
                     fe z = fe_zero();
                     fe_ops<DSM_VT>::sub(q.y, z, q.y);
                 }
-                pt_add<DSM_VT>(acc, acc, q);
+                if (s == DSM_ND - 1 && h == 0)
+                    acc = q;  // the accumulator is still the identity: the first addition is an assignment
+                else
+                    pt_add<DSM_VT>(acc, acc, q);
             }
         }
     }

@@ -76,18 +76,10 @@ S256_HD void pt_add(pt &v, const pt &p, const pt &q) {
     F::add(z3, t1, t2);
     F::sub(t1, t1, t2);
     F::mul_small(y3, y3, S256_B3);
-    F::mul(x3, t4, y3);
-    F::mul(t2, t3, t1);
-    F::sub(x3, t2, x3);
-    F::mul(y3, y3, t0);
-    F::mul(t1, t1, z3);
-    F::add(y3, t1, y3);
-    F::mul(t0, t0, t3);
-    F::mul(z3, z3, t4);
-    F::add(z3, z3, t0);
-    v.x = x3;
-    v.y = y3;
-    v.z = z3;
+    // X3 = t3 t1 - t4 y3, Y3 = t1 z3 + y3 t0, Z3 = z3 t4 + t0 t3: three sums of two products
+    F::mul2sub(v.x, t3, t1, t4, y3);
+    F::mul2add(v.y, t1, z3, y3, t0);
+    F::mul2add(v.z, z3, t4, t0, t3);
 }
 
 // v = p + (x2, y2, 1); complete for every p, addend must not be the identity
@@ -113,18 +105,9 @@ S256_HD void pt_add_mixed(pt &v, const pt &p, const fe &x2, const fe &y2) {
     F::add(z3, t1, t2);
     F::sub(t1, t1, t2);
     F::mul_small(y3, y3, S256_B3);
-    F::mul(x3, t4, y3);
-    F::mul(t2, t3, t1);
-    F::sub(x3, t2, x3);
-    F::mul(y3, y3, t0);
-    F::mul(t1, t1, z3);
-    F::add(y3, t1, y3);
-    F::mul(t0, t0, t3);
-    F::mul(z3, z3, t4);
-    F::add(z3, z3, t0);
-    v.x = x3;
-    v.y = y3;
-    v.z = z3;
+    F::mul2sub(v.x, t3, t1, t4, y3);
+    F::mul2add(v.y, t1, z3, y3, t0);
+    F::mul2add(v.z, z3, t4, t0, t3);
 }
 
 // v = 2p, complete (6 M + 2 S + 1 m3b + 9 a).
@@ -137,15 +120,14 @@ S256_HD void pt_double(pt &v, const pt &p) {
     F::mul(t1, p.y, p.z);
     F::sqr(t2, p.z);
     F::mul_small(t2, t2, S256_B3);
-    F::mul(x3, t2, z3);
+    fe z8 = z3, t23;
     F::add(y3, t0, t2);
-    F::mul(z3, t1, z3);
+    F::mul(z3, t1, z8);
     F::add(t1, t2, t2);
-    F::add(t2, t1, t2);
-    F::sub(t0, t0, t2);
-    F::mul(y3, t0, y3);
-    F::add(y3, x3, y3);
-    F::mul(t1, p.x, p.y);
+    F::add(t23, t1, t2);
+    F::sub(t0, t0, t23);
+    F::mul(t1, p.x, p.y);          // (before v.y is written: v may alias p)
+    F::mul2add(y3, t2, z8, t0, y3);  // Y3 = t2 (8 Y^2) + (Y^2 - 3 t2)(Y^2 + t2)
     F::mul(x3, t0, t1);
     F::add(x3, x3, x3);
     v.x = x3;

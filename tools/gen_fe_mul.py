@@ -301,6 +301,75 @@ def build_reduce(p, after=None, deferred=(), thread_tail=False, o14=True):
     s.op("addc", "t9", 0, 0)
 
 
+def build_product_acc(p, C, D):
+    """E, O += C * D on top of a finished first product (every pair is live now, so every chain can carry out).
+    The carries are captured with selects (cA_i at limb i + 8, cB_i at limb i + 9) and added when H is formed -- a ripple
+    through all the live limbs above would put up to eight dependent adds behind every chain.
+    Returns {limb: [carry names]} for limbs 8..16."""
+    def pair(pos):
+        arr, k = acc_name(pos)
+        return f"{arr}{k}", f"{arr}{k + 1}"
+
+    owed = {}
+    for i in range(8):
+        for kind, js, nm in (("A", (0, 2, 4, 6), f"ca{i}"), ("B", (1, 3, 5, 7), f"cb{i}")):
+            s = p.stmt()
+            for n, j in enumerate(js):
+                lo, hi = pair(i + j)
+                s.op("mad.lo.cc" if n == 0 else "madc.lo.cc", lo, C[j], D[i], lo)
+                s.op("madc.hi.cc", hi, C[j], D[i], hi)
+            s.op("addc", nm, 0, 0)
+            owed.setdefault(i + js[-1] + 2, []).append(nm)
+    return owed
+
+
+def build_reduce2(p, owed):
+    """Reduction of a SUM of two products: H = hi(E) + hi(O) + owed carries has nine limbs (h8 <= 1 since the sum is below
+    2^513); h0..h7 go through the same chains as for one product, h8 * 2^256 * delta is added to the top word pair
+    (t8, t9), which the fold handles for any small t9."""
+    # The owed carries are never summed with each other (ptxas turns a sum of two captured flags into predicated constant
+    # moves on the multiplier's pipe): the A-chain carries (one per limb 8..15) join hi(E), the B-chain carries (one per
+    # limb 9..16) join hi(O), and the two sums are added.
+    ca = {limb: [n for n in names if n.startswith("ca")] for limb, names in owed.items()}
+    cb = {limb: [n for n in names if n.startswith("cb")] for limb, names in owed.items()}
+    assert all(len(ca.get(8 + k, [])) == 1 for k in range(8)) and all(len(cb.get(9 + k, [])) == 1 for k in range(8))
+    s = p.stmt()
+    for k in range(8):
+        s.op("add.cc" if k == 0 else "addc.cc", f"g{k}", f"e{8 + k}", ca[8 + k][0])
+    s.op("addc", "g8", 0, 0)
+    s = p.stmt()
+    for k in range(1, 8):
+        s.op("add.cc" if k == 1 else "addc.cc", f"q{k}", f"o{7 + k}", cb[8 + k][0])
+    s.op("addc", "q8", cb[16][0], 0)
+    # H = G + Q (q0 = o7)
+    s = p.stmt()
+    for k in range(8):
+        s.op("add.cc" if k == 0 else "addc.cc", f"h{k}", f"g{k}", "o7" if k == 0 else f"q{k}")
+    s.op("addc", "h8", "g8", "q8")
+    # from here on as for one product
+    s = p.stmt()
+    for n, k in enumerate((0, 2, 4, 6)):
+        s.op("madc.lo.cc" if n else "mad.lo.cc", f"e{k}", f"h{k}", 977, f"e{k}")
+        s.op("madc.hi.cc", f"e{k + 1}", f"h{k}", 977, f"e{k + 1}")
+    s.op("addc", "o7", 0, 0)
+    s = p.stmt()
+    for n, k in enumerate((1, 3, 5, 7)):
+        s.op("mad.lo.cc" if n == 0 else "madc.lo.cc", f"o{k - 1}", f"h{k}", 977, f"o{k - 1}")
+        s.op("madc.hi.cc" if k < 7 else "madc.hi", f"o{k}", f"h{k}", 977, f"o{k}")
+    s = p.stmt()
+    for k in range(1, 9):
+        a = f"e{k}" if k < 8 else 0
+        s.op("add.cc" if k == 1 else ("addc.cc" if k < 8 else "addc"), f"s{k}", a, f"o{k - 1}")
+    s = p.stmt()
+    for k in range(1, 9):
+        s.op("addc.cc" if k > 1 else "add.cc", f"s{k}", f"s{k}", f"h{k - 1}")
+    s.op("addc", "t9", 0, 0)
+    # + h8 * delta on (t8, t9): h8 * 977 <= 977, h8 <= 1
+    s = p.stmt()
+    s.op("mad.lo.cc", "s8", "h8", 977, "s8")
+    s.op("addc", "t9", "t9", "h8")
+
+
 def build_square(p, A):
     """E, O <- cross = sum_{i<j} a_i a_j 2^(32(i+j)) in split form, with no carry ever leaving a chain.
 
@@ -449,6 +518,31 @@ def main():
             assert out["t9"] <= 1
         progs[suffix] = (mul, sqr, mode)
 
+    # a * b + c * d with one reduction (wavefront form only: the shared body the variable-time formulas call)
+    Cn = [f"c{k}" for k in range(8)]
+    Dn = [f"d{k}" for k in range(8)]
+    fused = Prog()
+    build_product(fused, A, B, "ripple")
+    owed = build_product_acc(fused, Cn, Dn)
+    build_reduce2(fused, owed)
+    rnd = random.Random(11)
+    t9_max = 0
+    for n_, (x, y) in enumerate(cases):
+        z, w = cases[(n_ * 7 + 3) % len(cases)]
+        if n_ % 3 == 0:
+            z, w = rnd.getrandbits(256), rnd.getrandbits(256)
+        if n_ % 50 == 1:
+            x = y = z = w = 2**256 - 1
+        regs = {f"a{k}": v for k, v in enumerate(limbs(x))}
+        regs.update({f"b{k}": v for k, v in enumerate(limbs(y))})
+        regs.update({f"c{k}": v for k, v in enumerate(limbs(z))})
+        regs.update({f"d{k}": v for k, v in enumerate(limbs(w))})
+        out = fused.run(regs)
+        assert value_reduced(out) % P == (x * y + z * w) % P, (hex(x), hex(y), hex(z), hex(w))
+        assert out["h8"] <= 1
+        t9_max = max(t9_max, out["t9"])
+    assert t9_max <= 3
+
     def cn(prefix_map):
         def f(r):
             for pre, fmt in prefix_map.items():
@@ -498,6 +592,36 @@ __device__ __forceinline__ void fe_sqr_core{suffix}(uint32_t r[9], uint32_t &t9,
     uint32_t {decl_o};
     uint32_t {decl_h}, x14, y14, y15;
 {sqr.emit(names)}
+    r[0] = e0;
+}}
+'''
+    names4 = cn({"a": "a[{}]", "b": "b[{}]", "c": "c[{}]", "d": "d[{}]", "s": "r[{}]"})
+    # register names of the fused program that collide with the operand prefixes are renamed for emission
+    def ren(r):
+        if r is None or isinstance(r, int):
+            return r
+        if r[0] == "c" and r[1] in "ab":        # captured carries ca0.. / cb0..
+            return "k" + r[1:]
+        if r[0] == "d" and r[1:].isdigit() and int(r[1:]) >= 8:   # owed sums d9..d15 (d0..d7 are operand limbs)
+            return "w" + r[1:]
+        return r
+    for st in fused.stmts:
+        st.ops = [(nm, ren(dst), tuple(ren(x) for x in src)) for nm, dst, src in st.ops]
+    decl_k = ", ".join([f"ka{i}" for i in range(8)] + [f"kb{i}" for i in range(8)])
+    decl_w = ", ".join(f"q{i}" for i in range(1, 9))
+    decl_g = ", ".join(f"g{i}" for i in range(9))
+    hdr += f'''
+// r + 2^256 (r[8] + 2^32 t9) == a * b + c * d (mod p) with ONE reduction ({wide(fused)} wide multiplications instead of 2 x {wide(mul0)}), t9 <= 3.
+// The complete formulas end in three such sums (X3, Y3, Z3); fewer calls and fewer reduction tails is what the
+// latency-bound ladders gain from it.
+__device__ __forceinline__ void fe_mul2add_core_w(uint32_t r[9], uint32_t &t9, const uint32_t a[8], const uint32_t b[8],
+                                                  const uint32_t c[8], const uint32_t d[8]) {{
+    uint32_t {decl_e};
+    uint32_t {decl_o};
+    uint32_t {decl_h}, h8;
+    uint32_t {decl_k};
+    uint32_t {decl_w}, {decl_g};
+{fused.emit(names4)}
     r[0] = e0;
 }}
 '''
