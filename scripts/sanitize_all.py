@@ -30,7 +30,27 @@ for n in (1, 33, 1500):
 wm = pkg.synth.msm_batch(6000, eng.scalar_base_mult)
 eng.msm(wm["k32"], wm["pt65"])
 eng.msm(np.tile(wm["k32"][:1], (6000, 1)), wm["pt65"])
+# round 2: the device-resident and sharded MSM entry points (a one-rank communicator still runs pack -> ncclAllGather ->
+# fold), a mid-size MSM (short slices + the parallel bucket fold), back-to-back calls on two streams
+import torch
+dk, dp = torch.from_numpy(wm["k32"]).cuda(), torch.from_numpy(wm["pt65"]).cuda()
+eng.msm(dk, dp)
+eng.comm_init(pkg.Engine.comm_unique_id(), 0, 1)
+eng.msm_sharded(wm["k32"], wm["pt65"]); eng.msm_sharded(dk, dp)
+eng.comm_free()
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+d = [torch.from_numpy(w[k]).cuda() for k in ("pk65", "digest32", "sig64")]
+with torch.cuda.stream(s1):
+    a = eng.ecdsa_verify(*d)
+with torch.cuda.stream(s2):
+    b = eng.ecdsa_verify(*d)
+torch.cuda.synchronize()
+assert np.array_equal(a.cpu().numpy(), w["expected"]) and np.array_equal(b.cpu().numpy(), w["expected"])
 eng.close()
+mid = pkg.Engine(device=0, max_batch=1 << 16)
+wmid = pkg.synth.msm_batch(1 << 16, mid.scalar_base_mult)
+mid.msm(wmid["k32"], wmid["pt65"])
+mid.close()
 if os.environ.get("SANITIZE_BIG", "1") == "1":
     # the three-part host pipeline of ecdsa_verify and the four-part one of the other entry points
     n = 1 << 18
