@@ -1,10 +1,10 @@
 """F_p multiplication probes: dependent products per second for the ladders'
-IMAD.WIDE multiplier (out of line / inlined) and the FP64-pipe experiment of csrc/fe52.cuh."""
+IMAD.WIDE multiplier, out of line and inlined."""
 import importlib, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("secp256k1-voi_b200")
 eng = pkg.Engine(device=0, max_batch=1024)
-names = ["fe_mul 8x32 IMAD.WIDE, out of line (as in k_dsm)", "fe_mul 8x32 IMAD.WIDE, inlined", "fe52_mul 5x52 DFMA (experiment)"]
+names = ["fe_mul 8x32 IMAD.WIDE, out of line (as in k_dsm)", "fe_mul 8x32 IMAD.WIDE, inlined"]
 out = {}
 for form, nm in enumerate(names):
     best = max(eng.microbench_fe_mul(form, 2048)[0] for _ in range(3))

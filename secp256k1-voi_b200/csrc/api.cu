@@ -6,7 +6,6 @@
 // device every entry point fails with S256_ERR_NO_DEVICE.
 #include "ctx.h"
 #include "microbench.cuh"
-#include "fe52.cuh"
 
 // ---------------------------------------------------------------------------
 // __global__ wrappers
@@ -1073,33 +1072,13 @@ extern "C" int s256_microbench_imad(s256_ctx *ctx, int iters, double *mac32_per_
 
 // Field-multiplication probes: dependent products in two interleaved chains, the
 // instruction-level parallelism a point formula offers.  form 0: fe_mul as the ladders call it (8x32 limbs,
-// IMAD.WIDE carry chains, out of line); 1: the same inlined; 2: fe52_mul (5x52 limbs on the FP64 pipe, fe52.cuh).
+// IMAD.WIDE carry chains, out of line); 1: the same inlined.  (Form 2 was the 5x52-limb FP64-pipe experiment of round 1:
+// parity with the integer multiplier, not adopted, removed in round 2 -- DESIGN.md section 5.)
 template <int FORM>
 __global__ void __launch_bounds__(128, 4) k_femul_probe(uint32_t seed, int iters, unsigned long long *sink) {
     uint32_t a = seed ^ (threadIdx.x * 2654435761u), b = seed + blockIdx.x * 40503u + 1u;
     unsigned long long acc = 0;
-    if (FORM == 2) {
-        fe52 x1, y1, x2, y2;
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            x1.v[k] = (double)(a + 7u * k);
-            y1.v[k] = (double)(b + 11u * k);
-            x2.v[k] = (double)(a ^ (0x9e3779b9u * (k + 1)));
-            y2.v[k] = (double)(b ^ (0x85ebca6bu * (k + 1)));
-        }
-#pragma unroll 1
-        for (int it = 0; it < iters; it++) {
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                fe52_mul(x1, x1, y1);
-                fe52_mul(x2, x2, y2);
-                fe52_mul(y1, y1, x2);
-                fe52_mul(y2, y2, x1);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 5; k++) acc ^= fe52_bits(x1.v[k]) ^ fe52_bits(y1.v[k]) ^ fe52_bits(x2.v[k]) ^ fe52_bits(y2.v[k]);
-    } else {
+    {
         fe x1, y1, x2, y2;
 #pragma unroll
         for (int k = 0; k < 8; k++) {
@@ -1136,9 +1115,9 @@ static void launch_femul_probe(int blocks, int iters, cudaStream_t s, unsigned l
 }
 extern "C" int s256_microbench_fe_mul(s256_ctx *ctx, int form, int iters, double *muls_per_s, double *ms_out) {
     ENTER(ctx);
-    if (iters < 1 || form < 0 || form > 2) return S256_ERR_ARG;
+    if (iters < 1 || form < 0 || form > 1) return S256_ERR_ARG;
     typedef void (*fn_t)(int, int, cudaStream_t, unsigned long long *);
-    static const fn_t fns[3] = {launch_femul_probe<0>, launch_femul_probe<1>, launch_femul_probe<2>};
+    static const fn_t fns[2] = {launch_femul_probe<0>, launch_femul_probe<1>};
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
