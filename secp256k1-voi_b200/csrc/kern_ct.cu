@@ -81,7 +81,11 @@ __global__ void __launch_bounds__(S256_TPB, S256_BM_MINB)
     if (live && part == 0) res[item] = acc;
 }
 
+static int g_sm_count = 148;  // B200; replaced by the device's own count at init
 void s256_ct_kernels_init() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+        g_sm_count = sms;
     cudaFuncSetAttribute(k_base_mult_ct_split<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_SMALL);
     cudaFuncSetAttribute(k_base_mult_ct_split<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_SMALL);
     cudaFuncSetAttribute(k_base_mult_ct_split<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_SMALL);
@@ -127,7 +131,7 @@ void s256_launch_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_big, 
         return;
     }
     size_t warps = (n + 31) / 32;
-    unsigned maxg = 148u * S256_BM_MINB_BIG;
+    unsigned maxg = (unsigned)g_sm_count * S256_BM_MINB_BIG;
     unsigned grid = warps < maxg ? (unsigned)warps : maxg;
     k_base_mult_ct<<<grid, S256_TPB_BIG, CT_BYTES_BIG, s>>>(k32, n, tab_big, res);
 }
