@@ -219,11 +219,11 @@ __global__ void __launch_bounds__(S256_TPB, S256_SM_MINB)
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
 #ifdef S256_CT_TABLE_GLOBAL
-    CtTableGlobal T{tbl + i * (size_t)DSM_TS};
+    CtTableGlobal T{tbl + i * (size_t)DSM_TSTRIDE};
 #else
     CtTableShared<S256_TPB> T{threadIdx.x};
 #endif
-    item_scalar_mult_ct_affine(i, aff, k32, T, tbl + i * (size_t)DSM_TS, res);
+    item_scalar_mult_ct_affine(i, aff, k32, T, tbl + i * (size_t)DSM_TSTRIDE, res);
 }
 #ifdef S256_CT_TABLE_GLOBAL
 constexpr size_t CT_SMEM_BYTES = 0;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a3
                                                        uint8_t *out32) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (op < 16) {
+    if (op < 16 || op >= 20) {
         fe a, b, r;
         fe_from_be32(a, a32 + 32 * i);
         fe_from_be32(b, b32 + 32 * i);
@@ -284,6 +284,10 @@ __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a3
             case 13: fe_mul_small_vt(r, a, 21u); break;
             case 14: fe_sqr_vt(r, a); break;
             case 15: fe_mul8_vt(r, a); break;
+            case 20: fe_mul2_vt(r, a); break;
+            case 21: fe_mul3_vt(r, a); break;
+            case 22: fe_sub2_vt(r, a, b); break;
+            case 23: fe_submul8_vt(r, a, b); break;
             default: r = fe_zero();
         }
         fe_normalize(r, r);
@@ -367,7 +371,7 @@ static int ctx_alloc(s256_ctx *ctx) {
     CK(cudaMalloc(&ctx->sfl, cap));
     CK(cudaMalloc(&ctx->pvalid, cap));
     CK(cudaMalloc(&ctx->cstat, cap));
-    CK(cudaMalloc(&ctx->tbl, sizeof(pt) * DSM_TS * cap));
+    CK(cudaMalloc(&ctx->tbl, sizeof(pt) * DSM_TSTRIDE * cap));
     CK(cudaMalloc(&ctx->res, sizeof(pt) * cap));
     CK(cudaMalloc(&ctx->in_a, 65 * cap));
     CK(cudaMalloc(&ctx->in_c, 65 * cap));
@@ -1171,17 +1175,45 @@ extern "C" int s256_debug_ladder_add_count(s256_ctx *ctx, size_t n, uint64_t *ad
     return check_launch(ctx);
 }
 // executed MAC32 of one k_dsm item given its measured number of ladder additions (both halves) and beta multiplications
-extern "C" double s256_mac32_k_dsm(double adds_per_item, double beta_muls_per_item) {
+// The Jacobian ladder (jac.cuh): doubling 2 M + 5 S (or 3 M + 4 S), mixed addition 6 M + 3 S + one fused pair, the table's
+// normalisation (suffix products, one safegcd inversion, 5 M + S per row) and the conversion of the result.
+struct dsm_costs {
+    double dbl, add, mix, table, tail;
+};
+static dsm_costs dsm_cost_model() {
     const double M = 73, S = 45;
 #ifndef S256_NO_FUSED
     const double F2 = 137;  // a b + c d with one reduction: 128 + 8 + 1
-    const double dbl = 4 * M + 2 * S + F2, add = 6 * M + 3 * F2, mix = 5 * M + 3 * F2;
 #else
-    const double dbl = 6 * M + 2 * S, add = 12 * M, mix = 11 * M;
+    const double F2 = 2 * M;
 #endif
+    dsm_costs c;
+#if defined(S256_DSM_JAC)
+#ifndef S256_JDBL_3M4S
+    c.dbl = 2 * M + 5 * S;
+#else
+    c.dbl = 3 * M + 4 * S;
+#endif
+    c.mix = 6 * M + 3 * S + F2;
+    c.add = c.mix;  // the ladder adds affine rows
+    const double inv_fe = 20 * 90;
+    c.table = (DSM_TS / 2) * c.dbl + (DSM_TS / 2 - 1) * c.mix + (DSM_TS - 2) * M + inv_fe + (DSM_TS - 2) * (5 * M + S) + (3 * M + S);
+    c.tail = 2 * M + S;
+#else
+#ifndef S256_NO_FUSED
+    c.dbl = 4 * M + 2 * S + F2, c.add = 6 * M + 3 * F2, c.mix = 5 * M + 3 * F2;
+#else
+    c.dbl = 6 * M + 2 * S, c.add = 12 * M, c.mix = 11 * M;
+#endif
+    c.table = (DSM_TS / 2) * c.dbl + (DSM_TS / 2 - 1) * c.mix;
+    c.tail = 0;
+#endif
+    return c;
+}
+extern "C" double s256_mac32_k_dsm(double adds_per_item, double beta_muls_per_item) {
+    const dsm_costs c = dsm_cost_model();
     // (the very first addition of the ladder is an assignment; bench.py subtracts it from the measured count)
-    return (DSM_TS / 2) * dbl + (DSM_TS / 2 - 1) * mix + (DSM_ND - 1) * DSM_W * dbl + adds_per_item * add +
-           beta_muls_per_item * M + COMB_NW * mix;
+    return c.table + (DSM_ND - 1) * DSM_W * c.dbl + adds_per_item * c.add + beta_muls_per_item * 73 + COMB_NW * c.mix + c.tail;
 }
 
 // MAC32 (32x32->64 multiply-accumulates, i.e. IMAD.WIDE issues) per item as EXECUTED:
@@ -1202,12 +1234,12 @@ extern "C" double s256_mac32_per_item(const char *name) {
     // inversions are safegcd (modinv.cuh): 20 batches x (54 + 36) 32x32->64 products, whatever the modulus
     const double inv_fe = 20 * 90, sqrt_fe = 254 * S + 13 * M + 2 * S + M, inv_sc = 20 * 90;
     const double oncurve = 2 * S + M;
-    const double table = (DSM_TS / 2) * dbl + (DSM_TS / 2 - 1) * mix;
+    const dsm_costs dc = dsm_cost_model();
     const double adds_per_half = (DSM_ND - 1) * (1.0 - 1.0 / (1 << DSM_W)) + 15.0 / 16.0;
     // (the first addition of the first half is an assignment: the accumulator is still the identity)
-    const double ladder = (DSM_ND - 1) * DSM_W * dbl + (2 * adds_per_half - 15.0 / 16.0) * add + adds_per_half * M;
-    const double comb = COMB_NW * mix;
-    const double dsm = table + ladder + comb;
+    const double ladder = (DSM_ND - 1) * DSM_W * dc.dbl + (2 * adds_per_half - 15.0 / 16.0) * dc.add + adds_per_half * M;
+    const double comb = COMB_NW * dc.mix;
+    const double dsm = dc.table + ladder + comb + dc.tail;
     const double split = 3 * ZN + 2 * 64;
     const double affine = (3 + 2) * M + inv_fe / INV_K;
     std::string s(name ? name : "");

@@ -120,7 +120,7 @@ static inline view view_at(const s256_ctx *ctx, size_t off) {
     v.sfl = ctx->sfl + off;
     v.pvalid = ctx->pvalid + off;
     v.cstat = ctx->cstat + off;
-    v.tbl = ctx->tbl + (size_t)DSM_TS * off;
+    v.tbl = ctx->tbl + (size_t)DSM_TSTRIDE * off;
     v.res = ctx->res + off;
     v.in_a = ctx->in_a + 65 * off;
     v.in_b = ctx->in_b + 32 * off;

@@ -256,6 +256,65 @@ S256_D void fe_mul8_vt(fe &r, const fe &a) {
     }
 }
 
+// ---- small multiples fused with the neighbouring addition / subtraction (Jacobian formulas, jac.cuh) ----
+// Each replaces two or three carry chains of dependent adds by one: the multiple is formed with funnel shifts
+// (independent of each other), the bits shifted out of limb 7 and the chain's carry / borrow are folded together.
+// r -= k * delta for a small k (k * 977 fits a word): three subtractions on limbs 0..2, the rest behind a branch
+S256_D void fe_fold_borrow_k_vt(fe &r, uint32_t k) {
+    uint32_t t = k * S256_DELTA_LO, b3;
+    asm("sub.cc.u32 %0,%0,%4; subc.cc.u32 %1,%1,%5; subc.cc.u32 %2,%2,0; subc.u32 %3,0,0;"
+        : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "=r"(b3)
+        : "r"(t), "r"(k));
+    if (b3) {
+        uint32_t bw2;
+        asm("sub.cc.u32 %0,%0,1; subc.cc.u32 %1,%1,0; subc.cc.u32 %2,%2,0; subc.cc.u32 %3,%3,0; subc.cc.u32 %4,%4,0;"
+            "subc.u32 %5,0,0;"
+            : "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]), "+r"(r.v[7]), "=r"(bw2));
+        if (bw2) {  // wrapped again: r >= 2^256 - k * delta now, subtracting delta cannot borrow
+            asm("sub.cc.u32 %0,%0,%8; subc.cc.u32 %1,%1,1; subc.cc.u32 %2,%2,0; subc.cc.u32 %3,%3,0;"
+                "subc.cc.u32 %4,%4,0; subc.cc.u32 %5,%5,0; subc.cc.u32 %6,%6,0; subc.u32 %7,%7,0;"
+                : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]),
+                  "+r"(r.v[7])
+                : "r"(S256_DELTA_LO));
+        }
+    }
+}
+// x = a << s (limbs), returns the s bits shifted out
+template <int SH>
+S256_D uint32_t fe_shl_limbs(uint32_t x[8], const fe &a) {
+#pragma unroll
+    for (int i = 7; i >= 1; i--) x[i] = __funnelshift_l(a.v[i - 1], a.v[i], SH);
+    x[0] = a.v[0] << SH;
+    return a.v[7] >> (32 - SH);
+}
+// r = 2a
+S256_D void fe_mul2_vt(fe &r, const fe &a) {
+    uint32_t x[8];
+    uint32_t top = fe_shl_limbs<1>(x, a);
+    fe_fold_small_vt(r, x, top);
+}
+// r = 3a = a + 2a
+S256_D void fe_mul3_vt(fe &r, const fe &a) {
+    fe x, e;
+    uint32_t top = fe_shl_limbs<1>(x.v, a);
+    uint32_t c = fe_add_raw(e, a, x);
+    fe_fold_small_vt(r, e.v, top + c);
+}
+// r = a - 2b
+S256_D void fe_sub2_vt(fe &r, const fe &a, const fe &b) {
+    fe x;
+    uint32_t top = fe_shl_limbs<1>(x.v, b);
+    uint32_t bw = fe_sub_raw(r, a, x);
+    fe_fold_borrow_k_vt(r, top + (bw & 1u));
+}
+// r = a - 8b
+S256_D void fe_submul8_vt(fe &r, const fe &a, const fe &b) {
+    fe x;
+    uint32_t top = fe_shl_limbs<3>(x.v, b);
+    uint32_t bw = fe_sub_raw(r, a, x);
+    fe_fold_borrow_k_vt(r, top + (bw & 1u));
+}
+
 #else  // portable: one implementation serves both flavours
 
 S256_HD void fe_add_vt(fe &r, const fe &a, const fe &b) { fe_add(r, a, b); }
@@ -274,6 +333,23 @@ S256_HD void fe_mul8_vt(fe &r, const fe &a) {
     fe_add(t, a, a);
     fe_add(t, t, t);
     fe_add(r, t, t);
+}
+
+S256_HD void fe_mul2_vt(fe &r, const fe &a) { fe_add(r, a, a); }
+S256_HD void fe_mul3_vt(fe &r, const fe &a) {
+    fe t;
+    fe_add(t, a, a);
+    fe_add(r, t, a);
+}
+S256_HD void fe_sub2_vt(fe &r, const fe &a, const fe &b) {
+    fe t;
+    fe_sub(t, a, b);
+    fe_sub(r, t, b);
+}
+S256_HD void fe_submul8_vt(fe &r, const fe &a, const fe &b) {
+    fe t;
+    fe_mul8_vt(t, b);
+    fe_sub(r, a, t);
 }
 
 #endif
@@ -326,6 +402,22 @@ struct fe_ops<false> {
         fe_add(r, t, t);
     }
 #endif
+    S256_HD static void mul2(fe &r, const fe &a) { fe_add(r, a, a); }
+    S256_HD static void mul3(fe &r, const fe &a) {
+        fe t;
+        fe_add(t, a, a);
+        fe_add(r, t, a);
+    }
+    S256_HD static void sub2(fe &r, const fe &a, const fe &b) {
+        fe t;
+        fe_sub(t, a, b);
+        fe_sub(r, t, b);
+    }
+    S256_HD static void submul8(fe &r, const fe &a, const fe &b) {
+        fe t;
+        mul8(t, b);
+        fe_sub(r, a, t);
+    }
 };
 template <>
 struct fe_ops<true> {
@@ -347,6 +439,29 @@ struct fe_ops<true> {
     S256_HD static void mul_small(fe &r, const fe &a, uint32_t k) { fe_mul_small_vt(r, a, k); }
 #endif
     S256_HD static void mul8(fe &r, const fe &a) { fe_mul8_vt(r, a); }
+#ifndef S256_NO_FUSED_SMALL
+    S256_HD static void mul2(fe &r, const fe &a) { fe_mul2_vt(r, a); }
+    S256_HD static void mul3(fe &r, const fe &a) { fe_mul3_vt(r, a); }
+    S256_HD static void sub2(fe &r, const fe &a, const fe &b) { fe_sub2_vt(r, a, b); }
+    S256_HD static void submul8(fe &r, const fe &a, const fe &b) { fe_submul8_vt(r, a, b); }
+#else
+    S256_HD static void mul2(fe &r, const fe &a) { fe_add_vt(r, a, a); }
+    S256_HD static void mul3(fe &r, const fe &a) {
+        fe t;
+        fe_add_vt(t, a, a);
+        fe_add_vt(r, t, a);
+    }
+    S256_HD static void sub2(fe &r, const fe &a, const fe &b) {
+        fe t;
+        fe_sub_vt(t, a, b);
+        fe_sub_vt(r, t, b);
+    }
+    S256_HD static void submul8(fe &r, const fe &a, const fe &b) {
+        fe t;
+        fe_mul8_vt(t, b);
+        fe_sub_vt(r, a, t);
+    }
+#endif
 };
 
 }  // namespace s256

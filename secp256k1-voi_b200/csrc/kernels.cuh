@@ -15,6 +15,7 @@
 #pragma once
 #include "fe.cuh"
 #include "point.cuh"
+#include "jac.cuh"
 #include "sc.cuh"
 #include "sha256.cuh"
 
@@ -27,6 +28,17 @@ namespace s256 {
 constexpr int DSM_W = S256_W;
 constexpr int DSM_ND = glv_recode<DSM_W>::ND;  // digits per 128-bit half
 constexpr int DSM_TS = 1 << (DSM_W - 1);       // table entries 1..TS
+// The verification ladder runs in Jacobian coordinates over an AFFINE per-item table (jac.cuh) unless S256_DSM_RCB
+// asks for the round-1 form (complete projective formulas, projective table).  Per-item table scratch in units of
+// sizeof(pt): the Jacobian build keeps the affine entry of P (64 B), the Jacobian multiples 2..TS (96 B each) and the
+// suffix products of their Z's for the shared inversion (32 B each) side by side, then overwrites the front with the
+// TS affine entries the ladder reads.
+#ifndef S256_DSM_RCB
+#define S256_DSM_JAC 1
+constexpr int DSM_TSTRIDE = (64 + (DSM_TS - 1) * 96 + (DSM_TS - 2) * 32 + 95) / 96;
+#else
+constexpr int DSM_TSTRIDE = DSM_TS;
+#endif
 // fixed-base comb for the G half of the verification ladder: COMB_NW windows of COMB_WB bits, SIGNED
 // digits in [-(2^(WB-1) - 1), 2^(WB-1)], entries (j + 1) * 2^(WB*w) * G for j = 0 .. 2^(WB-1) - 1.
 // No doublings, one mixed addition per window, so wider windows are fewer additions and the only
@@ -360,6 +372,148 @@ constexpr bool DSM_VT = true;
 // doublings, the digits loaded one step ahead and the comb entry of the next window requested before the current
 // addition -- the long-scoreboard waits they remove are 6.9 % of the stall samples, but the extra live values spill
 // (236 -> 400 bytes of spill stores under the 128-register cap): 21.34 ms against 21.22-21.39 without.  Not kept.)
+#if defined(S256_DSM_JAC)
+// an affine table row as eight 64-bit loads
+S256_HD void apt_fetch64(apt &r, const apt *p) {
+#if defined(__CUDA_ARCH__) && !defined(S256_DSM_LD32)
+    const uint2 *q = reinterpret_cast<const uint2 *>(p);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint2 a = q[k], b = q[4 + k];
+        r.x.v[2 * k] = a.x; r.x.v[2 * k + 1] = a.y;
+        r.y.v[2 * k] = b.x; r.y.v[2 * k + 1] = b.y;
+    }
+#else
+    r = *p;
+#endif
+}
+// Jacobian form (jac.cuh).  Table: [2..TS]P in Jacobian coordinates by doublings and mixed additions, then ONE
+// inversion per item (Montgomery's trick over the TS - 1 Z's, safegcd) turns it into TS affine rows, so that every
+// ladder addition is a mixed one.  Layout of the item's scratch (bytes): [0, 64) P; [64, 64 + 96 (TS - 1)) the
+// Jacobian multiples 2..TS; then the suffix products Z_k ... Z_TS for k = 3..TS.  The affine rows overwrite the front
+// in ascending order: row k ends at 64 k, the first Jacobian multiple still needed (k + 1) starts at 64 + 96 (k - 1).
+S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
+                      const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
+    char *base = reinterpret_cast<char *>(tbl + i * (size_t)DSM_TSTRIDE);
+    apt *A = reinterpret_cast<apt *>(base);
+    {
+        pt *J = reinterpret_cast<pt *>(base + 64);                          // J[k - 2] = k P
+        fe *C = reinterpret_cast<fe *>(base + 64 + 96 * (DSM_TS - 1));      // C[k - 3] = Z_k Z_(k+1) ... Z_TS
+        apt P = aff[i];
+        A[0] = P;
+        pt cur;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int k = 2; k <= DSM_TS; k += 2) {
+            pt h;
+            if (k == 2)
+                pt_from_affine(h, P);
+            else
+                h = J[k / 2 - 2];
+            jac_double<DSM_VT>(cur, h);
+            J[k - 2] = cur;
+            if (k < DSM_TS) {
+                jac_add_mixed_nocheck<DSM_VT>(cur, cur, P.x, P.y);
+                J[k - 1] = cur;
+            }
+        }
+        fe run = cur.z;  // Z_TS
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int k = DSM_TS - 1; k >= 2; k--) {
+            C[k + 1 - 3] = run;
+            fe zk = J[k - 2].z;
+            fe_ops<DSM_VT>::mul(run, run, zk);
+        }
+        fe inv;  // (Z_2 ... Z_TS)^-1, then (Z_k ... Z_TS)^-1 as k advances
+        fe_invert(inv, run);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int k = 2; k <= DSM_TS; k++) {
+            pt jk = J[k - 2];
+            fe zi = inv, zi2;
+            if (k < DSM_TS) {
+                fe ck = C[k + 1 - 3];
+                fe_ops<DSM_VT>::mul(zi, inv, ck);      // Z_k^-1
+                fe_ops<DSM_VT>::mul(inv, inv, jk.z);
+            }
+            apt a;
+            fe_ops<DSM_VT>::sqr(zi2, zi);
+            fe_ops<DSM_VT>::mul(a.x, jk.x, zi2);
+            fe_ops<DSM_VT>::mul(zi2, zi2, zi);
+            fe_ops<DSM_VT>::mul(a.y, jk.y, zi2);
+            A[k - 1] = a;
+        }
+    }
+    uint32_t fl = sfl[i];
+    pt acc;
+    pt_set_identity(acc);
+    uint32_t inf = 1u;
+    const fe beta = fe_beta();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int s = DSM_ND - 1; s >= 0; s--) {
+        // digits first: their loads and the table rows' trip from L2 overlap the doublings
+        int da = dig1[(size_t)s * n + i];
+        int db = dig2[(size_t)s * n + i];
+#if defined(__CUDA_ARCH__) && !defined(S256_DSM_NO_PREFETCH)
+        {
+            int ma = da < 0 ? -da : da, mb = db < 0 ? -db : db;
+            if (ma) asm volatile("prefetch.global.L1 [%0];" ::"l"(A + (ma - 1)));
+            if (mb) asm volatile("prefetch.global.L1 [%0];" ::"l"(A + (mb - 1)));
+        }
+#endif
+        if (s != DSM_ND - 1) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int k = 0; k < DSM_W; k++) jac_double<DSM_VT>(acc, acc);
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+        for (int h = 0; h < 2; h++) {
+            int d = h ? db : da;
+            if (d != 0) {
+                uint32_t neg = (uint32_t)(d < 0) ^ ((fl >> (1 + h)) & 1u);
+                int mag = d < 0 ? -d : d;
+                apt q;
+                apt_fetch64(q, A + (mag - 1));
+                if (h) fe_ops<DSM_VT>::mul(q.x, q.x, beta);
+                if (neg) {
+                    fe z = fe_zero();
+                    fe_ops<DSM_VT>::sub(q.y, z, q.y);
+                }
+                jac_add_mixed_var<DSM_VT>(acc, inf, q.x, q.y);
+            }
+        }
+    }
+    sc u1 = u1s[i];
+    uint32_t carry = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int w = 0; w < COMB_NW; w++) {
+        int32_t d = comb_digit(u1, w, carry);
+        if (d != 0) {
+            uint32_t mag = (uint32_t)(d < 0 ? -d : d);
+            apt g = comb[(size_t)w * COMB_SZ + (mag - 1u)];
+            if (d < 0) {
+                fe z = fe_zero();
+                fe_ops<DSM_VT>::sub(g.y, z, g.y);
+            }
+            jac_add_mixed_var<DSM_VT>(acc, inf, g.x, g.y);
+        }
+    }
+    pt out;
+    jac_to_projective<DSM_VT>(out, acc, inf);
+    res[i] = out;
+}
+#else
 S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
                       const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
     pt *T = tbl + i * (size_t)DSM_TS;
@@ -454,6 +608,8 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
     }
     res[i] = acc;
 }
+
+#endif
 
 // ---------------------------------------------------------------------------
 // ECDSA finish (secec/ecdsa.go:450-467) without leaving projective space:

@@ -56,7 +56,7 @@ struct scratch {
     std::vector<uint8_t> sfl, pvalid, cstat;
     std::vector<pt> tbl, res;
     explicit scratch(size_t n)
-        : aff(n), u1(n), dig1(n * DSM_ND), dig2(n * DSM_ND), sfl(n), pvalid(n), cstat(n), tbl(n * DSM_TS), res(n) {}
+        : aff(n), u1(n), dig1(n * DSM_ND), dig2(n * DSM_ND), sfl(n), pvalid(n), cstat(n), tbl(n * DSM_TSTRIDE), res(n) {}
 };
 
 static void run_dsm(scratch &s, size_t n) {
@@ -139,8 +139,8 @@ EXPORT void sim_scalar_mult(const uint8_t *k32, const uint8_t *pt65, size_t n, i
     scratch s(n);
     for (size_t i = 0; i < n; i++) s.pvalid[i] = item_decode_uncompressed(s.aff[i], pt65 + 65 * i);
     for (size_t i = 0; i < n; i++) {
-        CtTableGlobal T{s.tbl.data() + i * (size_t)DSM_TS};
-        item_scalar_mult_ct_affine(i, s.aff.data(), k32, T, s.tbl.data() + i * (size_t)DSM_TS, s.res.data());
+        CtTableGlobal T{s.tbl.data() + i * (size_t)DSM_TSTRIDE};
+        item_scalar_mult_ct_affine(i, s.aff.data(), k32, T, s.tbl.data() + i * (size_t)DSM_TSTRIDE, s.res.data());
     }
     run_finish(s, n, true, false, mode, out, status, nullptr);
 }
@@ -171,8 +171,8 @@ EXPORT void sim_msm(const uint8_t *k32, const uint8_t *pt65, size_t n, int varti
     pt_set_identity(acc);
     if (n && (!vartime || n < 32) && force_c == 0) {
         for (size_t i = 0; i < n; i++) {
-            CtTableGlobal T{s.tbl.data() + i * (size_t)DSM_TS};
-            item_scalar_mult_ct_affine(i, s.aff.data(), k32, T, s.tbl.data() + i * (size_t)DSM_TS, s.res.data());
+            CtTableGlobal T{s.tbl.data() + i * (size_t)DSM_TSTRIDE};
+            item_scalar_mult_ct_affine(i, s.aff.data(), k32, T, s.tbl.data() + i * (size_t)DSM_TSTRIDE, s.res.data());
         }
         for (size_t i = 0; i < n; i++) pt_add(acc, acc, s.res[i]);
     } else if (n) {
@@ -349,7 +349,7 @@ EXPORT void sim_gen_table(int wbits, int nwin, uint8_t *out) {
 }
 EXPORT void sim_field_op(int op, const uint8_t *a32, const uint8_t *b32, size_t n, uint8_t *out32) {
     for (size_t i = 0; i < n; i++) {
-        if (op < 16) {
+        if (op < 16 || op >= 20) {
             fe a, b, r;
             fe_from_be32(a, a32 + 32 * i);
             fe_from_be32(b, b32 + 32 * i);
@@ -368,6 +368,10 @@ EXPORT void sim_field_op(int op, const uint8_t *a32, const uint8_t *b32, size_t 
                 case 13: fe_mul_small_vt(r, a, 21u); break;
                 case 14: fe_sqr_vt(r, a); break;
                 case 15: fe_mul8_vt(r, a); break;
+                case 20: fe_mul2_vt(r, a); break;
+                case 21: fe_mul3_vt(r, a); break;
+                case 22: fe_sub2_vt(r, a, b); break;
+                case 23: fe_submul8_vt(r, a, b); break;
                 default: r = fe_zero();
             }
             fe_normalize(r, r);

@@ -72,8 +72,19 @@ def check_field_ops(be, rng_seed=7, n=256):
     # 8a: the bits shifted out fold back as (a >> 253) * delta; inputs chosen so that the fold ripples
     A += [2**256 - 1, (7 << 253) | (2**93 - 1 << 0), (1 << 253) | (2**93 - 2)]
     B += [0, 0, 0]
+    # the fused small multiples of the Jacobian formulas (2a, 3a, a - 2b, a - 8b; fe_vt.cuh): top bits shifted out plus
+    # the chain's carry / borrow fold together (k up to 8), with results that make the k * delta fold ripple and wrap
+    yy = int.from_bytes(rng.bytes(31), "big")
+    for k in (1, 2, 3, 7):
+        bb = (k << 253) + (yy >> 3)
+        A += [(8 * bb + 5) % 2**256, (8 * bb + 5 + 2**96) % 2**256, (2 * bb + 5) % 2**256, (2 * bb + 2**96 + 3) % 2**256, 0, 5]
+        B += [bb] * 6
+    A += [2**256 - 1 - r for r in range(4)] + [(2**256 + X3) // 3, (2**256 + X3 + 2**96) // 3, (2**257 + X3) // 3 + 1]
+    B += [2**256 - 1] * 4 + [0, 0, 0]
     a, b = rows([b32(x) for x in A], 32), rows([b32(x) for x in B], 32)
     ops = fe_ops + [(8 + op, f) for op, f in fe_ops] + [(15, lambda x, y: x * 8 % P)] + [
+        (20, lambda x, y: 2 * x % P), (21, lambda x, y: 3 * x % P), (22, lambda x, y: (x - 2 * y) % P),
+        (23, lambda x, y: (x - 8 * y) % P)] + [
         (3, lambda x, y: pow(x % P, P - 2, P)), (7, lambda x, y: pow(x % P, P - 2, P)),
         (19, lambda x, y: pow(x % N, N - 2, N)),
         (16, lambda x, y: (x % N) * (y % N) % N), (17, lambda x, y: (x % N + y % N) % N),
@@ -278,6 +289,15 @@ def check_double_scalar_mult(be, o, n=96):
     for j, v in enumerate(edge_u1):
         if 40 + j < n:
             u1[40 + j] = v
+    # the exceptional branches of the Jacobian ladder (csrc/jac.cuh) away from the final addition: the accumulator
+    # equals the comb entry of a middle window (doubling), is its negative (identity, then an assignment from the
+    # identity), and the same with the collision in the top window / with the lambda half of u2 empty or alone
+    mid = [(1, 2**22 + 3 * 2**44, 2**22), (N - 1, 2**22 + 5 * 2**44, 2**22), (1, 7 * 2**242, 7 * 2**242 % N),
+           (N - 1, 7 * 2**242, 7 * 2**242 % N), (1, 2**66 + 2**110, 2**66), (3, 3 * 2**44 + 1, 2**44),
+           (N - 3, 3 * 2**44 + 2**200, 2**44), (1, 1, 1), (1, 2, 1), (2, 2, 1), (N - 2, 2, 1), (1, 16, 16), (1, 17, 16)]
+    for j, (dd, a, b) in enumerate(mid):
+        if 50 + j < n:
+            d[50 + j], u1[50 + j], u2[50 + j] = dd, a, b
     pts, _ = o.batch_scalar_base_mult(rows([b32(x) for x in d], 32))
     U1, U2 = rows([b32(x) for x in u1], 32), rows([b32(x) for x in u2], 32)
     got, st = be.double_scalar_mult_basepoint_vartime(U1, U2, pts)
