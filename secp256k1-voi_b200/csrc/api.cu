@@ -201,13 +201,73 @@ __global__ void __launch_bounds__(S256_TPB) k_schnorr_scalars(const uint8_t *pkx
 #ifndef S256_DSM_MINB
 #define S256_DSM_MINB 4
 #endif
-__global__ void __launch_bounds__(S256_TPB, S256_DSM_MINB)
+#ifndef S256_DSM_TPB
+#define S256_DSM_TPB S256_TPB
+#endif
+#if defined(S256_DSM_JAC) && !defined(S256_DSM_OWN_INV)
+// One inversion per CTA instead of one per item (Montgomery's trick across the CTA): every thread leaves the product
+// of its table's Z's in shared memory, warp 0 takes S256_TPB / 32 of them per lane, multiplies them up, forms the
+// product of all OTHER lanes' values with an xor butterfly (9 products), inverts the CTA's total once (safegcd: 23 k
+// instructions, which each of the four warps used to spend) and walks back to the individual inverses.  Public data.
+__device__ __forceinline__ void fe_shfl_xor(fe &r, const fe &a, int m) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) r.v[k] = __shfl_xor_sync(0xFFFFFFFFu, a.v[k], m);
+}
+__device__ __forceinline__ void cta_invert(fe &inv, const fe &c, fe *sh) {
+    constexpr int PER = S256_DSM_TPB / 32;
+    typedef fe_ops<true> F;
+    sh[threadIdx.x] = c;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        fe *mine = sh + threadIdx.x * PER;
+        fe pre[PER];
+        pre[0] = mine[0];
+#pragma unroll
+        for (int k = 1; k < PER; k++) F::mul(pre[k], pre[k - 1], mine[k]);
+        fe all = pre[PER - 1], others, got;
+        fe_shfl_xor(others, all, 1);
+        F::mul(all, all, others);
+#pragma unroll 1
+        for (int m = 2; m < 32; m <<= 1) {
+            fe_shfl_xor(got, all, m);
+            F::mul(others, others, got);
+            F::mul(all, all, got);
+        }
+        fe o;
+        fe_invert(o, all);
+        F::mul(o, o, others);  // (this lane's product)^-1
+#pragma unroll
+        for (int k = PER - 1; k >= 1; k--) {
+            fe ck = mine[k], t;
+            F::mul(t, o, pre[k - 1]);
+            F::mul(o, o, ck);
+            mine[k] = t;
+        }
+        mine[0] = o;
+    }
+    __syncthreads();
+    inv = sh[threadIdx.x];
+}
+__global__ void __launch_bounds__(S256_DSM_TPB, S256_DSM_MINB)
+    k_dsm(size_t n, const apt *aff, const sc *u1, const int8_t *dig1, const int8_t *dig2, const uint8_t *sfl, pt *tbl,
+          pt *res, const apt *comb) {
+    __shared__ fe sh[S256_DSM_TPB];
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    fe zprod = fe_one(), inv;
+    if (live) item_dsm_table(i, aff, tbl, zprod);
+    cta_invert(inv, zprod, sh);
+    if (live) item_dsm_ladder(i, n, inv, u1, dig1, dig2, sfl, tbl, res, comb);
+}
+#else
+__global__ void __launch_bounds__(S256_DSM_TPB, S256_DSM_MINB)
     k_dsm(size_t n, const apt *aff, const sc *u1, const int8_t *dig1, const int8_t *dig2, const uint8_t *sfl, pt *tbl,
           pt *res, const apt *comb) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     item_dsm(i, n, aff, u1, dig1, dig2, sfl, tbl, res, comb);
 }
+#endif
 
 
 // 4-bit windows over an affine table: 8 entries x 64 bytes per thread = 64 KB of shared memory per CTA, three CTAs per SM
@@ -462,7 +522,9 @@ static void enqueue_dsm(s256_ctx *ctx, const view &v, size_t n, cudaStream_t s) 
         cudaEventCreate(&e1);
         cudaEventRecord(e0, s);
     }
-    LAUNCH(ctx, k_dsm, grid_for(n), 0, s, n, v.aff, v.u1, v.dig1, v.dig2, v.sfl, v.tbl, v.res, ctx->comb);
+    k_dsm<<<(unsigned)((n + S256_DSM_TPB - 1) / S256_DSM_TPB), S256_DSM_TPB, 0, s>>>(n, v.aff, v.u1, v.dig1, v.dig2, v.sfl, v.tbl,
+                                                                                         v.res, ctx->comb);
+    ctx->launches.fetch_add(1, std::memory_order_relaxed);
     if (ctx->profiling) {
         cudaEventRecord(e1, s);
         ctx->dsm_events.emplace_back(e0, e1);

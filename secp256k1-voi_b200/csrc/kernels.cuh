@@ -392,8 +392,10 @@ S256_HD void apt_fetch64(apt &r, const apt *p) {
 // ladder addition is a mixed one.  Layout of the item's scratch (bytes): [0, 64) P; [64, 64 + 96 (TS - 1)) the
 // Jacobian multiples 2..TS; then the suffix products Z_k ... Z_TS for k = 3..TS.  The affine rows overwrite the front
 // in ascending order: row k ends at 64 k, the first Jacobian multiple still needed (k + 1) starts at 64 + 96 (k - 1).
-S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
-                      const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
+// The ladder is three phases so that the kernel can share the inversion between the items of a CTA (api.cu k_dsm):
+// item_dsm_table leaves the Jacobian multiples and returns the product of their Z's; the caller inverts it;
+// item_dsm_ladder normalises the table with that inverse and runs the ladder.  item_dsm is the plain composition.
+S256_HD void item_dsm_table(size_t i, const apt *aff, pt *tbl, fe &zprod) {
     char *base = reinterpret_cast<char *>(tbl + i * (size_t)DSM_TSTRIDE);
     apt *A = reinterpret_cast<apt *>(base);
     {
@@ -427,8 +429,18 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
             fe zk = J[k - 2].z;
             fe_ops<DSM_VT>::mul(run, run, zk);
         }
-        fe inv;  // (Z_2 ... Z_TS)^-1, then (Z_k ... Z_TS)^-1 as k advances
-        fe_invert(inv, run);
+        zprod = run;
+    }
+}
+// inv = (Z_2 ... Z_TS)^-1 of this item's table
+S256_HD void item_dsm_ladder(size_t i, size_t n, fe inv, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
+                             const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
+    char *base = reinterpret_cast<char *>(tbl + i * (size_t)DSM_TSTRIDE);
+    apt *A = reinterpret_cast<apt *>(base);
+    {
+        pt *J = reinterpret_cast<pt *>(base + 64);
+        fe *C = reinterpret_cast<fe *>(base + 64 + 96 * (DSM_TS - 1));
+        // inv becomes (Z_k ... Z_TS)^-1 as k advances
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -512,6 +524,13 @@ S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const i
     pt out;
     jac_to_projective<DSM_VT>(out, acc, inf);
     res[i] = out;
+}
+S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
+                      const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
+    fe zprod, inv;
+    item_dsm_table(i, aff, tbl, zprod);
+    fe_invert(inv, zprod);
+    item_dsm_ladder(i, n, inv, u1s, dig1, dig2, sfl, tbl, res, comb);
 }
 #else
 S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
