@@ -206,16 +206,16 @@ __global__ void __launch_bounds__(S256_TPB) k_schnorr_scalars(const uint8_t *pkx
 #endif
 #if defined(S256_DSM_JAC) && !defined(S256_DSM_OWN_INV)
 // One inversion per CTA instead of one per item (Montgomery's trick across the CTA): every thread leaves the product
-// of its table's Z's in shared memory, warp 0 takes S256_TPB / 32 of them per lane, multiplies them up, forms the
+// of its table's Z's in shared memory, warp 0 takes S256_DSM_TPB / 32 of them per lane, multiplies them up, forms the
 // product of all OTHER lanes' values with an xor butterfly (9 products), inverts the CTA's total once (safegcd: 23 k
 // instructions, which each of the four warps used to spend) and walks back to the individual inverses.  Public data.
 __device__ __forceinline__ void fe_shfl_xor(fe &r, const fe &a, int m) {
 #pragma unroll
     for (int k = 0; k < 8; k++) r.v[k] = __shfl_xor_sync(0xFFFFFFFFu, a.v[k], m);
 }
-__device__ __forceinline__ void cta_invert(fe &inv, const fe &c, fe *sh) {
+template <class F>
+__device__ __forceinline__ void cta_invert(F &f, fe &inv, const fe &c, fe *sh) {
     constexpr int PER = S256_DSM_TPB / 32;
-    typedef fe_ops<true> F;
     sh[threadIdx.x] = c;
     __syncthreads();
     if (threadIdx.x < 32) {
@@ -223,24 +223,24 @@ __device__ __forceinline__ void cta_invert(fe &inv, const fe &c, fe *sh) {
         fe pre[PER];
         pre[0] = mine[0];
 #pragma unroll
-        for (int k = 1; k < PER; k++) F::mul(pre[k], pre[k - 1], mine[k]);
+        for (int k = 1; k < PER; k++) f.mul(pre[k], pre[k - 1], mine[k]);
         fe all = pre[PER - 1], others, got;
         fe_shfl_xor(others, all, 1);
-        F::mul(all, all, others);
+        f.mul(all, all, others);
 #pragma unroll 1
         for (int m = 2; m < 32; m <<= 1) {
             fe_shfl_xor(got, all, m);
-            F::mul(others, others, got);
-            F::mul(all, all, got);
+            f.mul(others, others, got);
+            f.mul(all, all, got);
         }
         fe o;
         fe_invert(o, all);
-        F::mul(o, o, others);  // (this lane's product)^-1
+        f.mul(o, o, others);  // (this lane's product)^-1
 #pragma unroll
         for (int k = PER - 1; k >= 1; k--) {
             fe ck = mine[k], t;
-            F::mul(t, o, pre[k - 1]);
-            F::mul(o, o, ck);
+            f.mul(t, o, pre[k - 1]);
+            f.mul(o, o, ck);
             mine[k] = t;
         }
         mine[0] = o;
@@ -254,10 +254,11 @@ __global__ void __launch_bounds__(S256_DSM_TPB, S256_DSM_MINB)
     __shared__ fe sh[S256_DSM_TPB];
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
+    fe_ops<DSM_VT> f;
     fe zprod = fe_one(), inv;
-    if (live) item_dsm_table(i, aff, tbl, zprod);
-    cta_invert(inv, zprod, sh);
-    if (live) item_dsm_ladder(i, n, inv, u1, dig1, dig2, sfl, tbl, res, comb);
+    if (live) item_dsm_table(f, i, aff, tbl, zprod);
+    cta_invert(f, inv, zprod, sh);
+    if (live) item_dsm_ladder(f, i, n, inv, u1, dig1, dig2, sfl, tbl, res, comb);
 }
 #else
 __global__ void __launch_bounds__(S256_DSM_TPB, S256_DSM_MINB)
@@ -268,7 +269,6 @@ __global__ void __launch_bounds__(S256_DSM_TPB, S256_DSM_MINB)
     item_dsm(i, n, aff, u1, dig1, dig2, sfl, tbl, res, comb);
 }
 #endif
-
 
 // 4-bit windows over an affine table: 8 entries x 64 bytes per thread = 64 KB of shared memory per CTA, three CTAs per SM
 #ifndef S256_SM_MINB

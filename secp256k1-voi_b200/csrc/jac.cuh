@@ -1,5 +1,7 @@
 // jac.cuh -- Jacobian-coordinate group law (x = X / Z^2, y = Y / Z^3) for the VARIABLE-TIME ladders only.
 //
+// Every function is a template over the field-operation set F, passed as an object (fe_ops<VT> of fe_vt.cuh).
+//
 // The reference runs every path on the Renes-Costello-Batina complete formulas (point_projective.go:24-273), and so do
 // the constant-time kernels and the Point API here (point.cuh).  The verification ladder
 // (DoubleScalarMultBasepointVartime, point_mul_glv.go:307-317) handles public data, is variable time in the reference
@@ -18,77 +20,60 @@
 
 namespace s256 {
 
-// v = 2p (a = 0).  p must not be at infinity for the result to mean anything; (0 : 1 : 0) maps to Z = 0 harmlessly.
-template <bool VT = true>
-S256_HD void jac_double(pt &v, const pt &p) {
-    typedef fe_ops<VT> F;
+// v = 2p (a = 0).  p must not be at infinity for the result to mean anything; (0, 0, 0) maps to itself.
+template <class F>
+S256_HD void jac_double(F &fo, pt &v, const pt &p) {
     fe a, b, c, d, e, f, t, z3;
-    F::sqr(a, p.x);
-    F::sqr(b, p.y);
-    F::sqr(c, b);
+    fo.sqr(a, p.x);
+    fo.sqr(b, p.y);
+    fo.sqr(c, b);
 #ifndef S256_JDBL_3M4S
-    F::add(t, p.x, b);  // D = 2 ((X + B)^2 - A - C)
-    F::sqr(t, t);
-    F::sub(t, t, a);
-    F::sub(t, t, c);
-    F::mul2(d, t);
+    fo.add(t, p.x, b);  // D = 2 ((X + B)^2 - A - C)
+    fo.sqr(t, t);
+    fo.sub(t, t, a);
+    fo.sub(t, t, c);
+    fo.mul2(d, t);
 #else
-    F::mul(t, p.x, b);  // D = 4 X B
-    F::mul2(t, t);
-    F::mul2(d, t);
+    fo.mul(t, p.x, b);  // D = 4 X B
+    fo.mul2(t, t);
+    fo.mul2(d, t);
 #endif
-    F::mul3(e, a);  // E = 3 A
-    F::sqr(f, e);
-    F::mul(z3, p.y, p.z);
-    F::mul2(v.z, z3);
-    F::sub2(t, f, d);  // X3 = F - 2 D
+    fo.mul3(e, a);  // E = 3 A
+    fo.sqr(f, e);
+    fo.mul(z3, p.y, p.z);
+    fo.mul2(v.z, z3);
+    fo.sub2(t, f, d);  // X3 = F - 2 D
     v.x = t;
-    F::sub(t, d, t);
-    F::mul(f, e, t);  // Y3 = E (D - X3) - 8 C
-    F::submul8(v.y, f, c);
+    fo.sub(t, d, t);
+    fo.mul(f, e, t);  // Y3 = E (D - X3) - 8 C
+    fo.submul8(v.y, f, c);
 }
-#if defined(__CUDA_ARCH__)
-static __device__ __noinline__ pt jac_double_call(pt a) {
-    pt r;
-    jac_double<true>(r, a);
-    return r;
-}
-#else
-static inline pt jac_double_call(pt a) {
-    pt r;
-    jac_double<true>(r, a);
-    return r;
-}
-#endif
-
 // v = p + (x2, y2) for a finite p whose sum with the addend is known not to be exceptional (table construction:
 // k P + P with 2 <= k < 16 on a curve of prime order).
-template <bool VT = true>
-S256_HD void jac_add_mixed_nocheck(pt &v, const pt &p, const fe &x2, const fe &y2) {
-    typedef fe_ops<VT> F;
+template <class F>
+S256_HD void jac_add_mixed_nocheck(F &fo, pt &v, const pt &p, const fe &x2, const fe &y2) {
     fe zz, u2, s2, h, r, hh, hhh, w, t, x3;
-    F::sqr(zz, p.z);
-    F::mul(u2, x2, zz);
-    F::mul(s2, y2, p.z);
-    F::mul(s2, s2, zz);
-    F::sub(h, u2, p.x);
-    F::sub(r, s2, p.y);
-    F::sqr(hh, h);
-    F::mul(hhh, h, hh);
-    F::mul(w, p.x, hh);
-    F::mul(v.z, p.z, h);
-    F::sqr(x3, r);
-    F::sub(x3, x3, hhh);
-    F::sub2(x3, x3, w);
-    F::sub(t, w, x3);
-    F::mul2sub(v.y, r, t, p.y, hhh);
+    fo.sqr(zz, p.z);
+    fo.mul(u2, x2, zz);
+    fo.mul(s2, y2, p.z);
+    fo.mul(s2, s2, zz);
+    fo.sub(h, u2, p.x);
+    fo.sub(r, s2, p.y);
+    fo.sqr(hh, h);
+    fo.mul(hhh, h, hh);
+    fo.mul(w, p.x, hh);
+    fo.mul(v.z, p.z, h);
+    fo.sqr(x3, r);
+    fo.sub(x3, x3, hhh);
+    fo.sub2(x3, x3, w);
+    fo.sub(t, w, x3);
+    fo.mul2sub(v.y, r, t, p.y, hhh);
     v.x = x3;
 }
 
 // acc += (x2, y2), every case handled; inf is the caller's "accumulator is the identity" flag.
-template <bool VT = true>
-S256_HD void jac_add_mixed_var(pt &acc, uint32_t &inf, const fe &x2, const fe &y2) {
-    typedef fe_ops<VT> F;
+template <class F>
+S256_HD void jac_add_mixed_var(F &fo, pt &acc, uint32_t &inf, const fe &x2, const fe &y2) {
     if (inf) {
         acc.x = x2;
         acc.y = y2;
@@ -97,44 +82,45 @@ S256_HD void jac_add_mixed_var(pt &acc, uint32_t &inf, const fe &x2, const fe &y
         return;
     }
     fe zz, u2, s2, h, r, hh, hhh, w, t, x3;
-    F::sqr(zz, acc.z);
-    F::mul(u2, x2, zz);
-    F::mul(s2, y2, acc.z);
-    F::mul(s2, s2, zz);
-    F::sub(h, u2, acc.x);
-    F::sub(r, s2, acc.y);
+    fo.sqr(zz, acc.z);
+    fo.mul(u2, x2, zz);
+    fo.mul(s2, y2, acc.z);
+    fo.mul(s2, s2, zz);
+    fo.sub(h, u2, acc.x);
+    fo.sub(r, s2, acc.y);
     if (fe_is_zero(h)) {
-        if (fe_is_zero(r))
-            acc = jac_double_call(acc);
-        else
+        if (!fe_is_zero(r)) {
             inf = 1u;
+            acc.x = acc.y = acc.z = fe_zero();  // (see item_dsm_ladder: zero coordinates under the flag)
+        } else {
+            jac_double(fo, acc, acc);
+        }
         return;
     }
-    F::sqr(hh, h);
-    F::mul(hhh, h, hh);
-    F::mul(w, acc.x, hh);
-    F::mul(acc.z, acc.z, h);
-    F::sqr(x3, r);
-    F::sub(x3, x3, hhh);
-    F::sub2(x3, x3, w);
-    F::sub(t, w, x3);
-    F::mul2sub(acc.y, r, t, acc.y, hhh);
+    fo.sqr(hh, h);
+    fo.mul(hhh, h, hh);
+    fo.mul(w, acc.x, hh);
+    fo.mul(acc.z, acc.z, h);
+    fo.sqr(x3, r);
+    fo.sub(x3, x3, hhh);
+    fo.sub2(x3, x3, w);
+    fo.sub(t, w, x3);
+    fo.mul2sub(acc.y, r, t, acc.y, hhh);
     acc.x = x3;
 }
 
 // Jacobian -> the homogeneous projective form every consumer of the ladder's result expects: (X Z : Y : Z^3)
-template <bool VT = true>
-S256_HD void jac_to_projective(pt &v, const pt &p, uint32_t inf) {
-    typedef fe_ops<VT> F;
+template <class F>
+S256_HD void jac_to_projective(F &fo, pt &v, const pt &p, uint32_t inf) {
     if (inf) {
         pt_set_identity(v);
         return;
     }
     fe zz;
-    F::sqr(zz, p.z);
-    F::mul(v.x, p.x, p.z);
+    fo.sqr(zz, p.z);
+    fo.mul(v.x, p.x, p.z);
     v.y = p.y;
-    F::mul(v.z, zz, p.z);
+    fo.mul(v.z, zz, p.z);
 }
 
 }  // namespace s256

@@ -395,7 +395,8 @@ S256_HD void apt_fetch64(apt &r, const apt *p) {
 // The ladder is three phases so that the kernel can share the inversion between the items of a CTA (api.cu k_dsm):
 // item_dsm_table leaves the Jacobian multiples and returns the product of their Z's; the caller inverts it;
 // item_dsm_ladder normalises the table with that inverse and runs the ladder.  item_dsm is the plain composition.
-S256_HD void item_dsm_table(size_t i, const apt *aff, pt *tbl, fe &zprod) {
+template <class F>
+S256_HD void item_dsm_table(F &f, size_t i, const apt *aff, pt *tbl, fe &zprod) {
     char *base = reinterpret_cast<char *>(tbl + i * (size_t)DSM_TSTRIDE);
     apt *A = reinterpret_cast<apt *>(base);
     {
@@ -413,10 +414,10 @@ S256_HD void item_dsm_table(size_t i, const apt *aff, pt *tbl, fe &zprod) {
                 pt_from_affine(h, P);
             else
                 h = J[k / 2 - 2];
-            jac_double<DSM_VT>(cur, h);
+            jac_double(f, cur, h);
             J[k - 2] = cur;
             if (k < DSM_TS) {
-                jac_add_mixed_nocheck<DSM_VT>(cur, cur, P.x, P.y);
+                jac_add_mixed_nocheck(f, cur, cur, P.x, P.y);
                 J[k - 1] = cur;
             }
         }
@@ -427,13 +428,14 @@ S256_HD void item_dsm_table(size_t i, const apt *aff, pt *tbl, fe &zprod) {
         for (int k = DSM_TS - 1; k >= 2; k--) {
             C[k + 1 - 3] = run;
             fe zk = J[k - 2].z;
-            fe_ops<DSM_VT>::mul(run, run, zk);
+            f.mul(run, run, zk);
         }
         zprod = run;
     }
 }
 // inv = (Z_2 ... Z_TS)^-1 of this item's table
-S256_HD void item_dsm_ladder(size_t i, size_t n, fe inv, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
+template <class F>
+S256_HD void item_dsm_ladder(F &f, size_t i, size_t n, fe inv, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
                              const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
     char *base = reinterpret_cast<char *>(tbl + i * (size_t)DSM_TSTRIDE);
     apt *A = reinterpret_cast<apt *>(base);
@@ -449,20 +451,24 @@ S256_HD void item_dsm_ladder(size_t i, size_t n, fe inv, const sc *u1s, const in
             fe zi = inv, zi2;
             if (k < DSM_TS) {
                 fe ck = C[k + 1 - 3];
-                fe_ops<DSM_VT>::mul(zi, inv, ck);      // Z_k^-1
-                fe_ops<DSM_VT>::mul(inv, inv, jk.z);
+                f.mul(zi, inv, ck);      // Z_k^-1
+                f.mul(inv, inv, jk.z);
             }
             apt a;
-            fe_ops<DSM_VT>::sqr(zi2, zi);
-            fe_ops<DSM_VT>::mul(a.x, jk.x, zi2);
-            fe_ops<DSM_VT>::mul(zi2, zi2, zi);
-            fe_ops<DSM_VT>::mul(a.y, jk.y, zi2);
+            f.sqr(zi2, zi);
+            f.mul(a.x, jk.x, zi2);
+            f.mul(zi2, zi2, zi);
+            f.mul(a.y, jk.y, zi2);
             A[k - 1] = a;
         }
     }
     uint32_t fl = sfl[i];
+    // the identity is the flag; the coordinates underneath are all zero, which every doubling maps to all zero (with
+    // (0 : 1 : 0) they become small negative numbers, i.e. values next to 2^256, whose products take the folds' rare path)
     pt acc;
-    pt_set_identity(acc);
+    acc.x = fe_zero();
+    acc.y = fe_zero();
+    acc.z = fe_zero();
     uint32_t inf = 1u;
     const fe beta = fe_beta();
 #if defined(__CUDA_ARCH__)
@@ -483,7 +489,7 @@ S256_HD void item_dsm_ladder(size_t i, size_t n, fe inv, const sc *u1s, const in
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-            for (int k = 0; k < DSM_W; k++) jac_double<DSM_VT>(acc, acc);
+            for (int k = 0; k < DSM_W; k++) jac_double(f, acc, acc);
         }
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
@@ -495,12 +501,12 @@ S256_HD void item_dsm_ladder(size_t i, size_t n, fe inv, const sc *u1s, const in
                 int mag = d < 0 ? -d : d;
                 apt q;
                 apt_fetch64(q, A + (mag - 1));
-                if (h) fe_ops<DSM_VT>::mul(q.x, q.x, beta);
+                if (h) f.mul(q.x, q.x, beta);
                 if (neg) {
                     fe z = fe_zero();
-                    fe_ops<DSM_VT>::sub(q.y, z, q.y);
+                    f.sub(q.y, z, q.y);
                 }
-                jac_add_mixed_var<DSM_VT>(acc, inf, q.x, q.y);
+                jac_add_mixed_var(f, acc, inf, q.x, q.y);
             }
         }
     }
@@ -516,21 +522,22 @@ S256_HD void item_dsm_ladder(size_t i, size_t n, fe inv, const sc *u1s, const in
             apt g = comb[(size_t)w * COMB_SZ + (mag - 1u)];
             if (d < 0) {
                 fe z = fe_zero();
-                fe_ops<DSM_VT>::sub(g.y, z, g.y);
+                f.sub(g.y, z, g.y);
             }
-            jac_add_mixed_var<DSM_VT>(acc, inf, g.x, g.y);
+            jac_add_mixed_var(f, acc, inf, g.x, g.y);
         }
     }
     pt out;
-    jac_to_projective<DSM_VT>(out, acc, inf);
+    jac_to_projective(f, out, acc, inf);
     res[i] = out;
 }
 S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
                       const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
+    fe_ops<DSM_VT> f;
     fe zprod, inv;
-    item_dsm_table(i, aff, tbl, zprod);
+    item_dsm_table(f, i, aff, tbl, zprod);
     fe_invert(inv, zprod);
-    item_dsm_ladder(i, n, inv, u1s, dig1, dig2, sfl, tbl, res, comb);
+    item_dsm_ladder(f, i, n, inv, u1s, dig1, dig2, sfl, tbl, res, comb);
 }
 #else
 S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
