@@ -218,6 +218,7 @@ __device__ __forceinline__ void cta_invert(F &f, fe &inv, const fe &c, fe *sh) {
     constexpr int PER = S256_DSM_TPB / 32;
     sh[threadIdx.x] = c;
     __syncthreads();
+    // (warp 0 always: rotating the inverting warp over the SM's four schedulers measured 0.5 % slower)
     if (threadIdx.x < 32) {
         fe *mine = sh + threadIdx.x * PER;
         fe pre[PER];
@@ -270,9 +271,9 @@ __global__ void __launch_bounds__(S256_DSM_TPB, S256_DSM_MINB)
 }
 #endif
 
-// 4-bit windows over an affine table: 8 entries x 64 bytes per thread = 64 KB of shared memory per CTA, three CTAs per SM
+// 4-bit windows over an affine table: entries 2..8 x 64 bytes per thread = 56 KB of shared memory per CTA, four CTAs per SM
 #ifndef S256_SM_MINB
-#define S256_SM_MINB 3
+#define S256_SM_MINB 4
 #endif
 __global__ void __launch_bounds__(S256_TPB, S256_SM_MINB)
     k_scalar_mult_ct(size_t n, const apt *aff, const uint8_t *k32, pt *tbl, pt *res) {
@@ -281,14 +282,14 @@ __global__ void __launch_bounds__(S256_TPB, S256_SM_MINB)
 #ifdef S256_CT_TABLE_GLOBAL
     CtTableGlobal T{tbl + i * (size_t)DSM_TSTRIDE};
 #else
-    CtTableShared<S256_TPB> T{threadIdx.x};
+    CtTableShared<S256_TPB> T{threadIdx.x, aff + i};
 #endif
     item_scalar_mult_ct_affine(i, aff, k32, T, tbl + i * (size_t)DSM_TSTRIDE, res);
 }
 #ifdef S256_CT_TABLE_GLOBAL
 constexpr size_t CT_SMEM_BYTES = 0;
 #else
-constexpr size_t CT_SMEM_BYTES = (size_t)CTM_TS * 4 * S256_TPB * sizeof(uint4);
+constexpr size_t CT_SMEM_BYTES = (size_t)(CTM_TS - 1) * 4 * S256_TPB * sizeof(uint4);
 #endif
 void s256_launch_scalar_mult_ct(size_t n, const apt *aff, const uint8_t *k32, pt *tbl, pt *res, cudaStream_t s) {
     if (n == 0) return;

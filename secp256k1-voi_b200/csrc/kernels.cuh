@@ -933,24 +933,38 @@ struct CtTableGlobal {
     S256_HD apt load_affine(int j) const { return reinterpret_cast<const apt *>(T + CTM_TS)[j]; }
 };
 #if defined(__CUDACC__)
+// Entry 1 (the point itself) is not kept in shared memory: it is read back from the item's input row `p0` (a public
+// address; 64 bytes that stay in L1), so that the columns of entries 2..TS take (TS - 1) x 64 x TPB bytes -- 56 KB for
+// TS = 8, which lets FOUR 128-thread CTAs share an SM's 228 KB instead of three.
 template <int TPB>
 struct CtTableShared {
     uint32_t t;
+    const apt *p0;
     // affine entries: 16 words = 4 x uint4 per entry, same conflict-free column layout
     __device__ __forceinline__ void store_affine(int j, const apt &a) const {
         extern __shared__ uint4 ct_smem[];
+        if (j == 0) return;
         const uint32_t *w = a.x.v;  // x, y are contiguous
 #pragma unroll
         for (int g = 0; g < 4; g++)
-            ct_smem[(uint32_t)(j * 4 + g) * TPB + t] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
+            ct_smem[(uint32_t)((j - 1) * 4 + g) * TPB + t] = make_uint4(w[4 * g], w[4 * g + 1], w[4 * g + 2], w[4 * g + 3]);
     }
     __device__ __forceinline__ apt load_affine(int j) const {
         extern __shared__ uint4 ct_smem[];
         apt a;
         uint32_t *w = a.x.v;
+        if (j == 0) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(p0);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                uint4 v = q[g];
+                w[4 * g] = v.x; w[4 * g + 1] = v.y; w[4 * g + 2] = v.z; w[4 * g + 3] = v.w;
+            }
+            return a;
+        }
 #pragma unroll
         for (int g = 0; g < 4; g++) {
-            uint4 q = ct_smem[(uint32_t)(j * 4 + g) * TPB + t];
+            uint4 q = ct_smem[(uint32_t)((j - 1) * 4 + g) * TPB + t];
             w[4 * g] = q.x; w[4 * g + 1] = q.y; w[4 * g + 2] = q.z; w[4 * g + 3] = q.w;
         }
         return a;
@@ -964,6 +978,13 @@ struct CtTableShared {
 // Every window then costs a mixed addition (11 M) instead of a complete one (12 M) and the entries are
 // a third smaller.  Digit 0 adds entry 1 and discards the sum (the mixed formula needs a finite addend),
 // as the fixed-base ladder does.  No branch and no address depends on the scalar.
+// The table holds multiples of the PUBLIC point: it is built with the variable-time field operations (fe_vt.cuh); the
+// secret scalar first appears in the recoding below, and everything from there on is the constant-time flavour.
+#ifndef S256_CTM_TAB_CT
+constexpr bool CTM_TAB_VT = true;
+#else
+constexpr bool CTM_TAB_VT = false;
+#endif
 template <class TAB>
 S256_HD void item_scalar_mult_ct_affine(size_t i, const apt *aff, const uint8_t *k32, const TAB &T, pt *G, pt *res) {
     const apt P = aff[i];
@@ -976,10 +997,10 @@ S256_HD void item_scalar_mult_ct_affine(size_t i, const apt *aff, const uint8_t 
 #endif
         for (int k = 2; k <= CTM_TS; k += 2) {
             pt h = G[k / 2 - 1];
-            pt_double(cur, h);
+            pt_double<CTM_TAB_VT>(cur, h);
             G[k - 1] = cur;
             if (k < CTM_TS) {
-                pt_add_mixed(cur, cur, P.x, P.y);
+                pt_add_mixed<CTM_TAB_VT>(cur, cur, P.x, P.y);
                 G[k] = cur;
             }
         }
@@ -991,7 +1012,7 @@ S256_HD void item_scalar_mult_ct_affine(size_t i, const apt *aff, const uint8_t 
         for (int j = 1; j < CTM_TS; j++) {
             pre[j] = run;
             fe z = G[j].z;
-            fe_mul(run, run, z);
+            fe_ops<CTM_TAB_VT>::mul(run, run, z);
         }
         fe_invert(inv, run);
 #if defined(__CUDA_ARCH__)
@@ -1001,10 +1022,10 @@ S256_HD void item_scalar_mult_ct_affine(size_t i, const apt *aff, const uint8_t 
             pt e = G[j];
             fe zi;
             apt a;
-            fe_mul(zi, inv, pre[j]);
-            fe_mul(inv, inv, e.z);
-            fe_mul(a.x, e.x, zi);
-            fe_mul(a.y, e.y, zi);
+            fe_ops<CTM_TAB_VT>::mul(zi, inv, pre[j]);
+            fe_ops<CTM_TAB_VT>::mul(inv, inv, e.z);
+            fe_ops<CTM_TAB_VT>::mul(a.x, e.x, zi);
+            fe_ops<CTM_TAB_VT>::mul(a.y, e.y, zi);
             T.store_affine(j, a);
         }
         T.store_affine(0, P);
