@@ -204,18 +204,17 @@ __global__ void __launch_bounds__(S256_TPB) k_schnorr_scalars(const uint8_t *pkx
 #ifndef S256_DSM_TPB
 #define S256_DSM_TPB S256_TPB
 #endif
-#if defined(S256_DSM_JAC) && !defined(S256_DSM_OWN_INV)
 // One inversion per CTA instead of one per item (Montgomery's trick across the CTA): every thread leaves the product
-// of its table's Z's in shared memory, warp 0 takes S256_DSM_TPB / 32 of them per lane, multiplies them up, forms the
+// of its table's Z's in shared memory, warp 0 takes TPB / 32 of them per lane, multiplies them up, forms the
 // product of all OTHER lanes' values with an xor butterfly (9 products), inverts the CTA's total once (safegcd: 23 k
 // instructions, which each of the four warps used to spend) and walks back to the individual inverses.  Public data.
 __device__ __forceinline__ void fe_shfl_xor(fe &r, const fe &a, int m) {
 #pragma unroll
     for (int k = 0; k < 8; k++) r.v[k] = __shfl_xor_sync(0xFFFFFFFFu, a.v[k], m);
 }
-template <class F>
+template <int TPB, class F>
 __device__ __forceinline__ void cta_invert(F &f, fe &inv, const fe &c, fe *sh) {
-    constexpr int PER = S256_DSM_TPB / 32;
+    constexpr int PER = TPB / 32;
     sh[threadIdx.x] = c;
     __syncthreads();
     // (warp 0 always: rotating the inverting warp over the SM's four schedulers measured 0.5 % slower)
@@ -249,6 +248,7 @@ __device__ __forceinline__ void cta_invert(F &f, fe &inv, const fe &c, fe *sh) {
     __syncthreads();
     inv = sh[threadIdx.x];
 }
+#if defined(S256_DSM_JAC) && !defined(S256_DSM_OWN_INV)
 __global__ void __launch_bounds__(S256_DSM_TPB, S256_DSM_MINB)
     k_dsm(size_t n, const apt *aff, const sc *u1, const int8_t *dig1, const int8_t *dig2, const uint8_t *sfl, pt *tbl,
           pt *res, const apt *comb) {
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(S256_DSM_TPB, S256_DSM_MINB)
     fe_ops<DSM_VT> f;
     fe zprod = fe_one(), inv;
     if (live) item_dsm_table(f, i, aff, tbl, zprod);
-    cta_invert(f, inv, zprod, sh);
+    cta_invert<S256_DSM_TPB>(f, inv, zprod, sh);
     if (live) item_dsm_ladder(f, i, n, inv, u1, dig1, dig2, sfl, tbl, res, comb);
 }
 #else
@@ -278,13 +278,25 @@ __global__ void __launch_bounds__(S256_DSM_TPB, S256_DSM_MINB)
 __global__ void __launch_bounds__(S256_TPB, S256_SM_MINB)
     k_scalar_mult_ct(size_t n, const apt *aff, const uint8_t *k32, pt *tbl, pt *res) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
 #ifdef S256_CT_TABLE_GLOBAL
+    if (i >= n) return;
     CtTableGlobal T{tbl + i * (size_t)DSM_TSTRIDE};
-#else
-    CtTableShared<S256_TPB> T{threadIdx.x, aff + i};
-#endif
     item_scalar_mult_ct_affine(i, aff, k32, T, tbl + i * (size_t)DSM_TSTRIDE, res);
+#else
+    // the table is public (multiples of the peer's point): one inversion for the CTA, as in k_dsm.  The exchange area
+    // is the front of the (not yet written) table columns: a static array would cost the fourth CTA of the SM.
+    extern __shared__ uint4 ct_smem[];
+    fe *sh = reinterpret_cast<fe *>(ct_smem);
+    const bool live = i < n;
+    fe_ops<true> f;
+    fe zprod = fe_one(), inv;
+    if (live) item_ctm_table(i, aff, tbl + i * (size_t)DSM_TSTRIDE, zprod);
+    cta_invert<S256_TPB>(f, inv, zprod, sh);
+    __syncthreads();  // every inverse has been read before the first table column lands on the exchange area
+    if (!live) return;
+    CtTableShared<S256_TPB> T{threadIdx.x, aff + i};
+    item_ctm_ladder(i, aff, k32, T, tbl + i * (size_t)DSM_TSTRIDE, inv, res);
+#endif
 }
 #ifdef S256_CT_TABLE_GLOBAL
 constexpr size_t CT_SMEM_BYTES = 0;

@@ -98,7 +98,7 @@ S256_HD uint32_t ct_window_bits(const sc &k, int w) {
 constexpr int CTM_W = S256_CTW;
 constexpr int CTM_ND = glv_recode<CTM_W>::ND;
 constexpr int CTM_TS = 1 << (CTM_W - 1);
-static_assert(CTM_TS * (96 + 64) <= DSM_TS * 96, "the ct ladder shares the per-item table scratch of the vartime ladder");
+static_assert(CTM_TS * (96 + 64 + 32) <= DSM_TSTRIDE * 96, "the ct ladder shares the per-item table scratch of the vartime ladder");
 
 enum : uint8_t { ST_INVALID = 0, ST_OK = 1, ST_IDENTITY = 2 };
 enum : uint32_t { FLAG_REJECT_MALLEABLE = 1u };
@@ -985,50 +985,58 @@ constexpr bool CTM_TAB_VT = true;
 #else
 constexpr bool CTM_TAB_VT = false;
 #endif
-template <class TAB>
-S256_HD void item_scalar_mult_ct_affine(size_t i, const apt *aff, const uint8_t *k32, const TAB &T, pt *G, pt *res) {
+// Phase 1 (public data): [1..TS]P in projective form in the item's scratch G, the prefix products of Z_2..Z_TS behind
+// them and the affine rows of CtTableGlobal, and their total, which the caller inverts -- alone (item_scalar_mult_ct_affine) or once
+// for the whole CTA (api.cu k_scalar_mult_ct).
+S256_HD void item_ctm_table(size_t i, const apt *aff, pt *G, fe &zprod) {
     const apt P = aff[i];
+    pt cur;
+    pt_from_affine(cur, P);
+    G[0] = cur;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = 2; k <= CTM_TS; k += 2) {
+        pt h = G[k / 2 - 1];
+        pt_double<CTM_TAB_VT>(cur, h);
+        G[k - 1] = cur;
+        if (k < CTM_TS) {
+            pt_add_mixed<CTM_TAB_VT>(cur, cur, P.x, P.y);
+            G[k] = cur;
+        }
+    }
+    // Z_1 = 1; the products Z_2 .. Z_j for the shared inversion
+    fe *pre = reinterpret_cast<fe *>(reinterpret_cast<char *>(G) + CTM_TS * (96 + 64));
+    fe run = fe_one();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int j = 1; j < CTM_TS; j++) {
+        pre[j] = run;
+        fe z = G[j].z;
+        fe_ops<CTM_TAB_VT>::mul(run, run, z);
+    }
+    zprod = run;
+}
+// Phase 2: inv = (Z_2 ... Z_TS)^-1; the affine table into T, then the constant-time ladder.
+template <class TAB>
+S256_HD void item_ctm_ladder(size_t i, const apt *aff, const uint8_t *k32, const TAB &T, pt *G, fe inv, pt *res) {
     {
-        pt cur;
-        pt_from_affine(cur, P);
-        G[0] = cur;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-        for (int k = 2; k <= CTM_TS; k += 2) {
-            pt h = G[k / 2 - 1];
-            pt_double<CTM_TAB_VT>(cur, h);
-            G[k - 1] = cur;
-            if (k < CTM_TS) {
-                pt_add_mixed<CTM_TAB_VT>(cur, cur, P.x, P.y);
-                G[k] = cur;
-            }
-        }
-        // Z_1 = 1; invert Z_2 .. Z_TS together
-        fe pre[CTM_TS], run = fe_one(), inv;
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-        for (int j = 1; j < CTM_TS; j++) {
-            pre[j] = run;
-            fe z = G[j].z;
-            fe_ops<CTM_TAB_VT>::mul(run, run, z);
-        }
-        fe_invert(inv, run);
+        const fe *pre = reinterpret_cast<const fe *>(reinterpret_cast<const char *>(G) + CTM_TS * (96 + 64));
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
         for (int j = CTM_TS - 1; j >= 1; j--) {
             pt e = G[j];
-            fe zi;
+            fe zi, pj = pre[j];
             apt a;
-            fe_ops<CTM_TAB_VT>::mul(zi, inv, pre[j]);
+            fe_ops<CTM_TAB_VT>::mul(zi, inv, pj);
             fe_ops<CTM_TAB_VT>::mul(inv, inv, e.z);
             fe_ops<CTM_TAB_VT>::mul(a.x, e.x, zi);
             fe_ops<CTM_TAB_VT>::mul(a.y, e.y, zi);
             T.store_affine(j, a);
         }
-        T.store_affine(0, P);
+        T.store_affine(0, aff[i]);
     }
     sc k;
     sc_from_be32(k, k32 + 32 * i);
@@ -1080,6 +1088,13 @@ S256_HD void item_scalar_mult_ct_affine(size_t i, const apt *aff, const uint8_t 
         }
     }
     res[i] = acc;
+}
+template <class TAB>
+S256_HD void item_scalar_mult_ct_affine(size_t i, const apt *aff, const uint8_t *k32, const TAB &T, pt *G, pt *res) {
+    fe zprod, inv;
+    item_ctm_table(i, aff, G, zprod);
+    fe_invert(inv, zprod);
+    item_ctm_ladder(i, aff, k32, T, G, inv, res);
 }
 
 // point_s11n.go:140-172 -- SetCompressedBytes: 02/03 || X
