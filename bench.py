@@ -52,7 +52,7 @@ def workload_config(n_gpus, batch):
     return {"workload": "ECDSA verify batch 2^20 per GPU (secec.Verify compact, DoubleScalarMultBasepointVartime)",
             "batch_per_gpu": batch, "global_batch": batch * n_gpus, "corrupted_fraction": 1.0 / 16,
             "sharding": "contiguous batch slices, no collective",
-            "l2_policy": "inputs (169 MB) plus 1.6 GB per-item tables exceed the 126 MB L2 every step"}
+            "l2_policy": "inputs (169 MB) plus 2.1 GB of per-item tables exceed the 126 MB L2 every step"}
 
 
 class ClockSampler:
@@ -483,6 +483,7 @@ def main():
         ladder_mac = pkg.load_library().s256_mac32_k_dsm((adds_a + adds_b) / n, adds_b / n)
         mac_item = pkg.mac32_per_item("ecdsa_verify") - pkg.mac32_per_item("k_dsm") + ladder_mac
         achieved = ladder_mac * n / ((dsm_ms / max(dsm_launches, 1)) * 1e-3) if dsm_launches else None
+        rcb_mac = 8 * 519 + 7 * 776 + 125 * 519 + ((adds_a + adds_b) / n) * 849 + (adds_b / n) * 73 + 12 * 776
         cpu = None
         if not args.skip_cpu_baseline:
             from oracle import oracle as orc
@@ -527,7 +528,7 @@ def main():
             "clocks": dict(clocks, per_rank_sm_mhz=rank_sm_mhz), "per_rank_ms_per_step": per_rank_ms,
             "roofline": {"bound": "int-mul",
                          "bound_note": "32x32->64 multiply issue (IMAD.WIDE.U32, half rate on sm_100); not hbm/tensor: "
-                                       "161 B and ~142k multiply-accumulates per verification",
+                                       "161 B and ~110k multiply-accumulates per verification",
                          "kernel": "k_dsm", "achieved": achieved / 1e12 if achieved else None,
                          "peak": imad_peak / 1e12, "unit": "TMAC32/s",
                          "frac": (achieved / imad_peak) if achieved else None,
@@ -546,10 +547,20 @@ def main():
                          "whole_step_frac": value / world * mac_item / imad_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_dsm launch at 2^20 items, from the
                          # committed capture profiles/r01_ncu_final_dsm.txt (4.752 GB + 1.850 GB); scaled if --batch-log2 differs
-                         "traffic": 6.602e9 * n / (1 << 20), "traffic_unit": "bytes per launch",
-                         "traffic_note": "ncu --set full, profiles/r01_ncu_final_dsm.txt: ~6.3 KB per item (per-item table "
-                                         "write + reads, comb gathers) = 0.29 TB/s, 4.5 % of the measured HBM copy peak; not the bound",
-                         "hbm_frac": (6.602e9 * n / (1 << 20)) / ((dsm_ms / max(dsm_launches, 1)) * 1e-3) / (hbm_peak_gbs() * 1e9),
+                         # The same launch counted with the complete-formula work of rounds 1-2a (doubling 519, addition 849,
+                         # mixed 776 MAC32: what this kernel executed before its ladder moved to Jacobian coordinates).  The
+                         # result is identical, so this is the rate at which the OLD amount of work is now retired -- quoted
+                         # only to compare with the earlier rounds' fractions; `frac` above counts executed work.
+                         "mac32_per_item_kernel_complete_formulas": rcb_mac,
+                         "frac_if_counted_as_complete_formulas": (rcb_mac * n / ((dsm_ms / max(dsm_launches, 1)) * 1e-3) / imad_peak)
+                         if dsm_launches else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_dsm launch at 2^20 items, from the
+                         # committed capture profiles/r02b_ncu_dsm.txt (4.887 GB + 2.966 GB); scaled if --batch-log2 differs
+                         "traffic": 7.853e9 * n / (1 << 20), "traffic_unit": "bytes per launch",
+                         "traffic_note": "ncu --set full, profiles/r02b_ncu_dsm.txt: ~7.5 KB per item (Jacobian multiples and "
+                                         "their Z products written and read back, 16 affine rows written, row and comb "
+                                         "gathers) = 0.41 TB/s, 5-6 % of the measured HBM copy peak; not the bound",
+                         "hbm_frac": (7.853e9 * n / (1 << 20)) / ((dsm_ms / max(dsm_launches, 1)) * 1e-3) / (hbm_peak_gbs() * 1e9),
                          "hbm_peak_gbs": hbm_peak_gbs()},
             "cpu_baseline": cpu,
             "msm": msm,

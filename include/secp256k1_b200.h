@@ -68,8 +68,8 @@ typedef struct s256_ctx s256_ctx;
  * the default chunk capacity (2^20 items); larger batches are processed in
  * chunks.  Builds the generator tables on the device (the reference does this
  * at package init, point_mul_table.go:75-100,147-160).  Device memory per
- * context: 1.5 GiB of generator tables plus about 2.1 KB of scratch per item of
- * max_batch (2.2 GB at the default); S256_ERR_NOMEM if that does not fit. */
+ * context: 1.5 GiB of generator tables plus about 2.6 KB of scratch per item of
+ * max_batch (2.7 GB at the default); S256_ERR_NOMEM if that does not fit. */
 int s256_init(s256_ctx **ctx, int device, size_t max_batch);
 void s256_free(s256_ctx *ctx);
 const char *s256_strerror(int code);

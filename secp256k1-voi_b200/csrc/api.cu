@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(S256_TPB) k_schnorr_scalars(const uint8_t *pkx
 #ifndef S256_DSM_TPB
 #define S256_DSM_TPB S256_TPB
 #endif
-// One inversion per CTA instead of one per item (Montgomery's trick across the CTA): every thread leaves the product
+// One inversion per CTA instead of one per item (Montgomery's trick across the CTA; used by the constant-time ladder
+// for its public table -- the verification ladder needs no inversion any more): every thread leaves the product
 // of its table's Z's in shared memory, warp 0 takes TPB / 32 of them per lane, multiplies them up, forms the
 // product of all OTHER lanes' values with an xor butterfly (9 products), inverts the CTA's total once (safegcd: 23 k
 // instructions, which each of the four warps used to spend) and walks back to the individual inverses.  Public data.
@@ -248,20 +249,6 @@ __device__ __forceinline__ void cta_invert(F &f, fe &inv, const fe &c, fe *sh) {
     __syncthreads();
     inv = sh[threadIdx.x];
 }
-#if defined(S256_DSM_JAC) && !defined(S256_DSM_OWN_INV)
-__global__ void __launch_bounds__(S256_DSM_TPB, S256_DSM_MINB)
-    k_dsm(size_t n, const apt *aff, const sc *u1, const int8_t *dig1, const int8_t *dig2, const uint8_t *sfl, pt *tbl,
-          pt *res, const apt *comb) {
-    __shared__ fe sh[S256_DSM_TPB];
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;
-    fe_ops<DSM_VT> f;
-    fe zprod = fe_one(), inv;
-    if (live) item_dsm_table(f, i, aff, tbl, zprod);
-    cta_invert<S256_DSM_TPB>(f, inv, zprod, sh);
-    if (live) item_dsm_ladder(f, i, n, inv, u1, dig1, dig2, sfl, tbl, res, comb);
-}
-#else
 __global__ void __launch_bounds__(S256_DSM_TPB, S256_DSM_MINB)
     k_dsm(size_t n, const apt *aff, const sc *u1, const int8_t *dig1, const int8_t *dig2, const uint8_t *sfl, pt *tbl,
           pt *res, const apt *comb) {
@@ -269,7 +256,6 @@ __global__ void __launch_bounds__(S256_DSM_TPB, S256_DSM_MINB)
     if (i >= n) return;
     item_dsm(i, n, aff, u1, dig1, dig2, sfl, tbl, res, comb);
 }
-#endif
 
 // 4-bit windows over an affine table: entries 2..8 x 64 bytes per thread = 56 KB of shared memory per CTA, four CTAs per SM
 #ifndef S256_SM_MINB
@@ -1251,7 +1237,7 @@ extern "C" int s256_debug_ladder_add_count(s256_ctx *ctx, size_t n, uint64_t *ad
 }
 // executed MAC32 of one k_dsm item given its measured number of ladder additions (both halves) and beta multiplications
 // The Jacobian ladder (jac.cuh): doubling 2 M + 5 S (or 3 M + 4 S), mixed addition 6 M + 3 S + one fused pair, the table's
-// normalisation (suffix products, one safegcd inversion, 5 M + S per row) and the conversion of the result.
+// scaling to a common denominator (kernels.cuh) and the conversion of the result.
 struct dsm_costs {
     double dbl, add, mix, table, tail;
 };
@@ -1271,8 +1257,11 @@ static dsm_costs dsm_cost_model() {
 #endif
     c.mix = 6 * M + 3 * S + F2;
     c.add = c.mix;  // the ladder adds affine rows
-    const double inv_fe = 20 * 90;
-    c.table = (DSM_TS / 2) * c.dbl + (DSM_TS / 2 - 1) * c.mix + (DSM_TS - 2) * M + inv_fe + (DSM_TS - 2) * (5 * M + S) + (3 * M + S);
+    // 8 doublings + 7 mixed additions; TS - 2 suffix products; per row k = 3 .. TS - 1 two products for the cofactor
+    // Z_all / Z_k and the running prefix (one for the last row), S + 3 M to scale a row, the same for P itself, and
+    // one product to come back from the isomorphic curve -- no inversion
+    c.table = (DSM_TS / 2) * c.dbl + (DSM_TS / 2 - 1) * c.mix + (DSM_TS - 2) * M + (2 * (DSM_TS - 3) + 1) * M +
+              DSM_TS * (3 * M + S) + M;
     c.tail = 2 * M + S;
 #else
 #ifndef S256_NO_FUSED

@@ -387,16 +387,18 @@ S256_HD void apt_fetch64(apt &r, const apt *p) {
     r = *p;
 #endif
 }
-// Jacobian form (jac.cuh).  Table: [2..TS]P in Jacobian coordinates by doublings and mixed additions, then ONE
-// inversion per item (Montgomery's trick over the TS - 1 Z's, safegcd) turns it into TS affine rows, so that every
-// ladder addition is a mixed one.  Layout of the item's scratch (bytes): [0, 64) P; [64, 64 + 96 (TS - 1)) the
-// Jacobian multiples 2..TS; then the suffix products Z_k ... Z_TS for k = 3..TS.  The affine rows overwrite the front
-// in ascending order: row k ends at 64 k, the first Jacobian multiple still needed (k + 1) starts at 64 + 96 (k - 1).
-// The ladder is three phases so that the kernel can share the inversion between the items of a CTA (api.cu k_dsm):
-// item_dsm_table leaves the Jacobian multiples and returns the product of their Z's; the caller inverts it;
-// item_dsm_ladder normalises the table with that inverse and runs the ladder.  item_dsm is the plain composition.
+// Jacobian form (jac.cuh).  Table: [2..TS]P in Jacobian coordinates by doublings and mixed additions, then every row
+// is scaled to the COMMON denominator Z_all = Z_2 ... Z_TS (no inversion), which makes the TS rows affine points of
+// an isomorphic curve; every ladder addition is then a mixed one.  Layout of the item's scratch (bytes): [0, 64) P;
+// [64, 64 + 96 (TS - 1)) the Jacobian multiples 2..TS; then the suffix products Z_k ... Z_TS for k = 3..TS.  The
+// affine rows overwrite the front in ascending order: row k ends at 64 k, the first Jacobian multiple still needed
+// (k + 1) starts at 64 + 96 (k - 1).  item_dsm_table builds the multiples, item_dsm_ladder scales them and runs the
+// ladder; item_dsm is the composition.
+// (Round 2 first divided every row by its own Z -- one safegcd inversion per item through Montgomery's trick, 20.01 ms
+// at 2^20; then one inversion per CTA, 19.14 ms, with 6 % of the warp time spent at the barrier around it; the
+// common denominator needs neither: 18.14 ms.)
 template <class F>
-S256_HD void item_dsm_table(F &f, size_t i, const apt *aff, pt *tbl, fe &zprod) {
+S256_HD void item_dsm_table(F &f, size_t i, const apt *aff, pt *tbl) {
     char *base = reinterpret_cast<char *>(tbl + i * (size_t)DSM_TSTRIDE);
     apt *A = reinterpret_cast<apt *>(base);
     {
@@ -430,36 +432,57 @@ S256_HD void item_dsm_table(F &f, size_t i, const apt *aff, pt *tbl, fe &zprod) 
             fe zk = J[k - 2].z;
             f.mul(run, run, zk);
         }
-        zprod = run;
     }
 }
 // inv = (Z_2 ... Z_TS)^-1 of this item's table
 template <class F>
-S256_HD void item_dsm_ladder(F &f, size_t i, size_t n, fe inv, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
+S256_HD void item_dsm_ladder(F &f, size_t i, size_t n, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
                              const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
     char *base = reinterpret_cast<char *>(tbl + i * (size_t)DSM_TSTRIDE);
     apt *A = reinterpret_cast<apt *>(base);
     {
         pt *J = reinterpret_cast<pt *>(base + 64);
         fe *C = reinterpret_cast<fe *>(base + 64 + 96 * (DSM_TS - 1));
-        // inv becomes (Z_k ... Z_TS)^-1 as k advances
+        // No inversion at all: every row is brought to the COMMON denominator Z_all = Z_2 ... Z_TS instead of to 1.
+        // (X_k w^2, Y_k w^3) with w = Z_all / Z_k = (Z_2 .. Z_(k-1)) (Z_(k+1) .. Z_TS) are the affine coordinates of k P
+        // on the isomorphic curve y^2 = x^3 + 7 Z_all^6; neither the a = 0 doubling nor the mixed addition nor x -> beta x
+        // involves b, so the ladder runs there unchanged, and its result (X', Y', Z') is (X', Y', Z' Z_all) on secp256k1.
+        // Same 5 M + S per row as the division by Z_k, minus the inversion and the CTA-wide exchange around it.
+        fe pre = fe_one();
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
         for (int k = 2; k <= DSM_TS; k++) {
             pt jk = J[k - 2];
-            fe zi = inv, zi2;
-            if (k < DSM_TS) {
-                fe ck = C[k + 1 - 3];
-                f.mul(zi, inv, ck);      // Z_k^-1
-                f.mul(inv, inv, jk.z);
+            fe w, w2;
+            if (k == 2) {
+                w = C[0];
+                pre = jk.z;
+            } else {
+                if (k < DSM_TS) {
+                    fe ck = C[k + 1 - 3];
+                    f.mul(w, pre, ck);
+                } else {
+                    w = pre;
+                }
+                f.mul(pre, pre, jk.z);
             }
             apt a;
-            f.sqr(zi2, zi);
-            f.mul(a.x, jk.x, zi2);
-            f.mul(zi2, zi2, zi);
-            f.mul(a.y, jk.y, zi2);
+            f.sqr(w2, w);
+            f.mul(a.x, jk.x, w2);
+            f.mul(w2, w2, w);
+            f.mul(a.y, jk.y, w2);
             A[k - 1] = a;
+        }
+        {
+            apt a = A[0];
+            fe zz;
+            f.sqr(zz, pre);
+            f.mul(a.x, a.x, zz);
+            f.mul(zz, zz, pre);
+            f.mul(a.y, a.y, zz);
+            A[0] = a;
+            C[0] = pre;  // Z_all, for the way back
         }
     }
     uint32_t fl = sfl[i];
@@ -510,6 +533,10 @@ S256_HD void item_dsm_ladder(F &f, size_t i, size_t n, fe inv, const sc *u1s, co
             }
         }
     }
+    if (!inf) {  // back from the isomorphic curve before the G half, whose rows are points of secp256k1 itself
+        fe zall = reinterpret_cast<const fe *>(base + 64 + 96 * (DSM_TS - 1))[0];
+        f.mul(acc.z, acc.z, zall);
+    }
     sc u1 = u1s[i];
     uint32_t carry = 0;
 #if defined(__CUDA_ARCH__)
@@ -534,10 +561,8 @@ S256_HD void item_dsm_ladder(F &f, size_t i, size_t n, fe inv, const sc *u1s, co
 S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
                       const uint8_t *sfl, pt *tbl, pt *res, const apt *comb) {
     fe_ops<DSM_VT> f;
-    fe zprod, inv;
-    item_dsm_table(f, i, aff, tbl, zprod);
-    fe_invert(inv, zprod);
-    item_dsm_ladder(f, i, n, inv, u1s, dig1, dig2, sfl, tbl, res, comb);
+    item_dsm_table(f, i, aff, tbl);
+    item_dsm_ladder(f, i, n, u1s, dig1, dig2, sfl, tbl, res, comb);
 }
 #else
 S256_HD void item_dsm(size_t i, size_t n, const apt *aff, const sc *u1s, const int8_t *dig1, const int8_t *dig2,
