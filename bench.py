@@ -555,12 +555,12 @@ def main():
                          "frac_if_counted_as_complete_formulas": (rcb_mac * n / ((dsm_ms / max(dsm_launches, 1)) * 1e-3) / imad_peak)
                          if dsm_launches else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_dsm launch at 2^20 items, from the
-                         # committed capture profiles/r02b_ncu_dsm.txt (4.887 GB + 2.966 GB); scaled if --batch-log2 differs
-                         "traffic": 7.853e9 * n / (1 << 20), "traffic_unit": "bytes per launch",
-                         "traffic_note": "ncu --set full, profiles/r02b_ncu_dsm.txt: ~7.5 KB per item (Jacobian multiples and "
+                         # committed capture profiles/r02b_ncu_dsm.txt (4.155 GB + 2.469 GB); scaled if --batch-log2 differs
+                         "traffic": 6.624e9 * n / (1 << 20), "traffic_unit": "bytes per launch",
+                         "traffic_note": "ncu --set full, profiles/r02b_ncu_dsm.txt: ~6.3 KB per item (Jacobian multiples and "
                                          "their Z products written and read back, 16 affine rows written, row and comb "
-                                         "gathers) = 0.41 TB/s, 5-6 % of the measured HBM copy peak; not the bound",
-                         "hbm_frac": (7.853e9 * n / (1 << 20)) / ((dsm_ms / max(dsm_launches, 1)) * 1e-3) / (hbm_peak_gbs() * 1e9),
+                                         "gathers) = 0.36 TB/s, 5-6 % of the measured HBM copy peak; not the bound",
+                         "hbm_frac": (6.624e9 * n / (1 << 20)) / ((dsm_ms / max(dsm_launches, 1)) * 1e-3) / (hbm_peak_gbs() * 1e9),
                          "hbm_peak_gbs": hbm_peak_gbs()},
             "cpu_baseline": cpu,
             "msm": msm,

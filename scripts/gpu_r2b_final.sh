@@ -12,4 +12,4 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 python scripts/launch_summary.py gpurun_out/r2b_launches_bench.csv > gpurun_out/r2b_launches_bench.txt; cat gpurun_out/r2b_launches_bench.txt
 LOG2N=20 WHICH=verify timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_dsm -s 2 -c 1 -o gpurun_out/r2b_prof_dsm -f python scripts/prof_kernels.py > gpurun_out/ncu1.log 2>&1
 LOG2N=18 WHICH=ecdh timeout 900 ncu --set full --clock-control none -k regex:k_scalar_mult_ct -s 2 -c 1 -o gpurun_out/r2b_prof_ct -f python scripts/prof_kernels.py > gpurun_out/ncu2.log 2>&1
-tail -1 gpurun_out/ncu*.log
+for f in gpurun_out/ncu*.log; do tail -1 $f; done
