@@ -312,6 +312,28 @@ def check_double_scalar_mult(be, o, n=96):
     assert not got[0].any() and not got[1].any()
 
 
+def check_double_scalar_mult_small_multiples(be, o):
+    """Small multiples of G everywhere: P = j G, u2 small, u1 = +-(j u2) + delta.  The partial sums of the two halves
+    collide all the time (equal points: the doubling branch of the Jacobian ladder; opposite points: its identity
+    flag; near misses on either side), in the first comb window, where every one of these u1 lives, and -- for the rows
+    with 2^22 and 2^44 factors -- in the second and third."""
+    rows_ = []
+    for j in (1, 2, 3, 5, 16, 17, 31):
+        for u2 in (0, 1, 2, 3, 15, 16, 17, 32, 33, 511):
+            for sign in (1, -1):
+                for delta in (-1, 0, 1):
+                    for scale in (1, 2**22, 2**44):
+                        rows_.append((j, (sign * j * u2 * scale + delta) % N, u2 * scale % N))
+    d = [r[0] for r in rows_]
+    pts, _ = o.batch_scalar_base_mult(rows([b32(x) for x in d], 32))
+    U1, U2 = rows([b32(r[1]) for r in rows_], 32), rows([b32(r[2]) for r in rows_], 32)
+    got, st = be.double_scalar_mult_basepoint_vartime(U1, U2, pts)
+    exp, est = o.batch_double_scalar_mult(U1, U2, pts)
+    assert np.array_equal(st, est), np.nonzero(st != est)[0][:10].tolist()
+    assert np.array_equal(got, exp), np.nonzero((got != exp).any(axis=1))[0][:10].tolist()
+    assert (st == 2).sum() >= len(rows_) // 12  # the identity really occurs (sign = -1, delta = 0, and u2 = 0 with delta = 0)
+
+
 def check_recover_synth(be, o, n=64):
     w = synth.ecdsa_batch(n, oracle_base_mult(o), corrupt_every=0)
     sig65 = np.concatenate([np.concatenate([w["sig64"], np.full((n, 1), v, np.uint8)], axis=1) for v in (0, 1, 2, 3, 4, 27)])

@@ -49,6 +49,7 @@ def test_ecdsa_edges(engine, oracle):
 
 def test_double_scalar_mult(engine, oracle):
     ps.check_double_scalar_mult(engine, oracle, n=2048)
+    ps.check_double_scalar_mult_small_multiples(engine, oracle)
 
 
 def test_recover(engine, oracle):

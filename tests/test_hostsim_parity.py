@@ -71,6 +71,8 @@ def test_ecdsa_edges(oracle):
 
 def test_double_scalar_mult(oracle):
     ps.check_double_scalar_mult(be, oracle, n=40)
+    ps.check_double_scalar_mult(be, oracle, n=96)   # with the crafted mid-ladder collision rows
+    ps.check_double_scalar_mult_small_multiples(be, oracle)
 
 
 def test_recover(oracle):
