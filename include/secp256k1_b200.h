@@ -16,7 +16,8 @@
  *     data-level outcomes: one status byte per item;
  *   - a context is bound to one CUDA device and may be used from any thread
  *     (calls on one context serialise on an internal mutex); use one context
- *     per GPU, one process per GPU for multi-GPU runs;
+ *     per GPU -- or two, from two host threads, so that one batch's copies
+ *     overlap the other's arithmetic -- and one process per GPU for multi-GPU runs;
  *   - there is NO CPU fallback: without a usable CUDA device s256_init fails.
  *
  * The *_dev twins take device pointers and a cudaStream_t (as void*; NULL =
