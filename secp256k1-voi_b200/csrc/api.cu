@@ -400,7 +400,7 @@ extern "C" void s256_free(s256_ctx *ctx) {
     {
         dev_guard g(ctx->device);
         s256_internal_comm_release(ctx);
-        void *ptrs[] = {ctx->comb, ctx->ct_tab, ctx->ct_tab_small, ctx->aff, ctx->u1,   ctx->dig1, ctx->dig2, ctx->sfl, ctx->pvalid,
+        void *ptrs[] = {ctx->comb, ctx->ct_tab, ctx->ct_tab_small, ctx->ct_tab_huge, ctx->aff, ctx->u1,   ctx->dig1, ctx->dig2, ctx->sfl, ctx->pvalid,
                         ctx->cstat, ctx->tbl,   ctx->res, ctx->in_a, ctx->in_b, ctx->in_c, ctx->out, ctx->st,
                         ctx->sink, ctx->msm_counts, ctx->msm_offsets, ctx->msm_cursor, ctx->msm_entries, ctx->msm_flag,
                         ctx->msm_buckets, ctx->msm_win, ctx->msm_acc, ctx->msm_tmp, ctx->msm_cub, ctx->msm_nsl, ctx->msm_sloff,
@@ -423,6 +423,7 @@ static int ctx_alloc(s256_ctx *ctx) {
     CK(cudaMalloc(&ctx->comb, sizeof(apt) * ((size_t)COMB_NW * COMB_SZ + COMB_NW)));  // + the window bases B_w
     CK(cudaMalloc(&ctx->ct_tab, sizeof(apt) * ct_cfg<CT_WB>::NW * ct_cfg<CT_WB>::SZ));
     CK(cudaMalloc(&ctx->ct_tab_small, sizeof(apt) * ct_cfg<CT_WB_SMALL>::NW * ct_cfg<CT_WB_SMALL>::SZ));
+    CK(cudaMalloc(&ctx->ct_tab_huge, sizeof(apt) * ct_cfg<7>::NW * ct_cfg<7>::SZ));
     CK(cudaMalloc(&ctx->aff, sizeof(apt) * cap));
     CK(cudaMalloc(&ctx->u1, sizeof(sc) * cap));
     CK(cudaMalloc(&ctx->dig1, (size_t)DSM_ND * cap));
@@ -480,6 +481,7 @@ extern "C" int s256_init(s256_ctx **out, int device, size_t max_batch) {
                ctx->ct_tab);
         LAUNCH(ctx, k_gen_ct_table<CT_WB_SMALL>, grid_for((size_t)ct_cfg<CT_WB_SMALL>::NW * ct_cfg<CT_WB_SMALL>::SZ), 0,
                ctx->stream, ctx->ct_tab_small);
+        LAUNCH(ctx, k_gen_ct_table<7>, grid_for((size_t)ct_cfg<7>::NW * ct_cfg<7>::SZ), 0, ctx->stream, ctx->ct_tab_huge);
         s256_ct_kernels_init();
         if (CT_SMEM_BYTES)
             cudaFuncSetAttribute(k_scalar_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM_BYTES);
@@ -579,7 +581,7 @@ static int chunk_dsm(s256_ctx *ctx, const view &v, const uint8_t *u1, const uint
 }
 static int chunk_base_mult(s256_ctx *ctx, const view &v, const uint8_t *k32, size_t n, uint8_t *out65, uint8_t *status,
                            cudaStream_t s) {
-    s256_launch_base_mult_ct(k32, n, ctx->ct_tab, ctx->ct_tab_small, v.res, s);
+    s256_launch_base_mult_ct(k32, n, ctx->ct_tab, ctx->ct_tab_small, ctx->ct_tab_huge, v.res, s);
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     DISPATCH_K(n, LAUNCH(ctx, k_finish_affine<KK>, grid_for_groups(n, KK), 0, s, n, v.res, (const uint8_t *)nullptr,
            (const uint8_t *)nullptr, v.cstat, 0, out65, status, (const uint8_t *)nullptr));
@@ -1312,9 +1314,9 @@ extern "C" double s256_mac32_per_item(const char *name) {
     if (s == "ecdsa_recover") return sqrt_fe + (6 * ZN + inv_sc / INV_K + split) + dsm + affine;
     if (s == "schnorr_verify") return sqrt_fe + (ZN + split) + dsm + affine;
     if (s == "double_scalar_mult_basepoint_vartime") return oncurve + split + dsm + affine;
-    if (s == "scalar_base_mult") return CT_NW * mix_ct + affine;
-    if (s == "schnorr_sign") return 2 * (CT_NW * mix_ct + affine) + 2 * ZN;  // + ~9 SHA-256 blocks
-    if (s == "ecdsa_sign_rfc6979") return CT_NW * mix_ct + affine + (5 * ZN + inv_sc / INV_K);  // + 22 SHA-256 blocks
+    if (s == "scalar_base_mult") return ct_cfg<7>::NW * mix_ct + affine;  // (large batches: the 7-bit kernel, kern_ct.cu)
+    if (s == "schnorr_sign") return 2 * (ct_cfg<7>::NW * mix_ct + affine) + 2 * ZN;  // + ~9 SHA-256 blocks
+    if (s == "ecdsa_sign_rfc6979") return ct_cfg<7>::NW * mix_ct + affine + (5 * ZN + inv_sc / INV_K);  // + 22 SHA-256 blocks
     if (s == "scalar_mult" || s == "ecdh") {
         const double tab = (CTM_TS / 2) * dbl_ct + (CTM_TS / 2 - 1) * mix_ct + 5 * (CTM_TS - 1) * M + inv_fe;  // + normalisation
         const double lad = (CTM_ND - 1) * CTM_W * dbl_ct + 2 * CTM_ND * mix_ct + CTM_ND * M;

@@ -43,7 +43,7 @@ static int chunk_sign(s256_ctx *ctx, const view &v, const uint8_t *priv32, const
                       uint8_t *sig64, uint8_t *recid, uint8_t *status, cudaStream_t s) {
     uint8_t *kbuf = reinterpret_cast<uint8_t *>(v.u1);
     LAUNCH(ctx, k_rfc6979_nonce, grid_for(n), 0, s, priv32, digest32, n, kbuf, v.pvalid);
-    s256_launch_base_mult_ct(kbuf, n, ctx->ct_tab, ctx->ct_tab_small, v.res, s);
+    s256_launch_base_mult_ct(kbuf, n, ctx->ct_tab, ctx->ct_tab_small, ctx->ct_tab_huge, v.res, s);
     ctx->launches.fetch_add(1, std::memory_order_relaxed);
     s256_launch_finish_affine(ctx, n, v.res, nullptr, nullptr, v.cstat, 0, v.out, v.sfl, nullptr, s);
     DISPATCH_K(n, LAUNCH(ctx, k_sign_finish<KK>, grid_for_groups(n, KK), 0, s, n, priv32, digest32, kbuf, v.pvalid, v.out,
@@ -59,10 +59,10 @@ static int chunk_schnorr_sign(s256_ctx *ctx, const view &v, const uint8_t *priv3
                               const uint8_t *aux32, size_t n, uint8_t *sig64, uint8_t *status, cudaStream_t s) {
     uint8_t *arena = reinterpret_cast<uint8_t *>(v.tbl);
     uint8_t *r65 = arena, *kbuf = arena + 65 * n;
-    s256_launch_base_mult_ct(priv32, n, ctx->ct_tab, ctx->ct_tab_small, v.res, s);
+    s256_launch_base_mult_ct(priv32, n, ctx->ct_tab, ctx->ct_tab_small, ctx->ct_tab_huge, v.res, s);
     s256_launch_finish_affine(ctx, n, v.res, nullptr, nullptr, v.cstat, 0, v.out, v.sfl, nullptr, s);
     LAUNCH(ctx, k_schnorr_nonce, grid_for(n), 0, s, priv32, v.out, msg, msg_len, aux32, n, kbuf, v.pvalid);
-    s256_launch_base_mult_ct(kbuf, n, ctx->ct_tab, ctx->ct_tab_small, v.res, s);
+    s256_launch_base_mult_ct(kbuf, n, ctx->ct_tab, ctx->ct_tab_small, ctx->ct_tab_huge, v.res, s);
     ctx->launches.fetch_add(2, std::memory_order_relaxed);
     s256_launch_finish_affine(ctx, n, v.res, nullptr, nullptr, v.cstat, 0, r65, v.sfl, nullptr, s);
     LAUNCH(ctx, k_schnorr_sign_finish, grid_for(n), 0, s, priv32, v.out, r65, kbuf, msg, msg_len, v.pvalid, n, sig64,

@@ -31,7 +31,7 @@ struct s256_ctx {
     std::atomic<uint64_t> launches{0};
     // constant tables
     apt *comb = nullptr;    // [COMB_NW][COMB_SZ]
-    apt *ct_tab = nullptr, *ct_tab_small = nullptr;  // signed-window tables of G, 6-bit and 5-bit (kernels.cuh)
+    apt *ct_tab = nullptr, *ct_tab_small = nullptr, *ct_tab_huge = nullptr;  // signed-window tables of G: 6-, 5- and 7-bit (kernels.cuh)
     // per-chunk scratch
     apt *aff = nullptr;
     sc *u1 = nullptr;

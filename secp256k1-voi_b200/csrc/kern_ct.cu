@@ -16,21 +16,32 @@ using namespace s256;
 #define S256_BM_MINB 4
 #endif
 #define S256_BM_MINB_BIG 2
+#ifndef S256_BM_W7_MIN_DEFAULT
+#define S256_BM_W7_MIN_DEFAULT 16385  // batches from this size on take the 7-bit kernel: faster than the 6-bit one at every
+                                       // size above the lane-split range (20 000: 0.304 vs 0.308 ms ... 2^20: 6.56 vs 6.84 ms)
+#endif
 #ifndef S256_BM_SPLIT4_MAX
 #define S256_BM_SPLIT4_MAX 16384
 #endif
-constexpr size_t CT_BYTES_BIG = (size_t)ct_cfg<CT_WB>::NW * ct_cfg<CT_WB>::SZ * sizeof(apt);
+template <int WB>
+__host__ __device__ constexpr size_t ct_bytes_big() { return (size_t)ct_cfg<WB>::NW * ct_cfg<WB>::SZ * sizeof(apt); }
+constexpr size_t CT_BYTES_BIG = ct_bytes_big<CT_WB>();
+// the large-batch flavour: 7-bit windows, 37 additions instead of 43 over a 152 KB table -- one CTA of 512 threads per SM
+// (the same 16 warps); staging 152 KB per CTA only pays when every CTA has many scalars to work through
+constexpr int CT_WB_HUGE = 7;
+#define S256_TPB_HUGE 512
+constexpr size_t CT_BYTES_HUGE = ct_bytes_big<CT_WB_HUGE>();
 // lane-split kernels: every window's row is followed by 16 bytes of padding (bank spreading, kernels.cuh)
 constexpr size_t CT_ROW_SMALL = (size_t)ct_cfg<CT_WB_SMALL>::SZ * sizeof(apt), CT_ROW_SMALL_PAD = CT_ROW_SMALL + 16;
 constexpr size_t CT_BYTES_SMALL = (size_t)ct_cfg<CT_WB_SMALL>::NW * CT_ROW_SMALL_PAD;
 
-__global__ void __launch_bounds__(S256_TPB_BIG, S256_BM_MINB_BIG)
-    k_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_g, pt *res) {
+template <int WB>
+__device__ __forceinline__ void base_mult_ct_body(const uint8_t *k32, size_t n, const apt *tab_g, pt *res) {
     extern __shared__ uint4 smem_raw[];
     apt *tab = reinterpret_cast<apt *>(smem_raw);
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(tab_g);
-        const int nvec = (int)(CT_BYTES_BIG / 16);
+        const int nvec = (int)(ct_bytes_big<WB>() / 16);
         for (int v = threadIdx.x; v < nvec; v += blockDim.x) smem_raw[v] = src[v];
     }
     __syncthreads();
@@ -43,9 +54,17 @@ __global__ void __launch_bounds__(S256_TPB_BIG, S256_BM_MINB_BIG)
         sc k;
         sc_from_be32(k, k32 + 32 * i);
         pt acc;
-        item_base_mult_ct<CT_WB>(acc, k, tab);
+        item_base_mult_ct<WB>(acc, k, tab);
         res[i] = acc;
     }
+}
+__global__ void __launch_bounds__(S256_TPB_BIG, S256_BM_MINB_BIG)
+    k_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_g, pt *res) {
+    base_mult_ct_body<CT_WB>(k32, n, tab_g, res);
+}
+__global__ void __launch_bounds__(S256_TPB_HUGE, 1)
+    k_base_mult_ct_w7(const uint8_t *k32, size_t n, const apt *tab_g, pt *res) {
+    base_mult_ct_body<CT_WB_HUGE>(k32, n, tab_g, res);
 }
 
 
@@ -93,6 +112,8 @@ void s256_ct_kernels_init() {
     cudaFuncSetAttribute(k_base_mult_ct_split<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_base_mult_ct_split<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(k_base_mult_ct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_BIG);
+    cudaFuncSetAttribute(k_base_mult_ct_w7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_BYTES_HUGE);
+    cudaFuncSetAttribute(k_base_mult_ct_w7, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // ask for the largest shared-memory carve-out: without the hint the driver sizes it for ONE CTA and the
     // second (fourth) CTA of an SM waits for the first to retire
     cudaFuncSetAttribute(k_base_mult_ct, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -108,10 +129,17 @@ void s256_ct_kernels_init() {
                 fa.numRegs, fa.sharedSizeBytes, CT_BYTES_BIG, b);
     }
 }
-// tab_big: [NW(6)][SZ(6)], tab_small: [NW(5)][SZ(5)] (ctx->ct_tab, ctx->ct_tab_small)
-void s256_launch_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_big, const apt *tab_small, pt *res,
-                              cudaStream_t s) {
+// tab_big: [NW(6)][SZ(6)], tab_small: [NW(5)][SZ(5)], tab_huge: [NW(7)][SZ(7)] (ctx->ct_tab, ctx->ct_tab_small, ctx->ct_tab_huge)
+void s256_launch_base_mult_ct(const uint8_t *k32, size_t n, const apt *tab_big, const apt *tab_small, const apt *tab_huge,
+                              pt *res, cudaStream_t s) {
     if (n == 0) return;
+    static const size_t w7_min = getenv("S256_BM_W7_MIN") ? (size_t)atoll(getenv("S256_BM_W7_MIN")) : (size_t)S256_BM_W7_MIN_DEFAULT;
+    if (tab_huge && n >= w7_min) {
+        size_t warps7 = (n + 31) / 32;
+        unsigned g7 = warps7 < (size_t)g_sm_count ? (unsigned)warps7 : (unsigned)g_sm_count;
+        k_base_mult_ct_w7<<<g7, S256_TPB_HUGE, CT_BYTES_HUGE, s>>>(k32, n, tab_huge, res);
+        return;
+    }
     // small batches are latency bound: deal the windows of each scalar to 8 / 4 lanes (16 lanes measured
     // slower at n = 4096: 0.227 against 0.198 ms)
     static const int force_t = getenv("S256_BM_T") ? atoi(getenv("S256_BM_T")) : 0;  // tuning knob: lanes per scalar

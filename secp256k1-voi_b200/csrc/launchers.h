@@ -11,4 +11,4 @@
 
 void s256_ct_kernels_init();
 void s256_launch_base_mult_ct(const uint8_t *k32, size_t n, const s256::apt *tab_big, const s256::apt *tab_small,
-                              s256::pt *res, cudaStream_t s);
+                              const s256::apt *tab_huge, s256::pt *res, cudaStream_t s);

@@ -32,7 +32,7 @@ def secret_sets(n):
 
 
 def main():
-    small, big = 4096, 40000        # the lane-split kernel (<= 16384 items) and the throughput kernel
+    small, big = 4096, 40000        # the lane-split kernel (<= 16384 items) and the throughput kernel (7-bit windows)
     eng = pkg.Engine(device=0, max_batch=big)
     pub_small, _ = eng.scalar_base_mult(pkg.synth.base_mult_scalars(small, start=100))       # fixed PUBLIC points
     pub_small = np.asarray(pub_small).copy()

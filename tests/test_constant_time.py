@@ -103,6 +103,7 @@ def test_secret_independent_counters(tmp_path):
     if keep:
         shutil.copy(str(log), keep)
     assert not violations, "counters depend on the secret:\n" + "\n".join(map(str, violations))
-    for k in ("k_base_mult_ct", "k_scalar_mult_ct", "k_rfc6979_nonce", "k_sign_finish", "k_schnorr_nonce", "k_finish_affine"):
+    for k in ("k_base_mult_ct_split", "k_base_mult_ct_w7", "k_scalar_mult_ct", "k_rfc6979_nonce", "k_sign_finish", "k_schnorr_nonce",
+              "k_finish_affine"):
         assert any(b.startswith(k) for b in seen), (k, sorted(seen))
     assert checked >= 8 * 12
