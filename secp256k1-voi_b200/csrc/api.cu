@@ -1314,9 +1314,14 @@ extern "C" double s256_mac32_per_item(const char *name) {
     if (s == "ecdsa_recover") return sqrt_fe + (6 * ZN + inv_sc / INV_K + split) + dsm + affine;
     if (s == "schnorr_verify") return sqrt_fe + (ZN + split) + dsm + affine;
     if (s == "double_scalar_mult_basepoint_vartime") return oncurve + split + dsm + affine;
-    if (s == "scalar_base_mult") return ct_cfg<7>::NW * mix_ct + affine;  // (large batches: the 7-bit kernel, kern_ct.cu)
-    if (s == "schnorr_sign") return 2 * (ct_cfg<7>::NW * mix_ct + affine) + 2 * ZN;  // + ~9 SHA-256 blocks
-    if (s == "ecdsa_sign_rfc6979") return ct_cfg<7>::NW * mix_ct + affine + (5 * ZN + inv_sc / INV_K);  // + 22 SHA-256 blocks
+#ifndef S256_BM_RCB
+    const double bm = ct_cfg<7>::NW * (8 * M + 3 * S) + 2 * M + S;  // large batches: 7-bit windows, Jacobian accumulator (kernels.cuh)
+#else
+    const double bm = ct_cfg<7>::NW * mix_ct;
+#endif
+    if (s == "scalar_base_mult") return bm + affine;
+    if (s == "schnorr_sign") return 2 * (bm + affine) + 2 * ZN;  // + ~9 SHA-256 blocks
+    if (s == "ecdsa_sign_rfc6979") return bm + affine + (5 * ZN + inv_sc / INV_K);  // + 22 SHA-256 blocks
     if (s == "scalar_mult" || s == "ecdh") {
         const double tab = (CTM_TS / 2) * dbl_ct + (CTM_TS / 2 - 1) * mix_ct + 5 * (CTM_TS - 1) * M + inv_fe;  // + normalisation
         const double lad = (CTM_ND - 1) * CTM_W * dbl_ct + 2 * CTM_ND * mix_ct + CTM_ND * M;

@@ -54,7 +54,11 @@ __device__ __forceinline__ void base_mult_ct_body(const uint8_t *k32, size_t n, 
         sc k;
         sc_from_be32(k, k32 + 32 * i);
         pt acc;
+#ifndef S256_BM_RCB
+        item_base_mult_ct_jac<WB>(acc, k, tab);  // Jacobian accumulator, result in homogeneous form (kernels.cuh)
+#else
         item_base_mult_ct<WB>(acc, k, tab);
+#endif
         res[i] = acc;
     }
 }

@@ -887,6 +887,82 @@ S256_HD void item_base_mult_ct(pt &acc, const sc &k, const apt *tab /* [NW][SZ] 
     }
 }
 
+// The throughput kernels run the same multiplication with a JACOBIAN accumulator and the mixed Jacobian addition
+// (jac.cuh) in its constant-time flavour: 8 M + 3 S = 719 MAC32 per window instead of 11 M = 805 for the complete mixed
+// addition, fewer additions / subtractions, still no branch and no address that depends on the scalar
+// (2^20 scalars: 6.55 -> 6.08 ms).  The formula is incomplete; here its exceptional cases CANNOT occur, and the only
+// special value, the identity the accumulator starts as, is a flag resolved by select:
+//   * Windows are taken in ascending order.  With B = 2^WB and digits |d_v| <= B/2, the accumulator before window w is
+//     A = sum_{v<w} d_v B^v, |A| <= (B/2)(B^w - 1)/(B - 1) < 0.51 B^w, and the entry added is E = d_w B^w with
+//     |E| >= B^w > |A| (a zero digit adds a dummy whose sum is discarded).  The formula fails iff A = +-E (mod n).
+//   * Below the top window |A -+ E| < (B/2 + 0.51) B^w < 2^252 < n, and A -+ E != 0 as integers: not congruent.
+//   * Top window (bits from 252 up): A + E = k, the scalar itself, reduced mod n by sc_from_be32: 0 <= k < n.
+//     A + E = 0 (mod n) would need k = 0, i.e. no non-zero digit at all.  A - E = 2A - k lies in (-n - 2^252.02,
+//     2^252.02); it is not 0 (|E| > |A|), and 2A - k = -n would need E = n + A to be a multiple of 2^252 with
+//     -0.51 * 2^252 < A < 0: A = (2^256 - n) - m 2^252 has no such value (m = 0 gives A > 0, m = 1 gives A < -0.9 * 2^252).
+//   * A = 0 (mod n) with |A| < n means A = 0, and then every lower digit is zero (the lowest non-zero digit d_v would
+//     have to satisfy B | d_v): the flag "all digits so far were zero" is exactly "the accumulator is the identity".
+// The lane-split small-batch kernels sum the windows in another order (partial sums per lane, folded by a tree) and
+// keep the complete formulas, as do their folds; -DS256_BM_RCB restores them here as well.
+#ifndef S256_BM_RCB
+template <int CT_WB = S256_CT_WB>
+S256_HD void item_base_mult_ct_jac(pt &out, const sc &k, const apt *tab) {
+    constexpr int CT_NW = ct_cfg<CT_WB>::NW, CT_SZ = ct_cfg<CT_WB>::SZ;
+    fe_ops<false> f;
+    pt acc;
+    acc.x = acc.y = acc.z = fe_zero();
+    uint32_t inf = 1u, carry = 0;
+    const fe one = fe_one();
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int w = 0; w < CT_NW; w++) {
+        uint32_t v = ct_window_bits<CT_WB>(k, w) + carry;
+        carry = (v + (uint32_t)CT_SZ - 1u) >> CT_WB;
+        int32_t d = (int32_t)v - (int32_t)(carry << CT_WB);
+        uint32_t sign = (uint32_t)d >> 31;
+        uint32_t mag = (uint32_t)((d ^ -(int32_t)sign) + (int32_t)sign);
+        apt sel;
+        sel.x = fe_zero();
+        sel.y = fe_zero();
+        const apt *row = tab + w * CT_SZ;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 2
+#endif
+        for (uint32_t j = 1; j <= (uint32_t)CT_SZ; j++) {
+            const bool hit = j == mag;
+            apt e = row[j - 1];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                sel.x.v[q] = hit ? e.x.v[q] : sel.x.v[q];
+                sel.y.v[q] = hit ? e.y.v[q] : sel.y.v[q];
+            }
+        }
+        uint32_t zero = (uint32_t)(mag == 0);
+        apt e1 = row[0];
+        fe_cmov(sel.x, sel.x, e1.x, zero);
+        fe_cmov(sel.y, sel.y, e1.y, zero);
+        fe_cneg(sel.y, sel.y, sign);
+        pt sum;
+        jac_add_mixed_nocheck(f, sum, acc, sel.x, sel.y);
+        // the accumulator is still the identity: the sum is the addend itself
+        fe_cmov(sum.x, sum.x, sel.x, inf);
+        fe_cmov(sum.y, sum.y, sel.y, inf);
+        fe_cmov(sum.z, sum.z, one, inf);
+        pt_cmov(acc, sum, acc, zero);
+        inf &= zero;
+    }
+    pt hom, id;
+    fe zz;
+    fe_sqr(zz, acc.z);
+    fe_mul(hom.x, acc.x, acc.z);
+    hom.y = acc.y;
+    fe_mul(hom.z, zz, acc.z);
+    pt_set_identity(id);
+    pt_cmov(out, hom, id, inf);
+}
+#endif
+
 // Small batches: the windows of one scalar are dealt round-robin to T lanes (window j*T + part in
 // iteration j, so the whole warp stays in lockstep); the caller folds the T partial points with
 // complete additions.  Digits are recoded first (carry chain) into a local array that is then read

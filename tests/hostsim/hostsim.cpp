@@ -129,8 +129,10 @@ EXPORT void sim_scalar_base_mult(const uint8_t *k32, size_t n, uint8_t *out65, u
             for (int off = T / 2; off >= 1; off >>= 1)
                 for (int p = 0; p < off; p++) pt_add(part[p], part[p], part[p + off]);
             s.res[i] = part[0];
-        } else {
+        } else if (i & 1) {
             item_base_mult_ct(s.res[i], k, g_ct.data());
+        } else {  // the throughput kernels' form: Jacobian accumulator (kernels.cuh)
+            item_base_mult_ct_jac(s.res[i], k, g_ct.data());
         }
     }
     run_finish(s, n, false, false, 0, out65, status, nullptr);

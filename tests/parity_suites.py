@@ -121,6 +121,31 @@ def check_base_mult(be, o, n=64):
     assert got[1].tobytes().hex() == kats["g_uncompressed"]
 
 
+def check_base_mult_edges(be, o, n=20000):
+    """The large-batch fixed-base kernel (7-bit windows, Jacobian accumulator whose exceptional cases are argued away in
+    kernels.cuh): scalars at the boundaries of the signed recoding -- every single window digit at +-1, at the largest
+    magnitude 2^(WB-1), runs of carries, the top window with its small range, values around n and n/2 -- placed at
+    EVEN and odd indices (the host simulation alternates the two formulas by index)."""
+    vals = [0, 1, 2, N - 1, N - 2, N, N + 1, 2**256 - 1, N // 2, N // 2 + 1, 2**252, 2**252 - 1, 2**252 + 1, 15 * 2**252,
+            2**255, 2**256 - N, 2 * (2**256 - N)]
+    for wb in (6, 7):
+        nw = (257 + wb - 1) // wb
+        for w in range(nw):
+            vals += [(1 << (wb * w)) % N, ((1 << (wb - 1)) << (wb * w)) % N, (((1 << (wb - 1)) + 1) << (wb * w)) % N]
+        vals += [sum(((1 << (wb - 1)) + 1) << (wb * w) for w in range(nw - 1)) % N,
+                 sum(((1 << wb) - 1) << (wb * w) for w in range(nw - 1)) % N, sum(1 << (wb * w) for w in range(nw)) % N]
+    vals = [v for v in vals for _ in (0, 1)]     # each value at an even and at an odd index
+    ks = synth.base_mult_scalars(n, start=1000)
+    edge = rows([b32(v % 2**256) for v in vals], 32)
+    ks[16:16 + len(edge)] = edge
+    got, st = be.scalar_base_mult(ks)
+    m = 16 + len(edge) + 64                       # the oracle on the crafted prefix and a few random rows
+    exp, est = o.batch_scalar_base_mult(ks[:m])
+    assert np.array_equal(st[:m], est)
+    assert np.array_equal(got[:m], exp)
+    return got, st
+
+
 def check_rfc6979_and_kats(be, o):
     doc = load_golden("rfc6979.json")
     privs = rows([H(r["priv"]) for r in doc["rows"]], 32)

@@ -23,6 +23,15 @@ def test_base_mult_config1(engine, oracle):
     ps.check_base_mult(engine, oracle, n=4096)
 
 
+def test_base_mult_large_batch_kernel_edges(engine, oracle):
+    # > 16384 items: the 7-bit kernel with its Jacobian accumulator; recoding-boundary scalars against the oracle
+    got, st = ps.check_base_mult_edges(engine, oracle, n=20000)
+    # and the same rows through the lane-split kernel (complete formulas) must agree bit for bit
+    ks = ps.synth.base_mult_scalars(20000, start=1000)
+    got2, st2 = engine.scalar_base_mult(ks[:4096])
+    assert np.array_equal(got2[:16], got[:16]) and np.array_equal(st2[:16], st[:16])
+
+
 def test_rfc6979(engine, oracle):
     ps.check_rfc6979_and_kats(engine, oracle)
 

@@ -43,6 +43,7 @@ def test_gen_table_matches_reference_bin():
 def test_base_mult(oracle):
     ps.check_base_mult(be, oracle, n=32)
     ps.check_base_mult(be, oracle, n=8)   # n <= 8 takes the lane-split form in the simulation
+    ps.check_base_mult_edges(be, oracle, n=700)
 
 
 def test_rfc6979(oracle):
