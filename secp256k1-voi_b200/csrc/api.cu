@@ -1327,6 +1327,10 @@ extern "C" double s256_mac32_per_item(const char *name) {
         const double lad = (CTM_ND - 1) * CTM_W * dbl_ct + 2 * CTM_ND * mix_ct + CTM_ND * M;
         return oncurve + split + tab + lad + affine;
     }
-    if (s == "msm_mixed_add") return mix;  // one bucket accumulation step of the Pippenger MSM (k_msm_slices)
+#ifndef S256_MSM_RCB
+    if (s == "msm_mixed_add") return dc.mix;  // one bucket accumulation step of the Pippenger MSM (k_msm_slices): Jacobian mixed
+#else
+    if (s == "msm_mixed_add") return mix;
+#endif
     return 0.0;
 }

@@ -27,6 +27,7 @@
 #pragma once
 #include "fe.cuh"
 #include "point.cuh"
+#include "jac.cuh"
 #include "sc.cuh"
 
 namespace s256 {
@@ -150,6 +151,35 @@ S256_HD void msm_glv_points(apt &p0, apt &p1, const apt &p) {
 
 // slice / bucket accumulation: entries hold (point index << 1) | negate
 S256_HD void msm_bucket_sum(pt &out, const uint32_t *entries, uint32_t start, uint32_t end, const apt *aff) {
+#ifndef S256_MSM_RCB
+    // Jacobian accumulator, mixed Jacobian additions with their exceptional cases handled by branches (jac.cuh): the
+    // vartime MSM handles public data like the verification ladder, and equal points in one bucket (repeated inputs,
+    // or P and -P with opposite digits) do reach the doubling and the identity here
+    fe_ops<true> f;
+    pt acc;
+    acc.x = acc.y = acc.z = fe_zero();
+    uint32_t inf = 1u;
+    if (start < end) {
+        uint32_t v = entries[start];
+        apt a = aff[v >> 1];
+        for (uint32_t e = start; e < end; e++) {
+            uint32_t vn = v;
+            apt an = a;
+            if (e + 1 < end) {
+                vn = entries[e + 1];
+                an = aff[vn >> 1];
+            }
+            if (v & 1u) {
+                fe z = fe_zero();
+                fe_sub_vt(a.y, z, a.y);
+            }
+            jac_add_mixed_var(f, acc, inf, a.x, a.y);
+            v = vn;
+            a = an;
+        }
+    }
+    jac_to_projective(f, out, acc, inf);
+#else
     pt acc;
     pt_set_identity(acc);
     if (start < end) {
@@ -173,6 +203,7 @@ S256_HD void msm_bucket_sum(pt &out, const uint32_t *entries, uint32_t start, ui
         }
     }
     out = acc;
+#endif
 }
 
 // slices of bucket b: max(1, ceil(count / MSM_SLICE))
