@@ -470,6 +470,8 @@ def check_msm(be, o, sizes=(0, 1, 2, 31, 32, 33, 64, 300), big=None, heavy=None)
     k[3] = np.frombuffer(b32(2**256 - 1), np.uint8)   # reduced like NewScalarFromBytes
     pts[5] = pts[4]
     pts[7] = pts[6]; k[7] = np.frombuffer(b32((N - int.from_bytes(k[6].tobytes(), "big")) % N), np.uint8)  # cancels
+    pts[11] = pts[10]; k[11] = k[10]            # the same term twice: equal points meet in every bucket (doubling branch)
+    pts[13] = pts[12]; pts[14] = pts[12]; k[13] = k[12]; k[14] = k[12]   # and three times
     got, st = be.msm(k, pts)
     exp, est = o.msm(k.tobytes(), pts.tobytes())
     assert (st, got.tobytes()) == (est, exp)
