@@ -95,3 +95,68 @@ def test_safegcd_inversion_matches_fermat_and_pow():
         assert ip.tobytes() == fp.tobytes(), hex(v)
         assert int.from_bytes(i_n.tobytes(), "big") == pow(v % N, N - 2, N), hex(v)
         assert i_n.tobytes() == fn.tobytes(), hex(v)
+
+
+# ---------------------------------------------------------------------------
+# The argument that lets the large-batch fixed-base kernel use the INCOMPLETE mixed Jacobian addition
+# (csrc/kernels.cuh, item_base_mult_ct_jac): with ascending windows the accumulator A = sum_{v<w} d_v B^v is never
+# congruent to +- the entry E = d_w B^w, and "all digits so far are zero" is the same as "A is the identity".
+# The recoding below restates the kernel's (ct_window_bits + carry, digits in [-(B/2 - 1), B/2]).
+# ---------------------------------------------------------------------------
+def _signed_digits(k, wb):
+    nw = (257 + wb - 1) // wb
+    out, carry = [], 0
+    for w in range(nw):
+        v = ((k >> (wb * w)) & ((1 << wb) - 1)) + carry
+        carry = 1 if v > (1 << (wb - 1)) else 0
+        out.append(v - (carry << wb))
+    assert carry == 0 and sum(d << (wb * w) for w, d in enumerate(out)) == k
+    return out
+
+
+def test_fixed_base_jacobian_argument_constants():
+    c = 2**256 - N
+    for wb in (6, 7):
+        B, nw = 1 << wb, (257 + wb - 1) // wb
+        for w in range(1, nw):
+            assert (B // 2) * (B**w - 1) * 100 < 51 * (B - 1) * B**w            # |A| < 0.51 B^w
+        assert wb * (nw - 1) == 252                                             # the top window starts at bit 252
+        assert (B // 2 + 1) * B**(nw - 2) < 2**252 < N                          # below the top window |A -+ E| < n
+        # top window: E = n + A would have to be a multiple of 2^252 with -0.51 * 2^252 < A < 0
+        for m in range(0, 64):
+            A = c - m * 2**252
+            assert not (-51 * 2**252 < 100 * A < 0), m
+
+
+@settings(**SET)
+@given(st.lists(scalar, min_size=1, max_size=8))
+def test_fixed_base_jacobian_argument_on_scalars(ks):
+    for k in ks:
+        k %= N                                                                  # sc_from_be32 reduces
+        for wb in (6, 7):
+            B, digits = 1 << wb, _signed_digits(k, wb)
+            A = 0
+            for w, d in enumerate(digits):
+                if d != 0:
+                    E = d * B**w
+                    assert (A - E) % N != 0 and (A + E) % N != 0, (hex(k), wb, w)   # no doubling, no cancellation
+                assert (A % N == 0) == all(x == 0 for x in digits[:w]), (hex(k), wb, w)
+                A += d * B**w
+            assert A == k
+
+
+def test_fixed_base_jacobian_argument_on_structured_scalars():
+    c = 2**256 - N
+    ks = set()
+    for base in (0, c, 2 * c, N - c, N // 2, 2**252, 15 * 2**252, N - 2**252, (N + c) // 2):
+        for d in range(-70, 71):
+            ks.add((base + d) % N)
+            ks.add((base + d * 2**252) % N)
+            ks.add((base + d * 2**245) % N)
+    for wb in (6, 7):
+        B = 1 << wb
+        for w in range(0, (257 + wb - 1) // wb):
+            for d in (1, B // 2 - 1, B // 2, B // 2 + 1, B - 1):
+                ks.add((d * B**w) % N)
+                ks.add((N - d * B**w) % N)
+    test_fixed_base_jacobian_argument_on_scalars.hypothesis.inner_test(sorted(ks))
