@@ -522,7 +522,9 @@ def main():
                     "callers": None if e2e_value is None else (2 if e2e_value == e2e_two else 1),
                     "single_caller": e2e_single, "two_callers": e2e_two,
                     "note": "value = the better of one synchronous caller and two callers (two contexts, two host threads, "
-                            "alternate batches); every batch crosses PCIe both ways inside the timed region",
+                            "alternate batches); every batch crosses PCIe both ways inside the timed region.  Two contexts also "
+                            "overlap each other's scalar kernels and kernel tails with a ladder, which the single device-resident "
+                            "caller behind `value` cannot, so two_callers may exceed `value` by ~0.5 %",
                     "h2d_gbs_per_rank_all_ranks_copying": h2d_gbs},
             "gpu_launches": int(launches),
             "clocks": dict(clocks, per_rank_sm_mhz=rank_sm_mhz), "per_rank_ms_per_step": per_rank_ms,
