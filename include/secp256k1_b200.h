@@ -102,6 +102,11 @@ int s256_ecdh_dev(s256_ctx *ctx, const uint8_t *d_k32, const uint8_t *d_pt65, si
  *     canonical x, square root, parity select): 33 B -> 65 B + status. */
 int s256_point_decompress(s256_ctx *ctx, const uint8_t *pt33, size_t n, uint8_t *out65, uint8_t *status);
 
+/* --- (*Point).CompressedBytes (point_s11n.go:90-117) behind NewPointFromBytes (point_s11n.go:234): validated
+ *     uncompressed 65 B -> compressed 33 B (02 | 03 by the parity of y, then X) + status; a row that does not
+ *     decode to a point of the curve gives zeros and S256_ST_INVALID. */
+int s256_point_compress(s256_ctx *ctx, const uint8_t *pt65, size_t n, uint8_t *out33, uint8_t *status);
+
 /* --- Point.DoubleScalarMultBasepointVartime (point_mul_glv.go:307):
  *     u1*G + u2*P, variable time. */
 int s256_double_scalar_mult_basepoint_vartime(s256_ctx *ctx, const uint8_t *u1_32, const uint8_t *u2_32,

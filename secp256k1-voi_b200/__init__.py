@@ -29,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "s256_init", "s256_free", "s256_strerror", "s256_last_cuda_error", "s256_device",
     "s256_scalar_base_mult", "s256_scalar_base_mult_dev",
     "s256_scalar_mult", "s256_scalar_mult_dev",
-    "s256_ecdh", "s256_ecdh_dev", "s256_point_decompress",
+    "s256_ecdh", "s256_ecdh_dev", "s256_point_decompress", "s256_point_compress",
     "s256_double_scalar_mult_basepoint_vartime", "s256_double_scalar_mult_basepoint_vartime_dev",
     "s256_ecdsa_verify", "s256_ecdsa_verify_dev",
     "s256_parse_asn1_signatures", "s256_is_valid_signature_encoding_bip0066",
@@ -347,6 +347,16 @@ class Engine:
         st = self._out(8, n)
         self._check(self._lib.s256_point_decompress(self._ctx, self._hp(p), C.c_size_t(n), self._hp(out), self._hp(st)),
                     "point_decompress")
+        return out, st
+
+    def point_compress(self, pt65):
+        """(*Point).CompressedBytes behind NewPointFromBytes: 65 B -> 33 B + status (point_s11n.go:90-117,234)."""
+        p = _host(pt65, 65)
+        n = len(p)
+        out = self._out(7, (n, 33))
+        st = self._out(8, n)
+        self._check(self._lib.s256_point_compress(self._ctx, self._hp(p), C.c_size_t(n), self._hp(out), self._hp(st)),
+                    "point_compress")
         return out, st
 
     # -- secec.NewPublicKey / ParseASN1PublicKey (secec/secec.go:183, secec/s11n.go:38) ----

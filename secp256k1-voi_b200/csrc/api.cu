@@ -133,6 +133,22 @@ __global__ void __launch_bounds__(S256_TPB) k_encode_affine(const apt *aff, cons
     }
     status[i] = ok ? ST_OK : ST_INVALID;
 }
+// affine (validated) -> 33-byte compressed encoding (point_s11n.go:90-117); invalid -> zeros
+__global__ void __launch_bounds__(S256_TPB) k_encode_compressed(const apt *aff, const uint8_t *pvalid, size_t n,
+                                                                uint8_t *out33, uint8_t *status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    apt a = aff[i];
+    uint32_t ok = pvalid[i] != 0;
+    uint8_t *o = out33 + 33 * i;
+    if (ok) {
+        o[0] = (uint8_t)(0x02u | fe_is_odd(a.y));
+        fe_to_be32(o + 1, a.x);
+    } else {
+        for (int b = 0; b < 33; b++) o[b] = 0;
+    }
+    status[i] = ok ? ST_OK : ST_INVALID;
+}
 __global__ void __launch_bounds__(S256_TPB) k_encode_public_key(const apt *aff, const uint8_t *pvalid, size_t n,
                                                                 uint8_t *out65, uint8_t *status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -929,6 +945,22 @@ extern "C" int s256_point_decompress(s256_ctx *ctx, const uint8_t *pt33, size_t 
         LAUNCH(ctx, k_decode_compressed, grid_for(c), 0, s, ctx->in_a, c, ctx->aff, ctx->pvalid);
         LAUNCH(ctx, k_encode_affine, grid_for(c), 0, s, ctx->aff, ctx->pvalid, c, ctx->out, ctx->st);
         CK(cudaMemcpyAsync(out65 + 65 * off, ctx->out, 65 * c, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        return S256_SUCCESS;
+    });
+    return rc != S256_SUCCESS ? rc : check_launch(ctx);
+}
+extern "C" int s256_point_compress(s256_ctx *ctx, const uint8_t *pt65, size_t n, uint8_t *out33, uint8_t *status) {
+    ENTER(ctx);
+    scratch_guard sg_(ctx, ctx->stream, true);
+    if (n && (!pt65 || !out33 || !status)) return S256_ERR_ARG;
+    cudaStream_t s = ctx->stream;
+    int rc = for_chunks(ctx, n, [&](size_t off, size_t c) {
+        CK(cudaMemcpyAsync(ctx->in_a, pt65 + 65 * off, 65 * c, cudaMemcpyHostToDevice, s));
+        LAUNCH(ctx, k_decode_uncompressed, grid_for(c), 0, s, ctx->in_a, c, ctx->aff, ctx->pvalid);
+        LAUNCH(ctx, k_encode_compressed, grid_for(c), 0, s, ctx->aff, ctx->pvalid, c, ctx->out, ctx->st);
+        CK(cudaMemcpyAsync(out33 + 33 * off, ctx->out, 33 * c, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(status + off, ctx->st, c, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         return S256_SUCCESS;

@@ -448,6 +448,25 @@ def check_point_decompress(be, o, n=64):
     assert st[0] == 1 and out[0].tobytes().hex() == kats["g_uncompressed"]
 
 
+def check_point_compress(be, o, n=64):
+    """(*Point).CompressedBytes (point_s11n.go:90-117): 02 | 03 by the parity of y, then X; the round trip through
+    the decompressor; rows that are not points of the curve are refused; the generator's known encoding."""
+    w = synth.ecdh_batch(n, oracle_base_mult(o))
+    exp = np.zeros((n, 33), np.uint8)
+    exp[:, 0] = 2 + (w["pt65"][:, 64] & 1)
+    exp[:, 1:] = w["pt65"][:, 1:33]
+    out, st = be.point_compress(w["pt65"])
+    assert st.tolist() == [1] * n and np.array_equal(out, exp)
+    back, st2 = be.point_decompress(out)
+    assert st2.all() and np.array_equal(back, w["pt65"])
+    bad = w["pt65"][:4].copy(); bad[0, 0] = 2; bad[1, 64] ^= 1; bad[2, 1:33] = 0xFF; bad[3, 1:] = 0
+    out, st = be.point_compress(bad)
+    assert st.tolist() == [0, 0, 0, 0] and not out.any()
+    kats = load_golden("kats.json")
+    out, st = be.point_compress(rows([H(kats["g_uncompressed"])], 65))
+    assert st[0] == 1 and out[0].tobytes().hex() == kats["g_compressed"]
+
+
 def check_msm(be, o, sizes=(0, 1, 2, 31, 32, 33, 64, 300), big=None, heavy=None):
     """point_mul_multi_test.go:14-70 (sizes 0, 1, 32, 64 vs sum of ScalarMult) and
     the closed form of config 5: sum s_i * (d_i G) == (sum s_i d_i mod n) G."""

@@ -77,6 +77,10 @@ def test_point_decompress(engine, oracle):
     ps.check_point_decompress(engine, oracle, n=1024)
 
 
+def test_point_compress(engine, oracle):
+    ps.check_point_compress(engine, oracle, n=1024)
+
+
 def test_msm(engine, oracle):
     ps.check_msm(engine, oracle, sizes=(0, 1, 2, 31, 32, 33, 64, 300, 1000, 4096), big=1 << 17, heavy=20000)
 
