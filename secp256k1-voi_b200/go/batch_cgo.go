@@ -245,6 +245,18 @@ func (e *Engine) ECDHBatch(k32, pt65 []byte) (x32 []byte, status []byte, err err
 	return
 }
 
+// CompressedBytesBatch is NewPointFromBytes + (*Point).CompressedBytes over rows of 65 bytes: 33 bytes per row
+// (02 | 03, X); status 0 marks a row that is not a point of the curve.
+func (e *Engine) CompressedBytesBatch(pt65 []byte) (pt33 []byte, status []byte, err error) {
+	if len(pt65)%65 != 0 {
+		panic("secp256k1b200: CompressedBytesBatch: length is not a multiple of 65")
+	}
+	n := len(pt65) / 65
+	pt33, status = make([]byte, 33*n), make([]byte, n)
+	err = e.err(C.s256_point_compress(e.ctx, ptr(pt65), C.size_t(n), ptr(pt33), ptr(status)))
+	return
+}
+
 // PinnedBytes returns a page-locked byte slice of length n for batch inputs / outputs: copies from and to
 // such memory run at PCIe speed and overlap the kernels, while ordinary Go heap memory is staged by the
 // driver.  The slice is C memory (not moved or freed by the Go GC); release it with FreePinned.
