@@ -363,6 +363,8 @@ __global__ void __launch_bounds__(S256_TPB) k_field_op(int op, const uint8_t *a3
             case 21: fe_mul3_vt(r, a); break;
             case 22: fe_sub2_vt(r, a, b); break;
             case 23: fe_submul8_vt(r, a, b); break;
+            case 24: fe_ops<false>::mul2add(r, a, b, b, a); break;  // the constant-time fused a b + c d (device)
+            case 25: fe_ops<false>::mul2sub(r, a, a, b, b); break;
             default: r = fe_zero();
         }
         fe_normalize(r, r);
@@ -1328,7 +1330,13 @@ extern "C" double s256_mac32_per_item(const char *name) {
 #else
     const double dbl = 6 * M + 2 * S, add = 12 * M, mix = 11 * M;
 #endif
+#if !defined(S256_NO_FUSED) && !defined(S256_NO_FUSED_CT)
+    const double dbl_ct = 4 * M + 2 * S + F2 + 2, mix_ct = 5 * M + 3 * F2 + 2;    // fused pairs in the constant-time flavour too
+    const double jmix_ct = 6 * M + 3 * S + F2;
+#else
     const double dbl_ct = 6 * M + 2 * S + 2, mix_ct = 11 * M + 2;                 // + the folds of 21a and 8a / 21a twice
+    const double jmix_ct = 8 * M + 3 * S;
+#endif
     // inversions are safegcd (modinv.cuh): 20 batches x (54 + 36) 32x32->64 products, whatever the modulus
     const double inv_fe = 20 * 90, sqrt_fe = 254 * S + 13 * M + 2 * S + M, inv_sc = 20 * 90;
     const double oncurve = 2 * S + M;
@@ -1347,7 +1355,7 @@ extern "C" double s256_mac32_per_item(const char *name) {
     if (s == "schnorr_verify") return sqrt_fe + (ZN + split) + dsm + affine;
     if (s == "double_scalar_mult_basepoint_vartime") return oncurve + split + dsm + affine;
 #ifndef S256_BM_RCB
-    const double bm = ct_cfg<7>::NW * (8 * M + 3 * S) + 2 * M + S;  // large batches: 7-bit windows, Jacobian accumulator (kernels.cuh)
+    const double bm = ct_cfg<7>::NW * jmix_ct + 2 * M + S;  // large batches: 7-bit windows, Jacobian accumulator (kernels.cuh)
 #else
     const double bm = ct_cfg<7>::NW * mix_ct;
 #endif

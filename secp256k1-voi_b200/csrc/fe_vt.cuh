@@ -179,6 +179,41 @@ S256_D void fe_mul2add_vt(fe &r, const fe &a, const fe &b, const fe &c, const fe
 S256_D void fe_mul_vt(fe &r, const fe &a, const fe &b) { fe_mul_inline_vt(r, a, b); }
 S256_D void fe_sqr_vt(fe &r, const fe &a) { fe_sqr_inline_vt(r, a); }
 #endif
+// The fused a b + c d for the CONSTANT-TIME flavour: the same core (its carry-outs are captured with selects, no
+// branch), a full-ripple fold of the top word pair (t9 <= 3) and a masked second fold -- fe_fold_top of fe.cuh with a
+// small multiple in place of its 0 / 1 mask.
+S256_D void fe_fold_top2_ct(fe &out, uint32_t t0, uint32_t t1, uint32_t t2, uint32_t t3, uint32_t t4, uint32_t t5,
+                            uint32_t t6, uint32_t t7, uint32_t t8, uint32_t t9) {
+    uint32_t u0, u1, u2, c;
+    uint32_t t9d = t9 * S256_DELTA_LO;
+    asm("mul.lo.u32 %0,%2,%3; mul.hi.u32 %1,%2,%3;" : "=r"(u0), "=r"(u1) : "r"(t8), "r"(S256_DELTA_LO));
+    asm("add.cc.u32 %0,%0,%2; addc.u32 %1,%3,0;" : "+r"(u1), "=r"(u2) : "r"(t8), "r"(t9));
+    asm("add.cc.u32 %0,%0,%2; addc.u32 %1,%1,0;" : "+r"(u1), "+r"(u2) : "r"(t9d));
+    asm("add.cc.u32 %0,%9,%17; addc.cc.u32 %1,%10,%18; addc.cc.u32 %2,%11,%19; addc.cc.u32 %3,%12,0;"
+        "addc.cc.u32 %4,%13,0; addc.cc.u32 %5,%14,0; addc.cc.u32 %6,%15,0; addc.cc.u32 %7,%16,0; addc.u32 %8,0,0;"
+        : "=r"(out.v[0]), "=r"(out.v[1]), "=r"(out.v[2]), "=r"(out.v[3]), "=r"(out.v[4]), "=r"(out.v[5]),
+          "=r"(out.v[6]), "=r"(out.v[7]), "=r"(c)
+        : "r"(t0), "r"(t1), "r"(t2), "r"(t3), "r"(t4), "r"(t5), "r"(t6), "r"(t7), "r"(u0), "r"(u1), "r"(u2));
+    // on carry the value is < 2^68 now: one more delta, no carry possible; masked, not branched
+    asm("add.cc.u32 %0,%0,%3; addc.cc.u32 %1,%1,%4; addc.u32 %2,%2,0;"
+        : "+r"(out.v[0]), "+r"(out.v[1]), "+r"(out.v[2])
+        : "r"((0u - c) & S256_DELTA_LO), "r"(c));
+}
+S256_D void fe_mul2add_inline_ct(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) {
+    uint32_t w[9], t9;
+    fe_mul2add_core_w(w, t9, a.v, b.v, c.v, d.v);
+    fe_fold_top2_ct(r, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7], w[8], t9);
+}
+#ifndef S256_MUL_INLINE
+static __device__ __noinline__ fe fe_mul2add_call_ct(fe a, fe b, fe c, fe d) {
+    fe r;
+    fe_mul2add_inline_ct(r, a, b, c, d);
+    return r;
+}
+S256_D void fe_mul2add_ct(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) { r = fe_mul2add_call_ct(a, b, c, d); }
+#else
+S256_D void fe_mul2add_ct(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) { fe_mul2add_inline_ct(r, a, b, c, d); }
+#endif
 S256_D void fe_mul_small_vt(fe &r, const fe &a, uint32_t k) {
     uint32_t e[8], t8;
     fe_mul_small_pre(e, t8, a, k);
@@ -362,7 +397,15 @@ struct fe_ops<false> {
     S256_HD static void sub(fe &r, const fe &a, const fe &b) { fe_sub(r, a, b); }
     S256_HD static void mul(fe &r, const fe &a, const fe &b) { fe_mul(r, a, b); }
     S256_HD static void sqr(fe &r, const fe &a) { fe_sqr(r, a); }
-    // a b + c d and a b - c d: two products and an addition here; one fused call in the variable-time flavour
+    // a b + c d and a b - c d: one fused, branch-free call on the device (fe_mul2add_ct), two products and an addition elsewhere
+#if S256_PTX && !defined(S256_NO_FUSED) && !defined(S256_NO_FUSED_CT)
+    S256_HD static void mul2add(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) { fe_mul2add_ct(r, a, b, c, d); }
+    S256_HD static void mul2sub(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) {
+        fe nd;
+        fe_neg(nd, d);
+        fe_mul2add_ct(r, a, b, c, nd);
+    }
+#else
     S256_HD static void mul2add(fe &r, const fe &a, const fe &b, const fe &c, const fe &d) {
         fe t, u;
         fe_mul(t, a, b);
@@ -375,6 +418,7 @@ struct fe_ops<false> {
         fe_mul(u, c, d);
         fe_sub(r, t, u);
     }
+#endif
 #if S256_PTX && !defined(S256_B3_MULT)
     // 21a and 8a by shifts and adds with the branch-free fold (the constant-time flavour of fe_mul21_vt / fe_mul8_vt)
     S256_HD static void mul_small(fe &r, const fe &a, uint32_t k) {

@@ -374,6 +374,8 @@ EXPORT void sim_field_op(int op, const uint8_t *a32, const uint8_t *b32, size_t 
                 case 21: fe_mul3_vt(r, a); break;
                 case 22: fe_sub2_vt(r, a, b); break;
                 case 23: fe_submul8_vt(r, a, b); break;
+                case 24: fe_ops<false>::mul2add(r, a, b, b, a); break;  // the constant-time fused a b + c d (device)
+                case 25: fe_ops<false>::mul2sub(r, a, a, b, b); break;
                 default: r = fe_zero();
             }
             fe_normalize(r, r);

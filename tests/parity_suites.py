@@ -84,7 +84,7 @@ def check_field_ops(be, rng_seed=7, n=256):
     a, b = rows([b32(x) for x in A], 32), rows([b32(x) for x in B], 32)
     ops = fe_ops + [(8 + op, f) for op, f in fe_ops] + [(15, lambda x, y: x * 8 % P)] + [
         (20, lambda x, y: 2 * x % P), (21, lambda x, y: 3 * x % P), (22, lambda x, y: (x - 2 * y) % P),
-        (23, lambda x, y: (x - 8 * y) % P)] + [
+        (23, lambda x, y: (x - 8 * y) % P), (24, lambda x, y: 2 * x * y % P), (25, lambda x, y: (x * x - y * y) % P)] + [
         (3, lambda x, y: pow(x % P, P - 2, P)), (7, lambda x, y: pow(x % P, P - 2, P)),
         (19, lambda x, y: pow(x % N, N - 2, N)),
         (16, lambda x, y: (x % N) * (y % N) % N), (17, lambda x, y: (x % N + y % N) % N),
