@@ -21,6 +21,7 @@ for n in (1, 33, 1500):
         eng.msm(we["k32"], we["pt65"], vartime=vt)
     comp = np.concatenate([2 + (we["pt65"][:, 64:] & 1), we["pt65"][:, 1:33]], axis=1)
     eng.point_decompress(comp)
+    eng.point_compress(we["pt65"])
     priv = ks.copy(); priv[:, 0] &= 0x7F; priv[:, 31] |= 1
     sig, rec, st = eng.ecdsa_sign_rfc6979(priv, w["digest32"])
     eng.schnorr_sign(priv, w["digest32"], ks)
