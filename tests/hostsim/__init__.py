@@ -163,3 +163,13 @@ def expand_message_xmd(dst, msgs, length):
         lib().sim_expand_xmd(dst, C.c_size_t(len(dst)), _p(m[i:i + 1].copy()), C.c_size_t(ml), int(length), _p(row))
         out[i] = row
     return out
+
+
+def jac_vs_complete(a65, b65, ops):
+    """The same chain of doublings / additions on the Jacobian and on the complete formulas: (out, status) of each."""
+    a, b = _a(a65, 65), _a(b65, 65)
+    ops = np.ascontiguousarray(ops, dtype=np.uint8)
+    oj, oc = np.zeros(65, np.uint8), np.zeros(65, np.uint8)
+    sj, sc_ = C.c_uint8(0), C.c_uint8(0)
+    lib().sim_jac_vs_complete(_p(a), _p(b), _p(ops), C.c_size_t(len(ops)), _p(oj), C.byref(sj), _p(oc), C.byref(sc_))
+    return (oj, sj.value), (oc, sc_.value)

@@ -339,6 +339,42 @@ EXPORT void sim_hash_to_curve(const uint8_t *dst, size_t dst_len, const uint8_t 
 EXPORT void sim_expand_xmd(const uint8_t *dst, size_t dst_len, const uint8_t *msg, size_t msg_len, int len, uint8_t *out) {
     h2c_expand_xmd(out, len, dst, (int)dst_len, msg, msg_len);
 }
+// Differential check of the two group laws: the same chain of operations on the Jacobian formulas (jac.cuh, with
+// their explicit exceptional cases) and on the complete ones (point.cuh).  ops[j]: 0 = double, 1 = add b, 2 = add -b,
+// 3 = add a, 4 = add -a; the accumulator starts at the identity.  Both results leave through the shared conversion.
+EXPORT void sim_jac_vs_complete(const uint8_t *a65, const uint8_t *b65, const uint8_t *ops, size_t nops, uint8_t *out_jac65,
+                                uint8_t *st_jac, uint8_t *out_rcb65, uint8_t *st_rcb) {
+    scratch s(2);
+    apt A, B;
+    if (!item_decode_uncompressed(A, a65) || !item_decode_uncompressed(B, b65)) {
+        *st_jac = *st_rcb = 0;
+        return;
+    }
+    fe_ops<true> f;
+    pt j, c;
+    j.x = j.y = j.z = fe_zero();
+    uint32_t inf = 1u;
+    pt_set_identity(c);
+    for (size_t k = 0; k < nops; k++) {
+        if (ops[k] == 0) {
+            jac_double(f, j, j);
+            pt_double<true>(c, c);
+        } else {
+            apt q = (ops[k] == 1 || ops[k] == 2) ? B : A;
+            if (ops[k] == 2 || ops[k] == 4) fe_neg(q.y, q.y);
+            jac_add_mixed_var(f, j, inf, q.x, q.y);
+            pt_add_mixed<true>(c, c, q.x, q.y);
+        }
+    }
+    jac_to_projective(f, s.res[0], j, inf);
+    s.res[1] = c;
+    uint8_t out[130], st[2];
+    run_finish(s, 2, false, false, 0, out, st, nullptr);
+    memcpy(out_jac65, out, 65);
+    memcpy(out_rcb65, out + 65, 65);
+    *st_jac = st[0];
+    *st_rcb = st[1];
+}
 EXPORT void sim_gen_table(int wbits, int nwin, uint8_t *out) {
     for (int w = 0; w < nwin; w++)
         for (uint32_t d = 1; d < (1u << wbits); d++) {

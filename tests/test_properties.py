@@ -160,3 +160,45 @@ def test_fixed_base_jacobian_argument_on_structured_scalars():
                 ks.add((d * B**w) % N)
                 ks.add((N - d * B**w) % N)
     test_fixed_base_jacobian_argument_on_scalars.hypothesis.inner_test(sorted(ks))
+
+
+# ---------------------------------------------------------------------------
+# The Jacobian formulas of the variable-time ladders (csrc/jac.cuh) against the complete ones (csrc/point.cuh): random
+# chains of doublings and additions of +-A and +-B from the identity, with B chosen so that the chain runs into the
+# explicit branches -- B = A, B = -A, B = 2A, B = -2A (equal / opposite accumulator and addend after one or two steps).
+# ---------------------------------------------------------------------------
+def _pt(o, k):
+    out, st = o.batch_scalar_base_mult(rows([k % N]))
+    assert st[0] == 1
+    return out[0]
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+@given(st.integers(1, 2**64), st.sampled_from([1, -1, 2, -2, 3, 5, 7, 2**31]), st.lists(st.integers(0, 4), min_size=1, max_size=24))
+def test_jacobian_chain_equals_complete_chain(a, rel, ops):
+    from oracle import oracle as o
+    o.lib()
+    A = _pt(o, a)
+    B = _pt(o, (a * rel) % N if abs(rel) <= 2 else rel)
+    (oj, sj), (oc, sc_) = hs.jac_vs_complete(A, B, ops)
+    assert sj == sc_ and np.array_equal(oj, oc), (a, rel, ops)
+
+
+def test_jacobian_chain_exceptional_branches_are_reached():
+    from oracle import oracle as o
+    o.lib()
+    A, A2, nA2 = _pt(o, 9), _pt(o, 18), _pt(o, N - 18)
+    cases = [
+        (A, A, [3, 1]),          # A + A: doubling inside the addition
+        (A, A, [3, 2]),          # A - A: the identity flag
+        (A, A, [3, 2, 1, 0, 3]), # ... then an assignment from the identity, a doubling, an addition
+        (A, A2, [3, 0, 1]),      # 2A + 2A
+        (A, nA2, [3, 0, 1]),     # 2A - 2A
+        (A, A2, [0, 0, 3]),      # doublings of the identity, then an assignment
+        (A, A2, [3, 0, 2, 2]),   # 2A - 2A - 2A = -2A
+    ]
+    for a_, b_, ops in cases:
+        (oj, sj), (oc, sc_) = hs.jac_vs_complete(a_, b_, ops)
+        assert sj == sc_ and np.array_equal(oj, oc), ops
+    (oj, sj), _ = hs.jac_vs_complete(A, A, [3, 2])
+    assert sj == 2 and not oj.any()                    # the identity is reported, not encoded
